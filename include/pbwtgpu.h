@@ -1,0 +1,120 @@
+/* pbwtgpu.h -- C ABI of the B200 (sm_100a) PBWT construction and match engine.
+ *
+ * Plain C: opaque handles, plain pointers and sizes, int return codes (0 = ok, <0 = error,
+ * never exit()).  This is the surface a maintainer of the reference binds to replace its hot
+ * path (INTEGRATION.md shows the host shim that does so); each entry point names the reference
+ * interface it stands in for (file:line into richarddurbin/pbwt).
+ *
+ * Panel format ("bit columns"): site-major; column k starts at word k*wpc of a uint32 array,
+ * bit (h & 31) of word (h >> 5) = allele of haplotype h at site k, wpc = pbwtgpu_words_per_col(M)
+ * = 4*ceil(M/128) so that every column is 16-byte aligned (a TMA bulk-copy unit).
+ * This is what the readers' per-site x[] (pbwtIO.c:572-573, pbwtHtslib.c:134) becomes when a
+ * batch of sites is handed over at once.
+ *
+ * Match records are exactly the arguments of the reference's report(ai,bi,start,end) callback
+ * (pbwt.h:208,213), in callback order, zero-length records included.
+ */
+#ifndef PBWTGPU_H
+#define PBWTGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pbwtgpu_ctx pbwtgpu_ctx;       /* one per GPU (device memory, stream, scratch) */
+typedef struct pbwtgpu_panel pbwtgpu_panel;   /* bit columns resident in HBM */
+typedef struct pbwtgpu_result pbwtgpu_result; /* device-resident outputs of one sweep */
+
+typedef struct { int32_t ai, bi, start, end; } pbwtgpu_match;
+typedef struct { int32_t query, allele, site; } pbwtgpu_nomatch; /* pbwtMatch.c:406-407 log line */
+
+enum {
+  PBWTGPU_OK = 0,
+  PBWTGPU_ERR_CUDA = -1,      /* a CUDA call failed; see pbwtgpu_last_error */
+  PBWTGPU_ERR_ARG = -2,       /* bad argument */
+  PBWTGPU_ERR_NOMEM = -3,     /* host or device allocation failed */
+  PBWTGPU_ERR_UNSUPPORTED = -4, /* shape outside what the kernels handle */
+  PBWTGPU_ERR_NODEVICE = -5   /* no CUDA device / not sm_100: there is NO CPU fallback */
+};
+
+/* what a sweep should produce */
+enum {
+  PBWTGPU_WANT_YZ = 1u,        /* pack3 stream of the sorted columns  (pbwtCore.c:240-277) */
+  PBWTGPU_WANT_D = 2u,         /* carry the divergence array           (pbwtCore.c:485-508) */
+  PBWTGPU_WANT_MAXWITHIN = 4u  /* set-maximal matches, implies WANT_D  (pbwtMatch.c:115-142) */
+};
+
+int pbwtgpu_words_per_col(int M);
+
+/* ---- context -------------------------------------------------------------------------------- */
+int pbwtgpu_init(int device, pbwtgpu_ctx **ctx);
+void pbwtgpu_destroy(pbwtgpu_ctx *ctx);
+const char *pbwtgpu_strerror(int code);
+const char *pbwtgpu_last_error(pbwtgpu_ctx *ctx);
+/* Run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL restores the context's
+ * own stream.  Lets a harness bracket the kernels with events on the launching stream. */
+int pbwtgpu_set_stream(pbwtgpu_ctx *ctx, void *cuda_stream);
+void *pbwtgpu_get_stream(pbwtgpu_ctx *ctx);
+int pbwtgpu_synchronize(pbwtgpu_ctx *ctx);
+/* Tuning knobs (0 = automatic): number of site windows swept concurrently, match-record capacity. */
+int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value);
+/* Per-kernel-class device times of the last sweep (ms, CUDA events on the launching stream) and
+ * launch counts; arrays of PBWTGPU_NUM_KERNEL_CLASSES. */
+enum { PBWTGPU_K_SWEEP = 0, PBWTGPU_K_PACK3 = 1, PBWTGPU_K_UNPACK3 = 2, PBWTGPU_K_QUERY = 3,
+       PBWTGPU_K_SYNTH = 4, PBWTGPU_K_AUX = 5, PBWTGPU_NUM_KERNEL_CLASSES = 6 };
+int pbwtgpu_profile(pbwtgpu_ctx *ctx, int enable);
+int pbwtgpu_last_timings(pbwtgpu_ctx *ctx, float *ms, int *launches);
+
+/* ---- panels --------------------------------------------------------------------------------- */
+int pbwtgpu_panel_from_host(pbwtgpu_ctx *ctx, const uint32_t *xbits, int M, int N, pbwtgpu_panel **panel);
+/* Counter-based synthetic mosaic panel generated on the device (bit-identical to
+ * oracle/pbwt_oracle.c:orc_generate). flip_thresh = P(flip) * 2^32. */
+int pbwtgpu_panel_synthetic(pbwtgpu_ctx *ctx, int M, int N, uint64_t seed, uint32_t L, uint32_t flip_thresh,
+                            pbwtgpu_panel **panel);
+int pbwtgpu_panel_to_host(pbwtgpu_ctx *ctx, const pbwtgpu_panel *panel, int first_site, int nsites, uint32_t *xbits);
+void pbwtgpu_panel_free(pbwtgpu_ctx *ctx, pbwtgpu_panel *panel);
+
+/* ---- device-resident sweeps ----------------------------------------------------------------- */
+/* Build from bit columns: replaces the readers' per-site loop
+ *   for j: u->y[j] = x[u->a[j]]; pbwtCursorWriteForwards(u)      (pbwtIO.c:572-574, pbwtCore.c:573-585)
+ * over all N sites, and (WANT_MAXWITHIN) the matchMaximalWithin sweep over the same states
+ * (pbwtMatch.c:115-142), in one pass.  a_start (host, may be NULL = identity) is p->aFstart. */
+int pbwtgpu_build_device(pbwtgpu_ctx *ctx, const pbwtgpu_panel *panel, const int32_t *a_start, unsigned flags,
+                         pbwtgpu_result **result);
+/* Sweep a stored pack3 stream (host buffer as read by pbwtRead, pbwtIO.c:172-217): device unpack3
+ * (pbwtCore.c:279-305) + pbwtCursorForwardsReadAD over all sites (pbwtCore.c:543-557)
+ * [+ matchMaximalWithin].  WANT_YZ is ignored. */
+int pbwtgpu_sweep_yz_device(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start,
+                            unsigned flags, pbwtgpu_result **result);
+int pbwtgpu_result_sizes(const pbwtgpu_result *result, int64_t *nyz, int64_t *nmatch);
+/* D2H of whatever is non-NULL: yz[nyz], a_end[M] (= p->aFend, pbwtCore.c:587-591), d_end[M+1],
+ * matches[nmatch]. */
+int pbwtgpu_result_fetch(pbwtgpu_ctx *ctx, const pbwtgpu_result *result, uint8_t *yz, int32_t *a_end, int32_t *d_end,
+                         pbwtgpu_match *matches);
+void pbwtgpu_result_free(pbwtgpu_ctx *ctx, pbwtgpu_result *result);
+
+/* ---- one-shot host-buffer entry points (what the host shim calls) --------------------------- */
+/* H2D of the columns, sweep, D2H.  *yz and *matches are malloc()'d (free with pbwtgpu_free or
+ * free); a_end / d_end are caller-allocated (int[M], int[M+1]) or NULL. */
+int pbwtgpu_build(pbwtgpu_ctx *ctx, const uint32_t *xbits, int M, int N, const int32_t *a_start, unsigned flags,
+                  uint8_t **yz, int64_t *nyz, int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches,
+                  int64_t *nmatch);
+/* matchMaximalWithin(p, report) over a stored stream (pbwtMatch.c:115-142). */
+int pbwtgpu_max_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start,
+                       int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches, int64_t *nmatch);
+/* matchSequencesSweep(p, q, report) (pbwtMatch.c:363-443): panel and query streams as stored. */
+int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int M, int N, const int32_t *pa_start,
+                        const uint8_t *qyz, int64_t nqyz, int Q, const int32_t *qa_start, pbwtgpu_match **matches,
+                        int64_t *nmatch, pbwtgpu_nomatch **nomatch, int64_t *nnomatch);
+/* pack3 / unpack3 of whole streams on the device (pbwtCore.c:254-305): y is N columns of M bytes. */
+int pbwtgpu_pack3(pbwtgpu_ctx *ctx, const uint8_t *y, int M, int N, uint8_t **yz, int64_t *nyz);
+int pbwtgpu_unpack3(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, uint8_t *y, int32_t *zero_counts);
+void pbwtgpu_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBWTGPU_H */

@@ -1,0 +1,277 @@
+"""ctypes binding of include/pbwtgpu.h (the C ABI of libpbwtgpu.so).
+
+Python here is plumbing for tests and bench.py only: every call goes straight into the CUDA
+library.  There is no CPU fallback -- if the library is missing or no sm_100 device is present
+the constructors raise.
+
+Host-side mirror of the reference interface for this path (names as in pbwt.h):
+  * ``Engine.build``          <- readers' loop + pbwtCursorWriteForwards  (pbwtIO.c:572-574)
+  * ``Engine.max_within``     <- matchMaximalWithin(p, report)            (pbwtMatch.c:115-142)
+  * ``Engine.match_sweep``    <- matchSequencesSweep(p, q, report)        (pbwtMatch.c:363-443)
+  * ``Engine.pack3/unpack3``  <- pack3 / unpack3                          (pbwtCore.c:254-305)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpbwtgpu.so")
+
+WANT_YZ, WANT_D, WANT_MAXWITHIN = 1, 2, 4
+KERNEL_CLASSES = ("sweep", "pack3", "unpack3", "query", "synth", "aux")
+
+MATCH_DTYPE = np.dtype([("ai", "<i4"), ("bi", "<i4"), ("start", "<i4"), ("end", "<i4")])
+NOMATCH_DTYPE = np.dtype([("query", "<i4"), ("allele", "<i4"), ("site", "<i4")])
+
+_vp = C.c_void_p
+_i64 = C.c_int64
+
+
+class PbwtGpuError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libpbwtgpu.so; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PbwtGpuError(f"{LIB_PATH} not built: run __graft_entry__.build() (there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        lib.pbwtgpu_strerror.restype = C.c_char_p
+        lib.pbwtgpu_last_error.restype = C.c_char_p
+        lib.pbwtgpu_last_error.argtypes = [_vp]
+        lib.pbwtgpu_get_stream.restype = _vp
+        lib.pbwtgpu_get_stream.argtypes = [_vp]
+        lib.pbwtgpu_set_stream.argtypes = [_vp, _vp]
+        lib.pbwtgpu_set_option.argtypes = [_vp, C.c_char_p, C.c_longlong]
+        lib.pbwtgpu_init.argtypes = [C.c_int, C.POINTER(_vp)]
+        lib.pbwtgpu_destroy.argtypes = [_vp]
+        lib.pbwtgpu_destroy.restype = None
+        lib.pbwtgpu_synchronize.argtypes = [_vp]
+        lib.pbwtgpu_profile.argtypes = [_vp, C.c_int]
+        lib.pbwtgpu_last_timings.argtypes = [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        lib.pbwtgpu_panel_from_host.argtypes = [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]
+        lib.pbwtgpu_panel_synthetic.argtypes = [_vp, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(_vp)]
+        lib.pbwtgpu_panel_to_host.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp]
+        lib.pbwtgpu_panel_free.argtypes = [_vp, _vp]
+        lib.pbwtgpu_panel_free.restype = None
+        lib.pbwtgpu_build_device.argtypes = [_vp, _vp, _vp, C.c_uint, C.POINTER(_vp)]
+        lib.pbwtgpu_sweep_yz_device.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, C.c_uint, C.POINTER(_vp)]
+        lib.pbwtgpu_result_sizes.argtypes = [_vp, C.POINTER(_i64), C.POINTER(_i64)]
+        lib.pbwtgpu_result_fetch.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
+        lib.pbwtgpu_result_free.argtypes = [_vp, _vp]
+        lib.pbwtgpu_result_free.restype = None
+        lib.pbwtgpu_build.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_uint, C.POINTER(_vp), C.POINTER(_i64), _vp, _vp,
+                                      C.POINTER(_vp), C.POINTER(_i64)]
+        lib.pbwtgpu_max_within.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_i64)]
+        lib.pbwtgpu_match_sweep.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _i64, C.c_int, _vp, C.POINTER(_vp),
+                                            C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_i64)]
+        lib.pbwtgpu_pack3.argtypes = [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_i64)]
+        lib.pbwtgpu_unpack3.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp]
+        lib.pbwtgpu_free.argtypes = [_vp]
+        lib.pbwtgpu_free.restype = None
+        _lib = lib
+    return _lib
+
+
+def words_per_col(M: int) -> int:
+    return 4 * ((M + 127) // 128)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def _take(lib, p: _vp, nbytes: int, dtype) -> np.ndarray:
+    """Copy a malloc()'d buffer returned by the library into numpy and free it."""
+    out = np.frombuffer(C.string_at(p, nbytes), dtype=dtype).copy() if nbytes else np.zeros(0, dtype)
+    lib.pbwtgpu_free(p)
+    return out
+
+
+class Panel:
+    def __init__(self, eng: "Engine", handle: _vp, M: int, N: int):
+        self.eng, self.handle, self.M, self.N = eng, handle, M, N
+
+    def to_host(self, first: int = 0, nsites: int | None = None) -> np.ndarray:
+        n = self.N - first if nsites is None else nsites
+        out = np.zeros((n, words_per_col(self.M)), np.uint32)
+        self.eng._check(self.eng.lib.pbwtgpu_panel_to_host(self.eng.ctx, self.handle, first, n, _ptr(out)))
+        return out
+
+    def free(self):
+        if self.handle:
+            self.eng.lib.pbwtgpu_panel_free(self.eng.ctx, self.handle)
+            self.handle = None
+
+
+class Result:
+    def __init__(self, eng: "Engine", handle: _vp, M: int, N: int, flags: int):
+        self.eng, self.handle, self.M, self.N, self.flags = eng, handle, M, N, flags
+        nyz, nm = _i64(0), _i64(0)
+        eng.lib.pbwtgpu_result_sizes(handle, C.byref(nyz), C.byref(nm))
+        self.nyz, self.nmatch = nyz.value, nm.value
+
+    def fetch(self, yz=True, a_end=True, d_end=True, matches=True, out=None):
+        """D2H. ``out`` may hold preallocated (e.g. pinned) numpy buffers keyed yz/a_end/d_end/matches."""
+        out = out or {}
+        has_d = bool(self.flags & (WANT_D | WANT_MAXWITHIN))
+        bufs = {
+            "yz": (out.get("yz", np.zeros(max(self.nyz, 1), np.uint8)) if yz and (self.flags & WANT_YZ) else None),
+            "a_end": out.get("a_end", np.zeros(self.M, np.int32)) if a_end else None,
+            "d_end": (out.get("d_end", np.zeros(self.M + 1, np.int32)) if d_end and has_d else None),
+            "matches": (out.get("matches", np.zeros(max(self.nmatch, 1), MATCH_DTYPE))
+                        if matches and (self.flags & WANT_MAXWITHIN) else None),
+        }
+        self.eng._check(self.eng.lib.pbwtgpu_result_fetch(self.eng.ctx, self.handle, _ptr(bufs["yz"]), _ptr(bufs["a_end"]),
+                                                          _ptr(bufs["d_end"]), _ptr(bufs["matches"])))
+        if bufs["yz"] is not None:
+            bufs["yz"] = bufs["yz"][: self.nyz]
+        if bufs["matches"] is not None:
+            bufs["matches"] = bufs["matches"][: self.nmatch]
+        return bufs
+
+    def free(self):
+        if self.handle:
+            self.eng.lib.pbwtgpu_result_free(self.eng.ctx, self.handle)
+            self.handle = None
+
+
+class Engine:
+    """One per GPU.  Raises PbwtGpuError if the CUDA library or an sm_100 device is unavailable."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        ctx = _vp()
+        rc = self.lib.pbwtgpu_init(device, C.byref(ctx))
+        if rc != 0:
+            raise PbwtGpuError(f"pbwtgpu_init({device}) failed: {self.lib.pbwtgpu_strerror(rc).decode()}")
+        self.ctx = ctx
+        self.device = device
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.pbwtgpu_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise PbwtGpuError(f"{self.lib.pbwtgpu_strerror(rc).decode()}: {self.lib.pbwtgpu_last_error(self.ctx).decode()}")
+
+    # ---- plumbing ------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._check(self.lib.pbwtgpu_set_stream(self.ctx, cuda_stream_ptr))
+
+    def get_stream(self) -> int:
+        return self.lib.pbwtgpu_get_stream(self.ctx)
+
+    def synchronize(self):
+        self._check(self.lib.pbwtgpu_synchronize(self.ctx))
+
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.pbwtgpu_set_option(self.ctx, name.encode(), value))
+
+    def profile(self, enable: bool):
+        self._check(self.lib.pbwtgpu_profile(self.ctx, int(enable)))
+
+    def last_timings(self):
+        n = len(KERNEL_CLASSES)
+        ms = (C.c_float * n)()
+        cnt = (C.c_int * n)()
+        self._check(self.lib.pbwtgpu_last_timings(self.ctx, ms, cnt))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(KERNEL_CLASSES)}
+
+    # ---- panels --------------------------------------------------------------------------
+    def panel_from_host(self, xbits: np.ndarray, M: int) -> Panel:
+        xbits = np.ascontiguousarray(xbits, np.uint32)
+        N = xbits.shape[0] if xbits.ndim == 2 else xbits.size // words_per_col(M)
+        h = _vp()
+        self._check(self.lib.pbwtgpu_panel_from_host(self.ctx, _ptr(xbits), M, N, C.byref(h)))
+        self.synchronize()
+        return Panel(self, h, M, N)
+
+    def panel_synthetic(self, M: int, N: int, seed: int, L: int = 2000, mu: float = 2.0) -> Panel:
+        thresh = min(int(mu / M * 2**32), 2**32 - 1)
+        h = _vp()
+        self._check(self.lib.pbwtgpu_panel_synthetic(self.ctx, M, N, C.c_uint64(seed), L, thresh, C.byref(h)))
+        return Panel(self, h, M, N)
+
+    # ---- device-resident sweeps ----------------------------------------------------------
+    def build_device(self, panel: Panel, flags: int, a_start=None) -> Result:
+        a0 = None if a_start is None else np.ascontiguousarray(a_start, np.int32)
+        h = _vp()
+        self._check(self.lib.pbwtgpu_build_device(self.ctx, panel.handle, _ptr(a0), flags, C.byref(h)))
+        return Result(self, h, panel.M, panel.N, flags)
+
+    def sweep_yz_device(self, yz: np.ndarray, M: int, N: int, flags: int, a_start=None) -> Result:
+        yz = np.ascontiguousarray(yz, np.uint8)
+        a0 = None if a_start is None else np.ascontiguousarray(a_start, np.int32)
+        h = _vp()
+        self._check(self.lib.pbwtgpu_sweep_yz_device(self.ctx, _ptr(yz), yz.size, M, N, _ptr(a0), flags, C.byref(h)))
+        return Result(self, h, M, N, flags | WANT_D)
+
+    # ---- one-shot host API (the drop-in boundary) ----------------------------------------
+    def build(self, xbits: np.ndarray, M: int, N: int, a_start=None, with_d=True, with_matches=False, with_yz=True):
+        """-> dict(yz, a_end, d_end, matches) exactly as the reference would leave them."""
+        xbits = np.ascontiguousarray(xbits, np.uint32)
+        a0 = None if a_start is None else np.ascontiguousarray(a_start, np.int32)
+        flags = (WANT_YZ if with_yz else 0) | (WANT_D if with_d else 0) | (WANT_MAXWITHIN if with_matches else 0)
+        yz, nyz, mt, nm = _vp(), _i64(0), _vp(), _i64(0)
+        a_end = np.zeros(M, np.int32)
+        d_end = np.zeros(M + 1, np.int32) if (with_d or with_matches) else None
+        self._check(self.lib.pbwtgpu_build(self.ctx, _ptr(xbits), M, N, _ptr(a0), flags, C.byref(yz), C.byref(nyz),
+                                           _ptr(a_end), _ptr(d_end), C.byref(mt), C.byref(nm)))
+        return {
+            "yz": _take(self.lib, yz, nyz.value, np.uint8) if with_yz else None,
+            "a_end": a_end,
+            "d_end": d_end,
+            "matches": _take(self.lib, mt, nm.value * 16, MATCH_DTYPE) if with_matches else None,
+        }
+
+    def max_within(self, yz: np.ndarray, M: int, N: int, a_start=None, with_matches=True):
+        yz = np.ascontiguousarray(yz, np.uint8)
+        a0 = None if a_start is None else np.ascontiguousarray(a_start, np.int32)
+        mt, nm = _vp(), _i64(0)
+        a_end, d_end = np.zeros(M, np.int32), np.zeros(M + 1, np.int32)
+        self._check(self.lib.pbwtgpu_max_within(self.ctx, _ptr(yz), yz.size, M, N, _ptr(a0), _ptr(a_end), _ptr(d_end),
+                                                C.byref(mt) if with_matches else None, C.byref(nm)))
+        return {"a_end": a_end, "d_end": d_end,
+                "matches": _take(self.lib, mt, nm.value * 16, MATCH_DTYPE) if with_matches else None}
+
+    def match_sweep(self, pyz, M, N, qyz, Q, pa_start=None, qa_start=None):
+        pyz = np.ascontiguousarray(pyz, np.uint8)
+        qyz = np.ascontiguousarray(qyz, np.uint8)
+        pa = None if pa_start is None else np.ascontiguousarray(pa_start, np.int32)
+        qa = None if qa_start is None else np.ascontiguousarray(qa_start, np.int32)
+        mt, nm, nom, nn = _vp(), _i64(0), _vp(), _i64(0)
+        self._check(self.lib.pbwtgpu_match_sweep(self.ctx, _ptr(pyz), pyz.size, M, N, _ptr(pa), _ptr(qyz), qyz.size, Q,
+                                                 _ptr(qa), C.byref(mt), C.byref(nm), C.byref(nom), C.byref(nn)))
+        return _take(self.lib, mt, nm.value * 16, MATCH_DTYPE), _take(self.lib, nom, nn.value * 12, NOMATCH_DTYPE)
+
+    def pack3(self, y: np.ndarray) -> np.ndarray:
+        """y: uint8 [N, M] sorted columns -> concatenated pack3 stream."""
+        y = np.ascontiguousarray(y, np.uint8)
+        N, M = y.shape
+        yz, nyz = _vp(), _i64(0)
+        self._check(self.lib.pbwtgpu_pack3(self.ctx, _ptr(y), M, N, C.byref(yz), C.byref(nyz)))
+        return _take(self.lib, yz, nyz.value, np.uint8)
+
+    def unpack3(self, yz: np.ndarray, M: int, N: int):
+        yz = np.ascontiguousarray(yz, np.uint8)
+        y = np.zeros((max(N, 1), M), np.uint8)
+        zc = np.zeros(max(N, 1), np.int32)
+        self._check(self.lib.pbwtgpu_unpack3(self.ctx, _ptr(yz), yz.size, M, N, _ptr(y), _ptr(zc)))
+        return y[:N], zc[:N]

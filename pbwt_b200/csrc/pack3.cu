@@ -1,0 +1,321 @@
+// pack3.cu -- the reference's 3-level run-length codec on the device.
+//
+// Encode (pack3 / pack3Add / pack3arrayAdd, pbwtCore.c:240-277): the sweep kernels hand over the
+// sorted columns y_k as bit columns; columns are independent, so one warp encodes one column.
+// Runs are found with word-wide bit tricks (a run ends where a bit differs from its successor),
+// per-lane byte counts are prefix-summed inside the warp, and column byte offsets come from an
+// exclusive scan of the per-column byte counts (runs never span columns: pack3 is called per column).
+//
+// Decode (unpack3, pbwtCore.c:279-305): a 64-bit prefix sum of the run lengths coded by every byte
+// gives each run's absolute symbol position; column boundaries fall where that position crosses a
+// multiple of M.  Runs of 1s are OR-ed into a zeroed bit-column buffer.
+#include "pack3.cuh"
+
+namespace pbwtgpu {
+namespace {
+
+// Visit the runs of one column that END inside the 32 words of the chunk [w0, w0+32) handled by
+// this warp (lane = word).  carryEnd = last run-end position before the chunk (-1 at column start).
+// f(runValue, runLength, ordinalWithinLane) is called per run, in order, by the owning lane.
+template <typename F>
+__device__ __forceinline__ void visit_runs(const uint32_t *col, int M, int nWords, int w0, int lane, int &carryEnd,
+                                           F &&f) {
+  const int wd = w0 + lane;
+  const int base = wd * 32;
+  uint32_t w = 0, vm = 0;
+  if (wd < nWords) {
+    w = col[wd];
+    vm = (M - base >= 32) ? kFull : ((1u << (M - base)) - 1u);
+  }
+  uint32_t nb = __shfl_down_sync(kFull, w, 1) & 1u;  // first bit of the next word
+  if (lane == 31) nb = (wd + 1 < nWords) ? (col[wd + 1] & 1u) : 0u;
+  uint32_t ends = (w ^ ((w >> 1) | (nb << 31))) & vm;
+  if (wd < nWords && M - 1 >= base && M - 1 < base + 32) ends |= 1u << ((M - 1) & 31);
+  // last end position at or before each lane's word, exclusive over lanes
+  int lastEnd = ends ? base + 31 - __clz(ends) : -1;
+  int x = lastEnd;
+#pragma unroll
+  for (int dl = 1; dl < 32; dl <<= 1) {
+    const int t = __shfl_up_sync(kFull, x, dl);
+    if (lane >= dl) x = max(x, t);
+  }
+  int prevEnd = __shfl_up_sync(kFull, x, 1);
+  if (lane == 0) prevEnd = -1;
+  prevEnd = max(prevEnd, carryEnd);
+  carryEnd = max(carryEnd, __shfl_sync(kFull, x, 31));
+  int ord = 0;
+  while (ends) {
+    const int j = __ffs(ends) - 1;
+    ends &= ends - 1;
+    const int pos = base + j;
+    f((int)((w >> j) & 1u), pos - prevEnd, ord++);
+    prevEnd = pos;
+  }
+}
+
+constexpr int kWarpsPerBlock = 8;
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) p3_count_kernel(const uint32_t *ycols, int wpc, int M, int N,
+                                                                        int32_t *colBytes) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (k >= N) return;
+  const uint32_t *col = ycols + (size_t)k * wpc;
+  const int nWords = (M + 31) / 32;
+  int carryEnd = -1, bytes = 0;
+  for (int w0 = 0; w0 < nWords; w0 += 32)
+    visit_runs(col, M, nWords, w0, lane, carryEnd, [&](int, int n, int) { bytes += p3_run_bytes(n); });
+  bytes = __reduce_add_sync(kFull, bytes);
+  if (lane == 0) colBytes[k] = bytes;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) p3_emit_kernel(const uint32_t *ycols, int wpc, int M, int N,
+                                                                       const int64_t *colBase, uint8_t *yz) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (k >= N) return;
+  const uint32_t *col = ycols + (size_t)k * wpc;
+  const int nWords = (M + 31) / 32;
+  uint8_t *out = yz + colBase[k];
+  int carryEnd = -1;
+  int chunkBase = 0;
+  for (int w0 = 0; w0 < nWords; w0 += 32) {
+    // two passes over the chunk: byte counts per lane, then emission at the prefix offsets
+    int c0 = carryEnd, bytes = 0;
+    visit_runs(col, M, nWords, w0, lane, c0, [&](int, int n, int) { bytes += p3_run_bytes(n); });
+    int x = bytes;
+#pragma unroll
+    for (int dl = 1; dl < 32; dl <<= 1) {
+      const int t = __shfl_up_sync(kFull, x, dl);
+      if (lane >= dl) x += t;
+    }
+    const int total = __shfl_sync(kFull, x, 31);
+    int off = chunkBase + x - bytes;
+    visit_runs(col, M, nWords, w0, lane, carryEnd, [&](int v, int n, int) { off += p3_run_emit(out + off, v, n); });
+    chunkBase += total;
+  }
+}
+
+// Exclusive scan of int32 counts into int64 offsets, out[n] = total. Single block.
+__global__ void __launch_bounds__(1024) scan_i32_to_i64_kernel(const int32_t *in, int64_t *out, int n) {
+  __shared__ long long warpSums[32];
+  __shared__ long long carryS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carryS = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + tid;
+    const long long v = i < n ? in[i] : 0;
+    long long x = v;
+#pragma unroll
+    for (int dl = 1; dl < 32; dl <<= 1) {
+      const long long t = __shfl_up_sync(kFull, x, dl);
+      if (lane >= dl) x += t;
+    }
+    if (lane == 31) warpSums[warp] = x;
+    __syncthreads();
+    long long wv = warpSums[lane];
+    long long wx = wv;
+#pragma unroll
+    for (int dl = 1; dl < 32; dl <<= 1) {
+      const long long t = __shfl_up_sync(kFull, wx, dl);
+      if (lane >= dl) wx += t;
+    }
+    const long long warpOff = __shfl_sync(kFull, wx - wv, warp);
+    const long long blockTotal = __shfl_sync(kFull, wx, 31);
+    const long long carry = carryS;
+    if (i < n) out[i] = carry + warpOff + x - v;
+    __syncthreads();
+    if (tid == 0) carryS = carry + blockTotal;
+    __syncthreads();
+  }
+  if (tid == 0) out[n] = carryS;
+}
+
+// ---- decode ---------------------------------------------------------------------------------
+constexpr int kDecThreads = 256;
+constexpr int kDecPerThread = 8;
+constexpr int kDecTile = kDecThreads * kDecPerThread;
+
+__global__ void __launch_bounds__(kDecThreads) p3_tile_sums_kernel(const uint8_t *yz, int64_t nyz, int64_t *tileSums) {
+  __shared__ long long ws[kDecThreads / 32];
+  const int64_t base = (int64_t)blockIdx.x * kDecTile;
+  long long s = 0;
+  for (int j = 0; j < kDecPerThread; ++j) {
+    const int64_t b = base + (int64_t)j * kDecThreads + threadIdx.x;
+    if (b < nyz) s += p3_byte_len(yz[b]);
+  }
+  s = __reduce_add_sync(kFull, (int)s);  // a tile holds < 2048 * 63488 symbols: fits in int32
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int i = 0; i < kDecThreads / 32; ++i) t += ws[i];
+    tileSums[blockIdx.x] = t;
+  }
+}
+
+// in-place exclusive scan of int64 values, out[n] = total. Single block.
+__global__ void __launch_bounds__(1024) scan_i64_kernel(int64_t *data, int n) {
+  __shared__ long long warpSums[32];
+  __shared__ long long carryS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carryS = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + tid;
+    const long long v = i < n ? data[i] : 0;
+    long long x = v;
+#pragma unroll
+    for (int dl = 1; dl < 32; dl <<= 1) {
+      const long long t = __shfl_up_sync(kFull, x, dl);
+      if (lane >= dl) x += t;
+    }
+    if (lane == 31) warpSums[warp] = x;
+    __syncthreads();
+    long long wv = warpSums[lane];
+    long long wx = wv;
+#pragma unroll
+    for (int dl = 1; dl < 32; dl <<= 1) {
+      const long long t = __shfl_up_sync(kFull, wx, dl);
+      if (lane >= dl) wx += t;
+    }
+    const long long warpOff = __shfl_sync(kFull, wx - wv, warp);
+    const long long blockTotal = __shfl_sync(kFull, wx, 31);
+    const long long carry = carryS;
+    if (i < n) data[i] = carry + warpOff + x - v;
+    __syncthreads();
+    if (tid == 0) carryS = carry + blockTotal;
+    __syncthreads();
+  }
+  if (tid == 0) data[n] = carryS;
+}
+
+__device__ __forceinline__ void or_bits(uint32_t *col, int lo, int hi) {  // set bits [lo, hi)
+  int w = lo >> 5;
+  const int wEnd = (hi - 1) >> 5;
+  uint32_t m = kFull << (lo & 31);
+  for (; w < wEnd; ++w) {
+    atomicOr(&col[w], m);
+    m = kFull;
+  }
+  const int r = hi & 31;
+  if (r) m &= (1u << r) - 1u;
+  atomicOr(&col[w], m);
+}
+
+__global__ void __launch_bounds__(kDecThreads) p3_expand_kernel(const uint8_t *yz, int64_t nyz, const int64_t *tileOff,
+                                                                 int M, int N, int wpc, uint32_t *ycols,
+                                                                 int32_t *zeroCounts) {
+  __shared__ long long ws[kDecThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // blocked assignment: thread t owns bytes [t*P, (t+1)*P) of the tile
+  const int64_t b0 = (int64_t)blockIdx.x * kDecTile + (int64_t)tid * kDecPerThread;
+  int len[kDecPerThread];
+  uint8_t val[kDecPerThread];
+  long long s = 0;
+#pragma unroll
+  for (int j = 0; j < kDecPerThread; ++j) {
+    const int64_t b = b0 + j;
+    const uint8_t byte = b < nyz ? yz[b] : 0;
+    len[j] = p3_byte_len(byte);
+    val[j] = byte >> 7;
+    s += len[j];
+  }
+  long long x = s;
+#pragma unroll
+  for (int dl = 1; dl < 32; dl <<= 1) {
+    const long long t = __shfl_up_sync(kFull, x, dl);
+    if (lane >= dl) x += t;
+  }
+  if (lane == 31) ws[warp] = x;
+  __syncthreads();
+  long long pos = tileOff[blockIdx.x] + x - s;
+  for (int i = 0; i < warp; ++i) pos += ws[i];
+#pragma unroll
+  for (int j = 0; j < kDecPerThread; ++j) {
+    if (len[j] && val[j]) {
+      const long long k = pos / M;
+      const int o = (int)(pos - k * M);
+      if (k < N && o + len[j] <= M) or_bits(ycols + (size_t)k * wpc, o, o + len[j]);
+    } else if (len[j] && zeroCounts) {
+      const long long k = pos / M;
+      if (k < N) atomicAdd(&zeroCounts[k], len[j]);
+    }
+    pos += len[j];
+  }
+}
+
+// bytes-per-allele columns -> bit columns (for the standalone pack3 entry point)
+__global__ void bytes_to_bits_kernel(const uint8_t *y, int M, int N, int wpc, uint32_t *ycols) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nWords = (M + 31) / 32;
+  if (gw >= (long long)N * nWords) return;
+  const int k = (int)(gw / nWords), wd = (int)(gw % nWords);
+  const int i = wd * 32 + lane;
+  const uint32_t bit = i < M ? (y[(size_t)k * M + i] & 1u) : 0u;
+  const uint32_t w = __ballot_sync(kFull, bit);
+  if (lane == 0) ycols[(size_t)k * wpc + wd] = w;
+}
+
+__global__ void bits_to_bytes_kernel(const uint32_t *ycols, int M, int N, int wpc, uint8_t *y) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)N * M) return;
+  const int k = (int)(g / M), i = (int)(g % M);
+  y[g] = (ycols[(size_t)k * wpc + (i >> 5)] >> (i & 31)) & 1u;
+}
+
+}  // namespace
+
+int p3_count_columns(const uint32_t *ycols, int wpc, int M, int N, int32_t *colBytes, int64_t *colBase,
+                     cudaStream_t stream) {
+  if (N > 0) {
+    p3_count_kernel<<<(N + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, stream>>>(ycols, wpc, M, N,
+                                                                                                   colBytes);
+  }
+  scan_i32_to_i64_kernel<<<1, 1024, 0, stream>>>(colBytes, colBase, N);
+  return (int)cudaGetLastError();
+}
+
+int p3_emit_columns(const uint32_t *ycols, int wpc, int M, int N, const int64_t *colBase, uint8_t *yz,
+                    cudaStream_t stream) {
+  if (N > 0)
+    p3_emit_kernel<<<(N + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, stream>>>(ycols, wpc, M, N,
+                                                                                                  colBase, yz);
+  return (int)cudaGetLastError();
+}
+
+int64_t p3_decode_num_tiles(int64_t nyz) { return (nyz + kDecTile - 1) / kDecTile; }
+
+int p3_decode_columns(const uint8_t *yz, int64_t nyz, int M, int N, int wpc, int64_t *tileScratch, uint32_t *ycols,
+                      int32_t *zeroCounts, cudaStream_t stream) {
+  const int64_t nTiles = p3_decode_num_tiles(nyz);
+  cudaMemsetAsync(ycols, 0, (size_t)N * wpc * 4, stream);
+  if (zeroCounts) cudaMemsetAsync(zeroCounts, 0, (size_t)N * 4, stream);
+  if (nTiles == 0) {
+    cudaMemsetAsync(tileScratch, 0, sizeof(int64_t), stream);
+    return (int)cudaGetLastError();
+  }
+  p3_tile_sums_kernel<<<(unsigned)nTiles, kDecThreads, 0, stream>>>(yz, nyz, tileScratch);
+  scan_i64_kernel<<<1, 1024, 0, stream>>>(tileScratch, (int)nTiles);
+  p3_expand_kernel<<<(unsigned)nTiles, kDecThreads, 0, stream>>>(yz, nyz, tileScratch, M, N, wpc, ycols, zeroCounts);
+  return (int)cudaGetLastError();
+}
+
+int bytes_to_bits(const uint8_t *y, int M, int N, int wpc, uint32_t *ycols, cudaStream_t stream) {
+  const long long threads = (long long)N * ((M + 31) / 32) * 32;
+  if (threads == 0) return 0;
+  cudaMemsetAsync(ycols, 0, (size_t)N * wpc * 4, stream);
+  bytes_to_bits_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(y, M, N, wpc, ycols);
+  return (int)cudaGetLastError();
+}
+
+int bits_to_bytes(const uint32_t *ycols, int M, int N, int wpc, uint8_t *y, cudaStream_t stream) {
+  const long long n = (long long)N * M;
+  if (n == 0) return 0;
+  bits_to_bytes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ycols, M, N, wpc, y);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace pbwtgpu

@@ -1,0 +1,19 @@
+// pack3.cuh -- device pack3 codec launchers (see pack3.cu).
+#pragma once
+#include "common.cuh"
+
+namespace pbwtgpu {
+
+// per-column byte counts (int32[N]) and their exclusive scan (int64[N+1], last = total bytes)
+int p3_count_columns(const uint32_t *ycols, int wpc, int M, int N, int32_t *colBytes, int64_t *colBase,
+                     cudaStream_t stream);
+int p3_emit_columns(const uint32_t *ycols, int wpc, int M, int N, const int64_t *colBase, uint8_t *yz,
+                    cudaStream_t stream);
+// decode: tileScratch needs p3_decode_num_tiles(nyz)+1 int64; tileScratch[nTiles] = symbols decoded
+int64_t p3_decode_num_tiles(int64_t nyz);
+int p3_decode_columns(const uint8_t *yz, int64_t nyz, int M, int N, int wpc, int64_t *tileScratch, uint32_t *ycols,
+                      int32_t *zeroCounts, cudaStream_t stream);
+int bytes_to_bits(const uint8_t *y, int M, int N, int wpc, uint32_t *ycols, cudaStream_t stream);
+int bits_to_bytes(const uint32_t *ycols, int M, int N, int wpc, uint8_t *y, cudaStream_t stream);
+
+}  // namespace pbwtgpu

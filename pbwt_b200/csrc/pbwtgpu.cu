@@ -1,0 +1,674 @@
+// pbwtgpu.cu -- C ABI (include/pbwtgpu.h) over the sm_100a kernels.  No CPU fallback anywhere:
+// every entry point either runs the CUDA kernels or returns an error code.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pack3.cuh"
+#include "query.cuh"
+#include "sweep.cuh"
+#include "synth.cuh"
+
+using namespace pbwtgpu;
+
+struct pbwtgpu_ctx {
+  int device = 0;
+  cudaStream_t ownStream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string lastError;
+  // options
+  long long optWindows = 0;    // 0 = automatic
+  long long optMatchCap = 0;   // 0 = automatic
+  // profiling
+  bool profile = false;
+  float ms[PBWTGPU_NUM_KERNEL_CLASSES] = {0};
+  int launches[PBWTGPU_NUM_KERNEL_CLASSES] = {0};
+  struct Pending { int cls; cudaEvent_t a, b; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> eventPool;
+  // freed device blocks kept for reuse (cudaMalloc is far slower than a sweep at small panels)
+  struct Block { void *p; size_t bytes; };
+  std::vector<Block> freeBlocks;
+  int smCount = 0;
+};
+
+struct pbwtgpu_panel {
+  uint32_t *bits = nullptr;
+  int M = 0, N = 0, wpc = 0;
+};
+
+struct pbwtgpu_result {
+  int M = 0, N = 0;
+  uint8_t *yz = nullptr;
+  int64_t nyz = 0;
+  int32_t *aEnd = nullptr;
+  int32_t *dEnd = nullptr;
+  pbwtgpu_match *rec = nullptr;
+  int64_t nrec = 0;
+  std::vector<void *> owned;  // device blocks released by pbwtgpu_result_free
+  std::vector<size_t> ownedBytes;
+};
+
+namespace {
+
+int fail(pbwtgpu_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->lastError = buf;
+  return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                        \
+  do {                                                                                             \
+    cudaError_t e_ = (cudaError_t)(expr);                                                          \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? PBWTGPU_ERR_NOMEM : PBWTGPU_ERR_CUDA,     \
+                  "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_));           \
+  } while (0)
+
+int dev_alloc(pbwtgpu_ctx *ctx, void **out, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  bytes = (bytes + 255) & ~(size_t)255;
+  int best = -1;
+  for (int i = 0; i < (int)ctx->freeBlocks.size(); ++i) {
+    const size_t b = ctx->freeBlocks[i].bytes;
+    if (b >= bytes && b <= 2 * bytes + (1u << 20) && (best < 0 || b < ctx->freeBlocks[best].bytes)) best = i;
+  }
+  if (best >= 0) {
+    *out = ctx->freeBlocks[best].p;
+    ctx->freeBlocks.erase(ctx->freeBlocks.begin() + best);
+    return 0;
+  }
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e != cudaSuccess) {  // drop the cache and retry once
+    for (auto &b : ctx->freeBlocks) cudaFree(b.p);
+    ctx->freeBlocks.clear();
+    e = cudaMalloc(out, bytes);
+  }
+  if (e != cudaSuccess) return fail(ctx, PBWTGPU_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  return 0;
+}
+
+size_t round_bytes(size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  return (bytes + 255) & ~(size_t)255;
+}
+
+void dev_release(pbwtgpu_ctx *ctx, void *p, size_t bytes) {
+  if (!p) return;
+  size_t cached = 0;
+  for (auto &b : ctx->freeBlocks) cached += b.bytes;
+  if (ctx->freeBlocks.size() < 64 && cached + bytes < ((size_t)48 << 30)) ctx->freeBlocks.push_back({p, round_bytes(bytes)});
+  else cudaFree(p);
+}
+
+// scoped temporary device allocations, returned to the context cache on scope exit
+struct Temps {
+  pbwtgpu_ctx *ctx;
+  std::vector<std::pair<void *, size_t>> blocks;
+  explicit Temps(pbwtgpu_ctx *c) : ctx(c) {}
+  ~Temps() {
+    for (auto &b : blocks) dev_release(ctx, b.first, b.second);
+  }
+  template <typename T>
+  int get(T **out, size_t count) {
+    void *p = nullptr;
+    const int rc = dev_alloc(ctx, &p, count * sizeof(T));
+    if (rc) return rc;
+    blocks.push_back({p, count * sizeof(T)});
+    *out = static_cast<T *>(p);
+    return 0;
+  }
+};
+
+template <typename T>
+int result_alloc(pbwtgpu_ctx *ctx, pbwtgpu_result *r, T **out, size_t count) {
+  void *p = nullptr;
+  const int rc = dev_alloc(ctx, &p, count * sizeof(T));
+  if (rc) return rc;
+  r->owned.push_back(p);
+  r->ownedBytes.push_back(count * sizeof(T));
+  *out = static_cast<T *>(p);
+  return 0;
+}
+
+struct ScopedTimer {  // brackets a kernel class with events on the launching stream
+  pbwtgpu_ctx *ctx;
+  int cls;
+  cudaEvent_t a = nullptr, b = nullptr;
+  ScopedTimer(pbwtgpu_ctx *c, int k) : ctx(c), cls(k) {
+    ctx->launches[cls] += 0;
+    if (!ctx->profile) return;
+    a = take();
+    b = take();
+    cudaEventRecord(a, ctx->stream);
+  }
+  cudaEvent_t take() {
+    if (!ctx->eventPool.empty()) {
+      cudaEvent_t e = ctx->eventPool.back();
+      ctx->eventPool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+  ~ScopedTimer() {
+    if (!ctx->profile) return;
+    cudaEventRecord(b, ctx->stream);
+    ctx->pending.push_back({cls, a, b});
+  }
+};
+
+void reset_timings(pbwtgpu_ctx *ctx) {
+  for (auto &p : ctx->pending) {
+    ctx->eventPool.push_back(p.a);
+    ctx->eventPool.push_back(p.b);
+  }
+  ctx->pending.clear();
+  memset(ctx->ms, 0, sizeof ctx->ms);
+  memset(ctx->launches, 0, sizeof ctx->launches);
+}
+
+// ---- the sweep driver shared by build (gather mode) and stored-stream sweeps (sorted mode) ----
+int run_sweep(pbwtgpu_ctx *ctx, const uint32_t *src, int wpc, int M, int N, SweepMode mode, const int32_t *aStartHost,
+              unsigned flags, pbwtgpu_result *res) {
+  const bool wantMatch = flags & PBWTGPU_WANT_MAXWITHIN;
+  const bool wantD = wantMatch || (flags & PBWTGPU_WANT_D);
+  const bool wantYz = (flags & PBWTGPU_WANT_YZ) && mode == kGather;
+  if (M < 1 || N < 0) return fail(ctx, PBWTGPU_ERR_ARG, "bad panel shape M=%d N=%d", M, N);
+  if (M > sweep_smem_max_m(wantD))
+    return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "M=%d exceeds the shared-memory sweep limit %d", M, sweep_smem_max_m(wantD));
+  Temps tmp(ctx);
+  res->M = M;
+  res->N = N;
+
+  int32_t *aStart = nullptr;
+  if (aStartHost) {
+    if (int rc = tmp.get(&aStart, (size_t)M)) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(aStart, aStartHost, sizeof(int32_t) * M, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (int rc = result_alloc(ctx, res, &res->aEnd, (size_t)M)) return rc;
+  if (wantD)
+    if (int rc = result_alloc(ctx, res, &res->dEnd, (size_t)M + 1)) return rc;
+  uint32_t *yOut = nullptr;
+  if (wantYz && N > 0)
+    if (int rc = tmp.get(&yOut, (size_t)N * wpc)) return rc;
+
+  unsigned long long *recCount = nullptr;
+  long long recCap = 0;
+  if (wantMatch) {
+    if (int rc = tmp.get(&recCount, 1)) return rc;
+    recCap = ctx->optMatchCap > 0 ? ctx->optMatchCap : std::min<long long>(std::max<long long>(1 << 20, 4096LL * M), 1LL << 28);
+    if (int rc = result_alloc(ctx, res, &res->rec, (size_t)recCap)) return rc;
+  }
+
+  SweepArgs a{};
+  a.src = src;
+  a.wpc = wpc;
+  a.M = M;
+  a.N = N;
+  a.sitesPerWindow = N > 0 ? N : 1;
+  a.nWindows = 1;
+  a.aStart = aStart;
+  a.dStart = nullptr;
+  a.aEnd = res->aEnd;
+  a.dEnd = res->dEnd;
+  a.yOut = yOut;
+  a.cOut = nullptr;
+  a.rec = res->rec;
+  a.recCap = recCap;
+  a.recCount = recCount;
+  a.reportAtN = 1;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    {
+      ScopedTimer t(ctx, PBWTGPU_K_SWEEP);
+      CUDA_TRY(ctx, launch_sweep_smem(a, mode, wantD, wantMatch, ctx->stream));
+      ctx->launches[PBWTGPU_K_SWEEP] += 1;
+    }
+    if (!wantMatch) break;
+    unsigned long long n = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&n, recCount, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    res->nrec = (int64_t)n;
+    if ((long long)n <= recCap) break;
+    if (attempt == 1) return fail(ctx, PBWTGPU_ERR_CUDA, "match buffer overflow persisted");
+    // the buffer was too small: records were counted but not all stored -- size exactly and rerun
+    recCap = (long long)n;
+    if (int rc = result_alloc(ctx, res, &res->rec, (size_t)recCap)) return rc;
+    a.rec = res->rec;
+    a.recCap = recCap;
+  }
+
+  if (wantYz) {
+    int32_t *colBytes = nullptr;
+    int64_t *colBase = nullptr;
+    if (int rc = tmp.get(&colBytes, (size_t)N + 1)) return rc;
+    if (int rc = tmp.get(&colBase, (size_t)N + 1)) return rc;
+    int64_t total = 0;
+    {
+      ScopedTimer t(ctx, PBWTGPU_K_PACK3);
+      CUDA_TRY(ctx, p3_count_columns(yOut, wpc, M, N, colBytes, colBase, ctx->stream));
+      ctx->launches[PBWTGPU_K_PACK3] += (N > 0) + 1;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(&total, colBase + N, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    res->nyz = total;
+    if (int rc = result_alloc(ctx, res, &res->yz, (size_t)total)) return rc;
+    {
+      ScopedTimer t(ctx, PBWTGPU_K_PACK3);
+      CUDA_TRY(ctx, p3_emit_columns(yOut, wpc, M, N, colBase, res->yz, ctx->stream));
+      ctx->launches[PBWTGPU_K_PACK3] += (N > 0);
+    }
+  }
+  return 0;
+}
+
+int decode_stream(pbwtgpu_ctx *ctx, Temps &tmp, const uint8_t *yzHost, int64_t nyz, int M, int N, uint32_t **ycolsOut,
+                  int32_t *zeroCountsDev) {
+  const int wpc = pbwtgpu_words_per_col(M);
+  uint8_t *yzDev = nullptr;
+  uint32_t *ycols = nullptr;
+  int64_t *tiles = nullptr;
+  if (int rc = tmp.get(&yzDev, (size_t)nyz + 16)) return rc;
+  if (int rc = tmp.get(&ycols, (size_t)std::max(N, 1) * wpc)) return rc;
+  const int64_t nTiles = p3_decode_num_tiles(nyz);
+  if (int rc = tmp.get(&tiles, (size_t)nTiles + 1)) return rc;
+  if (nyz) CUDA_TRY(ctx, cudaMemcpyAsync(yzDev, yzHost, (size_t)nyz, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    ScopedTimer t(ctx, PBWTGPU_K_UNPACK3);
+    CUDA_TRY(ctx, p3_decode_columns(yzDev, nyz, M, N, wpc, tiles, ycols, zeroCountsDev, ctx->stream));
+    ctx->launches[PBWTGPU_K_UNPACK3] += nTiles ? 3 : 0;
+  }
+  int64_t symbols = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&symbols, tiles + nTiles, sizeof symbols, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (symbols != (int64_t)M * N)  // the reference's isCheck assertion, pbwtCore.c:301-302
+    return fail(ctx, PBWTGPU_ERR_ARG, "pack3 stream decodes to %lld symbols, expected M*N = %lld", (long long)symbols,
+                (long long)M * N);
+  *ycolsOut = ycols;
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int pbwtgpu_words_per_col(int M) { return 4 * ((M + 127) / 128); }
+
+const char *pbwtgpu_strerror(int code) {
+  switch (code) {
+    case PBWTGPU_OK: return "ok";
+    case PBWTGPU_ERR_CUDA: return "CUDA error";
+    case PBWTGPU_ERR_ARG: return "invalid argument";
+    case PBWTGPU_ERR_NOMEM: return "out of memory";
+    case PBWTGPU_ERR_UNSUPPORTED: return "unsupported shape";
+    case PBWTGPU_ERR_NODEVICE: return "no sm_100 CUDA device (there is no CPU fallback)";
+    default: return "unknown error";
+  }
+}
+
+int pbwtgpu_init(int device, pbwtgpu_ctx **out) {
+  if (!out) return PBWTGPU_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return PBWTGPU_ERR_NODEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PBWTGPU_ERR_NODEVICE;
+  if (prop.major != 10) return PBWTGPU_ERR_NODEVICE;  // the kernels are built for sm_100a only
+  if (cudaSetDevice(device) != cudaSuccess) return PBWTGPU_ERR_CUDA;
+  pbwtgpu_ctx *ctx = new pbwtgpu_ctx;
+  ctx->device = device;
+  ctx->smCount = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return PBWTGPU_ERR_CUDA;
+  }
+  ctx->stream = ctx->ownStream;
+  *out = ctx;
+  return 0;
+}
+
+void pbwtgpu_destroy(pbwtgpu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  reset_timings(ctx);
+  for (auto e : ctx->eventPool) cudaEventDestroy(e);
+  for (auto &b : ctx->freeBlocks) cudaFree(b.p);
+  cudaStreamDestroy(ctx->ownStream);
+  delete ctx;
+}
+
+const char *pbwtgpu_last_error(pbwtgpu_ctx *ctx) { return ctx ? ctx->lastError.c_str() : "no context"; }
+
+int pbwtgpu_set_stream(pbwtgpu_ctx *ctx, void *s) {
+  if (!ctx) return PBWTGPU_ERR_ARG;
+  ctx->stream = s ? (cudaStream_t)s : ctx->ownStream;
+  return 0;
+}
+void *pbwtgpu_get_stream(pbwtgpu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int pbwtgpu_synchronize(pbwtgpu_ctx *ctx) {
+  if (!ctx) return PBWTGPU_ERR_ARG;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value) {
+  if (!ctx || !name) return PBWTGPU_ERR_ARG;
+  if (!strcmp(name, "windows")) ctx->optWindows = value;
+  else if (!strcmp(name, "match_capacity")) ctx->optMatchCap = value;
+  else return fail(ctx, PBWTGPU_ERR_ARG, "unknown option %s", name);
+  return 0;
+}
+
+int pbwtgpu_profile(pbwtgpu_ctx *ctx, int enable) {
+  if (!ctx) return PBWTGPU_ERR_ARG;
+  ctx->profile = enable != 0;
+  reset_timings(ctx);
+  return 0;
+}
+
+int pbwtgpu_last_timings(pbwtgpu_ctx *ctx, float *ms, int *launches) {
+  if (!ctx) return PBWTGPU_ERR_ARG;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto &p : ctx->pending) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) ctx->ms[p.cls] += t;
+    ctx->eventPool.push_back(p.a);
+    ctx->eventPool.push_back(p.b);
+  }
+  ctx->pending.clear();
+  for (int i = 0; i < PBWTGPU_NUM_KERNEL_CLASSES; ++i) {
+    if (ms) ms[i] = ctx->ms[i];
+    if (launches) launches[i] = ctx->launches[i];
+  }
+  memset(ctx->ms, 0, sizeof ctx->ms);
+  memset(ctx->launches, 0, sizeof ctx->launches);
+  return 0;
+}
+
+// ---- panels ------------------------------------------------------------------------------------
+int pbwtgpu_panel_from_host(pbwtgpu_ctx *ctx, const uint32_t *xbits, int M, int N, pbwtgpu_panel **out) {
+  if (!ctx || !out || M < 1 || N < 0 || (N > 0 && !xbits)) return fail(ctx, PBWTGPU_ERR_ARG, "panel_from_host: bad args");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  pbwtgpu_panel *p = new pbwtgpu_panel;
+  p->M = M;
+  p->N = N;
+  p->wpc = pbwtgpu_words_per_col(M);
+  void *d = nullptr;
+  if (int rc = dev_alloc(ctx, &d, (size_t)std::max(N, 1) * p->wpc * 4)) { delete p; return rc; }
+  p->bits = (uint32_t *)d;
+  if (N) CUDA_TRY(ctx, cudaMemcpyAsync(p->bits, xbits, (size_t)N * p->wpc * 4, cudaMemcpyHostToDevice, ctx->stream));
+  *out = p;
+  return 0;
+}
+
+int pbwtgpu_panel_synthetic(pbwtgpu_ctx *ctx, int M, int N, uint64_t seed, uint32_t L, uint32_t flip_thresh,
+                            pbwtgpu_panel **out) {
+  if (!ctx || !out || M < 1 || N < 0 || L < 1) return fail(ctx, PBWTGPU_ERR_ARG, "panel_synthetic: bad args");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  pbwtgpu_panel *p = new pbwtgpu_panel;
+  p->M = M;
+  p->N = N;
+  p->wpc = pbwtgpu_words_per_col(M);
+  void *d = nullptr;
+  if (int rc = dev_alloc(ctx, &d, (size_t)std::max(N, 1) * p->wpc * 4)) { delete p; return rc; }
+  p->bits = (uint32_t *)d;
+  {
+    ScopedTimer t(ctx, PBWTGPU_K_SYNTH);
+    CUDA_TRY(ctx, launch_synth(p->bits, p->wpc, M, N, 0, seed, L, flip_thresh, ctx->stream));
+    ctx->launches[PBWTGPU_K_SYNTH] += N > 0;
+  }
+  *out = p;
+  return 0;
+}
+
+int pbwtgpu_panel_to_host(pbwtgpu_ctx *ctx, const pbwtgpu_panel *p, int first, int n, uint32_t *xbits) {
+  if (!ctx || !p || first < 0 || n < 0 || first + n > p->N) return fail(ctx, PBWTGPU_ERR_ARG, "panel_to_host: bad range");
+  if (n)
+    CUDA_TRY(ctx, cudaMemcpyAsync(xbits, p->bits + (size_t)first * p->wpc, (size_t)n * p->wpc * 4, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+void pbwtgpu_panel_free(pbwtgpu_ctx *ctx, pbwtgpu_panel *p) {
+  if (!p) return;
+  if (ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    dev_release(ctx, p->bits, (size_t)std::max(p->N, 1) * p->wpc * 4);
+  }
+  delete p;
+}
+
+// ---- sweeps ------------------------------------------------------------------------------------
+int pbwtgpu_build_device(pbwtgpu_ctx *ctx, const pbwtgpu_panel *panel, const int32_t *a_start, unsigned flags,
+                         pbwtgpu_result **out) {
+  if (!ctx || !panel || !out) return fail(ctx, PBWTGPU_ERR_ARG, "build_device: bad args");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  pbwtgpu_result *res = new pbwtgpu_result;
+  const int rc = run_sweep(ctx, panel->bits, panel->wpc, panel->M, panel->N, kGather, a_start, flags, res);
+  if (rc) { pbwtgpu_result_free(ctx, res); return rc; }
+  *out = res;
+  return 0;
+}
+
+int pbwtgpu_sweep_yz_device(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start,
+                            unsigned flags, pbwtgpu_result **out) {
+  if (!ctx || !out || nyz < 0 || (nyz > 0 && !yz) || M < 1 || N < 0) return fail(ctx, PBWTGPU_ERR_ARG, "sweep_yz: bad args");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  Temps tmp(ctx);
+  uint32_t *ycols = nullptr;
+  if (int rc = decode_stream(ctx, tmp, yz, nyz, M, N, &ycols, nullptr)) return rc;
+  pbwtgpu_result *res = new pbwtgpu_result;
+  const int rc = run_sweep(ctx, ycols, pbwtgpu_words_per_col(M), M, N, kSorted, a_start, flags | PBWTGPU_WANT_D, res);
+  if (rc) { pbwtgpu_result_free(ctx, res); return rc; }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // temporaries are recycled on return
+  *out = res;
+  return 0;
+}
+
+int pbwtgpu_result_sizes(const pbwtgpu_result *r, int64_t *nyz, int64_t *nmatch) {
+  if (!r) return PBWTGPU_ERR_ARG;
+  if (nyz) *nyz = r->nyz;
+  if (nmatch) *nmatch = r->nrec;
+  return 0;
+}
+
+int pbwtgpu_result_fetch(pbwtgpu_ctx *ctx, const pbwtgpu_result *r, uint8_t *yz, int32_t *a_end, int32_t *d_end,
+                         pbwtgpu_match *matches) {
+  if (!ctx || !r) return fail(ctx, PBWTGPU_ERR_ARG, "result_fetch: bad args");
+  if (yz && r->yz && r->nyz)
+    CUDA_TRY(ctx, cudaMemcpyAsync(yz, r->yz, (size_t)r->nyz, cudaMemcpyDeviceToHost, ctx->stream));
+  if (a_end && r->aEnd)
+    CUDA_TRY(ctx, cudaMemcpyAsync(a_end, r->aEnd, sizeof(int32_t) * r->M, cudaMemcpyDeviceToHost, ctx->stream));
+  if (d_end && r->dEnd)
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_end, r->dEnd, sizeof(int32_t) * (r->M + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  if (matches && r->rec && r->nrec)
+    CUDA_TRY(ctx, cudaMemcpyAsync(matches, r->rec, sizeof(pbwtgpu_match) * (size_t)r->nrec, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+void pbwtgpu_result_free(pbwtgpu_ctx *ctx, pbwtgpu_result *r) {
+  if (!r) return;
+  if (ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    for (size_t i = 0; i < r->owned.size(); ++i) dev_release(ctx, r->owned[i], r->ownedBytes[i]);
+  }
+  delete r;
+}
+
+// ---- one-shot host-buffer entry points -----------------------------------------------------------
+static int fetch_to_malloc(pbwtgpu_ctx *ctx, pbwtgpu_result *res, uint8_t **yz, int64_t *nyz, int32_t *a_end,
+                           int32_t *d_end, pbwtgpu_match **matches, int64_t *nmatch) {
+  uint8_t *hy = nullptr;
+  pbwtgpu_match *hm = nullptr;
+  if (yz) {
+    hy = (uint8_t *)malloc((size_t)std::max<int64_t>(res->nyz, 1));
+    if (!hy) return fail(ctx, PBWTGPU_ERR_NOMEM, "malloc yz");
+  }
+  if (matches) {
+    hm = (pbwtgpu_match *)malloc(sizeof(pbwtgpu_match) * (size_t)std::max<int64_t>(res->nrec, 1));
+    if (!hm) { free(hy); return fail(ctx, PBWTGPU_ERR_NOMEM, "malloc matches"); }
+  }
+  const int rc = pbwtgpu_result_fetch(ctx, res, hy, a_end, d_end, hm);
+  if (rc) { free(hy); free(hm); return rc; }
+  if (yz) { *yz = hy; if (nyz) *nyz = res->nyz; }
+  if (matches) { *matches = hm; if (nmatch) *nmatch = res->nrec; }
+  return 0;
+}
+
+int pbwtgpu_build(pbwtgpu_ctx *ctx, const uint32_t *xbits, int M, int N, const int32_t *a_start, unsigned flags,
+                  uint8_t **yz, int64_t *nyz, int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches,
+                  int64_t *nmatch) {
+  pbwtgpu_panel *panel = nullptr;
+  if (int rc = pbwtgpu_panel_from_host(ctx, xbits, M, N, &panel)) return rc;
+  pbwtgpu_result *res = nullptr;
+  int rc = pbwtgpu_build_device(ctx, panel, a_start, flags, &res);
+  if (!rc) rc = fetch_to_malloc(ctx, res, (flags & PBWTGPU_WANT_YZ) ? yz : nullptr, nyz, a_end, d_end,
+                                (flags & PBWTGPU_WANT_MAXWITHIN) ? matches : nullptr, nmatch);
+  pbwtgpu_result_free(ctx, res);
+  pbwtgpu_panel_free(ctx, panel);
+  return rc;
+}
+
+int pbwtgpu_max_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start,
+                       int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches, int64_t *nmatch) {
+  pbwtgpu_result *res = nullptr;
+  int rc = pbwtgpu_sweep_yz_device(ctx, yz, nyz, M, N, a_start, matches ? PBWTGPU_WANT_MAXWITHIN : PBWTGPU_WANT_D, &res);
+  if (!rc) rc = fetch_to_malloc(ctx, res, nullptr, nullptr, a_end, d_end, matches, nmatch);
+  pbwtgpu_result_free(ctx, res);
+  return rc;
+}
+
+int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int M, int N, const int32_t *pa_start,
+                        const uint8_t *qyz, int64_t nqyz, int Q, const int32_t *qa_start, pbwtgpu_match **matches,
+                        int64_t *nmatch, pbwtgpu_nomatch **nomatch, int64_t *nnomatch) {
+  if (!ctx || !matches || !nmatch || M < 1 || Q < 1 || N < 0) return fail(ctx, PBWTGPU_ERR_ARG, "match_sweep: bad args");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (M > sweep_smem_max_m(true))
+    return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "match_sweep: panel M=%d exceeds %d", M, sweep_smem_max_m(true));
+  Temps tmp(ctx);
+  uint32_t *pcols = nullptr, *qcols = nullptr;
+  if (int rc = decode_stream(ctx, tmp, pyz, npyz, M, N, &pcols, nullptr)) return rc;
+  if (int rc = decode_stream(ctx, tmp, qyz, nqyz, Q, N, &qcols, nullptr)) return rc;
+  int32_t *pa = nullptr, *qa = nullptr;
+  if (pa_start) {
+    if (int rc = tmp.get(&pa, (size_t)M)) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(pa, pa_start, sizeof(int32_t) * M, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (qa_start) {
+    if (int rc = tmp.get(&qa, (size_t)Q)) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(qa, qa_start, sizeof(int32_t) * Q, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  unsigned long long *counts = nullptr;  // [0] records, [1] nomatch events
+  if (int rc = tmp.get(&counts, 2)) return rc;
+  long long recCap = ctx->optMatchCap > 0 ? ctx->optMatchCap : std::max<long long>(1 << 20, 64LL * Q * 64);
+  long long nmCap = 1 << 16;
+  pbwtgpu_match *rec = nullptr;
+  pbwtgpu_nomatch *nm = nullptr;
+  unsigned long long got[2] = {0, 0};
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (int rc = tmp.get(&rec, (size_t)recCap)) return rc;
+    if (int rc = tmp.get(&nm, (size_t)nmCap)) return rc;
+    QueryArgs q{};
+    q.pcols = pcols; q.qcols = qcols;
+    q.pwpc = pbwtgpu_words_per_col(M); q.qwpc = pbwtgpu_words_per_col(Q);
+    q.M = M; q.Q = Q; q.N = N;
+    q.paStart = pa; q.qaStart = qa;
+    q.rec = rec; q.recCap = recCap; q.nomatch = nm; q.nomatchCap = nmCap; q.counts = counts;
+    {
+      ScopedTimer t(ctx, PBWTGPU_K_QUERY);
+      CUDA_TRY(ctx, launch_query_sweep(q, ctx->stream));
+      ctx->launches[PBWTGPU_K_QUERY] += 1;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(got, counts, sizeof got, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((long long)got[0] <= recCap && (long long)got[1] <= nmCap) break;
+    if (attempt == 1) return fail(ctx, PBWTGPU_ERR_CUDA, "query sweep buffer overflow persisted");
+    recCap = std::max<long long>(recCap, (long long)got[0]);
+    nmCap = std::max<long long>(nmCap, (long long)got[1]);
+  }
+  pbwtgpu_match *hm = (pbwtgpu_match *)malloc(sizeof(pbwtgpu_match) * (size_t)std::max<unsigned long long>(got[0], 1));
+  pbwtgpu_nomatch *hn = (pbwtgpu_nomatch *)malloc(sizeof(pbwtgpu_nomatch) * (size_t)std::max<unsigned long long>(got[1], 1));
+  if (!hm || !hn) { free(hm); free(hn); return fail(ctx, PBWTGPU_ERR_NOMEM, "malloc records"); }
+  if (got[0]) CUDA_TRY(ctx, cudaMemcpyAsync(hm, rec, sizeof(pbwtgpu_match) * got[0], cudaMemcpyDeviceToHost, ctx->stream));
+  if (got[1]) CUDA_TRY(ctx, cudaMemcpyAsync(hn, nm, sizeof(pbwtgpu_nomatch) * got[1], cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *matches = hm;
+  *nmatch = (int64_t)got[0];
+  if (nomatch) *nomatch = hn; else free(hn);
+  if (nnomatch) *nnomatch = (int64_t)got[1];
+  return 0;
+}
+
+int pbwtgpu_pack3(pbwtgpu_ctx *ctx, const uint8_t *y, int M, int N, uint8_t **yz, int64_t *nyz) {
+  if (!ctx || !yz || !nyz || M < 1 || N < 0 || (N > 0 && !y)) return fail(ctx, PBWTGPU_ERR_ARG, "pack3: bad args");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  Temps tmp(ctx);
+  const int wpc = pbwtgpu_words_per_col(M);
+  uint8_t *yDev = nullptr, *yzDev = nullptr;
+  uint32_t *ycols = nullptr;
+  int32_t *colBytes = nullptr;
+  int64_t *colBase = nullptr;
+  if (int rc = tmp.get(&yDev, (size_t)M * std::max(N, 1))) return rc;
+  if (int rc = tmp.get(&ycols, (size_t)wpc * std::max(N, 1))) return rc;
+  if (int rc = tmp.get(&colBytes, (size_t)N + 1)) return rc;
+  if (int rc = tmp.get(&colBase, (size_t)N + 1)) return rc;
+  if (N) CUDA_TRY(ctx, cudaMemcpyAsync(yDev, y, (size_t)M * N, cudaMemcpyHostToDevice, ctx->stream));
+  int64_t total = 0;
+  {
+    ScopedTimer t(ctx, PBWTGPU_K_PACK3);
+    CUDA_TRY(ctx, bytes_to_bits(yDev, M, N, wpc, ycols, ctx->stream));
+    CUDA_TRY(ctx, p3_count_columns(ycols, wpc, M, N, colBytes, colBase, ctx->stream));
+    ctx->launches[PBWTGPU_K_PACK3] += 2 * (N > 0) + 1;
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(&total, colBase + N, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (int rc = tmp.get(&yzDev, (size_t)total + 16)) return rc;
+  {
+    ScopedTimer t(ctx, PBWTGPU_K_PACK3);
+    CUDA_TRY(ctx, p3_emit_columns(ycols, wpc, M, N, colBase, yzDev, ctx->stream));
+    ctx->launches[PBWTGPU_K_PACK3] += (N > 0);
+  }
+  uint8_t *h = (uint8_t *)malloc((size_t)std::max<int64_t>(total, 1));
+  if (!h) return fail(ctx, PBWTGPU_ERR_NOMEM, "malloc yz");
+  if (total) CUDA_TRY(ctx, cudaMemcpyAsync(h, yzDev, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *yz = h;
+  *nyz = total;
+  return 0;
+}
+
+int pbwtgpu_unpack3(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, uint8_t *y, int32_t *zero_counts) {
+  if (!ctx || !y || M < 1 || N < 0 || nyz < 0) return fail(ctx, PBWTGPU_ERR_ARG, "unpack3: bad args");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  Temps tmp(ctx);
+  uint32_t *ycols = nullptr;
+  int32_t *zc = nullptr;
+  uint8_t *yDev = nullptr;
+  if (int rc = tmp.get(&zc, (size_t)N + 1)) return rc;
+  if (int rc = decode_stream(ctx, tmp, yz, nyz, M, N, &ycols, zc)) return rc;
+  if (int rc = tmp.get(&yDev, (size_t)M * std::max(N, 1))) return rc;
+  CUDA_TRY(ctx, bits_to_bytes(ycols, M, N, pbwtgpu_words_per_col(M), yDev, ctx->stream));
+  if (N) CUDA_TRY(ctx, cudaMemcpyAsync(y, yDev, (size_t)M * N, cudaMemcpyDeviceToHost, ctx->stream));
+  if (zero_counts && N)
+    CUDA_TRY(ctx, cudaMemcpyAsync(zero_counts, zc, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+void pbwtgpu_free(void *p) { free(p); }
+
+}  // extern "C"

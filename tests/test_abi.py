@@ -1,0 +1,51 @@
+"""CPU tests: the C-ABI library is built, loads, and exports every symbol include/pbwtgpu.h declares
+(no compute calls without a GPU); without a device the constructors fail loudly -- no CPU fallback."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import pbwt_b200
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "pbwtgpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pbwtgpu_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    assert os.path.exists(pbwt_b200.LIB_PATH), "run __graft_entry__.build() first"
+    lib = ctypes.CDLL(pbwt_b200.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/pbwtgpu.h but not exported"
+
+
+def test_words_per_col_and_strerror():
+    lib = pbwt_b200.load_library()
+    for M in (1, 127, 128, 129, 10000, 100000):
+        assert lib.pbwtgpu_words_per_col(M) == pbwt_b200.words_per_col(M) == 4 * ((M + 127) // 128)
+    assert lib.pbwtgpu_strerror(0) == b"ok"
+    assert b"no CPU fallback" in lib.pbwtgpu_strerror(-5)
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pbwt_b200.PbwtGpuError):
+        pbwt_b200.Engine(0)
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pbwt_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle_lib" not in txt and "libpbwt_oracle" not in txt and "libpbwtref" not in txt, f

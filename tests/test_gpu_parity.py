@@ -1,0 +1,177 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs and against the committed golden fixtures.  Bit-exact: a[], d[], pack3 bytes and
+match records in callback order."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import pbwt_b200
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = pbwt_b200.Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return O.port()
+
+
+def rec4(rec):
+    return np.stack([rec["ai"], rec["bi"], rec["start"], rec["end"]], 1)
+
+
+def check_build(eng, orc, x, M, N, a_start=None, matches=True):
+    yz, a_end, d_end = orc.build(x, M, N, a_start, with_d=True)
+    got = eng.build(x, M, N, a_start=a_start, with_d=True, with_matches=matches and N > 0 and M > 1)
+    assert got["yz"].tobytes() == yz.tobytes()
+    assert (got["a_end"] == a_end).all()
+    assert (got["d_end"] == d_end).all()
+    if matches and N > 0 and M > 1:
+        rec, n = orc.max_within(yz, M, N, a_start)
+        assert len(got["matches"]) == n
+        assert (got["matches"] == rec).all()
+    # a-only build (pbwtCursorWriteForwards) must give the same stream and aFend
+    got2 = eng.build(x, M, N, a_start=a_start, with_d=False)
+    assert got2["yz"].tobytes() == yz.tobytes() and (got2["a_end"] == a_end).all()
+    # stored-stream route: device unpack3 + ForwardsReadAD [+ maxWithin] must agree as well
+    if N > 0:
+        got3 = eng.max_within(yz, M, N, a_start=a_start, with_matches=matches and M > 1)
+        assert (got3["a_end"] == a_end).all() and (got3["d_end"] == d_end).all()
+        if matches and M > 1:
+            assert len(got3["matches"]) == n and (got3["matches"] == rec).all()
+    return yz
+
+
+@pytest.mark.parametrize("name", ["merge1", "merge2", "omni", "mosaic300x400"])
+def test_golden_panels(eng, name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    M, N = int(g["M"]), int(g["N"])
+    got = eng.build(g["xbits"], M, N, with_d=True, with_matches=True)
+    assert got["yz"].tobytes() == g["yz"].tobytes()
+    assert (got["a_end"] == g["a_end"]).all() and (got["d_end"] == g["d_end"]).all()
+    assert (rec4(got["matches"]) == g["matches"]).all()
+    got = eng.max_within(g["yz"], M, N)
+    assert (got["a_end"] == g["a_end"]).all() and (got["d_end"] == g["d_end"]).all()
+    assert (rec4(got["matches"]) == g["matches"]).all()
+
+
+@pytest.mark.parametrize("M", [2, 3, 31, 32, 33, 63, 64, 65, 127, 128, 129, 1000, 1024, 1025, 2752, 4097, 10000, 13312])
+def test_shapes_random(eng, orc, M):
+    rng = np.random.default_rng(M)
+    N = 38 if M < 5000 else 12
+    for dens in (0.5, 0.03):
+        hap = (rng.random((M, N)) < dens).astype(np.uint8)
+        check_build(eng, orc, O.pack_panel(hap), M, N)
+
+
+@pytest.mark.parametrize("N", [0, 1, 2, 5, 38])
+def test_site_counts(eng, orc, N):
+    rng = np.random.default_rng(100 + N)
+    M = 200
+    hap = (rng.random((M, N)) < 0.3).astype(np.uint8)
+    check_build(eng, orc, O.pack_panel(hap) if N else np.zeros((0, O.words_per_col(M)), np.uint32), M, N)
+
+
+def test_special_columns(eng, orc):
+    M = 700
+    cols = [np.zeros(M), np.ones(M), np.eye(1, M, 0)[0], np.eye(1, M, M - 1)[0], np.arange(M) % 2, (np.arange(M) // 3) % 2,
+            np.zeros(M), np.arange(M) % 2, np.ones(M)]
+    rng = np.random.default_rng(5)
+    cols += [(rng.random(M) < 0.5) for _ in range(6)]
+    hap = np.array(cols, np.uint8).T.copy()
+    check_build(eng, orc, O.pack_panel(hap), M, hap.shape[1])
+
+
+def test_non_identity_start_and_duplicates(eng, orc):
+    rng = np.random.default_rng(9)
+    M, N = 600, 60
+    base = (rng.random((40, N)) < 0.4).astype(np.uint8)
+    hap = base[rng.integers(0, 40, M)]  # blocks of identical haplotypes: O(B^2) reports at k == N
+    a0 = rng.permutation(M).astype(np.int32)
+    check_build(eng, orc, O.pack_panel(hap), M, N, a_start=a0)
+
+
+def test_long_runs_pack3_thresholds(eng, orc):
+    """Runs around 64 / 2048 / 63488 inside real columns (a-only path, large M)."""
+    M = 20000
+    cols = []
+    for n in (63, 64, 65, 2047, 2048, 2049, 19000):
+        c = np.zeros(M, np.uint8)
+        c[0] = 1
+        c[n + 1:n + 3] = 1
+        cols.append(c)
+    hap = np.array(cols, np.uint8).T.copy()
+    x = O.pack_panel(hap)
+    yz, a_end, _ = orc.build(x, M, hap.shape[1], with_d=False)
+    got = eng.build(x, M, hap.shape[1], with_d=False)
+    assert got["yz"].tobytes() == yz.tobytes() and (got["a_end"] == a_end).all()
+
+
+def test_pack3_codec_vectors(eng):
+    g = np.load(os.path.join(GOLD, "pack3_vectors.npz"))
+    for key in g.files:
+        n = int(key[1:])
+        y = np.concatenate([[1], np.zeros(n, np.uint8), [1, 1]]).astype(np.uint8)[None, :]
+        enc = eng.pack3(y)
+        assert enc.tobytes() == g[key].tobytes(), key
+        dec, zc = eng.unpack3(enc, y.shape[1], 1)
+        assert (dec == y).all() and zc[0] == n, key
+
+
+def test_pack3_roundtrip_random(eng, orc):
+    rng = np.random.default_rng(3)
+    for M, N, dens in [(1, 5, 0.5), (37, 50, 0.5), (5000, 20, 0.01), (70003, 3, 0.0005), (200003, 2, 0.5)]:
+        y = (rng.random((N, M)) < dens).astype(np.uint8)
+        enc = eng.pack3(y)
+        ref = np.concatenate([orc.pack3(y[k]) for k in range(N)])
+        assert enc.tobytes() == ref.tobytes(), (M, N)
+        dec, zc = eng.unpack3(enc, M, N)
+        assert (dec == y).all() and (zc == (y == 0).sum(1)).all(), (M, N)
+
+
+def test_mosaic_panel_medium(eng, orc):
+    """A realistic low-diversity panel at a size the oracle finishes in seconds."""
+    M, N = 3000, 1500
+    x = O.generate_panel(M, N, seed=0x5EED0002, L=300, mu=2.0)
+    check_build(eng, orc, x, M, N)
+
+
+def test_generator_matches_cpu(eng):
+    for M, N, L, mu in [(500, 300, 50, 3.0), (10000, 40, 2000, 2.0), (33, 7, 5, 1.0)]:
+        p = eng.panel_synthetic(M, N, seed=77, L=L, mu=mu)
+        x = p.to_host()
+        p.free()
+        assert (x == O.generate_panel(M, N, seed=77, L=L, mu=mu)).all(), (M, N)
+
+
+def test_full_size_properties(eng):
+    """BASELINE config 2 shape (10,000 x N_prop sites): size-independent properties instead of the oracle:
+    aFend is a permutation, the stream decodes to exactly M*N symbols whose per-column zero counts match the
+    panel's popcounts, sweeping the emitted stream reproduces a/d, and match records are in range."""
+    M, N = 10000, 4000
+    p = eng.panel_synthetic(M, N, seed=0x5EED0002, L=2000, mu=2.0)
+    res = eng.build_device(p, pbwt_b200.WANT_YZ | pbwt_b200.WANT_MAXWITHIN)
+    out = res.fetch()
+    res.free()
+    x = p.to_host()
+    p.free()
+    assert sorted(out["a_end"].tolist()) == list(range(M))
+    assert out["d_end"][0] == N + 1 and out["d_end"][M] == N + 1 and out["d_end"][1:M].max() <= N
+    y, zc = eng.unpack3(out["yz"], M, N)
+    ones = np.unpackbits(np.ascontiguousarray(x).view(np.uint8), axis=1, bitorder="little").sum(1)
+    assert (zc == M - ones).all()
+    again = eng.max_within(out["yz"], M, N)
+    assert (again["a_end"] == out["a_end"]).all() and (again["d_end"] == out["d_end"]).all()
+    assert len(again["matches"]) == len(out["matches"]) and (again["matches"] == out["matches"]).all()
+    m = out["matches"]
+    assert ((m["start"] <= m["end"]) & (m["end"] <= N) & (m["ai"] != m["bi"]) & (m["ai"] < M) & (m["bi"] < M)).all()
+    assert (np.diff(m["end"]) >= 0).all()  # callback order: k ascending
