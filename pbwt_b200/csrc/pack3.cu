@@ -246,6 +246,18 @@ __global__ void __launch_bounds__(kDecThreads) p3_expand_kernel(const uint8_t *y
   }
 }
 
+// set the pad bits [M, 32*wpc) of every column to one: the sweep kernels treat positions >= M as
+// permanent 1-alleles (sweep_smem.cu)
+__global__ void p3_pad_ones_kernel(uint32_t *ycols, int M, int N, int wpc) {
+  const int firstWord = M >> 5;
+  const int padWords = wpc - firstWord;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)N * padWords) return;
+  const int k = (int)(g / padWords), w = firstWord + (int)(g % padWords);
+  const uint32_t m = (w == firstWord && (M & 31)) ? (kFull << (M & 31)) : kFull;
+  ycols[(size_t)k * wpc + w] |= m;
+}
+
 // bytes-per-allele columns -> bit columns (for the standalone pack3 entry point)
 __global__ void bytes_to_bits_kernel(const uint8_t *y, int M, int N, int wpc, uint32_t *ycols) {
   const int lane = threadIdx.x & 31;
@@ -300,6 +312,8 @@ int p3_decode_columns(const uint8_t *yz, int64_t nyz, int M, int N, int wpc, int
   p3_tile_sums_kernel<<<(unsigned)nTiles, kDecThreads, 0, stream>>>(yz, nyz, tileScratch);
   scan_i64_kernel<<<1, 1024, 0, stream>>>(tileScratch, (int)nTiles);
   p3_expand_kernel<<<(unsigned)nTiles, kDecThreads, 0, stream>>>(yz, nyz, tileScratch, M, N, wpc, ycols, zeroCounts);
+  const long long padThreads = (long long)N * (wpc - (M >> 5));
+  if (padThreads > 0) p3_pad_ones_kernel<<<(unsigned)((padThreads + 255) / 256), 256, 0, stream>>>(ycols, M, N, wpc);
   return (int)cudaGetLastError();
 }
 
