@@ -12,15 +12,21 @@
 // lane l of word j owns position 32*j + l ("striped"), so
 //   * one __ballot_sync per word IS the sorted bit column y_k (no transposition),
 //   * the stable-partition offsets are popcounts of ballots (no shuffles),
-//   * shared-memory accesses to a[]/d[] are conflict-free for every E, addressed base + immediate.
+//   * shared-memory accesses to a[]/d[] are conflict-free for every E, addressed lane base + immediate
+//     (the site loop is unrolled by two so the double-buffer offsets are compile-time constants).
 // Positions M..1024E-1 are pad elements: their a[] points at a column bit that is always 1, so they
 // sort to themselves forever and no per-element validity predicate is needed.
 // Divergence update, single segmented max-scan: d_{k+1}[new(i)] = d_k[i] unless
 // i is the head of a run of equal alleles, in which case it is max(d_k[i], max d_k over the previous
-// run); the first two run heads see the k+1 sentinel in d_k[0].
+// run); the first two run heads see the k+1 sentinel in d_k[0].  The sentinels d[0], d[M] are
+// (re)written by their owner threads at the top of each site.
 // Column bits are staged by 1-D TMA bulk copies (cp.async.bulk + mbarrier), kStages sites ahead.
-// Two __syncthreads per site.  matchMaximalWithin's block scans are warp-cooperative (32 positions
-// per step) and its records are written 32 at a time.
+// Two __syncthreads per site.
+// matchMaximalWithin: block boundaries are found with a two-level search (per-word maxima of d, then
+// within the word), reporters are queued per warp, and blocks of >= kBigBlock records are written by
+// all 32 warps together.
+#include <type_traits>
+
 #include "sweep.cuh"
 
 namespace pbwtgpu {
@@ -28,8 +34,10 @@ namespace {
 
 constexpr int kThreads = 1024;
 constexpr int kStages = 4;
+constexpr int kQueue = 8;       // reporter entries kept per warp between the count and emit phases
+constexpr int kBigBlock = 128;  // records; larger blocks are emitted by the whole CTA
 
-template <int E, bool WITH_D>
+template <int E, bool WITH_D, bool MATCH>
 struct SmemLayout {  // offsets in 32-bit words; every array start is 16-byte aligned
   static constexpr int MP = kThreads * E;
   static constexpr int WORDS = 32 * E;
@@ -42,7 +50,10 @@ struct SmemLayout {  // offsets in 32-bit words; every array start is 16-byte al
   static constexpr int xcol = ycol + 2 * WORDS;
   static constexpr int wsum = xcol + kStages * STAGE;
   static constexpr int mbar = wsum + 3 * 32;
-  static constexpr int totalWords = mbar + 2 * kStages;
+  static constexpr int wmax = mbar + 2 * kStages;
+  static constexpr int queue = wmax + (MATCH ? 2 * WORDS : 0);  // wmax is double-buffered like ycol
+  static constexpr int qcnt = queue + (MATCH ? 32 * kQueue * 4 : 0);
+  static constexpr int totalWords = qcnt + (MATCH ? 32 : 0);
   static constexpr size_t bytes = (size_t)totalWords * 4;
   static constexpr int padIndex = 32 * WORDS;  // "haplotype" whose allele is 1 at every site
 };
@@ -58,7 +69,7 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int &total) {
   return x - v;
 }
 
-// number of positions in [lo, hi) whose allele equals yi, counted from the sorted bit column
+// does any position in [lo, hi) carry allele yi?  (sorted bit column, pad bits beyond M are ones)
 __device__ __forceinline__ bool any_same_allele(const uint32_t *yc, int lo, int hi, uint32_t yi, int lane) {
   if (lo >= hi) return false;
   const int w0 = lo >> 5, w1 = (hi - 1) >> 5;
@@ -72,23 +83,77 @@ __device__ __forceinline__ bool any_same_allele(const uint32_t *yc, int lo, int 
   return __any_sync(kFull, hit);
 }
 
+// nearest q <= i with d[q] > t.  d[0] = k+1 exceeds every interior value, so q exists.
+__device__ __forceinline__ int search_up(const int32_t *sD, const int32_t *wmax, int i, int t, int lane) {
+  const int w = i >> 5;
+  {
+    const int idx = (w << 5) + lane;
+    const unsigned m = __ballot_sync(kFull, idx <= i && sD[idx] > t);
+    if (m) return (w << 5) + 31 - __clz(m);
+  }
+  int ws = w - 1;
+  for (;;) {
+    const int wi = ws - lane;
+    const unsigned m = __ballot_sync(kFull, wi < 0 || wmax[wi] > t);
+    if (m) { ws -= __ffs(m) - 1; break; }
+    ws -= 32;
+  }
+  if (ws < 0) return 0;
+  const unsigned m = __ballot_sync(kFull, sD[(ws << 5) + lane] > t);
+  return m ? (ws << 5) + 31 - __clz(m) : 0;
+}
+
+// nearest r >= from with d[r] > t, clamped to M.  d[M] = k+1 exceeds every interior value.
+__device__ __forceinline__ int search_down(const int32_t *sD, const int32_t *wmax, int from, int t, int M, int lane) {
+  const int w = from >> 5;
+  {
+    const int idx = (w << 5) + lane;
+    const unsigned m = __ballot_sync(kFull, idx >= from && (idx >= M || sD[idx] > t));
+    if (m) return min((w << 5) + __ffs(m) - 1, M);
+  }
+  int ws = w + 1;
+  for (;;) {
+    const int wi = ws + lane;
+    const unsigned m = __ballot_sync(kFull, (wi << 5) >= M || wmax[wi] > t);
+    if (m) { ws += __ffs(m) - 1; break; }
+    ws += 32;
+  }
+  if ((ws << 5) >= M) return M;
+  const int idx = (ws << 5) + lane;
+  const unsigned m = __ballot_sync(kFull, idx >= M || sD[idx] > t);
+  return m ? min((ws << 5) + __ffs(m) - 1, M) : M;
+}
+
+// write the records of reporter i: upward block [lo, i) with start di, then downward block (i, hi) with
+// start dn1 (callback order, pbwtMatch.c:133-134); record t of the block is written by "lane" t0 + t*step
+__device__ __forceinline__ void emit_block(pbwtgpu_match *out, long long cap, long long o, const int32_t *sA, int i,
+                                           int lo, int hi, int di, int dn1, int k, int t0, int step) {
+  const int cnt = (i - lo) + (hi - i - 1);
+  const int ai = sA[i];
+  const int nUp = i - lo;
+  for (int t = t0; t < cnt; t += step) {
+    const int jj = t < nUp ? lo + t : t + lo + 1;  // skips i itself
+    if (o + t < cap) reinterpret_cast<int4 *>(out)[o + t] = make_int4(ai, sA[jj], t < nUp ? di : dn1, k);
+  }
+}
+
 // One pass of matchMaximalWithin's per-site scan (pbwtMatch.c:122-137) over this warp's words.
-//   EMIT = false: count; returns the warp's record total and a bitmask of words that report.
-//   EMIT = true : redo the reporting words and write their records from offset off, in callback
-//                 order: i ascending, upward block (start d[i]) then downward block (start d[i+1]).
 // For a position i the upward block is [q, i) with q the nearest index <= i whose d exceeds d[i], the
 // downward block (i, r) with r the nearest index > i whose d exceeds d[i+1]; i reports nothing when a
 // member of either block carries the same allele (the match extends).  Only heads/tails of allele runs
 // can fail that test on their first neighbour, so interior positions are never scanned (live sites).
+//   EMIT = false: count; reporters are queued in queue[] (up to kQueue); returns the warp's record total
+//                 and the number of reporters seen (nq may exceed kQueue = queue overflow).
+//   EMIT = true : recompute everything and write the records from offset off (overflow fallback).
 template <int E, bool EMIT>
-__device__ __forceinline__ int match_pass(const int32_t *sA, const int32_t *sD, const uint32_t *yc, int M, int k,
-                                          bool live, int warp, int lane, unsigned &wordMask, pbwtgpu_match *out,
-                                          long long cap, long long off) {
+__device__ __forceinline__ int match_pass(const int32_t *sA, const int32_t *sD, const uint32_t *yc,
+                                          const int32_t *wmax, int M, int k, bool live, int warp, int lane, int4 *queue,
+                                          int &nq, bool &hasBig, pbwtgpu_match *out, long long cap, long long off) {
   int warpTotal = 0;
-  unsigned found = 0;
+  nq = 0;
+  hasBig = false;
 #pragma unroll 1
   for (int e = 0; e < E; ++e) {
-    if (EMIT && !((wordMask >> e) & 1u)) continue;
     const int wd = warp * E + e;
     const int base = wd * 32;
     if (base >= M) break;
@@ -97,7 +162,7 @@ __device__ __forceinline__ int match_pass(const int32_t *sA, const int32_t *sD, 
     uint32_t cand = vm;
     if (live) {
       const uint32_t pb = wd > 0 ? (yc[wd - 1] >> 31) : (cw & 1u);
-      const uint32_t nw = (base + 32 < M) ? yc[wd + 1] : 0u;
+      const uint32_t nw = yc[wd + 1 < 32 * E ? wd + 1 : wd];
       const uint32_t H = cw ^ ((cw << 1) | pb);
       const uint32_t Hn = (H >> 1) | (((nw & 1u) ^ (cw >> 31)) << 31);
       const uint32_t bm = (H | Hn) & vm;
@@ -109,9 +174,7 @@ __device__ __forceinline__ int match_pass(const int32_t *sA, const int32_t *sD, 
         mine = !((di <= dn1 && samePrev) || (di >= dn1 && sameNext));
       }
       cand = __ballot_sync(kFull, mine);
-      if (!cand) continue;
     }
-    int wordTotal = 0;
     while (cand) {
       const int j = __ffs(cand) - 1;
       cand &= cand - 1;
@@ -120,62 +183,42 @@ __device__ __forceinline__ int match_pass(const int32_t *sA, const int32_t *sD, 
       const int di = sD[i], dn1 = sD[i + 1];
       int lo = i, hi = i + 1;
       bool extends = false;
-      if (di <= dn1) {  // nearest q <= i with d[q] > d[i]  (d[0] = k+1 always stops the search)
-        int q = i;
-        for (;;) {
-          const int idx = q - lane;
-          const bool stop = idx <= 0 || sD[idx] > di;
-          const unsigned sm = __ballot_sync(kFull, stop);
-          if (sm) { q -= __ffs(sm) - 1; break; }
-          q -= 32;
-        }
-        lo = max(q, 0);
+      if (di <= dn1) {
+        lo = search_up(sD, wmax, i, di, lane);
         extends = live && any_same_allele(yc, lo, i, yi, lane);
       }
-      if (!extends && di >= dn1) {  // nearest r > i with d[r] > d[i+1]  (d[M] = k+1 always stops)
-        int r = i + 1;
-        for (;;) {
-          const int idx = r + lane;
-          const bool stop = idx >= M || sD[idx] > dn1;
-          const unsigned sm = __ballot_sync(kFull, stop);
-          if (sm) { r += __ffs(sm) - 1; break; }
-          r += 32;
-        }
-        hi = min(r, M);
+      if (!extends && di >= dn1) {
+        hi = search_down(sD, wmax, i + 1, dn1, M, lane);
         extends = live && any_same_allele(yc, i + 1, hi, yi, lane);
       }
       if (extends) continue;
       const int cnt = (i - lo) + (hi - i - 1);
-      if (EMIT && cnt) {
-        const long long o = off + wordTotal;
-        const int ai = sA[i];
-        for (int t = lane; t < cnt; t += 32) {
-          const int jj = t < i - lo ? lo + t : t + lo + 1;  // skip i itself
-          if (o + t < cap)
-            reinterpret_cast<int4 *>(out)[o + t] = make_int4(ai, sA[jj], t < i - lo ? di : dn1, k);
-        }
+      if (!cnt) continue;
+      if (EMIT) {
+        emit_block(out, cap, off + warpTotal, sA, i, lo, hi, di, dn1, k, lane, 32);
+      } else {
+        if (nq < kQueue && lane == 0) queue[nq] = make_int4(i, lo, hi, warpTotal);
+        ++nq;
+        hasBig |= cnt >= kBigBlock;
       }
-      wordTotal += cnt;
-    }
-    if (wordTotal) {
-      found |= 1u << e;
-      off += wordTotal;
-      warpTotal += wordTotal;
+      warpTotal += cnt;
     }
   }
-  if (!EMIT) wordMask = found;
   return warpTotal;
 }
 
 template <int E, int MODE, bool WITH_D, bool MATCH>
 __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs p) {
-  using L = SmemLayout<E, WITH_D>;
+  using L = SmemLayout<E, WITH_D, MATCH>;
   extern __shared__ __align__(16) uint32_t smem[];
   int32_t *const sI = reinterpret_cast<int32_t *>(smem);
   int32_t *const wsumZ = sI + L::wsum;
   uint32_t *const wsumR = smem + L::wsum + 32;
   int32_t *const wsumC = sI + L::wsum + 64;
   uint64_t *const mbar = reinterpret_cast<uint64_t *>(smem + L::mbar);
+  int32_t *const wmaxS = sI + L::wmax;
+  int4 *const queueS = reinterpret_cast<int4 *>(smem + L::queue);
+  int32_t *const qcntS = sI + L::qcnt;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = p.M, wpc = p.wpc;
@@ -185,7 +228,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
   const uint32_t colBytes = (uint32_t)wpc * 4u;
   const int wordBase = warp * E;
   const int laneOff = wordBase * 32 + lane;  // position of (word 0 of this warp, this lane)
-  // the thread owning position M (a pad element) also maintains the d[M] sentinel
+  int32_t *const sLane = sI + laneOff;
+  const uint32_t ltMask = lanemask_lt(lane), laneBit = 1u << lane;
+  // the thread owning position M (a pad element, or thread 0 when there is none) maintains d[M]
   const int ownerM = M < L::MP ? ((M >> 5) / E) * 32 + (M & 31) : 0;
 
   // ---- window start state (pbwtNakedCursorCreate, pbwtCore.c:402-418) ----
@@ -194,8 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
   if (WITH_D)
     for (int i = tid; i < L::MP + 4; i += kThreads) {
       int v = 0;
-      if (i == 0 || i == M) v = k0 + 1;
-      else if (i < M && p.dStart) v = p.dStart[(size_t)win * (M + 1) + i];
+      if (i > 0 && i < M && p.dStart) v = p.dStart[(size_t)win * (M + 1) + i];
       sI[L::d0 + i] = v;
       sI[L::d1 + i] = 0;
     }
@@ -216,20 +260,62 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
 
   pbwtgpu_match *recOut = MATCH && p.rec ? p.rec + (size_t)win * p.recCap : nullptr;
   long long recBase = 0;  // records produced so far by this window (uniform)
-  int cur = 0;
 
-  for (int k = k0; k < k1; ++k) {
+  // -------- the emit phase shared by live sites and the final k == N report --------
+  auto emit_phase = [&](const int32_t *sA, const int32_t *sD, const uint32_t *yc, const int32_t *wm, int k, bool live,
+                        int nq) {
+    const int cw = wsumC[lane];
+    int tot;
+    const int ex = warp_excl_scan(cw, lane, tot);
+    if (recOut && tot) {
+      const long long mine = recBase + __shfl_sync(kFull, ex, warp);
+      if (nq > kQueue) {  // queue overflow: this warp redoes its words and writes everything itself
+        int nq2;
+        bool hb;
+        match_pass<E, true>(sA, sD, yc, wm, M, k, live, warp, lane, queueS + warp * kQueue, nq2, hb, recOut, p.recCap,
+                            mine);
+      } else {
+        for (int q = 0; q < nq; ++q) {  // own small blocks
+          const int4 en = queueS[warp * kQueue + q];
+          if ((en.x - en.y) + (en.z - en.x - 1) < kBigBlock)
+            emit_block(recOut, p.recCap, mine + en.w, sA, en.x, en.y, en.z, sD[en.x], sD[en.x + 1], k, lane, 32);
+        }
+      }
+      unsigned bigWarps = __ballot_sync(kFull, qcntS[lane] < 0);  // sign bit: that warp queued a big block
+      while (bigWarps) {
+        const int w2 = __ffs(bigWarps) - 1;
+        bigWarps &= bigWarps - 1;
+        const int n2 = qcntS[w2] & 0xffff;
+        const long long base2 = recBase + __shfl_sync(kFull, ex, w2);
+        for (int q = 0; q < n2; ++q) {
+          const int4 en = queueS[w2 * kQueue + q];
+          if ((en.x - en.y) + (en.z - en.x - 1) >= kBigBlock)
+            emit_block(recOut, p.recCap, base2 + en.w, sA, en.x, en.y, en.z, sD[en.x], sD[en.x + 1], k, tid, kThreads);
+        }
+      }
+    }
+    recBase += tot;
+  };
+
+  // -------- one site; CUR selects which half of the double buffers holds state k --------
+  auto site = [&](auto curTag, const int k) {
+    constexpr int CUR = decltype(curTag)::value;
+    constexpr int aC = CUR ? L::a1 : L::a0, aN = CUR ? L::a0 : L::a1;
+    constexpr int dC = CUR ? L::d1 : L::d0, dN = CUR ? L::d0 : L::d1;
+    constexpr int ycOff = L::ycol + CUR * L::WORDS;
     const int it = k - k0;
     const int stage = it % kStages;
     mbar_wait(&mbar[stage], (uint32_t)(it / kStages) & 1u);
     const uint32_t *col = smem + L::xcol + stage * L::STAGE;
-    const int aC = cur ? L::a1 : L::a0, aN = cur ? L::a0 : L::a1;
-    const int dC = cur ? L::d1 : L::d0, dN = cur ? L::d0 : L::d1;
-    uint32_t *yc = smem + L::ycol + (it & 1) * L::WORDS;
+    uint32_t *yc = smem + ycOff;
+    int32_t *wmaxC = wmaxS + CUR * L::WORDS;
+    if (WITH_D) {  // sentinels of state k (pbwtCore.c:414,507), written by the threads that read them below
+      if (tid == 0) sI[dC] = k + 1;
+      if (tid == ownerM) sI[dC + M] = k + 1;
+    }
 
     // ---------------- phase A: gather, ballots, warp-local scans ----------------
     uint32_t B[E];
-    int32_t hv[E];
     int32_t dn[E];
     uint32_t pb = 0;  // allele just before this warp's first position
     if (warp > 0) {
@@ -238,29 +324,40 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
         pb = (col[hp >> 5] >> (hp & 31)) & 1u;
       } else pb = col[wordBase - 1] >> 31;
     }
-    int zw = 0;            // zeros in this warp so far
-    int carry = 0;         // max d since the last run head seen by this warp (or over all of it)
+    int carry = 0;         // max d since the last run head, over completed words (uniform)
+    int lmax = 0;          // per-lane max of d over head-free words since then (reduced lazily)
     bool anyHead = false;  // has this warp seen a run head
     // the warp's first run head additionally needs the carry entering the warp (patched after S1)
     int patchLane = 0, pDn = 0, pIdx = 0, pZ = 0;
     uint32_t pY = 0;
-    uint32_t myY = 0;
+    int zw = 0;  // zeros in this warp so far
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      const int idx = laneOff + e * 32;
-      hv[e] = sI[aC + idx];
-      if (MODE == kGather) B[e] = __ballot_sync(kFull, (col[hv[e] >> 5] >> (hv[e] & 31)) & 1u);
-      else B[e] = col[wordBase + e];
-      if (e == 0 && warp == 0) pb = (~B[0]) & 1u;  // sorted position 0 is always a run head
-      const uint32_t H = B[e] ^ ((B[e] << 1) | pb);
-      pb = B[e] >> 31;
-      if (lane == e) myY = B[e];
+      const int h = sLane[aC + e * 32];
+      uint32_t Bw;
+      if (MODE == kGather) Bw = __ballot_sync(kFull, (col[h >> 5] >> (h & 31)) & 1u);
+      else Bw = col[wordBase + e];
+      B[e] = Bw;
+      if (e == 0 && warp == 0) pb = (~Bw) & 1u;  // sorted position 0 is always a run head
+      const uint32_t H = Bw ^ ((Bw << 1) | pb);
+      pb = Bw >> 31;
+      if (lane == 0) yc[wordBase + e] = Bw;
       if (WITH_D) {
-        const int dv = sI[dC + idx];
+        const int dv = sLane[dC + e * 32];
+        int wm = 0;
+        if (MATCH) {
+          wm = __reduce_max_sync(kFull, dv);
+          if (lane == 0) wmaxC[wordBase + e] = wm;
+        }
         if (H == 0u) {
           dn[e] = dv;
-          carry = max(carry, __reduce_max_sync(kFull, dv));
+          if (MATCH) carry = max(carry, wm);
+          else lmax = max(lmax, dv);
         } else {
+          if (!MATCH) {
+            carry = max(carry, __reduce_max_sync(kFull, lmax));
+            lmax = 0;
+          }
           int v = dv;  // inclusive max since the nearest head at or below this lane
 #pragma unroll
           for (int dl = 1; dl < 32; dl <<= 1) {
@@ -268,28 +365,24 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
             if (lane >= dl && ((H >> (lane - dl + 1)) & ((1u << dl) - 1u)) == 0u) v = max(v, t);
           }
           const int prev = __shfl_up_sync(kFull, v, 1);
-          const bool isHead = (H >> lane) & 1u;
-          const bool headBelow = (H & lanemask_lt(lane)) != 0u;
+          const bool isHead = H & laneBit;
+          const bool headBelow = (H & ltMask) != 0u;
           const int prevMax = lane == 0 ? carry : (headBelow ? prev : max(carry, prev));
           dn[e] = isHead ? max(dv, prevMax) : dv;
           if (!anyHead) {
             anyHead = true;
             patchLane = __ffs(H) - 1;
             pDn = dn[e];
-            pIdx = idx;
-            pZ = zw + __popc(~B[e] & lanemask_lt(lane));
-            pY = (B[e] >> lane) & 1u;
+            pIdx = laneOff + e * 32;
+            pZ = zw + __popc(~Bw & ltMask);
+            pY = Bw & laneBit;
           }
           carry = __shfl_sync(kFull, v, 31);
         }
       }
-      zw += __popc(~B[e]);
+      zw += __popc(~Bw);
     }
-    if (lane < E) {
-      const int base = (wordBase + lane) * 32;
-      const uint32_t vm = (M - base >= 32) ? kFull : (M > base ? ((1u << (M - base)) - 1u) : 0u);
-      yc[wordBase + lane] = myY & vm;
-    }
+    if (WITH_D && !MATCH) carry = max(carry, __reduce_max_sync(kFull, lmax));
     if (lane == 0) {
       wsumZ[warp] = zw;
       if (WITH_D) wsumR[warp] = (anyHead ? 0x80000000u : 0u) | (uint32_t)carry;
@@ -326,49 +419,62 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     // ---------------- phase C: stable partition scatter ----------------
     {
       int zacc = zIn;
-      const int onesBase = c + laneOff;  // position of a one = c + i - zeros before i
+      const int onesLane = c + laneOff;  // a one at position i goes to c + i - (zeros before i)
 #pragma unroll
       for (int e = 0; e < E; ++e) {
-        const int z = zacc + __popc(~B[e] & lanemask_lt(lane));
-        const int pos = ((B[e] >> lane) & 1u) ? onesBase + e * 32 - z : z;
-        sI[aN + pos] = hv[e];
-        if (WITH_D) sI[dN + pos] = pos == 0 ? k + 2 : dn[e];
-        zacc += __popc(~B[e]);
+        const uint32_t Bw = B[e];
+        const int z = zacc + __popc(~Bw & ltMask);
+        const int pos = (Bw & laneBit) ? onesLane + e * 32 - z : z;
+        sI[aN + pos] = sLane[aC + e * 32];  // re-read (base + immediate) instead of holding E registers
+        if (WITH_D) sI[dN + pos] = dn[e];
+        zacc += __popc(~Bw);
       }
-      if (WITH_D) {
-        if (anyHead && lane == patchLane && cIn > pDn) {  // same thread wrote this slot above
-          const int z = zIn + pZ;
-          const int pos = pY ? c + pIdx - z : z;
-          if (pos != 0) sI[dN + pos] = cIn;
-        }
-        if (tid == ownerM) sI[dN + M] = k + 2;  // after this thread's own pad write to slot M
+      if (WITH_D && anyHead && lane == patchLane && cIn > pDn) {  // same thread wrote this slot above
+        const int z = zIn + pZ;
+        sI[dN + (pY ? c + pIdx - z : z)] = cIn;
       }
     }
-    if (p.yOut && tid < wpc) p.yOut[(size_t)k * wpc + tid] = yc[tid];
+    if (p.yOut && tid < wpc) {
+      const int base = tid * 32;
+      const uint32_t vm = (M - base >= 32) ? kFull : (M > base ? ((1u << (M - base)) - 1u) : 0u);
+      p.yOut[(size_t)k * wpc + tid] = yc[tid] & vm;
+    }
     if (p.cOut && tid == 0) p.cOut[k] = c;
 
     // ---------------- matchMaximalWithin on state k ----------------
-    unsigned wordMask = 0;
+    int nq = 0;
     if (MATCH) {
-      const int wt = match_pass<E, false>(sI + aC, sI + dC, yc, M, k, true, warp, lane, wordMask, nullptr, 0, 0);
-      if (lane == 0) wsumC[warp] = wt;
+      bool hasBig;
+      const int wt = match_pass<E, false>(sI + aC, sI + dC, yc, wmaxC, M, k, true, warp, lane, queueS + warp * kQueue, nq,
+                                          hasBig, nullptr, 0, 0);
+      if (lane == 0) {
+        wsumC[warp] = wt;
+        qcntS[warp] = nq > kQueue ? 0 : (nq | (hasBig ? 0x80000000 : 0));
+      }
     }
-    __syncthreads();  // S2: scatter complete; match counts published
-    if (MATCH) {
-      const int cw = wsumC[lane];
-      int tot;
-      const int ex = warp_excl_scan(cw, lane, tot);
-      const int mine = __shfl_sync(kFull, ex, warp);
-      if (wordMask && recOut)
-        match_pass<E, true>(sI + aC, sI + dC, yc, M, k, true, warp, lane, wordMask, recOut, p.recCap, recBase + mine);
-      recBase += tot;
-    }
-    cur ^= 1;
+    __syncthreads();  // S2: scatter complete; match counts and queues published
+    if (MATCH) emit_phase(sI + aC, sI + dC, yc, wmaxC, k, true, nq);
+  };
+
+  int k = k0;
+  for (; k + 1 < k1; k += 2) {
+    site(std::integral_constant<int, 0>{}, k);
+    site(std::integral_constant<int, 1>{}, k + 1);
+  }
+  int cur = 0;
+  if (k < k1) {
+    site(std::integral_constant<int, 0>{}, k);
+    cur = 1;
   }
 
-  // ---------------- window end ----------------
+  // ---------------- window end: state k1 ----------------
   const int aC = cur ? L::a1 : L::a0;
   const int dC = cur ? L::d1 : L::d0;
+  if (WITH_D && tid == 0) {
+    sI[dC] = k1 + 1;
+    sI[dC + M] = k1 + 1;
+  }
+  __syncthreads();
   if (p.aEnd)
     for (int i = tid; i < M; i += kThreads) p.aEnd[(size_t)win * M + i] = sI[aC + i];
   if (WITH_D && p.dEnd)
@@ -376,25 +482,29 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
 
   if (MATCH && p.reportAtN && k1 == p.N) {  // k == N: nothing extends, every block is reported
     const uint32_t *yc = smem + L::ycol;    // alleles are not consulted when live == false
-    unsigned wordMask = 0;
-    const int wt = match_pass<E, false>(sI + aC, sI + dC, yc, M, p.N, false, warp, lane, wordMask, nullptr, 0, 0);
-    __syncthreads();  // previous readers of wsumC are done
-    if (lane == 0) wsumC[warp] = wt;
+    for (int w = warp; w < L::WORDS; w += 32) {  // word maxima of the final d
+      const int wm = __reduce_max_sync(kFull, sI[dC + w * 32 + lane]);
+      if (lane == 0) wmaxS[w] = wm;
+    }
     __syncthreads();
-    const int cw = wsumC[lane];
-    int tot;
-    const int ex = warp_excl_scan(cw, lane, tot);
-    const int mine = __shfl_sync(kFull, ex, warp);
-    if (wordMask && recOut)
-      match_pass<E, true>(sI + aC, sI + dC, yc, M, p.N, false, warp, lane, wordMask, recOut, p.recCap, recBase + mine);
-    recBase += tot;
+    int nq;
+    bool hasBig;
+    const int wt = match_pass<E, false>(sI + aC, sI + dC, yc, wmaxS, M, p.N, false, warp, lane, queueS + warp * kQueue, nq,
+                                        hasBig, nullptr, 0, 0);
+    if (lane == 0) {
+      wsumC[warp] = wt;
+      qcntS[warp] = nq > kQueue ? 0 : (nq | (hasBig ? 0x80000000 : 0));
+    }
+    __syncthreads();
+    emit_phase(sI + aC, sI + dC, yc, wmaxS, p.N, false, nq);
   }
   if (MATCH && p.recCount && tid == 0) p.recCount[win] = (unsigned long long)recBase;
 }
 
 template <int E, int MODE, bool WITH_D, bool MATCH>
 int launch_one(const SweepArgs &a, cudaStream_t stream) {
-  using L = SmemLayout<E, WITH_D>;
+  using L = SmemLayout<E, WITH_D, MATCH>;
+  static_assert(L::bytes <= 232448, "shared memory layout exceeds the 227 KB per-CTA limit");
   auto kern = sweep_smem_kernel<E, MODE, WITH_D, MATCH>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
   if (err != cudaSuccess) return (int)err;
