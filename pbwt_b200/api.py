@@ -123,12 +123,16 @@ class Result:
         """D2H. ``out`` may hold preallocated (e.g. pinned) numpy buffers keyed yz/a_end/d_end/matches."""
         out = out or {}
         has_d = bool(self.flags & (WANT_D | WANT_MAXWITHIN))
+        def buf(key, want, make):
+            if not want:
+                return None
+            return out[key] if key in out else make()
+
         bufs = {
-            "yz": (out.get("yz", np.zeros(max(self.nyz, 1), np.uint8)) if yz and (self.flags & WANT_YZ) else None),
-            "a_end": out.get("a_end", np.zeros(self.M, np.int32)) if a_end else None,
-            "d_end": (out.get("d_end", np.zeros(self.M + 1, np.int32)) if d_end and has_d else None),
-            "matches": (out.get("matches", np.zeros(max(self.nmatch, 1), MATCH_DTYPE))
-                        if matches and (self.flags & WANT_MAXWITHIN) else None),
+            "yz": buf("yz", yz and (self.flags & WANT_YZ), lambda: np.zeros(max(self.nyz, 1), np.uint8)),
+            "a_end": buf("a_end", a_end, lambda: np.zeros(self.M, np.int32)),
+            "d_end": buf("d_end", d_end and has_d, lambda: np.zeros(self.M + 1, np.int32)),
+            "matches": buf("matches", matches and (self.flags & WANT_MAXWITHIN), lambda: np.zeros(max(self.nmatch, 1), MATCH_DTYPE)),
         }
         self.eng._check(self.eng.lib.pbwtgpu_result_fetch(self.eng.ctx, self.handle, _ptr(bufs["yz"]), _ptr(bufs["a_end"]),
                                                           _ptr(bufs["d_end"]), _ptr(bufs["matches"])))
