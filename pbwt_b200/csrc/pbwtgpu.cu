@@ -11,6 +11,7 @@
 #include "query.cuh"
 #include "sweep.cuh"
 #include "synth.cuh"
+#include "windows.cuh"
 
 using namespace pbwtgpu;
 
@@ -177,23 +178,35 @@ void reset_timings(pbwtgpu_ctx *ctx) {
 }
 
 // ---- the sweep driver shared by build (gather mode) and stored-stream sweeps (sorted mode) ----
+//
+// Windowed execution (gather mode, M within the divergence kernel's limit, enough sites): the N sites are cut
+// into W windows, one per SM.  Pass 1 sweeps every window on its own from the panel's start order; a
+// Hillis-Steele scan of window combines (windows.cu) turns those into the exact (a, d) at every window
+// boundary; pass 2 sweeps all windows concurrently from their exact start states and produces the outputs.
 int run_sweep(pbwtgpu_ctx *ctx, const uint32_t *src, int wpc, int M, int N, SweepMode mode, const int32_t *aStartHost,
               unsigned flags, pbwtgpu_result *res) {
   const bool wantMatch = flags & PBWTGPU_WANT_MAXWITHIN;
   const bool wantD = wantMatch || (flags & PBWTGPU_WANT_D);
   const bool wantYz = (flags & PBWTGPU_WANT_YZ) && mode == kGather;
   if (M < 1 || N < 0) return fail(ctx, PBWTGPU_ERR_ARG, "bad panel shape M=%d N=%d", M, N);
+  if (N >= kPseudoLabelBase - 64) return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "N=%d too large", N);
   if (M > sweep_smem_max_m(wantD))
     return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "M=%d exceeds the shared-memory sweep limit %d", M, sweep_smem_max_m(wantD));
   Temps tmp(ctx);
   res->M = M;
   res->N = N;
 
-  int32_t *aStart = nullptr;
-  if (aStartHost) {
-    if (int rc = tmp.get(&aStart, (size_t)M)) return rc;
-    CUDA_TRY(ctx, cudaMemcpyAsync(aStart, aStartHost, sizeof(int32_t) * M, cudaMemcpyHostToDevice, ctx->stream));
+  // ---- window plan ----
+  int W = 1;
+  if (mode == kGather && M >= 2 && M <= sweep_smem_max_m(true)) {
+    const long long want = ctx->optWindows > 0 ? ctx->optWindows : ctx->smCount;
+    const int minSites = ctx->optWindows > 0 ? 1 : 256;  // below this a window does not repay its two extra passes
+    W = (int)std::max<long long>(1, std::min<long long>(want, N / minSites));
   }
+  int spw = N > 0 ? (N + W - 1) / W : 1;
+  W = N > 0 ? (N + spw - 1) / spw : 1;
+  const int nodes = W - 1;
+
   if (int rc = result_alloc(ctx, res, &res->aEnd, (size_t)M)) return rc;
   if (wantD)
     if (int rc = result_alloc(ctx, res, &res->dEnd, (size_t)M + 1)) return rc;
@@ -201,49 +214,151 @@ int run_sweep(pbwtgpu_ctx *ctx, const uint32_t *src, int wpc, int M, int N, Swee
   if (wantYz && N > 0)
     if (int rc = tmp.get(&yOut, (size_t)N * wpc)) return rc;
 
-  unsigned long long *recCount = nullptr;
-  long long recCap = 0;
-  if (wantMatch) {
-    if (int rc = tmp.get(&recCount, 1)) return rc;
-    recCap = ctx->optMatchCap > 0 ? ctx->optMatchCap : std::min<long long>(std::max<long long>(1 << 20, 4096LL * M), 1LL << 28);
-    if (int rc = result_alloc(ctx, res, &res->rec, (size_t)recCap)) return rc;
+  // ---- start states: slot 0 = the panel's start order, slot w = state entering window w ----
+  int32_t *ord[2] = {nullptr, nullptr}, *dv[2] = {nullptr, nullptr};
+  if (int rc = tmp.get(&ord[0], (size_t)W * M)) return rc;
+  {
+    std::vector<int32_t> ident;
+    const int32_t *h = aStartHost;
+    if (!h) {
+      ident.resize(M);
+      for (int i = 0; i < M; ++i) ident[i] = i;
+      h = ident.data();
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ord[0], h, sizeof(int32_t) * M, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // ident goes out of scope
+  }
+  int cur = 0;
+  if (nodes > 0) {
+    int bits = 1;
+    while ((1 << bits) < M) ++bits;
+    int32_t *g[2], *gfd[2];
+    uint32_t *keys = nullptr;
+    if (int rc = tmp.get(&ord[1], (size_t)W * M)) return rc;
+    for (int b = 0; b < 2; ++b) {
+      if (int rc = tmp.get(&dv[b], (size_t)W * (M + 1))) return rc;
+      if (int rc = tmp.get(&g[b], (size_t)W * M)) return rc;
+      if (int rc = tmp.get(&gfd[b], (size_t)W * M)) return rc;
+      CUDA_TRY(ctx, cudaMemsetAsync(dv[b], 0, sizeof(int32_t) * (M + 1), ctx->stream));  // slot 0: fresh cursor
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ord[1], ord[0], sizeof(int32_t) * M, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (int rc = tmp.get(&keys, (size_t)nodes * bits * wpc)) return rc;
+    const size_t oA = M, oD = (size_t)M + 1;  // slot strides
+
+    // pass 1: every window but the last, on its own, from the start order
+    SweepArgs a1{};
+    a1.src = src; a1.wpc = wpc; a1.M = M; a1.N = N; a1.sitesPerWindow = spw; a1.nWindows = nodes;
+    a1.aStart = ord[0]; a1.aStartShared = 1;
+    a1.aEnd = ord[0] + oA; a1.dEnd = dv[0] + oD;
+    {
+      ScopedTimer t(ctx, PBWTGPU_K_SWEEP);
+      CUDA_TRY(ctx, launch_sweep_smem(a1, kGather, true, false, ctx->stream));
+      ctx->launches[PBWTGPU_K_SWEEP] += 1;
+    }
+    {
+      ScopedTimer t(ctx, PBWTGPU_K_AUX);
+      CUDA_TRY(ctx, launch_make_groups(ord[0] + oA, dv[0] + oD, nullptr, nullptr, g[0] + oA, gfd[0] + oA, M, nodes, ctx->stream));
+      ctx->launches[PBWTGPU_K_AUX] += 1;
+    }
+    // inclusive scan of window combines: node w (slot w+1) becomes the state at boundary w+1
+    for (int stride = 1; stride < nodes; stride *= 2) {
+      const int nxt = cur ^ 1, cnt = nodes - stride;
+      const size_t s1 = (size_t)(1 + stride);  // first slot that changes this round
+      {
+        ScopedTimer t(ctx, PBWTGPU_K_AUX);
+        CUDA_TRY(ctx, launch_key_bits(g[cur] + s1 * oA, M, cnt, bits, wpc, keys, ctx->stream));
+        ctx->launches[PBWTGPU_K_AUX] += 1;
+      }
+      SweepArgs c{};
+      c.src = keys; c.wpc = wpc; c.M = M; c.N = N; c.nWindows = cnt;
+      c.perWindowSites = bits; c.srcWindowStride = (long long)bits * wpc; c.kLabelBase = kPseudoLabelBase;
+      c.aStart = ord[cur] + oA; c.dStart = dv[cur] + oD;  // earlier part: node i (slot i+1)
+      c.aEnd = ord[nxt] + s1 * oA; c.dEnd = dv[nxt] + s1 * oD;
+      {
+        ScopedTimer t(ctx, PBWTGPU_K_SWEEP);
+        CUDA_TRY(ctx, launch_sweep_smem(c, kGather, true, false, ctx->stream));
+        ctx->launches[PBWTGPU_K_SWEEP] += 1;
+      }
+      {
+        ScopedTimer t(ctx, PBWTGPU_K_AUX);
+        CUDA_TRY(ctx, launch_make_groups(ord[nxt] + s1 * oA, dv[nxt] + s1 * oD, g[cur] + s1 * oA, gfd[cur] + s1 * oA,
+                                         g[nxt] + s1 * oA, gfd[nxt] + s1 * oA, M, cnt, ctx->stream));
+        ctx->launches[PBWTGPU_K_AUX] += 1;
+      }
+      // nodes below the stride are already final
+      CUDA_TRY(ctx, cudaMemcpyAsync(ord[nxt] + oA, ord[cur] + oA, sizeof(int32_t) * oA * stride, cudaMemcpyDeviceToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(dv[nxt] + oD, dv[cur] + oD, sizeof(int32_t) * oD * stride, cudaMemcpyDeviceToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(g[nxt] + oA, g[cur] + oA, sizeof(int32_t) * oA * stride, cudaMemcpyDeviceToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(gfd[nxt] + oA, gfd[cur] + oA, sizeof(int32_t) * oA * stride, cudaMemcpyDeviceToDevice, ctx->stream));
+      cur = nxt;
+    }
   }
 
+  // ---- pass 2 (or the only pass): all windows from their exact start states ----
+  unsigned long long *recCount = nullptr;
+  int *chunkCounter = nullptr, *chunkTab = nullptr;
+  pbwtgpu_match *pool = nullptr;
+  long long recCap = 0;
+  int poolChunks = 0;
+  if (wantMatch) {
+    if (int rc = tmp.get(&recCount, (size_t)W)) return rc;
+    if (int rc = tmp.get(&chunkCounter, 1)) return rc;
+    recCap = ctx->optMatchCap > 0 ? ctx->optMatchCap : std::min<long long>(std::max<long long>(1 << 20, 4096LL * M), 1LL << 28);
+  }
   SweepArgs a{};
-  a.src = src;
-  a.wpc = wpc;
-  a.M = M;
-  a.N = N;
-  a.sitesPerWindow = N > 0 ? N : 1;
-  a.nWindows = 1;
-  a.aStart = aStart;
-  a.dStart = nullptr;
-  a.aEnd = res->aEnd;
-  a.dEnd = res->dEnd;
+  a.src = src; a.wpc = wpc; a.M = M; a.N = N;
+  a.sitesPerWindow = spw; a.nWindows = W;
+  a.aStart = ord[cur];
+  a.dStart = nodes > 0 ? dv[cur] : nullptr;
+  a.aEnd = res->aEnd; a.dEnd = res->dEnd; a.endOnlyLast = 1;
   a.yOut = yOut;
-  a.cOut = nullptr;
-  a.rec = res->rec;
-  a.recCap = recCap;
-  a.recCount = recCount;
+  a.recCount = recCount; a.chunkCounter = chunkCounter;
   a.reportAtN = 1;
+  std::vector<unsigned long long> counts(W, 0);
   for (int attempt = 0; attempt < 2; ++attempt) {
+    if (wantMatch) {
+      poolChunks = (int)((recCap + kRecChunk - 1) >> kRecChunkLog) + W;
+      if (int rc = tmp.get(&pool, (size_t)poolChunks << kRecChunkLog)) return rc;
+      if (int rc = tmp.get(&chunkTab, (size_t)W * poolChunks)) return rc;
+      CUDA_TRY(ctx, cudaMemsetAsync(chunkCounter, 0, sizeof(int), ctx->stream));
+      a.recPool = pool; a.poolChunks = poolChunks; a.chunkTab = chunkTab;
+    }
     {
       ScopedTimer t(ctx, PBWTGPU_K_SWEEP);
       CUDA_TRY(ctx, launch_sweep_smem(a, mode, wantD, wantMatch, ctx->stream));
       ctx->launches[PBWTGPU_K_SWEEP] += 1;
     }
     if (!wantMatch) break;
-    unsigned long long n = 0;
-    CUDA_TRY(ctx, cudaMemcpyAsync(&n, recCount, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+    int used = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(counts.data(), recCount, sizeof(unsigned long long) * W, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(&used, chunkCounter, sizeof used, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    res->nrec = (int64_t)n;
-    if ((long long)n <= recCap) break;
-    if (attempt == 1) return fail(ctx, PBWTGPU_ERR_CUDA, "match buffer overflow persisted");
-    // the buffer was too small: records were counted but not all stored -- size exactly and rerun
-    recCap = (long long)n;
-    if (int rc = result_alloc(ctx, res, &res->rec, (size_t)recCap)) return rc;
-    a.rec = res->rec;
-    a.recCap = recCap;
+    if (used <= poolChunks) break;
+    if (attempt == 1) return fail(ctx, PBWTGPU_ERR_CUDA, "match record pool overflow persisted");
+    long long total = 0;  // the pool was too small: every window's count is known now, size it exactly and rerun
+    for (auto cnt : counts) total += (long long)cnt;
+    recCap = total;
+  }
+  if (wantMatch) {
+    std::vector<long long> offs(W, 0);
+    long long total = 0;
+    int maxChunks = 0;
+    for (int w = 0; w < W; ++w) {
+      offs[w] = total;
+      total += (long long)counts[w];
+      maxChunks = std::max<int>(maxChunks, (int)((counts[w] + kRecChunk - 1) >> kRecChunkLog));
+    }
+    res->nrec = total;
+    if (int rc = result_alloc(ctx, res, &res->rec, (size_t)std::max<long long>(total, 1))) return rc;
+    long long *offsDev = nullptr;
+    if (int rc = tmp.get(&offsDev, (size_t)W)) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(offsDev, offs.data(), sizeof(long long) * W, cudaMemcpyHostToDevice, ctx->stream));
+    {
+      ScopedTimer t(ctx, PBWTGPU_K_AUX);
+      CUDA_TRY(ctx, launch_gather_records(pool, chunkTab, poolChunks, offsDev, recCount, W, maxChunks, res->rec, ctx->stream));
+      ctx->launches[PBWTGPU_K_AUX] += maxChunks > 0;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // offs is a host temporary
   }
 
   if (wantYz) {

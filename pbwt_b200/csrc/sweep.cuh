@@ -4,25 +4,41 @@
 
 namespace pbwtgpu {
 
-// One launch sweeps W windows of consecutive sites concurrently (one CTA per window). Window w
-// covers sites [w*sitesPerWindow, min(N,(w+1)*sitesPerWindow)) and starts from the exact state
-// (a,d) entering its first site.
+constexpr int kRecChunkLog = 13;  // match records are allocated to windows in chunks of 8192 (128 KiB)
+constexpr int kRecChunk = 1 << kRecChunkLog;
+
+// One launch sweeps W windows concurrently (one CTA per window), each starting from the exact
+// state (a,d) entering its first site.
+//   regular mode (perWindowSites == 0): window w covers sites [w*sitesPerWindow, min(N,(w+1)*sitesPerWindow))
+//     of the shared column array src; site labels are the column indices.
+//   per-window mode (perWindowSites > 0): window w sweeps columns [0, perWindowSites) of its own block
+//     src + w*srcWindowStride; column j carries site label kLabelBase + j.  Used by the window-prefix
+//     combine (windows.cu), whose "sites" are the key bits of a later window's tie groups.
 struct SweepArgs {
   const uint32_t *src;  // gather mode: panel bit columns x_k; sorted mode: sorted columns y_k
   int wpc;              // words per column
   int M, N;
   int sitesPerWindow;
   int nWindows;
-  const int32_t *aStart;  // [W][M]; NULL = identity (only valid for W == 1)
-  const int32_t *dStart;  // [W][M+1]; NULL = fresh cursor: zeros, ends k0+1 (pbwtCore.c:413-414)
-  int32_t *aEnd;          // [W][M] state after the window's last site, or NULL
-  int32_t *dEnd;          // [W][M+1] or NULL
+  int perWindowSites;
+  long long srcWindowStride;  // words
+  int kLabelBase;
+  const int32_t *aStart;  // [W][M] ([M] if aStartShared); NULL = identity
+  int aStartShared;
+  const int32_t *dStart;  // [W][M+1] interior values (sentinels are implied); NULL = fresh cursor (zeros)
+  int32_t *aEnd;          // [W][M] state after the window's last site ([M], last window only, if endOnlyLast)
+  int32_t *dEnd;          // [W][M+1]
+  int endOnlyLast;
   uint32_t *yOut;         // [N][wpc] sorted columns y_k (input to the pack3 encoder), or NULL
   int32_t *cOut;          // [N] zero counts c_k, or NULL
-  pbwtgpu_match *rec;     // match records; window w writes rec + w*recCap
-  long long recCap;       // per-window capacity (records beyond it are counted, not stored)
+  // match records: a pool of poolChunks chunks of kRecChunk records handed out through chunkCounter;
+  // chunkTab[w*poolChunks + c] = pool chunk holding records [c*kRecChunk, (c+1)*kRecChunk) of window w
+  pbwtgpu_match *recPool;  // NULL = count only
+  int poolChunks;
+  int *chunkCounter;
+  int *chunkTab;
   unsigned long long *recCount;  // [W] records produced by each window
-  int reportAtN;          // the window that ends at N also reports the k == N blocks
+  int reportAtN;                 // the window that ends at N also reports the k == N blocks
 };
 
 enum SweepMode { kGather = 0, kSorted = 1 };

@@ -36,6 +36,7 @@ constexpr int kThreads = 1024;
 constexpr int kStages = 4;
 constexpr int kQueue = 8;       // reporter entries kept per warp between the count and emit phases
 constexpr int kBigBlock = 128;  // records; larger blocks are emitted by the whole CTA
+constexpr int kTabMirror = 64;  // newest chunk ids of this window mirrored in shared memory
 
 template <int E, bool WITH_D, bool MATCH>
 struct SmemLayout {  // offsets in 32-bit words; every array start is 16-byte aligned
@@ -53,7 +54,8 @@ struct SmemLayout {  // offsets in 32-bit words; every array start is 16-byte al
   static constexpr int wmax = mbar + 2 * kStages;
   static constexpr int queue = wmax + (MATCH ? 2 * WORDS : 0);  // wmax is double-buffered like ycol
   static constexpr int qcnt = queue + (MATCH ? 32 * kQueue * 4 : 0);
-  static constexpr int totalWords = qcnt + (MATCH ? 32 : 0);
+  static constexpr int ctab = qcnt + (MATCH ? 32 : 0);  // mirror of the newest kTabMirror chunk ids
+  static constexpr int totalWords = ctab + (MATCH ? kTabMirror : 0);
   static constexpr size_t bytes = (size_t)totalWords * 4;
   static constexpr int padIndex = 32 * WORDS;  // "haplotype" whose allele is 1 at every site
 };
@@ -124,16 +126,29 @@ __device__ __forceinline__ int search_down(const int32_t *sD, const int32_t *wma
   return m ? min((ws << 5) + __ffs(m) - 1, M) : M;
 }
 
+// Where a window's records go: chunks of kRecChunk records drawn from a global pool.
+struct RecSink {
+  int4 *pool;           // NULL = count only
+  const int *tab;       // this window's chunk table (global)
+  const int *mirror;    // shared-memory mirror of the newest kTabMirror entries
+  int nChunks;          // chunks allocated so far (uniform)
+  __device__ __forceinline__ void put(long long o, int4 rec) const {
+    const int c = (int)(o >> kRecChunkLog);
+    const int id = (nChunks - c <= kTabMirror) ? mirror[c & (kTabMirror - 1)] : __ldcg(tab + c);
+    if (id >= 0) pool[((long long)id << kRecChunkLog) + (o & (kRecChunk - 1))] = rec;
+  }
+};
+
 // write the records of reporter i: upward block [lo, i) with start di, then downward block (i, hi) with
 // start dn1 (callback order, pbwtMatch.c:133-134); record t of the block is written by "lane" t0 + t*step
-__device__ __forceinline__ void emit_block(pbwtgpu_match *out, long long cap, long long o, const int32_t *sA, int i,
-                                           int lo, int hi, int di, int dn1, int k, int t0, int step) {
+__device__ __forceinline__ void emit_block(const RecSink &out, long long o, const int32_t *sA, int i, int lo, int hi,
+                                           int di, int dn1, int k, int t0, int step) {
   const int cnt = (i - lo) + (hi - i - 1);
   const int ai = sA[i];
   const int nUp = i - lo;
   for (int t = t0; t < cnt; t += step) {
     const int jj = t < nUp ? lo + t : t + lo + 1;  // skips i itself
-    if (o + t < cap) reinterpret_cast<int4 *>(out)[o + t] = make_int4(ai, sA[jj], t < nUp ? di : dn1, k);
+    out.put(o + t, make_int4(ai, sA[jj], t < nUp ? di : dn1, k));
   }
 }
 
@@ -148,7 +163,7 @@ __device__ __forceinline__ void emit_block(pbwtgpu_match *out, long long cap, lo
 template <int E, bool EMIT>
 __device__ __forceinline__ int match_pass(const int32_t *sA, const int32_t *sD, const uint32_t *yc,
                                           const int32_t *wmax, int M, int k, bool live, int warp, int lane, int4 *queue,
-                                          int &nq, bool &hasBig, pbwtgpu_match *out, long long cap, long long off) {
+                                          int &nq, bool &hasBig, const RecSink &out, long long off) {
   int warpTotal = 0;
   nq = 0;
   hasBig = false;
@@ -195,7 +210,7 @@ __device__ __forceinline__ int match_pass(const int32_t *sA, const int32_t *sD, 
       const int cnt = (i - lo) + (hi - i - 1);
       if (!cnt) continue;
       if (EMIT) {
-        emit_block(out, cap, off + warpTotal, sA, i, lo, hi, di, dn1, k, lane, 32);
+        emit_block(out, off + warpTotal, sA, i, lo, hi, di, dn1, k, lane, 32);
       } else {
         if (nq < kQueue && lane == 0) queue[nq] = make_int4(i, lo, hi, warpTotal);
         ++nq;
@@ -223,8 +238,20 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = p.M, wpc = p.wpc;
   const int win = blockIdx.x;
-  const int k0 = win * p.sitesPerWindow;
-  const int k1 = min(p.N, k0 + p.sitesPerWindow);
+  // site labels [k0, k1); column of label k is k + colShift of this window's source block
+  int k0, k1, colShift;
+  const uint32_t *src;
+  if (p.perWindowSites) {
+    k0 = p.kLabelBase;
+    k1 = k0 + p.perWindowSites;
+    colShift = -k0;
+    src = p.src + (size_t)win * p.srcWindowStride;
+  } else {
+    k0 = win * p.sitesPerWindow;
+    k1 = min(p.N, k0 + p.sitesPerWindow);
+    colShift = 0;
+    src = p.src;
+  }
   const uint32_t colBytes = (uint32_t)wpc * 4u;
   const int wordBase = warp * E;
   const int laneOff = wordBase * 32 + lane;  // position of (word 0 of this warp, this lane)
@@ -235,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
 
   // ---- window start state (pbwtNakedCursorCreate, pbwtCore.c:402-418) ----
   for (int i = tid; i < L::MP; i += kThreads)
-    sI[L::a0 + i] = i < M ? (p.aStart ? p.aStart[(size_t)win * M + i] : i) : L::padIndex;
+    sI[L::a0 + i] = i < M ? (p.aStart ? p.aStart[(p.aStartShared ? 0 : (size_t)win * M) + i] : i) : L::padIndex;
   if (WITH_D)
     for (int i = tid; i < L::MP + 4; i += kThreads) {
       int v = 0;
@@ -254,11 +281,16 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     for (int s = 0; s < kStages; ++s)
       if (k0 + s < k1) {
         mbar_expect_tx(&mbar[s], colBytes);
-        tma_load_1d(smem + L::xcol + s * L::STAGE, p.src + (size_t)(k0 + s) * wpc, colBytes, &mbar[s]);
+        tma_load_1d(smem + L::xcol + s * L::STAGE, src + (size_t)(k0 + s + colShift) * wpc, colBytes, &mbar[s]);
       }
   }
 
-  pbwtgpu_match *recOut = MATCH && p.rec ? p.rec + (size_t)win * p.recCap : nullptr;
+  int32_t *const ctabS = sI + L::ctab;
+  RecSink sink;
+  sink.pool = MATCH ? reinterpret_cast<int4 *>(p.recPool) : nullptr;
+  sink.tab = MATCH && p.chunkTab ? p.chunkTab + (size_t)win * p.poolChunks : nullptr;
+  sink.mirror = ctabS;
+  sink.nChunks = 0;
   long long recBase = 0;  // records produced so far by this window (uniform)
 
   // -------- the emit phase shared by live sites and the final k == N report --------
@@ -267,18 +299,29 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     const int cw = wsumC[lane];
     int tot;
     const int ex = warp_excl_scan(cw, lane, tot);
-    if (recOut && tot) {
+    if (sink.pool && tot) {
+      const int need = (int)((recBase + tot + kRecChunk - 1) >> kRecChunkLog);
+      if (need > sink.nChunks) {  // uniform: draw more chunks from the pool
+        if (tid == 0)
+          for (int c2 = sink.nChunks; c2 < need; ++c2) {
+            int id = atomicAdd(p.chunkCounter, 1);
+            if (id >= p.poolChunks) id = -1;  // pool exhausted: records are dropped, the host reruns larger
+            p.chunkTab[(size_t)win * p.poolChunks + c2] = id;
+            ctabS[c2 & (kTabMirror - 1)] = id;
+          }
+        sink.nChunks = need;
+        __syncthreads();
+      }
       const long long mine = recBase + __shfl_sync(kFull, ex, warp);
       if (nq > kQueue) {  // queue overflow: this warp redoes its words and writes everything itself
         int nq2;
         bool hb;
-        match_pass<E, true>(sA, sD, yc, wm, M, k, live, warp, lane, queueS + warp * kQueue, nq2, hb, recOut, p.recCap,
-                            mine);
+        match_pass<E, true>(sA, sD, yc, wm, M, k, live, warp, lane, queueS + warp * kQueue, nq2, hb, sink, mine);
       } else {
         for (int q = 0; q < nq; ++q) {  // own small blocks
           const int4 en = queueS[warp * kQueue + q];
           if ((en.x - en.y) + (en.z - en.x - 1) < kBigBlock)
-            emit_block(recOut, p.recCap, mine + en.w, sA, en.x, en.y, en.z, sD[en.x], sD[en.x + 1], k, lane, 32);
+            emit_block(sink, mine + en.w, sA, en.x, en.y, en.z, sD[en.x], sD[en.x + 1], k, lane, 32);
         }
       }
       unsigned bigWarps = __ballot_sync(kFull, qcntS[lane] < 0);  // sign bit: that warp queued a big block
@@ -290,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
         for (int q = 0; q < n2; ++q) {
           const int4 en = queueS[w2 * kQueue + q];
           if ((en.x - en.y) + (en.z - en.x - 1) >= kBigBlock)
-            emit_block(recOut, p.recCap, base2 + en.w, sA, en.x, en.y, en.z, sD[en.x], sD[en.x + 1], k, tid, kThreads);
+            emit_block(sink, base2 + en.w, sA, en.x, en.y, en.z, sD[en.x], sD[en.x + 1], k, tid, kThreads);
         }
       }
     }
@@ -392,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     if (tid == 0 && k + kStages < k1) {  // refill the column slot just consumed
       fence_proxy_async();
       mbar_expect_tx(&mbar[stage], colBytes);
-      tma_load_1d(smem + L::xcol + stage * L::STAGE, p.src + (size_t)(k + kStages) * wpc, colBytes, &mbar[stage]);
+      tma_load_1d(smem + L::xcol + stage * L::STAGE, src + (size_t)(k + kStages + colShift) * wpc, colBytes, &mbar[stage]);
     }
 
     // ---------------- cross-warp prefixes (each warp redundantly) ----------------
@@ -437,16 +480,16 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     if (p.yOut && tid < wpc) {
       const int base = tid * 32;
       const uint32_t vm = (M - base >= 32) ? kFull : (M > base ? ((1u << (M - base)) - 1u) : 0u);
-      p.yOut[(size_t)k * wpc + tid] = yc[tid] & vm;
+      p.yOut[(size_t)(k + colShift) * wpc + tid] = yc[tid] & vm;
     }
-    if (p.cOut && tid == 0) p.cOut[k] = c;
+    if (p.cOut && tid == 0) p.cOut[k + colShift] = c;
 
     // ---------------- matchMaximalWithin on state k ----------------
     int nq = 0;
     if (MATCH) {
       bool hasBig;
       const int wt = match_pass<E, false>(sI + aC, sI + dC, yc, wmaxC, M, k, true, warp, lane, queueS + warp * kQueue, nq,
-                                          hasBig, nullptr, 0, 0);
+                                          hasBig, sink, 0);
       if (lane == 0) {
         wsumC[warp] = wt;
         qcntS[warp] = nq > kQueue ? 0 : (nq | (hasBig ? 0x80000000 : 0));
@@ -475,12 +518,14 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     sI[dC + M] = k1 + 1;
   }
   __syncthreads();
-  if (p.aEnd)
-    for (int i = tid; i < M; i += kThreads) p.aEnd[(size_t)win * M + i] = sI[aC + i];
-  if (WITH_D && p.dEnd)
-    for (int i = tid; i <= M; i += kThreads) p.dEnd[(size_t)win * (M + 1) + i] = sI[dC + i];
+  const bool writeEnd = !p.endOnlyLast || k1 == p.N;
+  const size_t endSlot = p.endOnlyLast ? 0 : (size_t)win;
+  if (p.aEnd && writeEnd)
+    for (int i = tid; i < M; i += kThreads) p.aEnd[endSlot * M + i] = sI[aC + i];
+  if (WITH_D && p.dEnd && writeEnd)
+    for (int i = tid; i <= M; i += kThreads) p.dEnd[endSlot * (M + 1) + i] = sI[dC + i];
 
-  if (MATCH && p.reportAtN && k1 == p.N) {  // k == N: nothing extends, every block is reported
+  if (MATCH && p.reportAtN && !p.perWindowSites && k1 == p.N) {  // k == N: nothing extends, every block is reported
     const uint32_t *yc = smem + L::ycol;    // alleles are not consulted when live == false
     for (int w = warp; w < L::WORDS; w += 32) {  // word maxima of the final d
       const int wm = __reduce_max_sync(kFull, sI[dC + w * 32 + lane]);
@@ -490,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     int nq;
     bool hasBig;
     const int wt = match_pass<E, false>(sI + aC, sI + dC, yc, wmaxS, M, p.N, false, warp, lane, queueS + warp * kQueue, nq,
-                                        hasBig, nullptr, 0, 0);
+                                        hasBig, sink, 0);
     if (lane == 0) {
       wsumC[warp] = wt;
       qcntS[warp] = nq > kQueue ? 0 : (nq | (hasBig ? 0x80000000 : 0));

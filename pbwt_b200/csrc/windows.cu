@@ -1,0 +1,132 @@
+// windows.cu -- exact (a, d) at the start of every site window, so that windows can be swept
+// concurrently on different SMs (the site recurrence a_k -> a_{k+1} is otherwise strictly sequential).
+//
+// Idea.  The order at a window boundary is the stable sort of the order at the previous boundary by the
+// window's own key (its alleles, most recent site most significant).  A window swept on its own from the
+// panel's start order yields that key's rank structure: its final order, and its final divergence array
+// whose zero entries mark haplotypes the window cannot tell apart ("tie groups").  Two adjacent windows
+// I (earlier), J (later) combine associatively:
+//     order(I+J)      = order(I) stably re-sorted by J's tie-group index,
+//     divergence(I+J) = J's boundary divergence between different J-groups, and inside one J-group the
+//                       maximum of I's divergence over the I-positions in between.
+// That is exactly a PBWT sweep of order(I), divergence(I) over pseudo-sites made of the bits of J's group
+// index (least significant first): the AD update rule carries the range maxima, and every pair separated by
+// a pseudo-site ends up with a label >= kPseudoLabelBase, which marks it for replacement by J's boundary
+// divergence.  So the combine reuses the sweep kernel, and an inclusive Hillis-Steele scan over the windows
+// (log2 W rounds, all windows in parallel) yields the exact state at every boundary.
+#include "windows.cuh"
+
+namespace pbwtgpu {
+namespace {
+
+__global__ void __launch_bounds__(1024) make_groups_kernel(const int32_t *ordAll, int32_t *dvAll, const int32_t *gJAll,
+                                                           const int32_t *gfdJAll, int32_t *gAll, int32_t *gfdAll, int M) {
+  __shared__ int warpSums[32];
+  __shared__ int carryS;
+  const int node = blockIdx.x;
+  const int32_t *ord = ordAll + (size_t)node * M;
+  int32_t *dv = dvAll + (size_t)node * (M + 1);
+  const int32_t *gJ = gJAll ? gJAll + (size_t)node * M : nullptr;
+  const int32_t *gfdJ = gfdJAll ? gfdJAll + (size_t)node * M : nullptr;
+  int32_t *g = gAll + (size_t)node * M;
+  int32_t *gfd = gfdAll + (size_t)node * M;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carryS = 0;
+  __syncthreads();
+  for (int base = 0; base < M; base += 1024) {
+    const int i = base + tid;
+    int h = 0, d = 0, flag = 0;
+    if (i < M) {
+      h = ord[i];
+      d = i == 0 ? 0 : dv[i];
+      if (d >= kPseudoLabelBase) {  // separated by a pseudo-site: different groups of the later window
+        d = gfdJ[gJ[h]];
+        dv[i] = d;
+      }
+      flag = i == 0 || d != 0;
+    }
+    int x = flag;
+#pragma unroll
+    for (int dl = 1; dl < 32; dl <<= 1) {
+      const int t = __shfl_up_sync(kFull, x, dl);
+      if (lane >= dl) x += t;
+    }
+    if (lane == 31) warpSums[warp] = x;
+    __syncthreads();
+    int wv = warpSums[lane], wx = wv;
+#pragma unroll
+    for (int dl = 1; dl < 32; dl <<= 1) {
+      const int t = __shfl_up_sync(kFull, wx, dl);
+      if (lane >= dl) wx += t;
+    }
+    const int warpOff = __shfl_sync(kFull, wx - wv, warp);
+    const int blockTotal = __shfl_sync(kFull, wx, 31);
+    const int carry = carryS;
+    if (i < M) {
+      const int rank = carry + warpOff + x - 1;  // inclusive count of group heads, minus one
+      g[h] = rank;
+      if (flag) gfd[rank] = d;
+    }
+    __syncthreads();
+    if (tid == 0) carryS = carry + blockTotal;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) key_bits_kernel(const int32_t *gAll, int M, int bits, int wpc, uint32_t *out) {
+  const int lane = threadIdx.x & 31;
+  const int nWords = (M + 31) / 32;
+  const int node = blockIdx.y;
+  const int wd = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (wd >= nWords) return;
+  const int h = wd * 32 + lane;
+  const int v = h < M ? gAll[(size_t)node * M + h] : 0;
+  for (int b = 0; b < bits; ++b) {
+    const uint32_t w = __ballot_sync(kFull, (v >> b) & 1);
+    if (lane == 0) out[((size_t)node * bits + b) * wpc + wd] = w;
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_records_kernel(const int4 *pool, const int *chunkTab, int poolChunks,
+                                                             const long long *winOffset,
+                                                             const unsigned long long *winCount, int4 *out) {
+  const int w = blockIdx.y, c = blockIdx.x;
+  const long long cnt = (long long)winCount[w];
+  const long long first = (long long)c << kRecChunkLog;
+  if (first >= cnt) return;
+  const int id = chunkTab[(size_t)w * poolChunks + c];
+  if (id < 0) return;
+  const int n = (int)min((long long)kRecChunk, cnt - first);
+  const int4 *srcp = pool + ((long long)id << kRecChunkLog);
+  int4 *dst = out + winOffset[w] + first;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) dst[t] = srcp[t];
+}
+
+}  // namespace
+
+int launch_make_groups(const int32_t *ord, int32_t *dv, const int32_t *gJ, const int32_t *gfdJ, int32_t *g, int32_t *gfd,
+                       int M, int nodes, cudaStream_t stream) {
+  if (nodes > 0) make_groups_kernel<<<nodes, 1024, 0, stream>>>(ord, dv, gJ, gfdJ, g, gfd, M);
+  return (int)cudaGetLastError();
+}
+
+int launch_key_bits(const int32_t *g, int M, int nodes, int bits, int wpc, uint32_t *out, cudaStream_t stream) {
+  if (nodes > 0) {
+    dim3 grid(((M + 31) / 32 + 7) / 8, nodes);
+    key_bits_kernel<<<grid, 256, 0, stream>>>(g, M, bits, wpc, out);
+  }
+  return (int)cudaGetLastError();
+}
+
+int launch_gather_records(const pbwtgpu_match *pool, const int *chunkTab, int poolChunks, const long long *winOffset,
+                          const unsigned long long *winCount, int nWindows, int maxChunksPerWindow, pbwtgpu_match *out,
+                          cudaStream_t stream) {
+  if (nWindows > 0 && maxChunksPerWindow > 0) {
+    dim3 grid(maxChunksPerWindow, nWindows);
+    gather_records_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const int4 *>(pool), chunkTab, poolChunks, winOffset,
+                                                    winCount, reinterpret_cast<int4 *>(out));
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace pbwtgpu

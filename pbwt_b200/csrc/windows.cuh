@@ -1,0 +1,23 @@
+// windows.cuh -- exact window-start states for the window-parallel sweep (see windows.cu).
+#pragma once
+#include "common.cuh"
+#include "sweep.cuh"
+
+namespace pbwtgpu {
+
+constexpr int kPseudoLabelBase = 1 << 29;  // site labels of the combine's pseudo-sites (above any real site)
+
+// Tie groups of `nodes` prefix nodes.  ord/dv: [nodes][M] / [nodes][M+1] (order and divergence of each node, the
+// divergence possibly still holding pseudo-site labels >= kPseudoLabelBase from a combine sweep, which are
+// replaced by the later window's boundary divergence gfdJ[gJ[hap]]).  Writes dv in place, g [nodes][M] (group
+// of each haplotype) and gfd [nodes][M] (divergence at the head of each group).
+int launch_make_groups(const int32_t *ord, int32_t *dv, const int32_t *gJ, const int32_t *gfdJ, int32_t *g, int32_t *gfd,
+                       int M, int nodes, cudaStream_t stream);
+// Pseudo-site columns of a node: column b, bit h = bit b of g[h].  out: [nodes][bits][wpc]
+int launch_key_bits(const int32_t *g, int M, int nodes, int bits, int wpc, uint32_t *out, cudaStream_t stream);
+// Gather the chunked match records of all windows into one contiguous array in window order.
+int launch_gather_records(const pbwtgpu_match *pool, const int *chunkTab, int poolChunks, const long long *winOffset,
+                          const unsigned long long *winCount, int nWindows, int maxChunksPerWindow, pbwtgpu_match *out,
+                          cudaStream_t stream);
+
+}  // namespace pbwtgpu

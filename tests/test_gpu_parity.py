@@ -175,3 +175,44 @@ def test_full_size_properties(eng):
     m = out["matches"]
     assert ((m["start"] <= m["end"]) & (m["end"] <= N) & (m["ai"] != m["bi"]) & (m["ai"] < M) & (m["bi"] < M)).all()
     assert (np.diff(m["end"]) >= 0).all()  # callback order: k ascending
+
+
+@pytest.mark.parametrize("M,N,W,dens", [(8, 10, 3, 0.3), (33, 40, 5, 0.5), (200, 64, 64, 0.2), (1000, 300, 7, 0.05),
+                                        (1025, 120, 16, 0.5), (2752, 38, 4, 0.3), (5000, 200, 148, 0.02)])
+def test_window_parallel_forced(eng, orc, M, N, W, dens):
+    """Force the window-parallel path (pass 1 + combine scan + pass 2) at small sizes: results must equal the
+    sequential reference sweep bit for bit, including match-record order across window boundaries."""
+    rng = np.random.default_rng(M * 7 + N)
+    hap = (rng.random((M, N)) < dens).astype(np.uint8)
+    hap[: M // 3] = hap[0]  # a block of identical haplotypes: ties that survive every window
+    x = O.pack_panel(hap)
+    a0 = rng.permutation(M).astype(np.int32)
+    eng.set_option("windows", W)
+    try:
+        check_build(eng, orc, x, M, N)
+        check_build(eng, orc, x, M, N, a_start=a0)
+    finally:
+        eng.set_option("windows", 0)
+
+
+def test_window_parallel_mosaic(eng, orc):
+    M, N = 2000, 2000
+    x = O.generate_panel(M, N, seed=0x5EED0003, L=300, mu=2.0)
+    eng.set_option("windows", 37)
+    try:
+        check_build(eng, orc, x, M, N)
+    finally:
+        eng.set_option("windows", 0)
+
+
+def test_small_record_pool_rerun(eng, orc):
+    """A deliberately tiny match-record pool must trigger the exact-size rerun, not drop records."""
+    M, N = 500, 100
+    rng = np.random.default_rng(77)
+    hap = (rng.random((M, N)) < 0.3).astype(np.uint8)
+    x = O.pack_panel(hap)
+    eng.set_option("match_capacity", 1)
+    try:
+        check_build(eng, orc, x, M, N)
+    finally:
+        eng.set_option("match_capacity", 0)
