@@ -63,8 +63,12 @@ int pbwtgpu_synchronize(pbwtgpu_ctx *ctx);
 int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value);
 /* Per-kernel-class device times of the last sweep (ms, CUDA events on the launching stream) and
  * launch counts; arrays of PBWTGPU_NUM_KERNEL_CLASSES. */
-enum { PBWTGPU_K_SWEEP = 0, PBWTGPU_K_PACK3 = 1, PBWTGPU_K_UNPACK3 = 2, PBWTGPU_K_QUERY = 3,
-       PBWTGPU_K_SYNTH = 4, PBWTGPU_K_AUX = 5, PBWTGPU_NUM_KERNEL_CLASSES = 6 };
+enum { PBWTGPU_K_SWEEP = 0,    /* the output-producing sweep (pass 2 of the window-parallel scheme) */
+       PBWTGPU_K_PACK3 = 1, PBWTGPU_K_UNPACK3 = 2, PBWTGPU_K_QUERY = 3, PBWTGPU_K_SYNTH = 4,
+       PBWTGPU_K_AUX = 5,      /* tie groups, key bits, record gather */
+       PBWTGPU_K_PREPASS = 6,  /* sweep kernel, pass 1: every window on its own */
+       PBWTGPU_K_COMBINE = 7,  /* sweep kernel over pseudo-sites: window-prefix combine rounds */
+       PBWTGPU_NUM_KERNEL_CLASSES = 8 };
 int pbwtgpu_profile(pbwtgpu_ctx *ctx, int enable);
 int pbwtgpu_last_timings(pbwtgpu_ctx *ctx, float *ms, int *launches);
 

@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpbwtgpu.so")
 
 WANT_YZ, WANT_D, WANT_MAXWITHIN = 1, 2, 4
-KERNEL_CLASSES = ("sweep", "pack3", "unpack3", "query", "synth", "aux")
+KERNEL_CLASSES = ("sweep", "pack3", "unpack3", "query", "synth", "aux", "prepass", "combine")
 
 MATCH_DTYPE = np.dtype([("ai", "<i4"), ("bi", "<i4"), ("start", "<i4"), ("end", "<i4")])
 NOMATCH_DTYPE = np.dtype([("query", "<i4"), ("allele", "<i4"), ("site", "<i4")])

@@ -23,6 +23,7 @@ struct pbwtgpu_ctx {
   // options
   long long optWindows = 0;    // 0 = automatic
   long long optMatchCap = 0;   // 0 = automatic
+  long long optWindowTimes = 0;  // debugging: print per-window CTA times of pass 2 to stderr
   // profiling
   bool profile = false;
   float ms[PBWTGPU_NUM_KERNEL_CLASSES] = {0};
@@ -251,9 +252,9 @@ int run_sweep(pbwtgpu_ctx *ctx, const uint32_t *src, int wpc, int M, int N, Swee
     a1.aStart = ord[0]; a1.aStartShared = 1;
     a1.aEnd = ord[0] + oA; a1.dEnd = dv[0] + oD;
     {
-      ScopedTimer t(ctx, PBWTGPU_K_SWEEP);
+      ScopedTimer t(ctx, PBWTGPU_K_PREPASS);
       CUDA_TRY(ctx, launch_sweep_smem(a1, kGather, true, false, ctx->stream));
-      ctx->launches[PBWTGPU_K_SWEEP] += 1;
+      ctx->launches[PBWTGPU_K_PREPASS] += 1;
     }
     {
       ScopedTimer t(ctx, PBWTGPU_K_AUX);
@@ -275,9 +276,9 @@ int run_sweep(pbwtgpu_ctx *ctx, const uint32_t *src, int wpc, int M, int N, Swee
       c.aStart = ord[cur] + oA; c.dStart = dv[cur] + oD;  // earlier part: node i (slot i+1)
       c.aEnd = ord[nxt] + s1 * oA; c.dEnd = dv[nxt] + s1 * oD;
       {
-        ScopedTimer t(ctx, PBWTGPU_K_SWEEP);
+        ScopedTimer t(ctx, PBWTGPU_K_COMBINE);
         CUDA_TRY(ctx, launch_sweep_smem(c, kGather, true, false, ctx->stream));
-        ctx->launches[PBWTGPU_K_SWEEP] += 1;
+        ctx->launches[PBWTGPU_K_COMBINE] += 1;
       }
       {
         ScopedTimer t(ctx, PBWTGPU_K_AUX);
@@ -315,6 +316,11 @@ int run_sweep(pbwtgpu_ctx *ctx, const uint32_t *src, int wpc, int M, int N, Swee
   a.recCount = recCount; a.chunkCounter = chunkCounter;
   a.reportAtN = 1;
   std::vector<unsigned long long> counts(W, 0);
+  long long *winNanos = nullptr;
+  if (ctx->optWindowTimes) {
+    if (int rc = tmp.get(&winNanos, (size_t)W)) return rc;
+    a.winNanos = winNanos;
+  }
   for (int attempt = 0; attempt < 2; ++attempt) {
     if (wantMatch) {
       poolChunks = (int)((recCap + kRecChunk - 1) >> kRecChunkLog) + W;
@@ -338,6 +344,14 @@ int run_sweep(pbwtgpu_ctx *ctx, const uint32_t *src, int wpc, int M, int N, Swee
     long long total = 0;  // the pool was too small: every window's count is known now, size it exactly and rerun
     for (auto cnt : counts) total += (long long)cnt;
     recCap = total;
+  }
+  if (winNanos) {
+    std::vector<long long> ns(W);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ns.data(), winNanos, sizeof(long long) * W, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    fprintf(stderr, "[pbwtgpu] pass-2 window times (us) and records:");
+    for (int w = 0; w < W; ++w) fprintf(stderr, " %d:%.0f/%llu", w, ns[w] * 1e-3, counts[w]);
+    fprintf(stderr, "\n");
   }
   if (wantMatch) {
     std::vector<long long> offs(W, 0);
@@ -481,6 +495,7 @@ int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value) {
   if (!ctx || !name) return PBWTGPU_ERR_ARG;
   if (!strcmp(name, "windows")) ctx->optWindows = value;
   else if (!strcmp(name, "match_capacity")) ctx->optMatchCap = value;
+  else if (!strcmp(name, "window_times")) ctx->optWindowTimes = value;
   else return fail(ctx, PBWTGPU_ERR_ARG, "unknown option %s", name);
   return 0;
 }

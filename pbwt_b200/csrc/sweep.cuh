@@ -39,6 +39,7 @@ struct SweepArgs {
   int *chunkTab;
   unsigned long long *recCount;  // [W] records produced by each window
   int reportAtN;                 // the window that ends at N also reports the k == N blocks
+  long long *winNanos;           // [W] optional: wall time of each window's CTA (globaltimer, debugging aid)
 };
 
 enum SweepMode { kGather = 0, kSorted = 1 };

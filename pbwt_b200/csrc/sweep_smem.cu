@@ -33,8 +33,8 @@ namespace pbwtgpu {
 namespace {
 
 constexpr int kThreads = 1024;
-constexpr int kStages = 4;
-constexpr int kQueue = 8;       // reporter entries kept per warp between the count and emit phases
+constexpr int kStages = 3;
+constexpr int kResMax = 256;    // match candidates processed per round (multiple of 32)
 constexpr int kBigBlock = 128;  // records; larger blocks are emitted by the whole CTA
 constexpr int kTabMirror = 64;  // newest chunk ids of this window mirrored in shared memory
 
@@ -48,13 +48,13 @@ struct SmemLayout {  // offsets in 32-bit words; every array start is 16-byte al
   static constexpr int d0 = a1 + MP;
   static constexpr int d1 = d0 + (WITH_D ? MP + 4 : 0);
   static constexpr int ycol = d1 + (WITH_D ? MP + 4 : 0);
-  static constexpr int xcol = ycol + 2 * WORDS;
+  static constexpr int xcol = ycol + WORDS;
   static constexpr int wsum = xcol + kStages * STAGE;
   static constexpr int mbar = wsum + 3 * 32;
-  static constexpr int wmax = mbar + 2 * kStages;
-  static constexpr int queue = wmax + (MATCH ? 2 * WORDS : 0);  // wmax is double-buffered like ycol
-  static constexpr int qcnt = queue + (MATCH ? 32 * kQueue * 4 : 0);
-  static constexpr int ctab = qcnt + (MATCH ? 32 : 0);  // mirror of the newest kTabMirror chunk ids
+  static constexpr int wmax = mbar + 8;  // room for up to 4 mbarriers, keeps 16-byte alignment
+  static constexpr int cmask = wmax + (MATCH ? WORDS : 0);
+  static constexpr int res = cmask + (MATCH ? WORDS : 0);       // per-word candidate masks, then result slots
+  static constexpr int ctab = res + (MATCH ? kResMax * 4 : 0);  // mirror of the newest kTabMirror chunk ids
   static constexpr int totalWords = ctab + (MATCH ? kTabMirror : 0);
   static constexpr size_t bytes = (size_t)totalWords * 4;
   static constexpr int padIndex = 32 * WORDS;  // "haplotype" whose allele is 1 at every site
@@ -152,74 +152,48 @@ __device__ __forceinline__ void emit_block(const RecSink &out, long long o, cons
   }
 }
 
-// One pass of matchMaximalWithin's per-site scan (pbwtMatch.c:122-137) over this warp's words.
+// ---- matchMaximalWithin's per-site scan (pbwtMatch.c:122-137), block-wide and load-balanced ----
 // For a position i the upward block is [q, i) with q the nearest index <= i whose d exceeds d[i], the
 // downward block (i, r) with r the nearest index > i whose d exceeds d[i+1]; i reports nothing when a
 // member of either block carries the same allele (the match extends).  Only heads/tails of allele runs
-// can fail that test on their first neighbour, so interior positions are never scanned (live sites).
-//   EMIT = false: count; reporters are queued in queue[] (up to kQueue); returns the warp's record total
-//                 and the number of reporters seen (nq may exceed kQueue = queue overflow).
-//   EMIT = true : recompute everything and write the records from offset off (overflow fallback).
-template <int E, bool EMIT>
-__device__ __forceinline__ int match_pass(const int32_t *sA, const int32_t *sD, const uint32_t *yc,
-                                          const int32_t *wmax, int M, int k, bool live, int warp, int lane, int4 *queue,
-                                          int &nq, bool &hasBig, const RecSink &out, long long off) {
-  int warpTotal = 0;
-  nq = 0;
-  hasBig = false;
-#pragma unroll 1
-  for (int e = 0; e < E; ++e) {
-    const int wd = warp * E + e;
-    const int base = wd * 32;
-    if (base >= M) break;
-    const uint32_t cw = yc[wd];
-    const uint32_t vm = (M - base >= 32) ? kFull : ((1u << (M - base)) - 1u);
-    uint32_t cand = vm;
-    if (live) {
-      const uint32_t pb = wd > 0 ? (yc[wd - 1] >> 31) : (cw & 1u);
-      const uint32_t nw = yc[wd + 1 < 32 * E ? wd + 1 : wd];
-      const uint32_t H = cw ^ ((cw << 1) | pb);
-      const uint32_t Hn = (H >> 1) | (((nw & 1u) ^ (cw >> 31)) << 31);
-      const uint32_t bm = (H | Hn) & vm;
-      if (!bm) continue;
-      bool mine = false;
-      if ((bm >> lane) & 1u) {
-        const int di = sD[base + lane], dn1 = sD[base + lane + 1];
-        const bool samePrev = !((H >> lane) & 1u), sameNext = !((Hn >> lane) & 1u);
-        mine = !((di <= dn1 && samePrev) || (di >= dn1 && sameNext));
-      }
-      cand = __ballot_sync(kFull, mine);
-    }
-    while (cand) {
-      const int j = __ffs(cand) - 1;
-      cand &= cand - 1;
-      const int i = base + j;
-      const uint32_t yi = (cw >> j) & 1u;
-      const int di = sD[i], dn1 = sD[i + 1];
-      int lo = i, hi = i + 1;
-      bool extends = false;
-      if (di <= dn1) {
-        lo = search_up(sD, wmax, i, di, lane);
-        extends = live && any_same_allele(yc, lo, i, yi, lane);
-      }
-      if (!extends && di >= dn1) {
-        hi = search_down(sD, wmax, i + 1, dn1, M, lane);
-        extends = live && any_same_allele(yc, i + 1, hi, yi, lane);
-      }
-      if (extends) continue;
-      const int cnt = (i - lo) + (hi - i - 1);
-      if (!cnt) continue;
-      if (EMIT) {
-        emit_block(out, off + warpTotal, sA, i, lo, hi, di, dn1, k, lane, 32);
-      } else {
-        if (nq < kQueue && lane == 0) queue[nq] = make_int4(i, lo, hi, warpTotal);
-        ++nq;
-        hasBig |= cnt >= kBigBlock;
-      }
-      warpTotal += cnt;
-    }
+// can fail that test on their first neighbour ("candidates"); PBWT order clusters them in a few words, so
+// they are numbered block-wide and dealt round-robin to the 32 warps, kResMax per round.
+
+// Candidate lanes of one word of state k.  cw: the word's alleles, pb: allele before the word, nb: allele
+// after it; d read from shared memory.  A lane is a candidate unless its first upward/downward neighbour
+// already carries its allele in the direction(s) the reference scans (pbwtMatch.c:124-129).
+__device__ __forceinline__ uint32_t candidate_mask(const int32_t *sD, uint32_t cw, uint32_t pb, uint32_t nb, int base,
+                                                   uint32_t vm, int lane) {
+  const uint32_t H = cw ^ ((cw << 1) | pb);
+  const uint32_t Hn = (H >> 1) | (((nb & 1u) ^ (cw >> 31)) << 31);
+  const uint32_t bm = (H | Hn) & vm;
+  bool mine = false;
+  if ((bm >> lane) & 1u) {
+    const int di = sD[base + lane], dn1 = sD[base + lane + 1];
+    const bool samePrev = !((H >> lane) & 1u), sameNext = !((Hn >> lane) & 1u);
+    mine = !((di <= dn1 && samePrev) || (di >= dn1 && sameNext));
   }
-  return warpTotal;
+  return __ballot_sync(kFull, mine);
+}
+
+// position of the g-th candidate of the block (g < T).  candBase: lane l holds the number of candidates in
+// warps < l; masks: per-word candidate masks, E words per warp.
+template <int E>
+__device__ __forceinline__ int locate_candidate(const uint32_t *masks, int candBase, int g, int lane) {
+  const int wv = 31 - __clz(__ballot_sync(kFull, candBase <= g));  // owning warp
+  int r = g - __shfl_sync(kFull, candBase, wv);                    // rank inside that warp
+  const uint32_t m = lane < E ? masks[wv * E + lane] : 0u;
+  const int pc = __popc(m);
+  int inc = pc;
+#pragma unroll
+  for (int dl = 1; dl < 32; dl <<= 1) {
+    const int t = __shfl_up_sync(kFull, inc, dl);
+    if (lane >= dl) inc += t;
+  }
+  const int e = __ffs(__ballot_sync(kFull, inc > r)) - 1;  // word holding it
+  r -= __shfl_sync(kFull, inc - pc, e);
+  const uint32_t me = __shfl_sync(kFull, m, e);
+  return (wv * E + e) * 32 + __fns(me, 0, r + 1);
 }
 
 template <int E, int MODE, bool WITH_D, bool MATCH>
@@ -232,12 +206,14 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
   int32_t *const wsumC = sI + L::wsum + 64;
   uint64_t *const mbar = reinterpret_cast<uint64_t *>(smem + L::mbar);
   int32_t *const wmaxS = sI + L::wmax;
-  int4 *const queueS = reinterpret_cast<int4 *>(smem + L::queue);
-  int32_t *const qcntS = sI + L::qcnt;
+  uint32_t *const cmaskS = smem + L::cmask;
+  int4 *const resS = reinterpret_cast<int4 *>(smem + L::res);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = p.M, wpc = p.wpc;
   const int win = blockIdx.x;
+  long long tStart = 0;
+  if (p.winNanos && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tStart));
   // site labels [k0, k1); column of label k is k + colShift of this window's source block
   int k0, k1, colShift;
   const uint32_t *src;
@@ -293,51 +269,72 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
   sink.nChunks = 0;
   long long recBase = 0;  // records produced so far by this window (uniform)
 
-  // -------- the emit phase shared by live sites and the final k == N report --------
-  auto emit_phase = [&](const int32_t *sA, const int32_t *sD, const uint32_t *yc, const int32_t *wm, int k, bool live,
-                        int nq) {
-    const int cw = wsumC[lane];
-    int tot;
-    const int ex = warp_excl_scan(cw, lane, tot);
-    if (sink.pool && tot) {
-      const int need = (int)((recBase + tot + kRecChunk - 1) >> kRecChunkLog);
-      if (need > sink.nChunks) {  // uniform: draw more chunks from the pool
-        if (tid == 0)
-          for (int c2 = sink.nChunks; c2 < need; ++c2) {
-            int id = atomicAdd(p.chunkCounter, 1);
-            if (id >= p.poolChunks) id = -1;  // pool exhausted: records are dropped, the host reruns larger
-            p.chunkTab[(size_t)win * p.poolChunks + c2] = id;
-            ctabS[c2 & (kTabMirror - 1)] = id;
-          }
-        sink.nChunks = need;
-        __syncthreads();
-      }
-      const long long mine = recBase + __shfl_sync(kFull, ex, warp);
-      if (nq > kQueue) {  // queue overflow: this warp redoes its words and writes everything itself
-        int nq2;
-        bool hb;
-        match_pass<E, true>(sA, sD, yc, wm, M, k, live, warp, lane, queueS + warp * kQueue, nq2, hb, sink, mine);
-      } else {
-        for (int q = 0; q < nq; ++q) {  // own small blocks
-          const int4 en = queueS[warp * kQueue + q];
-          if ((en.x - en.y) + (en.z - en.x - 1) < kBigBlock)
-            emit_block(sink, mine + en.w, sA, en.x, en.y, en.z, sD[en.x], sD[en.x + 1], k, lane, 32);
-        }
-      }
-      unsigned bigWarps = __ballot_sync(kFull, qcntS[lane] < 0);  // sign bit: that warp queued a big block
-      while (bigWarps) {
-        const int w2 = __ffs(bigWarps) - 1;
-        bigWarps &= bigWarps - 1;
-        const int n2 = qcntS[w2] & 0xffff;
-        const long long base2 = recBase + __shfl_sync(kFull, ex, w2);
-        for (int q = 0; q < n2; ++q) {
-          const int4 en = queueS[w2 * kQueue + q];
-          if ((en.x - en.y) + (en.z - en.x - 1) >= kBigBlock)
-            emit_block(sink, base2 + en.w, sA, en.x, en.y, en.z, sD[en.x], sD[en.x + 1], k, tid, kThreads);
-        }
-      }
+  // -------- candidates of a state -> records, in rounds of kResMax dealt round-robin to the 32 warps --------
+  // Expects cmaskS[] (per-word candidate masks) and wsumC[] (per-warp candidate counts) to have been published
+  // before the preceding barrier.  Contains at least one __syncthreads (the caller's "S2").
+  auto match_rounds = [&](const int32_t *sA, const int32_t *sD, const uint32_t *yc, const int32_t *wm, int k, bool live) {
+    int T;
+    const int candBase = warp_excl_scan(wsumC[lane], lane, T);
+    if (T == 0) {
+      __syncthreads();
+      return;
     }
-    recBase += tot;
+    for (int g0 = 0; g0 < T; g0 += kResMax) {
+      const int nR = min(kResMax, T - g0);
+      for (int g = g0 + warp; g < g0 + nR; g += 32) {
+        const int i = locate_candidate<E>(cmaskS, candBase, g, lane);
+        const uint32_t yi = (yc[i >> 5] >> (i & 31)) & 1u;
+        const int di = sD[i], dn1 = sD[i + 1];
+        int lo = i, hi = i + 1;
+        bool extends = false;
+        if (di <= dn1) {
+          lo = search_up(sD, wm, i, di, lane);
+          extends = live && any_same_allele(yc, lo, i, yi, lane);
+        }
+        if (!extends && di >= dn1) {
+          hi = search_down(sD, wm, i + 1, dn1, M, lane);
+          extends = live && any_same_allele(yc, i + 1, hi, yi, lane);
+        }
+        if (lane == 0) resS[g - g0] = make_int4(i, lo, hi, extends ? 0 : (i - lo) + (hi - i - 1));
+      }
+      __syncthreads();  // the round's results are published (first round: the scatter is complete too)
+      long long roundTotal = 0;
+      for (int c0 = 0; c0 < nR; c0 += 32) {
+        const int4 en = c0 + lane < nR ? resS[c0 + lane] : make_int4(0, 0, 0, 0);
+        int tot;
+        const int ex = warp_excl_scan(en.w, lane, tot);
+        if (sink.pool && tot) {
+          const long long base = recBase + roundTotal;
+          const int need = (int)((base + tot + kRecChunk - 1) >> kRecChunkLog);
+          if (need > sink.nChunks) {  // uniform: draw more chunks from the pool
+            if (tid == 0)
+              for (int c2 = sink.nChunks; c2 < need; ++c2) {
+                int id = atomicAdd(p.chunkCounter, 1);
+                if (id >= p.poolChunks) id = -1;  // pool exhausted: records are dropped, the host reruns larger
+                p.chunkTab[(size_t)win * p.poolChunks + c2] = id;
+                ctabS[c2 & (kTabMirror - 1)] = id;
+              }
+            sink.nChunks = need;
+            __syncthreads();
+          }
+          // entry c0 + warp is this warp's own (candidate g = g0 + c0 + warp); big blocks are shared by all warps
+          const int mi = __shfl_sync(kFull, en.x, warp), mlo = __shfl_sync(kFull, en.y, warp);
+          const int mhi = __shfl_sync(kFull, en.z, warp), mcnt = __shfl_sync(kFull, en.w, warp);
+          const int mex = __shfl_sync(kFull, ex, warp);
+          if (mcnt > 0 && mcnt < kBigBlock) emit_block(sink, base + mex, sA, mi, mlo, mhi, sD[mi], sD[mi + 1], k, lane, 32);
+          unsigned big = __ballot_sync(kFull, en.w >= kBigBlock);
+          while (big) {
+            const int j = __ffs(big) - 1;
+            big &= big - 1;
+            const int bi = __shfl_sync(kFull, en.x, j), blo = __shfl_sync(kFull, en.y, j), bhi = __shfl_sync(kFull, en.z, j);
+            emit_block(sink, base + __shfl_sync(kFull, ex, j), sA, bi, blo, bhi, sD[bi], sD[bi + 1], k, tid, kThreads);
+          }
+        }
+        roundTotal += tot;
+      }
+      recBase += roundTotal;
+      if (g0 + kResMax < T) __syncthreads();  // resS is reused by the next round
+    }
   };
 
   // -------- one site; CUR selects which half of the double buffers holds state k --------
@@ -345,13 +342,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     constexpr int CUR = decltype(curTag)::value;
     constexpr int aC = CUR ? L::a1 : L::a0, aN = CUR ? L::a0 : L::a1;
     constexpr int dC = CUR ? L::d1 : L::d0, dN = CUR ? L::d0 : L::d1;
-    constexpr int ycOff = L::ycol + CUR * L::WORDS;
     const int it = k - k0;
     const int stage = it % kStages;
     mbar_wait(&mbar[stage], (uint32_t)(it / kStages) & 1u);
     const uint32_t *col = smem + L::xcol + stage * L::STAGE;
-    uint32_t *yc = smem + ycOff;
-    int32_t *wmaxC = wmaxS + CUR * L::WORDS;
+    uint32_t *yc = smem + L::ycol;
+    int32_t *wmaxC = wmaxS;
     if (WITH_D) {  // sentinels of state k (pbwtCore.c:414,507), written by the threads that read them below
       if (tid == 0) sI[dC] = k + 1;
       if (tid == ownerM) sI[dC + M] = k + 1;
@@ -367,6 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
         pb = (col[hp >> 5] >> (hp & 31)) & 1u;
       } else pb = col[wordBase - 1] >> 31;
     }
+    const uint32_t pbFirst = pb;
     int carry = 0;         // max d since the last run head, over completed words (uniform)
     int lmax = 0;          // per-lane max of d over head-free words since then (reduced lazily)
     bool anyHead = false;  // has this warp seen a run head
@@ -374,6 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     int patchLane = 0, pDn = 0, pIdx = 0, pZ = 0;
     uint32_t pY = 0;
     int zw = 0;  // zeros in this warp so far
+    unsigned bnd = 0;  // words of this warp holding a head or a tail of an allele run (match candidates)
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int h = sLane[aC + e * 32];
@@ -384,6 +382,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
       if (e == 0 && warp == 0) pb = (~Bw) & 1u;  // sorted position 0 is always a run head
       const uint32_t H = Bw ^ ((Bw << 1) | pb);
       pb = Bw >> 31;
+      if (MATCH) {
+        if (H) bnd |= 1u << e;
+        if (e > 0 && (H & 1u)) bnd |= 1u << (e - 1);  // a head at lane 0 makes the previous word's last lane a tail
+      }
       if (lane == 0) yc[wordBase + e] = Bw;
       if (WITH_D) {
         const int dv = sLane[dC + e * 32];
@@ -430,7 +432,33 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
       wsumZ[warp] = zw;
       if (WITH_D) wsumR[warp] = (anyHead ? 0x80000000u : 0u) | (uint32_t)carry;
     }
-    __syncthreads();  // S1: ballots, warp sums published; everyone is done with col[]
+    if (MATCH) {  // candidate lanes of this warp's words (exact: the allele after the warp is looked up too)
+      uint32_t nb = 1u;  // pad positions carry ones
+      if (warp < 31) {
+        if (MODE == kGather) {
+          const int hn = sI[aC + (wordBase + E) * 32];
+          nb = (col[hn >> 5] >> (hn & 31)) & 1u;
+        } else nb = col[wordBase + E] & 1u;
+      }
+      __syncwarp();  // yc[] words of this warp were written by lane 0 above
+      unsigned words = bnd | (nb != pb ? 1u << (E - 1) : 0u);  // pb: this warp's last allele
+      uint32_t myMask = 0;
+      int tw = 0;
+      while (words) {
+        const int e = __ffs(words) - 1;
+        words &= words - 1;
+        const int wd = wordBase + e, base = wd * 32;
+        if (base >= M) break;
+        const uint32_t vm = (M - base >= 32) ? kFull : ((1u << (M - base)) - 1u);
+        const uint32_t m = candidate_mask(sI + dC, yc[wd], e > 0 ? yc[wd - 1] >> 31 : pbFirst,
+                                          e < E - 1 ? yc[wd + 1] & 1u : nb, base, vm, lane);
+        if (lane == e) myMask = m;
+        tw += __popc(m);
+      }
+      if (lane < E) cmaskS[wordBase + lane] = myMask;
+      if (lane == 0) wsumC[warp] = tw;
+    }
+    __syncthreads();  // S1: ballots, warp sums, match candidates published; everyone is done with col[]
 
     if (tid == 0 && k + kStages < k1) {  // refill the column slot just consumed
       fence_proxy_async();
@@ -484,19 +512,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     }
     if (p.cOut && tid == 0) p.cOut[k + colShift] = c;
 
-    // ---------------- matchMaximalWithin on state k ----------------
-    int nq = 0;
-    if (MATCH) {
-      bool hasBig;
-      const int wt = match_pass<E, false>(sI + aC, sI + dC, yc, wmaxC, M, k, true, warp, lane, queueS + warp * kQueue, nq,
-                                          hasBig, sink, 0);
-      if (lane == 0) {
-        wsumC[warp] = wt;
-        qcntS[warp] = nq > kQueue ? 0 : (nq | (hasBig ? 0x80000000 : 0));
-      }
-    }
-    __syncthreads();  // S2: scatter complete; match counts and queues published
-    if (MATCH) emit_phase(sI + aC, sI + dC, yc, wmaxC, k, true, nq);
+    // ---------------- matchMaximalWithin on state k (holds the S2 barrier) ----------------
+    if (MATCH) match_rounds(sI + aC, sI + dC, yc, wmaxC, k, true);
+    else __syncthreads();  // S2: scatter complete
   };
 
   int k = k0;
@@ -526,30 +544,37 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     for (int i = tid; i <= M; i += kThreads) p.dEnd[endSlot * (M + 1) + i] = sI[dC + i];
 
   if (MATCH && p.reportAtN && !p.perWindowSites && k1 == p.N) {  // k == N: nothing extends, every block is reported
-    const uint32_t *yc = smem + L::ycol;    // alleles are not consulted when live == false
-    for (int w = warp; w < L::WORDS; w += 32) {  // word maxima of the final d
+    const uint32_t *yc = smem + L::ycol;                           // alleles are not consulted when live == false
+    for (int w = warp; w < L::WORDS; w += 32) {                    // word maxima of the final d
       const int wm = __reduce_max_sync(kFull, sI[dC + w * 32 + lane]);
       if (lane == 0) wmaxS[w] = wm;
     }
-    __syncthreads();
-    int nq;
-    bool hasBig;
-    const int wt = match_pass<E, false>(sI + aC, sI + dC, yc, wmaxS, M, p.N, false, warp, lane, queueS + warp * kQueue, nq,
-                                        hasBig, sink, 0);
-    if (lane == 0) {
-      wsumC[warp] = wt;
-      qcntS[warp] = nq > kQueue ? 0 : (nq | (hasBig ? 0x80000000 : 0));
+    int tw = 0;
+    if (lane < E) {  // every valid position is a candidate
+      const int base = (wordBase + lane) * 32;
+      const uint32_t vm = (M - base >= 32) ? kFull : (M > base ? ((1u << (M - base)) - 1u) : 0u);
+      cmaskS[wordBase + lane] = vm;
+      tw = __popc(vm);
     }
+    tw = __reduce_add_sync(kFull, tw);
+    if (lane == 0) wsumC[warp] = tw;
     __syncthreads();
-    emit_phase(sI + aC, sI + dC, yc, wmaxS, p.N, false, nq);
+    match_rounds(sI + aC, sI + dC, yc, wmaxS, p.N, false);
   }
   if (MATCH && p.recCount && tid == 0) p.recCount[win] = (unsigned long long)recBase;
+  if (p.winNanos && tid == 0) {
+    long long tEnd;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tEnd));
+    p.winNanos[win] = tEnd - tStart;
+  }
 }
 
 template <int E, int MODE, bool WITH_D, bool MATCH>
 int launch_one(const SweepArgs &a, cudaStream_t stream) {
   using L = SmemLayout<E, WITH_D, MATCH>;
   static_assert(L::bytes <= 232448, "shared memory layout exceeds the 227 KB per-CTA limit");
+  static_assert(kStages <= 4 && L::xcol % 4 == 0 && L::mbar % 2 == 0 && L::res % 4 == 0 && L::d0 % 4 == 0 && L::d1 % 4 == 0,
+                "shared memory arrays must keep their alignment");
   auto kern = sweep_smem_kernel<E, MODE, WITH_D, MATCH>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
   if (err != cudaSuccess) return (int)err;
