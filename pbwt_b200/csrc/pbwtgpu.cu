@@ -8,7 +8,6 @@
 #include <vector>
 
 #include "pack3.cuh"
-#include "query.cuh"
 #include "sweep.cuh"
 #include "synth.cuh"
 #include "windows.cuh"
@@ -687,8 +686,9 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
                         int64_t *nmatch, pbwtgpu_nomatch **nomatch, int64_t *nnomatch) {
   if (!ctx || !matches || !nmatch || M < 1 || Q < 1 || N < 0) return fail(ctx, PBWTGPU_ERR_ARG, "match_sweep: bad args");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  if (M > sweep_smem_max_m(true))
-    return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "match_sweep: panel M=%d exceeds %d", M, sweep_smem_max_m(true));
+  if (M > query_sweep_max_m() || Q > query_sweep_max_q(M))
+    return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "match_sweep: panel M=%d (max %d) or Q=%d (max %d) beyond the shared-memory kernel",
+                M, query_sweep_max_m(), Q, query_sweep_max_q(M));
   Temps tmp(ctx);
   uint32_t *pcols = nullptr, *qcols = nullptr;
   if (int rc = decode_stream(ctx, tmp, pyz, npyz, M, N, &pcols, nullptr)) return rc;
@@ -703,37 +703,58 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
     CUDA_TRY(ctx, cudaMemcpyAsync(qa, qa_start, sizeof(int32_t) * Q, cudaMemcpyHostToDevice, ctx->stream));
   }
   unsigned long long *counts = nullptr;  // [0] records, [1] nomatch events
+  int *chunkCounter = nullptr, *chunkTab = nullptr;
   if (int rc = tmp.get(&counts, 2)) return rc;
-  long long recCap = ctx->optMatchCap > 0 ? ctx->optMatchCap : std::max<long long>(1 << 20, 64LL * Q * 64);
+  if (int rc = tmp.get(&chunkCounter, 1)) return rc;
+  long long recCap = ctx->optMatchCap > 0 ? ctx->optMatchCap : std::max<long long>(1 << 20, 4096LL * Q);
   long long nmCap = 1 << 16;
-  pbwtgpu_match *rec = nullptr;
+  pbwtgpu_match *pool = nullptr;
   pbwtgpu_nomatch *nm = nullptr;
   unsigned long long got[2] = {0, 0};
+  int poolChunks = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
-    if (int rc = tmp.get(&rec, (size_t)recCap)) return rc;
+    poolChunks = (int)((recCap + kRecChunk - 1) >> kRecChunkLog) + 1;
+    if (int rc = tmp.get(&pool, (size_t)poolChunks << kRecChunkLog)) return rc;
+    if (int rc = tmp.get(&chunkTab, (size_t)poolChunks)) return rc;
     if (int rc = tmp.get(&nm, (size_t)nmCap)) return rc;
-    QueryArgs q{};
-    q.pcols = pcols; q.qcols = qcols;
-    q.pwpc = pbwtgpu_words_per_col(M); q.qwpc = pbwtgpu_words_per_col(Q);
-    q.M = M; q.Q = Q; q.N = N;
-    q.paStart = pa; q.qaStart = qa;
-    q.rec = rec; q.recCap = recCap; q.nomatch = nm; q.nomatchCap = nmCap; q.counts = counts;
+    CUDA_TRY(ctx, cudaMemsetAsync(chunkCounter, 0, sizeof(int), ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    SweepArgs a{};
+    a.src = pcols; a.wpc = pbwtgpu_words_per_col(M); a.M = M; a.N = N;
+    a.sitesPerWindow = N > 0 ? N : 1; a.nWindows = 1;
+    a.aStart = pa;
+    a.qcols = qcols; a.qwpc = pbwtgpu_words_per_col(Q); a.Q = Q; a.qaStart = qa;
+    a.recPool = pool; a.poolChunks = poolChunks; a.chunkCounter = chunkCounter; a.chunkTab = chunkTab;
+    a.nomatch = nm; a.nomatchCap = nmCap; a.qCounts = counts;
     {
       ScopedTimer t(ctx, PBWTGPU_K_QUERY);
-      CUDA_TRY(ctx, launch_query_sweep(q, ctx->stream));
+      CUDA_TRY(ctx, launch_query_sweep_smem(a, ctx->stream));
       ctx->launches[PBWTGPU_K_QUERY] += 1;
     }
+    int used = 0;
     CUDA_TRY(ctx, cudaMemcpyAsync(got, counts, sizeof got, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(&used, chunkCounter, sizeof used, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if ((long long)got[0] <= recCap && (long long)got[1] <= nmCap) break;
+    if (used <= poolChunks && (long long)got[1] <= nmCap) break;
     if (attempt == 1) return fail(ctx, PBWTGPU_ERR_CUDA, "query sweep buffer overflow persisted");
     recCap = std::max<long long>(recCap, (long long)got[0]);
     nmCap = std::max<long long>(nmCap, (long long)got[1]);
   }
+  pbwtgpu_match *recDev = nullptr;
+  long long *offsDev = nullptr;
+  if (int rc = tmp.get(&recDev, (size_t)std::max<unsigned long long>(got[0], 1))) return rc;
+  if (int rc = tmp.get(&offsDev, 1)) return rc;
+  CUDA_TRY(ctx, cudaMemsetAsync(offsDev, 0, sizeof(long long), ctx->stream));
+  {
+    ScopedTimer t(ctx, PBWTGPU_K_AUX);
+    const int maxChunks = (int)((got[0] + kRecChunk - 1) >> kRecChunkLog);
+    CUDA_TRY(ctx, launch_gather_records(pool, chunkTab, poolChunks, offsDev, counts, 1, maxChunks, recDev, ctx->stream));
+    ctx->launches[PBWTGPU_K_AUX] += maxChunks > 0;
+  }
   pbwtgpu_match *hm = (pbwtgpu_match *)malloc(sizeof(pbwtgpu_match) * (size_t)std::max<unsigned long long>(got[0], 1));
   pbwtgpu_nomatch *hn = (pbwtgpu_nomatch *)malloc(sizeof(pbwtgpu_nomatch) * (size_t)std::max<unsigned long long>(got[1], 1));
   if (!hm || !hn) { free(hm); free(hn); return fail(ctx, PBWTGPU_ERR_NOMEM, "malloc records"); }
-  if (got[0]) CUDA_TRY(ctx, cudaMemcpyAsync(hm, rec, sizeof(pbwtgpu_match) * got[0], cudaMemcpyDeviceToHost, ctx->stream));
+  if (got[0]) CUDA_TRY(ctx, cudaMemcpyAsync(hm, recDev, sizeof(pbwtgpu_match) * got[0], cudaMemcpyDeviceToHost, ctx->stream));
   if (got[1]) CUDA_TRY(ctx, cudaMemcpyAsync(hn, nm, sizeof(pbwtgpu_nomatch) * got[1], cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   *matches = hm;

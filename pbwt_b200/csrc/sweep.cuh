@@ -40,6 +40,13 @@ struct SweepArgs {
   unsigned long long *recCount;  // [W] records produced by each window
   int reportAtN;                 // the window that ends at N also reports the k == N blocks
   long long *winNanos;           // [W] optional: wall time of each window's CTA (globaltimer, debugging aid)
+  // query sweep (matchSequencesSweep, pbwtMatch.c:363-443): single window, sorted mode, with d
+  const uint32_t *qcols;         // [N][qwpc] sorted query columns
+  int qwpc, Q;
+  const int32_t *qaStart;        // [Q] or NULL = identity
+  pbwtgpu_nomatch *nomatch;      // "no match" events, in emission order
+  long long nomatchCap;
+  unsigned long long *qCounts;   // [0] records, [1] "no match" events
 };
 
 enum SweepMode { kGather = 0, kSorted = 1 };
@@ -48,5 +55,9 @@ enum SweepMode { kGather = 0, kSorted = 1 };
 int sweep_smem_max_m(bool with_d);
 // returns cudaError_t as int
 int launch_sweep_smem(const SweepArgs &args, SweepMode mode, bool with_d, bool with_match, cudaStream_t stream);
+// query sweep: panel columns in args.src (sorted mode), queries in args.qcols; records go through the chunk pool
+int query_sweep_max_m();
+int query_sweep_max_q(int M);
+int launch_query_sweep_smem(const SweepArgs &args, cudaStream_t stream);
 
 }  // namespace pbwtgpu

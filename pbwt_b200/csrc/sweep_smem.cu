@@ -38,7 +38,7 @@ constexpr int kResMax = 256;    // match candidates processed per round (multipl
 constexpr int kBigBlock = 128;  // records; larger blocks are emitted by the whole CTA
 constexpr int kTabMirror = 64;  // newest chunk ids of this window mirrored in shared memory
 
-template <int E, bool WITH_D, bool MATCH>
+template <int E, bool WITH_D, bool MATCH, bool QUERY = false>
 struct SmemLayout {  // offsets in 32-bit words; every array start is 16-byte aligned
   static constexpr int MP = kThreads * E;
   static constexpr int WORDS = 32 * E;
@@ -55,7 +55,14 @@ struct SmemLayout {  // offsets in 32-bit words; every array start is 16-byte al
   static constexpr int cmask = wmax + (MATCH ? WORDS : 0);
   static constexpr int res = cmask + (MATCH ? WORDS : 0);       // per-word candidate masks, then result slots
   static constexpr int ctab = res + (MATCH ? kResMax * 4 : 0);  // mirror of the newest kTabMirror chunk ids
-  static constexpr int totalWords = ctab + (MATCH ? kTabMirror : 0);
+  static constexpr int QCAP = E <= 12 ? 1024 : 512;  // queries per launch (one thread each)
+  static constexpr int qf = ctab + ((MATCH || QUERY) ? kTabMirror : 0);  // per-query f (top of longest match)
+  static constexpr int qe = qf + (QUERY ? QCAP : 0);                      // per-query e (its start)
+  static constexpr int qa0 = qe + (QUERY ? QCAP : 0);                     // query prefix array, double buffered
+  static constexpr int qa1 = qa0 + (QUERY ? QCAP : 0);
+  static constexpr int zloc = qa1 + (QUERY ? QCAP : 0);                   // warp-local zero prefix of each word
+  static constexpr int wsq = zloc + (QUERY ? WORDS : 0);                  // 3 x 32 per-warp sums of the query phase
+  static constexpr int totalWords = wsq + (QUERY ? 96 : 0);
   static constexpr size_t bytes = (size_t)totalWords * 4;
   static constexpr int padIndex = 32 * WORDS;  // "haplotype" whose allele is 1 at every site
 };
@@ -70,6 +77,8 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int &total) {
   total = __shfl_sync(kFull, x, 31);
   return x - v;
 }
+
+__device__ __forceinline__ uint32_t ybit(const uint32_t *yc, int j) { return (yc[j >> 5] >> (j & 31)) & 1u; }
 
 // does any position in [lo, hi) carry allele yi?  (sorted bit column, pad bits beyond M are ones)
 __device__ __forceinline__ bool any_same_allele(const uint32_t *yc, int lo, int hi, uint32_t yi, int lane) {
@@ -196,9 +205,9 @@ __device__ __forceinline__ int locate_candidate(const uint32_t *masks, int candB
   return (wv * E + e) * 32 + __fns(me, 0, r + 1);
 }
 
-template <int E, int MODE, bool WITH_D, bool MATCH>
+template <int E, int MODE, bool WITH_D, bool MATCH, bool QUERY = false>
 __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs p) {
-  using L = SmemLayout<E, WITH_D, MATCH>;
+  using L = SmemLayout<E, WITH_D, MATCH, QUERY>;
   extern __shared__ __align__(16) uint32_t smem[];
   int32_t *const sI = reinterpret_cast<int32_t *>(smem);
   int32_t *const wsumZ = sI + L::wsum;
@@ -247,6 +256,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
       sI[L::d1 + i] = 0;
     }
   for (int i = tid; i < kStages * L::STAGE; i += kThreads) smem[L::xcol + i] = kFull;  // pad bits are ones
+  if (QUERY)
+    for (int i = tid; i < L::QCAP; i += kThreads) {
+      sI[L::qf + i] = 0;  // pbwtMatch.c:368-369: f and d start at zero
+      sI[L::qe + i] = 0;
+      sI[L::qa0 + i] = i < p.Q ? (p.qaStart ? p.qaStart[i] : i) : 0;
+    }
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&mbar[s], 1);
     mbar_fence_init();
@@ -263,11 +278,29 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
 
   int32_t *const ctabS = sI + L::ctab;
   RecSink sink;
-  sink.pool = MATCH ? reinterpret_cast<int4 *>(p.recPool) : nullptr;
-  sink.tab = MATCH && p.chunkTab ? p.chunkTab + (size_t)win * p.poolChunks : nullptr;
+  sink.pool = (MATCH || QUERY) ? reinterpret_cast<int4 *>(p.recPool) : nullptr;
+  sink.tab = (MATCH || QUERY) && p.chunkTab ? p.chunkTab + (size_t)win * p.poolChunks : nullptr;
   sink.mirror = ctabS;
   sink.nChunks = 0;
   long long recBase = 0;  // records produced so far by this window (uniform)
+  long long nmBase = 0;   // "no match" events so far (query sweep)
+  uint32_t qWord = (QUERY && tid < p.Q && k0 < k1) ? p.qcols[(size_t)(k0 + colShift) * p.qwpc + warp] : 0u;
+
+  // make sure chunks cover record offsets below upTo (uniform call; may contain a barrier)
+  auto ensure_chunks = [&](long long upTo) {
+    const int need = (int)((upTo + kRecChunk - 1) >> kRecChunkLog);
+    if (need > sink.nChunks) {
+      if (tid == 0)
+        for (int c2 = sink.nChunks; c2 < need; ++c2) {
+          int id = atomicAdd(p.chunkCounter, 1);
+          if (id >= p.poolChunks) id = -1;  // pool exhausted: records are dropped, the host reruns larger
+          p.chunkTab[(size_t)win * p.poolChunks + c2] = id;
+          ctabS[c2 & (kTabMirror - 1)] = id;
+        }
+      sink.nChunks = need;
+      __syncthreads();
+    }
+  };
 
   // -------- candidates of a state -> records, in rounds of kResMax dealt round-robin to the 32 warps --------
   // Expects cmaskS[] (per-word candidate masks) and wsumC[] (per-warp candidate counts) to have been published
@@ -305,18 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
         const int ex = warp_excl_scan(en.w, lane, tot);
         if (sink.pool && tot) {
           const long long base = recBase + roundTotal;
-          const int need = (int)((base + tot + kRecChunk - 1) >> kRecChunkLog);
-          if (need > sink.nChunks) {  // uniform: draw more chunks from the pool
-            if (tid == 0)
-              for (int c2 = sink.nChunks; c2 < need; ++c2) {
-                int id = atomicAdd(p.chunkCounter, 1);
-                if (id >= p.poolChunks) id = -1;  // pool exhausted: records are dropped, the host reruns larger
-                p.chunkTab[(size_t)win * p.poolChunks + c2] = id;
-                ctabS[c2 & (kTabMirror - 1)] = id;
-              }
-            sink.nChunks = need;
-            __syncthreads();
-          }
+          ensure_chunks(base + tot);
           // entry c0 + warp is this warp's own (candidate g = g0 + c0 + warp); big blocks are shared by all warps
           const int mi = __shfl_sync(kFull, en.x, warp), mlo = __shfl_sync(kFull, en.y, warp);
           const int mhi = __shfl_sync(kFull, en.z, warp), mcnt = __shfl_sync(kFull, en.w, warp);
@@ -425,6 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
           carry = __shfl_sync(kFull, v, 31);
         }
       }
+      if (QUERY && lane == 0) sI[L::zloc + wordBase + e] = zw;  // zeros of this warp before the word
       zw += __popc(~Bw);
     }
     if (WITH_D && !MATCH) carry = max(carry, __reduce_max_sync(kFull, lmax));
@@ -467,12 +490,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     }
 
     // ---------------- cross-warp prefixes (each warp redundantly) ----------------
-    int zIn, c;
+    int zIn, c, zExLane;  // zExLane: zeros in warps below warp index == lane
     {
       const int z = wsumZ[lane];
       int tot;
-      const int ex = warp_excl_scan(z, lane, tot);
-      zIn = __shfl_sync(kFull, ex, warp);
+      zExLane = warp_excl_scan(z, lane, tot);
+      zIn = __shfl_sync(kFull, zExLane, warp);
       c = tot;
     }
     int cIn = 0;
@@ -514,7 +537,89 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
 
     // ---------------- matchMaximalWithin on state k (holds the S2 barrier) ----------------
     if (MATCH) match_rounds(sI + aC, sI + dC, yc, wmaxC, k, true);
-    else __syncthreads();  // S2: scatter complete
+    else if (!QUERY) __syncthreads();  // S2: scatter complete
+    if (QUERY) {
+      // ---------------- matchSequencesSweep on state k (pbwtMatch.c:376-426), one thread per query ----------------
+      constexpr int qaC = CUR ? L::qa1 : L::qa0, qaN = CUR ? L::qa0 : L::qa1;
+      const int32_t *sD = sI + dC;
+      const bool active = tid < p.Q;
+      const uint32_t x = active ? (qWord >> lane) & 1u : 1u;  // query allele at sorted query position tid
+      if (active && k + 1 < k1) qWord = p.qcols[(size_t)(k + 1 + colShift) * p.qwpc + warp];  // prefetch next site
+      const int jj = active ? sI[qaC + tid] : 0;
+      int f = sI[L::qf + jj], e = sI[L::qe + jj];
+      int repLo = 0, repHi = 0, repStart = 0;
+      bool nm = false;
+      if (active && ybit(yc, f) != x) {
+        // an alternate of the same length further down that does extend? (pbwtMatch.c:381-383)
+        int hi = f + 1;
+        bool moved = false;
+        while (hi < M && sD[hi] <= e) {
+          if (ybit(yc, hi) == x) { f = hi; moved = true; break; }
+          ++hi;
+        }
+        if (!moved) {
+          repLo = f; repHi = hi; repStart = e;  // report [f, hi) with start e (pbwtMatch.c:385)
+          // reseed: widen alternately up and down by divergence tiers (pbwtMatch.c:389-411)
+          int lo = f;
+          int dDown = hi < M ? sD[hi] : k;
+          int dUp = sD[lo];
+          for (;;) {
+            if (dUp <= dDown) {
+              int top = -1;
+              while (lo > 0 && sD[lo] <= dUp) {
+                --lo;
+                if (ybit(yc, lo) == x) top = lo;
+              }
+              if (top >= 0) { f = top; e = dUp; break; }
+              dUp = sD[lo];
+            } else {
+              bool hit = false;
+              while (hi < M && sD[hi] <= dDown) {
+                if (ybit(yc, hi) == x) { f = hi; e = dDown; hit = true; break; }
+                ++hi;
+              }
+              if (hit) break;
+              dDown = hi == M ? k : sD[hi];
+              if (lo == 0 && hi == M) { nm = true; e = k + 1; break; }  // allele absent from the column
+            }
+          }
+        }
+      }
+      {  // FM step: f -> position in state k+1 (pbwtCursorCalculateU + pbwtCursorMap, pbwtCore.c:510-519, pbwt.h:130)
+        const int fw = f >> 5;
+        const int Z = __shfl_sync(kFull, zExLane, fw / E) + sI[L::zloc + fw] + __popc(~yc[fw] & lanemask_lt(f & 31));
+        int nf = x ? c + f - Z : Z;
+        if (nf == M) nf = 0;  // pbwtMatch.c:421-422
+        if (active) { sI[L::qf + jj] = nf; sI[L::qe + jj] = e; }
+      }
+      // per-warp sums: records, "no match" events, zeros of the query column
+      const int cnt = repHi - repLo;
+      int cntTot;
+      const int cntEx = warp_excl_scan(cnt, lane, cntTot);
+      const unsigned nmBal = __ballot_sync(kFull, nm), qzBal = __ballot_sync(kFull, active && x == 0u);
+      int32_t *wsq = sI + L::wsq;
+      if (lane == 0) { wsq[warp] = cntTot; wsq[32 + warp] = __popc(nmBal); wsq[64 + warp] = __popc(qzBal); }
+      __syncthreads();  // S2: scatter complete; query sums published
+      int recTot, nmTot, cq;
+      const int recEx = __shfl_sync(kFull, warp_excl_scan(wsq[lane], lane, recTot), warp);
+      const int nmEx = __shfl_sync(kFull, warp_excl_scan(wsq[32 + lane], lane, nmTot), warp);
+      const int qzEx = __shfl_sync(kFull, warp_excl_scan(wsq[64 + lane], lane, cq), warp);
+      if (sink.pool && recTot) {
+        ensure_chunks(recBase + recTot);
+        long long o = recBase + recEx + cntEx;
+        for (int i = repLo; i < repHi; ++i, ++o) sink.put(o, make_int4(jj, sI[aC + i], repStart, k));
+      }
+      if (nm && p.nomatch) {
+        const long long o = nmBase + nmEx + __popc(nmBal & ltMask);
+        if (o < p.nomatchCap) p.nomatch[o] = pbwtgpu_nomatch{jj, (int)x, k};
+      }
+      recBase += recTot;
+      nmBase += nmTot;
+      if (active) {  // query cursor step (pbwtCursorForwardsRead on uq, pbwtMatch.c:426)
+        const int zb = qzEx + __popc(qzBal & ltMask);
+        sI[qaN + (x ? cq + tid - zb : zb)] = jj;
+      }
+    }
   };
 
   int k = k0;
@@ -543,6 +648,29 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
   if (WITH_D && p.dEnd && writeEnd)
     for (int i = tid; i <= M; i += kThreads) p.dEnd[endSlot * (M + 1) + i] = sI[dC + i];
 
+  if (QUERY) {  // matches still open at N (pbwtMatch.c:430-436): a[f], then every following i with d[i] <= e
+    const int32_t *sD = sI + dC;
+    const bool active = tid < p.Q;
+    const int jj = active ? sI[(cur ? L::qa1 : L::qa0) + tid] : 0;
+    const int f = sI[L::qf + jj], e = sI[L::qe + jj];
+    int hi = f + 1;
+    if (active) while (hi < M && sD[hi] <= e) ++hi;
+    const int cnt = active ? hi - f : 0;
+    int cntTot;
+    const int cntEx = warp_excl_scan(cnt, lane, cntTot);
+    int32_t *wsq = sI + L::wsq;
+    if (lane == 0) wsq[warp] = cntTot;
+    __syncthreads();
+    int recTot;
+    const int recEx = __shfl_sync(kFull, warp_excl_scan(wsq[lane], lane, recTot), warp);
+    if (sink.pool && recTot) {
+      ensure_chunks(recBase + recTot);
+      long long o = recBase + recEx + cntEx;
+      for (int i = f; i < f + cnt; ++i, ++o) sink.put(o, make_int4(jj, sI[aC + i], e, p.N));
+    }
+    recBase += recTot;
+    if (tid == 0 && p.qCounts) { p.qCounts[0] = (unsigned long long)recBase; p.qCounts[1] = (unsigned long long)nmBase; }
+  }
   if (MATCH && p.reportAtN && !p.perWindowSites && k1 == p.N) {  // k == N: nothing extends, every block is reported
     const uint32_t *yc = smem + L::ycol;                           // alleles are not consulted when live == false
     for (int w = warp; w < L::WORDS; w += 32) {                    // word maxima of the final d
@@ -602,6 +730,30 @@ int launch_e(const SweepArgs &a, cudaStream_t stream) {
 }  // namespace
 
 int sweep_smem_max_m(bool with_d) { return with_d ? 13 * 1024 : 25 * 1024; }
+int query_sweep_max_m() { return 13 * 1024; }
+int query_sweep_max_q(int M) { return M <= 10 * 1024 ? 1024 : 512; }
+
+template <int E>
+static int launch_query_one(const SweepArgs &a, cudaStream_t stream) {
+  using L = SmemLayout<E, true, false, true>;
+  static_assert(L::bytes <= 232448, "shared memory layout exceeds the 227 KB per-CTA limit");
+  auto kern = sweep_smem_kernel<E, kSorted, true, false, true>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
+  if (err != cudaSuccess) return (int)err;
+  kern<<<1, kThreads, L::bytes, stream>>>(a);
+  return (int)cudaGetLastError();
+}
+
+int launch_query_sweep_smem(const SweepArgs &a, cudaStream_t stream) {
+  if (a.M < 1 || a.M > query_sweep_max_m() || a.Q < 1 || a.Q > query_sweep_max_q(a.M)) return (int)cudaErrorInvalidValue;
+  const int e = ((a.M + 31) / 32 + 31) / 32;
+  if (e <= 1) return launch_query_one<1>(a, stream);
+  if (e <= 2) return launch_query_one<2>(a, stream);
+  if (e <= 4) return launch_query_one<4>(a, stream);
+  if (e <= 7) return launch_query_one<7>(a, stream);
+  if (e <= 10) return launch_query_one<10>(a, stream);
+  return launch_query_one<13>(a, stream);
+}
 
 int launch_sweep_smem(const SweepArgs &a, SweepMode mode, bool with_d, bool with_match, cudaStream_t stream) {
   if (a.M < 1 || a.M > sweep_smem_max_m(with_d || with_match)) return (int)cudaErrorInvalidValue;

@@ -216,3 +216,44 @@ def test_small_record_pool_rerun(eng, orc):
         check_build(eng, orc, x, M, N)
     finally:
         eng.set_option("match_capacity", 0)
+
+
+def _split_streams(orc, hp, hq):
+    M, N = hp.shape
+    Q = hq.shape[0]
+    pyz = orc.build(O.pack_panel(hp), M, N, with_d=False)[0]
+    qyz = orc.build(O.pack_panel(hq), Q, N, with_d=False)[0]
+    return pyz, qyz
+
+
+def test_query_sweep_golden(eng):
+    g = np.load(os.path.join(GOLD, "query_sweep.npz"))
+    M, Q, N = int(g["M"]), int(g["Q"]), int(g["N"])
+    rec, nom = eng.match_sweep(g["pyz"], M, N, g["qyz"], Q)
+    assert (rec4(rec) == g["matches"]).all()
+    assert (np.stack([nom["query"], nom["allele"], nom["site"]], 1) == g["nomatch"]).all()
+
+
+@pytest.mark.parametrize("M,Q,N,dp,dq", [(60, 7, 80, 0.03, 0.3), (5, 9, 30, 0.5, 0.5), (200, 1, 50, 0.2, 0.2), (1000, 300, 120, 0.1, 0.1),
+                                         (33, 64, 40, 0.5, 0.02), (3000, 1000, 60, 0.05, 0.05)])
+def test_query_sweep_random(eng, orc, M, Q, N, dp, dq):
+    """matchSequencesSweep parity incl. 'no match' events, a query identical to a panel haplotype, Q=1, Q>M."""
+    rng = np.random.default_rng(M + Q)
+    hp = (rng.random((M, N)) < dp).astype(np.uint8)
+    hq = (rng.random((Q, N)) < dq).astype(np.uint8)
+    hq[0] = hp[M // 2]
+    pyz, qyz = _split_streams(orc, hp, hq)
+    want_rec, want_nom = orc.match_sweep(pyz, M, N, qyz, Q)
+    rec, nom = eng.match_sweep(pyz, M, N, qyz, Q)
+    assert len(rec) == len(want_rec) and (rec == want_rec).all()
+    assert len(nom) == len(want_nom) and (nom == want_nom).all()
+
+
+def test_query_sweep_mosaic(eng, orc):
+    M, Q, N = 4000, 500, 1500
+    x = O.generate_panel(M + Q, N, seed=0x5EED0005, L=300, mu=3.0)
+    hap = O.unpack_panel(x, M + Q)
+    pyz, qyz = _split_streams(orc, hap[:M], hap[M:])
+    want_rec, want_nom = orc.match_sweep(pyz, M, N, qyz, Q)
+    rec, nom = eng.match_sweep(pyz, M, N, qyz, Q)
+    assert len(rec) == len(want_rec) and (rec == want_rec).all() and (nom == want_nom).all()
