@@ -119,6 +119,18 @@ def pack3_fixture():
     print("pack3", {k: v.tobytes().hex() for k, v in out.items()})
 
 
+def write_pbwt(path, M, N, a_start, a_end, yz):
+    """PBW3 layout, pbwtIO.c:33-57."""
+    with open(path, "wb") as fh:
+        fh.write(b"PBW3")
+        fh.write(np.array([M, N], "<i4").tobytes())
+        fh.write(np.asarray(a_start, "<i4").tobytes())
+        fh.write(np.asarray(a_end, "<i4").tobytes())
+        fh.write(np.array([len(yz)], "<i8").tobytes())
+        fh.write(b"    ")
+        fh.write(np.asarray(yz, np.uint8).tobytes())
+
+
 def query_fixture():
     """matchSequencesSweep on a seeded mosaic split 550 panel / 50 query haplotypes x 500 sites."""
     ref = O.reference()
@@ -131,9 +143,19 @@ def query_fixture():
     rec, nom = ref.match_sweep(pyz, M, N, qyz, Q)
     rec4 = np.stack([rec["ai"], rec["bi"], rec["start"], rec["end"]], 1)
     nom3 = np.stack([nom["query"], nom["allele"], nom["site"]], 1)
+    # the CLI route: pbwt -read panel.pbwt -matchDynamic query.pbwt (pbwtMain.c:412) -> stdout + log
+    with tempfile.TemporaryDirectory() as td:
+        pp, qp, lg = os.path.join(td, "p.pbwt"), os.path.join(td, "q.pbwt"), os.path.join(td, "log")
+        write_pbwt(pp, M, N, np.arange(M), pa, pyz)
+        write_pbwt(qp, Q, N, np.arange(Q), qa, qyz)
+        out = subprocess.run([CLI, "-log", lg, "-read", pp, "-matchDynamic", qp], check=True, capture_output=True).stdout
+        log = [ln for ln in open(lg).read().splitlines() if ln.startswith("no match") or ln.startswith("Average number")]
+    printed = rec4[rec4[:, 2] != rec4[:, 3]]
+    assert (printed == stdout_records(out)).all()
     np.savez_compressed(os.path.join(HERE, "query_sweep.npz"), M=M, Q=Q, N=N, pxbits=px, qxbits=qx,
-                        pyz=pyz, qyz=qyz, matches=rec4, nomatch=nom3)
-    print("query_sweep records", len(rec4), "nomatch", len(nom3))
+                        pyz=pyz, qyz=qyz, pa_end=pa, qa_end=qa, matches=rec4, nomatch=nom3,
+                        matchdynamic_stdout_md5=hashlib.md5(out).hexdigest(), matchdynamic_log="\n".join(log))
+    print("query_sweep records", len(rec4), "nomatch", len(nom3), hashlib.md5(out).hexdigest(), log[-1])
 
 
 def main():

@@ -1,0 +1,64 @@
+"""GPU test of the drop-in CLI: the reference's own pbwtMain.c / pbwtIO.c linked with the host shim and
+libpbwtgpu.so (pbwt_b200/host/_build/pbwt_gpu, built where the reference is present and shipped prebuilt).
+stdout of -maxWithin / -matchDynamic and the bytes of -write must equal the reference's (golden md5s)."""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+CLI = os.path.join(ROOT, "pbwt_b200", "host", "_build", "pbwt_gpu")
+SELFTEST = os.path.join(ROOT, "pbwt_b200", "host", "_build", "shim_selftest")
+
+needs_cli = pytest.mark.skipif(not os.path.exists(CLI), reason="pbwt_gpu not built (needs the reference sources at build time)")
+
+
+def write_pbwt(path, M, N, a_start, a_end, yz):
+    with open(path, "wb") as fh:  # PBW3 layout, pbwtIO.c:33-57
+        fh.write(b"PBW3" + np.array([M, N], "<i4").tobytes() + np.asarray(a_start, "<i4").tobytes() +
+                 np.asarray(a_end, "<i4").tobytes() + np.array([len(yz)], "<i8").tobytes() + b"    " +
+                 np.asarray(yz, np.uint8).tobytes())
+
+
+@needs_cli
+@pytest.mark.parametrize("name", ["merge1", "omni", "mosaic300x400"])
+def test_cli_maxwithin_stdout(tmp_path, name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    M, N = int(g["M"]), int(g["N"])
+    pb = tmp_path / "x.pbwt"
+    write_pbwt(pb, M, N, np.arange(M), g["a_end"], g["yz"])
+    assert hashlib.md5(open(pb, "rb").read()).hexdigest() == str(g["pbwt_md5"])
+    out = subprocess.run([CLI, "-read", str(pb), "-maxWithin"], check=True, capture_output=True).stdout
+    assert len(out.splitlines()) == int(g["maxwithin_stdout_lines"])
+    assert hashlib.md5(out).hexdigest() == str(g["maxwithin_stdout_md5"])
+
+
+@needs_cli
+def test_cli_matchdynamic_stdout_and_log(tmp_path):
+    g = np.load(os.path.join(GOLD, "query_sweep.npz"))
+    M, Q, N = int(g["M"]), int(g["Q"]), int(g["N"])
+    pp, qp, lg = tmp_path / "p.pbwt", tmp_path / "q.pbwt", tmp_path / "log"
+    write_pbwt(pp, M, N, np.arange(M), g["pa_end"], g["pyz"])
+    write_pbwt(qp, Q, N, np.arange(Q), g["qa_end"], g["qyz"])
+    out = subprocess.run([CLI, "-log", str(lg), "-read", str(pp), "-matchDynamic", str(qp)], check=True, capture_output=True).stdout
+    assert hashlib.md5(out).hexdigest() == str(g["matchdynamic_stdout_md5"])
+    log = [ln for ln in open(lg).read().splitlines() if ln.startswith("no match") or ln.startswith("Average number")]
+    assert "\n".join(log) == str(g["matchdynamic_log"])
+
+
+@needs_cli
+def test_shim_batched_build_writes_reference_file(tmp_path):
+    """pbwtGpuBuildFromSites + the reference's own pbwtWrite must give the reference's .pbwt bytes."""
+    g = np.load(os.path.join(GOLD, "omni.npz"))
+    M, N = int(g["M"]), int(g["N"])
+    hap = O.unpack_panel(g["xbits"], M)  # [M, N]
+    xin, pb = tmp_path / "x.bytes", tmp_path / "x.pbwt"
+    np.ascontiguousarray(hap.T).tofile(xin)  # site-major bytes
+    subprocess.run([SELFTEST, str(xin), str(M), str(N), str(pb)], check=True, capture_output=True)
+    assert hashlib.md5(open(pb, "rb").read()).hexdigest() == str(g["pbwt_md5"])
