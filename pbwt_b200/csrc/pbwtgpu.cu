@@ -23,6 +23,7 @@ struct pbwtgpu_ctx {
   long long optWindows = 0;    // 0 = automatic
   long long optMatchCap = 0;   // 0 = automatic
   long long optWindowTimes = 0;  // debugging: print per-window CTA times of pass 2 to stderr
+  long long optForceGlobal = 0;  // testing: use the global-memory kernel even for narrow panels
   // profiling
   bool profile = false;
   float ms[PBWTGPU_NUM_KERNEL_CLASSES] = {0};
@@ -190,22 +191,46 @@ int run_sweep(pbwtgpu_ctx *ctx, const uint32_t *src, int wpc, int M, int N, Swee
   const bool wantYz = (flags & PBWTGPU_WANT_YZ) && mode == kGather;
   if (M < 1 || N < 0) return fail(ctx, PBWTGPU_ERR_ARG, "bad panel shape M=%d N=%d", M, N);
   if (N >= kPseudoLabelBase - 64) return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "N=%d too large", N);
-  if (M > sweep_smem_max_m(wantD))
-    return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "M=%d exceeds the shared-memory sweep limit %d", M, sweep_smem_max_m(wantD));
+  // panels wider than one CTA's shared memory sweep with their state in global memory (sweep_global.cu)
+  const bool useGlobal = M > sweep_smem_max_m(true) || ctx->optForceGlobal;
+  if (useGlobal && wantMatch)
+    return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "maxWithin needs M <= %d (shared-memory kernel); M=%d", sweep_smem_max_m(true), M);
   Temps tmp(ctx);
   res->M = M;
   res->N = N;
 
   // ---- window plan ----
-  int W = 1;
-  if (mode == kGather && M >= 2 && M <= sweep_smem_max_m(true)) {
+  int W = 1, G = 1, chunk = 0;
+  if (mode == kGather && M >= 2) {
     const long long want = ctx->optWindows > 0 ? ctx->optWindows : ctx->smCount;
     const int minSites = ctx->optWindows > 0 ? 1 : 256;  // below this a window does not repay its two extra passes
     W = (int)std::max<long long>(1, std::min<long long>(want, N / minSites));
   }
+  if (useGlobal) sweep_global_plan(M, ctx->smCount, W, &G, &chunk, &W);
   int spw = N > 0 ? (N + W - 1) / W : 1;
   W = N > 0 ? (N + spw - 1) / spw : 1;
   const int nodes = W - 1;
+
+  // the two kernels behind one launcher
+  int32_t *gA = nullptr, *gD = nullptr;
+  uint32_t *gPart = nullptr;
+  void *gSync = nullptr;
+  if (useGlobal) {
+    const size_t MS = (size_t)G * chunk;
+    if (int rc = tmp.get(&gA, (size_t)W * 2 * MS)) return rc;
+    if (int rc = tmp.get(&gD, (size_t)W * 2 * (MS + 4))) return rc;
+    if (int rc = tmp.get(&gPart, (size_t)W * G * 4)) return rc;
+    char *sy = nullptr;
+    if (int rc = tmp.get(&sy, sweep_global_sync_bytes(W))) return rc;
+    gSync = sy;
+  }
+  auto launch = [&](const SweepArgs &args, SweepMode md, bool withD, bool withMatch) -> int {
+    if (!useGlobal) return launch_sweep_smem(args, md, withD, withMatch, ctx->stream);
+    cudaError_t e = cudaMemsetAsync(gPart, 0, sizeof(uint32_t) * (size_t)W * G * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(gSync, 0, sweep_global_sync_bytes(W), ctx->stream);
+    if (e != cudaSuccess) return (int)e;
+    return launch_sweep_global(args, md, withD, G, chunk, gA, gD, gPart, gSync, ctx->stream);
+  };
 
   if (int rc = result_alloc(ctx, res, &res->aEnd, (size_t)M)) return rc;
   if (wantD)
@@ -252,7 +277,7 @@ int run_sweep(pbwtgpu_ctx *ctx, const uint32_t *src, int wpc, int M, int N, Swee
     a1.aEnd = ord[0] + oA; a1.dEnd = dv[0] + oD;
     {
       ScopedTimer t(ctx, PBWTGPU_K_PREPASS);
-      CUDA_TRY(ctx, launch_sweep_smem(a1, kGather, true, false, ctx->stream));
+      CUDA_TRY(ctx, launch(a1, kGather, true, false));
       ctx->launches[PBWTGPU_K_PREPASS] += 1;
     }
     {
@@ -276,7 +301,7 @@ int run_sweep(pbwtgpu_ctx *ctx, const uint32_t *src, int wpc, int M, int N, Swee
       c.aEnd = ord[nxt] + s1 * oA; c.dEnd = dv[nxt] + s1 * oD;
       {
         ScopedTimer t(ctx, PBWTGPU_K_COMBINE);
-        CUDA_TRY(ctx, launch_sweep_smem(c, kGather, true, false, ctx->stream));
+        CUDA_TRY(ctx, launch(c, kGather, true, false));
         ctx->launches[PBWTGPU_K_COMBINE] += 1;
       }
       {
@@ -330,7 +355,7 @@ int run_sweep(pbwtgpu_ctx *ctx, const uint32_t *src, int wpc, int M, int N, Swee
     }
     {
       ScopedTimer t(ctx, PBWTGPU_K_SWEEP);
-      CUDA_TRY(ctx, launch_sweep_smem(a, mode, wantD, wantMatch, ctx->stream));
+      CUDA_TRY(ctx, launch(a, mode, wantD, wantMatch));
       ctx->launches[PBWTGPU_K_SWEEP] += 1;
     }
     if (!wantMatch) break;
@@ -495,6 +520,7 @@ int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value) {
   if (!strcmp(name, "windows")) ctx->optWindows = value;
   else if (!strcmp(name, "match_capacity")) ctx->optMatchCap = value;
   else if (!strcmp(name, "window_times")) ctx->optWindowTimes = value;
+  else if (!strcmp(name, "force_global")) ctx->optForceGlobal = value;
   else return fail(ctx, PBWTGPU_ERR_ARG, "unknown option %s", name);
   return 0;
 }

@@ -60,4 +60,14 @@ int query_sweep_max_m();
 int query_sweep_max_q(int M);
 int launch_query_sweep_smem(const SweepArgs &args, cudaStream_t stream);
 
+
+// ---- wide panels: state in global memory, groups of cooperating CTAs (sweep_global.cu) ----
+// plan: G CTAs per window and their chunk of sorted positions; W = windows that fit in maxCtas co-resident CTAs
+void sweep_global_plan(int M, int maxCtas, int wantWindows, int *G, int *chunk, int *W);
+size_t sweep_global_state_ints(int G, int chunk, int W, bool with_d);  // a (and d) double buffers, in int32
+size_t sweep_global_sync_bytes(int W);
+// partials: W*G*4 uint32 and gsync: sweep_global_sync_bytes(W), both zeroed before every launch
+int launch_sweep_global(const SweepArgs &a, SweepMode mode, bool with_d, int G, int chunk, int32_t *aBuf, int32_t *dBuf,
+                        uint32_t *partials, void *gsync, cudaStream_t stream);
+
 }  // namespace pbwtgpu

@@ -1,0 +1,326 @@
+// sweep_global.cu -- per-site forward sweep for panels too wide for one CTA's shared memory
+// (M > 13,312 with d / 25,600 without; BASELINE configs 3-5: M = 1e5 .. 1e6).
+//
+// Same algorithm and outputs as sweep_smem.cu (pbwtCursorForwardsA/AD, the gather build, sorted-column
+// sweeps: pbwtCore.c:458-557, pbwtIO.c:572-574), different residency: a[] and d[] live in global memory,
+// double buffered, and stay L2-resident (16 B per haplotype: 16 MB at M = 1e6, L2 is 126 MB).
+// A window of sites is swept by a GROUP of G co-resident CTAs (cooperative launch); CTA g of a group owns
+// the contiguous sorted positions [g*chunk, (g+1)*chunk).  Per site:
+//   phase A  each CTA: coalesced ld.cg of a[]/d[] (L1 must be bypassed: other CTAs rewrite them every
+//            site), gather of the allele bit from the site's column (read-only, L1-cached), ballots,
+//            warp-local zero counts and the run-max scan for d (as in sweep_smem.cu); d' staged in smem.
+//   exchange each CTA publishes (zeros, run-max summary) with an epoch flag; every CTA reads all G partials
+//            (flag spin, no barrier) and derives its incoming zero count / carry and the column's c.
+//   phase C  stable-partition scatter of a (and d') into the other buffer.
+//   barrier  one group-wide barrier per site (monotonic arrival counter in global memory).
+// Windows are independent groups, so the window-parallel scheme of windows.cu applies unchanged.
+#include "sweep.cuh"
+
+namespace pbwtgpu {
+namespace {
+
+constexpr int kThreads = 1024;
+constexpr int kMaxChunk = 32768;  // sorted positions per CTA (d' staging: 128 KiB of shared memory)
+
+struct GroupSync {  // per group, in global memory
+  unsigned int arrive;         // monotonic barrier counter
+  unsigned int pad[31];
+};
+
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int &total) {
+  int x = v;
+#pragma unroll
+  for (int dl = 1; dl < 32; dl <<= 1) {
+    const int t = __shfl_up_sync(kFull, x, dl);
+    if (lane >= dl) x += t;
+  }
+  total = __shfl_sync(kFull, x, 31);
+  return x - v;
+}
+
+__device__ __forceinline__ unsigned ld_volatile(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// run-max summary: bit 31 = "contains a run head", low 31 bits = max d since the last head (or overall)
+__device__ __forceinline__ uint32_t rm_combine(uint32_t a, uint32_t b) {  // a earlier, b later
+  return (b >> 31) ? b : ((a & 0x80000000u) | max(a & 0x7fffffffu, b));
+}
+
+template <int MODE, bool WITH_D>
+__global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepArgs p, int G, int chunk, int32_t *aBuf,
+                                                                   int32_t *dBuf, uint32_t *partials, GroupSync *gsync) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int chunkWords = chunk / 32;
+  uint32_t *ycolS = smem;                                               // [chunkWords]
+  int32_t *dnS = reinterpret_cast<int32_t *>(smem + chunkWords);        // [chunk] (WITH_D)
+  __shared__ int wsumZ[32];
+  __shared__ uint32_t wsumR[32];
+  __shared__ int xZ, xC;        // zeros before this CTA, zeros in the whole column
+  __shared__ uint32_t xR;       // run-max carry entering this CTA
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int win = blockIdx.x / G, g = blockIdx.x % G;
+  const int M = p.M, wpc = p.wpc;
+  const size_t MS = (size_t)G * chunk;  // padded state stride per buffer
+  int32_t *aW = aBuf + (size_t)win * 2 * MS;
+  int32_t *dW = WITH_D ? dBuf + (size_t)win * 2 * (MS + 4) : nullptr;
+  uint32_t *part = partials + (size_t)win * G * 4;  // per CTA: zeros, rm, flag, unused
+  GroupSync *gs = gsync + win;
+
+  int k0, k1, colShift;
+  const uint32_t *src;
+  if (p.perWindowSites) {
+    k0 = p.kLabelBase; k1 = k0 + p.perWindowSites; colShift = -k0;
+    src = p.src + (size_t)win * p.srcWindowStride;
+  } else {
+    k0 = win * p.sitesPerWindow; k1 = min(p.N, k0 + p.sitesPerWindow); colShift = 0;
+    src = p.src;
+  }
+  const int p0 = g * chunk;                 // first sorted position of this CTA
+  const int EW = chunkWords / 32;           // words per warp
+  const uint32_t ltMask = lanemask_lt(lane), laneBit = 1u << lane;
+  unsigned int epoch = 0;                   // barriers passed so far
+
+  auto group_barrier = [&]() {
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(&gs->arrive, 1u);
+      const unsigned target = (epoch + 1) * (unsigned)G;
+      while (ld_volatile(&gs->arrive) < target) {}
+      __threadfence();
+    }
+    ++epoch;
+    __syncthreads();
+  };
+
+  // ---- window start state ----
+  for (int i = p0 + tid; i < p0 + chunk; i += kThreads) {
+    if (i < M) {
+      aW[i] = p.aStart ? p.aStart[(p.aStartShared ? 0 : (size_t)win * M) + i] : i;
+      if (WITH_D) dW[i] = (i > 0 && p.dStart) ? p.dStart[(size_t)win * (M + 1) + i] : 0;
+    }
+  }
+  group_barrier();
+
+  int cur = 0;
+  for (int k = k0; k < k1; ++k) {
+    const uint32_t *col = src + (size_t)(k + colShift) * wpc;
+    const int32_t *aC = aW + (size_t)cur * MS;
+    int32_t *aN = aW + (size_t)(cur ^ 1) * MS;
+    const int32_t *dC = WITH_D ? dW + (size_t)cur * (MS + 4) : nullptr;
+    int32_t *dN = WITH_D ? dW + (size_t)(cur ^ 1) * (MS + 4) : nullptr;
+
+    // ---------------- phase A ----------------
+    const int wordBase = warp * EW;          // CTA-local word index of this warp's first word
+    const int posBase = p0 + wordBase * 32;  // its first sorted position
+    uint32_t pb;                             // allele just before this warp's first position
+    if (posBase == 0 || posBase > M) pb = 2u;  // resolved at the first word: position 0 is a run head
+    else if (MODE == kGather) {
+      const int hp = __ldcg(aC + posBase - 1);
+      pb = (__ldg(col + (hp >> 5)) >> (hp & 31)) & 1u;
+    } else pb = __ldg(col + ((posBase - 1) >> 5)) >> 31;
+    int zw = 0, carry = 0, lmax = 0;
+    bool anyHead = false;
+    int patchIdx = -1;  // CTA-local index (word*32+lane) of the warp's first run head, held by that lane only
+#pragma unroll 1
+    for (int e = 0; e < EW; ++e) {
+      const int i = posBase + e * 32 + lane;
+      const bool valid = i < M;
+      uint32_t Bw;
+      if (MODE == kGather) {
+        const int h = valid ? __ldcg(aC + i) : 0;
+        Bw = __ballot_sync(kFull, valid ? (__ldg(col + (h >> 5)) >> (h & 31)) & 1u : 1u);
+      } else {
+        const int base = posBase + e * 32;
+        const uint32_t vm = (M - base >= 32) ? kFull : (M > base ? ((1u << (M - base)) - 1u) : 0u);
+        Bw = (base < M ? __ldg(col + (base >> 5)) : 0u) | ~vm;
+      }
+      if (pb == 2u) pb = (~Bw) & 1u;
+      const uint32_t H = Bw ^ ((Bw << 1) | pb);
+      pb = Bw >> 31;
+      if (lane == 0) ycolS[wordBase + e] = Bw;
+      if (WITH_D) {
+        int dv = valid ? __ldcg(dC + i) : 0;
+        if (i == 0) dv = k + 1;  // sentinel d[0] (pbwtCore.c:414,507)
+        int dnv = dv;
+        if (H == 0u) {
+          lmax = max(lmax, dv);
+        } else {
+          carry = max(carry, __reduce_max_sync(kFull, lmax));
+          lmax = 0;
+          int v = dv;
+#pragma unroll
+          for (int dl = 1; dl < 32; dl <<= 1) {
+            const int t = __shfl_up_sync(kFull, v, dl);
+            if (lane >= dl && ((H >> (lane - dl + 1)) & ((1u << dl) - 1u)) == 0u) v = max(v, t);
+          }
+          const int prev = __shfl_up_sync(kFull, v, 1);
+          const bool headBelow = (H & ltMask) != 0u;
+          const int prevMax = lane == 0 ? carry : (headBelow ? prev : max(carry, prev));
+          if (H & laneBit) dnv = max(dv, prevMax);
+          if (!anyHead) {
+            anyHead = true;
+            if (lane == __ffs(H) - 1) patchIdx = (wordBase + e) * 32 + lane;
+          }
+          carry = __shfl_sync(kFull, v, 31);
+        }
+        dnS[(wordBase + e) * 32 + lane] = dnv;
+      }
+      zw += __popc(~Bw);
+    }
+    if (WITH_D) carry = max(carry, __reduce_max_sync(kFull, lmax));
+    if (lane == 0) {
+      wsumZ[warp] = zw;
+      if (WITH_D) wsumR[warp] = (anyHead ? 0x80000000u : 0u) | (uint32_t)carry;
+    }
+    __syncthreads();
+
+    // ---------------- exchange: CTA totals out, all partials of the group in ----------------
+    int zExLane, zCta;
+    zExLane = warp_excl_scan(wsumZ[lane], lane, zCta);
+    uint32_t rInc = WITH_D ? wsumR[lane] : 0u;  // inclusive run-max scan over the CTA's warps
+    if (WITH_D) {
+#pragma unroll
+      for (int dl = 1; dl < 32; dl <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, rInc, dl);
+        if (lane >= dl) rInc = rm_combine(t, rInc);
+      }
+    }
+    if (warp == 0) {
+      const unsigned tag = (unsigned)(k - k0) + 1u;
+      const uint32_t rCta = __shfl_sync(kFull, rInc, 31);
+      if (lane == 0) {
+        part[g * 4 + 0] = (uint32_t)zCta;
+        part[g * 4 + 1] = rCta;
+        __threadfence();
+        atomicExch(&part[g * 4 + 2], tag);
+      }
+      // gather the group's partials (G <= 148 -> up to 5 per lane)
+      int zBefore = 0, zAll = 0;
+      uint32_t rBefore = 0u;  // combined summary of CTAs below g, in order
+      for (int base = 0; base < G; base += 32) {
+        const int gg = base + lane;
+        uint32_t z = 0, r = 0;
+        if (gg < G) {
+          while (ld_volatile(&part[gg * 4 + 2]) != tag) {}
+          __threadfence();
+          z = ld_volatile(&part[gg * 4 + 0]);
+          r = ld_volatile(&part[gg * 4 + 1]);
+        }
+        zAll += __reduce_add_sync(kFull, (int)z);
+        zBefore += __reduce_add_sync(kFull, gg < g ? (int)z : 0);
+        if (WITH_D) {  // ordered combine of the CTAs below g within this batch of 32
+          uint32_t x = gg < g ? r : 0u;  // identity = (no head, 0)
+#pragma unroll
+          for (int dl = 1; dl < 32; dl <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, x, dl);
+            if (lane >= dl) x = rm_combine(t, x);
+          }
+          rBefore = rm_combine(rBefore, __shfl_sync(kFull, x, 31));
+        }
+      }
+      if (lane == 0) { xZ = zBefore; xC = zAll; xR = rBefore; }
+    }
+    __syncthreads();
+    const int c = xC;
+    const int zIn = xZ + __shfl_sync(kFull, zExLane, warp);
+    int cIn = 0;
+    if (WITH_D) {  // carry entering this warp: CTAs below, then this CTA's warps below
+      const uint32_t below = __shfl_sync(kFull, rInc, warp > 0 ? warp - 1 : 0);
+      const uint32_t comb = warp > 0 ? rm_combine(xR, below) : xR;
+      cIn = (int)(comb & 0x7fffffffu);
+    }
+
+    // ---------------- phase C: scatter ----------------
+    {
+      int zacc = zIn;
+#pragma unroll 1
+      for (int e = 0; e < EW; ++e) {
+        const int li = (wordBase + e) * 32 + lane;
+        const int i = p0 + li;
+        const uint32_t Bw = ycolS[wordBase + e];
+        if (i < M) {
+          const int z = zacc + __popc(~Bw & ltMask);
+          const int pos = (Bw & laneBit) ? c + i - z : z;
+          aN[pos] = __ldcg(aC + i);
+          if (WITH_D) {
+            int dv = dnS[li];
+            if (li == patchIdx) dv = max(dv, cIn);
+            dN[pos] = dv;
+          }
+        }
+        zacc += __popc(~Bw);
+      }
+    }
+    if (p.yOut) {  // sorted column k, pad bits cleared
+      for (int w = tid; w < chunkWords; w += kThreads) {
+        const int gw = p0 / 32 + w;
+        if (gw < wpc) {
+          const int base = gw * 32;
+          const uint32_t vm = (M - base >= 32) ? kFull : (M > base ? ((1u << (M - base)) - 1u) : 0u);
+          p.yOut[(size_t)(k + colShift) * wpc + gw] = ycolS[w] & vm;
+        }
+      }
+    }
+    if (p.cOut && g == 0 && tid == 0) p.cOut[k + colShift] = c;
+    group_barrier();
+    cur ^= 1;
+  }
+
+  // ---- window end ----
+  const bool writeEnd = !p.endOnlyLast || k1 == p.N;
+  const size_t endSlot = p.endOnlyLast ? 0 : (size_t)win;
+  const int32_t *aC = aW + (size_t)cur * MS;
+  if (p.aEnd && writeEnd)
+    for (int i = p0 + tid; i < min(M, p0 + chunk); i += kThreads) p.aEnd[endSlot * M + i] = __ldcg(aC + i);
+  if (WITH_D && p.dEnd && writeEnd) {
+    const int32_t *dC = dW + (size_t)cur * (MS + 4);
+    for (int i = p0 + tid; i < min(M, p0 + chunk); i += kThreads)
+      p.dEnd[endSlot * (M + 1) + i] = i == 0 ? k1 + 1 : __ldcg(dC + i);
+    if (g == 0 && tid == 0) p.dEnd[endSlot * (M + 1) + M] = k1 + 1;
+  }
+}
+
+}  // namespace
+
+// Plan: G CTAs per window (positions per CTA <= kMaxChunk, multiple of 1024), W windows with W*G <= maxCtas.
+void sweep_global_plan(int M, int maxCtas, int wantWindows, int *G, int *chunk, int *W) {
+  const int gmin = (M + kMaxChunk - 1) / kMaxChunk;
+  int w = wantWindows > 0 ? wantWindows : 1;
+  if (w * gmin > maxCtas) w = maxCtas / gmin;
+  if (w < 1) w = 1;
+  int g = maxCtas / w;  // use every SM: more CTAs per window shorten the per-site critical path
+  if (g < gmin) g = gmin;
+  int ch = ((M + g - 1) / g + 1023) / 1024 * 1024;
+  if (ch > kMaxChunk) ch = kMaxChunk;
+  g = (M + ch - 1) / ch;
+  *G = g; *chunk = ch; *W = w;
+}
+
+size_t sweep_global_state_ints(int G, int chunk, int W, bool with_d) {
+  const size_t MS = (size_t)G * chunk;
+  return (size_t)W * 2 * MS + (with_d ? (size_t)W * 2 * (MS + 4) : 0);
+}
+
+int launch_sweep_global(const SweepArgs &a, SweepMode mode, bool with_d, int G, int chunk, int32_t *aBuf, int32_t *dBuf,
+                        uint32_t *partials, void *gsync, cudaStream_t stream) {
+  const size_t smemBytes = (size_t)(chunk / 32) * 4 + (with_d ? (size_t)chunk * 4 : 0);
+  void *kern;
+  if (mode == kGather) kern = with_d ? (void *)sweep_global_kernel<kGather, true> : (void *)sweep_global_kernel<kGather, false>;
+  else kern = with_d ? (void *)sweep_global_kernel<kSorted, true> : (void *)sweep_global_kernel<kSorted, false>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+  if (err != cudaSuccess) return (int)err;
+  SweepArgs args = a;
+  GroupSync *gs = static_cast<GroupSync *>(gsync);
+  void *params[] = {&args, &G, &chunk, &aBuf, &dBuf, &partials, &gs};
+  err = cudaLaunchCooperativeKernel(kern, dim3(a.nWindows * G), dim3(kThreads), params, smemBytes, stream);
+  return (int)err;
+}
+
+size_t sweep_global_sync_bytes(int W) { return sizeof(GroupSync) * (size_t)W; }
+
+}  // namespace pbwtgpu

@@ -257,3 +257,37 @@ def test_query_sweep_mosaic(eng, orc):
     want_rec, want_nom = orc.match_sweep(pyz, M, N, qyz, Q)
     rec, nom = eng.match_sweep(pyz, M, N, qyz, Q)
     assert len(rec) == len(want_rec) and (rec == want_rec).all() and (nom == want_nom).all()
+
+
+@pytest.mark.parametrize("M,N,W,dens", [(8, 10, 1, 0.3), (33, 40, 3, 0.5), (1000, 60, 1, 0.2), (3000, 200, 5, 0.05),
+                                        (5000, 64, 37, 0.3), (2752, 38, 2, 0.3)])
+def test_global_memory_kernel_forced(eng, orc, M, N, W, dens):
+    """The wide-panel kernel (state in global memory, cooperating CTA groups) forced onto narrow panels,
+    with and without window parallelism: same bits as the reference sweep."""
+    rng = np.random.default_rng(M * 3 + N)
+    hap = (rng.random((M, N)) < dens).astype(np.uint8)
+    hap[: M // 4] = hap[0]
+    x = O.pack_panel(hap)
+    a0 = rng.permutation(M).astype(np.int32)
+    eng.set_option("force_global", 1)
+    eng.set_option("windows", W)
+    try:
+        check_build(eng, orc, x, M, N, matches=False)
+        check_build(eng, orc, x, M, N, a_start=a0, matches=False)
+    finally:
+        eng.set_option("force_global", 0)
+        eng.set_option("windows", 0)
+
+
+@pytest.mark.parametrize("M,N,dens", [(13313, 20, 0.3), (40000, 30, 0.02), (70003, 12, 0.4), (200003, 6, 0.1)])
+def test_wide_panels(eng, orc, M, N, dens):
+    """M beyond the shared-memory limit (BASELINE configs 3-5 are 1e5..1e6 haplotypes)."""
+    rng = np.random.default_rng(M)
+    hap = (rng.random((M, N)) < dens).astype(np.uint8)
+    check_build(eng, orc, O.pack_panel(hap), M, N, matches=False)
+
+
+def test_wide_panel_windowed_mosaic(eng, orc):
+    M, N = 30000, 1200
+    x = O.generate_panel(M, N, seed=0x5EED0003, L=300, mu=4.0)
+    check_build(eng, orc, x, M, N, matches=False)
