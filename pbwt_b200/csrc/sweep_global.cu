@@ -21,6 +21,7 @@ namespace {
 
 constexpr int kThreads = 1024;
 constexpr int kMaxChunk = 32768;  // sorted positions per CTA (d' staging: 128 KiB of shared memory)
+constexpr int kBatch = 8;         // words per warp whose global loads are issued back to back
 
 struct GroupSync {  // per group, in global memory
   unsigned int arrive;         // monotonic barrier counter
@@ -126,51 +127,69 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     int zw = 0, carry = 0, lmax = 0;
     bool anyHead = false;
     int patchIdx = -1;  // CTA-local index (word*32+lane) of the warp's first run head, held by that lane only
-#pragma unroll 1
-    for (int e = 0; e < EW; ++e) {
-      const int i = posBase + e * 32 + lane;
-      const bool valid = i < M;
-      uint32_t Bw;
-      if (MODE == kGather) {
-        const int h = valid ? __ldcg(aC + i) : 0;
-        Bw = __ballot_sync(kFull, valid ? (__ldg(col + (h >> 5)) >> (h & 31)) & 1u : 1u);
-      } else {
-        const int base = posBase + e * 32;
-        const uint32_t vm = (M - base >= 32) ? kFull : (M > base ? ((1u << (M - base)) - 1u) : 0u);
-        Bw = (base < M ? __ldg(col + (base >> 5)) : 0u) | ~vm;
-      }
-      if (pb == 2u) pb = (~Bw) & 1u;
-      const uint32_t H = Bw ^ ((Bw << 1) | pb);
-      pb = Bw >> 31;
-      if (lane == 0) ycolS[wordBase + e] = Bw;
-      if (WITH_D) {
-        int dv = valid ? __ldcg(dC + i) : 0;
-        if (i == 0) dv = k + 1;  // sentinel d[0] (pbwtCore.c:414,507)
-        int dnv = dv;
-        if (H == 0u) {
-          lmax = max(lmax, dv);
-        } else {
-          carry = max(carry, __reduce_max_sync(kFull, lmax));
-          lmax = 0;
-          int v = dv;
+    for (int e0 = 0; e0 < EW; e0 += kBatch) {  // kBatch words in flight per warp: the loads are L2 round trips
+      int hB[kBatch], dB[kBatch];
+      uint32_t cB[kBatch];
 #pragma unroll
-          for (int dl = 1; dl < 32; dl <<= 1) {
-            const int t = __shfl_up_sync(kFull, v, dl);
-            if (lane >= dl && ((H >> (lane - dl + 1)) & ((1u << dl) - 1u)) == 0u) v = max(v, t);
-          }
-          const int prev = __shfl_up_sync(kFull, v, 1);
-          const bool headBelow = (H & ltMask) != 0u;
-          const int prevMax = lane == 0 ? carry : (headBelow ? prev : max(carry, prev));
-          if (H & laneBit) dnv = max(dv, prevMax);
-          if (!anyHead) {
-            anyHead = true;
-            if (lane == __ffs(H) - 1) patchIdx = (wordBase + e) * 32 + lane;
-          }
-          carry = __shfl_sync(kFull, v, 31);
-        }
-        dnS[(wordBase + e) * 32 + lane] = dnv;
+      for (int u = 0; u < kBatch; ++u) {
+        const int i = posBase + (e0 + u) * 32 + lane;
+        const bool valid = e0 + u < EW && i < M;
+        hB[u] = (MODE == kGather && valid) ? __ldcg(aC + i) : 0;
+        dB[u] = (WITH_D && valid) ? __ldcg(dC + i) : 0;
       }
-      zw += __popc(~Bw);
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int base = posBase + (e0 + u) * 32;
+        const bool valid = e0 + u < EW && base + lane < M;
+        if (MODE == kGather) cB[u] = valid ? __ldg(col + (hB[u] >> 5)) : kFull;
+        else cB[u] = (e0 + u < EW && base < M) ? __ldg(col + (base >> 5)) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int e = e0 + u;
+        if (e >= EW) break;
+        const int i = posBase + e * 32 + lane;
+        uint32_t Bw;
+        if (MODE == kGather) {
+          Bw = __ballot_sync(kFull, (cB[u] >> (hB[u] & 31)) & 1u);
+        } else {
+          const int base = posBase + e * 32;
+          const uint32_t vm = (M - base >= 32) ? kFull : (M > base ? ((1u << (M - base)) - 1u) : 0u);
+          Bw = cB[u] | ~vm;
+        }
+        if (pb == 2u) pb = (~Bw) & 1u;
+        const uint32_t H = Bw ^ ((Bw << 1) | pb);
+        pb = Bw >> 31;
+        if (lane == 0) ycolS[wordBase + e] = Bw;
+        if (WITH_D) {
+          int dv = dB[u];
+          if (i == 0) dv = k + 1;  // sentinel d[0] (pbwtCore.c:414,507)
+          int dnv = dv;
+          if (H == 0u) {
+            lmax = max(lmax, dv);
+          } else {
+            carry = max(carry, __reduce_max_sync(kFull, lmax));
+            lmax = 0;
+            int v = dv;
+#pragma unroll
+            for (int dl = 1; dl < 32; dl <<= 1) {
+              const int t = __shfl_up_sync(kFull, v, dl);
+              if (lane >= dl && ((H >> (lane - dl + 1)) & ((1u << dl) - 1u)) == 0u) v = max(v, t);
+            }
+            const int prev = __shfl_up_sync(kFull, v, 1);
+            const bool headBelow = (H & ltMask) != 0u;
+            const int prevMax = lane == 0 ? carry : (headBelow ? prev : max(carry, prev));
+            if (H & laneBit) dnv = max(dv, prevMax);
+            if (!anyHead) {
+              anyHead = true;
+              if (lane == __ffs(H) - 1) patchIdx = (wordBase + e) * 32 + lane;
+            }
+            carry = __shfl_sync(kFull, v, 31);
+          }
+          dnS[(wordBase + e) * 32 + lane] = dnv;
+        }
+        zw += __popc(~Bw);
+      }
     }
     if (WITH_D) carry = max(carry, __reduce_max_sync(kFull, lmax));
     if (lane == 0) {
@@ -238,22 +257,32 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     // ---------------- phase C: scatter ----------------
     {
       int zacc = zIn;
-#pragma unroll 1
-      for (int e = 0; e < EW; ++e) {
-        const int li = (wordBase + e) * 32 + lane;
-        const int i = p0 + li;
-        const uint32_t Bw = ycolS[wordBase + e];
-        if (i < M) {
-          const int z = zacc + __popc(~Bw & ltMask);
-          const int pos = (Bw & laneBit) ? c + i - z : z;
-          aN[pos] = __ldcg(aC + i);
-          if (WITH_D) {
-            int dv = dnS[li];
-            if (li == patchIdx) dv = max(dv, cIn);
-            dN[pos] = dv;
-          }
+      for (int e0 = 0; e0 < EW; e0 += kBatch) {
+        int hB[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int i = p0 + (wordBase + e0 + u) * 32 + lane;
+          hB[u] = (e0 + u < EW && i < M) ? __ldcg(aC + i) : 0;
         }
-        zacc += __popc(~Bw);
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int e = e0 + u;
+          if (e >= EW) break;
+          const int li = (wordBase + e) * 32 + lane;
+          const int i = p0 + li;
+          const uint32_t Bw = ycolS[wordBase + e];
+          if (i < M) {
+            const int z = zacc + __popc(~Bw & ltMask);
+            const int pos = (Bw & laneBit) ? c + i - z : z;
+            aN[pos] = hB[u];
+            if (WITH_D) {
+              int dv = dnS[li];
+              if (li == patchIdx) dv = max(dv, cIn);
+              dN[pos] = dv;
+            }
+          }
+          zacc += __popc(~Bw);
+        }
       }
     }
     if (p.yOut) {  // sorted column k, pad bits cleared
