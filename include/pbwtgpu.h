@@ -78,6 +78,9 @@ int pbwtgpu_panel_from_host(pbwtgpu_ctx *ctx, const uint32_t *xbits, int M, int 
  * oracle/pbwt_oracle.c:orc_generate). flip_thresh = P(flip) * 2^32. */
 int pbwtgpu_panel_synthetic(pbwtgpu_ctx *ctx, int M, int N, uint64_t seed, uint32_t L, uint32_t flip_thresh,
                             pbwtgpu_panel **panel);
+/* Columns first_site .. first_site+N-1 of the same synthetic panel (a site shard for one GPU). */
+int pbwtgpu_panel_synthetic_range(pbwtgpu_ctx *ctx, int M, int N, int first_site, uint64_t seed, uint32_t L,
+                                  uint32_t flip_thresh, pbwtgpu_panel **panel);
 int pbwtgpu_panel_to_host(pbwtgpu_ctx *ctx, const pbwtgpu_panel *panel, int first_site, int nsites, uint32_t *xbits);
 void pbwtgpu_panel_free(pbwtgpu_ctx *ctx, pbwtgpu_panel *panel);
 
@@ -99,6 +102,27 @@ int pbwtgpu_result_sizes(const pbwtgpu_result *result, int64_t *nyz, int64_t *nm
 int pbwtgpu_result_fetch(pbwtgpu_ctx *ctx, const pbwtgpu_result *result, uint8_t *yz, int32_t *a_end, int32_t *d_end,
                          pbwtgpu_match *matches);
 void pbwtgpu_result_free(pbwtgpu_ctx *ctx, pbwtgpu_result *result);
+
+/* ---- multi-GPU: the SITES of one panel are partitioned across GPUs (one process per GPU) ---------------
+ * Each GPU holds the columns [site_offset, site_offset + panel->N) of a panel of total_sites sites.
+ *   1. pbwtgpu_shard_prepare: sweeps the local windows on their own and reduces them to the shard's aggregate
+ *      node (its sort order and divergence relative to the panel's start order, with tie groups).
+ *   2. the caller all-gathers the aggregates of all shards, in site order, into one DEVICE buffer
+ *      (pbwtgpu_shard_aggregate_ints(M) int32 per shard; bench.py uses torch.distributed/NCCL over NVLink);
+ *      this is the path's only exchange step.
+ *   3. pbwtgpu_shard_finish: combines the aggregates of the earlier shards into the exact (a, d) entering this
+ *      shard and sweeps the local windows from their exact start states.  Site labels in d and in match
+ *      records are global.  a_end / d_end are only produced by the shard that ends at total_sites
+ *      (others are filled with -1); pack3 streams and match records concatenate across shards in site order.
+ * dev_dst / dev_aggs are device pointers on ctx's GPU. */
+typedef struct pbwtgpu_shard pbwtgpu_shard;
+size_t pbwtgpu_shard_aggregate_ints(int M);
+int pbwtgpu_shard_prepare(pbwtgpu_ctx *ctx, const pbwtgpu_panel *panel, const int32_t *a_start, int site_offset,
+                          int total_sites, unsigned flags, pbwtgpu_shard **shard);
+int pbwtgpu_shard_export(pbwtgpu_ctx *ctx, pbwtgpu_shard *shard, int32_t *dev_dst);
+int pbwtgpu_shard_finish(pbwtgpu_ctx *ctx, pbwtgpu_shard *shard, const int32_t *dev_aggs, int rank, unsigned flags,
+                         pbwtgpu_result **result);
+void pbwtgpu_shard_free(pbwtgpu_ctx *ctx, pbwtgpu_shard *shard);
 
 /* ---- one-shot host-buffer entry points (what the host shim calls) --------------------------- */
 /* H2D of the columns, sweep, D2H.  *yz and *matches are malloc()'d (free with pbwtgpu_free or

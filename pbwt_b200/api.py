@@ -59,6 +59,14 @@ def load_library() -> C.CDLL:
         lib.pbwtgpu_last_timings.argtypes = [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         lib.pbwtgpu_panel_from_host.argtypes = [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]
         lib.pbwtgpu_panel_synthetic.argtypes = [_vp, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(_vp)]
+        lib.pbwtgpu_panel_synthetic_range.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(_vp)]
+        lib.pbwtgpu_shard_aggregate_ints.restype = C.c_size_t
+        lib.pbwtgpu_shard_aggregate_ints.argtypes = [C.c_int]
+        lib.pbwtgpu_shard_prepare.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_uint, C.POINTER(_vp)]
+        lib.pbwtgpu_shard_export.argtypes = [_vp, _vp, _vp]
+        lib.pbwtgpu_shard_finish.argtypes = [_vp, _vp, _vp, C.c_int, C.c_uint, C.POINTER(_vp)]
+        lib.pbwtgpu_shard_free.argtypes = [_vp, _vp]
+        lib.pbwtgpu_shard_free.restype = None
         lib.pbwtgpu_panel_to_host.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp]
         lib.pbwtgpu_panel_free.argtypes = [_vp, _vp]
         lib.pbwtgpu_panel_free.restype = None
@@ -148,6 +156,27 @@ class Result:
             self.handle = None
 
 
+class Shard:
+    """One GPU's site range of a longer panel (see include/pbwtgpu.h, multi-GPU section)."""
+
+    def __init__(self, eng: "Engine", handle: _vp, M: int, N: int):
+        self.eng, self.handle, self.M, self.N = eng, handle, M, N
+
+    def export(self, dev_ptr: int):
+        """Copy this shard's aggregate node into device memory at dev_ptr (e.g. a torch tensor's data_ptr())."""
+        self.eng._check(self.eng.lib.pbwtgpu_shard_export(self.eng.ctx, self.handle, dev_ptr))
+
+    def finish(self, dev_aggs_ptr, rank: int, flags: int) -> Result:
+        h = _vp()
+        self.eng._check(self.eng.lib.pbwtgpu_shard_finish(self.eng.ctx, self.handle, dev_aggs_ptr, rank, flags, C.byref(h)))
+        return Result(self.eng, h, self.M, self.N, flags)
+
+    def free(self):
+        if self.handle:
+            self.eng.lib.pbwtgpu_shard_free(self.eng.ctx, self.handle)
+            self.handle = None
+
+
 class Engine:
     """One per GPU.  Raises PbwtGpuError if the CUDA library or an sm_100 device is unavailable."""
 
@@ -207,11 +236,21 @@ class Engine:
         self.synchronize()
         return Panel(self, h, M, N)
 
-    def panel_synthetic(self, M: int, N: int, seed: int, L: int = 2000, mu: float = 2.0) -> Panel:
+    def panel_synthetic(self, M: int, N: int, seed: int, L: int = 2000, mu: float = 2.0, first_site: int = 0) -> Panel:
         thresh = min(int(mu / M * 2**32), 2**32 - 1)
         h = _vp()
-        self._check(self.lib.pbwtgpu_panel_synthetic(self.ctx, M, N, C.c_uint64(seed), L, thresh, C.byref(h)))
+        self._check(self.lib.pbwtgpu_panel_synthetic_range(self.ctx, M, N, first_site, C.c_uint64(seed), L, thresh, C.byref(h)))
         return Panel(self, h, M, N)
+
+    # ---- multi-GPU site shards -----------------------------------------------------------
+    def shard_aggregate_ints(self, M: int) -> int:
+        return int(self.lib.pbwtgpu_shard_aggregate_ints(M))
+
+    def shard_prepare(self, panel: Panel, site_offset: int, total_sites: int, flags: int, a_start=None) -> "Shard":
+        a0 = None if a_start is None else np.ascontiguousarray(a_start, np.int32)
+        h = _vp()
+        self._check(self.lib.pbwtgpu_shard_prepare(self.ctx, panel.handle, _ptr(a0), site_offset, total_sites, flags, C.byref(h)))
+        return Shard(self, h, panel.M, panel.N)
 
     # ---- device-resident sweeps ----------------------------------------------------------
     def build_device(self, panel: Panel, flags: int, a_start=None) -> Result:

@@ -178,103 +178,140 @@ void reset_timings(pbwtgpu_ctx *ctx) {
   memset(ctx->launches, 0, sizeof ctx->launches);
 }
 
-// ---- the sweep driver shared by build (gather mode) and stored-stream sweeps (sorted mode) ----
+// ---- the sweep driver shared by build (gather mode), stored-stream sweeps (sorted mode) and shards ----
 //
-// Windowed execution (gather mode, M within the divergence kernel's limit, enough sites): the N sites are cut
-// into W windows, one per SM.  Pass 1 sweeps every window on its own from the panel's start order; a
-// Hillis-Steele scan of window combines (windows.cu) turns those into the exact (a, d) at every window
-// boundary; pass 2 sweeps all windows concurrently from their exact start states and produces the outputs.
-int run_sweep(pbwtgpu_ctx *ctx, const uint32_t *src, int wpc, int M, int N, SweepMode mode, const int32_t *aStartHost,
-              unsigned flags, pbwtgpu_result *res) {
-  const bool wantMatch = flags & PBWTGPU_WANT_MAXWITHIN;
-  const bool wantD = wantMatch || (flags & PBWTGPU_WANT_D);
-  const bool wantYz = (flags & PBWTGPU_WANT_YZ) && mode == kGather;
-  if (M < 1 || N < 0) return fail(ctx, PBWTGPU_ERR_ARG, "bad panel shape M=%d N=%d", M, N);
-  if (N >= kPseudoLabelBase - 64) return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "N=%d too large", N);
-  // panels wider than one CTA's shared memory sweep with their state in global memory (sweep_global.cu)
-  const bool useGlobal = M > sweep_smem_max_m(true) || ctx->optForceGlobal;
-  if (useGlobal && wantMatch)
-    return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "maxWithin needs M <= %d (shared-memory kernel); M=%d", sweep_smem_max_m(true), M);
-  Temps tmp(ctx);
-  res->M = M;
-  res->N = N;
-
-  // ---- window plan ----
-  int W = 1, G = 1, chunk = 0;
-  if (mode == kGather && M >= 2) {
-    const long long want = ctx->optWindows > 0 ? ctx->optWindows : ctx->smCount;
-    const int minSites = ctx->optWindows > 0 ? 1 : 256;  // below this a window does not repay its two extra passes
-    W = (int)std::max<long long>(1, std::min<long long>(want, N / minSites));
-  }
-  if (useGlobal) sweep_global_plan(M, ctx->smCount, W, &G, &chunk, &W);
-  int spw = N > 0 ? (N + W - 1) / W : 1;
-  W = N > 0 ? (N + spw - 1) / spw : 1;
-  const int nodes = W - 1;
-
-  // the two kernels behind one launcher
+// Windowed execution (gather mode, enough sites): the sites are cut into W windows, one per SM (or per group
+// of SMs for wide panels).  prepare(): pass 1 sweeps every window on its own from the panel's start order,
+// then a Hillis-Steele scan of window combines (windows.cu) turns those into the exact (a, d) at every window
+// boundary.  finish(): pass 2 sweeps all windows concurrently from their exact start states and produces the
+// outputs.  A shard of a longer panel (multi-GPU: sites are partitioned across GPUs) additionally exports the
+// aggregate node of its whole site range and applies the combined aggregate of all earlier shards before pass 2.
+struct WindowedSweep {
+  pbwtgpu_ctx *ctx;
+  Temps tmp;
+  const uint32_t *src = nullptr;
+  int wpc = 0, M = 0, N = 0;
+  SweepMode mode = kGather;
+  int siteOffset = 0, nTotal = 0;
+  bool sharded = false;
+  bool useGlobal = false;
+  int W = 1, G = 1, chunk = 0, spw = 1, nodes = 0, bits = 1, slots = 1, cur = 0;
   int32_t *gA = nullptr, *gD = nullptr;
   uint32_t *gPart = nullptr;
   void *gSync = nullptr;
-  if (useGlobal) {
-    const size_t MS = (size_t)G * chunk;
-    if (int rc = tmp.get(&gA, (size_t)W * 2 * MS)) return rc;
-    if (int rc = tmp.get(&gD, (size_t)W * 2 * (MS + 4))) return rc;
-    if (int rc = tmp.get(&gPart, (size_t)W * G * 4)) return rc;
-    char *sy = nullptr;
-    if (int rc = tmp.get(&sy, sweep_global_sync_bytes(W))) return rc;
-    gSync = sy;
-  }
-  auto launch = [&](const SweepArgs &args, SweepMode md, bool withD, bool withMatch) -> int {
+  // slot 0 = state entering window 0, slot w+1 = node w (after the scan: the state at the end of window w)
+  int32_t *ord[2] = {nullptr, nullptr}, *dv[2] = {nullptr, nullptr}, *g[2] = {nullptr, nullptr}, *gfd[2] = {nullptr, nullptr};
+  uint32_t *keys = nullptr;
+  bool haveDStart = false;
+
+  explicit WindowedSweep(pbwtgpu_ctx *c) : ctx(c), tmp(c) {}
+  size_t oA() const { return (size_t)M; }
+  size_t oD() const { return (size_t)M + 1; }
+
+  int launch(const SweepArgs &args, SweepMode md, bool withD, bool withMatch) {
     if (!useGlobal) return launch_sweep_smem(args, md, withD, withMatch, ctx->stream);
-    cudaError_t e = cudaMemsetAsync(gPart, 0, sizeof(uint32_t) * (size_t)W * G * 4, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(gSync, 0, sweep_global_sync_bytes(W), ctx->stream);
+    const int wl = std::max(W, 1);
+    cudaError_t e = cudaMemsetAsync(gPart, 0, sizeof(uint32_t) * (size_t)wl * G * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(gSync, 0, sweep_global_sync_bytes(wl), ctx->stream);
     if (e != cudaSuccess) return (int)e;
     return launch_sweep_global(args, md, withD, G, chunk, gA, gD, gPart, gSync, ctx->stream);
-  };
-
-  if (int rc = result_alloc(ctx, res, &res->aEnd, (size_t)M)) return rc;
-  if (wantD)
-    if (int rc = result_alloc(ctx, res, &res->dEnd, (size_t)M + 1)) return rc;
-  uint32_t *yOut = nullptr;
-  if (wantYz && N > 0)
-    if (int rc = tmp.get(&yOut, (size_t)N * wpc)) return rc;
-
-  // ---- start states: slot 0 = the panel's start order, slot w = state entering window w ----
-  int32_t *ord[2] = {nullptr, nullptr}, *dv[2] = {nullptr, nullptr};
-  if (int rc = tmp.get(&ord[0], (size_t)W * M)) return rc;
-  {
-    std::vector<int32_t> ident;
-    const int32_t *h = aStartHost;
-    if (!h) {
-      ident.resize(M);
-      for (int i = 0; i < M; ++i) ident[i] = i;
-      h = ident.data();
-    }
-    CUDA_TRY(ctx, cudaMemcpyAsync(ord[0], h, sizeof(int32_t) * M, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // ident goes out of scope
   }
-  int cur = 0;
-  if (nodes > 0) {
-    int bits = 1;
-    while ((1 << bits) < M) ++bits;
-    int32_t *g[2], *gfd[2];
-    uint32_t *keys = nullptr;
-    if (int rc = tmp.get(&ord[1], (size_t)W * M)) return rc;
-    for (int b = 0; b < 2; ++b) {
-      if (int rc = tmp.get(&dv[b], (size_t)W * (M + 1))) return rc;
-      if (int rc = tmp.get(&g[b], (size_t)W * M)) return rc;
-      if (int rc = tmp.get(&gfd[b], (size_t)W * M)) return rc;
-      CUDA_TRY(ctx, cudaMemsetAsync(dv[b], 0, sizeof(int32_t) * (M + 1), ctx->stream));  // slot 0: fresh cursor
-    }
-    CUDA_TRY(ctx, cudaMemcpyAsync(ord[1], ord[0], sizeof(int32_t) * M, cudaMemcpyDeviceToDevice, ctx->stream));
-    if (int rc = tmp.get(&keys, (size_t)nodes * bits * wpc)) return rc;
-    const size_t oA = M, oD = (size_t)M + 1;  // slot strides
 
-    // pass 1: every window but the last, on its own, from the start order
+  int init(const uint32_t *src_, int wpc_, int M_, int N_, SweepMode mode_, const int32_t *aStartHost, bool wantMatch,
+           bool sharded_, int siteOffset_, int nTotal_) {
+    src = src_; wpc = wpc_; M = M_; N = N_; mode = mode_; sharded = sharded_;
+    siteOffset = siteOffset_; nTotal = nTotal_ > 0 ? nTotal_ : N_;
+    if (M < 1 || N < 0) return fail(ctx, PBWTGPU_ERR_ARG, "bad panel shape M=%d N=%d", M, N);
+    if (nTotal >= kPseudoLabelBase - 64) return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "N=%d too large", nTotal);
+    // panels wider than one CTA's shared memory sweep with their state in global memory (sweep_global.cu)
+    useGlobal = M > sweep_smem_max_m(true) || ctx->optForceGlobal;
+    if (useGlobal && wantMatch)
+      return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "maxWithin needs M <= %d (shared-memory kernel); M=%d", sweep_smem_max_m(true), M);
+    W = 1;
+    if (mode == kGather && M >= 2) {
+      const long long want = ctx->optWindows > 0 ? ctx->optWindows : ctx->smCount;
+      const int minSites = ctx->optWindows > 0 ? 1 : 256;  // below this a window does not repay its two extra passes
+      W = (int)std::max<long long>(1, std::min<long long>(want, N / minSites));
+    }
+    if (useGlobal) sweep_global_plan(M, ctx->smCount, W, &G, &chunk, &W);
+    spw = N > 0 ? (N + W - 1) / W : 1;
+    W = N > 0 ? (N + spw - 1) / spw : 1;
+    nodes = sharded ? W : W - 1;  // a shard also needs the node of its last window (its aggregate)
+    slots = nodes + 1;
+    bits = 1;
+    while ((1 << bits) < M) ++bits;
+    if (useGlobal) {
+      const size_t MS = (size_t)G * chunk;
+      if (int rc = tmp.get(&gA, (size_t)W * 2 * MS)) return rc;
+      if (int rc = tmp.get(&gD, (size_t)W * 2 * (MS + 4))) return rc;
+      if (int rc = tmp.get(&gPart, (size_t)W * G * 4)) return rc;
+      char *sy = nullptr;
+      if (int rc = tmp.get(&sy, sweep_global_sync_bytes(W))) return rc;
+      gSync = sy;
+    }
+    const bool needNodes = nodes > 0;
+    for (int b = 0; b < (needNodes ? 2 : 1); ++b) {
+      if (int rc = tmp.get(&ord[b], (size_t)slots * M)) return rc;
+      if (needNodes) {
+        if (int rc = tmp.get(&dv[b], (size_t)slots * (M + 1))) return rc;
+        if (int rc = tmp.get(&g[b], (size_t)slots * M)) return rc;
+        if (int rc = tmp.get(&gfd[b], (size_t)slots * M)) return rc;
+        CUDA_TRY(ctx, cudaMemsetAsync(dv[b], 0, sizeof(int32_t) * (M + 1), ctx->stream));  // slot 0: fresh cursor
+      }
+    }
+    if (needNodes)
+      if (int rc = tmp.get(&keys, (size_t)std::max(nodes, 1) * bits * wpc)) return rc;
+    {  // slot 0: the panel's start order
+      std::vector<int32_t> ident;
+      const int32_t *h = aStartHost;
+      if (!h) {
+        ident.resize(M);
+        for (int i = 0; i < M; ++i) ident[i] = i;
+        h = ident.data();
+      }
+      CUDA_TRY(ctx, cudaMemcpyAsync(ord[0], h, sizeof(int32_t) * M, cudaMemcpyHostToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // ident goes out of scope
+      if (needNodes) CUDA_TRY(ctx, cudaMemcpyAsync(ord[1], ord[0], sizeof(int32_t) * M, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return 0;
+  }
+
+  // out[i] = I[i] (+) J[i] for cnt nodes (I earlier, J later); I is one node for all when sharedI
+  int combine(int cnt, const int32_t *ordI, const int32_t *dvI, bool sharedI, const int32_t *gJ, const int32_t *gfdJ,
+              int32_t *ordOut, int32_t *dvOut, int32_t *gOut, int32_t *gfdOut) {
+    if (cnt <= 0) return 0;
+    {
+      ScopedTimer t(ctx, PBWTGPU_K_AUX);
+      CUDA_TRY(ctx, launch_key_bits(gJ, M, cnt, bits, wpc, keys, ctx->stream));
+      ctx->launches[PBWTGPU_K_AUX] += 1;
+    }
+    SweepArgs c{};
+    c.src = keys; c.wpc = wpc; c.M = M; c.N = N; c.nWindows = cnt;
+    c.perWindowSites = bits; c.srcWindowStride = (long long)bits * wpc; c.kLabelBase = kPseudoLabelBase;
+    c.aStart = ordI; c.dStart = dvI; c.aStartShared = sharedI; c.dStartShared = sharedI;
+    c.aEnd = ordOut; c.dEnd = dvOut;
+    {
+      ScopedTimer t(ctx, PBWTGPU_K_COMBINE);
+      CUDA_TRY(ctx, launch(c, kGather, true, false));
+      ctx->launches[PBWTGPU_K_COMBINE] += 1;
+    }
+    {
+      ScopedTimer t(ctx, PBWTGPU_K_AUX);
+      CUDA_TRY(ctx, launch_make_groups(ordOut, dvOut, gJ, gfdJ, gOut, gfdOut, M, cnt, ctx->stream));
+      ctx->launches[PBWTGPU_K_AUX] += 1;
+    }
+    return 0;
+  }
+
+  // pass 1 + tie groups + inclusive scan: afterwards slot w+1 holds the exact state at the end of window w
+  // (relative to the start order in slot 0)
+  int prepare() {
+    if (nodes <= 0) return 0;
     SweepArgs a1{};
     a1.src = src; a1.wpc = wpc; a1.M = M; a1.N = N; a1.sitesPerWindow = spw; a1.nWindows = nodes;
+    a1.siteOffset = siteOffset; a1.nTotal = nTotal;
     a1.aStart = ord[0]; a1.aStartShared = 1;
-    a1.aEnd = ord[0] + oA; a1.dEnd = dv[0] + oD;
+    a1.aEnd = ord[0] + oA(); a1.dEnd = dv[0] + oD();
     {
       ScopedTimer t(ctx, PBWTGPU_K_PREPASS);
       CUDA_TRY(ctx, launch(a1, kGather, true, false));
@@ -282,145 +319,197 @@ int run_sweep(pbwtgpu_ctx *ctx, const uint32_t *src, int wpc, int M, int N, Swee
     }
     {
       ScopedTimer t(ctx, PBWTGPU_K_AUX);
-      CUDA_TRY(ctx, launch_make_groups(ord[0] + oA, dv[0] + oD, nullptr, nullptr, g[0] + oA, gfd[0] + oA, M, nodes, ctx->stream));
+      CUDA_TRY(ctx, launch_make_groups(ord[0] + oA(), dv[0] + oD(), nullptr, nullptr, g[0] + oA(), gfd[0] + oA(), M, nodes, ctx->stream));
       ctx->launches[PBWTGPU_K_AUX] += 1;
     }
-    // inclusive scan of window combines: node w (slot w+1) becomes the state at boundary w+1
+    cur = 0;
     for (int stride = 1; stride < nodes; stride *= 2) {
       const int nxt = cur ^ 1, cnt = nodes - stride;
       const size_t s1 = (size_t)(1 + stride);  // first slot that changes this round
-      {
-        ScopedTimer t(ctx, PBWTGPU_K_AUX);
-        CUDA_TRY(ctx, launch_key_bits(g[cur] + s1 * oA, M, cnt, bits, wpc, keys, ctx->stream));
-        ctx->launches[PBWTGPU_K_AUX] += 1;
-      }
-      SweepArgs c{};
-      c.src = keys; c.wpc = wpc; c.M = M; c.N = N; c.nWindows = cnt;
-      c.perWindowSites = bits; c.srcWindowStride = (long long)bits * wpc; c.kLabelBase = kPseudoLabelBase;
-      c.aStart = ord[cur] + oA; c.dStart = dv[cur] + oD;  // earlier part: node i (slot i+1)
-      c.aEnd = ord[nxt] + s1 * oA; c.dEnd = dv[nxt] + s1 * oD;
-      {
-        ScopedTimer t(ctx, PBWTGPU_K_COMBINE);
-        CUDA_TRY(ctx, launch(c, kGather, true, false));
-        ctx->launches[PBWTGPU_K_COMBINE] += 1;
-      }
-      {
-        ScopedTimer t(ctx, PBWTGPU_K_AUX);
-        CUDA_TRY(ctx, launch_make_groups(ord[nxt] + s1 * oA, dv[nxt] + s1 * oD, g[cur] + s1 * oA, gfd[cur] + s1 * oA,
-                                         g[nxt] + s1 * oA, gfd[nxt] + s1 * oA, M, cnt, ctx->stream));
-        ctx->launches[PBWTGPU_K_AUX] += 1;
-      }
+      if (int rc = combine(cnt, ord[cur] + oA(), dv[cur] + oD(), false, g[cur] + s1 * oA(), gfd[cur] + s1 * oA(),
+                           ord[nxt] + s1 * oA(), dv[nxt] + s1 * oD(), g[nxt] + s1 * oA(), gfd[nxt] + s1 * oA()))
+        return rc;
       // nodes below the stride are already final
-      CUDA_TRY(ctx, cudaMemcpyAsync(ord[nxt] + oA, ord[cur] + oA, sizeof(int32_t) * oA * stride, cudaMemcpyDeviceToDevice, ctx->stream));
-      CUDA_TRY(ctx, cudaMemcpyAsync(dv[nxt] + oD, dv[cur] + oD, sizeof(int32_t) * oD * stride, cudaMemcpyDeviceToDevice, ctx->stream));
-      CUDA_TRY(ctx, cudaMemcpyAsync(g[nxt] + oA, g[cur] + oA, sizeof(int32_t) * oA * stride, cudaMemcpyDeviceToDevice, ctx->stream));
-      CUDA_TRY(ctx, cudaMemcpyAsync(gfd[nxt] + oA, gfd[cur] + oA, sizeof(int32_t) * oA * stride, cudaMemcpyDeviceToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(ord[nxt] + oA(), ord[cur] + oA(), sizeof(int32_t) * oA() * stride, cudaMemcpyDeviceToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(dv[nxt] + oD(), dv[cur] + oD(), sizeof(int32_t) * oD() * stride, cudaMemcpyDeviceToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(g[nxt] + oA(), g[cur] + oA(), sizeof(int32_t) * oA() * stride, cudaMemcpyDeviceToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(gfd[nxt] + oA(), gfd[cur] + oA(), sizeof(int32_t) * oA() * stride, cudaMemcpyDeviceToDevice, ctx->stream));
       cur = nxt;
     }
+    haveDStart = true;
+    return 0;
   }
 
-  // ---- pass 2 (or the only pass): all windows from their exact start states ----
-  unsigned long long *recCount = nullptr;
-  int *chunkCounter = nullptr, *chunkTab = nullptr;
-  pbwtgpu_match *pool = nullptr;
-  long long recCap = 0;
-  int poolChunks = 0;
-  if (wantMatch) {
-    if (int rc = tmp.get(&recCount, (size_t)W)) return rc;
-    if (int rc = tmp.get(&chunkCounter, 1)) return rc;
-    recCap = ctx->optMatchCap > 0 ? ctx->optMatchCap : std::min<long long>(std::max<long long>(1 << 20, 4096LL * M), 1LL << 28);
+  // aggregate node of the whole shard: ord[M] | dv[M+1] | g[M] | gfd[M]
+  static size_t agg_ints(int M) { return 4 * (size_t)M + 1; }
+  int export_aggregate(int32_t *dst) {
+    if (!sharded || nodes < 1) return fail(ctx, PBWTGPU_ERR_ARG, "export_aggregate: not a shard");
+    const size_t s = (size_t)nodes;  // last node's slot
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst, ord[cur] + s * oA(), sizeof(int32_t) * M, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst + M, dv[cur] + s * oD(), sizeof(int32_t) * (M + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst + 2 * M + 1, g[cur] + s * oA(), sizeof(int32_t) * M, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst + 3 * M + 1, gfd[cur] + s * oA(), sizeof(int32_t) * M, cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
   }
-  SweepArgs a{};
-  a.src = src; a.wpc = wpc; a.M = M; a.N = N;
-  a.sitesPerWindow = spw; a.nWindows = W;
-  a.aStart = ord[cur];
-  a.dStart = nodes > 0 ? dv[cur] : nullptr;
-  a.aEnd = res->aEnd; a.dEnd = res->dEnd; a.endOnlyLast = 1;
-  a.yOut = yOut;
-  a.recCount = recCount; a.chunkCounter = chunkCounter;
-  a.reportAtN = 1;
-  std::vector<unsigned long long> counts(W, 0);
-  long long *winNanos = nullptr;
-  if (ctx->optWindowTimes) {
-    if (int rc = tmp.get(&winNanos, (size_t)W)) return rc;
-    a.winNanos = winNanos;
+
+  // aggs: [R][agg_ints] aggregates of all shards in site order.  Combines shards 0..rank-1 into the state
+  // entering this shard and applies it to every local node and to slot 0.
+  int apply_prefix(const int32_t *aggs, int rank) {
+    if (rank <= 0) return 0;
+    const size_t AI = agg_ints(M);
+    int32_t *P[2];
+    if (int rc = tmp.get(&P[0], AI)) return rc;
+    if (int rc = tmp.get(&P[1], AI)) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(P[0], aggs, sizeof(int32_t) * AI, cudaMemcpyDeviceToDevice, ctx->stream));
+    int pc = 0;
+    for (int r = 1; r < rank; ++r) {  // P = P (+) Z_r
+      const int32_t *Z = aggs + (size_t)r * AI;
+      if (int rc = combine(1, P[pc], P[pc] + M, true, Z + 2 * M + 1, Z + 3 * M + 1, P[pc ^ 1], P[pc ^ 1] + M,
+                           P[pc ^ 1] + 2 * M + 1, P[pc ^ 1] + 3 * M + 1))
+        return rc;
+      pc ^= 1;
+    }
+    const int nxt = cur ^ 1;
+    if (int rc = combine(nodes, P[pc], P[pc] + M, true, g[cur] + oA(), gfd[cur] + oA(), ord[nxt] + oA(), dv[nxt] + oD(),
+                         g[nxt] + oA(), gfd[nxt] + oA()))
+      return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ord[nxt], P[pc], sizeof(int32_t) * M, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(dv[nxt], P[pc] + M, sizeof(int32_t) * (M + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+    cur = nxt;
+    haveDStart = true;
+    return 0;
   }
-  for (int attempt = 0; attempt < 2; ++attempt) {
+
+  // pass 2 (or the only pass): all windows from their exact start states; outputs into res
+  int finish(unsigned flags, pbwtgpu_result *res) {
+    const bool wantMatch = flags & PBWTGPU_WANT_MAXWITHIN;
+    const bool wantD = wantMatch || (flags & PBWTGPU_WANT_D);
+    const bool wantYz = (flags & PBWTGPU_WANT_YZ) && mode == kGather;
+    res->M = M;
+    res->N = N;
+    if (int rc = result_alloc(ctx, res, &res->aEnd, (size_t)M)) return rc;
+    if (wantD)
+      if (int rc = result_alloc(ctx, res, &res->dEnd, (size_t)M + 1)) return rc;
+    uint32_t *yOut = nullptr;
+    if (wantYz && N > 0)
+      if (int rc = tmp.get(&yOut, (size_t)N * wpc)) return rc;
+
+    unsigned long long *recCount = nullptr;
+    int *chunkCounter = nullptr, *chunkTab = nullptr;
+    pbwtgpu_match *pool = nullptr;
+    long long recCap = 0;
+    int poolChunks = 0;
     if (wantMatch) {
-      poolChunks = (int)((recCap + kRecChunk - 1) >> kRecChunkLog) + W;
-      if (int rc = tmp.get(&pool, (size_t)poolChunks << kRecChunkLog)) return rc;
-      if (int rc = tmp.get(&chunkTab, (size_t)W * poolChunks)) return rc;
-      CUDA_TRY(ctx, cudaMemsetAsync(chunkCounter, 0, sizeof(int), ctx->stream));
-      a.recPool = pool; a.poolChunks = poolChunks; a.chunkTab = chunkTab;
+      if (int rc = tmp.get(&recCount, (size_t)W)) return rc;
+      if (int rc = tmp.get(&chunkCounter, 1)) return rc;
+      recCap = ctx->optMatchCap > 0 ? ctx->optMatchCap : std::min<long long>(std::max<long long>(1 << 20, 4096LL * M), 1LL << 28);
     }
-    {
-      ScopedTimer t(ctx, PBWTGPU_K_SWEEP);
-      CUDA_TRY(ctx, launch(a, mode, wantD, wantMatch));
-      ctx->launches[PBWTGPU_K_SWEEP] += 1;
+    if (siteOffset + N != nTotal) {  // not the shard that ends the panel: no final state here
+      CUDA_TRY(ctx, cudaMemsetAsync(res->aEnd, 0xFF, sizeof(int32_t) * M, ctx->stream));
+      if (res->dEnd) CUDA_TRY(ctx, cudaMemsetAsync(res->dEnd, 0xFF, sizeof(int32_t) * (M + 1), ctx->stream));
     }
-    if (!wantMatch) break;
-    int used = 0;
-    CUDA_TRY(ctx, cudaMemcpyAsync(counts.data(), recCount, sizeof(unsigned long long) * W, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(&used, chunkCounter, sizeof used, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (used <= poolChunks) break;
-    if (attempt == 1) return fail(ctx, PBWTGPU_ERR_CUDA, "match record pool overflow persisted");
-    long long total = 0;  // the pool was too small: every window's count is known now, size it exactly and rerun
-    for (auto cnt : counts) total += (long long)cnt;
-    recCap = total;
-  }
-  if (winNanos) {
-    std::vector<long long> ns(W);
-    CUDA_TRY(ctx, cudaMemcpyAsync(ns.data(), winNanos, sizeof(long long) * W, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    fprintf(stderr, "[pbwtgpu] pass-2 window times (us) and records:");
-    for (int w = 0; w < W; ++w) fprintf(stderr, " %d:%.0f/%llu", w, ns[w] * 1e-3, counts[w]);
-    fprintf(stderr, "\n");
-  }
-  if (wantMatch) {
-    std::vector<long long> offs(W, 0);
-    long long total = 0;
-    int maxChunks = 0;
-    for (int w = 0; w < W; ++w) {
-      offs[w] = total;
-      total += (long long)counts[w];
-      maxChunks = std::max<int>(maxChunks, (int)((counts[w] + kRecChunk - 1) >> kRecChunkLog));
+    SweepArgs a{};
+    a.src = src; a.wpc = wpc; a.M = M; a.N = N;
+    a.sitesPerWindow = spw; a.nWindows = W;
+    a.siteOffset = siteOffset; a.nTotal = nTotal;
+    a.aStart = ord[cur];
+    a.dStart = haveDStart ? dv[cur] : nullptr;
+    a.aEnd = res->aEnd; a.dEnd = res->dEnd; a.endOnlyLast = 1;
+    a.yOut = yOut;
+    a.recCount = recCount; a.chunkCounter = chunkCounter;
+    a.reportAtN = 1;
+    std::vector<unsigned long long> counts(W, 0);
+    long long *winNanos = nullptr;
+    if (ctx->optWindowTimes) {
+      if (int rc = tmp.get(&winNanos, (size_t)W)) return rc;
+      a.winNanos = winNanos;
     }
-    res->nrec = total;
-    if (int rc = result_alloc(ctx, res, &res->rec, (size_t)std::max<long long>(total, 1))) return rc;
-    long long *offsDev = nullptr;
-    if (int rc = tmp.get(&offsDev, (size_t)W)) return rc;
-    CUDA_TRY(ctx, cudaMemcpyAsync(offsDev, offs.data(), sizeof(long long) * W, cudaMemcpyHostToDevice, ctx->stream));
-    {
-      ScopedTimer t(ctx, PBWTGPU_K_AUX);
-      CUDA_TRY(ctx, launch_gather_records(pool, chunkTab, poolChunks, offsDev, recCount, W, maxChunks, res->rec, ctx->stream));
-      ctx->launches[PBWTGPU_K_AUX] += maxChunks > 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      if (wantMatch) {
+        poolChunks = (int)((recCap + kRecChunk - 1) >> kRecChunkLog) + W;
+        if (int rc = tmp.get(&pool, (size_t)poolChunks << kRecChunkLog)) return rc;
+        if (int rc = tmp.get(&chunkTab, (size_t)W * poolChunks)) return rc;
+        CUDA_TRY(ctx, cudaMemsetAsync(chunkCounter, 0, sizeof(int), ctx->stream));
+        a.recPool = pool; a.poolChunks = poolChunks; a.chunkTab = chunkTab;
+      }
+      {
+        ScopedTimer t(ctx, PBWTGPU_K_SWEEP);
+        CUDA_TRY(ctx, launch(a, mode, wantD, wantMatch));
+        ctx->launches[PBWTGPU_K_SWEEP] += 1;
+      }
+      if (!wantMatch) break;
+      int used = 0;
+      CUDA_TRY(ctx, cudaMemcpyAsync(counts.data(), recCount, sizeof(unsigned long long) * W, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(&used, chunkCounter, sizeof used, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      if (used <= poolChunks) break;
+      if (attempt == 1) return fail(ctx, PBWTGPU_ERR_CUDA, "match record pool overflow persisted");
+      long long total = 0;  // the pool was too small: every window's count is known now, size it exactly and rerun
+      for (auto cnt : counts) total += (long long)cnt;
+      recCap = total;
     }
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // offs is a host temporary
-  }
+    if (winNanos) {
+      std::vector<long long> ns(W);
+      CUDA_TRY(ctx, cudaMemcpyAsync(ns.data(), winNanos, sizeof(long long) * W, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      fprintf(stderr, "[pbwtgpu] pass-2 window times (us) and records:");
+      for (int w = 0; w < W; ++w) fprintf(stderr, " %d:%.0f/%llu", w, ns[w] * 1e-3, counts[w]);
+      fprintf(stderr, "\n");
+    }
+    if (wantMatch) {
+      std::vector<long long> offs(W, 0);
+      long long total = 0;
+      int maxChunks = 0;
+      for (int w = 0; w < W; ++w) {
+        offs[w] = total;
+        total += (long long)counts[w];
+        maxChunks = std::max<int>(maxChunks, (int)((counts[w] + kRecChunk - 1) >> kRecChunkLog));
+      }
+      res->nrec = total;
+      if (int rc = result_alloc(ctx, res, &res->rec, (size_t)std::max<long long>(total, 1))) return rc;
+      long long *offsDev = nullptr;
+      if (int rc = tmp.get(&offsDev, (size_t)W)) return rc;
+      CUDA_TRY(ctx, cudaMemcpyAsync(offsDev, offs.data(), sizeof(long long) * W, cudaMemcpyHostToDevice, ctx->stream));
+      {
+        ScopedTimer t(ctx, PBWTGPU_K_AUX);
+        CUDA_TRY(ctx, launch_gather_records(pool, chunkTab, poolChunks, offsDev, recCount, W, maxChunks, res->rec, ctx->stream));
+        ctx->launches[PBWTGPU_K_AUX] += maxChunks > 0;
+      }
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // offs is a host temporary
+    }
 
-  if (wantYz) {
-    int32_t *colBytes = nullptr;
-    int64_t *colBase = nullptr;
-    if (int rc = tmp.get(&colBytes, (size_t)N + 1)) return rc;
-    if (int rc = tmp.get(&colBase, (size_t)N + 1)) return rc;
-    int64_t total = 0;
-    {
-      ScopedTimer t(ctx, PBWTGPU_K_PACK3);
-      CUDA_TRY(ctx, p3_count_columns(yOut, wpc, M, N, colBytes, colBase, ctx->stream));
-      ctx->launches[PBWTGPU_K_PACK3] += (N > 0) + 1;
+    if (wantYz) {
+      int32_t *colBytes = nullptr;
+      int64_t *colBase = nullptr;
+      if (int rc = tmp.get(&colBytes, (size_t)N + 1)) return rc;
+      if (int rc = tmp.get(&colBase, (size_t)N + 1)) return rc;
+      int64_t total = 0;
+      {
+        ScopedTimer t(ctx, PBWTGPU_K_PACK3);
+        CUDA_TRY(ctx, p3_count_columns(yOut, wpc, M, N, colBytes, colBase, ctx->stream));
+        ctx->launches[PBWTGPU_K_PACK3] += (N > 0) + 1;
+      }
+      CUDA_TRY(ctx, cudaMemcpyAsync(&total, colBase + N, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      res->nyz = total;
+      if (int rc = result_alloc(ctx, res, &res->yz, (size_t)total)) return rc;
+      {
+        ScopedTimer t(ctx, PBWTGPU_K_PACK3);
+        CUDA_TRY(ctx, p3_emit_columns(yOut, wpc, M, N, colBase, res->yz, ctx->stream));
+        ctx->launches[PBWTGPU_K_PACK3] += (N > 0);
+      }
     }
-    CUDA_TRY(ctx, cudaMemcpyAsync(&total, colBase + N, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    res->nyz = total;
-    if (int rc = result_alloc(ctx, res, &res->yz, (size_t)total)) return rc;
-    {
-      ScopedTimer t(ctx, PBWTGPU_K_PACK3);
-      CUDA_TRY(ctx, p3_emit_columns(yOut, wpc, M, N, colBase, res->yz, ctx->stream));
-      ctx->launches[PBWTGPU_K_PACK3] += (N > 0);
-    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // temporaries go back to the cache with this object
+    return 0;
   }
-  return 0;
+};
+
+int run_sweep(pbwtgpu_ctx *ctx, const uint32_t *src, int wpc, int M, int N, SweepMode mode, const int32_t *aStartHost,
+              unsigned flags, pbwtgpu_result *res) {
+  WindowedSweep ws(ctx);
+  if (int rc = ws.init(src, wpc, M, N, mode, aStartHost, flags & PBWTGPU_WANT_MAXWITHIN, false, 0, 0)) return rc;
+  if (int rc = ws.prepare()) return rc;
+  return ws.finish(flags, res);
 }
 
 int decode_stream(pbwtgpu_ctx *ctx, Temps &tmp, const uint8_t *yzHost, int64_t nyz, int M, int N, uint32_t **ycolsOut,
@@ -569,7 +658,12 @@ int pbwtgpu_panel_from_host(pbwtgpu_ctx *ctx, const uint32_t *xbits, int M, int 
 
 int pbwtgpu_panel_synthetic(pbwtgpu_ctx *ctx, int M, int N, uint64_t seed, uint32_t L, uint32_t flip_thresh,
                             pbwtgpu_panel **out) {
-  if (!ctx || !out || M < 1 || N < 0 || L < 1) return fail(ctx, PBWTGPU_ERR_ARG, "panel_synthetic: bad args");
+  return pbwtgpu_panel_synthetic_range(ctx, M, N, 0, seed, L, flip_thresh, out);
+}
+
+int pbwtgpu_panel_synthetic_range(pbwtgpu_ctx *ctx, int M, int N, int first_site, uint64_t seed, uint32_t L,
+                                  uint32_t flip_thresh, pbwtgpu_panel **out) {
+  if (!ctx || !out || M < 1 || N < 0 || L < 1 || first_site < 0) return fail(ctx, PBWTGPU_ERR_ARG, "panel_synthetic: bad args");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   pbwtgpu_panel *p = new pbwtgpu_panel;
   p->M = M;
@@ -580,7 +674,7 @@ int pbwtgpu_panel_synthetic(pbwtgpu_ctx *ctx, int M, int N, uint64_t seed, uint3
   p->bits = (uint32_t *)d;
   {
     ScopedTimer t(ctx, PBWTGPU_K_SYNTH);
-    CUDA_TRY(ctx, launch_synth(p->bits, p->wpc, M, N, 0, seed, L, flip_thresh, ctx->stream));
+    CUDA_TRY(ctx, launch_synth(p->bits, p->wpc, M, N, first_site, seed, L, flip_thresh, ctx->stream));
     ctx->launches[PBWTGPU_K_SYNTH] += N > 0;
   }
   *out = p;
@@ -662,6 +756,53 @@ void pbwtgpu_result_free(pbwtgpu_ctx *ctx, pbwtgpu_result *r) {
     for (size_t i = 0; i < r->owned.size(); ++i) dev_release(ctx, r->owned[i], r->ownedBytes[i]);
   }
   delete r;
+}
+
+// ---- multi-GPU site shards ---------------------------------------------------------------------------
+struct pbwtgpu_shard {
+  WindowedSweep ws;
+  explicit pbwtgpu_shard(pbwtgpu_ctx *c) : ws(c) {}
+};
+
+size_t pbwtgpu_shard_aggregate_ints(int M) { return WindowedSweep::agg_ints(M); }
+
+int pbwtgpu_shard_prepare(pbwtgpu_ctx *ctx, const pbwtgpu_panel *panel, const int32_t *a_start, int site_offset,
+                          int total_sites, unsigned flags, pbwtgpu_shard **out) {
+  if (!ctx || !panel || !out || site_offset < 0 || total_sites < site_offset + panel->N || panel->N < 1)
+    return fail(ctx, PBWTGPU_ERR_ARG, "shard_prepare: bad args");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  pbwtgpu_shard *sh = new pbwtgpu_shard(ctx);
+  int rc = sh->ws.init(panel->bits, panel->wpc, panel->M, panel->N, kGather, a_start, flags & PBWTGPU_WANT_MAXWITHIN, true,
+                       site_offset, total_sites);
+  if (!rc) rc = sh->ws.prepare();
+  if (rc) { delete sh; return rc; }
+  *out = sh;
+  return 0;
+}
+
+int pbwtgpu_shard_export(pbwtgpu_ctx *ctx, pbwtgpu_shard *sh, int32_t *dev_dst) {
+  if (!ctx || !sh || !dev_dst) return fail(ctx, PBWTGPU_ERR_ARG, "shard_export: bad args");
+  if (int rc = sh->ws.export_aggregate(dev_dst)) return rc;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int pbwtgpu_shard_finish(pbwtgpu_ctx *ctx, pbwtgpu_shard *sh, const int32_t *dev_aggs, int rank, unsigned flags,
+                         pbwtgpu_result **out) {
+  if (!ctx || !sh || !out || rank < 0 || (rank > 0 && !dev_aggs)) return fail(ctx, PBWTGPU_ERR_ARG, "shard_finish: bad args");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (int rc = sh->ws.apply_prefix(dev_aggs, rank)) return rc;
+  pbwtgpu_result *res = new pbwtgpu_result;
+  const int rc = sh->ws.finish(flags, res);
+  if (rc) { pbwtgpu_result_free(ctx, res); return rc; }
+  *out = res;
+  return 0;
+}
+
+void pbwtgpu_shard_free(pbwtgpu_ctx *ctx, pbwtgpu_shard *sh) {
+  if (!sh) return;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  delete sh;
 }
 
 // ---- one-shot host-buffer entry points -----------------------------------------------------------

@@ -20,12 +20,15 @@ struct SweepArgs {
   int M, N;
   int sitesPerWindow;
   int nWindows;
+  int siteOffset;  // regular mode: global label of column 0 (a shard of a longer panel), 0 otherwise
+  int nTotal;      // global site count (labels run to nTotal); 0 = N
   int perWindowSites;
   long long srcWindowStride;  // words
   int kLabelBase;
   const int32_t *aStart;  // [W][M] ([M] if aStartShared); NULL = identity
   int aStartShared;
   const int32_t *dStart;  // [W][M+1] interior values (sentinels are implied); NULL = fresh cursor (zeros)
+  int dStartShared;       // dStart is one [M+1] array used by every window
   int32_t *aEnd;          // [W][M] state after the window's last site ([M], last window only, if endOnlyLast)
   int32_t *dEnd;          // [W][M+1]
   int endOnlyLast;

@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int win = blockIdx.x / G, g = blockIdx.x % G;
   const int M = p.M, wpc = p.wpc;
+  const int nTotal = p.nTotal ? p.nTotal : p.N;
   const size_t MS = (size_t)G * chunk;  // padded state stride per buffer
   int32_t *aW = aBuf + (size_t)win * 2 * MS;
   int32_t *dW = WITH_D ? dBuf + (size_t)win * 2 * (MS + 4) : nullptr;
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     k0 = p.kLabelBase; k1 = k0 + p.perWindowSites; colShift = -k0;
     src = p.src + (size_t)win * p.srcWindowStride;
   } else {
-    k0 = win * p.sitesPerWindow; k1 = min(p.N, k0 + p.sitesPerWindow); colShift = 0;
+    k0 = p.siteOffset + win * p.sitesPerWindow; k1 = min(p.siteOffset + p.N, k0 + p.sitesPerWindow); colShift = -p.siteOffset;
     src = p.src;
   }
   const int p0 = g * chunk;                 // first sorted position of this CTA
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
   for (int i = p0 + tid; i < p0 + chunk; i += kThreads) {
     if (i < M) {
       aW[i] = p.aStart ? p.aStart[(p.aStartShared ? 0 : (size_t)win * M) + i] : i;
-      if (WITH_D) dW[i] = (i > 0 && p.dStart) ? p.dStart[(size_t)win * (M + 1) + i] : 0;
+      if (WITH_D) dW[i] = (i > 0 && p.dStart) ? p.dStart[(p.dStartShared ? 0 : (size_t)win * (M + 1)) + i] : 0;
     }
   }
   group_barrier();
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
   }
 
   // ---- window end ----
-  const bool writeEnd = !p.endOnlyLast || k1 == p.N;
+  const bool writeEnd = !p.endOnlyLast || k1 == nTotal;
   const size_t endSlot = p.endOnlyLast ? 0 : (size_t)win;
   const int32_t *aC = aW + (size_t)cur * MS;
   if (p.aEnd && writeEnd)

@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = p.M, wpc = p.wpc;
+  const int nTotal = p.nTotal ? p.nTotal : p.N;
   const int win = blockIdx.x;
   long long tStart = 0;
   if (p.winNanos && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tStart));
@@ -232,9 +233,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     colShift = -k0;
     src = p.src + (size_t)win * p.srcWindowStride;
   } else {
-    k0 = win * p.sitesPerWindow;
-    k1 = min(p.N, k0 + p.sitesPerWindow);
-    colShift = 0;
+    k0 = p.siteOffset + win * p.sitesPerWindow;
+    k1 = min(p.siteOffset + p.N, k0 + p.sitesPerWindow);
+    colShift = -p.siteOffset;
     src = p.src;
   }
   const uint32_t colBytes = (uint32_t)wpc * 4u;
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
   if (WITH_D)
     for (int i = tid; i < L::MP + 4; i += kThreads) {
       int v = 0;
-      if (i > 0 && i < M && p.dStart) v = p.dStart[(size_t)win * (M + 1) + i];
+      if (i > 0 && i < M && p.dStart) v = p.dStart[(p.dStartShared ? 0 : (size_t)win * (M + 1)) + i];
       sI[L::d0 + i] = v;
       sI[L::d1 + i] = 0;
     }
@@ -641,7 +642,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     sI[dC + M] = k1 + 1;
   }
   __syncthreads();
-  const bool writeEnd = !p.endOnlyLast || k1 == p.N;
+  const bool writeEnd = !p.endOnlyLast || k1 == nTotal;
   const size_t endSlot = p.endOnlyLast ? 0 : (size_t)win;
   if (p.aEnd && writeEnd)
     for (int i = tid; i < M; i += kThreads) p.aEnd[endSlot * M + i] = sI[aC + i];
@@ -666,12 +667,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     if (sink.pool && recTot) {
       ensure_chunks(recBase + recTot);
       long long o = recBase + recEx + cntEx;
-      for (int i = f; i < f + cnt; ++i, ++o) sink.put(o, make_int4(jj, sI[aC + i], e, p.N));
+      for (int i = f; i < f + cnt; ++i, ++o) sink.put(o, make_int4(jj, sI[aC + i], e, nTotal));
     }
     recBase += recTot;
     if (tid == 0 && p.qCounts) { p.qCounts[0] = (unsigned long long)recBase; p.qCounts[1] = (unsigned long long)nmBase; }
   }
-  if (MATCH && p.reportAtN && !p.perWindowSites && k1 == p.N) {  // k == N: nothing extends, every block is reported
+  if (MATCH && p.reportAtN && !p.perWindowSites && k1 == nTotal) {  // k == N: nothing extends, every block is reported
     const uint32_t *yc = smem + L::ycol;                           // alleles are not consulted when live == false
     for (int w = warp; w < L::WORDS; w += 32) {                    // word maxima of the final d
       const int wm = __reduce_max_sync(kFull, sI[dC + w * 32 + lane]);
@@ -687,7 +688,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     tw = __reduce_add_sync(kFull, tw);
     if (lane == 0) wsumC[warp] = tw;
     __syncthreads();
-    match_rounds(sI + aC, sI + dC, yc, wmaxS, p.N, false);
+    match_rounds(sI + aC, sI + dC, yc, wmaxS, nTotal, false);
   }
   if (MATCH && p.recCount && tid == 0) p.recCount[win] = (unsigned long long)recBase;
   if (p.winNanos && tid == 0) {

@@ -291,3 +291,45 @@ def test_wide_panel_windowed_mosaic(eng, orc):
     M, N = 30000, 1200
     x = O.generate_panel(M, N, seed=0x5EED0003, L=300, mu=4.0)
     check_build(eng, orc, x, M, N, matches=False)
+
+
+@pytest.mark.parametrize("M,N,R,W,dens,with_start", [(200, 90, 3, 2, 0.3, False), (1000, 240, 4, 5, 0.05, True), (33, 64, 8, 1, 0.5, False),
+                                                      (3000, 400, 2, 7, 0.02, True)])
+def test_site_shards_sequential(eng, orc, M, N, R, W, dens, with_start):
+    """The multi-GPU protocol (sites partitioned into R shards: prepare -> gather aggregates -> finish) run
+    shard by shard on one GPU: concatenated streams / records and the last shard's a, d equal the sequential sweep."""
+    import torch
+
+    rng = np.random.default_rng(M + R)
+    hap = (rng.random((M, N)) < dens).astype(np.uint8)
+    hap[: M // 3] = hap[1]
+    x = O.pack_panel(hap)
+    a0 = rng.permutation(M).astype(np.int32) if with_start else None
+    yz, a_end, d_end = orc.build(x, M, N, a0, with_d=True)
+    rec, n = orc.max_within(yz, M, N, a0)
+    flags = pbwt_b200.WANT_YZ | pbwt_b200.WANT_MAXWITHIN
+    bounds = [N * r // R for r in range(R + 1)]
+    eng.set_option("windows", W)
+    try:
+        panels = [eng.panel_from_host(x[bounds[r]:bounds[r + 1]], M) for r in range(R)]
+        shards = [eng.shard_prepare(panels[r], bounds[r], N, flags, a_start=a0) for r in range(R)]
+        ai = eng.shard_aggregate_ints(M)
+        aggs = torch.zeros((R, ai), dtype=torch.int32, device="cuda")
+        for r in range(R):
+            shards[r].export(aggs[r].data_ptr())
+        outs = []
+        for r in range(R):
+            res = shards[r].finish(aggs.data_ptr(), r, flags)
+            outs.append(res.fetch())
+            res.free()
+        for s in shards:
+            s.free()
+        for p in panels:
+            p.free()
+    finally:
+        eng.set_option("windows", 0)
+    assert np.concatenate([o["yz"] for o in outs]).tobytes() == yz.tobytes()
+    got = np.concatenate([o["matches"] for o in outs])
+    assert len(got) == n and (got == rec).all()
+    assert (outs[-1]["a_end"] == a_end).all() and (outs[-1]["d_end"] == d_end).all()
+    assert all((o["a_end"] == -1).all() for o in outs[:-1])
