@@ -145,12 +145,28 @@ def main():
     eng.set_stream(stream.cuda_stream)
     eng.profile(True)
 
-    # one panel per rank (weak scaling: independent panels, no data-path collective)
-    panel = eng.panel_synthetic(M, N, seed=SEED + rank, L=L_RECOMB, mu=MU)
+    # N GPUs: the SITES of one panel of world*N sites are partitioned across the ranks (weak scaling: N sites per
+    # GPU); the only exchange is one NCCL all-gather of per-shard aggregates (include/pbwtgpu.h, multi-GPU)
+    n_total = N * world
+    panel = eng.panel_synthetic(M, N, seed=SEED, L=L_RECOMB, mu=MU, first_site=rank * N)
     eng.synchronize()
     eng.last_timings()
     flags = P.WANT_YZ | P.WANT_MAXWITHIN
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    agg_ints = eng.shard_aggregate_ints(M)
+    agg = torch.zeros(agg_ints, dtype=torch.int32, device="cuda")
+    aggs = torch.zeros((world, agg_ints), dtype=torch.int32, device="cuda")
+
+    def device_step(pnl):
+        """One build + maxWithin step over this rank's sites; returns the Result (device resident)."""
+        if world == 1:
+            return eng.build_device(pnl, flags)
+        sh = eng.shard_prepare(pnl, rank * N, n_total, flags)
+        sh.export(agg.data_ptr())
+        dist.all_gather_into_tensor(aggs, agg)
+        res = sh.finish(aggs.data_ptr(), rank, flags)
+        sh.free()
+        return res
 
     def barrier():
         torch.cuda.synchronize()
@@ -161,7 +177,7 @@ def main():
     # ---- device-resident steps -------------------------------------------------------------------
     nyz = nmatch = 0
     for _ in range(warmup):
-        r = eng.build_device(panel, flags)
+        r = device_step(panel)
         nyz, nmatch = r.nyz, r.nmatch
         r.free()
     eng.synchronize()
@@ -173,7 +189,7 @@ def main():
         for s in range(args.steps):
             flush.zero_()  # evict L2 between timed steps (not inside the step's events)
             ev[s][0].record(stream)
-            r = eng.build_device(panel, flags)
+            r = device_step(panel)
             ev[s][1].record(stream)
             r.free()
         barrier()
@@ -201,7 +217,7 @@ def main():
 
     def e2e_step():
         pnl = eng.panel_from_host(x_np, M)
-        res = eng.build_device(pnl, flags)
+        res = device_step(pnl)
         res.fetch(out=pin)
         res.free()
         pnl.free()
@@ -220,6 +236,10 @@ def main():
         dist.all_reduce(t_step, op=dist.ReduceOp.MAX)
     ms_per_step, ms_e2e = float(t_step[0]), float(t_step[1])
     total_hs = float(M) * N * world
+    stats = torch.tensor([float(nyz), float(nmatch), float(h2d), float(d2h), float(launches)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats)
+    nyz_all, nmatch_all, h2d_all, d2h_all, launches_all = [int(v) for v in stats.tolist()]
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -227,7 +247,7 @@ def main():
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        algo_bytes = BYTES_PER_HS * M * N + nyz + 16.0 * nmatch
+        algo_bytes = BYTES_PER_HS * M * N + nyz + 16.0 * nmatch  # rank 0's shard; the roofline is per GPU
         # one unit of algorithmic work (a step) needs ALL sweep-kernel launches of that step (pass 1 + combine
         # rounds + pass 2), so the denominator is their summed duration per step, not one launch's
         sweep_ms_per_step = sweep_ms / args.steps
@@ -250,13 +270,14 @@ def main():
             "metric": METRIC, "value": total_hs / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": workload_name(M, N), "haplotypes": M, "sites": N, "panels": world,
-                       "parallelism": "one independent panel per GPU (no data-path collective)" if world > 1 else "single GPU",
+            "config": {"workload": workload_name(M, n_total), "haplotypes": M, "sites": n_total, "sites_per_gpu": N,
+                       "parallelism": (f"sites partitioned across {world} GPUs, one NCCL all-gather of per-shard aggregates "
+                                       f"({agg_ints * 4} B per rank) per step") if world > 1 else "single GPU",
                        "l2": "256 MiB device memset between timed steps; per-step CUDA events on the launching stream",
-                       "matches_per_haplotype": nmatch / M, "pack3_bytes": nyz, "generator": f"seed {SEED:#x}, L={L_RECOMB}, mu={MU}"},
-            "e2e": {"value": total_hs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "matches_per_haplotype": nmatch_all / M, "pack3_bytes": nyz_all, "generator": f"seed {SEED:#x}, L={L_RECOMB}, mu={MU}"},
+            "e2e": {"value": total_hs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
                     "ms_per_step": ms_e2e},
-            "gpu_launches": launches,
+            "gpu_launches": launches_all,
             "kernel_ms": {k: v[0] for k, v in kt.items() if v[1]},
             "clocks": clocks.summary(),
             "roofline": roofline,

@@ -156,6 +156,27 @@ class Oracle:
         return tb.value, tm.value, nyz.value, nm.value
 
 
+def sweep_from(xbits, M, N, k0, ntotal, a_start, d_start):
+    """oracle/pbwt_oracle.c:orc_sweep_from -- build + maxWithin of one site shard from a given state."""
+    o = port()
+    wpc = words_per_col(M)
+    xbits = np.ascontiguousarray(xbits, np.uint32)
+    a0 = None if a_start is None else np.ascontiguousarray(a_start, np.int32)
+    d0 = None if d_start is None else np.ascontiguousarray(d_start, np.int32)
+    cap = max(16, N * (M + 8))
+    yz = np.zeros(cap, np.uint8)
+    nyz, nrec = C.c_int64(0), C.c_int64(0)
+    a_end, d_end = np.zeros(M, np.int32), np.zeros(M + 1, np.int32)
+    f = o.lib.orc_sweep_from
+    args = lambda rec, rcap: (_p(xbits, c_u32p), wpc, M, N, k0, ntotal, _p(a0, c_i32p), _p(d0, c_i32p), _p(yz, c_u8p), C.c_int64(cap),
+                              C.byref(nyz), _p(a_end, c_i32p), _p(d_end, c_i32p), rec, C.c_int64(rcap), C.byref(nrec))
+    f(*args(None, 0))
+    rec = np.zeros(max(nrec.value, 1), MATCH_DTYPE)
+    n = nrec.value
+    f(*args(rec.ctypes.data_as(C.c_void_p), n))
+    return yz[: nyz.value].copy(), a_end, d_end, rec[:n]
+
+
 def build_oracles():
     """(Re)compile the oracle libraries. The reference arm is only rebuilt where /root/reference exists."""
     subprocess.run(["make", "-C", ORACLE_DIR, "port"], check=True, capture_output=True)
