@@ -203,6 +203,10 @@ struct WindowedSweep {
   int32_t *ord[2] = {nullptr, nullptr}, *dv[2] = {nullptr, nullptr}, *g[2] = {nullptr, nullptr}, *gfd[2] = {nullptr, nullptr};
   uint32_t *keys = nullptr;
   bool haveDStart = false;
+  // stored-stream sweeps combine windows in POSITION space: a window swept from the identity yields the exact
+  // permutation of sorted positions over its sites (the sorted columns do not depend on the labels)
+  bool positionSpace = false;
+  int32_t *iota = nullptr, *ordScratch = nullptr;
 
   explicit WindowedSweep(pbwtgpu_ctx *c) : ctx(c), tmp(c) {}
   size_t oA() const { return (size_t)M; }
@@ -228,7 +232,8 @@ struct WindowedSweep {
     if (useGlobal && wantMatch)
       return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "maxWithin needs M <= %d (shared-memory kernel); M=%d", sweep_smem_max_m(true), M);
     W = 1;
-    if (mode == kGather && M >= 2) {
+    positionSpace = mode == kSorted;
+    if (M >= 2 && !(positionSpace && sharded_)) {
       const long long want = ctx->optWindows > 0 ? ctx->optWindows : ctx->smCount;
       const int minSites = ctx->optWindows > 0 ? 1 : 256;  // below this a window does not repay its two extra passes
       W = (int)std::max<long long>(1, std::min<long long>(want, N / minSites));
@@ -261,6 +266,11 @@ struct WindowedSweep {
     }
     if (needNodes)
       if (int rc = tmp.get(&keys, (size_t)std::max(nodes, 1) * bits * wpc)) return rc;
+    if (needNodes && positionSpace) {
+      if (int rc = tmp.get(&iota, (size_t)M)) return rc;
+      if (int rc = tmp.get(&ordScratch, (size_t)nodes * M)) return rc;
+      CUDA_TRY(ctx, launch_iota(iota, M, ctx->stream));
+    }
     {  // slot 0: the panel's start order
       std::vector<int32_t> ident;
       const int32_t *h = aStartHost;
@@ -280,6 +290,22 @@ struct WindowedSweep {
   int combine(int cnt, const int32_t *ordI, const int32_t *dvI, bool sharedI, const int32_t *gJ, const int32_t *gfdJ,
               int32_t *ordOut, int32_t *dvOut, int32_t *gOut, int32_t *gfdOut) {
     if (cnt <= 0) return 0;
+    if (positionSpace) {
+      // ids are sorted positions at the I/J boundary: I's end order is the identity there, so the pseudo-site
+      // sweep only has to produce the divergence (its order output equals J's own permutation); the node's
+      // permutation is then the composition ord_I[ord_J[.]] and its groups are re-derived in I's start ids
+      if (int rc = combine_ids(cnt, iota, true, dvI, sharedI, gJ, gfdJ, ordScratch, dvOut, gOut, gfdOut)) return rc;
+      ScopedTimer t(ctx, PBWTGPU_K_AUX);
+      CUDA_TRY(ctx, launch_compose(ordOut, ordI, sharedI, ordScratch, M, cnt, ctx->stream));
+      CUDA_TRY(ctx, launch_make_groups(ordOut, dvOut, nullptr, nullptr, gOut, gfdOut, M, cnt, ctx->stream));
+      ctx->launches[PBWTGPU_K_AUX] += 2;
+      return 0;
+    }
+    return combine_ids(cnt, ordI, sharedI, dvI, sharedI, gJ, gfdJ, ordOut, dvOut, gOut, gfdOut);
+  }
+
+  int combine_ids(int cnt, const int32_t *ordI, bool ordShared, const int32_t *dvI, bool dvShared, const int32_t *gJ,
+                  const int32_t *gfdJ, int32_t *ordOut, int32_t *dvOut, int32_t *gOut, int32_t *gfdOut) {
     {
       ScopedTimer t(ctx, PBWTGPU_K_AUX);
       CUDA_TRY(ctx, launch_key_bits(gJ, M, cnt, bits, wpc, keys, ctx->stream));
@@ -288,7 +314,7 @@ struct WindowedSweep {
     SweepArgs c{};
     c.src = keys; c.wpc = wpc; c.M = M; c.N = N; c.nWindows = cnt;
     c.perWindowSites = bits; c.srcWindowStride = (long long)bits * wpc; c.kLabelBase = kPseudoLabelBase;
-    c.aStart = ordI; c.dStart = dvI; c.aStartShared = sharedI; c.dStartShared = sharedI;
+    c.aStart = ordI; c.dStart = dvI; c.aStartShared = ordShared; c.dStartShared = dvShared;
     c.aEnd = ordOut; c.dEnd = dvOut;
     {
       ScopedTimer t(ctx, PBWTGPU_K_COMBINE);
@@ -310,11 +336,11 @@ struct WindowedSweep {
     SweepArgs a1{};
     a1.src = src; a1.wpc = wpc; a1.M = M; a1.N = N; a1.sitesPerWindow = spw; a1.nWindows = nodes;
     a1.siteOffset = siteOffset; a1.nTotal = nTotal;
-    a1.aStart = ord[0]; a1.aStartShared = 1;
+    a1.aStart = positionSpace ? iota : ord[0]; a1.aStartShared = 1;
     a1.aEnd = ord[0] + oA(); a1.dEnd = dv[0] + oD();
     {
       ScopedTimer t(ctx, PBWTGPU_K_PREPASS);
-      CUDA_TRY(ctx, launch(a1, kGather, true, false));
+      CUDA_TRY(ctx, launch(a1, mode, true, false));
       ctx->launches[PBWTGPU_K_PREPASS] += 1;
     }
     {
@@ -335,6 +361,13 @@ struct WindowedSweep {
       CUDA_TRY(ctx, cudaMemcpyAsync(g[nxt] + oA(), g[cur] + oA(), sizeof(int32_t) * oA() * stride, cudaMemcpyDeviceToDevice, ctx->stream));
       CUDA_TRY(ctx, cudaMemcpyAsync(gfd[nxt] + oA(), gfd[cur] + oA(), sizeof(int32_t) * oA() * stride, cudaMemcpyDeviceToDevice, ctx->stream));
       cur = nxt;
+    }
+    if (positionSpace) {  // positions relative to the sweep's start -> haplotypes: compose with the start order
+      const int nxt = cur ^ 1;
+      ScopedTimer t(ctx, PBWTGPU_K_AUX);
+      CUDA_TRY(ctx, launch_compose(ord[nxt] + oA(), ord[cur], true, ord[cur] + oA(), M, nodes, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(ord[cur] + oA(), ord[nxt] + oA(), sizeof(int32_t) * oA() * nodes, cudaMemcpyDeviceToDevice, ctx->stream));
+      ctx->launches[PBWTGPU_K_AUX] += 1;
     }
     haveDStart = true;
     return 0;

@@ -87,6 +87,21 @@ __global__ void __launch_bounds__(256) key_bits_kernel(const int32_t *gAll, int 
   }
 }
 
+// out[n][j] = table[n][idx[n][j]] (table shared by all n when tableShared): composition of permutations
+__global__ void __launch_bounds__(256) compose_kernel(int32_t *out, const int32_t *table, int tableShared,
+                                                      const int32_t *idx, int M) {
+  const int n = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  const int32_t *t = table + (tableShared ? 0 : (size_t)n * M);
+  out[(size_t)n * M + j] = t[idx[(size_t)n * M + j]];
+}
+
+__global__ void iota_kernel(int32_t *out, int M) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < M) out[j] = j;
+}
+
 __global__ void __launch_bounds__(256) gather_records_kernel(const int4 *pool, const int *chunkTab, int poolChunks,
                                                              const long long *winOffset,
                                                              const unsigned long long *winCount, int4 *out) {
@@ -115,6 +130,20 @@ int launch_key_bits(const int32_t *g, int M, int nodes, int bits, int wpc, uint3
     dim3 grid(((M + 31) / 32 + 7) / 8, nodes);
     key_bits_kernel<<<grid, 256, 0, stream>>>(g, M, bits, wpc, out);
   }
+  return (int)cudaGetLastError();
+}
+
+int launch_compose(int32_t *out, const int32_t *table, bool tableShared, const int32_t *idx, int M, int n,
+                   cudaStream_t stream) {
+  if (n > 0 && M > 0) {
+    dim3 grid((M + 255) / 256, n);
+    compose_kernel<<<grid, 256, 0, stream>>>(out, table, tableShared ? 1 : 0, idx, M);
+  }
+  return (int)cudaGetLastError();
+}
+
+int launch_iota(int32_t *out, int M, cudaStream_t stream) {
+  if (M > 0) iota_kernel<<<(M + 255) / 256, 256, 0, stream>>>(out, M);
   return (int)cudaGetLastError();
 }
 

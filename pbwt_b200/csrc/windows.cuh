@@ -15,6 +15,9 @@ int launch_make_groups(const int32_t *ord, int32_t *dv, const int32_t *gJ, const
                        int M, int nodes, cudaStream_t stream);
 // Pseudo-site columns of a node: column b, bit h = bit b of g[h].  out: [nodes][bits][wpc]
 int launch_key_bits(const int32_t *g, int M, int nodes, int bits, int wpc, uint32_t *out, cudaStream_t stream);
+// out[n][j] = table[n or 0][idx[n][j]]: composition of permutations (position-space window combine, start order)
+int launch_compose(int32_t *out, const int32_t *table, bool tableShared, const int32_t *idx, int M, int n, cudaStream_t stream);
+int launch_iota(int32_t *out, int M, cudaStream_t stream);
 // Gather the chunked match records of all windows into one contiguous array in window order.
 int launch_gather_records(const pbwtgpu_match *pool, const int *chunkTab, int poolChunks, const long long *winOffset,
                           const unsigned long long *winCount, int nWindows, int maxChunksPerWindow, pbwtgpu_match *out,
