@@ -52,7 +52,7 @@ struct SmemLayout {  // offsets in 32-bit words; every array start is 16-byte al
   static constexpr int wsum = xcol + kStages * STAGE;
   static constexpr int mbar = wsum + 3 * 32;
   static constexpr int wmax = mbar + 8;  // room for up to 4 mbarriers, keeps 16-byte alignment
-  static constexpr int cmask = wmax + (MATCH ? WORDS : 0);
+  static constexpr int cmask = wmax + (MATCH ? WORDS : 0);  // per-word maxima of d (skip structure for long blocks)
   static constexpr int res = cmask + (MATCH ? WORDS : 0);       // per-word candidate masks, then result slots
   static constexpr int ctab = res + (MATCH ? kResMax * 4 : 0);  // mirror of the newest kTabMirror chunk ids
   static constexpr int QCAP = E <= 12 ? 1024 : 512;  // queries per launch (one thread each)
@@ -94,45 +94,101 @@ __device__ __forceinline__ bool any_same_allele(const uint32_t *yc, int lo, int 
   return __any_sync(kFull, hit);
 }
 
-// nearest q <= i with d[q] > t.  d[0] = k+1 exceeds every interior value, so q exists.
-__device__ __forceinline__ int search_up(const int32_t *sD, const int32_t *wmax, int i, int t, int lane) {
-  const int w = i >> 5;
+constexpr int kEarlySteps = 2;  // 32-position steps scanned with the reference's early exit before skipping by words
+
+// The reference's upward scan of position i (pbwtMatch.c:124-126):
+//   lo = i; while (d[lo] <= d[i]) { --lo; if (y[lo] == y[i]) -> the match extends }
+// First kEarlySteps x 32 positions exactly as the reference walks them (most candidates resolve here: a
+// neighbour with the same allele, or the block's end); longer blocks are closed with the per-word maxima of d
+// (1024 positions per step) and tested for the allele by masked popcounts.  Lane l of a step looks at
+// p = top - l, visited iff no d[q] > di for q in (p, i].  Returns true when the match extends, else sets lo.
+__device__ __forceinline__ bool scan_up(const int32_t *sD, const uint32_t *yc, const int32_t *wmax, int i, uint32_t yi,
+                                        int di, bool live, int lane, int &lo) {
+  int top = i - 1;
+  for (int step = 0; step < kEarlySteps; ++step, top -= 32) {
+    const int p = top - lane;
+    const bool blk = p < -1 || (p + 1 < i && sD[p + 1] > di);  // d[0] = k+1 blocks at p = -1
+    const unsigned mBlk = __ballot_sync(kFull, blk);
+    const unsigned before = mBlk ? ((1u << (__ffs(mBlk) - 1)) - 1u) : kFull;  // lanes visited in this step
+    if (live) {
+      const unsigned mSame = __ballot_sync(kFull, p >= 0 && ((yc[p >> 5] >> (p & 31)) & 1u) == yi);
+      if (mSame & before) return true;
+    }
+    if (mBlk) {
+      lo = top - (__ffs(mBlk) - 1) + 1;
+      return false;
+    }
+  }
+  // positions (top, i) are visited and clean; nearest q <= top + 1 with d[q] > di closes the block
+  int q;
   {
+    const int from = top + 1;
+    const int w = from >> 5;
     const int idx = (w << 5) + lane;
-    const unsigned m = __ballot_sync(kFull, idx <= i && sD[idx] > t);
-    if (m) return (w << 5) + 31 - __clz(m);
+    const unsigned m = __ballot_sync(kFull, idx <= from && (idx <= 0 || sD[idx] > di));
+    if (m) q = (w << 5) + 31 - __clz(m);
+    else {
+      int ws = w - 1;
+      for (;;) {
+        const int wi = ws - lane;
+        const unsigned mw = __ballot_sync(kFull, wi < 0 || wmax[wi] > di);
+        if (mw) { ws -= __ffs(mw) - 1; break; }
+        ws -= 32;
+      }
+      if (ws < 0) q = 0;
+      else {
+        const unsigned m2 = __ballot_sync(kFull, sD[(ws << 5) + lane] > di);
+        q = m2 ? (ws << 5) + 31 - __clz(m2) : 0;
+      }
+    }
   }
-  int ws = w - 1;
-  for (;;) {
-    const int wi = ws - lane;
-    const unsigned m = __ballot_sync(kFull, wi < 0 || wmax[wi] > t);
-    if (m) { ws -= __ffs(m) - 1; break; }
-    ws -= 32;
-  }
-  if (ws < 0) return 0;
-  const unsigned m = __ballot_sync(kFull, sD[(ws << 5) + lane] > t);
-  return m ? (ws << 5) + 31 - __clz(m) : 0;
+  lo = max(q, 0);
+  return live && any_same_allele(yc, lo, top + 1, yi, lane);
 }
 
-// nearest r >= from with d[r] > t, clamped to M.  d[M] = k+1 exceeds every interior value.
-__device__ __forceinline__ int search_down(const int32_t *sD, const int32_t *wmax, int from, int t, int M, int lane) {
-  const int w = from >> 5;
+// The downward scan (pbwtMatch.c:127-129): hi = i+1; while (d[hi] <= d[i+1]) { if (y[hi] == y[i]) extends; ++hi }
+__device__ __forceinline__ bool scan_down(const int32_t *sD, const uint32_t *yc, const int32_t *wmax, int i, uint32_t yi,
+                                          int dn1, int M, bool live, int lane, int &hi) {
+  int bot = i + 1;
+  for (int step = 0; step < kEarlySteps; ++step, bot += 32) {
+    const int p = bot + lane;
+    const bool blk = p >= M || sD[p] > dn1;  // d[M] = k+1 blocks at p = M
+    const unsigned mBlk = __ballot_sync(kFull, blk);
+    const unsigned before = mBlk ? ((1u << (__ffs(mBlk) - 1)) - 1u) : kFull;
+    if (live) {
+      const unsigned mSame = __ballot_sync(kFull, p < M && ((yc[p >> 5] >> (p & 31)) & 1u) == yi);
+      if (mSame & before) return true;
+    }
+    if (mBlk) {
+      hi = bot + __ffs(mBlk) - 1;
+      return false;
+    }
+  }
+  // positions (i, bot) are visited and clean; nearest r >= bot with d[r] > dn1 closes the block
+  int r;
   {
+    const int w = bot >> 5;
     const int idx = (w << 5) + lane;
-    const unsigned m = __ballot_sync(kFull, idx >= from && (idx >= M || sD[idx] > t));
-    if (m) return min((w << 5) + __ffs(m) - 1, M);
+    const unsigned m = __ballot_sync(kFull, idx >= bot && (idx >= M || sD[idx] > dn1));
+    if (m) r = (w << 5) + __ffs(m) - 1;
+    else {
+      int ws = w + 1;
+      for (;;) {
+        const int wi = ws + lane;
+        const unsigned mw = __ballot_sync(kFull, (wi << 5) >= M || wmax[wi] > dn1);
+        if (mw) { ws += __ffs(mw) - 1; break; }
+        ws += 32;
+      }
+      if ((ws << 5) >= M) r = M;
+      else {
+        const int idx2 = (ws << 5) + lane;
+        const unsigned m2 = __ballot_sync(kFull, idx2 >= M || sD[idx2] > dn1);
+        r = m2 ? (ws << 5) + __ffs(m2) - 1 : M;
+      }
+    }
   }
-  int ws = w + 1;
-  for (;;) {
-    const int wi = ws + lane;
-    const unsigned m = __ballot_sync(kFull, (wi << 5) >= M || wmax[wi] > t);
-    if (m) { ws += __ffs(m) - 1; break; }
-    ws += 32;
-  }
-  if ((ws << 5) >= M) return M;
-  const int idx = (ws << 5) + lane;
-  const unsigned m = __ballot_sync(kFull, idx >= M || sD[idx] > t);
-  return m ? min((ws << 5) + __ffs(m) - 1, M) : M;
+  hi = min(r, M);
+  return live && any_same_allele(yc, bot, hi, yi, lane);
 }
 
 // Where a window's records go: chunks of kRecChunk records drawn from a global pool.
@@ -202,7 +258,9 @@ __device__ __forceinline__ int locate_candidate(const uint32_t *masks, int candB
   const int e = __ffs(__ballot_sync(kFull, inc > r)) - 1;  // word holding it
   r -= __shfl_sync(kFull, inc - pc, e);
   const uint32_t me = __shfl_sync(kFull, m, e);
-  return (wv * E + e) * 32 + __fns(me, 0, r + 1);
+  uint32_t mm = me;
+  for (int q = 0; q < r; ++q) mm &= mm - 1;  // drop the r lowest set bits (r is small)
+  return (wv * E + e) * 32 + __ffs(mm) - 1;
 }
 
 template <int E, int MODE, bool WITH_D, bool MATCH, bool QUERY = false>
@@ -306,12 +364,17 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
   // -------- candidates of a state -> records, in rounds of kResMax dealt round-robin to the 32 warps --------
   // Expects cmaskS[] (per-word candidate masks) and wsumC[] (per-warp candidate counts) to have been published
   // before the preceding barrier.  Contains at least one __syncthreads (the caller's "S2").
-  auto match_rounds = [&](const int32_t *sA, const int32_t *sD, const uint32_t *yc, const int32_t *wm, int k, bool live) {
-    int T;
-    const int candBase = warp_excl_scan(wsumC[lane], lane, T);
+  auto match_rounds = [&](const int32_t *sA, const int32_t *sD, const uint32_t *yc, int k, bool live) {
+    const int myCnt = wsumC[lane];
+    const int T = __reduce_add_sync(kFull, myCnt);
     if (T == 0) {
       __syncthreads();
       return;
+    }
+    int candBase = 0;
+    if (warp < T) {  // only warps that will own a candidate need the per-warp bases
+      int tot;
+      candBase = warp_excl_scan(myCnt, lane, tot);
     }
     for (int g0 = 0; g0 < T; g0 += kResMax) {
       const int nR = min(kResMax, T - g0);
@@ -321,36 +384,32 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
         const int di = sD[i], dn1 = sD[i + 1];
         int lo = i, hi = i + 1;
         bool extends = false;
-        if (di <= dn1) {
-          lo = search_up(sD, wm, i, di, lane);
-          extends = live && any_same_allele(yc, lo, i, yi, lane);
-        }
-        if (!extends && di >= dn1) {
-          hi = search_down(sD, wm, i + 1, dn1, M, lane);
-          extends = live && any_same_allele(yc, i + 1, hi, yi, lane);
-        }
+        if (di <= dn1) extends = scan_up(sD, yc, wmaxS, i, yi, di, live, lane, lo);
+        if (!extends && di >= dn1) extends = scan_down(sD, yc, wmaxS, i, yi, dn1, M, live, lane, hi);
         if (lane == 0) resS[g - g0] = make_int4(i, lo, hi, extends ? 0 : (i - lo) + (hi - i - 1));
       }
       __syncthreads();  // the round's results are published (first round: the scatter is complete too)
       long long roundTotal = 0;
       for (int c0 = 0; c0 < nR; c0 += 32) {
-        const int4 en = c0 + lane < nR ? resS[c0 + lane] : make_int4(0, 0, 0, 0);
-        int tot;
-        const int ex = warp_excl_scan(en.w, lane, tot);
+        const int cntL = c0 + lane < nR ? resS[c0 + lane].w : 0;  // record count of entry c0 + lane
+        const int tot = __reduce_add_sync(kFull, cntL);
         if (sink.pool && tot) {
           const long long base = recBase + roundTotal;
           ensure_chunks(base + tot);
           // entry c0 + warp is this warp's own (candidate g = g0 + c0 + warp); big blocks are shared by all warps
-          const int mi = __shfl_sync(kFull, en.x, warp), mlo = __shfl_sync(kFull, en.y, warp);
-          const int mhi = __shfl_sync(kFull, en.z, warp), mcnt = __shfl_sync(kFull, en.w, warp);
-          const int mex = __shfl_sync(kFull, ex, warp);
-          if (mcnt > 0 && mcnt < kBigBlock) emit_block(sink, base + mex, sA, mi, mlo, mhi, sD[mi], sD[mi + 1], k, lane, 32);
-          unsigned big = __ballot_sync(kFull, en.w >= kBigBlock);
+          const int mcnt = __shfl_sync(kFull, cntL, warp);
+          if (mcnt > 0 && mcnt < kBigBlock) {
+            const int4 en = resS[c0 + warp];
+            const int mex = __reduce_add_sync(kFull, lane < warp ? cntL : 0);
+            emit_block(sink, base + mex, sA, en.x, en.y, en.z, sD[en.x], sD[en.x + 1], k, lane, 32);
+          }
+          unsigned big = __ballot_sync(kFull, cntL >= kBigBlock);
           while (big) {
             const int j = __ffs(big) - 1;
             big &= big - 1;
-            const int bi = __shfl_sync(kFull, en.x, j), blo = __shfl_sync(kFull, en.y, j), bhi = __shfl_sync(kFull, en.z, j);
-            emit_block(sink, base + __shfl_sync(kFull, ex, j), sA, bi, blo, bhi, sD[bi], sD[bi + 1], k, tid, kThreads);
+            const int4 en = resS[c0 + j];
+            const int bex = __reduce_add_sync(kFull, lane < j ? cntL : 0);
+            emit_block(sink, base + bex, sA, en.x, en.y, en.z, sD[en.x], sD[en.x + 1], k, tid, kThreads);
           }
         }
         roundTotal += tot;
@@ -370,7 +429,6 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     mbar_wait(&mbar[stage], (uint32_t)(it / kStages) & 1u);
     const uint32_t *col = smem + L::xcol + stage * L::STAGE;
     uint32_t *yc = smem + L::ycol;
-    int32_t *wmaxC = wmaxS;
     if (WITH_D) {  // sentinels of state k (pbwtCore.c:414,507), written by the threads that read them below
       if (tid == 0) sI[dC] = k + 1;
       if (tid == ownerM) sI[dC + M] = k + 1;
@@ -387,6 +445,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
       } else pb = col[wordBase - 1] >> 31;
     }
     const uint32_t pbFirst = pb;
+    const bool storeY = lane == 0 && (MATCH || QUERY || p.yOut != nullptr);  // the sorted column, when someone consumes it
     int carry = 0;         // max d since the last run head, over completed words (uniform)
     int lmax = 0;          // per-lane max of d over head-free words since then (reduced lazily)
     bool anyHead = false;  // has this warp seen a run head
@@ -409,23 +468,19 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
         if (H) bnd |= 1u << e;
         if (e > 0 && (H & 1u)) bnd |= 1u << (e - 1);  // a head at lane 0 makes the previous word's last lane a tail
       }
-      if (lane == 0) yc[wordBase + e] = Bw;
+      if (storeY) yc[wordBase + e] = Bw;
       if (WITH_D) {
         const int dv = sLane[dC + e * 32];
-        int wm = 0;
-        if (MATCH) {
-          wm = __reduce_max_sync(kFull, dv);
-          if (lane == 0) wmaxC[wordBase + e] = wm;
+        if (MATCH) {  // word maximum of d: lets the match scans skip over long blocks 1024 positions per step
+          const int wm = __reduce_max_sync(kFull, dv);
+          if (lane == 0) wmaxS[wordBase + e] = wm;
         }
         if (H == 0u) {
           dn[e] = dv;
-          if (MATCH) carry = max(carry, wm);
-          else lmax = max(lmax, dv);
+          lmax = max(lmax, dv);
         } else {
-          if (!MATCH) {
-            carry = max(carry, __reduce_max_sync(kFull, lmax));
-            lmax = 0;
-          }
+          carry = max(carry, __reduce_max_sync(kFull, lmax));
+          lmax = 0;
           int v = dv;  // inclusive max since the nearest head at or below this lane
 #pragma unroll
           for (int dl = 1; dl < 32; dl <<= 1) {
@@ -451,7 +506,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
       if (QUERY && lane == 0) sI[L::zloc + wordBase + e] = zw;  // zeros of this warp before the word
       zw += __popc(~Bw);
     }
-    if (WITH_D && !MATCH) carry = max(carry, __reduce_max_sync(kFull, lmax));
+    if (WITH_D) carry = max(carry, __reduce_max_sync(kFull, lmax));
     if (lane == 0) {
       wsumZ[warp] = zw;
       if (WITH_D) wsumR[warp] = (anyHead ? 0x80000000u : 0u) | (uint32_t)carry;
@@ -537,7 +592,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     if (p.cOut && tid == 0) p.cOut[k + colShift] = c;
 
     // ---------------- matchMaximalWithin on state k (holds the S2 barrier) ----------------
-    if (MATCH) match_rounds(sI + aC, sI + dC, yc, wmaxC, k, true);
+    if (MATCH) match_rounds(sI + aC, sI + dC, yc, k, true);
     else if (!QUERY) __syncthreads();  // S2: scatter complete
     if (QUERY) {
       // ---------------- matchSequencesSweep on state k (pbwtMatch.c:376-426), one thread per query ----------------
@@ -674,7 +729,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
   }
   if (MATCH && p.reportAtN && !p.perWindowSites && k1 == nTotal) {  // k == N: nothing extends, every block is reported
     const uint32_t *yc = smem + L::ycol;                           // alleles are not consulted when live == false
-    for (int w = warp; w < L::WORDS; w += 32) {                    // word maxima of the final d
+    for (int w = warp; w < L::WORDS; w += 32) {  // word maxima of the final d
       const int wm = __reduce_max_sync(kFull, sI[dC + w * 32 + lane]);
       if (lane == 0) wmaxS[w] = wm;
     }
@@ -688,7 +743,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     tw = __reduce_add_sync(kFull, tw);
     if (lane == 0) wsumC[warp] = tw;
     __syncthreads();
-    match_rounds(sI + aC, sI + dC, yc, wmaxS, nTotal, false);
+    match_rounds(sI + aC, sI + dC, yc, nTotal, false);
   }
   if (MATCH && p.recCount && tid == 0) p.recCount[win] = (unsigned long long)recBase;
   if (p.winNanos && tid == 0) {
