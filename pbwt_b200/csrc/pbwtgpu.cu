@@ -23,6 +23,7 @@ struct pbwtgpu_ctx {
   long long optWindows = 0;    // 0 = automatic
   long long optMatchCap = 0;   // 0 = automatic
   long long optWindowTimes = 0;  // debugging: print per-window CTA times of pass 2 to stderr
+  long long optNoCandidates = 0;  // profiling aid
   long long optForceGlobal = 0;  // testing: use the global-memory kernel even for narrow panels
   // profiling
   bool profile = false;
@@ -451,6 +452,7 @@ struct WindowedSweep {
     a.yOut = yOut;
     a.recCount = recCount; a.chunkCounter = chunkCounter;
     a.reportAtN = 1;
+    a.debugNoCandidates = (int)ctx->optNoCandidates;
     std::vector<unsigned long long> counts(W, 0);
     long long *winNanos = nullptr;
     if (ctx->optWindowTimes) {
@@ -643,6 +645,7 @@ int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value) {
   else if (!strcmp(name, "match_capacity")) ctx->optMatchCap = value;
   else if (!strcmp(name, "window_times")) ctx->optWindowTimes = value;
   else if (!strcmp(name, "force_global")) ctx->optForceGlobal = value;
+  else if (!strcmp(name, "debug_no_candidates")) ctx->optNoCandidates = value;
   else return fail(ctx, PBWTGPU_ERR_ARG, "unknown option %s", name);
   return 0;
 }

@@ -43,6 +43,7 @@ struct SweepArgs {
   unsigned long long *recCount;  // [W] records produced by each window
   int reportAtN;                 // the window that ends at N also reports the k == N blocks
   long long *winNanos;           // [W] optional: wall time of each window's CTA (globaltimer, debugging aid)
+  int debugNoCandidates;         // profiling aid: publish zero match candidates per site (sweep-side cost only)
   // query sweep (matchSequencesSweep, pbwtMatch.c:363-443): single window, sorted mode, with d
   const uint32_t *qcols;         // [N][qwpc] sorted query columns
   int qwpc, Q;

@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
         tw += __popc(m);
       }
       if (lane < E) cmaskS[wordBase + lane] = myMask;
-      if (lane == 0) wsumC[warp] = tw;
+      if (lane == 0) wsumC[warp] = p.debugNoCandidates ? 0 : tw;
     }
     __syncthreads();  // S1: ballots, warp sums, match candidates published; everyone is done with col[]
 

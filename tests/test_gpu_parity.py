@@ -333,3 +333,11 @@ def test_site_shards_sequential(eng, orc, M, N, R, W, dens, with_start):
     assert len(got) == n and (got == rec).all()
     assert (outs[-1]["a_end"] == a_end).all() and (outs[-1]["d_end"] == d_end).all()
     assert all((o["a_end"] == -1).all() for o in outs[:-1])
+
+
+def test_smem_limit_without_matches(eng, orc):
+    """M between the match kernel's limit (12,544) and the shared-memory limit (13,312): a/d/pack3 only."""
+    rng = np.random.default_rng(13)
+    M, N = 13312, 10
+    hap = (rng.random((M, N)) < 0.3).astype(np.uint8)
+    check_build(eng, orc, O.pack_panel(hap), M, N, matches=False)
