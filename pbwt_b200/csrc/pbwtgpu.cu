@@ -889,10 +889,25 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
                         int64_t *nmatch, pbwtgpu_nomatch **nomatch, int64_t *nnomatch) {
   if (!ctx || !matches || !nmatch || M < 1 || Q < 1 || N < 0) return fail(ctx, PBWTGPU_ERR_ARG, "match_sweep: bad args");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  if (M > query_sweep_max_m() || Q > query_sweep_max_q(M))
-    return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "match_sweep: panel M=%d (max %d) or Q=%d (max %d) beyond the shared-memory kernel",
-                M, query_sweep_max_m(), Q, query_sweep_max_q(M));
+  // narrow panels: state in shared memory; wide panels: state in global memory, a group of cooperating CTAs
+  const bool wide = M > query_sweep_max_m() || ctx->optForceGlobal;
+  const int maxQ = wide ? query_sweep_global_max_q() : query_sweep_max_q(M);
+  if (Q > maxQ) return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "match_sweep: Q=%d exceeds %d queries per call", Q, maxQ);
   Temps tmp(ctx);
+  int G = 1, chunk = 0, Wd = 1;
+  int32_t *gA = nullptr, *gD = nullptr, *zpre = nullptr;
+  uint32_t *gPart = nullptr, *ySorted = nullptr;
+  char *gSync = nullptr;
+  if (wide) {
+    sweep_global_plan(M, ctx->smCount, 1, &G, &chunk, &Wd);
+    const size_t MS = (size_t)G * chunk, WG = MS / 32;
+    if (int rc = tmp.get(&gA, 2 * MS)) return rc;
+    if (int rc = tmp.get(&gD, 2 * (MS + 4))) return rc;
+    if (int rc = tmp.get(&gPart, (size_t)G * 4)) return rc;
+    if (int rc = tmp.get(&gSync, sweep_global_sync_bytes(1))) return rc;
+    if (int rc = tmp.get(&ySorted, 2 * WG)) return rc;
+    if (int rc = tmp.get(&zpre, 2 * WG)) return rc;
+  }
   uint32_t *pcols = nullptr, *qcols = nullptr;
   if (int rc = decode_stream(ctx, tmp, pyz, npyz, M, N, &pcols, nullptr)) return rc;
   if (int rc = decode_stream(ctx, tmp, qyz, nqyz, Q, N, &qcols, nullptr)) return rc;
@@ -931,7 +946,13 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
     a.nomatch = nm; a.nomatchCap = nmCap; a.qCounts = counts;
     {
       ScopedTimer t(ctx, PBWTGPU_K_QUERY);
-      CUDA_TRY(ctx, launch_query_sweep_smem(a, ctx->stream));
+      if (wide) {
+        CUDA_TRY(ctx, cudaMemsetAsync(gPart, 0, sizeof(uint32_t) * (size_t)G * 4, ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(gSync, 0, sweep_global_sync_bytes(1), ctx->stream));
+        CUDA_TRY(ctx, launch_query_sweep_global(a, G, chunk, gA, gD, gPart, gSync, ySorted, zpre, ctx->stream));
+      } else {
+        CUDA_TRY(ctx, launch_query_sweep_smem(a, ctx->stream));
+      }
       ctx->launches[PBWTGPU_K_QUERY] += 1;
     }
     int used = 0;

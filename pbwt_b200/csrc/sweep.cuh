@@ -55,6 +55,23 @@ struct SweepArgs {
 
 enum SweepMode { kGather = 0, kSorted = 1 };
 
+constexpr int kTabMirror = 64;  // newest chunk ids of a window mirrored in shared memory
+
+#ifdef __CUDACC__
+// Where a window's records go: chunks of kRecChunk records drawn from a global pool.
+struct RecSink {
+  int4 *pool;           // NULL = count only
+  const int *tab;       // this window's chunk table (global)
+  const int *mirror;    // shared-memory mirror of the newest kTabMirror entries
+  int nChunks;          // chunks allocated so far (uniform)
+  __device__ __forceinline__ void put(long long o, int4 rec) const {
+    const int c = (int)(o >> kRecChunkLog);
+    const int id = (nChunks - c <= kTabMirror) ? mirror[c & (kTabMirror - 1)] : __ldcg(tab + c);
+    if (id >= 0) pool[((long long)id << kRecChunkLog) + (o & (kRecChunk - 1))] = rec;
+  }
+};
+#endif
+
 // largest M the shared-memory-resident kernel handles with / without the divergence array
 int sweep_smem_max_m(bool with_d);
 // returns cudaError_t as int
@@ -73,5 +90,9 @@ size_t sweep_global_sync_bytes(int W);
 // partials: W*G*4 uint32 and gsync: sweep_global_sync_bytes(W), both zeroed before every launch
 int launch_sweep_global(const SweepArgs &a, SweepMode mode, bool with_d, int G, int chunk, int32_t *aBuf, int32_t *dBuf,
                         uint32_t *partials, void *gsync, cudaStream_t stream);
+// query sweep over a wide panel: one window, sorted mode, with d; ySorted / zpre: 2*G*chunk/32 words each
+int launch_query_sweep_global(const SweepArgs &a, int G, int chunk, int32_t *aBuf, int32_t *dBuf, uint32_t *partials,
+                              void *gsync, uint32_t *ySorted, int32_t *zpre, cudaStream_t stream);
+int query_sweep_global_max_q();
 
 }  // namespace pbwtgpu

@@ -50,13 +50,22 @@ __device__ __forceinline__ uint32_t rm_combine(uint32_t a, uint32_t b) {  // a e
   return (b >> 31) ? b : ((a & 0x80000000u) | max(a & 0x7fffffffu, b));
 }
 
-template <int MODE, bool WITH_D>
+constexpr int kQCap = 1024;  // queries handled by the query sweep (one thread each, CTA 0 of the group)
+
+template <int MODE, bool WITH_D, bool QUERY = false>
 __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepArgs p, int G, int chunk, int32_t *aBuf,
-                                                                   int32_t *dBuf, uint32_t *partials, GroupSync *gsync) {
+                                                                   int32_t *dBuf, uint32_t *partials, GroupSync *gsync,
+                                                                   uint32_t *ySorted, int32_t *zpre) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int chunkWords = chunk / 32;
   uint32_t *ycolS = smem;                                               // [chunkWords]
   int32_t *dnS = reinterpret_cast<int32_t *>(smem + chunkWords);        // [chunk] (WITH_D)
+  // query sweep only: warp-local zero prefix per word, per-query state, chunk-id mirror, per-warp sums
+  int32_t *zlocS = dnS + (WITH_D ? chunk : 0);                          // [chunkWords]
+  int32_t *qfS = zlocS + chunkWords, *qeS = qfS + kQCap, *qaS = qeS + kQCap;  // qaS: [2][kQCap]
+  int32_t *ctabS = qaS + 2 * kQCap;                                     // [kTabMirror]
+  int32_t *wsq = ctabS + kTabMirror;                                    // [96]
+  __shared__ int wexS[32];      // zeros in this CTA's warps below each warp
   __shared__ int wsumZ[32];
   __shared__ uint32_t wsumR[32];
   __shared__ int xZ, xC;        // zeros before this CTA, zeros in the whole column
@@ -98,6 +107,36 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     ++epoch;
     __syncthreads();
   };
+
+  RecSink sink;
+  sink.pool = QUERY ? reinterpret_cast<int4 *>(p.recPool) : nullptr;
+  sink.tab = QUERY ? p.chunkTab : nullptr;
+  sink.mirror = ctabS;
+  sink.nChunks = 0;
+  long long recBase = 0, nmBase = 0;
+  uint32_t qWord = 0;
+  auto ensure_chunks = [&](long long upTo) {  // CTA 0 only
+    const int need = (int)((upTo + kRecChunk - 1) >> kRecChunkLog);
+    if (need > sink.nChunks) {
+      if (tid == 0)
+        for (int c2 = sink.nChunks; c2 < need; ++c2) {
+          int id = atomicAdd(p.chunkCounter, 1);
+          if (id >= p.poolChunks) id = -1;
+          p.chunkTab[c2] = id;
+          ctabS[c2 & (kTabMirror - 1)] = id;
+        }
+      sink.nChunks = need;
+      __syncthreads();
+    }
+  };
+  if (QUERY && g == 0) {
+    for (int i = tid; i < kQCap; i += kThreads) {
+      qfS[i] = 0;
+      qeS[i] = 0;
+      qaS[i] = i < p.Q ? (p.qaStart ? p.qaStart[i] : i) : 0;
+    }
+    if (tid < p.Q && k0 < k1) qWord = p.qcols[(size_t)(k0 + colShift) * p.qwpc + warp];
+  }
 
   // ---- window start state ----
   for (int i = p0 + tid; i < p0 + chunk; i += kThreads) {
@@ -162,6 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
         const uint32_t H = Bw ^ ((Bw << 1) | pb);
         pb = Bw >> 31;
         if (lane == 0) ycolS[wordBase + e] = Bw;
+        if (QUERY && lane == 0) zlocS[wordBase + e] = zw;  // zeros of this warp before the word
         if (WITH_D) {
           int dv = dB[u];
           if (i == 0) dv = k + 1;  // sentinel d[0] (pbwtCore.c:414,507)
@@ -244,6 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
         }
       }
       if (lane == 0) { xZ = zBefore; xC = zAll; xR = rBefore; }
+      wexS[lane] = zExLane;
     }
     __syncthreads();
     const int c = xC;
@@ -253,6 +294,16 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
       const uint32_t below = __shfl_sync(kFull, rInc, warp > 0 ? warp - 1 : 0);
       const uint32_t comb = warp > 0 ? rm_combine(xR, below) : xR;
       cIn = (int)(comb & 0x7fffffffu);
+    }
+
+    const int par = (k - k0) & 1;
+    const int WG = G * chunkWords;  // words of the whole (padded) sorted column
+    if (QUERY) {  // publish this CTA's part of the sorted column and of the zero prefix, then meet the group
+      for (int w = tid; w < chunkWords; w += kThreads) {
+        ySorted[(size_t)par * WG + p0 / 32 + w] = ycolS[w];
+        zpre[(size_t)par * WG + p0 / 32 + w] = xZ + wexS[w / EW] + zlocS[w];
+      }
+      group_barrier();
     }
 
     // ---------------- phase C: scatter ----------------
@@ -297,8 +348,114 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
       }
     }
     if (p.cOut && g == 0 && tid == 0) p.cOut[k + colShift] = c;
+    if (QUERY && g == 0) {
+      // ---------------- matchSequencesSweep on state k (pbwtMatch.c:376-426), one thread per query ----------------
+      const uint32_t *yk = ySorted + (size_t)par * WG;
+      const int32_t *zk = zpre + (size_t)par * WG;
+      auto dAt = [&](int idx) { return (idx == 0 || idx == M) ? k + 1 : __ldcg(dC + idx); };
+      auto yAt = [&](int j) { return (__ldcg(yk + (j >> 5)) >> (j & 31)) & 1u; };
+      const bool active = tid < p.Q;
+      const uint32_t x = active ? (qWord >> lane) & 1u : 1u;
+      if (active && k + 1 < k1) qWord = p.qcols[(size_t)(k + 1 + colShift) * p.qwpc + warp];
+      const int qC = par * kQCap, qN = (par ^ 1) * kQCap;
+      const int jj = active ? qaS[qC + tid] : 0;
+      int f = qfS[jj], e = qeS[jj];
+      int repLo = 0, repHi = 0, repStart = 0;
+      bool nm = false;
+      if (active && yAt(f) != x) {
+        int hi = f + 1;
+        bool moved = false;
+        while (hi < M && dAt(hi) <= e) {  // an alternate of the same length that extends? (pbwtMatch.c:381-383)
+          if (yAt(hi) == x) { f = hi; moved = true; break; }
+          ++hi;
+        }
+        if (!moved) {
+          repLo = f; repHi = hi; repStart = e;  // report [f, hi) with start e (pbwtMatch.c:385)
+          int lo = f;
+          int dDown = hi < M ? dAt(hi) : k;
+          int dUp = dAt(lo);
+          for (;;) {  // reseed by divergence tiers, upper side first on ties (pbwtMatch.c:389-411)
+            if (dUp <= dDown) {
+              int top = -1;
+              while (lo > 0 && dAt(lo) <= dUp) {
+                --lo;
+                if (yAt(lo) == x) top = lo;
+              }
+              if (top >= 0) { f = top; e = dUp; break; }
+              dUp = dAt(lo);
+            } else {
+              bool hit = false;
+              while (hi < M && dAt(hi) <= dDown) {
+                if (yAt(hi) == x) { f = hi; e = dDown; hit = true; break; }
+                ++hi;
+              }
+              if (hit) break;
+              dDown = hi == M ? k : dAt(hi);
+              if (lo == 0 && hi == M) { nm = true; e = k + 1; break; }
+            }
+          }
+        }
+      }
+      {  // FM step (pbwtCursorCalculateU + pbwtCursorMap, pbwtCore.c:510-519, pbwt.h:130; pbwtMatch.c:417-423)
+        const int fw = f >> 5;
+        const int Z = __ldcg(zk + fw) + __popc(~__ldcg(yk + fw) & lanemask_lt(f & 31));
+        int nf = x ? c + f - Z : Z;
+        if (nf == M) nf = 0;
+        if (active) { qfS[jj] = nf; qeS[jj] = e; }
+      }
+      const int cnt = repHi - repLo;
+      int cntTot;
+      const int cntEx = warp_excl_scan(cnt, lane, cntTot);
+      const unsigned nmBal = __ballot_sync(kFull, nm), qzBal = __ballot_sync(kFull, active && x == 0u);
+      if (lane == 0) { wsq[warp] = cntTot; wsq[32 + warp] = __popc(nmBal); wsq[64 + warp] = __popc(qzBal); }
+      __syncthreads();
+      int recTot, nmTot, cq;
+      const int recEx = __shfl_sync(kFull, warp_excl_scan(wsq[lane], lane, recTot), warp);
+      const int nmEx = __shfl_sync(kFull, warp_excl_scan(wsq[32 + lane], lane, nmTot), warp);
+      const int qzEx = __shfl_sync(kFull, warp_excl_scan(wsq[64 + lane], lane, cq), warp);
+      if (sink.pool && recTot) {
+        ensure_chunks(recBase + recTot);
+        long long o = recBase + recEx + cntEx;
+        for (int i = repLo; i < repHi; ++i, ++o) sink.put(o, make_int4(jj, __ldcg(aC + i), repStart, k));
+      }
+      if (nm && p.nomatch) {
+        const long long o = nmBase + nmEx + __popc(nmBal & ltMask);
+        if (o < p.nomatchCap) p.nomatch[o] = pbwtgpu_nomatch{jj, (int)x, k};
+      }
+      recBase += recTot;
+      nmBase += nmTot;
+      if (active) {  // query cursor step (pbwtCursorForwardsRead on uq, pbwtMatch.c:426)
+        const int zb = qzEx + __popc(qzBal & ltMask);
+        qaS[qN + (x ? cq + tid - zb : zb)] = jj;
+      }
+      __syncthreads();  // wsq is reused at the next site
+    }
     group_barrier();
     cur ^= 1;
+  }
+
+  if (QUERY && g == 0) {  // matches still open at N (pbwtMatch.c:430-436): a[f], then every following i with d[i] <= e
+    const int32_t *aE = aW + (size_t)cur * MS;
+    const int32_t *dE = dW + (size_t)cur * (MS + 4);
+    const bool active = tid < p.Q;
+    const int jj = active ? qaS[((k1 - k0) & 1) * kQCap + tid] : 0;
+    const int f = qfS[jj], e = qeS[jj];
+    int hi = f + 1;
+    if (active) while (hi < M && __ldcg(dE + hi) <= e) ++hi;
+    const int cnt = active ? hi - f : 0;
+    int cntTot;
+    const int cntEx = warp_excl_scan(cnt, lane, cntTot);
+    if (lane == 0) wsq[warp] = cntTot;
+    __syncthreads();
+    int recTot;
+    const int recEx = __shfl_sync(kFull, warp_excl_scan(wsq[lane], lane, recTot), warp);
+    if (sink.pool && recTot) {
+      ensure_chunks(recBase + recTot);
+      long long o = recBase + recEx + cntEx;
+      for (int i = f; i < f + cnt; ++i, ++o) sink.put(o, make_int4(jj, __ldcg(aE + i), e, nTotal));
+    }
+    recBase += recTot;
+    if (tid == 0 && p.qCounts) { p.qCounts[0] = (unsigned long long)recBase; p.qCounts[1] = (unsigned long long)nmBase; }
   }
 
   // ---- window end ----
@@ -346,8 +503,27 @@ int launch_sweep_global(const SweepArgs &a, SweepMode mode, bool with_d, int G, 
   if (err != cudaSuccess) return (int)err;
   SweepArgs args = a;
   GroupSync *gs = static_cast<GroupSync *>(gsync);
-  void *params[] = {&args, &G, &chunk, &aBuf, &dBuf, &partials, &gs};
+  uint32_t *ys = nullptr;
+  int32_t *zp = nullptr;
+  void *params[] = {&args, &G, &chunk, &aBuf, &dBuf, &partials, &gs, &ys, &zp};
   err = cudaLaunchCooperativeKernel(kern, dim3(a.nWindows * G), dim3(kThreads), params, smemBytes, stream);
+  return (int)err;
+}
+
+int query_sweep_global_max_q() { return kQCap; }
+
+int launch_query_sweep_global(const SweepArgs &a, int G, int chunk, int32_t *aBuf, int32_t *dBuf, uint32_t *partials,
+                              void *gsync, uint32_t *ySorted, int32_t *zpre, cudaStream_t stream) {
+  if (a.Q < 1 || a.Q > kQCap) return (int)cudaErrorInvalidValue;
+  const size_t smemBytes = (size_t)(chunk / 32) * 4 * 2 + (size_t)chunk * 4 + (size_t)(4 * kQCap + kTabMirror + 96) * 4;
+  void *kern = (void *)sweep_global_kernel<kSorted, true, true>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+  if (err != cudaSuccess) return (int)err;
+  SweepArgs args = a;
+  args.nWindows = 1;
+  GroupSync *gs = static_cast<GroupSync *>(gsync);
+  void *params[] = {&args, &G, &chunk, &aBuf, &dBuf, &partials, &gs, &ySorted, &zpre};
+  err = cudaLaunchCooperativeKernel(kern, dim3(G), dim3(kThreads), params, smemBytes, stream);
   return (int)err;
 }
 

@@ -36,7 +36,6 @@ constexpr int kThreads = 1024;
 constexpr int kStages = 3;
 constexpr int kResMax = 256;    // match candidates processed per round (multiple of 32)
 constexpr int kBigBlock = 128;  // records; larger blocks are emitted by the whole CTA
-constexpr int kTabMirror = 64;  // newest chunk ids of this window mirrored in shared memory
 
 template <int E, bool WITH_D, bool MATCH, bool QUERY = false>
 struct SmemLayout {  // offsets in 32-bit words; every array start is 16-byte aligned
@@ -190,19 +189,6 @@ __device__ __forceinline__ bool scan_down(const int32_t *sD, const uint32_t *yc,
   hi = min(r, M);
   return live && any_same_allele(yc, bot, hi, yi, lane);
 }
-
-// Where a window's records go: chunks of kRecChunk records drawn from a global pool.
-struct RecSink {
-  int4 *pool;           // NULL = count only
-  const int *tab;       // this window's chunk table (global)
-  const int *mirror;    // shared-memory mirror of the newest kTabMirror entries
-  int nChunks;          // chunks allocated so far (uniform)
-  __device__ __forceinline__ void put(long long o, int4 rec) const {
-    const int c = (int)(o >> kRecChunkLog);
-    const int id = (nChunks - c <= kTabMirror) ? mirror[c & (kTabMirror - 1)] : __ldcg(tab + c);
-    if (id >= 0) pool[((long long)id << kRecChunkLog) + (o & (kRecChunk - 1))] = rec;
-  }
-};
 
 // write the records of reporter i: upward block [lo, i) with start di, then downward block (i, hi) with
 // start dn1 (callback order, pbwtMatch.c:133-134); record t of the block is written by "lane" t0 + t*step

@@ -341,3 +341,32 @@ def test_smem_limit_without_matches(eng, orc):
     M, N = 13312, 10
     hap = (rng.random((M, N)) < 0.3).astype(np.uint8)
     check_build(eng, orc, O.pack_panel(hap), M, N, matches=False)
+
+
+@pytest.mark.parametrize("M,Q,N,dp,dq", [(60, 7, 80, 0.03, 0.3), (1000, 300, 120, 0.1, 0.1), (3000, 1000, 60, 0.05, 0.05)])
+def test_query_sweep_wide_kernel_forced(eng, orc, M, Q, N, dp, dq):
+    """The wide-panel query sweep (state in global memory) forced onto narrow panels."""
+    rng = np.random.default_rng(M + Q + 1)
+    hp = (rng.random((M, N)) < dp).astype(np.uint8)
+    hq = (rng.random((Q, N)) < dq).astype(np.uint8)
+    hq[0] = hp[M // 2]
+    pyz, qyz = _split_streams(orc, hp, hq)
+    want_rec, want_nom = orc.match_sweep(pyz, M, N, qyz, Q)
+    eng.set_option("force_global", 1)
+    try:
+        rec, nom = eng.match_sweep(pyz, M, N, qyz, Q)
+    finally:
+        eng.set_option("force_global", 0)
+    assert len(rec) == len(want_rec) and (rec == want_rec).all()
+    assert len(nom) == len(want_nom) and (nom == want_nom).all()
+
+
+def test_query_sweep_wide_panel(eng, orc):
+    """BASELINE config 5's shape class: a panel wider than shared memory (M = 40,000), 300 queries."""
+    M, Q, N = 40000, 300, 400
+    x = O.generate_panel(M + Q, N, seed=0x5EED0005, L=200, mu=6.0)
+    hap = O.unpack_panel(x, M + Q)
+    pyz, qyz = _split_streams(orc, hap[:M], hap[M:])
+    want_rec, want_nom = orc.match_sweep(pyz, M, N, qyz, Q)
+    rec, nom = eng.match_sweep(pyz, M, N, qyz, Q)
+    assert len(rec) == len(want_rec) and (rec == want_rec).all() and (nom == want_nom).all()
