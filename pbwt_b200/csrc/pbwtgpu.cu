@@ -197,9 +197,8 @@ struct WindowedSweep {
   bool sharded = false;
   bool useGlobal = false;
   int W = 1, G = 1, chunk = 0, spw = 1, nodes = 0, bits = 1, slots = 1, cur = 0;
-  int32_t *gA = nullptr, *gD = nullptr;
-  uint32_t *gPart = nullptr;
-  void *gSync = nullptr;
+  GlobalBuffers gb;  // wide panels: state, exchange and match-scan buffers of sweep_global.cu
+  bool matchWanted = false;
   // slot 0 = state entering window 0, slot w+1 = node w (after the scan: the state at the end of window w)
   int32_t *ord[2] = {nullptr, nullptr}, *dv[2] = {nullptr, nullptr}, *g[2] = {nullptr, nullptr}, *gfd[2] = {nullptr, nullptr};
   uint32_t *keys = nullptr;
@@ -216,10 +215,10 @@ struct WindowedSweep {
   int launch(const SweepArgs &args, SweepMode md, bool withD, bool withMatch) {
     if (!useGlobal) return launch_sweep_smem(args, md, withD, withMatch, ctx->stream);
     const int wl = std::max(W, 1);
-    cudaError_t e = cudaMemsetAsync(gPart, 0, sizeof(uint32_t) * (size_t)wl * G * 4, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(gSync, 0, sweep_global_sync_bytes(wl), ctx->stream);
+    cudaError_t e = cudaMemsetAsync(gb.partials, 0, sizeof(uint32_t) * (size_t)wl * G * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(gb.gsync, 0, sweep_global_sync_bytes(wl), ctx->stream);
     if (e != cudaSuccess) return (int)e;
-    return launch_sweep_global(args, md, withD, G, chunk, gA, gD, gPart, gSync, ctx->stream);
+    return launch_sweep_global(args, md, withD, withMatch, gb, ctx->stream);
   }
 
   int init(const uint32_t *src_, int wpc_, int M_, int N_, SweepMode mode_, const int32_t *aStartHost, bool wantMatch,
@@ -230,8 +229,7 @@ struct WindowedSweep {
     if (nTotal >= kPseudoLabelBase - 64) return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "N=%d too large", nTotal);
     // panels wider than one CTA's shared memory sweep with their state in global memory (sweep_global.cu)
     useGlobal = M > sweep_smem_max_m(true) || ctx->optForceGlobal;
-    if (useGlobal && wantMatch)
-      return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "maxWithin needs M <= %d (shared-memory kernel); M=%d", sweep_smem_max_m(true), M);
+    matchWanted = wantMatch;
     W = 1;
     positionSpace = mode == kSorted;
     if (M >= 2 && !(positionSpace && sharded_)) {
@@ -248,12 +246,19 @@ struct WindowedSweep {
     while ((1 << bits) < M) ++bits;
     if (useGlobal) {
       const size_t MS = (size_t)G * chunk;
-      if (int rc = tmp.get(&gA, (size_t)W * 2 * MS)) return rc;
-      if (int rc = tmp.get(&gD, (size_t)W * 2 * (MS + 4))) return rc;
-      if (int rc = tmp.get(&gPart, (size_t)W * G * 4)) return rc;
+      gb.G = G; gb.chunk = chunk;
+      if (int rc = tmp.get(&gb.aBuf, (size_t)W * 2 * MS)) return rc;
+      if (int rc = tmp.get(&gb.dBuf, (size_t)W * 2 * (MS + 4))) return rc;
+      if (int rc = tmp.get(&gb.partials, (size_t)W * G * 4)) return rc;
       char *sy = nullptr;
       if (int rc = tmp.get(&sy, sweep_global_sync_bytes(W))) return rc;
-      gSync = sy;
+      gb.gsync = sy;
+      if (wantMatch) {
+        if (int rc = tmp.get(&gb.ySorted, sweep_global_column_words(G, chunk, W))) return rc;
+        if (int rc = tmp.get(&gb.wmaxG, sweep_global_column_words(G, chunk, W))) return rc;
+        if (int rc = tmp.get(&gb.segCnt, (size_t)(N + 1) * G + 1)) return rc;
+        if (int rc = tmp.get(&gb.segSrc, (size_t)(N + 1) * G + 1)) return rc;
+      }
     }
     const bool needNodes = nodes > 0;
     for (int b = 0; b < (needNodes ? 2 : 1); ++b) {
@@ -459,12 +464,27 @@ struct WindowedSweep {
       if (int rc = tmp.get(&winNanos, (size_t)W)) return rc;
       a.winNanos = winNanos;
     }
+    // record streams: one per window (shared-memory kernel) or one per CTA (wide-panel kernel)
+    const int producers = useGlobal ? W * G : W;
+    const long long nSeg = useGlobal ? (long long)(N + 1) * G + 1 : 0;
+    long long *segDst = nullptr;
+    void *scanTemp = nullptr;
+    size_t scanTempBytes = 0;
+    long long segTotal = 0;
+    if (wantMatch && useGlobal) {
+      if (int rc = tmp.get(&segDst, (size_t)nSeg)) return rc;
+      scanTempBytes = segment_scan_temp_bytes(nSeg);
+      char *st = nullptr;
+      if (int rc = tmp.get(&st, scanTempBytes)) return rc;
+      scanTemp = st;
+    }
     for (int attempt = 0; attempt < 2; ++attempt) {
       if (wantMatch) {
-        poolChunks = (int)((recCap + kRecChunk - 1) >> kRecChunkLog) + W;
+        poolChunks = (int)((recCap + kRecChunk - 1) >> kRecChunkLog) + producers;
         if (int rc = tmp.get(&pool, (size_t)poolChunks << kRecChunkLog)) return rc;
-        if (int rc = tmp.get(&chunkTab, (size_t)W * poolChunks)) return rc;
+        if (int rc = tmp.get(&chunkTab, (size_t)producers * poolChunks)) return rc;
         CUDA_TRY(ctx, cudaMemsetAsync(chunkCounter, 0, sizeof(int), ctx->stream));
+        if (useGlobal) CUDA_TRY(ctx, cudaMemsetAsync(gb.segCnt, 0, sizeof(int32_t) * (size_t)nSeg, ctx->stream));
         a.recPool = pool; a.poolChunks = poolChunks; a.chunkTab = chunkTab;
       }
       {
@@ -474,12 +494,19 @@ struct WindowedSweep {
       }
       if (!wantMatch) break;
       int used = 0;
-      CUDA_TRY(ctx, cudaMemcpyAsync(counts.data(), recCount, sizeof(unsigned long long) * W, cudaMemcpyDeviceToHost, ctx->stream));
+      if (useGlobal) {
+        ScopedTimer t(ctx, PBWTGPU_K_AUX);
+        CUDA_TRY(ctx, launch_segment_scan(gb.segCnt, nSeg, segDst, scanTemp, scanTempBytes, ctx->stream));
+        ctx->launches[PBWTGPU_K_AUX] += 1;
+        CUDA_TRY(ctx, cudaMemcpyAsync(&segTotal, segDst + nSeg - 1, sizeof segTotal, cudaMemcpyDeviceToHost, ctx->stream));
+      } else {
+        CUDA_TRY(ctx, cudaMemcpyAsync(counts.data(), recCount, sizeof(unsigned long long) * W, cudaMemcpyDeviceToHost, ctx->stream));
+      }
       CUDA_TRY(ctx, cudaMemcpyAsync(&used, chunkCounter, sizeof used, cudaMemcpyDeviceToHost, ctx->stream));
       CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
       if (used <= poolChunks) break;
       if (attempt == 1) return fail(ctx, PBWTGPU_ERR_CUDA, "match record pool overflow persisted");
-      long long total = 0;  // the pool was too small: every window's count is known now, size it exactly and rerun
+      long long total = segTotal;  // the pool was too small: every count is known now, size it exactly and rerun
       for (auto cnt : counts) total += (long long)cnt;
       recCap = total;
     }
@@ -491,7 +518,14 @@ struct WindowedSweep {
       for (int w = 0; w < W; ++w) fprintf(stderr, " %d:%.0f/%llu", w, ns[w] * 1e-3, counts[w]);
       fprintf(stderr, "\n");
     }
-    if (wantMatch) {
+    if (wantMatch && useGlobal) {
+      res->nrec = segTotal;
+      if (int rc = result_alloc(ctx, res, &res->rec, (size_t)std::max<long long>(segTotal, 1))) return rc;
+      ScopedTimer t(ctx, PBWTGPU_K_AUX);
+      CUDA_TRY(ctx, launch_gather_segments(pool, chunkTab, poolChunks, gb.segCnt, gb.segSrc, segDst, nSeg - 1, G, spw, N, W,
+                                           res->rec, ctx->stream));
+      ctx->launches[PBWTGPU_K_AUX] += 1;
+    } else if (wantMatch) {
       std::vector<long long> offs(W, 0);
       long long total = 0;
       int maxChunks = 0;
@@ -890,23 +924,38 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
   if (!ctx || !matches || !nmatch || M < 1 || Q < 1 || N < 0) return fail(ctx, PBWTGPU_ERR_ARG, "match_sweep: bad args");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   // narrow panels: state in shared memory; wide panels: state in global memory, a group of cooperating CTAs
-  const bool wide = M > query_sweep_max_m() || ctx->optForceGlobal;
+  // (more queries than the shared-memory kernel holds also go to the wide kernel, which spreads them over its CTAs)
+  const bool wide = M > query_sweep_max_m() || ctx->optForceGlobal || Q > query_sweep_max_q(M);
   const int maxQ = wide ? query_sweep_global_max_q() : query_sweep_max_q(M);
   if (Q > maxQ) return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "match_sweep: Q=%d exceeds %d queries per call", Q, maxQ);
   Temps tmp(ctx);
   int G = 1, chunk = 0, Wd = 1;
-  int32_t *gA = nullptr, *gD = nullptr, *zpre = nullptr;
-  uint32_t *gPart = nullptr, *ySorted = nullptr;
-  char *gSync = nullptr;
+  GlobalBuffers gb;
+  long long nSeg = 0;
+  long long *segDst = nullptr;
+  char *scanTemp = nullptr;
+  size_t scanTempBytes = 0;
   if (wide) {
     sweep_global_plan(M, ctx->smCount, 1, &G, &chunk, &Wd);
-    const size_t MS = (size_t)G * chunk, WG = MS / 32;
-    if (int rc = tmp.get(&gA, 2 * MS)) return rc;
-    if (int rc = tmp.get(&gD, 2 * (MS + 4))) return rc;
-    if (int rc = tmp.get(&gPart, (size_t)G * 4)) return rc;
-    if (int rc = tmp.get(&gSync, sweep_global_sync_bytes(1))) return rc;
-    if (int rc = tmp.get(&ySorted, 2 * WG)) return rc;
-    if (int rc = tmp.get(&zpre, 2 * WG)) return rc;
+    const size_t MS = (size_t)G * chunk;
+    gb.G = G; gb.chunk = chunk;
+    nSeg = (long long)(N + 1) * G + 1;
+    char *sy = nullptr;
+    if (int rc = tmp.get(&gb.aBuf, 2 * MS)) return rc;
+    if (int rc = tmp.get(&gb.dBuf, 2 * (MS + 4))) return rc;
+    if (int rc = tmp.get(&gb.partials, (size_t)G * 4)) return rc;
+    if (int rc = tmp.get(&sy, sweep_global_sync_bytes(1))) return rc;
+    gb.gsync = sy;
+    if (int rc = tmp.get(&gb.ySorted, sweep_global_column_words(G, chunk, 1))) return rc;
+    if (int rc = tmp.get(&gb.wmaxG, sweep_global_column_words(G, chunk, 1))) return rc;
+    if (int rc = tmp.get(&gb.zpre, sweep_global_column_words(G, chunk, 1))) return rc;
+    if (int rc = tmp.get(&gb.segCnt, (size_t)nSeg)) return rc;
+    if (int rc = tmp.get(&gb.segSrc, (size_t)nSeg)) return rc;
+    if (int rc = tmp.get(&gb.qf, (size_t)Q)) return rc;
+    if (int rc = tmp.get(&gb.qe, (size_t)Q)) return rc;
+    if (int rc = tmp.get(&segDst, (size_t)nSeg)) return rc;
+    scanTempBytes = segment_scan_temp_bytes(nSeg);
+    if (int rc = tmp.get(&scanTemp, scanTempBytes)) return rc;
   }
   uint32_t *pcols = nullptr, *qcols = nullptr;
   if (int rc = decode_stream(ctx, tmp, pyz, npyz, M, N, &pcols, nullptr)) return rc;
@@ -930,11 +979,14 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
   pbwtgpu_nomatch *nm = nullptr;
   unsigned long long got[2] = {0, 0};
   int poolChunks = 0;
+  const int producers = wide ? G : 1;
   for (int attempt = 0; attempt < 2; ++attempt) {
-    poolChunks = (int)((recCap + kRecChunk - 1) >> kRecChunkLog) + 1;
+    poolChunks = (int)((recCap + kRecChunk - 1) >> kRecChunkLog) + producers;
     if (int rc = tmp.get(&pool, (size_t)poolChunks << kRecChunkLog)) return rc;
-    if (int rc = tmp.get(&chunkTab, (size_t)poolChunks)) return rc;
+    if (int rc = tmp.get(&chunkTab, (size_t)producers * poolChunks)) return rc;
     if (int rc = tmp.get(&nm, (size_t)nmCap)) return rc;
+    if (wide)
+      if (int rc = tmp.get(&gb.nmKeys, (size_t)nmCap)) return rc;
     CUDA_TRY(ctx, cudaMemsetAsync(chunkCounter, 0, sizeof(int), ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), ctx->stream));
     SweepArgs a{};
@@ -947,29 +999,50 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
     {
       ScopedTimer t(ctx, PBWTGPU_K_QUERY);
       if (wide) {
-        CUDA_TRY(ctx, cudaMemsetAsync(gPart, 0, sizeof(uint32_t) * (size_t)G * 4, ctx->stream));
-        CUDA_TRY(ctx, cudaMemsetAsync(gSync, 0, sweep_global_sync_bytes(1), ctx->stream));
-        CUDA_TRY(ctx, launch_query_sweep_global(a, G, chunk, gA, gD, gPart, gSync, ySorted, zpre, ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(gb.partials, 0, sizeof(uint32_t) * (size_t)G * 4, ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(gb.gsync, 0, sweep_global_sync_bytes(1), ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(gb.segCnt, 0, sizeof(int32_t) * (size_t)nSeg, ctx->stream));
+        CUDA_TRY(ctx, launch_query_sweep_global(a, gb, ctx->stream));
       } else {
         CUDA_TRY(ctx, launch_query_sweep_smem(a, ctx->stream));
       }
       ctx->launches[PBWTGPU_K_QUERY] += 1;
     }
     int used = 0;
+    long long segTotal = 0;
+    if (wide) {
+      ScopedTimer t(ctx, PBWTGPU_K_AUX);
+      CUDA_TRY(ctx, launch_segment_scan(gb.segCnt, nSeg, segDst, scanTemp, scanTempBytes, ctx->stream));
+      ctx->launches[PBWTGPU_K_AUX] += 1;
+      CUDA_TRY(ctx, cudaMemcpyAsync(&segTotal, segDst + nSeg - 1, sizeof segTotal, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CUDA_TRY(ctx, cudaMemcpyAsync(got, counts, sizeof got, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(&used, chunkCounter, sizeof used, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (wide) got[0] = (unsigned long long)segTotal;
     if (used <= poolChunks && (long long)got[1] <= nmCap) break;
     if (attempt == 1) return fail(ctx, PBWTGPU_ERR_CUDA, "query sweep buffer overflow persisted");
     recCap = std::max<long long>(recCap, (long long)got[0]);
     nmCap = std::max<long long>(nmCap, (long long)got[1]);
   }
   pbwtgpu_match *recDev = nullptr;
-  long long *offsDev = nullptr;
+  pbwtgpu_nomatch *nmSorted = nm;
   if (int rc = tmp.get(&recDev, (size_t)std::max<unsigned long long>(got[0], 1))) return rc;
-  if (int rc = tmp.get(&offsDev, 1)) return rc;
-  CUDA_TRY(ctx, cudaMemsetAsync(offsDev, 0, sizeof(long long), ctx->stream));
-  {
+  if (wide) {
+    {
+      ScopedTimer t(ctx, PBWTGPU_K_AUX);
+      CUDA_TRY(ctx, launch_gather_segments(pool, chunkTab, poolChunks, gb.segCnt, gb.segSrc, segDst, nSeg - 1, G, std::max(N, 1), N,
+                                           1, recDev, ctx->stream));
+      ctx->launches[PBWTGPU_K_AUX] += 1;
+    }
+    if (got[1]) {  // events were appended in arrival order: put them in (site, query-PBWT position) order
+      if (int rc = tmp.get(&nmSorted, (size_t)got[1])) return rc;
+      CUDA_TRY(ctx, sort_nomatch(gb.nmKeys, nm, (long long)got[1], nmSorted, ctx->stream));
+    }
+  } else {
+    long long *offsDev = nullptr;
+    if (int rc = tmp.get(&offsDev, 1)) return rc;
+    CUDA_TRY(ctx, cudaMemsetAsync(offsDev, 0, sizeof(long long), ctx->stream));
     ScopedTimer t(ctx, PBWTGPU_K_AUX);
     const int maxChunks = (int)((got[0] + kRecChunk - 1) >> kRecChunkLog);
     CUDA_TRY(ctx, launch_gather_records(pool, chunkTab, poolChunks, offsDev, counts, 1, maxChunks, recDev, ctx->stream));
@@ -979,7 +1052,7 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
   pbwtgpu_nomatch *hn = (pbwtgpu_nomatch *)malloc(sizeof(pbwtgpu_nomatch) * (size_t)std::max<unsigned long long>(got[1], 1));
   if (!hm || !hn) { free(hm); free(hn); return fail(ctx, PBWTGPU_ERR_NOMEM, "malloc records"); }
   if (got[0]) CUDA_TRY(ctx, cudaMemcpyAsync(hm, recDev, sizeof(pbwtgpu_match) * got[0], cudaMemcpyDeviceToHost, ctx->stream));
-  if (got[1]) CUDA_TRY(ctx, cudaMemcpyAsync(hn, nm, sizeof(pbwtgpu_nomatch) * got[1], cudaMemcpyDeviceToHost, ctx->stream));
+  if (got[1]) CUDA_TRY(ctx, cudaMemcpyAsync(hn, nmSorted, sizeof(pbwtgpu_nomatch) * got[1], cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   *matches = hm;
   *nmatch = (int64_t)got[0];

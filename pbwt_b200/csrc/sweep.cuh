@@ -87,12 +87,29 @@ int launch_query_sweep_smem(const SweepArgs &args, cudaStream_t stream);
 void sweep_global_plan(int M, int maxCtas, int wantWindows, int *G, int *chunk, int *W);
 size_t sweep_global_state_ints(int G, int chunk, int W, bool with_d);  // a (and d) double buffers, in int32
 size_t sweep_global_sync_bytes(int W);
-// partials: W*G*4 uint32 and gsync: sweep_global_sync_bytes(W), both zeroed before every launch
-int launch_sweep_global(const SweepArgs &a, SweepMode mode, bool with_d, int G, int chunk, int32_t *aBuf, int32_t *dBuf,
-                        uint32_t *partials, void *gsync, cudaStream_t stream);
-// query sweep over a wide panel: one window, sorted mode, with d; ySorted / zpre: 2*G*chunk/32 words each
-int launch_query_sweep_global(const SweepArgs &a, int G, int chunk, int32_t *aBuf, int32_t *dBuf, uint32_t *partials,
-                              void *gsync, uint32_t *ySorted, int32_t *zpre, cudaStream_t stream);
+size_t sweep_global_column_words(int G, int chunk, int W);  // words of ySorted / wmaxG / zpre (double buffered)
+// device buffers of a wide-panel launch.  partials (W*G*4 uint32) and gsync (sweep_global_sync_bytes(W)) must be
+// zeroed before every launch.
+struct GlobalBuffers {
+  int G = 1, chunk = 0;
+  int32_t *aBuf = nullptr, *dBuf = nullptr;  // sweep_global_state_ints
+  uint32_t *partials = nullptr;
+  void *gsync = nullptr;
+  // match scans only (maxWithin / query sweep): sweep_global_column_words each
+  uint32_t *ySorted = nullptr;
+  int32_t *wmaxG = nullptr;
+  int32_t *zpre = nullptr;          // query sweep only
+  // record segments, one per (column, CTA of the window's group), (N+1)*G entries; chunk table rows are per CTA
+  int32_t *segCnt = nullptr;
+  long long *segSrc = nullptr;
+  int32_t *qf = nullptr, *qe = nullptr;      // query sweep: [Q] each
+  unsigned long long *nmKeys = nullptr;      // query sweep: [nomatchCap] sort keys of the "no match" events
+};
+int launch_sweep_global(const SweepArgs &a, SweepMode mode, bool with_d, bool with_match, const GlobalBuffers &b,
+                        cudaStream_t stream);
+// query sweep over a wide panel: one window, sorted mode, with d; every CTA of the group serves its share of the
+// queries.  args.qCounts[1] counts the "no match" events (zero it before the launch).
+int launch_query_sweep_global(const SweepArgs &a, const GlobalBuffers &b, cudaStream_t stream);
 int query_sweep_global_max_q();
 
 }  // namespace pbwtgpu

@@ -14,6 +14,14 @@
 //   phase C  stable-partition scatter of a (and d') into the other buffer.
 //   barrier  one group-wide barrier per site (monotonic arrival counter in global memory).
 // Windows are independent groups, so the window-parallel scheme of windows.cu applies unchanged.
+//
+// Match scans on wide panels (matchMaximalWithin, pbwtMatch.c:115-142; matchSequencesSweep, pbwtMatch.c:363-443):
+// every CTA publishes its part of the sorted column y_k, the per-word maxima of d_k and (queries) the zero
+// prefix, the group meets at a second barrier, and then each CTA runs the warp-cooperative scans of
+// match_scan.cuh on state k in global memory (L2) -- maxWithin over the candidates among its own positions,
+// the query sweep over its share of the queries (in query-PBWT order, one warp per query).  Records go to a
+// per-CTA chunked stream; (site, CTA) segment tables put them into callback order afterwards (windows.cu).
+#include "match_scan.cuh"
 #include "sweep.cuh"
 
 namespace pbwtgpu {
@@ -50,24 +58,121 @@ __device__ __forceinline__ uint32_t rm_combine(uint32_t a, uint32_t b) {  // a e
   return (b >> 31) ? b : ((a & 0x80000000u) | max(a & 0x7fffffffu, b));
 }
 
-constexpr int kQCap = 1024;  // queries handled by the query sweep (one thread each, CTA 0 of the group)
+constexpr int kQCap = 8192;  // queries per query sweep (their PBWT order is kept in every CTA's shared memory)
 
-template <int MODE, bool WITH_D, bool QUERY = false>
-__global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepArgs p, int G, int chunk, int32_t *aBuf,
-                                                                   int32_t *dBuf, uint32_t *partials, GroupSync *gsync,
-                                                                   uint32_t *ySorted, int32_t *zpre) {
+// state k in global memory (L2), for the scans of match_scan.cuh; other CTAs rewrite these arrays every site,
+// so every load bypasses L1
+struct GlobalState {
+  const int32_t *aC, *dC;
+  const uint32_t *yk;
+  const int32_t *wm;
+  int M, sentinel;  // d[0] = d[M] = k + 1
+  __device__ __forceinline__ int d(int i) const { return (i <= 0 || i >= M) ? sentinel : __ldcg(dC + i); }
+  __device__ __forceinline__ uint32_t yw(int w) const { return __ldcg(yk + w); }
+  __device__ __forceinline__ int wmax(int w) const { return __ldcg(wm + w); }
+  __device__ __forceinline__ int a(int i) const { return __ldcg(aC + i); }
+};
+
+// First event at or after `from` walking down: a position p with d[p] > t (the block ends: returns false,
+// r = p, or M), or before that a position with allele x (returns true, r = p).  pbwtMatch.c:381-383,400-402.
+__device__ __forceinline__ bool first_allele_down(const GlobalState &s, int from, int t, uint32_t x, int lane, int &r) {
+  const int M = s.M;
+  int w = from >> 5;
+  unsigned notBefore = kFull << (from & 31);
+  for (;;) {
+    if ((w << 5) >= M) { r = M; return false; }
+    const int idx = (w << 5) + lane;
+    const unsigned mB = __ballot_sync(kFull, idx >= M || s.d(idx) > t) & notBefore;
+    const uint32_t yw = s.yw(w);
+    const unsigned vm = (M - (w << 5) >= 32) ? kFull : ((1u << (M - (w << 5))) - 1u);
+    const unsigned hits = (x ? yw : ~yw) & vm & notBefore;
+    const unsigned ev = mB | hits;
+    if (ev) {
+      const int b = __ffs(ev) - 1;
+      r = min((w << 5) + b, M);
+      return !((mB >> b) & 1u);
+    }
+    // skip clean words, 32 at a time: a word is an event if it may hold a block end or the allele
+    int ws = w + 1;
+    for (;;) {
+      const int wi = ws + lane;
+      bool evw = (wi << 5) >= M;
+      if (!evw) {
+        const uint32_t y2 = s.yw(wi);
+        evw = s.wmax(wi) > t || (x ? y2 : ~y2) != 0u;
+      }
+      const unsigned mw = __ballot_sync(kFull, evw);
+      if (mw) { ws += __ffs(mw) - 1; break; }
+      ws += 32;
+    }
+    w = ws;
+    notBefore = kFull;
+  }
+}
+
+// lowest position in [lo, hi) carrying allele x, or -1 (the "topmost hit" of an upward tier, pbwtMatch.c:394-396)
+__device__ __forceinline__ int first_allele_in(const GlobalState &s, int lo, int hi, uint32_t x, int lane) {
+  if (lo >= hi) return -1;
+  const int w0 = lo >> 5, w1 = (hi - 1) >> 5;
+  for (int wb = w0; wb <= w1; wb += 32) {
+    const int w = wb + lane;
+    uint32_t bits = 0u;
+    if (w <= w1) {
+      const uint32_t yw = s.yw(w);
+      bits = x ? yw : ~yw;
+      if (w == w0) bits &= kFull << (lo & 31);
+      if (w == w1 && (hi & 31)) bits &= (1u << (hi & 31)) - 1u;
+    }
+    const unsigned m = __ballot_sync(kFull, bits != 0u);
+    if (m) {
+      const int l = __ffs(m) - 1;
+      const uint32_t bw = __shfl_sync(kFull, bits, l);
+      return ((wb + l) << 5) + __ffs(bw) - 1;
+    }
+  }
+  return -1;
+}
+
+// Extra arguments of the wide-panel kernel (all device pointers).
+struct GlobalArgs {
+  int G, chunk;
+  int32_t *aBuf, *dBuf;
+  uint32_t *partials;
+  GroupSync *gsync;
+  // published per site by every CTA, double buffered by site parity: [2][G*chunk/32]
+  uint32_t *ySorted;
+  int32_t *wmaxG;
+  int32_t *zpre;      // query sweep: zeros before each word of the sorted column
+  // records: one chunked stream per CTA (chunk table row = blockIdx.x), ordered by the segment tables
+  int32_t *segCnt;    // [(N+1)*G] records of (column, CTA); row N = the final state
+  long long *segSrc;  // [(N+1)*G] offset of the segment in its CTA's stream
+  // query sweep state, by query id
+  int32_t *qf, *qe;
+  unsigned long long *nmKeys;  // sort key (site * Q + query-PBWT position) of each "no match" event
+};
+
+template <int MODE, bool WITH_D, bool MATCH, bool QUERY>
+__global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepArgs p, const GlobalArgs ga) {
   extern __shared__ __align__(16) uint32_t smem[];
+  constexpr bool SCAN = MATCH || QUERY;
+  const int G = ga.G, chunk = ga.chunk;
   const int chunkWords = chunk / 32;
+  const int QW = QUERY ? ((p.Q + 31) / 32 + 31) / 32 * 32 : 0;  // words of a query column, padded
   uint32_t *ycolS = smem;                                               // [chunkWords]
   int32_t *dnS = reinterpret_cast<int32_t *>(smem + chunkWords);        // [chunk] (WITH_D)
-  // query sweep only: warp-local zero prefix per word, per-query state, chunk-id mirror, per-warp sums
-  int32_t *zlocS = dnS + (WITH_D ? chunk : 0);                          // [chunkWords]
-  int32_t *qfS = zlocS + chunkWords, *qeS = qfS + kQCap, *qaS = qeS + kQCap;  // qaS: [2][kQCap]
-  int32_t *ctabS = qaS + 2 * kQCap;                                     // [kTabMirror]
-  int32_t *wsq = ctabS + kTabMirror;                                    // [96]
+  int32_t *wmaxS = dnS + (WITH_D ? chunk : 0);                          // [chunkWords] (SCAN)
+  uint32_t *cmaskS = reinterpret_cast<uint32_t *>(wmaxS + (SCAN ? chunkWords : 0));  // [chunkWords] (MATCH)
+  int32_t *zlocS = reinterpret_cast<int32_t *>(cmaskS + (MATCH ? chunkWords : 0));   // [chunkWords] (QUERY)
+  int4 *resS = reinterpret_cast<int4 *>(zlocS + (QUERY ? chunkWords : 0));           // [kResMax] (SCAN)
+  int32_t *ctabS = reinterpret_cast<int32_t *>(resS + (SCAN ? kResMax : 0));         // [kTabMirror] (SCAN)
+  int32_t *nmS = ctabS + (SCAN ? kTabMirror : 0);                                    // [kResMax] (QUERY)
+  uint32_t *qwS = reinterpret_cast<uint32_t *>(nmS + (QUERY ? kResMax : 0));         // [QW] query column
+  int32_t *qzS = reinterpret_cast<int32_t *>(qwS + QW);                              // [QW] zeros before each word
+  int32_t *qaS = qzS + QW;                                                           // [2][QW*32] query PBWT order
   __shared__ int wexS[32];      // zeros in this CTA's warps below each warp
   __shared__ int wsumZ[32];
   __shared__ uint32_t wsumR[32];
+  __shared__ int wsumC[32];
   __shared__ int xZ, xC;        // zeros before this CTA, zeros in the whole column
   __shared__ uint32_t xR;       // run-max carry entering this CTA
 
@@ -76,10 +181,14 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
   const int M = p.M, wpc = p.wpc;
   const int nTotal = p.nTotal ? p.nTotal : p.N;
   const size_t MS = (size_t)G * chunk;  // padded state stride per buffer
-  int32_t *aW = aBuf + (size_t)win * 2 * MS;
-  int32_t *dW = WITH_D ? dBuf + (size_t)win * 2 * (MS + 4) : nullptr;
-  uint32_t *part = partials + (size_t)win * G * 4;  // per CTA: zeros, rm, flag, unused
-  GroupSync *gs = gsync + win;
+  int32_t *aW = ga.aBuf + (size_t)win * 2 * MS;
+  int32_t *dW = WITH_D ? ga.dBuf + (size_t)win * 2 * (MS + 4) : nullptr;
+  uint32_t *part = ga.partials + (size_t)win * G * 4;  // per CTA: zeros, rm, flag, unused
+  GroupSync *gs = ga.gsync + win;
+  const int WG = G * chunkWords;  // words of the whole (padded) sorted column
+  uint32_t *ySortedW = SCAN ? ga.ySorted + (size_t)win * 2 * WG : nullptr;
+  int32_t *wmaxW = SCAN ? ga.wmaxG + (size_t)win * 2 * WG : nullptr;
+  int32_t *zpreW = QUERY ? ga.zpre + (size_t)win * 2 * WG : nullptr;
 
   int k0, k1, colShift;
   const uint32_t *src;
@@ -91,6 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     src = p.src;
   }
   const int p0 = g * chunk;                 // first sorted position of this CTA
+  const int w0g = p0 / 32;                  // its first word of the sorted column
   const int EW = chunkWords / 32;           // words per warp
   const uint32_t ltMask = lanemask_lt(lane), laneBit = 1u << lane;
   unsigned int epoch = 0;                   // barriers passed so far
@@ -109,34 +219,66 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
   };
 
   RecSink sink;
-  sink.pool = QUERY ? reinterpret_cast<int4 *>(p.recPool) : nullptr;
-  sink.tab = QUERY ? p.chunkTab : nullptr;
+  sink.pool = SCAN ? reinterpret_cast<int4 *>(p.recPool) : nullptr;
+  sink.tab = SCAN && p.chunkTab ? p.chunkTab + (size_t)blockIdx.x * p.poolChunks : nullptr;
   sink.mirror = ctabS;
   sink.nChunks = 0;
-  long long recBase = 0, nmBase = 0;
-  uint32_t qWord = 0;
-  auto ensure_chunks = [&](long long upTo) {  // CTA 0 only
+  long long recBase = 0;  // records produced so far by this CTA (uniform)
+  auto ensure_chunks = [&](long long upTo) {
     const int need = (int)((upTo + kRecChunk - 1) >> kRecChunkLog);
     if (need > sink.nChunks) {
       if (tid == 0)
         for (int c2 = sink.nChunks; c2 < need; ++c2) {
           int id = atomicAdd(p.chunkCounter, 1);
-          if (id >= p.poolChunks) id = -1;
-          p.chunkTab[c2] = id;
+          if (id >= p.poolChunks) id = -1;  // pool exhausted: records are dropped, the host reruns larger
+          p.chunkTab[(size_t)blockIdx.x * p.poolChunks + c2] = id;
           ctabS[c2 & (kTabMirror - 1)] = id;
         }
       sink.nChunks = need;
       __syncthreads();
     }
   };
-  if (QUERY && g == 0) {
-    for (int i = tid; i < kQCap; i += kThreads) {
-      qfS[i] = 0;
-      qeS[i] = 0;
-      qaS[i] = i < p.Q ? (p.qaStart ? p.qaStart[i] : i) : 0;
+  // this CTA's share of the queries: positions [qLo, qHi) of the query PBWT order
+  const int qPer = QUERY ? (p.Q + G - 1) / G : 0;
+  const int qLo = min(p.Q, g * qPer), qHi = min(p.Q, qLo + qPer);
+  if (QUERY) {
+    for (int i = tid; i < QW * 32; i += kThreads) qaS[i] = i < p.Q ? (p.qaStart ? p.qaStart[i] : i) : 0;
+    for (int i = qLo + tid; i < qHi; i += kThreads) {  // pbwtMatch.c:368-369: f and d start at zero
+      const int jj = p.qaStart ? p.qaStart[i] : i;
+      ga.qf[jj] = 0;
+      ga.qe[jj] = 0;
     }
-    if (tid < p.Q && k0 < k1) qWord = p.qcols[(size_t)(k0 + colShift) * p.qwpc + warp];
   }
+
+  // records of state k (label kLabel, segment row) for the query share of this CTA: report lists, in rounds
+  auto query_emit = [&](const GlobalState &st, int nR, int kLabel) {
+    long long roundTotal = 0;
+    for (int c0 = 0; c0 < nR; c0 += 32) {
+      const int4 en0 = c0 + lane < nR ? resS[c0 + lane] : make_int4(0, 0, 0, 0);
+      const int cntL = en0.y - en0.x;
+      const int tot = __reduce_add_sync(kFull, cntL);
+      if (sink.pool && tot) {
+        const long long base = recBase + roundTotal;
+        ensure_chunks(base + tot);
+        const int mcnt = __shfl_sync(kFull, cntL, warp);
+        if (mcnt > 0 && mcnt < kBigBlock) {
+          const int4 en = resS[c0 + warp];
+          const long long o = base + __reduce_add_sync(kFull, lane < warp ? cntL : 0);
+          for (int t = lane; t < mcnt; t += 32) sink.put(o + t, make_int4(en.w, st.a(en.x + t), en.z, kLabel));
+        }
+        unsigned big = __ballot_sync(kFull, cntL >= kBigBlock);
+        while (big) {
+          const int j = __ffs(big) - 1;
+          big &= big - 1;
+          const int4 en = resS[c0 + j];
+          const long long o = base + __reduce_add_sync(kFull, lane < j ? cntL : 0);
+          for (int t = tid; t < en.y - en.x; t += kThreads) sink.put(o + t, make_int4(en.w, st.a(en.x + t), en.z, kLabel));
+        }
+      }
+      roundTotal += tot;
+    }
+    recBase += roundTotal;
+  };
 
   // ---- window start state ----
   for (int i = p0 + tid; i < p0 + chunk; i += kThreads) {
@@ -154,6 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     int32_t *aN = aW + (size_t)(cur ^ 1) * MS;
     const int32_t *dC = WITH_D ? dW + (size_t)cur * (MS + 4) : nullptr;
     int32_t *dN = WITH_D ? dW + (size_t)(cur ^ 1) * (MS + 4) : nullptr;
+    if (QUERY && tid < QW) qwS[tid] = tid < p.qwpc ? p.qcols[(size_t)(k + colShift) * p.qwpc + tid] : 0u;
 
     // ---------------- phase A ----------------
     const int wordBase = warp * EW;          // CTA-local word index of this warp's first word
@@ -205,6 +348,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
         if (WITH_D) {
           int dv = dB[u];
           if (i == 0) dv = k + 1;  // sentinel d[0] (pbwtCore.c:414,507)
+          if (SCAN) {  // word maximum of d: lets the match scans skip long blocks 1024 positions per step
+            const int wm = __reduce_max_sync(kFull, dv);
+            if (lane == 0) wmaxS[wordBase + e] = wm;
+          }
           int dnv = dv;
           if (H == 0u) {
             lmax = max(lmax, dv);
@@ -297,11 +444,11 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     }
 
     const int par = (k - k0) & 1;
-    const int WG = G * chunkWords;  // words of the whole (padded) sorted column
-    if (QUERY) {  // publish this CTA's part of the sorted column and of the zero prefix, then meet the group
+    if (SCAN) {  // publish this CTA's part of the sorted column, of the word maxima of d (and of the zero prefix)
       for (int w = tid; w < chunkWords; w += kThreads) {
-        ySorted[(size_t)par * WG + p0 / 32 + w] = ycolS[w];
-        zpre[(size_t)par * WG + p0 / 32 + w] = xZ + wexS[w / EW] + zlocS[w];
+        ySortedW[(size_t)par * WG + w0g + w] = ycolS[w];
+        wmaxW[(size_t)par * WG + w0g + w] = wmaxS[w];
+        if (QUERY) zpreW[(size_t)par * WG + w0g + w] = xZ + wexS[w / EW] + zlocS[w];
       }
       group_barrier();
     }
@@ -339,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     }
     if (p.yOut) {  // sorted column k, pad bits cleared
       for (int w = tid; w < chunkWords; w += kThreads) {
-        const int gw = p0 / 32 + w;
+        const int gw = w0g + w;
         if (gw < wpc) {
           const int base = gw * 32;
           const uint32_t vm = (M - base >= 32) ? kFull : (M > base ? ((1u << (M - base)) - 1u) : 0u);
@@ -348,126 +495,196 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
       }
     }
     if (p.cOut && g == 0 && tid == 0) p.cOut[k + colShift] = c;
-    if (QUERY && g == 0) {
-      // ---------------- matchSequencesSweep on state k (pbwtMatch.c:376-426), one thread per query ----------------
-      const uint32_t *yk = ySorted + (size_t)par * WG;
-      const int32_t *zk = zpre + (size_t)par * WG;
-      auto dAt = [&](int idx) { return (idx == 0 || idx == M) ? k + 1 : __ldcg(dC + idx); };
-      auto yAt = [&](int j) { return (__ldcg(yk + (j >> 5)) >> (j & 31)) & 1u; };
-      const bool active = tid < p.Q;
-      const uint32_t x = active ? (qWord >> lane) & 1u : 1u;
-      if (active && k + 1 < k1) qWord = p.qcols[(size_t)(k + 1 + colShift) * p.qwpc + warp];
-      const int qC = par * kQCap, qN = (par ^ 1) * kQCap;
-      const int jj = active ? qaS[qC + tid] : 0;
-      int f = qfS[jj], e = qeS[jj];
-      int repLo = 0, repHi = 0, repStart = 0;
-      bool nm = false;
-      if (active && yAt(f) != x) {
-        int hi = f + 1;
-        bool moved = false;
-        while (hi < M && dAt(hi) <= e) {  // an alternate of the same length that extends? (pbwtMatch.c:381-383)
-          if (yAt(hi) == x) { f = hi; moved = true; break; }
-          ++hi;
-        }
-        if (!moved) {
-          repLo = f; repHi = hi; repStart = e;  // report [f, hi) with start e (pbwtMatch.c:385)
-          int lo = f;
-          int dDown = hi < M ? dAt(hi) : k;
-          int dUp = dAt(lo);
-          for (;;) {  // reseed by divergence tiers, upper side first on ties (pbwtMatch.c:389-411)
-            if (dUp <= dDown) {
-              int top = -1;
-              while (lo > 0 && dAt(lo) <= dUp) {
-                --lo;
-                if (yAt(lo) == x) top = lo;
-              }
-              if (top >= 0) { f = top; e = dUp; break; }
-              dUp = dAt(lo);
+
+    if (MATCH) {
+      // ---------------- matchMaximalWithin on state k: candidates among this CTA's positions ----------------
+      const GlobalState st{aC, dC, ySortedW + (size_t)par * WG, wmaxW + (size_t)par * WG, M, k + 1};
+      uint32_t myMask = 0;
+      int tw = 0;
+      for (int e = 0; e < EW; ++e) {
+        const int lw = wordBase + e, gw = w0g + lw, base = gw * 32;
+        if (base >= M) break;
+        const uint32_t cw = ycolS[lw];
+        const uint32_t pbit = gw == 0 ? (~cw & 1u) : (lw > 0 ? ycolS[lw - 1] >> 31 : st.yw(gw - 1) >> 31);
+        const uint32_t nbit = gw + 1 >= WG ? 1u : (lw + 1 < chunkWords ? ycolS[lw + 1] & 1u : st.yw(gw + 1) & 1u);
+        const uint32_t vm = (M - base >= 32) ? kFull : ((1u << (M - base)) - 1u);
+        const uint32_t m = candidate_mask(st, cw, pbit, nbit, base, vm, lane);
+        if (lane == e) myMask = m;
+        tw += __popc(m);
+      }
+      if (lane < EW) cmaskS[wordBase + lane] = myMask;
+      if (lane == 0) wsumC[warp] = p.debugNoCandidates ? 0 : tw;
+      __syncthreads();
+      const long long before = recBase;
+      match_rounds(st, k, true, M, EW, wsumC, cmaskS, resS, sink, recBase, ensure_chunks, tid, lane, warp, p0);
+      if (tid == 0) {
+        const size_t seg = (size_t)(k + colShift) * G + g;
+        ga.segCnt[seg] = (int32_t)(recBase - before);
+        ga.segSrc[seg] = before;
+      }
+    }
+    if (QUERY) {
+      // ---------------- matchSequencesSweep on state k (pbwtMatch.c:376-426): one warp per query ----------------
+      const GlobalState st{aC, dC, ySortedW + (size_t)par * WG, wmaxW + (size_t)par * WG, M, k + 1};
+      const int32_t *zk = zpreW + (size_t)par * WG;
+      const int32_t *qaC = qaS + par * QW * 32;
+      int32_t *qaN = qaS + (par ^ 1) * QW * 32;
+      const long long before = recBase;
+      for (int r0 = qLo; r0 < qHi; r0 += kResMax) {
+        const int nR = min(kResMax, qHi - r0);
+        for (int r = warp; r < nR; r += 32) {
+          const int t = r0 + r;
+          const int jj = qaC[t];
+          const uint32_t x = (qwS[t >> 5] >> (t & 31)) & 1u;
+          int f = __ldcg(ga.qf + jj), e = __ldcg(ga.qe + jj);
+          int repLo = 0, repHi = 0, repStart = 0;
+          bool nm = false;
+          if (ybit(st, f) != x) {
+            int hi;
+            if (first_allele_down(st, f + 1, e, x, lane, hi)) {
+              f = hi;  // an alternate of the same length that extends (pbwtMatch.c:381-383)
             } else {
-              bool hit = false;
-              while (hi < M && dAt(hi) <= dDown) {
-                if (yAt(hi) == x) { f = hi; e = dDown; hit = true; break; }
-                ++hi;
+              repLo = f; repHi = hi; repStart = e;  // report [f, hi) with start e (pbwtMatch.c:385)
+              int lo = f;
+              int dDown = hi < M ? st.d(hi) : k;
+              int dUp = st.d(lo);
+              for (;;) {  // reseed by divergence tiers, upper side first on ties (pbwtMatch.c:389-411)
+                if (dUp <= dDown) {
+                  const int q = block_start(st, lo, dUp, lane);  // the tier is [q, lo)
+                  const int top = first_allele_in(st, q, lo, x, lane);
+                  if (top >= 0) { f = top; e = dUp; break; }
+                  lo = q;
+                  dUp = st.d(lo);
+                } else {
+                  int r2;
+                  if (first_allele_down(st, hi, dDown, x, lane, r2)) { f = r2; e = dDown; break; }
+                  hi = r2;
+                  dDown = hi == M ? k : st.d(hi);
+                  if (lo == 0 && hi == M) { nm = true; e = k + 1; break; }  // allele absent from the column
+                }
               }
-              if (hit) break;
-              dDown = hi == M ? k : dAt(hi);
-              if (lo == 0 && hi == M) { nm = true; e = k + 1; break; }
             }
           }
+          // FM step (pbwtCursorCalculateU + pbwtCursorMap, pbwtCore.c:510-519, pbwt.h:130; pbwtMatch.c:417-423)
+          const int fw = f >> 5;
+          const int Z = __ldcg(zk + fw) + __popc(~st.yw(fw) & lanemask_lt(f & 31));
+          int nf = x ? c + f - Z : Z;
+          if (nf == M) nf = 0;
+          if (lane == 0) {
+            ga.qf[jj] = nf;
+            ga.qe[jj] = e;
+            resS[r] = make_int4(repLo, repHi, repStart, jj);
+            nmS[r] = nm ? (int)(2u | x) : 0;
+          }
         }
+        __syncthreads();
+        query_emit(st, nR, k);
+        if (p.nomatch && tid < nR && nmS[tid]) {  // rare: global append, sorted by (site, position) afterwards
+          const unsigned long long o = atomicAdd(&p.qCounts[1], 1ull);
+          if ((long long)o < p.nomatchCap) {
+            p.nomatch[o] = pbwtgpu_nomatch{resS[tid].w, nmS[tid] & 1, k};
+            ga.nmKeys[o] = (unsigned long long)(k + colShift) * (unsigned)p.Q + (unsigned)(r0 + tid);
+          }
+        }
+        __syncthreads();  // resS / nmS are reused by the next round
       }
-      {  // FM step (pbwtCursorCalculateU + pbwtCursorMap, pbwtCore.c:510-519, pbwt.h:130; pbwtMatch.c:417-423)
-        const int fw = f >> 5;
-        const int Z = __ldcg(zk + fw) + __popc(~__ldcg(yk + fw) & lanemask_lt(f & 31));
-        int nf = x ? c + f - Z : Z;
-        if (nf == M) nf = 0;
-        if (active) { qfS[jj] = nf; qeS[jj] = e; }
+      if (tid == 0) {
+        const size_t seg = (size_t)(k + colShift) * G + g;
+        ga.segCnt[seg] = (int32_t)(recBase - before);
+        ga.segSrc[seg] = before;
       }
-      const int cnt = repHi - repLo;
-      int cntTot;
-      const int cntEx = warp_excl_scan(cnt, lane, cntTot);
-      const unsigned nmBal = __ballot_sync(kFull, nm), qzBal = __ballot_sync(kFull, active && x == 0u);
-      if (lane == 0) { wsq[warp] = cntTot; wsq[32 + warp] = __popc(nmBal); wsq[64 + warp] = __popc(qzBal); }
+      // query cursor step (pbwtCursorForwardsRead on uq, pbwtMatch.c:426), redundantly in every CTA
+      int v = 0, inc = 0;
+      if (tid < QW) {
+        const int base = tid * 32;
+        const uint32_t vm = (p.Q - base >= 32) ? kFull : (p.Q > base ? ((1u << (p.Q - base)) - 1u) : 0u);
+        v = __popc(~qwS[tid] & vm);
+        inc = v;
+#pragma unroll
+        for (int dl = 1; dl < 32; dl <<= 1) {
+          const int t = __shfl_up_sync(kFull, inc, dl);
+          if (lane >= dl) inc += t;
+        }
+        if (lane == 31) wsumC[warp] = inc;
+      }
       __syncthreads();
-      int recTot, nmTot, cq;
-      const int recEx = __shfl_sync(kFull, warp_excl_scan(wsq[lane], lane, recTot), warp);
-      const int nmEx = __shfl_sync(kFull, warp_excl_scan(wsq[32 + lane], lane, nmTot), warp);
-      const int qzEx = __shfl_sync(kFull, warp_excl_scan(wsq[64 + lane], lane, cq), warp);
-      if (sink.pool && recTot) {
-        ensure_chunks(recBase + recTot);
-        long long o = recBase + recEx + cntEx;
-        for (int i = repLo; i < repHi; ++i, ++o) sink.put(o, make_int4(jj, __ldcg(aC + i), repStart, k));
+      int cq = 0, wbase = 0;
+      for (int j = 0; j < QW / 32; ++j) {
+        const int t = wsumC[j];
+        if (j < warp) wbase += t;
+        cq += t;
       }
-      if (nm && p.nomatch) {
-        const long long o = nmBase + nmEx + __popc(nmBal & ltMask);
-        if (o < p.nomatchCap) p.nomatch[o] = pbwtgpu_nomatch{jj, (int)x, k};
+      if (tid < QW) qzS[tid] = wbase + inc - v;
+      __syncthreads();
+      for (int t = tid; t < p.Q; t += kThreads) {
+        const uint32_t w = qwS[t >> 5];
+        const uint32_t x = (w >> (t & 31)) & 1u;
+        const int zb = qzS[t >> 5] + __popc(~w & lanemask_lt(t & 31));
+        qaN[x ? cq + t - zb : zb] = qaC[t];
       }
-      recBase += recTot;
-      nmBase += nmTot;
-      if (active) {  // query cursor step (pbwtCursorForwardsRead on uq, pbwtMatch.c:426)
-        const int zb = qzEx + __popc(qzBal & ltMask);
-        qaS[qN + (x ? cq + tid - zb : zb)] = jj;
-      }
-      __syncthreads();  // wsq is reused at the next site
     }
     group_barrier();
     cur ^= 1;
   }
 
-  if (QUERY && g == 0) {  // matches still open at N (pbwtMatch.c:430-436): a[f], then every following i with d[i] <= e
-    const int32_t *aE = aW + (size_t)cur * MS;
-    const int32_t *dE = dW + (size_t)cur * (MS + 4);
-    const bool active = tid < p.Q;
-    const int jj = active ? qaS[((k1 - k0) & 1) * kQCap + tid] : 0;
-    const int f = qfS[jj], e = qeS[jj];
-    int hi = f + 1;
-    if (active) while (hi < M && __ldcg(dE + hi) <= e) ++hi;
-    const int cnt = active ? hi - f : 0;
-    int cntTot;
-    const int cntEx = warp_excl_scan(cnt, lane, cntTot);
-    if (lane == 0) wsq[warp] = cntTot;
-    __syncthreads();
-    int recTot;
-    const int recEx = __shfl_sync(kFull, warp_excl_scan(wsq[lane], lane, recTot), warp);
-    if (sink.pool && recTot) {
-      ensure_chunks(recBase + recTot);
-      long long o = recBase + recEx + cntEx;
-      for (int i = f; i < f + cnt; ++i, ++o) sink.put(o, make_int4(jj, __ldcg(aE + i), e, nTotal));
+  // ---- state k1 ----
+  const int32_t *aE = aW + (size_t)cur * MS;
+  const int32_t *dE = WITH_D ? dW + (size_t)cur * (MS + 4) : nullptr;
+  const bool finalScan = !p.perWindowSites && k1 == nTotal && ((MATCH && p.reportAtN) || QUERY);
+  if (SCAN && finalScan) {  // word maxima of the final d, published to the group
+    const int parE = (k1 - k0) & 1;
+    for (int w = warp; w < chunkWords; w += 32) {
+      const int i = p0 + w * 32 + lane;
+      const int dv = i == 0 ? nTotal + 1 : (i < M ? __ldcg(dE + i) : 0);
+      const int wm = __reduce_max_sync(kFull, dv);
+      if (lane == 0) wmaxW[(size_t)parE * WG + w0g + w] = wm;
     }
-    recBase += recTot;
-    if (tid == 0 && p.qCounts) { p.qCounts[0] = (unsigned long long)recBase; p.qCounts[1] = (unsigned long long)nmBase; }
+    group_barrier();
+    const GlobalState st{aE, dE, ySortedW + (size_t)parE * WG, wmaxW + (size_t)parE * WG, M, nTotal + 1};
+    const long long before = recBase;
+    if (MATCH) {  // k == N: nothing extends, every block is reported (alleles are not consulted when live == false)
+      int tw = 0;
+      if (lane < EW) {
+        const int base = p0 + (warp * EW + lane) * 32;
+        const uint32_t vm = (M - base >= 32) ? kFull : (M > base ? ((1u << (M - base)) - 1u) : 0u);
+        cmaskS[warp * EW + lane] = vm;
+        tw = __popc(vm);
+      }
+      tw = __reduce_add_sync(kFull, tw);
+      if (lane == 0) wsumC[warp] = tw;
+      __syncthreads();
+      match_rounds(st, nTotal, false, M, EW, wsumC, cmaskS, resS, sink, recBase, ensure_chunks, tid, lane, warp, p0);
+    }
+    if (QUERY) {  // matches still open at N (pbwtMatch.c:430-436): a[f], then every following i with d[i] <= e
+      const int32_t *qaC = qaS + parE * QW * 32;
+      for (int r0 = qLo; r0 < qHi; r0 += kResMax) {
+        const int nR = min(kResMax, qHi - r0);
+        for (int r = warp; r < nR; r += 32) {
+          const int jj = qaC[r0 + r];
+          const int f = __ldcg(ga.qf + jj), e = __ldcg(ga.qe + jj);
+          const int hi = block_end(st, f + 1, e, M, lane);
+          if (lane == 0) resS[r] = make_int4(f, hi, e, jj);
+        }
+        __syncthreads();
+        query_emit(st, nR, nTotal);
+        __syncthreads();
+      }
+    }
+    if (tid == 0) {
+      const size_t seg = (size_t)p.N * G + g;
+      ga.segCnt[seg] = (int32_t)(recBase - before);
+      ga.segSrc[seg] = before;
+    }
   }
 
   // ---- window end ----
   const bool writeEnd = !p.endOnlyLast || k1 == nTotal;
   const size_t endSlot = p.endOnlyLast ? 0 : (size_t)win;
-  const int32_t *aC = aW + (size_t)cur * MS;
   if (p.aEnd && writeEnd)
-    for (int i = p0 + tid; i < min(M, p0 + chunk); i += kThreads) p.aEnd[endSlot * M + i] = __ldcg(aC + i);
+    for (int i = p0 + tid; i < min(M, p0 + chunk); i += kThreads) p.aEnd[endSlot * M + i] = __ldcg(aE + i);
   if (WITH_D && p.dEnd && writeEnd) {
-    const int32_t *dC = dW + (size_t)cur * (MS + 4);
     for (int i = p0 + tid; i < min(M, p0 + chunk); i += kThreads)
-      p.dEnd[endSlot * (M + 1) + i] = i == 0 ? k1 + 1 : __ldcg(dC + i);
+      p.dEnd[endSlot * (M + 1) + i] = i == 0 ? k1 + 1 : __ldcg(dE + i);
     if (g == 0 && tid == 0) p.dEnd[endSlot * (M + 1) + M] = k1 + 1;
   }
 }
@@ -493,37 +710,59 @@ size_t sweep_global_state_ints(int G, int chunk, int W, bool with_d) {
   return (size_t)W * 2 * MS + (with_d ? (size_t)W * 2 * (MS + 4) : 0);
 }
 
-int launch_sweep_global(const SweepArgs &a, SweepMode mode, bool with_d, int G, int chunk, int32_t *aBuf, int32_t *dBuf,
-                        uint32_t *partials, void *gsync, cudaStream_t stream) {
-  const size_t smemBytes = (size_t)(chunk / 32) * 4 + (with_d ? (size_t)chunk * 4 : 0);
+size_t sweep_global_column_words(int G, int chunk, int W) { return (size_t)W * 2 * G * (chunk / 32); }
+
+static size_t smem_bytes(int chunk, bool with_d, bool match, bool query, int Q) {
+  const size_t cw = chunk / 32;
+  const bool scan = match || query;
+  const size_t QW = query ? (size_t)((Q + 31) / 32 + 31) / 32 * 32 : 0;
+  size_t words = cw + (with_d ? chunk : 0) + (scan ? cw : 0) + (match ? cw : 0) + (query ? cw : 0) +
+                 (scan ? kResMax * 4 + kTabMirror : 0) + (query ? kResMax : 0) + QW * 2 + QW * 32 * 2;
+  return words * 4;
+}
+
+int launch_sweep_global(const SweepArgs &a, SweepMode mode, bool with_d, bool with_match, const GlobalBuffers &b,
+                        cudaStream_t stream) {
+  if (with_match && !with_d) return (int)cudaErrorInvalidValue;
+  const size_t smemBytes = smem_bytes(b.chunk, with_d, with_match, false, 0);
   void *kern;
-  if (mode == kGather) kern = with_d ? (void *)sweep_global_kernel<kGather, true> : (void *)sweep_global_kernel<kGather, false>;
-  else kern = with_d ? (void *)sweep_global_kernel<kSorted, true> : (void *)sweep_global_kernel<kSorted, false>;
+  if (mode == kGather)
+    kern = with_match ? (void *)sweep_global_kernel<kGather, true, true, false>
+                      : with_d ? (void *)sweep_global_kernel<kGather, true, false, false>
+                               : (void *)sweep_global_kernel<kGather, false, false, false>;
+  else
+    kern = with_match ? (void *)sweep_global_kernel<kSorted, true, true, false>
+                      : with_d ? (void *)sweep_global_kernel<kSorted, true, false, false>
+                               : (void *)sweep_global_kernel<kSorted, false, false, false>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
   if (err != cudaSuccess) return (int)err;
   SweepArgs args = a;
-  GroupSync *gs = static_cast<GroupSync *>(gsync);
-  uint32_t *ys = nullptr;
-  int32_t *zp = nullptr;
-  void *params[] = {&args, &G, &chunk, &aBuf, &dBuf, &partials, &gs, &ys, &zp};
-  err = cudaLaunchCooperativeKernel(kern, dim3(a.nWindows * G), dim3(kThreads), params, smemBytes, stream);
+  GlobalArgs ga{};
+  ga.G = b.G; ga.chunk = b.chunk; ga.aBuf = b.aBuf; ga.dBuf = b.dBuf; ga.partials = b.partials;
+  ga.gsync = static_cast<GroupSync *>(b.gsync);
+  ga.ySorted = b.ySorted; ga.wmaxG = b.wmaxG; ga.zpre = b.zpre; ga.segCnt = b.segCnt; ga.segSrc = b.segSrc;
+  void *params[] = {&args, &ga};
+  err = cudaLaunchCooperativeKernel(kern, dim3(a.nWindows * b.G), dim3(kThreads), params, smemBytes, stream);
   return (int)err;
 }
 
 int query_sweep_global_max_q() { return kQCap; }
 
-int launch_query_sweep_global(const SweepArgs &a, int G, int chunk, int32_t *aBuf, int32_t *dBuf, uint32_t *partials,
-                              void *gsync, uint32_t *ySorted, int32_t *zpre, cudaStream_t stream) {
+int launch_query_sweep_global(const SweepArgs &a, const GlobalBuffers &b, cudaStream_t stream) {
   if (a.Q < 1 || a.Q > kQCap) return (int)cudaErrorInvalidValue;
-  const size_t smemBytes = (size_t)(chunk / 32) * 4 * 2 + (size_t)chunk * 4 + (size_t)(4 * kQCap + kTabMirror + 96) * 4;
-  void *kern = (void *)sweep_global_kernel<kSorted, true, true>;
+  const size_t smemBytes = smem_bytes(b.chunk, true, false, true, a.Q);
+  void *kern = (void *)sweep_global_kernel<kSorted, true, false, true>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
   if (err != cudaSuccess) return (int)err;
   SweepArgs args = a;
   args.nWindows = 1;
-  GroupSync *gs = static_cast<GroupSync *>(gsync);
-  void *params[] = {&args, &G, &chunk, &aBuf, &dBuf, &partials, &gs, &ySorted, &zpre};
-  err = cudaLaunchCooperativeKernel(kern, dim3(G), dim3(kThreads), params, smemBytes, stream);
+  GlobalArgs ga{};
+  ga.G = b.G; ga.chunk = b.chunk; ga.aBuf = b.aBuf; ga.dBuf = b.dBuf; ga.partials = b.partials;
+  ga.gsync = static_cast<GroupSync *>(b.gsync);
+  ga.ySorted = b.ySorted; ga.wmaxG = b.wmaxG; ga.zpre = b.zpre; ga.segCnt = b.segCnt; ga.segSrc = b.segSrc;
+  ga.qf = b.qf; ga.qe = b.qe; ga.nmKeys = b.nmKeys;
+  void *params[] = {&args, &ga};
+  err = cudaLaunchCooperativeKernel(kern, dim3(b.G), dim3(kThreads), params, smemBytes, stream);
   return (int)err;
 }
 

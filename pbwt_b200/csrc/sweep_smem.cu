@@ -27,6 +27,7 @@
 // all 32 warps together.
 #include <type_traits>
 
+#include "match_scan.cuh"
 #include "sweep.cuh"
 
 namespace pbwtgpu {
@@ -34,8 +35,6 @@ namespace {
 
 constexpr int kThreads = 1024;
 constexpr int kStages = 3;
-constexpr int kResMax = 256;    // match candidates processed per round (multiple of 32)
-constexpr int kBigBlock = 128;  // records; larger blocks are emitted by the whole CTA
 
 template <int E, bool WITH_D, bool MATCH, bool QUERY = false>
 struct SmemLayout {  // offsets in 32-bit words; every array start is 16-byte aligned
@@ -77,177 +76,17 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int &total) {
   return x - v;
 }
 
+// accessor of the shared-memory resident state for the scans of match_scan.cuh
+struct SmemState {
+  const int32_t *sA, *sD;
+  const uint32_t *yc;
+  const int32_t *wm;
+  __device__ __forceinline__ int d(int i) const { return sD[i]; }
+  __device__ __forceinline__ uint32_t yw(int w) const { return yc[w]; }
+  __device__ __forceinline__ int wmax(int w) const { return wm[w]; }
+  __device__ __forceinline__ int a(int i) const { return sA[i]; }
+};
 __device__ __forceinline__ uint32_t ybit(const uint32_t *yc, int j) { return (yc[j >> 5] >> (j & 31)) & 1u; }
-
-// does any position in [lo, hi) carry allele yi?  (sorted bit column, pad bits beyond M are ones)
-__device__ __forceinline__ bool any_same_allele(const uint32_t *yc, int lo, int hi, uint32_t yi, int lane) {
-  if (lo >= hi) return false;
-  const int w0 = lo >> 5, w1 = (hi - 1) >> 5;
-  bool hit = false;
-  for (int w = w0 + lane; w <= w1; w += 32) {
-    uint32_t bits = yi ? yc[w] : ~yc[w];
-    if (w == w0) bits &= kFull << (lo & 31);
-    if (w == w1 && (hi & 31)) bits &= (1u << (hi & 31)) - 1u;
-    hit |= bits != 0u;
-  }
-  return __any_sync(kFull, hit);
-}
-
-constexpr int kEarlySteps = 2;  // 32-position steps scanned with the reference's early exit before skipping by words
-
-// The reference's upward scan of position i (pbwtMatch.c:124-126):
-//   lo = i; while (d[lo] <= d[i]) { --lo; if (y[lo] == y[i]) -> the match extends }
-// First kEarlySteps x 32 positions exactly as the reference walks them (most candidates resolve here: a
-// neighbour with the same allele, or the block's end); longer blocks are closed with the per-word maxima of d
-// (1024 positions per step) and tested for the allele by masked popcounts.  Lane l of a step looks at
-// p = top - l, visited iff no d[q] > di for q in (p, i].  Returns true when the match extends, else sets lo.
-__device__ __forceinline__ bool scan_up(const int32_t *sD, const uint32_t *yc, const int32_t *wmax, int i, uint32_t yi,
-                                        int di, bool live, int lane, int &lo) {
-  int top = i - 1;
-  for (int step = 0; step < kEarlySteps; ++step, top -= 32) {
-    const int p = top - lane;
-    const bool blk = p < -1 || (p + 1 < i && sD[p + 1] > di);  // d[0] = k+1 blocks at p = -1
-    const unsigned mBlk = __ballot_sync(kFull, blk);
-    const unsigned before = mBlk ? ((1u << (__ffs(mBlk) - 1)) - 1u) : kFull;  // lanes visited in this step
-    if (live) {
-      const unsigned mSame = __ballot_sync(kFull, p >= 0 && ((yc[p >> 5] >> (p & 31)) & 1u) == yi);
-      if (mSame & before) return true;
-    }
-    if (mBlk) {
-      lo = top - (__ffs(mBlk) - 1) + 1;
-      return false;
-    }
-  }
-  // positions (top, i) are visited and clean; nearest q <= top + 1 with d[q] > di closes the block
-  int q;
-  {
-    const int from = top + 1;
-    const int w = from >> 5;
-    const int idx = (w << 5) + lane;
-    const unsigned m = __ballot_sync(kFull, idx <= from && (idx <= 0 || sD[idx] > di));
-    if (m) q = (w << 5) + 31 - __clz(m);
-    else {
-      int ws = w - 1;
-      for (;;) {
-        const int wi = ws - lane;
-        const unsigned mw = __ballot_sync(kFull, wi < 0 || wmax[wi] > di);
-        if (mw) { ws -= __ffs(mw) - 1; break; }
-        ws -= 32;
-      }
-      if (ws < 0) q = 0;
-      else {
-        const unsigned m2 = __ballot_sync(kFull, sD[(ws << 5) + lane] > di);
-        q = m2 ? (ws << 5) + 31 - __clz(m2) : 0;
-      }
-    }
-  }
-  lo = max(q, 0);
-  return live && any_same_allele(yc, lo, top + 1, yi, lane);
-}
-
-// The downward scan (pbwtMatch.c:127-129): hi = i+1; while (d[hi] <= d[i+1]) { if (y[hi] == y[i]) extends; ++hi }
-__device__ __forceinline__ bool scan_down(const int32_t *sD, const uint32_t *yc, const int32_t *wmax, int i, uint32_t yi,
-                                          int dn1, int M, bool live, int lane, int &hi) {
-  int bot = i + 1;
-  for (int step = 0; step < kEarlySteps; ++step, bot += 32) {
-    const int p = bot + lane;
-    const bool blk = p >= M || sD[p] > dn1;  // d[M] = k+1 blocks at p = M
-    const unsigned mBlk = __ballot_sync(kFull, blk);
-    const unsigned before = mBlk ? ((1u << (__ffs(mBlk) - 1)) - 1u) : kFull;
-    if (live) {
-      const unsigned mSame = __ballot_sync(kFull, p < M && ((yc[p >> 5] >> (p & 31)) & 1u) == yi);
-      if (mSame & before) return true;
-    }
-    if (mBlk) {
-      hi = bot + __ffs(mBlk) - 1;
-      return false;
-    }
-  }
-  // positions (i, bot) are visited and clean; nearest r >= bot with d[r] > dn1 closes the block
-  int r;
-  {
-    const int w = bot >> 5;
-    const int idx = (w << 5) + lane;
-    const unsigned m = __ballot_sync(kFull, idx >= bot && (idx >= M || sD[idx] > dn1));
-    if (m) r = (w << 5) + __ffs(m) - 1;
-    else {
-      int ws = w + 1;
-      for (;;) {
-        const int wi = ws + lane;
-        const unsigned mw = __ballot_sync(kFull, (wi << 5) >= M || wmax[wi] > dn1);
-        if (mw) { ws += __ffs(mw) - 1; break; }
-        ws += 32;
-      }
-      if ((ws << 5) >= M) r = M;
-      else {
-        const int idx2 = (ws << 5) + lane;
-        const unsigned m2 = __ballot_sync(kFull, idx2 >= M || sD[idx2] > dn1);
-        r = m2 ? (ws << 5) + __ffs(m2) - 1 : M;
-      }
-    }
-  }
-  hi = min(r, M);
-  return live && any_same_allele(yc, bot, hi, yi, lane);
-}
-
-// write the records of reporter i: upward block [lo, i) with start di, then downward block (i, hi) with
-// start dn1 (callback order, pbwtMatch.c:133-134); record t of the block is written by "lane" t0 + t*step
-__device__ __forceinline__ void emit_block(const RecSink &out, long long o, const int32_t *sA, int i, int lo, int hi,
-                                           int di, int dn1, int k, int t0, int step) {
-  const int cnt = (i - lo) + (hi - i - 1);
-  const int ai = sA[i];
-  const int nUp = i - lo;
-  for (int t = t0; t < cnt; t += step) {
-    const int jj = t < nUp ? lo + t : t + lo + 1;  // skips i itself
-    out.put(o + t, make_int4(ai, sA[jj], t < nUp ? di : dn1, k));
-  }
-}
-
-// ---- matchMaximalWithin's per-site scan (pbwtMatch.c:122-137), block-wide and load-balanced ----
-// For a position i the upward block is [q, i) with q the nearest index <= i whose d exceeds d[i], the
-// downward block (i, r) with r the nearest index > i whose d exceeds d[i+1]; i reports nothing when a
-// member of either block carries the same allele (the match extends).  Only heads/tails of allele runs
-// can fail that test on their first neighbour ("candidates"); PBWT order clusters them in a few words, so
-// they are numbered block-wide and dealt round-robin to the 32 warps, kResMax per round.
-
-// Candidate lanes of one word of state k.  cw: the word's alleles, pb: allele before the word, nb: allele
-// after it; d read from shared memory.  A lane is a candidate unless its first upward/downward neighbour
-// already carries its allele in the direction(s) the reference scans (pbwtMatch.c:124-129).
-__device__ __forceinline__ uint32_t candidate_mask(const int32_t *sD, uint32_t cw, uint32_t pb, uint32_t nb, int base,
-                                                   uint32_t vm, int lane) {
-  const uint32_t H = cw ^ ((cw << 1) | pb);
-  const uint32_t Hn = (H >> 1) | (((nb & 1u) ^ (cw >> 31)) << 31);
-  const uint32_t bm = (H | Hn) & vm;
-  bool mine = false;
-  if ((bm >> lane) & 1u) {
-    const int di = sD[base + lane], dn1 = sD[base + lane + 1];
-    const bool samePrev = !((H >> lane) & 1u), sameNext = !((Hn >> lane) & 1u);
-    mine = !((di <= dn1 && samePrev) || (di >= dn1 && sameNext));
-  }
-  return __ballot_sync(kFull, mine);
-}
-
-// position of the g-th candidate of the block (g < T).  candBase: lane l holds the number of candidates in
-// warps < l; masks: per-word candidate masks, E words per warp.
-template <int E>
-__device__ __forceinline__ int locate_candidate(const uint32_t *masks, int candBase, int g, int lane) {
-  const int wv = 31 - __clz(__ballot_sync(kFull, candBase <= g));  // owning warp
-  int r = g - __shfl_sync(kFull, candBase, wv);                    // rank inside that warp
-  const uint32_t m = lane < E ? masks[wv * E + lane] : 0u;
-  const int pc = __popc(m);
-  int inc = pc;
-#pragma unroll
-  for (int dl = 1; dl < 32; dl <<= 1) {
-    const int t = __shfl_up_sync(kFull, inc, dl);
-    if (lane >= dl) inc += t;
-  }
-  const int e = __ffs(__ballot_sync(kFull, inc > r)) - 1;  // word holding it
-  r -= __shfl_sync(kFull, inc - pc, e);
-  const uint32_t me = __shfl_sync(kFull, m, e);
-  uint32_t mm = me;
-  for (int q = 0; q < r; ++q) mm &= mm - 1;  // drop the r lowest set bits (r is small)
-  return (wv * E + e) * 32 + __ffs(mm) - 1;
-}
 
 template <int E, int MODE, bool WITH_D, bool MATCH, bool QUERY = false>
 __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs p) {
@@ -347,62 +186,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     }
   };
 
-  // -------- candidates of a state -> records, in rounds of kResMax dealt round-robin to the 32 warps --------
-  // Expects cmaskS[] (per-word candidate masks) and wsumC[] (per-warp candidate counts) to have been published
-  // before the preceding barrier.  Contains at least one __syncthreads (the caller's "S2").
+  // candidates of a state -> records (match_scan.cuh); holds the caller's "S2" barrier
   auto match_rounds = [&](const int32_t *sA, const int32_t *sD, const uint32_t *yc, int k, bool live) {
-    const int myCnt = wsumC[lane];
-    const int T = __reduce_add_sync(kFull, myCnt);
-    if (T == 0) {
-      __syncthreads();
-      return;
-    }
-    int candBase = 0;
-    if (warp < T) {  // only warps that will own a candidate need the per-warp bases
-      int tot;
-      candBase = warp_excl_scan(myCnt, lane, tot);
-    }
-    for (int g0 = 0; g0 < T; g0 += kResMax) {
-      const int nR = min(kResMax, T - g0);
-      for (int g = g0 + warp; g < g0 + nR; g += 32) {
-        const int i = locate_candidate<E>(cmaskS, candBase, g, lane);
-        const uint32_t yi = (yc[i >> 5] >> (i & 31)) & 1u;
-        const int di = sD[i], dn1 = sD[i + 1];
-        int lo = i, hi = i + 1;
-        bool extends = false;
-        if (di <= dn1) extends = scan_up(sD, yc, wmaxS, i, yi, di, live, lane, lo);
-        if (!extends && di >= dn1) extends = scan_down(sD, yc, wmaxS, i, yi, dn1, M, live, lane, hi);
-        if (lane == 0) resS[g - g0] = make_int4(i, lo, hi, extends ? 0 : (i - lo) + (hi - i - 1));
-      }
-      __syncthreads();  // the round's results are published (first round: the scatter is complete too)
-      long long roundTotal = 0;
-      for (int c0 = 0; c0 < nR; c0 += 32) {
-        const int cntL = c0 + lane < nR ? resS[c0 + lane].w : 0;  // record count of entry c0 + lane
-        const int tot = __reduce_add_sync(kFull, cntL);
-        if (sink.pool && tot) {
-          const long long base = recBase + roundTotal;
-          ensure_chunks(base + tot);
-          // entry c0 + warp is this warp's own (candidate g = g0 + c0 + warp); big blocks are shared by all warps
-          const int mcnt = __shfl_sync(kFull, cntL, warp);
-          if (mcnt > 0 && mcnt < kBigBlock) {
-            const int4 en = resS[c0 + warp];
-            const int mex = __reduce_add_sync(kFull, lane < warp ? cntL : 0);
-            emit_block(sink, base + mex, sA, en.x, en.y, en.z, sD[en.x], sD[en.x + 1], k, lane, 32);
-          }
-          unsigned big = __ballot_sync(kFull, cntL >= kBigBlock);
-          while (big) {
-            const int j = __ffs(big) - 1;
-            big &= big - 1;
-            const int4 en = resS[c0 + j];
-            const int bex = __reduce_add_sync(kFull, lane < j ? cntL : 0);
-            emit_block(sink, base + bex, sA, en.x, en.y, en.z, sD[en.x], sD[en.x + 1], k, tid, kThreads);
-          }
-        }
-        roundTotal += tot;
-      }
-      recBase += roundTotal;
-      if (g0 + kResMax < T) __syncthreads();  // resS is reused by the next round
-    }
+    const SmemState st{sA, sD, yc, wmaxS};
+    pbwtgpu::match_rounds(st, k, live, M, E, wsumC, cmaskS, resS, sink, recBase, ensure_chunks, tid, lane, warp);
   };
 
   // -------- one site; CUR selects which half of the double buffers holds state k --------
@@ -515,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
         const int wd = wordBase + e, base = wd * 32;
         if (base >= M) break;
         const uint32_t vm = (M - base >= 32) ? kFull : ((1u << (M - base)) - 1u);
-        const uint32_t m = candidate_mask(sI + dC, yc[wd], e > 0 ? yc[wd - 1] >> 31 : pbFirst,
+        const uint32_t m = candidate_mask(SmemState{nullptr, sI + dC, yc, nullptr}, yc[wd], e > 0 ? yc[wd - 1] >> 31 : pbFirst,
                                           e < E - 1 ? yc[wd + 1] & 1u : nb, base, vm, lane);
         if (lane == e) myMask = m;
         tw += __popc(m);

@@ -16,6 +16,10 @@
 // (log2 W rounds, all windows in parallel) yields the exact state at every boundary.
 #include "windows.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
 namespace pbwtgpu {
 namespace {
 
@@ -117,6 +121,49 @@ __global__ void __launch_bounds__(256) gather_records_kernel(const int4 *pool, c
   for (int t = threadIdx.x; t < n; t += blockDim.x) dst[t] = srcp[t];
 }
 
+
+// Records of a wide-panel sweep: one segment per (column, CTA of the window's group), in callback order
+// (column-major, CTAs in position order).  One warp copies 32 segments, one after the other.
+__global__ void __launch_bounds__(256) gather_segments_kernel(const int4 *pool, const int *chunkTab, int poolChunks,
+                                                              const int32_t *segCnt, const long long *segSrc,
+                                                              const long long *segDst, long long nSeg, int G, int spw,
+                                                              int N, int W, int4 *out) {
+  const int lane = threadIdx.x & 31;
+  const long long first = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  if (first >= nSeg) return;
+  const long long mine = first + lane;
+  const int cnt = mine < nSeg ? segCnt[mine] : 0;
+  unsigned live = __ballot_sync(kFull, cnt > 0);
+  while (live) {
+    const int l = __ffs(live) - 1;
+    live &= live - 1;
+    const long long seg = first + l;
+    const int n = __shfl_sync(kFull, cnt, l);
+    const int col = (int)(seg / G), g = (int)(seg % G);
+    const int win = col >= N ? W - 1 : col / spw;
+    const int *tab = chunkTab + (size_t)(win * G + g) * poolChunks;
+    const long long so = segSrc[seg], dof = segDst[seg];
+    for (int t = lane; t < n; t += 32) {
+      const long long o = so + t;
+      const int id = tab[o >> kRecChunkLog];
+      if (id >= 0) out[dof + t] = pool[((long long)id << kRecChunkLog) + (o & (kRecChunk - 1))];
+    }
+  }
+}
+
+struct IntToLL {
+  __host__ __device__ long long operator()(int32_t v) const { return (long long)v; }
+};
+
+__global__ void permute_nomatch_kernel(const pbwtgpu_nomatch *in, const uint32_t *idx, long long n, pbwtgpu_nomatch *out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[idx[i]];
+}
+__global__ void iota_u32_kernel(uint32_t *out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)i;
+}
+
 }  // namespace
 
 int launch_make_groups(const int32_t *ord, int32_t *dv, const int32_t *gJ, const int32_t *gfdJ, int32_t *g, int32_t *gfd,
@@ -156,6 +203,56 @@ int launch_gather_records(const pbwtgpu_match *pool, const int *chunkTab, int po
                                                     winCount, reinterpret_cast<int4 *>(out));
   }
   return (int)cudaGetLastError();
+}
+
+size_t segment_scan_temp_bytes(long long nSeg) {
+  size_t bytes = 0;
+  cub::TransformInputIterator<long long, IntToLL, const int32_t *> it(nullptr, IntToLL());
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, (long long *)nullptr, (int)nSeg);
+  return bytes;
+}
+
+int launch_segment_scan(const int32_t *segCnt, long long nSeg, long long *segDst, void *temp, size_t tempBytes,
+                        cudaStream_t stream) {
+  cub::TransformInputIterator<long long, IntToLL, const int32_t *> it(segCnt, IntToLL());
+  return (int)cub::DeviceScan::ExclusiveSum(temp, tempBytes, it, segDst, (int)nSeg, stream);
+}
+
+int launch_gather_segments(const pbwtgpu_match *pool, const int *chunkTab, int poolChunks, const int32_t *segCnt,
+                           const long long *segSrc, const long long *segDst, long long nSeg, int G, int spw, int N, int W,
+                           pbwtgpu_match *out, cudaStream_t stream) {
+  if (nSeg > 0) {
+    const long long warps = (nSeg + 31) / 32;
+    gather_segments_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const int4 *>(pool), chunkTab,
+                                                                           poolChunks, segCnt, segSrc, segDst, nSeg, G, spw,
+                                                                           N, W, reinterpret_cast<int4 *>(out));
+  }
+  return (int)cudaGetLastError();
+}
+
+int sort_nomatch(const unsigned long long *keys, const pbwtgpu_nomatch *events, long long n, pbwtgpu_nomatch *out,
+                 cudaStream_t stream) {
+  if (n <= 0) return 0;
+  unsigned long long *keysOut = nullptr;
+  uint32_t *idxIn = nullptr, *idxOut = nullptr;
+  void *temp = nullptr;
+  size_t tempBytes = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, keys, keysOut, idxIn, idxOut, (int)n, 0, 64, stream);
+  if (e == cudaSuccess) e = cudaMalloc(&keysOut, sizeof(unsigned long long) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&idxIn, sizeof(uint32_t) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&idxOut, sizeof(uint32_t) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&temp, tempBytes);
+  if (e == cudaSuccess) {
+    iota_u32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(idxIn, n);
+    e = cub::DeviceRadixSort::SortPairs(temp, tempBytes, keys, keysOut, idxIn, idxOut, (int)n, 0, 64, stream);
+  }
+  if (e == cudaSuccess) {
+    permute_nomatch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(events, idxOut, n, out);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(keysOut); cudaFree(idxIn); cudaFree(idxOut); cudaFree(temp);
+  return (int)e;
 }
 
 }  // namespace pbwtgpu

@@ -23,4 +23,16 @@ int launch_gather_records(const pbwtgpu_match *pool, const int *chunkTab, int po
                           const unsigned long long *winCount, int nWindows, int maxChunksPerWindow, pbwtgpu_match *out,
                           cudaStream_t stream);
 
+// Wide-panel sweeps write one record segment per (column, CTA): exclusive 64-bit scan of the segment counts
+// (nSeg entries, the last one a zero so that segDst[nSeg-1] is the total) and the gather into callback order.
+size_t segment_scan_temp_bytes(long long nSeg);
+int launch_segment_scan(const int32_t *segCnt, long long nSeg, long long *segDst, void *temp, size_t tempBytes,
+                        cudaStream_t stream);
+int launch_gather_segments(const pbwtgpu_match *pool, const int *chunkTab, int poolChunks, const int32_t *segCnt,
+                           const long long *segSrc, const long long *segDst, long long nSeg, int G, int spw, int N, int W,
+                           pbwtgpu_match *out, cudaStream_t stream);
+// "no match" events of a wide query sweep arrive in arbitrary order: sort them by key (site, query-PBWT position)
+int sort_nomatch(const unsigned long long *keys, const pbwtgpu_nomatch *events, long long n, pbwtgpu_nomatch *out,
+                 cudaStream_t stream);
+
 }  // namespace pbwtgpu

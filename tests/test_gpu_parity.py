@@ -272,8 +272,8 @@ def test_global_memory_kernel_forced(eng, orc, M, N, W, dens):
     eng.set_option("force_global", 1)
     eng.set_option("windows", W)
     try:
-        check_build(eng, orc, x, M, N, matches=False)
-        check_build(eng, orc, x, M, N, a_start=a0, matches=False)
+        check_build(eng, orc, x, M, N)
+        check_build(eng, orc, x, M, N, a_start=a0)
     finally:
         eng.set_option("force_global", 0)
         eng.set_option("windows", 0)
@@ -288,9 +288,36 @@ def test_wide_panels(eng, orc, M, N, dens):
 
 
 def test_wide_panel_windowed_mosaic(eng, orc):
+    """Wide panel, window-parallel, with maxWithin (records from per-CTA streams put into callback order)."""
     M, N = 30000, 1200
-    x = O.generate_panel(M, N, seed=0x5EED0003, L=300, mu=4.0)
-    check_build(eng, orc, x, M, N, matches=False)
+    x = O.generate_panel(M, N, seed=0x5EED0003, L=300, mu=40.0)
+    check_build(eng, orc, x, M, N)
+
+
+@pytest.mark.parametrize("M,N,dens,W", [(13313, 48, 0.5, 0), (20000, 40, 0.5, 3), (50021, 64, 0.08, 1), (100000, 40, 0.3, 0)])
+def test_wide_panels_max_within(eng, orc, M, N, dens, W):
+    """matchMaximalWithin on panels wider than shared memory: random panels with a block of duplicates (big
+    blocks written by the whole CTA, several candidate rounds) through the build and the stored-stream route."""
+    rng = np.random.default_rng(M + 7)
+    hap = (rng.random((M, N)) < dens).astype(np.uint8)
+    hap[100:400] = hap[100]
+    hap[M - 200:] = hap[M - 1]
+    eng.set_option("windows", W)
+    try:
+        check_build(eng, orc, O.pack_panel(hap), M, N)
+    finally:
+        eng.set_option("windows", 0)
+
+
+def test_wide_panel_small_record_pool(eng, orc):
+    """The record pool overflows on the first attempt and the sweep is rerun with the exact size."""
+    M, N = 16000, 60
+    x = O.generate_panel(M, N, seed=0x5EED0013, L=20, mu=300.0)
+    eng.set_option("match_capacity", 10000)
+    try:
+        check_build(eng, orc, x, M, N)
+    finally:
+        eng.set_option("match_capacity", 0)
 
 
 @pytest.mark.parametrize("M,N,R,W,dens,with_start", [(200, 90, 3, 2, 0.3, False), (1000, 240, 4, 5, 0.05, True), (33, 64, 8, 1, 0.5, False),
@@ -343,7 +370,8 @@ def test_smem_limit_without_matches(eng, orc):
     check_build(eng, orc, O.pack_panel(hap), M, N, matches=False)
 
 
-@pytest.mark.parametrize("M,Q,N,dp,dq", [(60, 7, 80, 0.03, 0.3), (1000, 300, 120, 0.1, 0.1), (3000, 1000, 60, 0.05, 0.05)])
+@pytest.mark.parametrize("M,Q,N,dp,dq", [(60, 7, 80, 0.03, 0.3), (1000, 300, 120, 0.1, 0.1), (3000, 1000, 60, 0.05, 0.05),
+                                         (5000, 2500, 50, 0.2, 0.2), (300, 8192, 40, 0.4, 0.4), (2000, 700, 90, 0.004, 0.01)])
 def test_query_sweep_wide_kernel_forced(eng, orc, M, Q, N, dp, dq):
     """The wide-panel query sweep (state in global memory) forced onto narrow panels."""
     rng = np.random.default_rng(M + Q + 1)
@@ -361,10 +389,21 @@ def test_query_sweep_wide_kernel_forced(eng, orc, M, Q, N, dp, dq):
     assert len(nom) == len(want_nom) and (nom == want_nom).all()
 
 
-def test_query_sweep_wide_panel(eng, orc):
-    """BASELINE config 5's shape class: a panel wider than shared memory (M = 40,000), 300 queries."""
-    M, Q, N = 40000, 300, 400
-    x = O.generate_panel(M + Q, N, seed=0x5EED0005, L=200, mu=6.0)
+def test_query_sweep_many_queries_narrow_panel(eng, orc):
+    """More queries than the shared-memory kernel holds: routed to the wide kernel without forcing."""
+    M, Q, N = 900, 3000, 70
+    x = O.generate_panel(M + Q, N, seed=0x5EED0015, L=30, mu=5.0)
+    hap = O.unpack_panel(x, M + Q)
+    pyz, qyz = _split_streams(orc, hap[:M], hap[M:])
+    want_rec, want_nom = orc.match_sweep(pyz, M, N, qyz, Q)
+    rec, nom = eng.match_sweep(pyz, M, N, qyz, Q)
+    assert len(rec) == len(want_rec) and (rec == want_rec).all() and (nom == want_nom).all()
+
+
+@pytest.mark.parametrize("M,Q,N,L,mu", [(40000, 300, 400, 200, 6.0), (100000, 2000, 150, 50, 2000.0)])
+def test_query_sweep_wide_panel(eng, orc, M, Q, N, L, mu):
+    """BASELINE config 5's shape class: a panel wider than shared memory, queries spread over the group's CTAs."""
+    x = O.generate_panel(M + Q, N, seed=0x5EED0005, L=L, mu=mu)
     hap = O.unpack_panel(x, M + Q)
     pyz, qyz = _split_streams(orc, hap[:M], hap[M:])
     want_rec, want_nom = orc.match_sweep(pyz, M, N, qyz, Q)
