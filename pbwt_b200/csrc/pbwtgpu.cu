@@ -25,6 +25,7 @@ struct pbwtgpu_ctx {
   long long optWindowTimes = 0;  // debugging: print per-window CTA times of pass 2 to stderr
   long long optNoCandidates = 0;  // profiling aid
   long long optForceGlobal = 0;  // testing: use the global-memory kernel even for narrow panels
+  long long optNoCluster = 0;    // testing: wide panels through the cooperative-grid path even where clusters fit
   // profiling
   bool profile = false;
   float ms[PBWTGPU_NUM_KERNEL_CLASSES] = {0};
@@ -237,7 +238,9 @@ struct WindowedSweep {
       const int minSites = ctx->optWindows > 0 ? 1 : 256;  // below this a window does not repay its two extra passes
       W = (int)std::max<long long>(1, std::min<long long>(want, N / minSites));
     }
-    if (useGlobal) sweep_global_plan(M, ctx->smCount, W, &G, &chunk, &W);
+    if (useGlobal) {
+      sweep_global_plan(M, ctx->smCount, W, mode, true, wantMatch, false, 0, !ctx->optNoCluster, &G, &chunk, &W, &gb.cluster);
+    }
     spw = N > 0 ? (N + W - 1) / W : 1;
     W = N > 0 ? (N + spw - 1) / spw : 1;
     nodes = sharded ? W : W - 1;  // a shard also needs the node of its last window (its aggregate)
@@ -679,6 +682,7 @@ int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value) {
   else if (!strcmp(name, "match_capacity")) ctx->optMatchCap = value;
   else if (!strcmp(name, "window_times")) ctx->optWindowTimes = value;
   else if (!strcmp(name, "force_global")) ctx->optForceGlobal = value;
+  else if (!strcmp(name, "no_cluster")) ctx->optNoCluster = value;
   else if (!strcmp(name, "debug_no_candidates")) ctx->optNoCandidates = value;
   else return fail(ctx, PBWTGPU_ERR_ARG, "unknown option %s", name);
   return 0;
@@ -936,7 +940,7 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
   char *scanTemp = nullptr;
   size_t scanTempBytes = 0;
   if (wide) {
-    sweep_global_plan(M, ctx->smCount, 1, &G, &chunk, &Wd);
+    sweep_global_plan(M, ctx->smCount, 1, kSorted, true, false, true, Q, !ctx->optNoCluster, &G, &chunk, &Wd, &gb.cluster);
     const size_t MS = (size_t)G * chunk;
     gb.G = G; gb.chunk = chunk;
     nSeg = (long long)(N + 1) * G + 1;

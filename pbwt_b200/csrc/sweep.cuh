@@ -7,6 +7,8 @@ namespace pbwtgpu {
 constexpr int kRecChunkLog = 13;  // match records are allocated to windows in chunks of 8192 (128 KiB)
 constexpr int kRecChunk = 1 << kRecChunkLog;
 
+enum SweepMode { kGather = 0, kSorted = 1 };
+
 // One launch sweeps W windows concurrently (one CTA per window), each starting from the exact
 // state (a,d) entering its first site.
 //   regular mode (perWindowSites == 0): window w covers sites [w*sitesPerWindow, min(N,(w+1)*sitesPerWindow))
@@ -53,7 +55,6 @@ struct SweepArgs {
   unsigned long long *qCounts;   // [0] records, [1] "no match" events
 };
 
-enum SweepMode { kGather = 0, kSorted = 1 };
 
 constexpr int kTabMirror = 64;  // newest chunk ids of a window mirrored in shared memory
 
@@ -83,8 +84,10 @@ int launch_query_sweep_smem(const SweepArgs &args, cudaStream_t stream);
 
 
 // ---- wide panels: state in global memory, groups of cooperating CTAs (sweep_global.cu) ----
-// plan: G CTAs per window and their chunk of sorted positions; W = windows that fit in maxCtas co-resident CTAs
-void sweep_global_plan(int M, int maxCtas, int wantWindows, int *G, int *chunk, int *W);
+// plan: G CTAs per window and their chunk of sorted positions, W = windows swept concurrently, and whether each
+// group is a thread-block cluster (M <= 16 * 32768) or part of a cooperative grid (W * G <= maxCtas)
+void sweep_global_plan(int M, int maxCtas, int wantWindows, SweepMode mode, bool with_d, bool match, bool query, int Q,
+                       bool allowCluster, int *G, int *chunk, int *W, int *cluster);
 size_t sweep_global_state_ints(int G, int chunk, int W, bool with_d);  // a (and d) double buffers, in int32
 size_t sweep_global_sync_bytes(int W);
 size_t sweep_global_column_words(int G, int chunk, int W);  // words of ySorted / wmaxG / zpre (double buffered)
@@ -92,6 +95,7 @@ size_t sweep_global_column_words(int G, int chunk, int W);  // words of ySorted 
 // zeroed before every launch.
 struct GlobalBuffers {
   int G = 1, chunk = 0;
+  int cluster = 0;  // groups are thread-block clusters (sweep_global_plan)
   int32_t *aBuf = nullptr, *dBuf = nullptr;  // sweep_global_state_ints
   uint32_t *partials = nullptr;
   void *gsync = nullptr;

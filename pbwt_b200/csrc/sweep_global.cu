@@ -21,6 +21,8 @@
 // match_scan.cuh on state k in global memory (L2) -- maxWithin over the candidates among its own positions,
 // the query sweep over its share of the queries (in query-PBWT order, one warp per query).  Records go to a
 // per-CTA chunked stream; (site, CTA) segment tables put them into callback order afterwards (windows.cu).
+#include <algorithm>
+
 #include "match_scan.cuh"
 #include "sweep.cuh"
 
@@ -51,6 +53,16 @@ __device__ __forceinline__ unsigned ld_volatile(const unsigned *p) {
   unsigned v;
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
+}
+
+// ---- thread-block clusters: hardware barrier + distributed shared memory for groups of up to 16 CTAs ----
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(const void *localSmem, unsigned ctaRank, uint32_t v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(localSmem)), "r"(ctaRank));
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(v) : "memory");
 }
 
 // run-max summary: bit 31 = "contains a run head", low 31 bits = max d since the last head (or overall)
@@ -151,7 +163,10 @@ struct GlobalArgs {
   unsigned long long *nmKeys;  // sort key (site * Q + query-PBWT position) of each "no match" event
 };
 
-template <int MODE, bool WITH_D, bool MATCH, bool QUERY>
+// CLUSTER: the group is one thread-block cluster (G <= 16): the per-site exchange goes through distributed
+// shared memory and the group barriers are hardware cluster barriers (release/acquire at cluster scope, which
+// also orders the a[]/d[] stores to global memory) instead of flags and an arrival counter in global memory.
+template <int MODE, bool WITH_D, bool MATCH, bool QUERY, bool CLUSTER>
 __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepArgs p, const GlobalArgs ga) {
   extern __shared__ __align__(16) uint32_t smem[];
   constexpr bool SCAN = MATCH || QUERY;
@@ -175,6 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
   __shared__ int wsumC[32];
   __shared__ int xZ, xC;        // zeros before this CTA, zeros in the whole column
   __shared__ uint32_t xR;       // run-max carry entering this CTA
+  __shared__ uint32_t cpart[16][2];  // CLUSTER: (zeros, run-max summary) of every CTA of the group, written by its owner
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int win = blockIdx.x / G, g = blockIdx.x % G;
@@ -206,6 +222,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
   unsigned int epoch = 0;                   // barriers passed so far
 
   auto group_barrier = [&]() {
+    if (CLUSTER) {
+      cluster_sync_all();
+      return;
+    }
     __syncthreads();
     if (tid == 0) {
       __threadfence();
@@ -397,6 +417,33 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
         if (lane >= dl) rInc = rm_combine(t, rInc);
       }
     }
+    if (CLUSTER) {
+      if (warp == 0) {
+        const uint32_t rCta = __shfl_sync(kFull, rInc, 31);
+        if (lane < G) {  // lane l delivers this CTA's totals to CTA l of the cluster
+          st_cluster_u32(&cpart[g][0], (unsigned)lane, (uint32_t)zCta);
+          st_cluster_u32(&cpart[g][1], (unsigned)lane, rCta);
+        }
+        wexS[lane] = zExLane;
+      }
+      cluster_sync_all();
+      if (warp == 0) {
+        const uint32_t z = lane < G ? cpart[lane][0] : 0u;
+        const uint32_t r = lane < G ? cpart[lane][1] : 0u;
+        const int zAll = __reduce_add_sync(kFull, (int)z);
+        const int zBefore = __reduce_add_sync(kFull, lane < g ? (int)z : 0);
+        uint32_t x = lane < g ? r : 0u;  // identity = (no head, 0)
+        if (WITH_D) {
+#pragma unroll
+          for (int dl = 1; dl < 32; dl <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, x, dl);
+            if (lane >= dl) x = rm_combine(t, x);
+          }
+          x = __shfl_sync(kFull, x, 31);
+        }
+        if (lane == 0) { xZ = zBefore; xC = zAll; xR = x; }
+      }
+    } else
     if (warp == 0) {
       const unsigned tag = (unsigned)(k - k0) + 1u;
       const uint32_t rCta = __shfl_sync(kFull, rInc, 31);
@@ -691,10 +738,75 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
 
 }  // namespace
 
-// Plan: G CTAs per window (positions per CTA <= kMaxChunk, multiple of 1024), W windows with W*G <= maxCtas.
-void sweep_global_plan(int M, int maxCtas, int wantWindows, int *G, int *chunk, int *W) {
+static size_t smem_bytes(int chunk, bool with_d, bool match, bool query, int Q) {
+  const size_t cw = chunk / 32;
+  const bool scan = match || query;
+  const size_t QW = query ? (size_t)((Q + 31) / 32 + 31) / 32 * 32 : 0;
+  size_t words = cw + (with_d ? chunk : 0) + (scan ? cw : 0) + (match ? cw : 0) + (query ? cw : 0) +
+                 (scan ? kResMax * 4 + kTabMirror : 0) + (query ? kResMax : 0) + QW * 2 + QW * 32 * 2;
+  return words * 4;
+}
+
+template <bool CLUSTER>
+static void *pick_kernel(SweepMode mode, bool with_d, bool match, bool query) {
+  if (query) return (void *)sweep_global_kernel<kSorted, true, false, true, CLUSTER>;
+  if (mode == kGather)
+    return match ? (void *)sweep_global_kernel<kGather, true, true, false, CLUSTER>
+                 : with_d ? (void *)sweep_global_kernel<kGather, true, false, false, CLUSTER>
+                          : (void *)sweep_global_kernel<kGather, false, false, false, CLUSTER>;
+  return match ? (void *)sweep_global_kernel<kSorted, true, true, false, CLUSTER>
+               : with_d ? (void *)sweep_global_kernel<kSorted, true, false, false, CLUSTER>
+                        : (void *)sweep_global_kernel<kSorted, false, false, false, CLUSTER>;
+}
+
+static int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p <<= 1; return p; }
+
+// clusters of G CTAs that can be co-resident (0 = this cluster size cannot be launched)
+static int max_active_clusters(void *kern, int G, size_t smemBytes) {
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes) != cudaSuccess) return 0;
+  if (G > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(G);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smemBytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+// Plan.  A window of sites is swept by G CTAs, each owning `chunk` (multiple of 1024, <= kMaxChunk) sorted
+// positions; W windows run concurrently.  Panels up to 16 * kMaxChunk haplotypes use one thread-block cluster per
+// window (hardware barriers, exchange through distributed shared memory); wider ones a cooperative grid of
+// W * G <= maxCtas CTAs synchronised through global memory.
+void sweep_global_plan(int M, int maxCtas, int wantWindows, SweepMode mode, bool with_d, bool match, bool query, int Q,
+                       bool allowCluster, int *G, int *chunk, int *W, int *cluster) {
   const int gmin = (M + kMaxChunk - 1) / kMaxChunk;
   int w = wantWindows > 0 ? wantWindows : 1;
+  *cluster = 0;
+  if (allowCluster && gmin <= 16) {
+    const int gLo = pow2_ceil(gmin), gHi = std::max(gLo, std::min(16, pow2_floor(std::max(1, (M + 1023) / 1024))));
+    int g = std::min(gHi, std::max(gLo, pow2_floor(std::max(1, maxCtas / w))));
+    for (; g >= gLo; g >>= 1) {
+      const int ch = ((M + g - 1) / g + 1023) / 1024 * 1024;
+      const int n = max_active_clusters(pick_kernel<true>(mode, with_d, match, query), g, smem_bytes(ch, with_d, match, query, Q));
+      if (n >= 1) {
+        *G = g; *chunk = ch; *W = std::min(w, n); *cluster = 1;
+        return;
+      }
+    }
+  }
   if (w * gmin > maxCtas) w = maxCtas / gmin;
   if (w < 1) w = 1;
   int g = maxCtas / w;  // use every SM: more CTAs per window shorten the per-site critical path
@@ -712,58 +824,52 @@ size_t sweep_global_state_ints(int G, int chunk, int W, bool with_d) {
 
 size_t sweep_global_column_words(int G, int chunk, int W) { return (size_t)W * 2 * G * (chunk / 32); }
 
-static size_t smem_bytes(int chunk, bool with_d, bool match, bool query, int Q) {
-  const size_t cw = chunk / 32;
-  const bool scan = match || query;
-  const size_t QW = query ? (size_t)((Q + 31) / 32 + 31) / 32 * 32 : 0;
-  size_t words = cw + (with_d ? chunk : 0) + (scan ? cw : 0) + (match ? cw : 0) + (query ? cw : 0) +
-                 (scan ? kResMax * 4 + kTabMirror : 0) + (query ? kResMax : 0) + QW * 2 + QW * 32 * 2;
-  return words * 4;
-}
-
-int launch_sweep_global(const SweepArgs &a, SweepMode mode, bool with_d, bool with_match, const GlobalBuffers &b,
-                        cudaStream_t stream) {
-  if (with_match && !with_d) return (int)cudaErrorInvalidValue;
-  const size_t smemBytes = smem_bytes(b.chunk, with_d, with_match, false, 0);
-  void *kern;
-  if (mode == kGather)
-    kern = with_match ? (void *)sweep_global_kernel<kGather, true, true, false>
-                      : with_d ? (void *)sweep_global_kernel<kGather, true, false, false>
-                               : (void *)sweep_global_kernel<kGather, false, false, false>;
-  else
-    kern = with_match ? (void *)sweep_global_kernel<kSorted, true, true, false>
-                      : with_d ? (void *)sweep_global_kernel<kSorted, true, false, false>
-                               : (void *)sweep_global_kernel<kSorted, false, false, false>;
+static int launch_any(void *kern, bool cluster, const SweepArgs &a, const GlobalBuffers &b, int ctas, size_t smemBytes,
+                      cudaStream_t stream) {
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
   if (err != cudaSuccess) return (int)err;
   SweepArgs args = a;
-  GlobalArgs ga{};
-  ga.G = b.G; ga.chunk = b.chunk; ga.aBuf = b.aBuf; ga.dBuf = b.dBuf; ga.partials = b.partials;
-  ga.gsync = static_cast<GroupSync *>(b.gsync);
-  ga.ySorted = b.ySorted; ga.wmaxG = b.wmaxG; ga.zpre = b.zpre; ga.segCnt = b.segCnt; ga.segSrc = b.segSrc;
-  void *params[] = {&args, &ga};
-  err = cudaLaunchCooperativeKernel(kern, dim3(a.nWindows * b.G), dim3(kThreads), params, smemBytes, stream);
-  return (int)err;
-}
-
-int query_sweep_global_max_q() { return kQCap; }
-
-int launch_query_sweep_global(const SweepArgs &a, const GlobalBuffers &b, cudaStream_t stream) {
-  if (a.Q < 1 || a.Q > kQCap) return (int)cudaErrorInvalidValue;
-  const size_t smemBytes = smem_bytes(b.chunk, true, false, true, a.Q);
-  void *kern = (void *)sweep_global_kernel<kSorted, true, false, true>;
-  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
-  if (err != cudaSuccess) return (int)err;
-  SweepArgs args = a;
-  args.nWindows = 1;
   GlobalArgs ga{};
   ga.G = b.G; ga.chunk = b.chunk; ga.aBuf = b.aBuf; ga.dBuf = b.dBuf; ga.partials = b.partials;
   ga.gsync = static_cast<GroupSync *>(b.gsync);
   ga.ySorted = b.ySorted; ga.wmaxG = b.wmaxG; ga.zpre = b.zpre; ga.segCnt = b.segCnt; ga.segSrc = b.segSrc;
   ga.qf = b.qf; ga.qe = b.qe; ga.nmKeys = b.nmKeys;
   void *params[] = {&args, &ga};
-  err = cudaLaunchCooperativeKernel(kern, dim3(b.G), dim3(kThreads), params, smemBytes, stream);
-  return (int)err;
+  if (!cluster) return (int)cudaLaunchCooperativeKernel(kern, dim3(ctas), dim3(kThreads), params, smemBytes, stream);
+  if (b.G > 8) {
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (err != cudaSuccess) return (int)err;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = b.G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelExC(&cfg, kern, params);
+}
+
+int launch_sweep_global(const SweepArgs &a, SweepMode mode, bool with_d, bool with_match, const GlobalBuffers &b,
+                        cudaStream_t stream) {
+  if (with_match && !with_d) return (int)cudaErrorInvalidValue;
+  if (b.cluster && b.G > 16) return (int)cudaErrorInvalidValue;
+  void *kern = b.cluster ? pick_kernel<true>(mode, with_d, with_match, false) : pick_kernel<false>(mode, with_d, with_match, false);
+  return launch_any(kern, b.cluster, a, b, a.nWindows * b.G, smem_bytes(b.chunk, with_d, with_match, false, 0), stream);
+}
+
+int query_sweep_global_max_q() { return kQCap; }
+
+int launch_query_sweep_global(const SweepArgs &a, const GlobalBuffers &b, cudaStream_t stream) {
+  if (a.Q < 1 || a.Q > kQCap) return (int)cudaErrorInvalidValue;
+  if (b.cluster && b.G > 16) return (int)cudaErrorInvalidValue;
+  void *kern = b.cluster ? pick_kernel<true>(kSorted, true, false, true) : pick_kernel<false>(kSorted, true, false, true);
+  SweepArgs args = a;
+  args.nWindows = 1;
+  return launch_any(kern, b.cluster, args, b, b.G, smem_bytes(b.chunk, true, false, true, a.Q), stream);
 }
 
 size_t sweep_global_sync_bytes(int W) { return sizeof(GroupSync) * (size_t)W; }

@@ -261,21 +261,25 @@ def test_query_sweep_mosaic(eng, orc):
 
 @pytest.mark.parametrize("M,N,W,dens", [(8, 10, 1, 0.3), (33, 40, 3, 0.5), (1000, 60, 1, 0.2), (3000, 200, 5, 0.05),
                                         (5000, 64, 37, 0.3), (2752, 38, 2, 0.3)])
-def test_global_memory_kernel_forced(eng, orc, M, N, W, dens):
-    """The wide-panel kernel (state in global memory, cooperating CTA groups) forced onto narrow panels,
-    with and without window parallelism: same bits as the reference sweep."""
+@pytest.mark.parametrize("no_cluster", [0, 1])
+def test_global_memory_kernel_forced(eng, orc, M, N, W, dens, no_cluster):
+    """The wide-panel kernel (state in global memory; groups of CTAs as thread-block clusters, or as a cooperative
+    grid synchronised through global memory) forced onto narrow panels, with and without window parallelism:
+    same bits as the reference sweep."""
     rng = np.random.default_rng(M * 3 + N)
     hap = (rng.random((M, N)) < dens).astype(np.uint8)
     hap[: M // 4] = hap[0]
     x = O.pack_panel(hap)
     a0 = rng.permutation(M).astype(np.int32)
     eng.set_option("force_global", 1)
+    eng.set_option("no_cluster", no_cluster)
     eng.set_option("windows", W)
     try:
         check_build(eng, orc, x, M, N)
         check_build(eng, orc, x, M, N, a_start=a0)
     finally:
         eng.set_option("force_global", 0)
+        eng.set_option("no_cluster", 0)
         eng.set_option("windows", 0)
 
 
@@ -294,8 +298,10 @@ def test_wide_panel_windowed_mosaic(eng, orc):
     check_build(eng, orc, x, M, N)
 
 
-@pytest.mark.parametrize("M,N,dens,W", [(13313, 48, 0.5, 0), (20000, 40, 0.5, 3), (50021, 64, 0.08, 1), (100000, 40, 0.3, 0)])
-def test_wide_panels_max_within(eng, orc, M, N, dens, W):
+@pytest.mark.parametrize("M,N,dens,W,no_cluster", [(13313, 48, 0.5, 0, 0), (20000, 40, 0.5, 3, 0), (20000, 40, 0.5, 3, 1),
+                                                   (50021, 64, 0.08, 1, 0), (100000, 40, 0.3, 0, 0), (100000, 40, 0.3, 0, 1),
+                                                   (600000, 26, 0.5, 0, 0)])
+def test_wide_panels_max_within(eng, orc, M, N, dens, W, no_cluster):
     """matchMaximalWithin on panels wider than shared memory: random panels with a block of duplicates (big
     blocks written by the whole CTA, several candidate rounds) through the build and the stored-stream route."""
     rng = np.random.default_rng(M + 7)
@@ -303,10 +309,12 @@ def test_wide_panels_max_within(eng, orc, M, N, dens, W):
     hap[100:400] = hap[100]
     hap[M - 200:] = hap[M - 1]
     eng.set_option("windows", W)
+    eng.set_option("no_cluster", no_cluster)
     try:
         check_build(eng, orc, O.pack_panel(hap), M, N)
     finally:
         eng.set_option("windows", 0)
+        eng.set_option("no_cluster", 0)
 
 
 def test_wide_panel_small_record_pool(eng, orc):
@@ -372,7 +380,8 @@ def test_smem_limit_without_matches(eng, orc):
 
 @pytest.mark.parametrize("M,Q,N,dp,dq", [(60, 7, 80, 0.03, 0.3), (1000, 300, 120, 0.1, 0.1), (3000, 1000, 60, 0.05, 0.05),
                                          (5000, 2500, 50, 0.2, 0.2), (300, 8192, 40, 0.4, 0.4), (2000, 700, 90, 0.004, 0.01)])
-def test_query_sweep_wide_kernel_forced(eng, orc, M, Q, N, dp, dq):
+@pytest.mark.parametrize("no_cluster", [0, 1])
+def test_query_sweep_wide_kernel_forced(eng, orc, M, Q, N, dp, dq, no_cluster):
     """The wide-panel query sweep (state in global memory) forced onto narrow panels."""
     rng = np.random.default_rng(M + Q + 1)
     hp = (rng.random((M, N)) < dp).astype(np.uint8)
@@ -381,10 +390,12 @@ def test_query_sweep_wide_kernel_forced(eng, orc, M, Q, N, dp, dq):
     pyz, qyz = _split_streams(orc, hp, hq)
     want_rec, want_nom = orc.match_sweep(pyz, M, N, qyz, Q)
     eng.set_option("force_global", 1)
+    eng.set_option("no_cluster", no_cluster)
     try:
         rec, nom = eng.match_sweep(pyz, M, N, qyz, Q)
     finally:
         eng.set_option("force_global", 0)
+        eng.set_option("no_cluster", 0)
     assert len(rec) == len(want_rec) and (rec == want_rec).all()
     assert len(nom) == len(want_nom) and (nom == want_nom).all()
 
@@ -400,12 +411,17 @@ def test_query_sweep_many_queries_narrow_panel(eng, orc):
     assert len(rec) == len(want_rec) and (rec == want_rec).all() and (nom == want_nom).all()
 
 
-@pytest.mark.parametrize("M,Q,N,L,mu", [(40000, 300, 400, 200, 6.0), (100000, 2000, 150, 50, 2000.0)])
-def test_query_sweep_wide_panel(eng, orc, M, Q, N, L, mu):
+@pytest.mark.parametrize("M,Q,N,L,mu,no_cluster", [(40000, 300, 400, 200, 6.0, 0), (40000, 300, 400, 200, 6.0, 1),
+                                                   (100000, 2000, 150, 50, 2000.0, 0), (100000, 2000, 150, 50, 2000.0, 1)])
+def test_query_sweep_wide_panel(eng, orc, M, Q, N, L, mu, no_cluster):
     """BASELINE config 5's shape class: a panel wider than shared memory, queries spread over the group's CTAs."""
     x = O.generate_panel(M + Q, N, seed=0x5EED0005, L=L, mu=mu)
     hap = O.unpack_panel(x, M + Q)
     pyz, qyz = _split_streams(orc, hap[:M], hap[M:])
     want_rec, want_nom = orc.match_sweep(pyz, M, N, qyz, Q)
-    rec, nom = eng.match_sweep(pyz, M, N, qyz, Q)
+    eng.set_option("no_cluster", no_cluster)
+    try:
+        rec, nom = eng.match_sweep(pyz, M, N, qyz, Q)
+    finally:
+        eng.set_option("no_cluster", 0)
     assert len(rec) == len(want_rec) and (rec == want_rec).all() and (nom == want_nom).all()
