@@ -239,7 +239,9 @@ struct WindowedSweep {
       W = (int)std::max<long long>(1, std::min<long long>(want, N / minSites));
     }
     if (useGlobal) {
-      sweep_global_plan(M, ctx->smCount, W, mode, true, wantMatch, false, 0, !ctx->optNoCluster, &G, &chunk, &W, &gb.cluster);
+      // planned for gather mode: the window combine sweeps pseudo-site columns in gather mode whatever the mode here
+      sweep_global_plan(M, ctx->smCount, W, kGather, true, wantMatch, false, 0, !ctx->optNoCluster, &G, &chunk, &W, &gb.cluster,
+                        &gb.stageCol);
     }
     spw = N > 0 ? (N + W - 1) / W : 1;
     W = N > 0 ? (N + spw - 1) / spw : 1;
@@ -464,7 +466,7 @@ struct WindowedSweep {
     std::vector<unsigned long long> counts(W, 0);
     long long *winNanos = nullptr;
     if (ctx->optWindowTimes) {
-      if (int rc = tmp.get(&winNanos, (size_t)W)) return rc;
+      if (int rc = tmp.get(&winNanos, (size_t)std::max(W, 4))) return rc;
       a.winNanos = winNanos;
     }
     // record streams: one per window (shared-memory kernel) or one per CTA (wide-panel kernel)
@@ -514,18 +516,23 @@ struct WindowedSweep {
       recCap = total;
     }
     if (winNanos) {
-      std::vector<long long> ns(W);
-      CUDA_TRY(ctx, cudaMemcpyAsync(ns.data(), winNanos, sizeof(long long) * W, cudaMemcpyDeviceToHost, ctx->stream));
+      std::vector<long long> ns(std::max(W, 4));
+      CUDA_TRY(ctx, cudaMemcpyAsync(ns.data(), winNanos, sizeof(long long) * ns.size(), cudaMemcpyDeviceToHost, ctx->stream));
       CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-      fprintf(stderr, "[pbwtgpu] pass-2 window times (us) and records:");
-      for (int w = 0; w < W; ++w) fprintf(stderr, " %d:%.0f/%llu", w, ns[w] * 1e-3, counts[w]);
-      fprintf(stderr, "\n");
+      if (useGlobal)
+        fprintf(stderr, "[pbwtgpu] wide kernel, CTA 0, cycles per site (%d sites, G=%d chunk=%d W=%d cluster=%d stage=%d): phase A %.0f, exchange %.0f, scatter+scans %.0f, end barrier %.0f\n",
+                spw, G, chunk, W, gb.cluster, gb.stageCol, (double)ns[0] / spw, (double)ns[1] / spw, (double)ns[2] / spw, (double)ns[3] / spw);
+      else {
+        fprintf(stderr, "[pbwtgpu] pass-2 window times (us) and records:");
+        for (int w = 0; w < W; ++w) fprintf(stderr, " %d:%.0f/%llu", w, ns[w] * 1e-3, counts[w]);
+        fprintf(stderr, "\n");
+      }
     }
     if (wantMatch && useGlobal) {
       res->nrec = segTotal;
       if (int rc = result_alloc(ctx, res, &res->rec, (size_t)std::max<long long>(segTotal, 1))) return rc;
       ScopedTimer t(ctx, PBWTGPU_K_AUX);
-      CUDA_TRY(ctx, launch_gather_segments(pool, chunkTab, poolChunks, gb.segCnt, gb.segSrc, segDst, nSeg - 1, G, spw, N, W,
+      CUDA_TRY(ctx, launch_gather_segments(pool, chunkTab, poolChunks, gb.segSrc, segDst, nSeg - 1, segTotal, G, spw, N, W,
                                            res->rec, ctx->stream));
       ctx->launches[PBWTGPU_K_AUX] += 1;
     } else if (wantMatch) {
@@ -940,7 +947,7 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
   char *scanTemp = nullptr;
   size_t scanTempBytes = 0;
   if (wide) {
-    sweep_global_plan(M, ctx->smCount, 1, kSorted, true, false, true, Q, !ctx->optNoCluster, &G, &chunk, &Wd, &gb.cluster);
+    sweep_global_plan(M, ctx->smCount, 1, kSorted, true, false, true, Q, !ctx->optNoCluster, &G, &chunk, &Wd, &gb.cluster, &gb.stageCol);
     const size_t MS = (size_t)G * chunk;
     gb.G = G; gb.chunk = chunk;
     nSeg = (long long)(N + 1) * G + 1;
@@ -953,6 +960,9 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
     if (int rc = tmp.get(&gb.ySorted, sweep_global_column_words(G, chunk, 1))) return rc;
     if (int rc = tmp.get(&gb.wmaxG, sweep_global_column_words(G, chunk, 1))) return rc;
     if (int rc = tmp.get(&gb.zpre, sweep_global_column_words(G, chunk, 1))) return rc;
+    if (int rc = tmp.get(&gb.any1, sweep_global_column_words(G, chunk, 1) / 32)) return rc;
+    if (int rc = tmp.get(&gb.any0, sweep_global_column_words(G, chunk, 1) / 32)) return rc;
+    if (int rc = tmp.get(&gb.wmax2, sweep_global_column_words(G, chunk, 1) / 32)) return rc;
     if (int rc = tmp.get(&gb.segCnt, (size_t)nSeg)) return rc;
     if (int rc = tmp.get(&gb.segSrc, (size_t)nSeg)) return rc;
     if (int rc = tmp.get(&gb.qf, (size_t)Q)) return rc;
@@ -1035,8 +1045,8 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
   if (wide) {
     {
       ScopedTimer t(ctx, PBWTGPU_K_AUX);
-      CUDA_TRY(ctx, launch_gather_segments(pool, chunkTab, poolChunks, gb.segCnt, gb.segSrc, segDst, nSeg - 1, G, std::max(N, 1), N,
-                                           1, recDev, ctx->stream));
+      CUDA_TRY(ctx, launch_gather_segments(pool, chunkTab, poolChunks, gb.segSrc, segDst, nSeg - 1, (long long)got[0], G,
+                                           std::max(N, 1), N, 1, recDev, ctx->stream));
       ctx->launches[PBWTGPU_K_AUX] += 1;
     }
     if (got[1]) {  // events were appended in arrival order: put them in (site, query-PBWT position) order

@@ -87,7 +87,7 @@ int launch_query_sweep_smem(const SweepArgs &args, cudaStream_t stream);
 // plan: G CTAs per window and their chunk of sorted positions, W = windows swept concurrently, and whether each
 // group is a thread-block cluster (M <= 16 * 32768) or part of a cooperative grid (W * G <= maxCtas)
 void sweep_global_plan(int M, int maxCtas, int wantWindows, SweepMode mode, bool with_d, bool match, bool query, int Q,
-                       bool allowCluster, int *G, int *chunk, int *W, int *cluster);
+                       bool allowCluster, int *G, int *chunk, int *W, int *cluster, int *stageCol);
 size_t sweep_global_state_ints(int G, int chunk, int W, bool with_d);  // a (and d) double buffers, in int32
 size_t sweep_global_sync_bytes(int W);
 size_t sweep_global_column_words(int G, int chunk, int W);  // words of ySorted / wmaxG / zpre (double buffered)
@@ -95,7 +95,8 @@ size_t sweep_global_column_words(int G, int chunk, int W);  // words of ySorted 
 // zeroed before every launch.
 struct GlobalBuffers {
   int G = 1, chunk = 0;
-  int cluster = 0;  // groups are thread-block clusters (sweep_global_plan)
+  int cluster = 0;   // groups are thread-block clusters (sweep_global_plan)
+  int stageCol = 0;  // gather mode: bit columns are staged in shared memory (sweep_global_plan)
   int32_t *aBuf = nullptr, *dBuf = nullptr;  // sweep_global_state_ints
   uint32_t *partials = nullptr;
   void *gsync = nullptr;
@@ -103,6 +104,8 @@ struct GlobalBuffers {
   uint32_t *ySorted = nullptr;
   int32_t *wmaxG = nullptr;
   int32_t *zpre = nullptr;          // query sweep only
+  uint32_t *any1 = nullptr, *any0 = nullptr;  // query sweep only: sweep_global_column_words / 32 each
+  int32_t *wmax2 = nullptr;
   // record segments, one per (column, CTA of the window's group), (N+1)*G entries; chunk table rows are per CTA
   int32_t *segCnt = nullptr;
   long long *segSrc = nullptr;

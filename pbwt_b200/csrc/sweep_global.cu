@@ -79,6 +79,18 @@ struct GlobalState {
   const uint32_t *yk;
   const int32_t *wm;
   int M, sentinel;  // d[0] = d[M] = k + 1
+  // second level, one entry per 32 words (1024 positions); query sweep only
+  const uint32_t *any1 = nullptr, *any0 = nullptr;  // bit j: word 32*e + j holds a one / a zero among its valid positions
+  const int32_t *wm2 = nullptr;                     // max of wmax over words [32e, 32e + 32)
+  __device__ __forceinline__ uint32_t anyw(int e, uint32_t x) const { return __ldcg((x ? any1 : any0) + e); }
+  __device__ __forceinline__ int wmax2(int e) const { return __ldcg(wm2 + e); }
+  // alleles equal to x among the valid positions of word w
+  __device__ __forceinline__ uint32_t hits(int w, uint32_t x) const {
+    const uint32_t v = __ldcg(yk + w);
+    const int base = w << 5;
+    const uint32_t vm = (M - base >= 32) ? kFull : (M > base ? ((1u << (M - base)) - 1u) : 0u);
+    return (x ? v : ~v) & vm;
+  }
   __device__ __forceinline__ int d(int i) const { return (i <= 0 || i >= M) ? sentinel : __ldcg(dC + i); }
   __device__ __forceinline__ uint32_t yw(int w) const { return __ldcg(yk + w); }
   __device__ __forceinline__ int wmax(int w) const { return __ldcg(wm + w); }
@@ -145,9 +157,96 @@ __device__ __forceinline__ int first_allele_in(const GlobalState &s, int lo, int
   return -1;
 }
 
+// nearest position <= from carrying allele x, or -1; two-level: word, its group of 32 words, then 32 groups per step
+__device__ __forceinline__ int prev_allele(const GlobalState &s, int from, uint32_t x, int lane) {
+  if (from < 0) return -1;
+  const int w = from >> 5;
+  {
+    const uint32_t b = s.hits(w, x) & (kFull >> (31 - (from & 31)));
+    if (b) return (w << 5) + 31 - __clz(b);
+  }
+  const int e = w >> 5;
+  {  // earlier words of the same group
+    const uint32_t m = s.anyw(e, x) & ((1u << (w & 31)) - 1u);
+    if (m) {
+      const int w2 = (e << 5) + 31 - __clz(m);
+      return (w2 << 5) + 31 - __clz(s.hits(w2, x));
+    }
+  }
+  for (int eb = e - 1; eb >= 0; eb -= 32) {
+    const int ei = eb - lane;
+    const uint32_t m = ei >= 0 ? s.anyw(ei, x) : 0u;
+    const unsigned bal = __ballot_sync(kFull, m != 0u);
+    if (bal) {
+      const int l = __ffs(bal) - 1;
+      const uint32_t mm = __shfl_sync(kFull, m, l);
+      const int w2 = ((eb - l) << 5) + 31 - __clz(mm);
+      return (w2 << 5) + 31 - __clz(s.hits(w2, x));
+    }
+  }
+  return -1;
+}
+
+// nearest position >= from carrying allele x, or M
+__device__ __forceinline__ int next_allele(const GlobalState &s, int from, uint32_t x, int lane) {
+  const int M = s.M;
+  if (from >= M) return M;
+  const int w = from >> 5;
+  {
+    const uint32_t b = s.hits(w, x) & (kFull << (from & 31));
+    if (b) return (w << 5) + __ffs(b) - 1;
+  }
+  const int e = w >> 5, nGroups = (((M + 31) >> 5) + 31) >> 5;
+  {  // later words of the same group
+    const uint32_t m = (w & 31) == 31 ? 0u : s.anyw(e, x) & (kFull << ((w & 31) + 1));
+    if (m) {
+      const int w2 = (e << 5) + __ffs(m) - 1;
+      return (w2 << 5) + __ffs(s.hits(w2, x)) - 1;
+    }
+  }
+  for (int eb = e + 1; eb < nGroups; eb += 32) {
+    const int ei = eb + lane;
+    const uint32_t m = ei < nGroups ? s.anyw(ei, x) : 0u;
+    const unsigned bal = __ballot_sync(kFull, m != 0u);
+    if (bal) {
+      const int l = __ffs(bal) - 1;
+      const uint32_t mm = __shfl_sync(kFull, m, l);
+      const int w2 = ((eb + l) << 5) + __ffs(mm) - 1;
+      return (w2 << 5) + __ffs(s.hits(w2, x)) - 1;
+    }
+  }
+  return M;
+}
+
+// max of d over positions [lo, hi] (1 <= lo <= hi < M): partial words exactly, whole words through their maxima,
+// whole groups of 32 words through the second level
+__device__ __forceinline__ int range_max_d(const GlobalState &s, int lo, int hi, int lane) {
+  const int w0 = lo >> 5, w1 = hi >> 5;
+  int m = 0;
+  {
+    const int idx = (w0 << 5) + lane;
+    if (idx >= lo && idx <= hi) m = s.d(idx);
+  }
+  if (w1 > w0) {
+    const int idx = (w1 << 5) + lane;
+    if (idx <= hi) m = max(m, s.d(idx));
+    int wa = w0 + 1;
+    const int wb = w1 - 1;  // whole words [wa, wb]
+    const int ea = (wa + 31) >> 5, eb = ((wb + 1) >> 5) - 1;  // whole groups [ea, eb]
+    if (ea <= eb) {
+      for (int w = wa + lane; w < (ea << 5); w += 32) m = max(m, s.wmax(w));
+      for (int e = ea + lane; e <= eb; e += 32) m = max(m, s.wmax2(e));
+      wa = (eb + 1) << 5;
+    }
+    for (int w = wa + lane; w <= wb; w += 32) m = max(m, s.wmax(w));
+  }
+  return __reduce_max_sync(kFull, m);
+}
+
 // Extra arguments of the wide-panel kernel (all device pointers).
 struct GlobalArgs {
   int G, chunk;
+  int stageCol;  // gather mode: the site's bit column is staged in shared memory by a TMA bulk copy
   int32_t *aBuf, *dBuf;
   uint32_t *partials;
   GroupSync *gsync;
@@ -155,6 +254,8 @@ struct GlobalArgs {
   uint32_t *ySorted;
   int32_t *wmaxG;
   int32_t *zpre;      // query sweep: zeros before each word of the sorted column
+  uint32_t *any1, *any0;  // query sweep, second level (one entry per 32 words): [2][G*chunk/1024] each
+  int32_t *wmax2;
   // records: one chunked stream per CTA (chunk table row = blockIdx.x), ordered by the segment tables
   int32_t *segCnt;    // [(N+1)*G] records of (column, CTA); row N = the final state
   long long *segSrc;  // [(N+1)*G] offset of the segment in its CTA's stream
@@ -184,6 +285,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
   uint32_t *qwS = reinterpret_cast<uint32_t *>(nmS + (QUERY ? kResMax : 0));         // [QW] query column
   int32_t *qzS = reinterpret_cast<int32_t *>(qwS + QW);                              // [QW] zeros before each word
   int32_t *qaS = qzS + QW;                                                           // [2][QW*32] query PBWT order
+  // gather mode: the site's bit column, fetched by one TMA bulk copy per site (a gather straight from global
+  // memory costs one L1 wavefront per distinct 128-byte line, ~28 per warp instruction)
+  uint32_t *colS = reinterpret_cast<uint32_t *>(qaS + 2 * QW * 32);                  // [wpc] (stageCol)
+  __shared__ __align__(8) uint64_t colBar;
   __shared__ int wexS[32];      // zeros in this CTA's warps below each warp
   __shared__ int wsumZ[32];
   __shared__ uint32_t wsumR[32];
@@ -205,6 +310,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
   uint32_t *ySortedW = SCAN ? ga.ySorted + (size_t)win * 2 * WG : nullptr;
   int32_t *wmaxW = SCAN ? ga.wmaxG + (size_t)win * 2 * WG : nullptr;
   int32_t *zpreW = QUERY ? ga.zpre + (size_t)win * 2 * WG : nullptr;
+  const int WG2 = WG / 32;
+  uint32_t *any1W = QUERY ? ga.any1 + (size_t)win * 2 * WG2 : nullptr, *any0W = QUERY ? ga.any0 + (size_t)win * 2 * WG2 : nullptr;
+  int32_t *wmax2W = QUERY ? ga.wmax2 + (size_t)win * 2 * WG2 : nullptr;
 
   int k0, k1, colShift;
   const uint32_t *src;
@@ -300,6 +408,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     recBase += roundTotal;
   };
 
+  const bool stage = MODE == kGather && ga.stageCol;
+  const uint32_t colBytes = (uint32_t)wpc * 4u;
+  if (stage && tid == 0) {
+    mbar_init(&colBar, 1);
+    mbar_fence_init();
+  }
   // ---- window start state ----
   for (int i = p0 + tid; i < p0 + chunk; i += kThreads) {
     if (i < M) {
@@ -308,10 +422,29 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     }
   }
   group_barrier();
+  if (stage && tid == 0 && k0 < k1) {
+    fence_proxy_async();
+    mbar_expect_tx(&colBar, colBytes);
+    tma_load_1d(colS, src + (size_t)(k0 + colShift) * wpc, colBytes, &colBar);
+  }
+
+  // debugging aid (option window_times): cycles CTA 0 spends in phase A / exchange / scatter+scans / end barrier
+  const bool timing = p.winNanos != nullptr && blockIdx.x == 0 && tid == 0;
+  long long tAcc[4] = {0, 0, 0, 0}, tPrev = 0;
+  auto tick = [&](int slot) {
+    if (timing) {
+      const long long now = clock64();
+      tAcc[slot] += now - tPrev;
+      tPrev = now;
+    }
+  };
+  if (timing) tPrev = clock64();
 
   int cur = 0;
   for (int k = k0; k < k1; ++k) {
-    const uint32_t *col = src + (size_t)(k + colShift) * wpc;
+    const uint32_t *colG = src + (size_t)(k + colShift) * wpc;
+    if (stage) mbar_wait(&colBar, (uint32_t)(k - k0) & 1u);
+    const uint32_t *col = stage ? colS : colG;
     const int32_t *aC = aW + (size_t)cur * MS;
     int32_t *aN = aW + (size_t)(cur ^ 1) * MS;
     const int32_t *dC = WITH_D ? dW + (size_t)cur * (MS + 4) : nullptr;
@@ -325,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     if (posBase == 0 || posBase > M) pb = 2u;  // resolved at the first word: position 0 is a run head
     else if (MODE == kGather) {
       const int hp = __ldcg(aC + posBase - 1);
-      pb = (__ldg(col + (hp >> 5)) >> (hp & 31)) & 1u;
+      pb = ((stage ? col[hp >> 5] : __ldg(col + (hp >> 5))) >> (hp & 31)) & 1u;
     } else pb = __ldg(col + ((posBase - 1) >> 5)) >> 31;
     int zw = 0, carry = 0, lmax = 0;
     bool anyHead = false;
@@ -344,7 +477,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
       for (int u = 0; u < kBatch; ++u) {
         const int base = posBase + (e0 + u) * 32;
         const bool valid = e0 + u < EW && base + lane < M;
-        if (MODE == kGather) cB[u] = valid ? __ldg(col + (hB[u] >> 5)) : kFull;
+        if (MODE == kGather) cB[u] = valid ? (stage ? col[hB[u] >> 5] : __ldg(col + (hB[u] >> 5))) : kFull;
         else cB[u] = (e0 + u < EW && base < M) ? __ldg(col + (base >> 5)) : 0u;
       }
 #pragma unroll
@@ -405,6 +538,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
       if (WITH_D) wsumR[warp] = (anyHead ? 0x80000000u : 0u) | (uint32_t)carry;
     }
     __syncthreads();
+    tick(0);
+    if (stage && tid == 0 && k + 1 < k1) {  // every gather of this site is done: fetch the next site's column
+      fence_proxy_async();
+      mbar_expect_tx(&colBar, colBytes);
+      tma_load_1d(colS, src + (size_t)(k + 1 + colShift) * wpc, colBytes, &colBar);
+    }
 
     // ---------------- exchange: CTA totals out, all partials of the group in ----------------
     int zExLane, zCta;
@@ -481,6 +620,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
       wexS[lane] = zExLane;
     }
     __syncthreads();
+    tick(1);
     const int c = xC;
     const int zIn = xZ + __shfl_sync(kFull, zExLane, warp);
     int cIn = 0;
@@ -492,10 +632,20 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
 
     const int par = (k - k0) & 1;
     if (SCAN) {  // publish this CTA's part of the sorted column, of the word maxima of d (and of the zero prefix)
-      for (int w = tid; w < chunkWords; w += kThreads) {
+      for (int w = tid; w < chunkWords; w += kThreads) {  // chunkWords is a multiple of 32: whole warps, whole groups
         ySortedW[(size_t)par * WG + w0g + w] = ycolS[w];
         wmaxW[(size_t)par * WG + w0g + w] = wmaxS[w];
-        if (QUERY) zpreW[(size_t)par * WG + w0g + w] = xZ + wexS[w / EW] + zlocS[w];
+        if (QUERY) {
+          zpreW[(size_t)par * WG + w0g + w] = xZ + wexS[w / EW] + zlocS[w];
+          const int base = (w0g + w) << 5;
+          const uint32_t vm = (M - base >= 32) ? kFull : (M > base ? ((1u << (M - base)) - 1u) : 0u);
+          const unsigned b1 = __ballot_sync(kFull, (ycolS[w] & vm) != 0u), b0 = __ballot_sync(kFull, (~ycolS[w] & vm) != 0u);
+          const int m2 = __reduce_max_sync(kFull, wmaxS[w]);
+          if (lane == 0) {
+            const size_t e2 = (size_t)par * WG2 + ((w0g + w) >> 5);
+            any1W[e2] = b1; any0W[e2] = b0; wmax2W[e2] = m2;
+          }
+        }
       }
       group_barrier();
     }
@@ -572,7 +722,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     }
     if (QUERY) {
       // ---------------- matchSequencesSweep on state k (pbwtMatch.c:376-426): one warp per query ----------------
-      const GlobalState st{aC, dC, ySortedW + (size_t)par * WG, wmaxW + (size_t)par * WG, M, k + 1};
+      GlobalState st{aC, dC, ySortedW + (size_t)par * WG, wmaxW + (size_t)par * WG, M, k + 1};
+      st.any1 = any1W + (size_t)par * WG2; st.any0 = any0W + (size_t)par * WG2; st.wm2 = wmax2W + (size_t)par * WG2;
       const int32_t *zk = zpreW + (size_t)par * WG;
       const int32_t *qaC = qaS + par * QW * 32;
       int32_t *qaN = qaS + (par ^ 1) * QW * 32;
@@ -592,22 +743,26 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
               f = hi;  // an alternate of the same length that extends (pbwtMatch.c:381-383)
             } else {
               repLo = f; repHi = hi; repStart = e;  // report [f, hi) with start e (pbwtMatch.c:385)
-              int lo = f;
-              int dDown = hi < M ? st.d(hi) : k;
-              int dUp = st.d(lo);
-              for (;;) {  // reseed by divergence tiers, upper side first on ties (pbwtMatch.c:389-411)
-                if (dUp <= dDown) {
-                  const int q = block_start(st, lo, dUp, lane);  // the tier is [q, lo)
-                  const int top = first_allele_in(st, q, lo, x, lane);
-                  if (top >= 0) { f = top; e = dUp; break; }
-                  lo = q;
-                  dUp = st.d(lo);
+              // Reseed (pbwtMatch.c:389-411).  The reference widens [f, hi) tier by tier of divergence, upper side
+              // first on ties, until a tier holds allele x.  The tier that reaches a position p above f has value
+              // max d(p, f], below hi it has max d[hi, p]; so the winner is decided by the nearest carriers u (above)
+              // and v (below): up if max d(u, f] <= max d[hi, v].  Up: the new f is the topmost carrier of that whole
+              // tier; down: v itself.  No carrier at all: the "no match" event.
+              const int u = prev_allele(st, f - 1, x, lane);
+              const int v = next_allele(st, hi, x, lane);
+              if (u < 0 && v >= M) {
+                nm = true;
+                e = k + 1;
+              } else {
+                const int tUp = u >= 0 ? range_max_d(st, u + 1, f, lane) : 0x7fffffff;
+                const int tDown = v < M ? range_max_d(st, hi, v, lane) : 0x7fffffff;
+                if (tUp <= tDown) {
+                  const int q = block_start(st, u, tUp, lane);
+                  f = first_allele_in(st, q, u + 1, x, lane);
+                  e = tUp;
                 } else {
-                  int r2;
-                  if (first_allele_down(st, hi, dDown, x, lane, r2)) { f = r2; e = dDown; break; }
-                  hi = r2;
-                  dDown = hi == M ? k : st.d(hi);
-                  if (lo == 0 && hi == M) { nm = true; e = k + 1; break; }  // allele absent from the column
+                  f = v;
+                  e = tDown;
                 }
               }
             }
@@ -670,9 +825,13 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
         qaN[x ? cq + t - zb : zb] = qaC[t];
       }
     }
+    tick(2);
     group_barrier();
+    tick(3);
     cur ^= 1;
   }
+  if (timing)
+    for (int i = 0; i < 4; ++i) p.winNanos[i] = tAcc[i];
 
   // ---- state k1 ----
   const int32_t *aE = aW + (size_t)cur * MS;
@@ -738,13 +897,29 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
 
 }  // namespace
 
-static size_t smem_bytes(int chunk, bool with_d, bool match, bool query, int Q) {
-  const size_t cw = chunk / 32;
+// dynamic shared memory: per-position arrays (chunk-proportional) + fixed part; colWords = staged bit column
+static size_t smem_fixed_words(bool match, bool query, int Q, int colWords) {
   const bool scan = match || query;
   const size_t QW = query ? (size_t)((Q + 31) / 32 + 31) / 32 * 32 : 0;
-  size_t words = cw + (with_d ? chunk : 0) + (scan ? cw : 0) + (match ? cw : 0) + (query ? cw : 0) +
-                 (scan ? kResMax * 4 + kTabMirror : 0) + (query ? kResMax : 0) + QW * 2 + QW * 32 * 2;
+  return (scan ? kResMax * 4 + kTabMirror : 0) + (query ? kResMax : 0) + QW * 2 + QW * 32 * 2 + (size_t)colWords;
+}
+static size_t smem_bytes(int chunk, bool with_d, bool match, bool query, int Q, int colWords) {
+  const size_t cw = chunk / 32;
+  const bool scan = match || query;
+  const size_t words = cw + (with_d ? chunk : 0) + (scan ? cw : 0) + (match ? cw : 0) + (query ? cw : 0) +
+                       smem_fixed_words(match, query, Q, colWords);
   return words * 4;
+}
+constexpr size_t kSmemBudget = 232448 - 2048;  // 227 KB per CTA minus the static arrays
+// largest chunk (multiple of 1024, <= kMaxChunk) whose arrays fit beside the fixed part; 0 = does not fit
+static int max_chunk(bool with_d, bool match, bool query, int Q, int colWords) {
+  const size_t fixed = smem_fixed_words(match, query, Q, colWords) * 4;
+  if (fixed + 4096 > kSmemBudget) return 0;
+  const bool scan = match || query;
+  const double perPos = (with_d ? 4.0 : 0.0) + 4.0 * (1 + (scan ? 1 : 0) + (match ? 1 : 0) + (query ? 1 : 0)) / 32.0;
+  long long c = (long long)((kSmemBudget - fixed) / perPos);
+  c = c / 1024 * 1024;
+  return (int)std::min<long long>(c, kMaxChunk);
 }
 
 template <bool CLUSTER>
@@ -791,8 +966,17 @@ static int max_active_clusters(void *kern, int G, size_t smemBytes) {
 // window (hardware barriers, exchange through distributed shared memory); wider ones a cooperative grid of
 // W * G <= maxCtas CTAs synchronised through global memory.
 void sweep_global_plan(int M, int maxCtas, int wantWindows, SweepMode mode, bool with_d, bool match, bool query, int Q,
-                       bool allowCluster, int *G, int *chunk, int *W, int *cluster) {
-  const int gmin = (M + kMaxChunk - 1) / kMaxChunk;
+                       bool allowCluster, int *G, int *chunk, int *W, int *cluster, int *stageCol) {
+  // gather mode stages the site's bit column (wpc words) in shared memory when it leaves room for a useful chunk
+  const int wpc = pbwtgpu_words_per_col(M);
+  int colWords = mode == kGather ? wpc + 4 : 0;
+  int chunkMax = max_chunk(with_d, match, query, Q, colWords);
+  if (colWords && (chunkMax < 4096 || (M + chunkMax - 1) / chunkMax > maxCtas)) {
+    colWords = 0;
+    chunkMax = max_chunk(with_d, match, query, Q, 0);
+  }
+  *stageCol = colWords != 0;
+  const int gmin = (M + chunkMax - 1) / chunkMax;
   int w = wantWindows > 0 ? wantWindows : 1;
   *cluster = 0;
   if (allowCluster && gmin <= 16) {
@@ -800,7 +984,8 @@ void sweep_global_plan(int M, int maxCtas, int wantWindows, SweepMode mode, bool
     int g = std::min(gHi, std::max(gLo, pow2_floor(std::max(1, maxCtas / w))));
     for (; g >= gLo; g >>= 1) {
       const int ch = ((M + g - 1) / g + 1023) / 1024 * 1024;
-      const int n = max_active_clusters(pick_kernel<true>(mode, with_d, match, query), g, smem_bytes(ch, with_d, match, query, Q));
+      const int n = max_active_clusters(pick_kernel<true>(mode, with_d, match, query), g,
+                                        smem_bytes(ch, with_d, match, query, Q, colWords));
       if (n >= 1) {
         *G = g; *chunk = ch; *W = std::min(w, n); *cluster = 1;
         return;
@@ -812,7 +997,7 @@ void sweep_global_plan(int M, int maxCtas, int wantWindows, SweepMode mode, bool
   int g = maxCtas / w;  // use every SM: more CTAs per window shorten the per-site critical path
   if (g < gmin) g = gmin;
   int ch = ((M + g - 1) / g + 1023) / 1024 * 1024;
-  if (ch > kMaxChunk) ch = kMaxChunk;
+  if (ch > chunkMax) ch = chunkMax;
   g = (M + ch - 1) / ch;
   *G = g; *chunk = ch; *W = w;
 }
@@ -830,10 +1015,11 @@ static int launch_any(void *kern, bool cluster, const SweepArgs &a, const Global
   if (err != cudaSuccess) return (int)err;
   SweepArgs args = a;
   GlobalArgs ga{};
-  ga.G = b.G; ga.chunk = b.chunk; ga.aBuf = b.aBuf; ga.dBuf = b.dBuf; ga.partials = b.partials;
+  ga.G = b.G; ga.chunk = b.chunk; ga.stageCol = b.stageCol; ga.aBuf = b.aBuf; ga.dBuf = b.dBuf; ga.partials = b.partials;
   ga.gsync = static_cast<GroupSync *>(b.gsync);
   ga.ySorted = b.ySorted; ga.wmaxG = b.wmaxG; ga.zpre = b.zpre; ga.segCnt = b.segCnt; ga.segSrc = b.segSrc;
   ga.qf = b.qf; ga.qe = b.qe; ga.nmKeys = b.nmKeys;
+  ga.any1 = b.any1; ga.any0 = b.any0; ga.wmax2 = b.wmax2;
   void *params[] = {&args, &ga};
   if (!cluster) return (int)cudaLaunchCooperativeKernel(kern, dim3(ctas), dim3(kThreads), params, smemBytes, stream);
   if (b.G > 8) {
@@ -858,7 +1044,8 @@ int launch_sweep_global(const SweepArgs &a, SweepMode mode, bool with_d, bool wi
   if (with_match && !with_d) return (int)cudaErrorInvalidValue;
   if (b.cluster && b.G > 16) return (int)cudaErrorInvalidValue;
   void *kern = b.cluster ? pick_kernel<true>(mode, with_d, with_match, false) : pick_kernel<false>(mode, with_d, with_match, false);
-  return launch_any(kern, b.cluster, a, b, a.nWindows * b.G, smem_bytes(b.chunk, with_d, with_match, false, 0), stream);
+  const int colWords = (mode == kGather && b.stageCol) ? a.wpc + 4 : 0;
+  return launch_any(kern, b.cluster, a, b, a.nWindows * b.G, smem_bytes(b.chunk, with_d, with_match, false, 0, colWords), stream);
 }
 
 int query_sweep_global_max_q() { return kQCap; }
@@ -869,7 +1056,7 @@ int launch_query_sweep_global(const SweepArgs &a, const GlobalBuffers &b, cudaSt
   void *kern = b.cluster ? pick_kernel<true>(kSorted, true, false, true) : pick_kernel<false>(kSorted, true, false, true);
   SweepArgs args = a;
   args.nWindows = 1;
-  return launch_any(kern, b.cluster, args, b, b.G, smem_bytes(b.chunk, true, false, true, a.Q), stream);
+  return launch_any(kern, b.cluster, args, b, b.G, smem_bytes(b.chunk, true, false, true, a.Q, 0), stream);
 }
 
 size_t sweep_global_sync_bytes(int W) { return sizeof(GroupSync) * (size_t)W; }

@@ -16,6 +16,7 @@
 // (log2 W rounds, all windows in parallel) yields the exact state at every boundary.
 #include "windows.cuh"
 
+#include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -123,31 +124,24 @@ __global__ void __launch_bounds__(256) gather_records_kernel(const int4 *pool, c
 
 
 // Records of a wide-panel sweep: one segment per (column, CTA of the window's group), in callback order
-// (column-major, CTAs in position order).  One warp copies 32 segments, one after the other.
+// (column-major, CTAs in position order).  One thread per output record: binary search of its segment in the
+// exclusive scan of the segment counts (segments differ in size by orders of magnitude and most are empty).
 __global__ void __launch_bounds__(256) gather_segments_kernel(const int4 *pool, const int *chunkTab, int poolChunks,
-                                                              const int32_t *segCnt, const long long *segSrc,
-                                                              const long long *segDst, long long nSeg, int G, int spw,
-                                                              int N, int W, int4 *out) {
-  const int lane = threadIdx.x & 31;
-  const long long first = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
-  if (first >= nSeg) return;
-  const long long mine = first + lane;
-  const int cnt = mine < nSeg ? segCnt[mine] : 0;
-  unsigned live = __ballot_sync(kFull, cnt > 0);
-  while (live) {
-    const int l = __ffs(live) - 1;
-    live &= live - 1;
-    const long long seg = first + l;
-    const int n = __shfl_sync(kFull, cnt, l);
+                                                              const long long *segSrc, const long long *segDst,
+                                                              long long nSeg, long long total, int G, int spw, int N, int W,
+                                                              int4 *out) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (long long)gridDim.x * blockDim.x) {
+    long long lo = 0, hi = nSeg - 1;  // last segment with segDst[seg] <= r (segDst[nSeg] = total > r)
+    while (lo < hi) {
+      const long long mid = (lo + hi + 1) >> 1;
+      if (__ldg(segDst + mid) <= r) lo = mid; else hi = mid - 1;
+    }
+    const long long seg = lo;
     const int col = (int)(seg / G), g = (int)(seg % G);
     const int win = col >= N ? W - 1 : col / spw;
-    const int *tab = chunkTab + (size_t)(win * G + g) * poolChunks;
-    const long long so = segSrc[seg], dof = segDst[seg];
-    for (int t = lane; t < n; t += 32) {
-      const long long o = so + t;
-      const int id = tab[o >> kRecChunkLog];
-      if (id >= 0) out[dof + t] = pool[((long long)id << kRecChunkLog) + (o & (kRecChunk - 1))];
-    }
+    const long long o = __ldg(segSrc + seg) + (r - __ldg(segDst + seg));
+    const int id = __ldg(chunkTab + (size_t)(win * G + g) * poolChunks + (o >> kRecChunkLog));
+    if (id >= 0) out[r] = pool[((long long)id << kRecChunkLog) + (o & (kRecChunk - 1))];
   }
 }
 
@@ -218,14 +212,14 @@ int launch_segment_scan(const int32_t *segCnt, long long nSeg, long long *segDst
   return (int)cub::DeviceScan::ExclusiveSum(temp, tempBytes, it, segDst, (int)nSeg, stream);
 }
 
-int launch_gather_segments(const pbwtgpu_match *pool, const int *chunkTab, int poolChunks, const int32_t *segCnt,
-                           const long long *segSrc, const long long *segDst, long long nSeg, int G, int spw, int N, int W,
+int launch_gather_segments(const pbwtgpu_match *pool, const int *chunkTab, int poolChunks, const long long *segSrc,
+                           const long long *segDst, long long nSeg, long long total, int G, int spw, int N, int W,
                            pbwtgpu_match *out, cudaStream_t stream) {
-  if (nSeg > 0) {
-    const long long warps = (nSeg + 31) / 32;
-    gather_segments_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const int4 *>(pool), chunkTab,
-                                                                           poolChunks, segCnt, segSrc, segDst, nSeg, G, spw,
-                                                                           N, W, reinterpret_cast<int4 *>(out));
+  if (nSeg > 0 && total > 0) {
+    const long long blocks = std::min<long long>((total + 255) / 256, 148LL * 64);
+    gather_segments_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const int4 *>(pool), chunkTab, poolChunks,
+                                                                 segSrc, segDst, nSeg, total, G, spw, N, W,
+                                                                 reinterpret_cast<int4 *>(out));
   }
   return (int)cudaGetLastError();
 }

@@ -28,8 +28,9 @@ int launch_gather_records(const pbwtgpu_match *pool, const int *chunkTab, int po
 size_t segment_scan_temp_bytes(long long nSeg);
 int launch_segment_scan(const int32_t *segCnt, long long nSeg, long long *segDst, void *temp, size_t tempBytes,
                         cudaStream_t stream);
-int launch_gather_segments(const pbwtgpu_match *pool, const int *chunkTab, int poolChunks, const int32_t *segCnt,
-                           const long long *segSrc, const long long *segDst, long long nSeg, int G, int spw, int N, int W,
+// segDst: exclusive scan with nSeg + 1 entries (segDst[nSeg] = total)
+int launch_gather_segments(const pbwtgpu_match *pool, const int *chunkTab, int poolChunks, const long long *segSrc,
+                           const long long *segDst, long long nSeg, long long total, int G, int spw, int N, int W,
                            pbwtgpu_match *out, cudaStream_t stream);
 // "no match" events of a wide query sweep arrive in arbitrary order: sort them by key (site, query-PBWT position)
 int sort_nomatch(const unsigned long long *keys, const pbwtgpu_nomatch *events, long long n, pbwtgpu_nomatch *out,
