@@ -57,6 +57,10 @@ int ORC(trace)(const uint32_t *xbits, int wpc, int M, int N, const int32_t *aSta
 int ORC(max_within)(const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *aStart,
                     oracle_match *rec, int64_t cap, int64_t *nrec);
 
+/* pbwtLongMatches(p, T) with T > 0 = matchLongWithin2 over a stored pack3 stream. pbwtMatch.c:85-113. */
+int ORC(long_within)(const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *aStart, int T,
+                     oracle_match *rec, int64_t cap, int64_t *nrec);
+
 /* N x pbwtCursorForwardsReadAD from a fresh cursor: final a int[M], d int[M+1].
  * pbwtCore.c:543-557. */
 int ORC(sweep_ad)(const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *aStart,

@@ -109,6 +109,35 @@ int ref_max_within(const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *
   return 0;
 }
 
+/* matchLongWithin2 is static in the reference and only reachable through pbwtLongMatches (pbwtMatch.c:148-183),
+ * whose printer writes MATCH lines to stdout (pbwtMatch.c:46-49): capture stdout and parse the lines back. */
+int ref_long_within(const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *aStart, int T,
+                    oracle_match *rec, int64_t cap, int64_t *nrec) {
+  ensure_init();
+  PBWT *p = pbwt_from_yz(yz, nyz, M, N, aStart);
+  char *buf = 0; size_t len = 0;
+  fflush(stdout);
+  FILE *saved = stdout;
+  stdout = open_memstream(&buf, &len); /* glibc: stdout is an assignable FILE* */
+  pbwtLongMatches(p, T);
+  fclose(stdout);
+  stdout = saved;
+  int64_t n = 0;
+  for (char *line = buf; line && *line; ) {
+    int ai, bi, st, en, ln;
+    if (sscanf(line, "MATCH\t%d\t%d\t%d\t%d\t%d", &ai, &bi, &st, &en, &ln) == 5) {
+      if (n < cap && rec) { rec[n].ai = ai; rec[n].bi = bi; rec[n].start = st; rec[n].end = en; }
+      ++n;
+    }
+    line = strchr(line, '\n');
+    if (line) ++line;
+  }
+  *nrec = n;
+  free(buf);
+  pbwtDestroy(p);
+  return 0;
+}
+
 int ref_sweep_ad(const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *aStart,
                  int32_t *aEnd, int32_t *dEnd) {
   ensure_init();

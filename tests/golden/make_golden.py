@@ -158,6 +158,27 @@ def query_fixture():
     print("query_sweep records", len(rec4), "nomatch", len(nom3), hashlib.md5(out).hexdigest(), log[-1])
 
 
+def long_within_fixture():
+    """pbwt -read X.pbwt -longWithin L (matchLongWithin2, pbwtMatch.c:85-113) through the reference CLI, on the
+    panels of the other fixtures: records (all have length >= L > 0, so the printer drops none)."""
+    out = {}
+    for name, Ls in [("merge1", (1, 2, 4)), ("merge2", (1, 3)), ("omni", (20, 30)), ("mosaic300x400", (40, 100))]:
+        g = np.load(os.path.join(HERE, name + ".npz"))
+        M, N = int(g["M"]), int(g["N"])
+        with tempfile.TemporaryDirectory() as td:
+            pb = os.path.join(td, "x.pbwt")
+            write_pbwt(pb, M, N, np.arange(M), g["a_end"], g["yz"])
+            for L in Ls:
+                txt = subprocess.run([CLI, "-read", pb, "-longWithin", str(L)], check=True, capture_output=True).stdout
+                rec = stdout_records(txt)
+                lib, n = O.reference().long_within(g["yz"], M, N, L)
+                assert n == len(rec) and (np.stack([lib["ai"], lib["bi"], lib["start"], lib["end"]], 1) == rec).all()
+                out[f"{name}_L{L}"] = rec
+                out[f"{name}_L{L}_md5"] = hashlib.md5(txt).hexdigest()
+                print("longWithin", name, "L", L, "records", len(rec), out[f"{name}_L{L}_md5"])
+    np.savez_compressed(os.path.join(HERE, "long_within.npz"), **out)
+
+
 def main():
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref", "port"], check=True, capture_output=True)
     panel_fixture("merge1", read_vcfq(os.path.join(REF, "test", "merge.1.tab")), with_trace=True)
@@ -167,6 +188,7 @@ def main():
     panel_fixture("mosaic300x400", O.unpack_panel(x, 300), with_trace=False)
     pack3_fixture()
     query_fixture()
+    long_within_fixture()
 
 
 if __name__ == "__main__":

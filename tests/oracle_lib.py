@@ -99,6 +99,18 @@ class Oracle:
                               rec.ctypes.data_as(C.c_void_p), C.c_int64(cap), C.byref(n))
         return rec[: min(cap, n.value)], n.value
 
+    def long_within(self, yz, M, N, T, a_start=None):
+        """pbwtLongMatches(p, T), T > 0 (matchLongWithin2, pbwtMatch.c:85-113)."""
+        yz = np.ascontiguousarray(yz, np.uint8)
+        a0 = None if a_start is None else np.ascontiguousarray(a_start, np.int32)
+        n = C.c_int64(0)
+        self._f("long_within")(_p(yz, c_u8p), C.c_int64(yz.size), M, N, _p(a0, c_i32p), T, None, C.c_int64(0), C.byref(n))
+        cap = n.value
+        rec = np.zeros(max(cap, 1), MATCH_DTYPE)
+        self._f("long_within")(_p(yz, c_u8p), C.c_int64(yz.size), M, N, _p(a0, c_i32p), T,
+                               rec.ctypes.data_as(C.c_void_p), C.c_int64(cap), C.byref(n))
+        return rec[:cap], n.value
+
     def sweep_ad(self, yz, M, N, a_start=None):
         yz = np.ascontiguousarray(yz, np.uint8)
         a0 = None if a_start is None else np.ascontiguousarray(a_start, np.int32)

@@ -52,6 +52,38 @@ def test_panel_goldens(name):
             assert (y_tr == g["y_trace"]).all() and (c_tr == g["c_trace"]).all(), label
 
 
+def test_long_within_goldens():
+    """-longWithin L (matchLongWithin2, pbwtMatch.c:85-113): records printed by the reference CLI."""
+    g = load("long_within")
+    for key in [k for k in g.files if not k.endswith("_md5")]:
+        name, L = key.rsplit("_L", 1)
+        p = load(name)
+        M, N = int(p["M"]), int(p["N"])
+        for label, imp in impls():
+            rec, n = imp.long_within(p["yz"], M, N, int(L))
+            assert n == len(g[key]) and (rec4(rec) == g[key]).all(), (label, key)
+
+
+def test_long_within_port_equals_reference_random():
+    ref = O.reference()
+    if ref is None:
+        pytest.skip("compiled reference not present")
+    port = O.port()
+    rng = np.random.default_rng(5)
+    for it in range(40):
+        M, N = int(rng.integers(2, 200)), int(rng.integers(0, 60))
+        hap = (rng.random((M, N)) < rng.choice([0.02, 0.2, 0.5])).astype(np.uint8)
+        if M > 8:
+            hap[: M // 3] = hap[0]
+        a0 = rng.permutation(M).astype(np.int32) if it % 2 else None
+        x = O.pack_panel(hap) if N else np.zeros((0, O.words_per_col(M)), np.uint32)
+        yz = port.build(x, M, N, a0, with_d=False)[0]
+        for T in (1, 3, 10):
+            r1, n1 = port.long_within(yz, M, N, T, a0)
+            r2, n2 = ref.long_within(yz, M, N, T, a0)
+            assert n1 == n2 and (r1 == r2).all(), (M, N, T)
+
+
 def test_merge1_known_answers():
     """the 34-byte stream, aFend and the first/last MATCH lines."""
     g = load("merge1")
