@@ -44,7 +44,9 @@ enum {
 enum {
   PBWTGPU_WANT_YZ = 1u,        /* pack3 stream of the sorted columns  (pbwtCore.c:240-277) */
   PBWTGPU_WANT_D = 2u,         /* carry the divergence array           (pbwtCore.c:485-508) */
-  PBWTGPU_WANT_MAXWITHIN = 4u  /* set-maximal matches, implies WANT_D  (pbwtMatch.c:115-142) */
+  PBWTGPU_WANT_MAXWITHIN = 4u, /* set-maximal matches, implies WANT_D  (pbwtMatch.c:115-142) */
+  PBWTGPU_WANT_LONGWITHIN = 8u /* all matches of >= L sites (-longWithin L, matchLongWithin2, pbwtMatch.c:85-113),
+                                  implies WANT_D; L is the option "long_within"; exclusive with WANT_MAXWITHIN */
 };
 
 int pbwtgpu_words_per_col(int M);
@@ -133,6 +135,12 @@ int pbwtgpu_build(pbwtgpu_ctx *ctx, const uint32_t *xbits, int M, int N, const i
 /* matchMaximalWithin(p, report) over a stored stream (pbwtMatch.c:115-142). */
 int pbwtgpu_max_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start,
                        int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches, int64_t *nmatch);
+/* pbwtLongMatches(p, L) with L > 0 = matchLongWithin2 (pbwtMatch.c:85-113, 148-183) over a stored stream: every
+ * pair of haplotypes whose match ending at a site is at least L sites long and cannot be extended.  Records in the
+ * reference's callback order, including its quirks (the last block of a site is never reported; at k == N the
+ * alleles of site N-1 are consulted). */
+int pbwtgpu_long_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start, int L,
+                        int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches, int64_t *nmatch);
 /* matchSequencesSweep(p, q, report) (pbwtMatch.c:363-443): panel and query streams as stored. */
 int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int M, int N, const int32_t *pa_start,
                         const uint8_t *qyz, int64_t nqyz, int Q, const int32_t *qa_start, pbwtgpu_match **matches,

@@ -7,6 +7,7 @@ the constructors raise.
 Host-side mirror of the reference interface for this path (names as in pbwt.h):
   * ``Engine.build``          <- readers' loop + pbwtCursorWriteForwards  (pbwtIO.c:572-574)
   * ``Engine.max_within``     <- matchMaximalWithin(p, report)            (pbwtMatch.c:115-142)
+  * ``Engine.long_within``    <- pbwtLongMatches(p, L), L > 0             (pbwtMatch.c:85-113,148-183)
   * ``Engine.match_sweep``    <- matchSequencesSweep(p, q, report)        (pbwtMatch.c:363-443)
   * ``Engine.pack3/unpack3``  <- pack3 / unpack3                          (pbwtCore.c:254-305)
 """
@@ -20,7 +21,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpbwtgpu.so")
 
-WANT_YZ, WANT_D, WANT_MAXWITHIN = 1, 2, 4
+WANT_YZ, WANT_D, WANT_MAXWITHIN, WANT_LONGWITHIN = 1, 2, 4, 8
 KERNEL_CLASSES = ("sweep", "pack3", "unpack3", "query", "synth", "aux", "prepass", "combine")
 
 MATCH_DTYPE = np.dtype([("ai", "<i4"), ("bi", "<i4"), ("start", "<i4"), ("end", "<i4")])
@@ -79,6 +80,7 @@ def load_library() -> C.CDLL:
         lib.pbwtgpu_build.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_uint, C.POINTER(_vp), C.POINTER(_i64), _vp, _vp,
                                       C.POINTER(_vp), C.POINTER(_i64)]
         lib.pbwtgpu_max_within.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_i64)]
+        lib.pbwtgpu_long_within.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, C.POINTER(_vp), C.POINTER(_i64)]
         lib.pbwtgpu_match_sweep.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _i64, C.c_int, _vp, C.POINTER(_vp),
                                             C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_i64)]
         lib.pbwtgpu_pack3.argtypes = [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_i64)]
@@ -130,7 +132,7 @@ class Result:
     def fetch(self, yz=True, a_end=True, d_end=True, matches=True, out=None):
         """D2H. ``out`` may hold preallocated (e.g. pinned) numpy buffers keyed yz/a_end/d_end/matches."""
         out = out or {}
-        has_d = bool(self.flags & (WANT_D | WANT_MAXWITHIN))
+        has_d = bool(self.flags & (WANT_D | WANT_MAXWITHIN | WANT_LONGWITHIN))
         def buf(key, want, make):
             if not want:
                 return None
@@ -140,7 +142,7 @@ class Result:
             "yz": buf("yz", yz and (self.flags & WANT_YZ), lambda: np.zeros(max(self.nyz, 1), np.uint8)),
             "a_end": buf("a_end", a_end, lambda: np.zeros(self.M, np.int32)),
             "d_end": buf("d_end", d_end and has_d, lambda: np.zeros(self.M + 1, np.int32)),
-            "matches": buf("matches", matches and (self.flags & WANT_MAXWITHIN), lambda: np.zeros(max(self.nmatch, 1), MATCH_DTYPE)),
+            "matches": buf("matches", matches and (self.flags & (WANT_MAXWITHIN | WANT_LONGWITHIN)), lambda: np.zeros(max(self.nmatch, 1), MATCH_DTYPE)),
         }
         self.eng._check(self.eng.lib.pbwtgpu_result_fetch(self.eng.ctx, self.handle, _ptr(bufs["yz"]), _ptr(bufs["a_end"]),
                                                           _ptr(bufs["d_end"]), _ptr(bufs["matches"])))
@@ -267,11 +269,16 @@ class Engine:
         return Result(self, h, M, N, flags | WANT_D)
 
     # ---- one-shot host API (the drop-in boundary) ----------------------------------------
-    def build(self, xbits: np.ndarray, M: int, N: int, a_start=None, with_d=True, with_matches=False, with_yz=True):
-        """-> dict(yz, a_end, d_end, matches) exactly as the reference would leave them."""
+    def build(self, xbits: np.ndarray, M: int, N: int, a_start=None, with_d=True, with_matches=False, with_yz=True, long_L=0):
+        """-> dict(yz, a_end, d_end, matches) exactly as the reference would leave them.
+        long_L > 0: matches are those of -longWithin long_L instead of -maxWithin."""
         xbits = np.ascontiguousarray(xbits, np.uint32)
         a0 = None if a_start is None else np.ascontiguousarray(a_start, np.int32)
-        flags = (WANT_YZ if with_yz else 0) | (WANT_D if with_d else 0) | (WANT_MAXWITHIN if with_matches else 0)
+        flags = (WANT_YZ if with_yz else 0) | (WANT_D if with_d else 0) | (WANT_MAXWITHIN if with_matches and not long_L else 0)
+        if long_L:
+            flags |= WANT_LONGWITHIN
+            with_matches = True
+            self.set_option("long_within", long_L)
         yz, nyz, mt, nm = _vp(), _i64(0), _vp(), _i64(0)
         a_end = np.zeros(M, np.int32)
         d_end = np.zeros(M + 1, np.int32) if (with_d or with_matches) else None
@@ -293,6 +300,15 @@ class Engine:
                                                 C.byref(mt) if with_matches else None, C.byref(nm)))
         return {"a_end": a_end, "d_end": d_end,
                 "matches": _take(self.lib, mt, nm.value * 16, MATCH_DTYPE) if with_matches else None}
+
+    def long_within(self, yz: np.ndarray, M: int, N: int, L: int, a_start=None):
+        yz = np.ascontiguousarray(yz, np.uint8)
+        a0 = None if a_start is None else np.ascontiguousarray(a_start, np.int32)
+        mt, nm = _vp(), _i64(0)
+        a_end, d_end = np.zeros(M, np.int32), np.zeros(M + 1, np.int32)
+        self._check(self.lib.pbwtgpu_long_within(self.ctx, _ptr(yz), yz.size, M, N, _ptr(a0), L, _ptr(a_end), _ptr(d_end),
+                                                 C.byref(mt), C.byref(nm)))
+        return {"a_end": a_end, "d_end": d_end, "matches": _take(self.lib, mt, nm.value * 16, MATCH_DTYPE)}
 
     def match_sweep(self, pyz, M, N, qyz, Q, pa_start=None, qa_start=None):
         pyz = np.ascontiguousarray(pyz, np.uint8)

@@ -257,4 +257,131 @@ __device__ __forceinline__ void match_rounds(const S &s, int k, bool live, int M
   }
 }
 
+// ---- matchLongWithin2's per-site scan (-longWithin L, pbwtMatch.c:85-113) ----
+// State k is cut into blocks at every position with d > thr = k - L.  A block that holds both alleles and does not
+// run to M is reported: all pairs ia < ib with different alleles, start = max d(ia, ib], in (ia, ib) order.
+// A block holds both alleles iff it contains an "interior head": a position h with y[h] != y[h-1] and d[h] <= thr.
+// Interior heads are the candidates; the first one of each block owns the block, one warp emits it.
+
+// interior heads of one word.  cw: the word's alleles, pb: allele before the word.
+template <class S>
+__device__ __forceinline__ uint32_t long_candidate_mask(const S &s, uint32_t cw, uint32_t pb, int base, uint32_t vm, int thr,
+                                                        int lane) {
+  const uint32_t H = (cw ^ ((cw << 1) | pb)) & vm;
+  bool mine = false;
+  if ((H >> lane) & 1u) mine = s.d(base + lane) <= thr;
+  return __ballot_sync(kFull, mine);
+}
+
+// zero alleles among positions [lo, hi)
+template <class S>
+__device__ __forceinline__ int count_zeros(const S &s, int lo, int hi, int lane) {
+  if (lo >= hi) return 0;
+  const int w0 = lo >> 5, w1 = (hi - 1) >> 5;
+  int n = 0;
+  for (int w = w0 + lane; w <= w1; w += 32) {
+    uint32_t bits = ~s.yw(w);
+    if (w == w0) bits &= kFull << (lo & 31);
+    if (w == w1 && (hi & 31)) bits &= (1u << (hi & 31)) - 1u;
+    n += __popc(bits);
+  }
+  return __reduce_add_sync(kFull, n);
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int dl = 16; dl > 0; dl >>= 1) v += __shfl_xor_sync(kFull, v, dl);
+  return v;
+}
+
+// all records of block [q, r), by one warp: rows ia ascending, 32 positions ib per step with a running max of d
+template <class S>
+__device__ __forceinline__ void emit_long_block(const RecSink &out, long long o, const S &s, int q, int r, int k, int lane) {
+  const uint32_t ltMask = lanemask_lt(lane);
+  for (int ia = q; ia + 1 < r; ++ia) {
+    const uint32_t yia = ybit(s, ia);
+    const int aia = s.a(ia);
+    int running = 0;
+    for (int base = ia + 1; base < r; base += 32) {
+      const int ib = base + lane;
+      const bool valid = ib < r;
+      int v = valid ? s.d(ib) : 0;
+#pragma unroll
+      for (int dl = 1; dl < 32; dl <<= 1) {
+        const int t = __shfl_up_sync(kFull, v, dl);
+        if (lane >= dl) v = max(v, t);
+      }
+      v = max(v, running);
+      const bool diff = valid && ybit(s, ib) != yia;
+      const unsigned bal = __ballot_sync(kFull, diff);
+      if (diff) out.put(o + __popc(bal & ltMask), make_int4(aia, s.a(ib), v, k));
+      o += __popc(bal);
+      running = __shfl_sync(kFull, v, 31);
+    }
+  }
+}
+
+// Same calling convention as match_rounds; cmaskS[] holds the interior heads.
+template <class S, class Ensure>
+__device__ __forceinline__ void long_rounds(const S &s, int k, int thr, int M, int E, const int32_t *wsumC,
+                                            const uint32_t *cmaskS, int4 *resS, RecSink &sink, long long &recBase,
+                                            Ensure &&ensure, int tid, int lane, int warp, int posOffset = 0) {
+  const int myCnt = wsumC[lane];
+  const int T = __reduce_add_sync(kFull, myCnt);
+  if (T == 0) {
+    __syncthreads();
+    return;
+  }
+  int candBase = 0;
+  if (warp < T) {
+    int x = myCnt;
+#pragma unroll
+    for (int dl = 1; dl < 32; dl <<= 1) {
+      const int t = __shfl_up_sync(kFull, x, dl);
+      if (lane >= dl) x += t;
+    }
+    candBase = x - myCnt;
+  }
+  for (int g0 = 0; g0 < T; g0 += kResMax) {
+    const int nR = min(kResMax, T - g0);
+    for (int g = g0 + warp; g < g0 + nR; g += 32) {
+      const int h = posOffset + locate_candidate(cmaskS, E, candBase, g, lane);
+      const uint32_t yh = ybit(s, h);
+      const int q = block_start(s, h, thr, lane);  // d[h] <= thr, so q < h
+      long long cnt = 0;
+      int r = 0;
+      if (!any_same_allele(s, q, h, yh, lane)) {  // the block's first interior head owns it
+        r = block_end(s, h + 1, thr, M, lane);
+        if (r < M) {  // the reference never reports the block that runs to M (pbwtMatch.c:93-104)
+          const long long z = count_zeros(s, q, r, lane);
+          cnt = z * (long long)(r - q - z);
+        }
+      }
+      if (lane == 0) resS[g - g0] = make_int4(q, r, (int)(cnt & 0xffffffffll), (int)(cnt >> 32));
+    }
+    __syncthreads();
+    long long roundTotal = 0;
+    for (int c0 = 0; c0 < nR; c0 += 32) {
+      const int4 en0 = c0 + lane < nR ? resS[c0 + lane] : make_int4(0, 0, 0, 0);
+      const long long cntL = ((long long)en0.w << 32) | (unsigned)en0.z;
+      const long long tot = warp_sum_ll(cntL);
+      if (sink.pool && tot) {
+        const long long base = recBase + roundTotal;
+        ensure(base + tot);
+        const long long mex = warp_sum_ll(lane < warp ? cntL : 0);
+        const long long mcnt = __shfl_sync(kFull, cntL, warp);
+        if (mcnt > 0) {
+          const int4 en = resS[c0 + warp];
+          emit_long_block(sink, base + mex, s, en.x, en.y, k, lane);
+        }
+      }
+      roundTotal += tot;
+    }
+    recBase += roundTotal;
+    // unlike matchMaximalWithin's emission, this one reads the alleles: no warp may start the next site (and
+    // overwrite the sorted column in shared memory) or the next round before every warp is done here
+    __syncthreads();
+  }
+}
+
 }  // namespace pbwtgpu

@@ -25,6 +25,7 @@ struct pbwtgpu_ctx {
   long long optWindowTimes = 0;  // debugging: print per-window CTA times of pass 2 to stderr
   long long optNoCandidates = 0;  // profiling aid
   long long optForceGlobal = 0;  // testing: use the global-memory kernel even for narrow panels
+  long long optLongT = 0;        // L of PBWTGPU_WANT_LONGWITHIN
   long long optNoCluster = 0;    // testing: wide panels through the cooperative-grid path even where clusters fit
   // profiling
   bool profile = false;
@@ -213,7 +214,7 @@ struct WindowedSweep {
   size_t oA() const { return (size_t)M; }
   size_t oD() const { return (size_t)M + 1; }
 
-  int launch(const SweepArgs &args, SweepMode md, bool withD, bool withMatch) {
+  int launch(const SweepArgs &args, SweepMode md, bool withD, int withMatch) {
     if (!useGlobal) return launch_sweep_smem(args, md, withD, withMatch, ctx->stream);
     const int wl = std::max(W, 1);
     cudaError_t e = cudaMemsetAsync(gb.partials, 0, sizeof(uint32_t) * (size_t)wl * G * 4, ctx->stream);
@@ -426,8 +427,12 @@ struct WindowedSweep {
 
   // pass 2 (or the only pass): all windows from their exact start states; outputs into res
   int finish(unsigned flags, pbwtgpu_result *res) {
-    const bool wantMatch = flags & PBWTGPU_WANT_MAXWITHIN;
-    const bool wantD = wantMatch || (flags & PBWTGPU_WANT_D);
+    // -longWithin on an empty panel reports nothing (the cursor's alleles are all zero, pbwtCore.c:406)
+    const int matchMode = (flags & PBWTGPU_WANT_LONGWITHIN) ? (N > 0 ? 2 : 0) : (flags & PBWTGPU_WANT_MAXWITHIN) ? 1 : 0;
+    const bool wantMatch = matchMode != 0;
+    const bool wantD = wantMatch || (flags & (PBWTGPU_WANT_MAXWITHIN | PBWTGPU_WANT_LONGWITHIN)) || (flags & PBWTGPU_WANT_D);
+    if (matchMode == 2 && ctx->optLongT < 1) return fail(ctx, PBWTGPU_ERR_ARG, "long_within: set option long_within to L >= 1 first");
+    if (wantMatch && useGlobal && !gb.segCnt) return fail(ctx, PBWTGPU_ERR_ARG, "sweep was prepared without match flags");
     const bool wantYz = (flags & PBWTGPU_WANT_YZ) && mode == kGather;
     res->M = M;
     res->N = N;
@@ -462,6 +467,7 @@ struct WindowedSweep {
     a.yOut = yOut;
     a.recCount = recCount; a.chunkCounter = chunkCounter;
     a.reportAtN = 1;
+    a.longT = (int)ctx->optLongT;
     a.debugNoCandidates = (int)ctx->optNoCandidates;
     std::vector<unsigned long long> counts(W, 0);
     long long *winNanos = nullptr;
@@ -494,7 +500,7 @@ struct WindowedSweep {
       }
       {
         ScopedTimer t(ctx, PBWTGPU_K_SWEEP);
-        CUDA_TRY(ctx, launch(a, mode, wantD, wantMatch));
+        CUDA_TRY(ctx, launch(a, mode, wantD, matchMode));
         ctx->launches[PBWTGPU_K_SWEEP] += 1;
       }
       if (!wantMatch) break;
@@ -586,7 +592,7 @@ struct WindowedSweep {
 int run_sweep(pbwtgpu_ctx *ctx, const uint32_t *src, int wpc, int M, int N, SweepMode mode, const int32_t *aStartHost,
               unsigned flags, pbwtgpu_result *res) {
   WindowedSweep ws(ctx);
-  if (int rc = ws.init(src, wpc, M, N, mode, aStartHost, flags & PBWTGPU_WANT_MAXWITHIN, false, 0, 0)) return rc;
+  if (int rc = ws.init(src, wpc, M, N, mode, aStartHost, (flags & (PBWTGPU_WANT_MAXWITHIN | PBWTGPU_WANT_LONGWITHIN)) != 0, false, 0, 0)) return rc;
   if (int rc = ws.prepare()) return rc;
   return ws.finish(flags, res);
 }
@@ -690,6 +696,7 @@ int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value) {
   else if (!strcmp(name, "window_times")) ctx->optWindowTimes = value;
   else if (!strcmp(name, "force_global")) ctx->optForceGlobal = value;
   else if (!strcmp(name, "no_cluster")) ctx->optNoCluster = value;
+  else if (!strcmp(name, "long_within")) ctx->optLongT = value;
   else if (!strcmp(name, "debug_no_candidates")) ctx->optNoCandidates = value;
   else return fail(ctx, PBWTGPU_ERR_ARG, "unknown option %s", name);
   return 0;
@@ -853,7 +860,7 @@ int pbwtgpu_shard_prepare(pbwtgpu_ctx *ctx, const pbwtgpu_panel *panel, const in
     return fail(ctx, PBWTGPU_ERR_ARG, "shard_prepare: bad args");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   pbwtgpu_shard *sh = new pbwtgpu_shard(ctx);
-  int rc = sh->ws.init(panel->bits, panel->wpc, panel->M, panel->N, kGather, a_start, flags & PBWTGPU_WANT_MAXWITHIN, true,
+  int rc = sh->ws.init(panel->bits, panel->wpc, panel->M, panel->N, kGather, a_start, (flags & (PBWTGPU_WANT_MAXWITHIN | PBWTGPU_WANT_LONGWITHIN)) != 0, true,
                        site_offset, total_sites);
   if (!rc) rc = sh->ws.prepare();
   if (rc) { delete sh; return rc; }
@@ -914,7 +921,7 @@ int pbwtgpu_build(pbwtgpu_ctx *ctx, const uint32_t *xbits, int M, int N, const i
   pbwtgpu_result *res = nullptr;
   int rc = pbwtgpu_build_device(ctx, panel, a_start, flags, &res);
   if (!rc) rc = fetch_to_malloc(ctx, res, (flags & PBWTGPU_WANT_YZ) ? yz : nullptr, nyz, a_end, d_end,
-                                (flags & PBWTGPU_WANT_MAXWITHIN) ? matches : nullptr, nmatch);
+                                (flags & (PBWTGPU_WANT_MAXWITHIN | PBWTGPU_WANT_LONGWITHIN)) ? matches : nullptr, nmatch);
   pbwtgpu_result_free(ctx, res);
   pbwtgpu_panel_free(ctx, panel);
   return rc;
@@ -924,6 +931,19 @@ int pbwtgpu_max_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, 
                        int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches, int64_t *nmatch) {
   pbwtgpu_result *res = nullptr;
   int rc = pbwtgpu_sweep_yz_device(ctx, yz, nyz, M, N, a_start, matches ? PBWTGPU_WANT_MAXWITHIN : PBWTGPU_WANT_D, &res);
+  if (!rc) rc = fetch_to_malloc(ctx, res, nullptr, nullptr, a_end, d_end, matches, nmatch);
+  pbwtgpu_result_free(ctx, res);
+  return rc;
+}
+
+int pbwtgpu_long_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start, int L,
+                        int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches, int64_t *nmatch) {
+  if (!ctx || L < 1 || !matches) return fail(ctx, PBWTGPU_ERR_ARG, "long_within: bad args (L must be >= 1)");
+  const long long saved = ctx->optLongT;
+  ctx->optLongT = L;
+  pbwtgpu_result *res = nullptr;
+  int rc = pbwtgpu_sweep_yz_device(ctx, yz, nyz, M, N, a_start, PBWTGPU_WANT_LONGWITHIN, &res);
+  ctx->optLongT = saved;
   if (!rc) rc = fetch_to_malloc(ctx, res, nullptr, nullptr, a_end, d_end, matches, nmatch);
   pbwtgpu_result_free(ctx, res);
   return rc;

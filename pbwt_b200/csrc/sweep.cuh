@@ -44,6 +44,7 @@ struct SweepArgs {
   int *chunkTab;
   unsigned long long *recCount;  // [W] records produced by each window
   int reportAtN;                 // the window that ends at N also reports the k == N blocks
+  int longT;                     // -longWithin L: report matches of at least this many sites (match mode 2)
   long long *winNanos;           // [W] optional: wall time of each window's CTA (globaltimer, debugging aid)
   int debugNoCandidates;         // profiling aid: publish zero match candidates per site (sweep-side cost only)
   // query sweep (matchSequencesSweep, pbwtMatch.c:363-443): single window, sorted mode, with d
@@ -76,7 +77,8 @@ struct RecSink {
 // largest M the shared-memory-resident kernel handles with / without the divergence array
 int sweep_smem_max_m(bool with_d);
 // returns cudaError_t as int
-int launch_sweep_smem(const SweepArgs &args, SweepMode mode, bool with_d, bool with_match, cudaStream_t stream);
+// match_mode: 0 none, 1 matchMaximalWithin, 2 matchLongWithin2 with args.longT (both imply d)
+int launch_sweep_smem(const SweepArgs &args, SweepMode mode, bool with_d, int match_mode, cudaStream_t stream);
 // query sweep: panel columns in args.src (sorted mode), queries in args.qcols; records go through the chunk pool
 int query_sweep_max_m();
 int query_sweep_max_q(int M);
@@ -112,7 +114,7 @@ struct GlobalBuffers {
   int32_t *qf = nullptr, *qe = nullptr;      // query sweep: [Q] each
   unsigned long long *nmKeys = nullptr;      // query sweep: [nomatchCap] sort keys of the "no match" events
 };
-int launch_sweep_global(const SweepArgs &a, SweepMode mode, bool with_d, bool with_match, const GlobalBuffers &b,
+int launch_sweep_global(const SweepArgs &a, SweepMode mode, bool with_d, int match_mode, const GlobalBuffers &b,
                         cudaStream_t stream);
 // query sweep over a wide panel: one window, sorted mode, with d; every CTA of the group serves its share of the
 // queries.  args.qCounts[1] counts the "no match" events (zero it before the launch).

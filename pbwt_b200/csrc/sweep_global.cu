@@ -267,10 +267,11 @@ struct GlobalArgs {
 // CLUSTER: the group is one thread-block cluster (G <= 16): the per-site exchange goes through distributed
 // shared memory and the group barriers are hardware cluster barriers (release/acquire at cluster scope, which
 // also orders the a[]/d[] stores to global memory) instead of flags and an arrival counter in global memory.
-template <int MODE, bool WITH_D, bool MATCH, bool QUERY, bool CLUSTER>
+// MATCH: 0 none, 1 matchMaximalWithin, 2 matchLongWithin2 (-longWithin L)
+template <int MODE, bool WITH_D, int MATCH, bool QUERY, bool CLUSTER>
 __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepArgs p, const GlobalArgs ga) {
   extern __shared__ __align__(16) uint32_t smem[];
-  constexpr bool SCAN = MATCH || QUERY;
+  constexpr bool SCAN = MATCH != 0 || QUERY;
   const int G = ga.G, chunk = ga.chunk;
   const int chunkWords = chunk / 32;
   const int QW = QUERY ? ((p.Q + 31) / 32 + 31) / 32 * 32 : 0;  // words of a query column, padded
@@ -705,7 +706,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
         const uint32_t pbit = gw == 0 ? (~cw & 1u) : (lw > 0 ? ycolS[lw - 1] >> 31 : st.yw(gw - 1) >> 31);
         const uint32_t nbit = gw + 1 >= WG ? 1u : (lw + 1 < chunkWords ? ycolS[lw + 1] & 1u : st.yw(gw + 1) & 1u);
         const uint32_t vm = (M - base >= 32) ? kFull : ((1u << (M - base)) - 1u);
-        const uint32_t m = candidate_mask(st, cw, pbit, nbit, base, vm, lane);
+        const uint32_t m = MATCH == 2 ? long_candidate_mask(st, cw, pbit, base, vm, k - p.longT, lane)
+                                      : candidate_mask(st, cw, pbit, nbit, base, vm, lane);
         if (lane == e) myMask = m;
         tw += __popc(m);
       }
@@ -713,7 +715,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
       if (lane == 0) wsumC[warp] = p.debugNoCandidates ? 0 : tw;
       __syncthreads();
       const long long before = recBase;
-      match_rounds(st, k, true, M, EW, wsumC, cmaskS, resS, sink, recBase, ensure_chunks, tid, lane, warp, p0);
+      if (MATCH == 2) long_rounds(st, k, k - p.longT, M, EW, wsumC, cmaskS, resS, sink, recBase, ensure_chunks, tid, lane, warp, p0);
+      else match_rounds(st, k, true, M, EW, wsumC, cmaskS, resS, sink, recBase, ensure_chunks, tid, lane, warp, p0);
       if (tid == 0) {
         const size_t seg = (size_t)(k + colShift) * G + g;
         ga.segCnt[seg] = (int32_t)(recBase - before);
@@ -836,7 +839,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
   // ---- state k1 ----
   const int32_t *aE = aW + (size_t)cur * MS;
   const int32_t *dE = WITH_D ? dW + (size_t)cur * (MS + 4) : nullptr;
-  const bool finalScan = !p.perWindowSites && k1 == nTotal && ((MATCH && p.reportAtN) || QUERY);
+  const bool finalScan = !p.perWindowSites && k1 == nTotal && ((MATCH != 0 && p.reportAtN && (MATCH == 1 || k1 > k0)) || QUERY);
   if (SCAN && finalScan) {  // word maxima of the final d, published to the group
     const int parE = (k1 - k0) & 1;
     for (int w = warp; w < chunkWords; w += 32) {
@@ -848,7 +851,25 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     group_barrier();
     const GlobalState st{aE, dE, ySortedW + (size_t)parE * WG, wmaxW + (size_t)parE * WG, M, nTotal + 1};
     const long long before = recBase;
-    if (MATCH) {  // k == N: nothing extends, every block is reported (alleles are not consulted when live == false)
+    if (MATCH == 2) {  // the reference scans state N with the stale alleles of site N-1 (pbwtCore.c:551-556)
+      const GlobalState sl{aE, dE, ySortedW + (size_t)(parE ^ 1) * WG, wmaxW + (size_t)parE * WG, M, nTotal + 1};
+      uint32_t myMask = 0;
+      int tw = 0;
+      for (int e = 0; e < EW; ++e) {
+        const int gw = w0g + warp * EW + e, base = gw * 32;
+        if (base >= M) break;
+        const uint32_t cw = sl.yw(gw);
+        const uint32_t vm = (M - base >= 32) ? kFull : ((1u << (M - base)) - 1u);
+        const uint32_t m = long_candidate_mask(sl, cw, gw == 0 ? (~cw & 1u) : sl.yw(gw - 1) >> 31, base, vm, nTotal - p.longT, lane);
+        if (lane == e) myMask = m;
+        tw += __popc(m);
+      }
+      if (lane < EW) cmaskS[warp * EW + lane] = myMask;
+      if (lane == 0) wsumC[warp] = tw;
+      __syncthreads();
+      long_rounds(sl, nTotal, nTotal - p.longT, M, EW, wsumC, cmaskS, resS, sink, recBase, ensure_chunks, tid, lane, warp, p0);
+    }
+    if (MATCH == 1) {  // k == N: nothing extends, every block is reported (alleles are not consulted when live == false)
       int tw = 0;
       if (lane < EW) {
         const int base = p0 + (warp * EW + lane) * 32;
@@ -923,15 +944,17 @@ static int max_chunk(bool with_d, bool match, bool query, int Q, int colWords) {
 }
 
 template <bool CLUSTER>
-static void *pick_kernel(SweepMode mode, bool with_d, bool match, bool query) {
-  if (query) return (void *)sweep_global_kernel<kSorted, true, false, true, CLUSTER>;
+static void *pick_kernel(SweepMode mode, bool with_d, int match, bool query) {
+  if (query) return (void *)sweep_global_kernel<kSorted, true, 0, true, CLUSTER>;
   if (mode == kGather)
-    return match ? (void *)sweep_global_kernel<kGather, true, true, false, CLUSTER>
-                 : with_d ? (void *)sweep_global_kernel<kGather, true, false, false, CLUSTER>
-                          : (void *)sweep_global_kernel<kGather, false, false, false, CLUSTER>;
-  return match ? (void *)sweep_global_kernel<kSorted, true, true, false, CLUSTER>
-               : with_d ? (void *)sweep_global_kernel<kSorted, true, false, false, CLUSTER>
-                        : (void *)sweep_global_kernel<kSorted, false, false, false, CLUSTER>;
+    return match == 2 ? (void *)sweep_global_kernel<kGather, true, 2, false, CLUSTER>
+           : match    ? (void *)sweep_global_kernel<kGather, true, 1, false, CLUSTER>
+           : with_d   ? (void *)sweep_global_kernel<kGather, true, 0, false, CLUSTER>
+                      : (void *)sweep_global_kernel<kGather, false, 0, false, CLUSTER>;
+  return match == 2 ? (void *)sweep_global_kernel<kSorted, true, 2, false, CLUSTER>
+         : match    ? (void *)sweep_global_kernel<kSorted, true, 1, false, CLUSTER>
+         : with_d   ? (void *)sweep_global_kernel<kSorted, true, 0, false, CLUSTER>
+                    : (void *)sweep_global_kernel<kSorted, false, 0, false, CLUSTER>;
 }
 
 static int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -1039,13 +1062,14 @@ static int launch_any(void *kern, bool cluster, const SweepArgs &a, const Global
   return (int)cudaLaunchKernelExC(&cfg, kern, params);
 }
 
-int launch_sweep_global(const SweepArgs &a, SweepMode mode, bool with_d, bool with_match, const GlobalBuffers &b,
+int launch_sweep_global(const SweepArgs &a, SweepMode mode, bool with_d, int with_match, const GlobalBuffers &b,
                         cudaStream_t stream) {
   if (with_match && !with_d) return (int)cudaErrorInvalidValue;
+  if (with_match == 2 && a.longT < 1) return (int)cudaErrorInvalidValue;
   if (b.cluster && b.G > 16) return (int)cudaErrorInvalidValue;
   void *kern = b.cluster ? pick_kernel<true>(mode, with_d, with_match, false) : pick_kernel<false>(mode, with_d, with_match, false);
   const int colWords = (mode == kGather && b.stageCol) ? a.wpc + 4 : 0;
-  return launch_any(kern, b.cluster, a, b, a.nWindows * b.G, smem_bytes(b.chunk, with_d, with_match, false, 0, colWords), stream);
+  return launch_any(kern, b.cluster, a, b, a.nWindows * b.G, smem_bytes(b.chunk, with_d, with_match != 0, false, 0, colWords), stream);
 }
 
 int query_sweep_global_max_q() { return kQCap; }

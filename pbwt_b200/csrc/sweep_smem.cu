@@ -88,9 +88,10 @@ struct SmemState {
 };
 __device__ __forceinline__ uint32_t ybit(const uint32_t *yc, int j) { return (yc[j >> 5] >> (j & 31)) & 1u; }
 
-template <int E, int MODE, bool WITH_D, bool MATCH, bool QUERY = false>
+// MATCH: 0 = none, 1 = matchMaximalWithin (pbwtMatch.c:115-142), 2 = matchLongWithin2 (-longWithin L, pbwtMatch.c:85-113)
+template <int E, int MODE, bool WITH_D, int MATCH, bool QUERY = false>
 __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs p) {
-  using L = SmemLayout<E, WITH_D, MATCH, QUERY>;
+  using L = SmemLayout<E, WITH_D, MATCH != 0, QUERY>;
   extern __shared__ __align__(16) uint32_t smem[];
   int32_t *const sI = reinterpret_cast<int32_t *>(smem);
   int32_t *const wsumZ = sI + L::wsum;
@@ -189,7 +190,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
   // candidates of a state -> records (match_scan.cuh); holds the caller's "S2" barrier
   auto match_rounds = [&](const int32_t *sA, const int32_t *sD, const uint32_t *yc, int k, bool live) {
     const SmemState st{sA, sD, yc, wmaxS};
-    pbwtgpu::match_rounds(st, k, live, M, E, wsumC, cmaskS, resS, sink, recBase, ensure_chunks, tid, lane, warp);
+    if (MATCH == 2) pbwtgpu::long_rounds(st, k, k - p.longT, M, E, wsumC, cmaskS, resS, sink, recBase, ensure_chunks, tid, lane, warp);
+    else pbwtgpu::match_rounds(st, k, live, M, E, wsumC, cmaskS, resS, sink, recBase, ensure_chunks, tid, lane, warp);
   };
 
   // -------- one site; CUR selects which half of the double buffers holds state k --------
@@ -227,6 +229,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     uint32_t pY = 0;
     int zw = 0;  // zeros in this warp so far
     unsigned bnd = 0;  // words of this warp holding a head or a tail of an allele run (match candidates)
+    uint32_t longMask = 0;  // MATCH == 2: lane e holds the interior heads of word e
+    int longCnt = 0;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int h = sLane[aC + e * 32];
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
       if (e == 0 && warp == 0) pb = (~Bw) & 1u;  // sorted position 0 is always a run head
       const uint32_t H = Bw ^ ((Bw << 1) | pb);
       pb = Bw >> 31;
-      if (MATCH) {
+      if (MATCH == 1) {
         if (H) bnd |= 1u << e;
         if (e > 0 && (H & 1u)) bnd |= 1u << (e - 1);  // a head at lane 0 makes the previous word's last lane a tail
       }
@@ -247,6 +251,11 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
         if (MATCH) {  // word maximum of d: lets the match scans skip over long blocks 1024 positions per step
           const int wm = __reduce_max_sync(kFull, dv);
           if (lane == 0) wmaxS[wordBase + e] = wm;
+        }
+        if (MATCH == 2) {  // interior heads: the allele changes here and the match with the neighbour above is long
+          const uint32_t m = H ? (H & __ballot_sync(kFull, dv <= k - p.longT)) : 0u;
+          if (lane == e) longMask = m;
+          longCnt += __popc(m);
         }
         if (H == 0u) {
           dn[e] = dv;
@@ -284,7 +293,11 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
       wsumZ[warp] = zw;
       if (WITH_D) wsumR[warp] = (anyHead ? 0x80000000u : 0u) | (uint32_t)carry;
     }
-    if (MATCH) {  // candidate lanes of this warp's words (exact: the allele after the warp is looked up too)
+    if (MATCH == 2) {
+      if (lane < E) cmaskS[wordBase + lane] = longMask;
+      if (lane == 0) wsumC[warp] = longCnt;
+    }
+    if (MATCH == 1) {  // candidate lanes of this warp's words (exact: the allele after the warp is looked up too)
       uint32_t nb = 1u;  // pad positions carry ones
       if (warp < 31) {
         if (MODE == kGather) {
@@ -507,13 +520,25 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
       if (lane == 0) wmaxS[w] = wm;
     }
     int tw = 0;
-    if (lane < E) {  // every valid position is a candidate
+    if (MATCH == 2) {  // the reference scans state N with the stale alleles of site N-1 (pbwtCore.c:551-556): yc still holds them
+      const SmemState st{sI + aC, sI + dC, yc, wmaxS};
+      uint32_t myMask = 0;
+      for (int e = 0; e < E; ++e) {
+        const int wd = wordBase + e, base = wd * 32;
+        if (base >= M) break;
+        const uint32_t vm = (M - base >= 32) ? kFull : ((1u << (M - base)) - 1u);
+        const uint32_t m = long_candidate_mask(st, yc[wd], wd > 0 ? yc[wd - 1] >> 31 : (~yc[wd] & 1u), base, vm, nTotal - p.longT, lane);
+        if (lane == e) myMask = m;
+        tw += __popc(m);
+      }
+      if (lane < E) cmaskS[wordBase + lane] = myMask;
+    } else if (lane < E) {  // every valid position is a candidate
       const int base = (wordBase + lane) * 32;
       const uint32_t vm = (M - base >= 32) ? kFull : (M > base ? ((1u << (M - base)) - 1u) : 0u);
       cmaskS[wordBase + lane] = vm;
       tw = __popc(vm);
     }
-    tw = __reduce_add_sync(kFull, tw);
+    if (MATCH != 2) tw = __reduce_add_sync(kFull, tw);
     if (lane == 0) wsumC[warp] = tw;
     __syncthreads();
     match_rounds(sI + aC, sI + dC, yc, nTotal, false);
@@ -526,9 +551,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
   }
 }
 
-template <int E, int MODE, bool WITH_D, bool MATCH>
+template <int E, int MODE, bool WITH_D, int MATCH>
 int launch_one(const SweepArgs &a, cudaStream_t stream) {
-  using L = SmemLayout<E, WITH_D, MATCH>;
+  using L = SmemLayout<E, WITH_D, MATCH != 0>;
   static_assert(L::bytes <= 232448, "shared memory layout exceeds the 227 KB per-CTA limit");
   static_assert(kStages <= 4 && L::xcol % 4 == 0 && L::mbar % 2 == 0 && L::res % 4 == 0 && L::d0 % 4 == 0 && L::d1 % 4 == 0,
                 "shared memory arrays must keep their alignment");
@@ -539,7 +564,7 @@ int launch_one(const SweepArgs &a, cudaStream_t stream) {
   return (int)cudaGetLastError();
 }
 
-template <int MODE, bool WITH_D, bool MATCH>
+template <int MODE, bool WITH_D, int MATCH>
 int launch_e(const SweepArgs &a, cudaStream_t stream) {
   const int words = (a.M + 31) / 32;
   const int e = (words + 31) / 32;
@@ -566,7 +591,7 @@ template <int E>
 static int launch_query_one(const SweepArgs &a, cudaStream_t stream) {
   using L = SmemLayout<E, true, false, true>;
   static_assert(L::bytes <= 232448, "shared memory layout exceeds the 227 KB per-CTA limit");
-  auto kern = sweep_smem_kernel<E, kSorted, true, false, true>;
+  auto kern = sweep_smem_kernel<E, kSorted, true, 0, true>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
   if (err != cudaSuccess) return (int)err;
   kern<<<1, kThreads, L::bytes, stream>>>(a);
@@ -584,16 +609,19 @@ int launch_query_sweep_smem(const SweepArgs &a, cudaStream_t stream) {
   return launch_query_one<13>(a, stream);
 }
 
-int launch_sweep_smem(const SweepArgs &a, SweepMode mode, bool with_d, bool with_match, cudaStream_t stream) {
-  if (a.M < 1 || a.M > sweep_smem_max_m(with_d || with_match)) return (int)cudaErrorInvalidValue;
+int launch_sweep_smem(const SweepArgs &a, SweepMode mode, bool with_d, int match_mode, cudaStream_t stream) {
+  if (a.M < 1 || a.M > sweep_smem_max_m(with_d || match_mode)) return (int)cudaErrorInvalidValue;
+  if (match_mode == 2 && a.longT < 1) return (int)cudaErrorInvalidValue;
   if (mode == kGather) {
-    if (with_match) return launch_e<kGather, true, true>(a, stream);
-    if (with_d) return launch_e<kGather, true, false>(a, stream);
-    return launch_e<kGather, false, false>(a, stream);
+    if (match_mode == 2) return launch_e<kGather, true, 2>(a, stream);
+    if (match_mode) return launch_e<kGather, true, 1>(a, stream);
+    if (with_d) return launch_e<kGather, true, 0>(a, stream);
+    return launch_e<kGather, false, 0>(a, stream);
   } else {
-    if (with_match) return launch_e<kSorted, true, true>(a, stream);
-    if (with_d) return launch_e<kSorted, true, false>(a, stream);
-    return launch_e<kSorted, false, false>(a, stream);
+    if (match_mode == 2) return launch_e<kSorted, true, 2>(a, stream);
+    if (match_mode) return launch_e<kSorted, true, 1>(a, stream);
+    if (with_d) return launch_e<kSorted, true, 0>(a, stream);
+    return launch_e<kSorted, false, 0>(a, stream);
   }
 }
 

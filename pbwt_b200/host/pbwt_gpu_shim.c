@@ -9,7 +9,7 @@
  * reaches the functions below instead, with unchanged signatures and callback contract
  * (pbwt.h:208-213: report(ai, bi, start, end), synchronous, in the reference's order).
  * Errors follow the reference's convention: die() (utils.c:31-44).  There is no CPU fallback for the
- * GPU-backed paths; options this shim does not accelerate (-check, -stats, -longWithin L>0) are passed to
+ * GPU-backed paths; options this shim does not accelerate (-check, -stats) are passed to
  * the reference's renamed originals and say so on the log.
  */
 #include "pbwt.h"
@@ -63,12 +63,21 @@ void pbwtLongMatches (PBWT *p, int L)
 {
   if (!p || !p->yz) die ("option -longWithin called without a PBWT") ;
   if (L < 0) die ("L %d for longWithin must be >= 0", L) ;
-  if (L || isCheck || isStats)
-    { fprintf (logFile, "pbwt_gpu: -longWithin L>0 / -check / -stats run the reference CPU path\n") ;
+  if (isCheck || isStats)
+    { fprintf (logFile, "pbwt_gpu: -check / -stats run the reference CPU path\n") ;
       ref_pbwtLongMatches (p, L) ;
       return ;
     }
-  matchMaximalWithin (p, reportMatchLine) ;
+  if (L)			/* matchLongWithin2 (pbwtMatch.c:85-113) */
+    { pbwtgpu_match *rec = 0 ;
+      int64_t n = 0, i ;
+      gpuCheck (pbwtgpu_long_within (gpuContext (), arrp(p->yz,0,uchar), arrayMax(p->yz), p->M, p->N,
+				     p->aFstart, L, 0, 0, &rec, &n), "pbwtgpu_long_within") ;
+      for (i = 0 ; i < n ; ++i) reportMatchLine (rec[i].ai, rec[i].bi, rec[i].start, rec[i].end) ;
+      pbwtgpu_free (rec) ;
+    }
+  else
+    matchMaximalWithin (p, reportMatchLine) ;
 }
 
 /* ---- matchSequencesSweep (pbwtMatch.c:363-443) ---- */

@@ -40,6 +40,20 @@ def test_cli_maxwithin_stdout(tmp_path, name):
 
 
 @needs_cli
+@pytest.mark.parametrize("name,L", [("merge1", 2), ("omni", 20), ("mosaic300x400", 40)])
+def test_cli_longwithin_stdout(tmp_path, name, L):
+    """pbwt_gpu -read X.pbwt -longWithin L prints the reference's MATCH lines (golden md5 of its stdout)."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    lw = np.load(os.path.join(GOLD, "long_within.npz"))
+    M, N = int(g["M"]), int(g["N"])
+    pb = tmp_path / "x.pbwt"
+    write_pbwt(pb, M, N, np.arange(M), g["a_end"], g["yz"])
+    out = subprocess.run([CLI, "-read", str(pb), "-longWithin", str(L)], check=True, capture_output=True).stdout
+    assert len(out.splitlines()) == len(lw[f"{name}_L{L}"])
+    assert hashlib.md5(out).hexdigest() == str(lw[f"{name}_L{L}_md5"])
+
+
+@needs_cli
 def test_cli_matchdynamic_stdout_and_log(tmp_path):
     g = np.load(os.path.join(GOLD, "query_sweep.npz"))
     M, Q, N = int(g["M"]), int(g["Q"]), int(g["N"])

@@ -425,3 +425,81 @@ def test_query_sweep_wide_panel(eng, orc, M, Q, N, L, mu, no_cluster):
     finally:
         eng.set_option("no_cluster", 0)
     assert len(rec) == len(want_rec) and (rec == want_rec).all() and (nom == want_nom).all()
+
+
+# ---- -longWithin L (matchLongWithin2, pbwtMatch.c:85-113) ----------------------------------------------------
+
+def test_long_within_goldens(eng):
+    """Records printed by the reference CLI for -longWithin L on the golden panels."""
+    g = np.load(os.path.join(GOLD, "long_within.npz"))
+    for key in [k for k in g.files if not k.endswith("_md5")]:
+        name, L = key.rsplit("_L", 1)
+        p = np.load(os.path.join(GOLD, name + ".npz"))
+        M, N = int(p["M"]), int(p["N"])
+        got = eng.long_within(p["yz"], M, N, int(L))
+        assert (got["a_end"] == p["a_end"]).all() and (got["d_end"] == p["d_end"]).all()
+        assert len(got["matches"]) == len(g[key]) and (rec4(got["matches"]) == g[key]).all(), key
+
+
+def check_long(eng, orc, hap, L, a_start=None):
+    M, N = hap.shape
+    x = O.pack_panel(hap)
+    yz = orc.build(x, M, N, a_start, with_d=False)[0]
+    want, n = orc.long_within(yz, M, N, L, a_start)
+    got = eng.long_within(yz, M, N, L, a_start=a_start)  # stored-stream route (the CLI's)
+    assert len(got["matches"]) == n and (got["matches"] == want).all()
+    got2 = eng.build(x, M, N, a_start=a_start, long_L=L)  # build route: gather mode, same scan
+    assert got2["yz"].tobytes() == yz.tobytes()
+    assert len(got2["matches"]) == n and (got2["matches"] == want).all()
+    return n
+
+
+@pytest.mark.parametrize("M,N,L,W,dens", [(8, 10, 1, 1, 0.3), (33, 40, 2, 3, 0.5), (500, 64, 4, 5, 0.3), (1000, 90, 6, 1, 0.1),
+                                          (3000, 300, 40, 9, 0.05), (10000, 200, 14, 0, 0.5), (12544, 100, 13, 0, 0.4)])
+def test_long_within_random(eng, orc, M, N, L, W, dens):
+    rng = np.random.default_rng(M + L)
+    hap = (rng.random((M, N)) < dens).astype(np.uint8)
+    if M > 40:
+        hap[3:23] = hap[3]  # a block of identical haplotypes (never separated: reported only when both alleles ... none)
+        hap[23:33, : N // 2] = hap[3, : N // 2]
+    a0 = rng.permutation(M).astype(np.int32) if M % 2 else None
+    eng.set_option("windows", W)
+    try:
+        check_long(eng, orc, hap, L, a0)
+    finally:
+        eng.set_option("windows", 0)
+
+
+def test_long_within_mosaic(eng, orc):
+    M, N = 4000, 2000
+    hap = O.unpack_panel(O.generate_panel(M, N, seed=0x5EED0021, L=200, mu=20.0), M)
+    n = check_long(eng, orc, hap, 200)
+    assert n > 1000
+
+
+@pytest.mark.parametrize("M,N,L,W,dens,no_cluster", [(33, 40, 2, 3, 0.5, 0), (3000, 200, 30, 5, 0.05, 0), (3000, 200, 30, 5, 0.05, 1),
+                                                     (5000, 64, 12, 37, 0.3, 0)])
+def test_long_within_wide_kernel_forced(eng, orc, M, N, L, W, dens, no_cluster):
+    rng = np.random.default_rng(M + L + 1)
+    hap = (rng.random((M, N)) < dens).astype(np.uint8)
+    eng.set_option("force_global", 1)
+    eng.set_option("no_cluster", no_cluster)
+    eng.set_option("windows", W)
+    try:
+        check_long(eng, orc, hap, L)
+    finally:
+        eng.set_option("force_global", 0)
+        eng.set_option("no_cluster", 0)
+        eng.set_option("windows", 0)
+
+
+@pytest.mark.parametrize("M,N,L,no_cluster", [(20000, 60, 16, 0), (100000, 48, 18, 0), (100000, 48, 18, 1)])
+def test_long_within_wide_panels(eng, orc, M, N, L, no_cluster):
+    rng = np.random.default_rng(M + 3)
+    hap = (rng.random((M, N)) < 0.5).astype(np.uint8)
+    eng.set_option("no_cluster", no_cluster)
+    try:
+        n = check_long(eng, orc, hap, L)
+    finally:
+        eng.set_option("no_cluster", 0)
+    assert n > 0
