@@ -8,6 +8,8 @@
  * so that every caller in the program (pbwtMain.c:404-413, pbwtPaint.c:87,237, pbwtImpute.c:1142-1146)
  * reaches the functions below instead, with unchanged signatures and callback contract
  * (pbwt.h:208-213: report(ai, bi, start, end), synchronous, in the reference's order).
+ * The readers of pbwtIO.c are batched onto the GPU by two more renames applied to pbwtIO.c only (see
+ * gpuReaderWriteForwards below).
  * Errors follow the reference's convention: die() (utils.c:31-44).  There is no CPU fallback for the
  * GPU-backed paths; options this shim does not accelerate (-check, -stats) are passed to
  * the reference's renamed originals and say so on the log.
@@ -119,6 +121,90 @@ void matchSequencesDynamic (PBWT *p, FILE *fp)	/* pbwtMatch.c:352-357 */
   PBWT *q = pbwtRead (fp) ;
   matchSequencesSweep (p, q, reportMatchLine) ;
   pbwtDestroy (q) ;
+}
+
+/* ---- batched ingest: the readers of pbwtIO.c (pbwtReadLineFile :558-586, pbwtReadLineTwoFile :595-623,
+   pbwtReadMacs :460-492, the phase reader :820-826, pbwtCheckPoint :158-168) all run, per parsed site,
+       for (j = 0 ; j < M ; ++j) u->y[j] = x[u->a[j]] ;  pbwtCursorWriteForwards (u) ;
+   and finish with pbwtCursorToAFend (u, p).  pbwtIO.c is compiled with
+       -DpbwtCursorWriteForwards=gpuReaderWriteForwards -DpbwtCursorToAFend=gpuReaderToAFend
+   so those calls land here ("lazy cursor"): u->a is left at the identity, which makes the gathered u->y the
+   UNSORTED column x; columns are bit-packed into a batch, and a full batch (or the final partial one) is swept
+   on the GPU by pbwtgpu_build from the true order carried between batches, the pack3 bytes are appended to
+   u->z exactly where pack3arrayAdd would have put them, and ToAFend hands the true order to p->aFend.
+   The readers themselves are untouched.  Cursors that do not start from the identity fall back to the
+   reference's functions. ---- */
+
+void pbwtCursorWriteForwards (PbwtCursor *u) ;	/* the reference's own (pbwtCore.c:573-578, :587-591) */
+void pbwtCursorToAFend (PbwtCursor *u, PBWT *p) ;
+
+static struct
+{ PbwtCursor *u ;		/* the reader's cursor being batched */
+  int M, wpc, cap, n ;		/* batch capacity and fill, in sites */
+  long written ;		/* bytes appended to u->z so far */
+  uint32_t *bits ;
+  int *aTrue ;			/* the real a[] entering the batch */
+  PbwtCursor *plain ;		/* a cursor handed to the reference's functions instead */
+} rb ;
+
+static void readerFlush (PbwtCursor *u)
+{
+  uint8_t *yz = 0 ; int64_t nyz = 0 ;
+  int *aNew ;
+  long max ;
+
+  if (!rb.n) return ;
+  aNew = myalloc (rb.M, int) ;
+  gpuCheck (pbwtgpu_build (gpuContext (), rb.bits, rb.M, rb.n, rb.aTrue, PBWTGPU_WANT_YZ, &yz, &nyz, aNew, 0, 0, 0),
+	    "pbwtgpu_build") ;
+  max = arrayMax(u->z) ;
+  arrayExtend (u->z, max + nyz) ;	/* as pack3arrayAdd does, pbwtCore.c:270-277 */
+  memcpy (arrp(u->z,max,uchar), yz, nyz) ;
+  arrayMax(u->z) = max + nyz ;
+  u->n += nyz ;
+  rb.written += nyz ;
+  memcpy (rb.aTrue, aNew, rb.M*sizeof(int)) ;
+  memset (rb.bits, 0, (size_t)rb.wpc * rb.cap * sizeof(uint32_t)) ;
+  rb.n = 0 ;
+  pbwtgpu_free (yz) ; free (aNew) ;
+}
+
+void gpuReaderWriteForwards (PbwtCursor *u)
+{
+  int j ;
+  uint32_t *col ;
+
+  if (u == rb.plain && u != rb.u) { pbwtCursorWriteForwards (u) ; return ; }
+  if (u != rb.u || arrayMax(u->z) != rb.written)	/* a new reader (possibly at a recycled address) */
+    { BOOL isIdentity = (arrayMax(u->z) == 0) ;
+      for (j = 0 ; isIdentity && j < u->M ; ++j) if (u->a[j] != j) isIdentity = FALSE ;
+      if (!isIdentity) { rb.plain = u ; if (rb.u == u) rb.u = 0 ; pbwtCursorWriteForwards (u) ; return ; }
+      if (rb.u && rb.n) die ("gpuReaderWriteForwards: a batch of another cursor is still pending") ;
+      free (rb.bits) ; free (rb.aTrue) ;
+      rb.u = u ; rb.plain = 0 ; rb.M = u->M ; rb.wpc = pbwtgpu_words_per_col (u->M) ; rb.n = 0 ; rb.written = 0 ;
+      { const char *e = getenv ("PBWTGPU_READER_BATCH") ;	/* sites per batch; default bounded by 256 MB of columns */
+	long cap = e ? atol (e) : 65536 ;
+	long most = (256L << 20) / (4L * rb.wpc) ;
+	if (cap > most) cap = most ;
+	if (cap < 1) cap = 1 ;
+	rb.cap = (int) cap ;
+      }
+      rb.bits = mycalloc ((size_t)rb.wpc * rb.cap, uint32_t) ;
+      rb.aTrue = myalloc (rb.M, int) ;
+      for (j = 0 ; j < rb.M ; ++j) rb.aTrue[j] = j ;
+    }
+  col = rb.bits + (size_t)rb.n * rb.wpc ;	/* u->a is the identity, so u->y is the column as parsed */
+  for (j = 0 ; j < rb.M ; ++j) if (u->y[j]) col[j >> 5] |= 1u << (j & 31) ;
+  u->isBlockEnd = FALSE ;
+  if (++rb.n == rb.cap) readerFlush (u) ;
+}
+
+void gpuReaderToAFend (PbwtCursor *u, PBWT *p)
+{
+  if (u != rb.u) { pbwtCursorToAFend (u, p) ; return ; }
+  readerFlush (u) ;
+  if (!p->aFend) p->aFend = myalloc (p->M, int) ;
+  memcpy (p->aFend, rb.aTrue, p->M*sizeof(int)) ;
 }
 
 /* ---- batched build: what the readers' per-site loop (pbwtIO.c:558-586) becomes when a batch of

@@ -67,6 +67,29 @@ def test_cli_matchdynamic_stdout_and_log(tmp_path):
 
 
 @needs_cli
+@pytest.mark.parametrize("name,batch", [("merge1", 3), ("omni", 7), ("omni", 0), ("mosaic300x400", 128)])
+def test_cli_reader_batched_ingest(tmp_path, name, batch):
+    """pbwt_gpu -readVcfq x -write y: the reference's own reader and writer, with the reader's per-site cursor
+    step batched onto the GPU by the shim (several batches: the order is carried between them): the .pbwt
+    file must be the reference's, byte for byte."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    M, N = int(g["M"]), int(g["N"])
+    hap = O.unpack_panel(g["xbits"], M)
+    vq, pb = tmp_path / "x.vcfq", tmp_path / "x.pbwt"
+    with open(vq, "w") as fh:  # parseVcfqLine, pbwtIO.c:511-554
+        for k in range(N):
+            fh.write("20\t%d\tA\tC\t" % (1000 + k) + "\t".join(str(int(v)) for v in hap[:, k]) + "\n")
+    env = dict(os.environ)
+    if batch:
+        env["PBWTGPU_READER_BATCH"] = str(batch)
+    subprocess.run([CLI, "-readVcfq", str(vq), "-write", str(pb)], check=True, capture_output=True, env=env)
+    assert hashlib.md5(open(pb, "rb").read()).hexdigest() == str(g["pbwt_md5"])
+    # and straight into a match command, without a file in between
+    out = subprocess.run([CLI, "-readVcfq", str(vq), "-maxWithin"], check=True, capture_output=True, env=env).stdout
+    assert hashlib.md5(out).hexdigest() == str(g["maxwithin_stdout_md5"])
+
+
+@needs_cli
 def test_shim_batched_build_writes_reference_file(tmp_path):
     """pbwtGpuBuildFromSites + the reference's own pbwtWrite must give the reference's .pbwt bytes."""
     g = np.load(os.path.join(GOLD, "omni.npz"))
