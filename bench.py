@@ -288,9 +288,9 @@ def main():
         sweep_ms_per_step = sweep_ms / args.steps
         achieved = algo_bytes / (sweep_ms_per_step * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    # dram__bytes_read+write of the kernel's two big launches (pass 1: 131.1 MB, pass 2: 501.8 MB) from the
-                    # ncu --set full captures in profiles/r01_c2_pass{1,2}_ncu_full_summary.txt; only valid for this config
-                    "traffic": 632.9e6 if (M, N) == (M_DEFAULT, N_DEFAULT) else None, "kernel": "sweep_smem_kernel",
+                    # dram__bytes_read+write of the kernel's two big launches (pass 1: 131.1 MB, pass 2: 502.2 MB) from the
+                    # ncu --set full captures in profiles/r01b_c2_pass{1,2}_ncu_full_summary.txt; only valid for this config
+                    "traffic": 633.3e6 if (M, N) == (M_DEFAULT, N_DEFAULT) else None, "kernel": "sweep_smem_kernel",
                     "kernel_ms_per_step": sweep_ms_per_step, "kernel_launches_per_step": sweep_launches / args.steps,
                     "kernel_ms_per_step_by_role": {"pass1": kt["prepass"][0] / args.steps, "combine": kt["combine"][0] / args.steps,
                                                    "pass2": kt["sweep"][0] / args.steps},
