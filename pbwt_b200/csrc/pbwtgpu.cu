@@ -26,6 +26,7 @@ struct pbwtgpu_ctx {
   long long optNoCandidates = 0;  // profiling aid
   long long optForceGlobal = 0;  // testing: use the global-memory kernel even for narrow panels
   long long optLongT = 0;        // L of PBWTGPU_WANT_LONGWITHIN
+  long long optNoSortPass1 = 0;  // testing: pass 1 by sweeping even where the window sort applies
   long long optNoCluster = 0;    // testing: wide panels through the cooperative-grid path even where clusters fit
   // profiling
   bool profile = false;
@@ -350,7 +351,17 @@ struct WindowedSweep {
     a1.siteOffset = siteOffset; a1.nTotal = nTotal;
     a1.aStart = positionSpace ? iota : ord[0]; a1.aStartShared = 1;
     a1.aEnd = ord[0] + oA(); a1.dEnd = dv[0] + oD();
-    {
+    // Pass 1 only has to deliver each window's node.  Building from panel columns on a panel that fits the
+    // shared-memory kernels, the node is computed by a radix sort of the haplotypes' window keys (window_sort.cu)
+    // instead of a site-by-site sweep; stored streams and wide panels sweep.
+    const bool sortPass1 = !useGlobal && mode == kGather && M <= window_sort_max_m() && !ctx->optNoSortPass1;
+    if (sortPass1) {
+      uint32_t *T = nullptr;
+      if (int rc = tmp.get(&T, (size_t)nodes * M * window_sort_key_words(spw))) return rc;
+      ScopedTimer t(ctx, PBWTGPU_K_PREPASS);
+      CUDA_TRY(ctx, launch_window_sort(src, wpc, M, N, spw, siteOffset, a1.aStart, nodes, T, a1.aEnd, a1.dEnd, ctx->stream));
+      ctx->launches[PBWTGPU_K_PREPASS] += 2;
+    } else {
       ScopedTimer t(ctx, PBWTGPU_K_PREPASS);
       CUDA_TRY(ctx, launch(a1, mode, true, false));
       ctx->launches[PBWTGPU_K_PREPASS] += 1;
@@ -697,6 +708,7 @@ int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value) {
   else if (!strcmp(name, "force_global")) ctx->optForceGlobal = value;
   else if (!strcmp(name, "no_cluster")) ctx->optNoCluster = value;
   else if (!strcmp(name, "long_within")) ctx->optLongT = value;
+  else if (!strcmp(name, "no_sort_pass1")) ctx->optNoSortPass1 = value;
   else if (!strcmp(name, "debug_no_candidates")) ctx->optNoCandidates = value;
   else return fail(ctx, PBWTGPU_ERR_ARG, "unknown option %s", name);
   return 0;

@@ -177,22 +177,27 @@ def test_full_size_properties(eng):
     assert (np.diff(m["end"]) >= 0).all()  # callback order: k ascending
 
 
+@pytest.mark.parametrize("no_sort", [0, 1])
 @pytest.mark.parametrize("M,N,W,dens", [(8, 10, 3, 0.3), (33, 40, 5, 0.5), (200, 64, 64, 0.2), (1000, 300, 7, 0.05),
-                                        (1025, 120, 16, 0.5), (2752, 38, 4, 0.3), (5000, 200, 148, 0.02)])
-def test_window_parallel_forced(eng, orc, M, N, W, dens):
+                                        (1025, 120, 16, 0.5), (2752, 38, 4, 0.3), (5000, 200, 148, 0.02),
+                                        (12288, 400, 6, 0.3), (12289, 90, 4, 0.3), (9000, 1000, 11, 0.003)])
+def test_window_parallel_forced(eng, orc, M, N, W, dens, no_sort):
     """Force the window-parallel path (pass 1 + combine scan + pass 2) at small sizes: results must equal the
-    sequential reference sweep bit for bit, including match-record order across window boundaries."""
+    sequential reference sweep bit for bit, including match-record order across window boundaries.  Pass 1 runs
+    as the window sort (window_sort.cu) or, with no_sort_pass1, as a sweep."""
     rng = np.random.default_rng(M * 7 + N)
     hap = (rng.random((M, N)) < dens).astype(np.uint8)
     hap[: M // 3] = hap[0]  # a block of identical haplotypes: ties that survive every window
     x = O.pack_panel(hap)
     a0 = rng.permutation(M).astype(np.int32)
     eng.set_option("windows", W)
+    eng.set_option("no_sort_pass1", no_sort)
     try:
-        check_build(eng, orc, x, M, N)
-        check_build(eng, orc, x, M, N, a_start=a0)
+        check_build(eng, orc, x, M, N, matches=M * N < 2000000)
+        check_build(eng, orc, x, M, N, a_start=a0, matches=M * N < 2000000)
     finally:
         eng.set_option("windows", 0)
+        eng.set_option("no_sort_pass1", 0)
 
 
 def test_window_parallel_mosaic(eng, orc):
