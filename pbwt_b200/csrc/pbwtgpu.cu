@@ -357,7 +357,7 @@ struct WindowedSweep {
     const bool sortPass1 = !useGlobal && mode == kGather && M <= window_sort_max_m() && !ctx->optNoSortPass1;
     if (sortPass1) {
       uint32_t *T = nullptr;
-      if (int rc = tmp.get(&T, (size_t)nodes * M * window_sort_key_words(spw))) return rc;
+      if (int rc = tmp.get(&T, window_sort_scratch_words(M, spw, nodes))) return rc;
       ScopedTimer t(ctx, PBWTGPU_K_PREPASS);
       CUDA_TRY(ctx, launch_window_sort(src, wpc, M, N, spw, siteOffset, a1.aStart, nodes, T, a1.aEnd, a1.dEnd, ctx->stream));
       ctx->launches[PBWTGPU_K_PREPASS] += 2;

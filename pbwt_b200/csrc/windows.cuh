@@ -37,11 +37,11 @@ int sort_nomatch(const unsigned long long *keys, const pbwtgpu_nomatch *events, 
                  cudaStream_t stream);
 
 // Pass 1 as a sort (window_sort.cu): nodes (order, divergence) of windows [w*spw, (w+1)*spw) of the panel columns,
-// w < nodes, each swept on its own from aStart ([M], NULL = identity).  T: scratch of nodes * M *
-// window_sort_key_words(spw) words.  ordOut [nodes][M], dvOut [nodes][M+1]; labels are siteOffset + column + 1.
+// w < nodes, each swept on its own from aStart ([M], NULL = identity).  scratch: window_sort_scratch_words words.
+// ordOut [nodes][M], dvOut [nodes][M+1]; labels are siteOffset + column + 1.
 int window_sort_max_m();
-int window_sort_key_words(int spw);
+size_t window_sort_scratch_words(int M, int spw, int nodes);
 int launch_window_sort(const uint32_t *panel, int wpc, int M, int N, int spw, int siteOffset, const int32_t *aStart, int nodes,
-                       uint32_t *T, int32_t *ordOut, int32_t *dvOut, cudaStream_t stream);
+                       uint32_t *scratch, int32_t *ordOut, int32_t *dvOut, cudaStream_t stream);
 
 }  // namespace pbwtgpu
