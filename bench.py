@@ -198,7 +198,8 @@ def main():
     ms_per_step = float(np.mean(ms_steps))
     kt = eng.last_timings()
     launches = sum(v[1] for v in kt.values())
-    # the sweep kernel runs in three roles per step: pass 1 (prepass), combine rounds, pass 2 (sweep)
+    # one step's sweep work: pass 1 (window nodes: transpose + window sort), the combine rounds and pass 2 (both the
+    # sweep kernel); the roofline is quoted on their summed duration
     sweep_ms = kt["sweep"][0] + kt["prepass"][0] + kt["combine"][0]
     sweep_launches = kt["sweep"][1] + kt["prepass"][1] + kt["combine"][1]
 
@@ -288,16 +289,18 @@ def main():
         sweep_ms_per_step = sweep_ms / args.steps
         achieved = algo_bytes / (sweep_ms_per_step * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    # dram__bytes_read+write of the kernel's two big launches (pass 1: 131.1 MB, pass 2: 502.2 MB) from the
-                    # ncu --set full captures in profiles/r01b_c2_pass{1,2}_ncu_full_summary.txt; only valid for this config
-                    "traffic": 633.3e6 if (M, N) == (M_DEFAULT, N_DEFAULT) else None, "kernel": "sweep_smem_kernel",
+                    # dram__bytes_read+write of pass 2, the dominant launch (502.2 MB; ncu --set full capture in
+                    # profiles/r01b_c2_pass2_ncu_full_summary.txt), plus the window sort (13.8 MB) and its transpose
+                    # (read 125 MB + write 130 MB); only valid for this config
+                    "traffic": 771.0e6 if (M, N) == (M_DEFAULT, N_DEFAULT) else None, "kernel": "sweep_smem_kernel",
                     "kernel_ms_per_step": sweep_ms_per_step, "kernel_launches_per_step": sweep_launches / args.steps,
                     "kernel_ms_per_step_by_role": {"pass1": kt["prepass"][0] / args.steps, "combine": kt["combine"][0] / args.steps,
                                                    "pass2": kt["sweep"][0] / args.steps},
                     "algorithmic_bytes_per_step": algo_bytes, "peak_source": peak_src,
-                    "note": "algorithmic bytes (16.125 B per haplotype-site + emitted bytes) over the summed duration of all "
-                            "sweep-kernel launches of a step; a[]/d[] stay resident in shared memory, so DRAM traffic is "
-                            "far below the algorithmic bytes"}
+                    "note": "algorithmic bytes (16.125 B per haplotype-site + emitted bytes) over the summed duration of the "
+                            "launches that do a step's sweep work: pass 1 (window nodes by transpose + radix sort of window "
+                            "keys), combine rounds and pass 2 (sweep_smem_kernel, the dominant launch); a[]/d[] stay resident "
+                            "in shared memory, so DRAM traffic is far below the algorithmic bytes"}
         cpu = None
         if not args.no_cpu_baseline:
             n_cpu = args.cpu_sites or min(N, 20000)

@@ -10,6 +10,7 @@
 // gives each run's absolute symbol position; column boundaries fall where that position crosses a
 // multiple of M.  Runs of 1s are OR-ed into a zeroed bit-column buffer.
 #include "pack3.cuh"
+#include "windows.cuh"
 
 namespace pbwtgpu {
 namespace {
@@ -280,15 +281,23 @@ __global__ void bits_to_bytes_kernel(const uint32_t *ycols, int M, int N, int wp
 
 }  // namespace
 
-int p3_count_columns(const uint32_t *ycols, int wpc, int M, int N, int32_t *colBytes, int64_t *colBase,
-                     cudaStream_t stream) {
+int p3_count_columns(const uint32_t *ycols, int wpc, int M, int N, int32_t *colBytes, int64_t *colBase, void *scratch,
+                     size_t scratchBytes, cudaStream_t stream) {
   if (N > 0) {
     p3_count_kernel<<<(N + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, stream>>>(ycols, wpc, M, N,
                                                                                                    colBytes);
   }
-  scan_i32_to_i64_kernel<<<1, 1024, 0, stream>>>(colBytes, colBase, N);
-  return (int)cudaGetLastError();
+  if (N < 4096 || !scratch) {  // short streams: one block is quicker than a library scan
+    scan_i32_to_i64_kernel<<<1, 1024, 0, stream>>>(colBytes, colBase, N);
+    return (int)cudaGetLastError();
+  }
+  // exclusive 64-bit scan of N counts plus a trailing zero, so that colBase[N] = total (CUB)
+  cudaError_t err = cudaMemsetAsync(colBytes + N, 0, sizeof(int32_t), stream);
+  if (err != cudaSuccess) return (int)err;
+  return launch_segment_scan(colBytes, (long long)N + 1, reinterpret_cast<long long *>(colBase), scratch, scratchBytes, stream);
 }
+
+size_t p3_scan_scratch_bytes(int N) { return segment_scan_temp_bytes((long long)N + 1); }
 
 int p3_emit_columns(const uint32_t *ycols, int wpc, int M, int N, const int64_t *colBase, uint8_t *yz,
                     cudaStream_t stream) {

@@ -4,9 +4,11 @@
 
 namespace pbwtgpu {
 
-// per-column byte counts (int32[N]) and their exclusive scan (int64[N+1], last = total bytes)
-int p3_count_columns(const uint32_t *ycols, int wpc, int M, int N, int32_t *colBytes, int64_t *colBase,
-                     cudaStream_t stream);
+// per-column byte counts (int32[N+1]) and their exclusive scan (int64[N+1], last = total bytes);
+// scratch: p3_scan_scratch_bytes(N) bytes of device memory (NULL: a single-block scan is used)
+size_t p3_scan_scratch_bytes(int N);
+int p3_count_columns(const uint32_t *ycols, int wpc, int M, int N, int32_t *colBytes, int64_t *colBase, void *scratch,
+                     size_t scratchBytes, cudaStream_t stream);
 int p3_emit_columns(const uint32_t *ycols, int wpc, int M, int N, const int64_t *colBase, uint8_t *yz,
                     cudaStream_t stream);
 // decode: tileScratch needs p3_decode_num_tiles(nyz)+1 int64; tileScratch[nTiles] = symbols decoded

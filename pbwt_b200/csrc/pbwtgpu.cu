@@ -26,6 +26,7 @@ struct pbwtgpu_ctx {
   long long optNoCandidates = 0;  // profiling aid
   long long optForceGlobal = 0;  // testing: use the global-memory kernel even for narrow panels
   long long optLongT = 0;        // L of PBWTGPU_WANT_LONGWITHIN
+  long long optStageColumns = 0; // wide panels: stage bit columns in shared memory (measured neutral to slower; off)
   long long optNoSortPass1 = 0;  // testing: pass 1 by sweeping even where the window sort applies
   long long optNoCluster = 0;    // testing: wide panels through the cooperative-grid path even where clusters fit
   // profiling
@@ -241,9 +242,10 @@ struct WindowedSweep {
       W = (int)std::max<long long>(1, std::min<long long>(want, N / minSites));
     }
     if (useGlobal) {
-      // planned for gather mode: the window combine sweeps pseudo-site columns in gather mode whatever the mode here
-      sweep_global_plan(M, ctx->smCount, W, kGather, true, wantMatch, false, 0, !ctx->optNoCluster, &G, &chunk, &W, &gb.cluster,
-                        &gb.stageCol);
+      // (option stage_columns plans room for a staged bit column: every launch with gather-mode columns uses it, and the
+      // window combine sweeps its pseudo-site columns in gather mode whatever the mode here)
+      sweep_global_plan(M, ctx->smCount, W, ctx->optStageColumns ? kGather : kSorted, true, wantMatch, false, 0,
+                        !ctx->optNoCluster, &G, &chunk, &W, &gb.cluster, &gb.stageCol);
     }
     spw = N > 0 ? (N + W - 1) / W : 1;
     W = N > 0 ? (N + spw - 1) / spw : 1;
@@ -582,7 +584,10 @@ struct WindowedSweep {
       int64_t total = 0;
       {
         ScopedTimer t(ctx, PBWTGPU_K_PACK3);
-        CUDA_TRY(ctx, p3_count_columns(yOut, wpc, M, N, colBytes, colBase, ctx->stream));
+        char *scanScratch = nullptr;
+        const size_t scanBytes = p3_scan_scratch_bytes(N);
+        if (int rc = tmp.get(&scanScratch, scanBytes)) return rc;
+        CUDA_TRY(ctx, p3_count_columns(yOut, wpc, M, N, colBytes, colBase, scanScratch, scanBytes, ctx->stream));
         ctx->launches[PBWTGPU_K_PACK3] += (N > 0) + 1;
       }
       CUDA_TRY(ctx, cudaMemcpyAsync(&total, colBase + N, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
@@ -709,6 +714,7 @@ int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value) {
   else if (!strcmp(name, "no_cluster")) ctx->optNoCluster = value;
   else if (!strcmp(name, "long_within")) ctx->optLongT = value;
   else if (!strcmp(name, "no_sort_pass1")) ctx->optNoSortPass1 = value;
+  else if (!strcmp(name, "stage_columns")) ctx->optStageColumns = value;
   else if (!strcmp(name, "debug_no_candidates")) ctx->optNoCandidates = value;
   else return fail(ctx, PBWTGPU_ERR_ARG, "unknown option %s", name);
   return 0;
@@ -1125,7 +1131,7 @@ int pbwtgpu_pack3(pbwtgpu_ctx *ctx, const uint8_t *y, int M, int N, uint8_t **yz
   {
     ScopedTimer t(ctx, PBWTGPU_K_PACK3);
     CUDA_TRY(ctx, bytes_to_bits(yDev, M, N, wpc, ycols, ctx->stream));
-    CUDA_TRY(ctx, p3_count_columns(ycols, wpc, M, N, colBytes, colBase, ctx->stream));
+    CUDA_TRY(ctx, p3_count_columns(ycols, wpc, M, N, colBytes, colBase, nullptr, 0, ctx->stream));
     ctx->launches[PBWTGPU_K_PACK3] += 2 * (N > 0) + 1;
   }
   CUDA_TRY(ctx, cudaMemcpyAsync(&total, colBase + N, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));

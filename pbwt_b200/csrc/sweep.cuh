@@ -66,9 +66,10 @@ struct RecSink {
   const int *tab;       // this window's chunk table (global)
   const int *mirror;    // shared-memory mirror of the newest kTabMirror entries
   int nChunks;          // chunks allocated so far (uniform)
+  int cap;              // entries of the chunk table row (chunks beyond it do not exist: the pool overflowed)
   __device__ __forceinline__ void put(long long o, int4 rec) const {
     const int c = (int)(o >> kRecChunkLog);
-    const int id = (nChunks - c <= kTabMirror) ? mirror[c & (kTabMirror - 1)] : __ldcg(tab + c);
+    const int id = (nChunks - c <= kTabMirror) ? mirror[c & (kTabMirror - 1)] : (c < cap ? __ldcg(tab + c) : -1);
     if (id >= 0) pool[((long long)id << kRecChunkLog) + (o & (kRecChunk - 1))] = rec;
   }
 };

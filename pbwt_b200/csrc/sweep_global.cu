@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
   sink.tab = SCAN && p.chunkTab ? p.chunkTab + (size_t)blockIdx.x * p.poolChunks : nullptr;
   sink.mirror = ctabS;
   sink.nChunks = 0;
+  sink.cap = p.poolChunks;
   long long recBase = 0;  // records produced so far by this CTA (uniform)
   auto ensure_chunks = [&](long long upTo) {
     const int need = (int)((upTo + kRecChunk - 1) >> kRecChunkLog);
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
         for (int c2 = sink.nChunks; c2 < need; ++c2) {
           int id = atomicAdd(p.chunkCounter, 1);
           if (id >= p.poolChunks) id = -1;  // pool exhausted: records are dropped, the host reruns larger
-          p.chunkTab[(size_t)blockIdx.x * p.poolChunks + c2] = id;
+          if (c2 < p.poolChunks) p.chunkTab[(size_t)blockIdx.x * p.poolChunks + c2] = id;  // (the table row ends there)
           ctabS[c2 & (kTabMirror - 1)] = id;
         }
       sink.nChunks = need;

@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
   sink.tab = (MATCH || QUERY) && p.chunkTab ? p.chunkTab + (size_t)win * p.poolChunks : nullptr;
   sink.mirror = ctabS;
   sink.nChunks = 0;
+  sink.cap = p.poolChunks;
   long long recBase = 0;  // records produced so far by this window (uniform)
   long long nmBase = 0;   // "no match" events so far (query sweep)
   uint32_t qWord = (QUERY && tid < p.Q && k0 < k1) ? p.qcols[(size_t)(k0 + colShift) * p.qwpc + warp] : 0u;
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
         for (int c2 = sink.nChunks; c2 < need; ++c2) {
           int id = atomicAdd(p.chunkCounter, 1);
           if (id >= p.poolChunks) id = -1;  // pool exhausted: records are dropped, the host reruns larger
-          p.chunkTab[(size_t)win * p.poolChunks + c2] = id;
+          if (c2 < p.poolChunks) p.chunkTab[(size_t)win * p.poolChunks + c2] = id;  // (the table row ends there)
           ctabS[c2 & (kTabMirror - 1)] = id;
         }
       sink.nChunks = need;
