@@ -61,6 +61,11 @@ int ORC(max_within)(const uint8_t *yz, int64_t nyz, int M, int N, const int32_t 
 int ORC(long_within)(const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *aStart, int T,
                      oracle_match *rec, int64_t cap, int64_t *nrec);
 
+/* pbwtBuildReverse (pbwtCore.c:151-191) on a stored stream: aFend int[M] (= aRstart), the reverse stream zz
+ * (returns -1 if zz_cap is too small; *nzz is the byte count either way) and aRend int[M]. */
+int ORC(build_reverse)(const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *aStart,
+                       int32_t *aFend, uint8_t *zz_out, int64_t zz_cap, int64_t *nzz, int32_t *aRend);
+
 /* N x pbwtCursorForwardsReadAD from a fresh cursor: final a int[M], d int[M+1].
  * pbwtCore.c:543-557. */
 int ORC(sweep_ad)(const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *aStart,

@@ -138,6 +138,21 @@ int ref_long_within(const uint8_t *yz, int64_t nyz, int M, int N, const int32_t 
   return 0;
 }
 
+int ref_build_reverse(const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *aStart,
+                      int32_t *aFend, uint8_t *zz_out, int64_t zz_cap, int64_t *nzz, int32_t *aRend) {
+  ensure_init();
+  PBWT *p = pbwt_from_yz(yz, nyz, M, N, aStart);
+  pbwtBuildReverse(p); /* pbwtCore.c:151 */
+  int rc = 0;
+  *nzz = arrayMax(p->zz);
+  if (*nzz > zz_cap) rc = -1;
+  else if (*nzz) memcpy(zz_out, arrp(p->zz, 0, uchar), *nzz);
+  memcpy(aFend, p->aFend, M * sizeof(int));
+  memcpy(aRend, p->aRend, M * sizeof(int));
+  pbwtDestroy(p);
+  return rc;
+}
+
 int ref_sweep_ad(const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *aStart,
                  int32_t *aEnd, int32_t *dEnd) {
   ensure_init();

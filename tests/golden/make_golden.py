@@ -179,6 +179,27 @@ def long_within_fixture():
     np.savez_compressed(os.path.join(HERE, "long_within.npz"), **out)
 
 
+def reverse_fixture():
+    """pbwt -read X.pbwt -buildReverse -writeReverse R.pbwt through the reference CLI (pbwtBuildReverse, pbwtCore.c:151-191):
+    the reverse file's md5 and its parsed contents (aRstart = aFend, aRend, zz)."""
+    out = {}
+    for name in ("merge1", "merge2", "omni", "mosaic300x400"):
+        g = np.load(os.path.join(HERE, name + ".npz"))
+        M, N = int(g["M"]), int(g["N"])
+        with tempfile.TemporaryDirectory() as td:
+            pb, rv = os.path.join(td, "x.pbwt"), os.path.join(td, "r.pbwt")
+            write_pbwt(pb, M, N, np.arange(M), g["a_end"], g["yz"])
+            subprocess.run([CLI, "-read", pb, "-buildReverse", "-writeReverse", rv], check=True, capture_output=True)
+            raw = open(rv, "rb").read()
+        M2, N2, a_rstart, a_rend, zz = parse_pbwt(raw)
+        lib_fend, lib_zz, lib_rend = O.reference().build_reverse(g["yz"], M, N)
+        assert (a_rstart == g["a_end"]).all() and (lib_fend == a_rstart).all() and (lib_rend == a_rend).all()
+        assert lib_zz.tobytes() == zz.tobytes()
+        out[name + "_zz"], out[name + "_a_rend"], out[name + "_md5"] = zz, a_rend, hashlib.md5(raw).hexdigest()
+        print("reverse", name, "zz", zz.size, out[name + "_md5"])
+    np.savez_compressed(os.path.join(HERE, "reverse.npz"), **out)
+
+
 def main():
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref", "port"], check=True, capture_output=True)
     panel_fixture("merge1", read_vcfq(os.path.join(REF, "test", "merge.1.tab")), with_trace=True)
@@ -189,6 +210,7 @@ def main():
     pack3_fixture()
     query_fixture()
     long_within_fixture()
+    reverse_fixture()
 
 
 if __name__ == "__main__":

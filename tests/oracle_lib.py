@@ -111,6 +111,19 @@ class Oracle:
                                rec.ctypes.data_as(C.c_void_p), C.c_int64(cap), C.byref(n))
         return rec[:cap], n.value
 
+    def build_reverse(self, yz, M, N, a_start=None):
+        """pbwtBuildReverse (pbwtCore.c:151-191) -> (aFend, zz, aRend)."""
+        yz = np.ascontiguousarray(yz, np.uint8)
+        a0 = None if a_start is None else np.ascontiguousarray(a_start, np.int32)
+        cap = M * max(N, 1) + 16
+        zz = np.zeros(cap, np.uint8)
+        a_fend, a_rend = np.zeros(M, np.int32), np.zeros(M, np.int32)
+        n = C.c_int64(0)
+        rc = self._f("build_reverse")(_p(yz, c_u8p), C.c_int64(yz.size), M, N, _p(a0, c_i32p), _p(a_fend, c_i32p),
+                                      _p(zz, c_u8p), C.c_int64(cap), C.byref(n), _p(a_rend, c_i32p))
+        assert rc == 0
+        return a_fend, zz[: n.value].copy(), a_rend
+
     def sweep_ad(self, yz, M, N, a_start=None):
         yz = np.ascontiguousarray(yz, np.uint8)
         a0 = None if a_start is None else np.ascontiguousarray(a_start, np.int32)

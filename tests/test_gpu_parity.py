@@ -335,9 +335,10 @@ def test_wide_panel_small_record_pool(eng, orc):
         eng.set_option("match_capacity", 0)
 
 
+@pytest.mark.parametrize("force_global", [0, 1])
 @pytest.mark.parametrize("M,N,R,W,dens,with_start", [(200, 90, 3, 2, 0.3, False), (1000, 240, 4, 5, 0.05, True), (33, 64, 8, 1, 0.5, False),
                                                       (3000, 400, 2, 7, 0.02, True)])
-def test_site_shards_sequential(eng, orc, M, N, R, W, dens, with_start):
+def test_site_shards_sequential(eng, orc, M, N, R, W, dens, with_start, force_global):
     """The multi-GPU protocol (sites partitioned into R shards: prepare -> gather aggregates -> finish) run
     shard by shard on one GPU: concatenated streams / records and the last shard's a, d equal the sequential sweep."""
     import torch
@@ -352,6 +353,7 @@ def test_site_shards_sequential(eng, orc, M, N, R, W, dens, with_start):
     flags = pbwt_b200.WANT_YZ | pbwt_b200.WANT_MAXWITHIN
     bounds = [N * r // R for r in range(R + 1)]
     eng.set_option("windows", W)
+    eng.set_option("force_global", force_global)  # 1: the wide-panel kernel (what a 1M-haplotype shard runs)
     try:
         panels = [eng.panel_from_host(x[bounds[r]:bounds[r + 1]], M) for r in range(R)]
         shards = [eng.shard_prepare(panels[r], bounds[r], N, flags, a_start=a0) for r in range(R)]
@@ -370,6 +372,7 @@ def test_site_shards_sequential(eng, orc, M, N, R, W, dens, with_start):
             p.free()
     finally:
         eng.set_option("windows", 0)
+        eng.set_option("force_global", 0)
     assert np.concatenate([o["yz"] for o in outs]).tobytes() == yz.tobytes()
     got = np.concatenate([o["matches"] for o in outs])
     assert len(got) == n and (got == rec).all()
@@ -461,7 +464,7 @@ def check_long(eng, orc, hap, L, a_start=None):
     return n
 
 
-@pytest.mark.parametrize("M,N,L,W,dens", [(8, 10, 1, 1, 0.3), (33, 40, 2, 3, 0.5), (500, 64, 4, 5, 0.3), (1000, 90, 6, 1, 0.1),
+@pytest.mark.parametrize("M,N,L,W,dens", [(2, 5, 1, 1, 0.5), (8, 0, 3, 1, 0.3), (9, 1, 1, 1, 0.5), (8, 10, 1, 1, 0.3), (33, 40, 2, 3, 0.5), (500, 64, 4, 5, 0.3), (1000, 90, 6, 1, 0.1),
                                           (3000, 300, 40, 9, 0.05), (10000, 200, 14, 0, 0.5), (12544, 100, 13, 0, 0.4)])
 def test_long_within_random(eng, orc, M, N, L, W, dens):
     rng = np.random.default_rng(M + L)

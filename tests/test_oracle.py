@@ -84,6 +84,17 @@ def test_long_within_port_equals_reference_random():
             assert n1 == n2 and (r1 == r2).all(), (M, N, T)
 
 
+@pytest.mark.parametrize("name", ["merge1", "merge2", "omni", "mosaic300x400"])
+def test_reverse_goldens(name):
+    """pbwtBuildReverse (pbwtCore.c:151-191): the reverse stream and orders written by the reference CLI."""
+    g, r = load(name), load("reverse")
+    M, N = int(g["M"]), int(g["N"])
+    for label, imp in impls():
+        a_fend, zz, a_rend = imp.build_reverse(g["yz"], M, N)
+        assert (a_fend == g["a_end"]).all() and (a_rend == r[name + "_a_rend"]).all(), label
+        assert zz.tobytes() == r[name + "_zz"].tobytes(), label
+
+
 def test_merge1_known_answers():
     """the 34-byte stream, aFend and the first/last MATCH lines."""
     g = load("merge1")
