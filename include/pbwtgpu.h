@@ -141,6 +141,11 @@ int pbwtgpu_max_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, 
  * alleles of site N-1 are consulted). */
 int pbwtgpu_long_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start, int L,
                         int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches, int64_t *nmatch);
+/* pbwtBuildReverse(p) (pbwtCore.c:151-191) over a stored stream: sweeps forwards to aFend (= aRstart), un-sorts every
+ * column on the device, and builds the reverse stream zz (malloc()'d) and aRend from the sites in reverse order.
+ * a_fend may be NULL. */
+int pbwtgpu_build_reverse(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start,
+                          int32_t *a_fend, uint8_t **zz, int64_t *nzz, int32_t *a_rend);
 /* matchSequencesSweep(p, q, report) (pbwtMatch.c:363-443): panel and query streams as stored. */
 int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int M, int N, const int32_t *pa_start,
                         const uint8_t *qyz, int64_t nqyz, int Q, const int32_t *qa_start, pbwtgpu_match **matches,

@@ -7,6 +7,7 @@ the constructors raise.
 Host-side mirror of the reference interface for this path (names as in pbwt.h):
   * ``Engine.build``          <- readers' loop + pbwtCursorWriteForwards  (pbwtIO.c:572-574)
   * ``Engine.max_within``     <- matchMaximalWithin(p, report)            (pbwtMatch.c:115-142)
+  * ``Engine.build_reverse``  <- pbwtBuildReverse(p)                      (pbwtCore.c:151-191)
   * ``Engine.long_within``    <- pbwtLongMatches(p, L), L > 0             (pbwtMatch.c:85-113,148-183)
   * ``Engine.match_sweep``    <- matchSequencesSweep(p, q, report)        (pbwtMatch.c:363-443)
   * ``Engine.pack3/unpack3``  <- pack3 / unpack3                          (pbwtCore.c:254-305)
@@ -80,6 +81,7 @@ def load_library() -> C.CDLL:
         lib.pbwtgpu_build.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_uint, C.POINTER(_vp), C.POINTER(_i64), _vp, _vp,
                                       C.POINTER(_vp), C.POINTER(_i64)]
         lib.pbwtgpu_max_within.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_i64)]
+        lib.pbwtgpu_build_reverse.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, C.POINTER(_vp), C.POINTER(_i64), _vp]
         lib.pbwtgpu_long_within.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, C.POINTER(_vp), C.POINTER(_i64)]
         lib.pbwtgpu_match_sweep.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _i64, C.c_int, _vp, C.POINTER(_vp),
                                             C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_i64)]
@@ -300,6 +302,16 @@ class Engine:
                                                 C.byref(mt) if with_matches else None, C.byref(nm)))
         return {"a_end": a_end, "d_end": d_end,
                 "matches": _take(self.lib, mt, nm.value * 16, MATCH_DTYPE) if with_matches else None}
+
+    def build_reverse(self, yz: np.ndarray, M: int, N: int, a_start=None):
+        """pbwtBuildReverse (pbwtCore.c:151-191) -> (aFend, zz, aRend)."""
+        yz = np.ascontiguousarray(yz, np.uint8)
+        a0 = None if a_start is None else np.ascontiguousarray(a_start, np.int32)
+        zz, nzz = _vp(), _i64(0)
+        a_fend, a_rend = np.zeros(M, np.int32), np.zeros(M, np.int32)
+        self._check(self.lib.pbwtgpu_build_reverse(self.ctx, _ptr(yz), yz.size, M, N, _ptr(a0), _ptr(a_fend), C.byref(zz),
+                                                   C.byref(nzz), _ptr(a_rend)))
+        return a_fend, _take(self.lib, zz, nzz.value, np.uint8), a_rend
 
     def long_within(self, yz: np.ndarray, M: int, N: int, L: int, a_start=None):
         yz = np.ascontiguousarray(yz, np.uint8)

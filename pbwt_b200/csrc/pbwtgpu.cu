@@ -201,6 +201,7 @@ struct WindowedSweep {
   bool sharded = false;
   bool useGlobal = false;
   int W = 1, G = 1, chunk = 0, spw = 1, nodes = 0, bits = 1, slots = 1, cur = 0;
+  uint32_t *xOutRev = nullptr;  // sorted mode: un-sorted columns in reverse site order (pbwtgpu_build_reverse)
   GlobalBuffers gb;  // wide panels: state, exchange and match-scan buffers of sweep_global.cu
   bool matchWanted = false;
   // slot 0 = state entering window 0, slot w+1 = node w (after the scan: the state at the end of window w)
@@ -478,6 +479,7 @@ struct WindowedSweep {
     a.dStart = haveDStart ? dv[cur] : nullptr;
     a.aEnd = res->aEnd; a.dEnd = res->dEnd; a.endOnlyLast = 1;
     a.yOut = yOut;
+    a.xOut = xOutRev;
     a.recCount = recCount; a.chunkCounter = chunkCounter;
     a.reportAtN = 1;
     a.longT = (int)ctx->optLongT;
@@ -952,6 +954,39 @@ int pbwtgpu_max_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, 
   if (!rc) rc = fetch_to_malloc(ctx, res, nullptr, nullptr, a_end, d_end, matches, nmatch);
   pbwtgpu_result_free(ctx, res);
   return rc;
+}
+
+int pbwtgpu_build_reverse(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start,
+                          int32_t *a_fend, uint8_t **zz, int64_t *nzz, int32_t *a_rend) {
+  if (!ctx || nyz < 0 || (nyz > 0 && !yz) || M < 1 || N < 0 || !zz || !nzz || !a_rend)
+    return fail(ctx, PBWTGPU_ERR_ARG, "build_reverse: bad args");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  Temps tmp(ctx);
+  const int wpc = pbwtgpu_words_per_col(M);
+  uint32_t *ycols = nullptr, *xRev = nullptr;
+  if (int rc = decode_stream(ctx, tmp, yz, nyz, M, N, &ycols, nullptr)) return rc;
+  if (int rc = tmp.get(&xRev, (size_t)std::max(N, 1) * wpc)) return rc;
+  CUDA_TRY(ctx, cudaMemsetAsync(xRev, 0, sizeof(uint32_t) * (size_t)std::max(N, 1) * wpc, ctx->stream));
+  std::vector<int32_t> aFend((size_t)M);
+  {  // forwards to the end (pbwtCore.c:159-164), un-sorting every column on the way (:172)
+    pbwtgpu_result *fwd = new pbwtgpu_result;
+    WindowedSweep ws(ctx);
+    int rc = ws.init(ycols, wpc, M, N, kSorted, a_start, false, false, 0, 0);
+    ws.xOutRev = xRev;
+    if (!rc) rc = ws.prepare();
+    if (!rc) rc = ws.finish(0, fwd);
+    if (!rc) rc = pbwtgpu_result_fetch(ctx, fwd, nullptr, aFend.data(), nullptr, nullptr);
+    pbwtgpu_result_free(ctx, fwd);
+    if (rc) return rc;
+  }
+  // the reverse cursor starts from aFend and sweeps the sites backwards (pbwtCore.c:166-176)
+  pbwtgpu_result *rev = new pbwtgpu_result;
+  int rc = run_sweep(ctx, xRev, wpc, M, N, kGather, aFend.data(), PBWTGPU_WANT_YZ, rev);
+  if (!rc) rc = fetch_to_malloc(ctx, rev, zz, nzz, a_rend, nullptr, nullptr, nullptr);
+  pbwtgpu_result_free(ctx, rev);
+  if (rc) return rc;
+  if (a_fend) memcpy(a_fend, aFend.data(), sizeof(int32_t) * (size_t)M);
+  return 0;
 }
 
 int pbwtgpu_long_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start, int L,

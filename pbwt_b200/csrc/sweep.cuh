@@ -36,6 +36,9 @@ struct SweepArgs {
   int endOnlyLast;
   uint32_t *yOut;         // [N][wpc] sorted columns y_k (input to the pack3 encoder), or NULL
   int32_t *cOut;          // [N] zero counts c_k, or NULL
+  uint32_t *xOut;         // sorted mode: [N][wpc] the UN-sorted columns x_k (bit a_k[i] = y_k[i]), written in REVERSE
+                          // site order (row N-1-k): the input of the reverse build (pbwtCore.c:170-175); or NULL.
+                          // Wide-panel kernel: must be zeroed by the caller (bits are OR-ed in)
   // match records: a pool of poolChunks chunks of kRecChunk records handed out through chunkCounter;
   // chunkTab[w*poolChunks + c] = pool chunk holding records [c*kRecChunk, (c+1)*kRecChunk) of window w
   pbwtgpu_match *recPool;  // NULL = count only

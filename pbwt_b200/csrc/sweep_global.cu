@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
       for (int u = 0; u < kBatch; ++u) {
         const int i = posBase + (e0 + u) * 32 + lane;
         const bool valid = e0 + u < EW && i < M;
-        hB[u] = (MODE == kGather && valid) ? __ldcg(aC + i) : 0;
+        hB[u] = ((MODE == kGather || p.xOut) && valid) ? __ldcg(aC + i) : 0;
         dB[u] = (WITH_D && valid) ? __ldcg(dC + i) : 0;
       }
 #pragma unroll
@@ -495,6 +495,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
           const uint32_t vm = (M - base >= 32) ? kFull : (M > base ? ((1u << (M - base)) - 1u) : 0u);
           Bw = cB[u] | ~vm;
         }
+        if (MODE == kSorted && p.xOut && ((Bw >> lane) & 1u) && i < M)  // un-sort: x_k[a_k[i]] = y_k[i], reverse site order
+          atomicOr(&p.xOut[(size_t)(p.N - 1 - (k + colShift)) * wpc + (hB[u] >> 5)], 1u << (hB[u] & 31));
         if (pb == 2u) pb = (~Bw) & 1u;
         const uint32_t H = Bw ^ ((Bw << 1) | pb);
         pb = Bw >> 31;

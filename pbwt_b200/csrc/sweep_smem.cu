@@ -47,7 +47,8 @@ struct SmemLayout {  // offsets in 32-bit words; every array start is 16-byte al
   static constexpr int d1 = d0 + (WITH_D ? MP + 4 : 0);
   static constexpr int ycol = d1 + (WITH_D ? MP + 4 : 0);
   static constexpr int xcol = ycol + WORDS;
-  static constexpr int wsum = xcol + kStages * STAGE;
+  static constexpr int xs = xcol + kStages * STAGE;  // un-sorted column being assembled (XOUT kernels)
+  static constexpr int wsum = xs + WORDS;
   static constexpr int mbar = wsum + 3 * 32;
   static constexpr int wmax = mbar + 8;  // room for up to 4 mbarriers, keeps 16-byte alignment
   static constexpr int cmask = wmax + (MATCH ? WORDS : 0);  // per-word maxima of d (skip structure for long blocks)
@@ -89,7 +90,8 @@ struct SmemState {
 __device__ __forceinline__ uint32_t ybit(const uint32_t *yc, int j) { return (yc[j >> 5] >> (j & 31)) & 1u; }
 
 // MATCH: 0 = none, 1 = matchMaximalWithin (pbwtMatch.c:115-142), 2 = matchLongWithin2 (-longWithin L, pbwtMatch.c:85-113)
-template <int E, int MODE, bool WITH_D, int MATCH, bool QUERY = false>
+// XOUT: also un-sort every column into p.xOut (sorted mode, no d, no matches: the forward half of pbwtBuildReverse)
+template <int E, int MODE, bool WITH_D, int MATCH, bool QUERY = false, bool XOUT = false>
 __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs p) {
   using L = SmemLayout<E, WITH_D, MATCH != 0, QUERY>;
   extern __shared__ __align__(16) uint32_t smem[];
@@ -141,6 +143,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
       sI[L::d1 + i] = 0;
     }
   for (int i = tid; i < kStages * L::STAGE; i += kThreads) smem[L::xcol + i] = kFull;  // pad bits are ones
+  if (XOUT)
+    for (int i = tid; i < L::WORDS; i += kThreads) smem[L::xs + i] = 0u;
   if (QUERY)
     for (int i = tid; i < L::QCAP; i += kThreads) {
       sI[L::qf + i] = 0;  // pbwtMatch.c:368-369: f and d start at zero
@@ -239,6 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
       if (MODE == kGather) Bw = __ballot_sync(kFull, (col[h >> 5] >> (h & 31)) & 1u);
       else Bw = col[wordBase + e];
       B[e] = Bw;
+      if (XOUT && ((Bw >> lane) & 1u) && h < M) atomicOr(&smem[L::xs + (h >> 5)], 1u << (h & 31));  // x_k[a_k[i]] = y_k[i]
       if (e == 0 && warp == 0) pb = (~Bw) & 1u;  // sorted position 0 is always a run head
       const uint32_t H = Bw ^ ((Bw << 1) | pb);
       pb = Bw >> 31;
@@ -326,6 +331,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     }
     __syncthreads();  // S1: ballots, warp sums, match candidates published; everyone is done with col[]
 
+    if (XOUT && tid < wpc) {  // the un-sorted column is complete: hand it over (reverse site order) and clear it
+      p.xOut[(size_t)(p.N - 1 - (k + colShift)) * wpc + tid] = smem[L::xs + tid];
+      smem[L::xs + tid] = 0u;
+    }
     if (tid == 0 && k + kStages < k1) {  // refill the column slot just consumed
       fence_proxy_async();
       mbar_expect_tx(&mbar[stage], colBytes);
@@ -610,8 +619,34 @@ int launch_query_sweep_smem(const SweepArgs &a, cudaStream_t stream) {
   return launch_query_one<13>(a, stream);
 }
 
+template <int E>
+static int launch_xout_one(const SweepArgs &a, cudaStream_t stream) {
+  using L = SmemLayout<E, false, false>;
+  auto kern = sweep_smem_kernel<E, kSorted, false, 0, false, true>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
+  if (err != cudaSuccess) return (int)err;
+  kern<<<a.nWindows, kThreads, L::bytes, stream>>>(a);
+  return (int)cudaGetLastError();
+}
+
+static int launch_xout(const SweepArgs &a, cudaStream_t stream) {
+  const int e = ((a.M + 31) / 32 + 31) / 32;
+  if (e <= 1) return launch_xout_one<1>(a, stream);
+  if (e <= 2) return launch_xout_one<2>(a, stream);
+  if (e <= 4) return launch_xout_one<4>(a, stream);
+  if (e <= 7) return launch_xout_one<7>(a, stream);
+  if (e <= 10) return launch_xout_one<10>(a, stream);
+  if (e <= 13) return launch_xout_one<13>(a, stream);
+  if (e <= 19) return launch_xout_one<19>(a, stream);
+  return launch_xout_one<25>(a, stream);
+}
+
 int launch_sweep_smem(const SweepArgs &a, SweepMode mode, bool with_d, int match_mode, cudaStream_t stream) {
   if (a.M < 1 || a.M > sweep_smem_max_m(with_d || match_mode)) return (int)cudaErrorInvalidValue;
+  if (a.xOut) {
+    if (mode != kSorted || with_d || match_mode) return (int)cudaErrorInvalidValue;
+    return launch_xout(a, stream);
+  }
   if (match_mode == 2 && a.longT < 1) return (int)cudaErrorInvalidValue;
   if (mode == kGather) {
     if (match_mode == 2) return launch_e<kGather, true, 2>(a, stream);

@@ -82,6 +82,33 @@ void pbwtLongMatches (PBWT *p, int L)
     matchMaximalWithin (p, reportMatchLine) ;
 }
 
+/* ---- pbwtBuildReverse (pbwtCore.c:151-191); pbwtCore.c is compiled with -DpbwtBuildReverse=ref_pbwtBuildReverse ---- */
+
+void ref_pbwtBuildReverse (PBWT *p) ;
+
+void pbwtBuildReverse (PBWT *p)
+{
+  uint8_t *zz = 0 ; int64_t nzz = 0 ;
+  int *aFend, *aRend ;
+
+  if (isCheck) { ref_pbwtBuildReverse (p) ; return ; }	/* -check also dumps the reversed haplotypes */
+  aFend = myalloc (p->M, int) ; aRend = myalloc (p->M, int) ;
+  gpuCheck (pbwtgpu_build_reverse (gpuContext (), arrp(p->yz,0,uchar), arrayMax(p->yz), p->M, p->N, p->aFstart,
+				   aFend, &zz, &nzz, aRend), "pbwtgpu_build_reverse") ;
+  if (!p->aFend) p->aFend = aFend ; else free (aFend) ;	/* an aFend read from the file is kept, :157-164 */
+  if (!p->aRstart) p->aRstart = myalloc (p->M, int) ;
+  memcpy (p->aRstart, p->aFend, p->M * sizeof(int)) ;
+  p->zz = arrayReCreate (p->zz, nzz > 0 ? nzz : 1, uchar) ;
+  if (nzz > 0)
+    { array(p->zz, nzz-1, uchar) = 0 ;
+      memcpy (arrp(p->zz,0,uchar), zz, nzz) ;
+    }
+  if (p->aRend) free (p->aRend) ;
+  p->aRend = aRend ;
+  fprintf (logFile, "built reverse PBWT - size %ld\n", arrayMax(p->zz)) ;
+  pbwtgpu_free (zz) ;
+}
+
 /* ---- matchSequencesSweep (pbwtMatch.c:363-443) ---- */
 
 void matchSequencesSweep (PBWT *p, PBWT *q, void (*report)(int ai, int bi, int start, int end))

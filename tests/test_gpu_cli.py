@@ -54,6 +54,18 @@ def test_cli_longwithin_stdout(tmp_path, name, L):
 
 
 @needs_cli
+@pytest.mark.parametrize("name", ["merge1", "omni", "mosaic300x400"])
+def test_cli_build_reverse_file(tmp_path, name):
+    """pbwt_gpu -read X.pbwt -buildReverse -writeReverse R.pbwt writes the reference's reverse file byte for byte."""
+    g, r = np.load(os.path.join(GOLD, name + ".npz")), np.load(os.path.join(GOLD, "reverse.npz"))
+    M, N = int(g["M"]), int(g["N"])
+    pb, rv = tmp_path / "x.pbwt", tmp_path / "r.pbwt"
+    write_pbwt(pb, M, N, np.arange(M), g["a_end"], g["yz"])
+    subprocess.run([CLI, "-read", str(pb), "-buildReverse", "-writeReverse", str(rv)], check=True, capture_output=True)
+    assert hashlib.md5(open(rv, "rb").read()).hexdigest() == str(r[name + "_md5"])
+
+
+@needs_cli
 def test_cli_matchdynamic_stdout_and_log(tmp_path):
     g = np.load(os.path.join(GOLD, "query_sweep.npz"))
     M, Q, N = int(g["M"]), int(g["Q"]), int(g["N"])

@@ -453,7 +453,7 @@ def test_long_within_goldens(eng):
 
 def check_long(eng, orc, hap, L, a_start=None):
     M, N = hap.shape
-    x = O.pack_panel(hap)
+    x = O.pack_panel(hap) if N else np.zeros((0, O.words_per_col(M)), np.uint32)
     yz = orc.build(x, M, N, a_start, with_d=False)[0]
     want, n = orc.long_within(yz, M, N, L, a_start)
     got = eng.long_within(yz, M, N, L, a_start=a_start)  # stored-stream route (the CLI's)
@@ -513,3 +513,40 @@ def test_long_within_wide_panels(eng, orc, M, N, L, no_cluster):
     finally:
         eng.set_option("no_cluster", 0)
     assert n > 0
+
+
+# ---- reverse PBWT (pbwtBuildReverse, pbwtCore.c:151-191) -------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["merge1", "merge2", "omni", "mosaic300x400"])
+def test_build_reverse_goldens(eng, name):
+    g, r = np.load(os.path.join(GOLD, name + ".npz")), np.load(os.path.join(GOLD, "reverse.npz"))
+    M, N = int(g["M"]), int(g["N"])
+    a_fend, zz, a_rend = eng.build_reverse(g["yz"], M, N)
+    assert (a_fend == g["a_end"]).all() and (a_rend == r[name + "_a_rend"]).all()
+    assert zz.tobytes() == r[name + "_zz"].tobytes()
+
+
+@pytest.mark.parametrize("M,N,W,dens,force_global,no_cluster", [
+    (2, 3, 1, 0.5, 0, 0), (8, 0, 1, 0.3, 0, 0), (33, 40, 3, 0.5, 0, 0), (1000, 300, 7, 0.05, 0, 0), (5000, 200, 37, 0.3, 0, 0),
+    (13312, 30, 2, 0.4, 0, 0), (20000, 24, 1, 0.5, 0, 0), (1000, 300, 7, 0.05, 1, 0), (3000, 120, 5, 0.2, 1, 1), (40000, 40, 3, 0.1, 0, 0),
+    (40000, 40, 3, 0.1, 0, 1)])
+def test_build_reverse_random(eng, orc, M, N, W, dens, force_global, no_cluster):
+    """Forward sweep of the stored stream with every column un-sorted on the device, then the build over the sites
+    in reverse order from aFend: aFend, the reverse stream zz and aRend equal the reference's."""
+    rng = np.random.default_rng(M + N + 17)
+    hap = (rng.random((M, N)) < dens).astype(np.uint8)
+    a0 = rng.permutation(M).astype(np.int32) if M % 2 else None
+    x = O.pack_panel(hap) if N else np.zeros((0, O.words_per_col(M)), np.uint32)
+    yz = orc.build(x, M, N, a0, with_d=False)[0]
+    want_fend, want_zz, want_rend = orc.build_reverse(yz, M, N, a0)
+    eng.set_option("windows", W)
+    eng.set_option("force_global", force_global)
+    eng.set_option("no_cluster", no_cluster)
+    try:
+        a_fend, zz, a_rend = eng.build_reverse(yz, M, N, a_start=a0)
+    finally:
+        eng.set_option("windows", 0)
+        eng.set_option("force_global", 0)
+        eng.set_option("no_cluster", 0)
+    assert (a_fend == want_fend).all() and (a_rend == want_rend).all()
+    assert zz.tobytes() == want_zz.tobytes()
