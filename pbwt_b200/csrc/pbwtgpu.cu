@@ -40,6 +40,9 @@ struct pbwtgpu_ctx {
   struct Block { void *p; size_t bytes; };
   std::vector<Block> freeBlocks;
   int smCount = 0;
+  // pinned host scratch for the few counters read back per sweep (one stream synchronisation instead of one per copy)
+  unsigned long long *pinned = nullptr;
+  static constexpr int kPinnedWords = 1024;
 };
 
 struct pbwtgpu_panel {
@@ -485,6 +488,7 @@ struct WindowedSweep {
     a.longT = (int)ctx->optLongT;
     a.debugNoCandidates = (int)ctx->optNoCandidates;
     std::vector<unsigned long long> counts(W, 0);
+    std::vector<long long> offs;  // per-window record offsets: a host temporary that must outlive the last synchronisation
     long long *winNanos = nullptr;
     if (ctx->optWindowTimes) {
       if (int rc = tmp.get(&winNanos, (size_t)std::max(W, 4))) return rc;
@@ -504,6 +508,16 @@ struct WindowedSweep {
       if (int rc = tmp.get(&st, scanTempBytes)) return rc;
       scanTemp = st;
     }
+    // pack3 byte counts are enqueued right behind the sweep, so that one synchronisation returns every counter
+    int32_t *colBytes = nullptr;
+    int64_t *colBase = nullptr;
+    if (wantYz) {
+      if (int rc = tmp.get(&colBytes, (size_t)N + 1)) return rc;
+      if (int rc = tmp.get(&colBase, (size_t)N + 1)) return rc;
+    }
+    // pinned readback layout: [0] chunks used, [1] pack3 bytes, [2] segment total, [3 ...] per-window record counts
+    unsigned long long *pin = ctx->pinned;
+    if (W + 3 > pbwtgpu_ctx::kPinnedWords) return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "too many windows");
     for (int attempt = 0; attempt < 2; ++attempt) {
       if (wantMatch) {
         poolChunks = (int)((recCap + kRecChunk - 1) >> kRecChunkLog) + producers;
@@ -518,24 +532,40 @@ struct WindowedSweep {
         CUDA_TRY(ctx, launch(a, mode, wantD, matchMode));
         ctx->launches[PBWTGPU_K_SWEEP] += 1;
       }
-      if (!wantMatch) break;
-      int used = 0;
-      if (useGlobal) {
-        ScopedTimer t(ctx, PBWTGPU_K_AUX);
-        CUDA_TRY(ctx, launch_segment_scan(gb.segCnt, nSeg, segDst, scanTemp, scanTempBytes, ctx->stream));
-        ctx->launches[PBWTGPU_K_AUX] += 1;
-        CUDA_TRY(ctx, cudaMemcpyAsync(&segTotal, segDst + nSeg - 1, sizeof segTotal, cudaMemcpyDeviceToHost, ctx->stream));
-      } else {
-        CUDA_TRY(ctx, cudaMemcpyAsync(counts.data(), recCount, sizeof(unsigned long long) * W, cudaMemcpyDeviceToHost, ctx->stream));
+      pin[0] = pin[1] = pin[2] = 0;
+      if (wantYz && attempt == 0) {  // (a rerun rewrites the same sorted columns)
+        ScopedTimer t(ctx, PBWTGPU_K_PACK3);
+        char *scanScratch = nullptr;
+        const size_t scanBytes = p3_scan_scratch_bytes(N);
+        if (int rc = tmp.get(&scanScratch, scanBytes)) return rc;
+        CUDA_TRY(ctx, p3_count_columns(yOut, wpc, M, N, colBytes, colBase, scanScratch, scanBytes, ctx->stream));
+        ctx->launches[PBWTGPU_K_PACK3] += (N > 0) + 1;
       }
-      CUDA_TRY(ctx, cudaMemcpyAsync(&used, chunkCounter, sizeof used, cudaMemcpyDeviceToHost, ctx->stream));
-      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      if (wantYz) CUDA_TRY(ctx, cudaMemcpyAsync(&pin[1], colBase + N, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+      if (wantMatch) {
+        if (useGlobal) {
+          ScopedTimer t(ctx, PBWTGPU_K_AUX);
+          CUDA_TRY(ctx, launch_segment_scan(gb.segCnt, nSeg, segDst, scanTemp, scanTempBytes, ctx->stream));
+          ctx->launches[PBWTGPU_K_AUX] += 1;
+          CUDA_TRY(ctx, cudaMemcpyAsync(&pin[2], segDst + nSeg - 1, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+          CUDA_TRY(ctx, cudaMemcpyAsync(&pin[3], recCount, sizeof(unsigned long long) * W, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CUDA_TRY(ctx, cudaMemcpyAsync(&pin[0], chunkCounter, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      }
+      if (wantMatch || wantYz) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      if (!wantMatch) break;
+      const int used = (int)(pin[0] & 0xffffffffull);
+      segTotal = (long long)pin[2];
+      if (!useGlobal)
+        for (int w = 0; w < W; ++w) counts[w] = pin[3 + w];
       if (used <= poolChunks) break;
       if (attempt == 1) return fail(ctx, PBWTGPU_ERR_CUDA, "match record pool overflow persisted");
       long long total = segTotal;  // the pool was too small: every count is known now, size it exactly and rerun
       for (auto cnt : counts) total += (long long)cnt;
       recCap = total;
     }
+    const int64_t yzTotal = (int64_t)pin[1];
     if (winNanos) {
       std::vector<long long> ns(std::max(W, 4));
       CUDA_TRY(ctx, cudaMemcpyAsync(ns.data(), winNanos, sizeof(long long) * ns.size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -557,7 +587,7 @@ struct WindowedSweep {
                                            res->rec, ctx->stream));
       ctx->launches[PBWTGPU_K_AUX] += 1;
     } else if (wantMatch) {
-      std::vector<long long> offs(W, 0);
+      offs.assign(W, 0);
       long long total = 0;
       int maxChunks = 0;
       for (int w = 0; w < W; ++w) {
@@ -575,32 +605,14 @@ struct WindowedSweep {
         CUDA_TRY(ctx, launch_gather_records(pool, chunkTab, poolChunks, offsDev, recCount, W, maxChunks, res->rec, ctx->stream));
         ctx->launches[PBWTGPU_K_AUX] += maxChunks > 0;
       }
-      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // offs is a host temporary
     }
 
     if (wantYz) {
-      int32_t *colBytes = nullptr;
-      int64_t *colBase = nullptr;
-      if (int rc = tmp.get(&colBytes, (size_t)N + 1)) return rc;
-      if (int rc = tmp.get(&colBase, (size_t)N + 1)) return rc;
-      int64_t total = 0;
-      {
-        ScopedTimer t(ctx, PBWTGPU_K_PACK3);
-        char *scanScratch = nullptr;
-        const size_t scanBytes = p3_scan_scratch_bytes(N);
-        if (int rc = tmp.get(&scanScratch, scanBytes)) return rc;
-        CUDA_TRY(ctx, p3_count_columns(yOut, wpc, M, N, colBytes, colBase, scanScratch, scanBytes, ctx->stream));
-        ctx->launches[PBWTGPU_K_PACK3] += (N > 0) + 1;
-      }
-      CUDA_TRY(ctx, cudaMemcpyAsync(&total, colBase + N, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
-      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-      res->nyz = total;
-      if (int rc = result_alloc(ctx, res, &res->yz, (size_t)total)) return rc;
-      {
-        ScopedTimer t(ctx, PBWTGPU_K_PACK3);
-        CUDA_TRY(ctx, p3_emit_columns(yOut, wpc, M, N, colBase, res->yz, ctx->stream));
-        ctx->launches[PBWTGPU_K_PACK3] += (N > 0);
-      }
+      res->nyz = yzTotal;
+      if (int rc = result_alloc(ctx, res, &res->yz, (size_t)yzTotal)) return rc;
+      ScopedTimer t(ctx, PBWTGPU_K_PACK3);
+      CUDA_TRY(ctx, p3_emit_columns(yOut, wpc, M, N, colBase, res->yz, ctx->stream));
+      ctx->launches[PBWTGPU_K_PACK3] += (N > 0);
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // temporaries go back to the cache with this object
     return 0;
@@ -677,6 +689,11 @@ int pbwtgpu_init(int device, pbwtgpu_ctx **out) {
     return PBWTGPU_ERR_CUDA;
   }
   ctx->stream = ctx->ownStream;
+  if (cudaMallocHost((void **)&ctx->pinned, sizeof(unsigned long long) * pbwtgpu_ctx::kPinnedWords) != cudaSuccess) {
+    cudaStreamDestroy(ctx->ownStream);
+    delete ctx;
+    return PBWTGPU_ERR_NOMEM;
+  }
   *out = ctx;
   return 0;
 }
@@ -688,6 +705,7 @@ void pbwtgpu_destroy(pbwtgpu_ctx *ctx) {
   reset_timings(ctx);
   for (auto e : ctx->eventPool) cudaEventDestroy(e);
   for (auto &b : ctx->freeBlocks) cudaFree(b.p);
+  cudaFreeHost(ctx->pinned);
   cudaStreamDestroy(ctx->ownStream);
   delete ctx;
 }
