@@ -26,7 +26,6 @@ struct pbwtgpu_ctx {
   long long optNoCandidates = 0;  // profiling aid
   long long optForceGlobal = 0;  // testing: use the global-memory kernel even for narrow panels
   long long optLongT = 0;        // L of PBWTGPU_WANT_LONGWITHIN
-  long long optStageColumns = 0; // wide panels: stage bit columns in shared memory (measured neutral to slower; off)
   long long optNoSortPass1 = 0;  // testing: pass 1 by sweeping even where the window sort applies
   long long optNoCluster = 0;    // testing: wide panels through the cooperative-grid path even where clusters fit
   // profiling
@@ -246,10 +245,8 @@ struct WindowedSweep {
       W = (int)std::max<long long>(1, std::min<long long>(want, N / minSites));
     }
     if (useGlobal) {
-      // (option stage_columns plans room for a staged bit column: every launch with gather-mode columns uses it, and the
-      // window combine sweeps its pseudo-site columns in gather mode whatever the mode here)
-      sweep_global_plan(M, ctx->smCount, W, ctx->optStageColumns ? kGather : kSorted, true, wantMatch, false, 0,
-                        !ctx->optNoCluster, &G, &chunk, &W, &gb.cluster, &gb.stageCol);
+      sweep_global_plan(M, ctx->smCount, W, kGather, true, wantMatch, false, 0, !ctx->optNoCluster, &G, &chunk, &W, &gb.cluster,
+                        &gb.stageCol);
     }
     spw = N > 0 ? (N + W - 1) / W : 1;
     W = N > 0 ? (N + spw - 1) / spw : 1;
@@ -367,6 +364,13 @@ struct WindowedSweep {
       ScopedTimer t(ctx, PBWTGPU_K_PREPASS);
       CUDA_TRY(ctx, launch_window_sort(src, wpc, M, N, spw, siteOffset, a1.aStart, nodes, T, a1.aEnd, a1.dEnd, ctx->stream));
       ctx->launches[PBWTGPU_K_PREPASS] += 2;
+    } else if (useGlobal && mode == kGather && !ctx->optNoSortPass1 && window_sort_wide_supported(M, spw)) {
+      // wide panels (to ~120k haplotypes): the same sort, one 16-CTA cluster per window (window_sort_wide.cu)
+      uint32_t *T = nullptr;
+      if (int rc = tmp.get(&T, window_sort_wide_scratch_words(M, spw, nodes))) return rc;
+      ScopedTimer t(ctx, PBWTGPU_K_PREPASS);
+      CUDA_TRY(ctx, launch_window_sort_wide(src, wpc, M, N, spw, siteOffset, a1.aStart, nodes, T, a1.aEnd, a1.dEnd, ctx->stream));
+      ctx->launches[PBWTGPU_K_PREPASS] += 3;
     } else {
       ScopedTimer t(ctx, PBWTGPU_K_PREPASS);
       CUDA_TRY(ctx, launch(a1, mode, true, false));
@@ -734,7 +738,6 @@ int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value) {
   else if (!strcmp(name, "no_cluster")) ctx->optNoCluster = value;
   else if (!strcmp(name, "long_within")) ctx->optLongT = value;
   else if (!strcmp(name, "no_sort_pass1")) ctx->optNoSortPass1 = value;
-  else if (!strcmp(name, "stage_columns")) ctx->optStageColumns = value;
   else if (!strcmp(name, "debug_no_candidates")) ctx->optNoCandidates = value;
   else return fail(ctx, PBWTGPU_ERR_ARG, "unknown option %s", name);
   return 0;

@@ -246,7 +246,6 @@ __device__ __forceinline__ int range_max_d(const GlobalState &s, int lo, int hi,
 // Extra arguments of the wide-panel kernel (all device pointers).
 struct GlobalArgs {
   int G, chunk;
-  int stageCol;  // gather mode: the site's bit column is staged in shared memory by a TMA bulk copy
   int32_t *aBuf, *dBuf;
   uint32_t *partials;
   GroupSync *gsync;
@@ -286,10 +285,6 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
   uint32_t *qwS = reinterpret_cast<uint32_t *>(nmS + (QUERY ? kResMax : 0));         // [QW] query column
   int32_t *qzS = reinterpret_cast<int32_t *>(qwS + QW);                              // [QW] zeros before each word
   int32_t *qaS = qzS + QW;                                                           // [2][QW*32] query PBWT order
-  // gather mode: the site's bit column, fetched by one TMA bulk copy per site (a gather straight from global
-  // memory costs one L1 wavefront per distinct 128-byte line, ~28 per warp instruction)
-  uint32_t *colS = reinterpret_cast<uint32_t *>(qaS + 2 * QW * 32);                  // [wpc] (stageCol)
-  __shared__ __align__(8) uint64_t colBar;
   __shared__ int wexS[32];      // zeros in this CTA's warps below each warp
   __shared__ int wsumZ[32];
   __shared__ uint32_t wsumR[32];
@@ -410,12 +405,6 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     recBase += roundTotal;
   };
 
-  const bool stage = MODE == kGather && ga.stageCol;
-  const uint32_t colBytes = (uint32_t)wpc * 4u;
-  if (stage && tid == 0) {
-    mbar_init(&colBar, 1);
-    mbar_fence_init();
-  }
   // ---- window start state ----
   for (int i = p0 + tid; i < p0 + chunk; i += kThreads) {
     if (i < M) {
@@ -424,29 +413,26 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     }
   }
   group_barrier();
-  if (stage && tid == 0 && k0 < k1) {
-    fence_proxy_async();
-    mbar_expect_tx(&colBar, colBytes);
-    tma_load_1d(colS, src + (size_t)(k0 + colShift) * wpc, colBytes, &colBar);
-  }
 
   // debugging aid (option window_times): cycles CTA 0 spends in phase A / exchange / scatter+scans / end barrier
+  // (accumulators in shared memory: held in registers they cost the hot loop ten registers and spills)
+  __shared__ long long tAcc[5];
   const bool timing = p.winNanos != nullptr && blockIdx.x == 0 && tid == 0;
-  long long tAcc[4] = {0, 0, 0, 0}, tPrev = 0;
   auto tick = [&](int slot) {
     if (timing) {
       const long long now = clock64();
-      tAcc[slot] += now - tPrev;
-      tPrev = now;
+      tAcc[slot] += now - tAcc[4];
+      tAcc[4] = now;
     }
   };
-  if (timing) tPrev = clock64();
+  if (timing) {
+    tAcc[0] = tAcc[1] = tAcc[2] = tAcc[3] = 0;
+    tAcc[4] = clock64();
+  }
 
   int cur = 0;
   for (int k = k0; k < k1; ++k) {
-    const uint32_t *colG = src + (size_t)(k + colShift) * wpc;
-    if (stage) mbar_wait(&colBar, (uint32_t)(k - k0) & 1u);
-    const uint32_t *col = stage ? colS : colG;
+    const uint32_t *col = src + (size_t)(k + colShift) * wpc;
     const int32_t *aC = aW + (size_t)cur * MS;
     int32_t *aN = aW + (size_t)(cur ^ 1) * MS;
     const int32_t *dC = WITH_D ? dW + (size_t)cur * (MS + 4) : nullptr;
@@ -460,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     if (posBase == 0 || posBase > M) pb = 2u;  // resolved at the first word: position 0 is a run head
     else if (MODE == kGather) {
       const int hp = __ldcg(aC + posBase - 1);
-      pb = ((stage ? col[hp >> 5] : __ldg(col + (hp >> 5))) >> (hp & 31)) & 1u;
+      pb = (__ldg(col + (hp >> 5)) >> (hp & 31)) & 1u;
     } else pb = __ldg(col + ((posBase - 1) >> 5)) >> 31;
     int zw = 0, carry = 0, lmax = 0;
     bool anyHead = false;
@@ -479,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
       for (int u = 0; u < kBatch; ++u) {
         const int base = posBase + (e0 + u) * 32;
         const bool valid = e0 + u < EW && base + lane < M;
-        if (MODE == kGather) cB[u] = valid ? (stage ? col[hB[u] >> 5] : __ldg(col + (hB[u] >> 5))) : kFull;
+        if (MODE == kGather) cB[u] = valid ? __ldg(col + (hB[u] >> 5)) : kFull;
         else cB[u] = (e0 + u < EW && base < M) ? __ldg(col + (base >> 5)) : 0u;
       }
 #pragma unroll
@@ -543,11 +529,6 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     }
     __syncthreads();
     tick(0);
-    if (stage && tid == 0 && k + 1 < k1) {  // every gather of this site is done: fetch the next site's column
-      fence_proxy_async();
-      mbar_expect_tx(&colBar, colBytes);
-      tma_load_1d(colS, src + (size_t)(k + 1 + colShift) * wpc, colBytes, &colBar);
-    }
 
     // ---------------- exchange: CTA totals out, all partials of the group in ----------------
     int zExLane, zCta;
@@ -993,15 +974,11 @@ static int max_active_clusters(void *kern, int G, size_t smemBytes) {
 // W * G <= maxCtas CTAs synchronised through global memory.
 void sweep_global_plan(int M, int maxCtas, int wantWindows, SweepMode mode, bool with_d, bool match, bool query, int Q,
                        bool allowCluster, int *G, int *chunk, int *W, int *cluster, int *stageCol) {
-  // gather mode stages the site's bit column (wpc words) in shared memory when it leaves room for a useful chunk
-  const int wpc = pbwtgpu_words_per_col(M);
-  int colWords = mode == kGather ? wpc + 4 : 0;
-  int chunkMax = max_chunk(with_d, match, query, Q, colWords);
-  if (colWords && (chunkMax < 4096 || (M + chunkMax - 1) / chunkMax > maxCtas)) {
-    colWords = 0;
-    chunkMax = max_chunk(with_d, match, query, Q, 0);
-  }
-  *stageCol = colWords != 0;
+  // (staging the gather-mode bit column in shared memory by TMA was measured neutral to slower -- the kernel is issue
+  // bound and the gather hits L1 -- and is not done)
+  const int colWords = 0;
+  const int chunkMax = max_chunk(with_d, match, query, Q, colWords);
+  *stageCol = 0;
   const int gmin = (M + chunkMax - 1) / chunkMax;
   int w = wantWindows > 0 ? wantWindows : 1;
   *cluster = 0;
@@ -1041,7 +1018,7 @@ static int launch_any(void *kern, bool cluster, const SweepArgs &a, const Global
   if (err != cudaSuccess) return (int)err;
   SweepArgs args = a;
   GlobalArgs ga{};
-  ga.G = b.G; ga.chunk = b.chunk; ga.stageCol = b.stageCol; ga.aBuf = b.aBuf; ga.dBuf = b.dBuf; ga.partials = b.partials;
+  ga.G = b.G; ga.chunk = b.chunk; ga.aBuf = b.aBuf; ga.dBuf = b.dBuf; ga.partials = b.partials;
   ga.gsync = static_cast<GroupSync *>(b.gsync);
   ga.ySorted = b.ySorted; ga.wmaxG = b.wmaxG; ga.zpre = b.zpre; ga.segCnt = b.segCnt; ga.segSrc = b.segSrc;
   ga.qf = b.qf; ga.qe = b.qe; ga.nmKeys = b.nmKeys;
@@ -1071,7 +1048,7 @@ int launch_sweep_global(const SweepArgs &a, SweepMode mode, bool with_d, int wit
   if (with_match == 2 && a.longT < 1) return (int)cudaErrorInvalidValue;
   if (b.cluster && b.G > 16) return (int)cudaErrorInvalidValue;
   void *kern = b.cluster ? pick_kernel<true>(mode, with_d, with_match, false) : pick_kernel<false>(mode, with_d, with_match, false);
-  const int colWords = (mode == kGather && b.stageCol) ? a.wpc + 4 : 0;
+  const int colWords = 0;
   return launch_any(kern, b.cluster, a, b, a.nWindows * b.G, smem_bytes(b.chunk, with_d, with_match != 0, false, 0, colWords), stream);
 }
 

@@ -44,4 +44,10 @@ size_t window_sort_scratch_words(int M, int spw, int nodes);
 int launch_window_sort(const uint32_t *panel, int wpc, int M, int N, int spw, int siteOffset, const int32_t *aStart, int nodes,
                        uint32_t *scratch, int32_t *ordOut, int32_t *dvOut, cudaStream_t stream);
 
+// The same for wide panels (window_sort_wide.cu): one window = one cluster of 16 CTAs, ids in distributed shared memory.
+bool window_sort_wide_supported(int M, int spw);
+size_t window_sort_wide_scratch_words(int M, int spw, int nodes);
+int launch_window_sort_wide(const uint32_t *panel, int wpc, int M, int N, int spw, int siteOffset, const int32_t *aStart, int nodes,
+                            uint32_t *scratch, int32_t *ordOut, int32_t *dvOut, cudaStream_t stream);
+
 }  // namespace pbwtgpu

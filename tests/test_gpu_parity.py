@@ -278,7 +278,6 @@ def test_global_memory_kernel_forced(eng, orc, M, N, W, dens, no_cluster):
     a0 = rng.permutation(M).astype(np.int32)
     eng.set_option("force_global", 1)
     eng.set_option("no_cluster", no_cluster)
-    eng.set_option("stage_columns", 1 - no_cluster)  # the TMA-staged column variant rides along with the cluster runs
     eng.set_option("windows", W)
     try:
         check_build(eng, orc, x, M, N)
@@ -286,7 +285,6 @@ def test_global_memory_kernel_forced(eng, orc, M, N, W, dens, no_cluster):
     finally:
         eng.set_option("force_global", 0)
         eng.set_option("no_cluster", 0)
-        eng.set_option("stage_columns", 0)
         eng.set_option("windows", 0)
 
 
