@@ -322,6 +322,20 @@ def test_wide_panels_max_within(eng, orc, M, N, dens, W, no_cluster):
         eng.set_option("no_cluster", 0)
 
 
+@pytest.mark.parametrize("M,N,W,no_sort", [(50000, 2000, 7, 0), (125000, 600, 2, 0), (125000, 600, 2, 1), (140000, 300, 2, 0)])
+def test_wide_panel_window_sort(eng, orc, M, N, W, no_sort):
+    """Pass 1 of wide panels as a cluster sort (window_sort_wide.cu; ids in distributed shared memory) up to its
+    shared-memory limit (~127k haplotypes), the sweep beyond it or with no_sort_pass1: same bits either way."""
+    x = O.generate_panel(M, N, seed=0x5EED0031, L=250, mu=M / 50.0)
+    eng.set_option("windows", W)
+    eng.set_option("no_sort_pass1", no_sort)
+    try:
+        check_build(eng, orc, x, M, N, matches=False)
+    finally:
+        eng.set_option("windows", 0)
+        eng.set_option("no_sort_pass1", 0)
+
+
 def test_wide_panel_small_record_pool(eng, orc):
     """The record pool overflows on the first attempt and the sweep is rerun with the exact size."""
     M, N = 16000, 60
