@@ -22,6 +22,7 @@
 // the query sweep over its share of the queries (in query-PBWT order, one warp per query).  Records go to a
 // per-CTA chunked stream; (site, CTA) segment tables put them into callback order afterwards (windows.cu).
 #include <algorithm>
+#include <type_traits>
 
 #include "match_scan.cuh"
 #include "sweep.cuh"
@@ -285,6 +286,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
   uint32_t *qwS = reinterpret_cast<uint32_t *>(nmS + (QUERY ? kResMax : 0));         // [QW] query column
   int32_t *qzS = reinterpret_cast<int32_t *>(qwS + QW);                              // [QW] zeros before each word
   int32_t *qaS = qzS + QW;                                                           // [2][QW*32] query PBWT order
+  // the same arrays as indices into smem[] for the hot loops (accesses through the derived pointers above are
+  // compiled as generic loads/stores with a per-access shared-window conversion in cluster kernels)
+  const int oY = 0, oDn = chunkWords, oWmax = oDn + (WITH_D ? chunk : 0), oZloc = oWmax + (SCAN ? chunkWords : 0) + (MATCH ? chunkWords : 0);
   __shared__ int wexS[32];      // zeros in this CTA's warps below each warp
   __shared__ int wsumZ[32];
   __shared__ uint32_t wsumR[32];
@@ -451,31 +455,37 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     int zw = 0, carry = 0, lmax = 0;
     bool anyHead = false;
     int patchIdx = -1;  // CTA-local index (word*32+lane) of the warp's first run head, held by that lane only
-    for (int e0 = 0; e0 < EW; e0 += kBatch) {  // kBatch words in flight per warp: the loads are L2 round trips
+    // kBatch words in flight per warp: the loads are L2 round trips.  FULL batches (entirely inside the warp's words
+    // and below M: all but the last one) carry no validity predicates.
+    auto phaseA_batch = [&](auto fullTag, const int e0) {
+      constexpr bool FULL = decltype(fullTag)::value;
       int hB[kBatch], dB[kBatch];
       uint32_t cB[kBatch];
+      const unsigned iBase = (unsigned)(posBase + e0 * 32 + lane);
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
-        const int i = posBase + (e0 + u) * 32 + lane;
-        const bool valid = e0 + u < EW && i < M;
+        const unsigned i = iBase + u * 32;
+        const bool valid = FULL || (e0 + u < EW && (int)i < M);
         hB[u] = ((MODE == kGather || p.xOut) && valid) ? __ldcg(aC + i) : 0;
         dB[u] = (WITH_D && valid) ? __ldcg(dC + i) : 0;
       }
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
         const int base = posBase + (e0 + u) * 32;
-        const bool valid = e0 + u < EW && base + lane < M;
-        if (MODE == kGather) cB[u] = valid ? __ldg(col + (hB[u] >> 5)) : kFull;
-        else cB[u] = (e0 + u < EW && base < M) ? __ldg(col + (base >> 5)) : 0u;
+        const bool valid = FULL || (e0 + u < EW && base + lane < M);
+        if (MODE == kGather) cB[u] = valid ? __ldg(col + ((unsigned)hB[u] >> 5)) : kFull;
+        else cB[u] = (FULL || (e0 + u < EW && base < M)) ? __ldg(col + ((unsigned)base >> 5)) : 0u;
       }
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
         const int e = e0 + u;
-        if (e >= EW) break;
+        if (!FULL && e >= EW) break;
         const int i = posBase + e * 32 + lane;
         uint32_t Bw;
         if (MODE == kGather) {
           Bw = __ballot_sync(kFull, (cB[u] >> (hB[u] & 31)) & 1u);
+        } else if (FULL) {
+          Bw = cB[u];
         } else {
           const int base = posBase + e * 32;
           const uint32_t vm = (M - base >= 32) ? kFull : (M > base ? ((1u << (M - base)) - 1u) : 0u);
@@ -486,14 +496,14 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
         if (pb == 2u) pb = (~Bw) & 1u;
         const uint32_t H = Bw ^ ((Bw << 1) | pb);
         pb = Bw >> 31;
-        if (lane == 0) ycolS[wordBase + e] = Bw;
-        if (QUERY && lane == 0) zlocS[wordBase + e] = zw;  // zeros of this warp before the word
+        if (lane == 0) smem[oY + wordBase + e] = Bw;
+        if (QUERY && lane == 0) smem[oZloc + wordBase + e] = (uint32_t)zw;  // zeros of this warp before the word
         if (WITH_D) {
           int dv = dB[u];
           if (i == 0) dv = k + 1;  // sentinel d[0] (pbwtCore.c:414,507)
           if (SCAN) {  // word maximum of d: lets the match scans skip long blocks 1024 positions per step
             const int wm = __reduce_max_sync(kFull, dv);
-            if (lane == 0) wmaxS[wordBase + e] = wm;
+            if (lane == 0) smem[oWmax + wordBase + e] = (uint32_t)wm;
           }
           int dnv = dv;
           if (H == 0u) {
@@ -517,10 +527,14 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
             }
             carry = __shfl_sync(kFull, v, 31);
           }
-          dnS[(wordBase + e) * 32 + lane] = dnv;
+          smem[oDn + (wordBase + e) * 32 + lane] = (uint32_t)dnv;
         }
         zw += __popc(~Bw);
       }
+    };
+    for (int e0 = 0; e0 < EW; e0 += kBatch) {
+      if (e0 + kBatch <= EW && posBase + (e0 + kBatch) * 32 <= M) phaseA_batch(std::true_type{}, e0);
+      else phaseA_batch(std::false_type{}, e0);
     }
     if (WITH_D) carry = max(carry, __reduce_max_sync(kFull, lmax));
     if (lane == 0) {
@@ -638,32 +652,36 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     // ---------------- phase C: scatter ----------------
     {
       int zacc = zIn;
-      for (int e0 = 0; e0 < EW; e0 += kBatch) {
+      auto phaseC_batch = [&](auto fullTag, const int e0) {
+        constexpr bool FULL = decltype(fullTag)::value;
         int hB[kBatch];
+        const unsigned iBase = (unsigned)(p0 + (wordBase + e0) * 32 + lane);
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
-          const int i = p0 + (wordBase + e0 + u) * 32 + lane;
-          hB[u] = (e0 + u < EW && i < M) ? __ldcg(aC + i) : 0;
+          const unsigned i = iBase + u * 32;
+          hB[u] = (FULL || (e0 + u < EW && (int)i < M)) ? __ldcg(aC + i) : 0;
         }
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
           const int e = e0 + u;
-          if (e >= EW) break;
+          if (!FULL && e >= EW) break;
           const int li = (wordBase + e) * 32 + lane;
           const int i = p0 + li;
-          const uint32_t Bw = ycolS[wordBase + e];
-          if (i < M) {
-            const int z = zacc + __popc(~Bw & ltMask);
-            const int pos = (Bw & laneBit) ? c + i - z : z;
-            aN[pos] = hB[u];
-            if (WITH_D) {
-              int dv = dnS[li];
-              if (li == patchIdx) dv = max(dv, cIn);
-              dN[pos] = dv;
-            }
+          const uint32_t Bw = smem[oY + wordBase + e];
+          const int z = zacc + __popc(~Bw & ltMask);
+          const unsigned pos = (unsigned)((Bw & laneBit) ? c + i - z : z);
+          if (FULL || i < M) aN[pos] = hB[u];
+          if (WITH_D) {
+            int dv = (int)smem[oDn + li];
+            if (li == patchIdx) dv = max(dv, cIn);
+            if (FULL || i < M) dN[pos] = dv;
           }
           zacc += __popc(~Bw);
         }
+      };
+      for (int e0 = 0; e0 < EW; e0 += kBatch) {
+        if (e0 + kBatch <= EW && p0 + (wordBase + e0 + kBatch) * 32 <= M) phaseC_batch(std::true_type{}, e0);
+        else phaseC_batch(std::false_type{}, e0);
       }
     }
     if (p.yOut) {  // sorted column k, pad bits cleared
