@@ -364,12 +364,20 @@ struct WindowedSweep {
       ScopedTimer t(ctx, PBWTGPU_K_PREPASS);
       CUDA_TRY(ctx, launch_window_sort(src, wpc, M, N, spw, siteOffset, a1.aStart, nodes, T, a1.aEnd, a1.dEnd, ctx->stream));
       ctx->launches[PBWTGPU_K_PREPASS] += 2;
-    } else if (useGlobal && mode == kGather && !ctx->optNoSortPass1 && window_sort_wide_supported(M, spw)) {
+    } else if (useGlobal && mode == kGather && !ctx->optNoSortPass1 && !ctx->optNoCluster && window_sort_wide_supported(M, spw)) {
       // wide panels (to ~120k haplotypes): the same sort, one 16-CTA cluster per window (window_sort_wide.cu)
       uint32_t *T = nullptr;
       if (int rc = tmp.get(&T, window_sort_wide_scratch_words(M, spw, nodes))) return rc;
       ScopedTimer t(ctx, PBWTGPU_K_PREPASS);
       CUDA_TRY(ctx, launch_window_sort_wide(src, wpc, M, N, spw, siteOffset, a1.aStart, nodes, T, a1.aEnd, a1.dEnd, ctx->stream));
+      ctx->launches[PBWTGPU_K_PREPASS] += 3;
+    } else if (useGlobal && mode == kGather && !ctx->optNoSortPass1 && window_sort_global_supported(M, nodes, ctx->smCount)) {
+      // wider still: the sort with its elements in global memory, a group of co-resident CTAs per window
+      uint32_t *T = nullptr;
+      if (int rc = tmp.get(&T, window_sort_global_scratch_words(M, spw, nodes, ctx->smCount))) return rc;
+      ScopedTimer t(ctx, PBWTGPU_K_PREPASS);
+      CUDA_TRY(ctx, launch_window_sort_global(src, wpc, M, N, spw, siteOffset, a1.aStart, nodes, ctx->smCount, T, a1.aEnd, a1.dEnd,
+                                              ctx->stream));
       ctx->launches[PBWTGPU_K_PREPASS] += 3;
     } else {
       ScopedTimer t(ctx, PBWTGPU_K_PREPASS);

@@ -46,9 +46,11 @@ __global__ void __launch_bounds__(256) transpose_wide_kernel(const uint32_t *pan
     const int h = (hw0 + u) * 32 + lane;
     if (h < M) {
       Trow[((size_t)win * M + h) * nw + qw] = mine;
+      if (T8) {
 #pragma unroll
-      for (int b = 0; b < 4; ++b)
-        if (4 * qw + b < nq8) T8[((size_t)win * nq8 + 4 * qw + b) * mpad + h] = (uint8_t)(mine >> (8 * b));
+        for (int b = 0; b < 4; ++b)
+          if (4 * qw + b < nq8) T8[((size_t)win * nq8 + 4 * qw + b) * mpad + h] = (uint8_t)(mine >> (8 * b));
+      }
     }
   }
 }
@@ -185,6 +187,164 @@ __global__ void __launch_bounds__(kThreads, 1) window_sort_cluster_kernel(const 
   }
 }
 
+// ---- very wide panels (beyond the cluster's shared memory): the same sort with the elements in global memory ----
+// One window = a group of G co-resident CTAs (cooperative launch, as in sweep_global.cu), CTA g ranks the elements at
+// sorted positions [g*chunk, (g+1)*chunk).  Elements are (id, 32 key bits) pairs in an L2-resident double buffer;
+// the key word is refreshed from the row-major keys every fourth pass; per-CTA digit totals go through a small
+// global table; two group barriers per pass.
+struct SortGroupSync {
+  unsigned int arrive;
+  unsigned int pad[31];
+};
+
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) window_sort_global_kernel(const uint32_t *Trow, int nw, int M, int N, int spw,
+                                                                         const int32_t *aStart, uint2 *bufAll,
+                                                                         uint32_t *ctaTotAll, SortGroupSync *gsync, int G,
+                                                                         int chunk, int32_t *ordOut) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint16_t *hist = reinterpret_cast<uint16_t *>(smem);                    // [32 warps][256 digits]
+  uint32_t *digBase = smem + 32 * 256 / 2;                                // [256]
+  uint16_t *offS = reinterpret_cast<uint16_t *>(digBase + 256);           // [chunk] rank of each element inside its warp
+  __shared__ uint32_t warpTot[32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int win = blockIdx.x / G, g = blockIdx.x % G;
+  const int k0 = win * spw, k1 = min(N, k0 + spw);
+  const int nDigits = (k1 - k0 + 7) / 8;
+  const size_t MS = (size_t)G * chunk;
+  uint2 *cur = bufAll + (size_t)win * 2 * MS, *nxt = cur + MS;
+  uint32_t *ctaTot = ctaTotAll + (size_t)win * G * 256;
+  SortGroupSync *gs = gsync + win;
+  const uint32_t *Tw = Trow + (size_t)win * M * nw;
+  const uint32_t ltMask = lanemask_lt(lane);
+  const int EW = chunk / 1024;                     // words per warp
+  const int posBase = g * chunk + warp * EW * 32;  // first sorted position of this warp
+  unsigned epoch = 0;
+
+  auto group_barrier = [&]() {
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(&gs->arrive, 1u);
+      const unsigned target = (epoch + 1) * (unsigned)G;
+      while (ld_volatile_u32(&gs->arrive) < target) {}
+      __threadfence();
+    }
+    ++epoch;
+    __syncthreads();
+  };
+
+  for (int i = g * chunk + tid; i < (g + 1) * chunk; i += kThreads)
+    if (i < M) cur[i] = make_uint2((uint32_t)(aStart ? aStart[i] : i), 0u);
+  for (int i = tid; i < 32 * 256 / 2; i += kThreads) smem[i] = 0u;
+  group_barrier();
+
+  for (int t = 0; t < nDigits; ++t) {
+    const int shift = (t & 3) * 8;
+    // ---- P1: digits, ranks inside the warp, per-warp histogram (words in order: stable) ----
+    for (int e0 = 0; e0 < EW; e0 += 4) {
+      uint2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = posBase + (e0 + u) * 32 + lane;
+        v[u] = (e0 + u < EW && i < M) ? __ldcg(cur + i) : make_uint2(kPadId, 0xffffffffu);
+      }
+      if (shift == 0) {  // a new key word every fourth pass
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = posBase + (e0 + u) * 32 + lane;
+          if (e0 + u < EW && i < M) {
+            v[u].y = __ldg(Tw + (size_t)v[u].x * nw + (t >> 2));
+            cur[i].y = v[u].y;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (e0 + u >= EW) break;
+        const int i = posBase + (e0 + u) * 32 + lane;
+        const bool valid = i < M;
+        const uint32_t digit = valid ? (v[u].y >> shift) & 255u : 256u;
+        const unsigned peers = __match_any_sync(kFull, digit);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) {
+          old = hist[warp * 256 + digit];
+          hist[warp * 256 + digit] = (uint16_t)(old + __popc(peers));
+        }
+        __syncwarp();
+        old = __shfl_sync(kFull, old, leader);
+        offS[(warp * EW + e0 + u) * 32 + lane] = (uint16_t)(old + __popc(peers & ltMask));
+      }
+    }
+    __syncthreads();
+    // ---- P2a: per digit, this CTA's total and the exclusive prefix over its warps; totals to the group's table ----
+    if (tid < 256) {
+      uint32_t run = 0;
+#pragma unroll 8
+      for (int w = 0; w < 32; ++w) {
+        const uint32_t c = hist[w * 256 + tid];
+        hist[w * 256 + tid] = (uint16_t)run;
+        run += c;
+      }
+      ctaTot[g * 256 + tid] = run;
+    }
+    group_barrier();
+    // ---- P2b: global base of this CTA's elements of each digit ----
+    if (tid < 256) {
+      uint32_t colSum = 0, before = 0;
+      for (int c = 0; c < G; ++c) {
+        const uint32_t x = __ldcg(ctaTot + c * 256 + tid);
+        colSum += x;
+        if (c < g) before += x;
+      }
+      uint32_t inc = colSum;
+#pragma unroll
+      for (int dl = 1; dl < 32; dl <<= 1) {
+        const uint32_t x = __shfl_up_sync(kFull, inc, dl);
+        if (lane >= dl) inc += x;
+      }
+      if (lane == 31) warpTot[warp] = inc;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      uint32_t wb = 0;
+      for (int w = 0; w < warp; ++w) wb += warpTot[w];
+      digBase[tid] = wb + inc - colSum + before;
+    }
+    __syncthreads();
+    // ---- P3: stable scatter ----
+    for (int e0 = 0; e0 < EW; e0 += 4) {
+      uint2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = posBase + (e0 + u) * 32 + lane;
+        v[u] = (e0 + u < EW && i < M) ? __ldcg(cur + i) : make_uint2(kPadId, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = posBase + (e0 + u) * 32 + lane;
+        if (e0 + u < EW && i < M) {
+          const uint32_t digit = (v[u].y >> shift) & 255u;
+          const uint32_t pos = digBase[digit] + (uint32_t)hist[warp * 256 + digit] + (uint32_t)offS[(warp * EW + e0 + u) * 32 + lane];
+          nxt[pos] = v[u];
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < 32 * 256 / 2; i += kThreads) smem[i] = 0u;
+    group_barrier();  // every element of the pass has landed (and the totals table may be rewritten)
+    uint2 *sw = cur; cur = nxt; nxt = sw;
+  }
+  int32_t *ord = ordOut + (size_t)win * M;
+  for (int i = g * chunk + tid; i < (g + 1) * chunk; i += kThreads)
+    if (i < M) ord[i] = (int32_t)__ldcg(cur + i).x;
+}
+
 // divergence of neighbours in the sorted order: 1 + the most recent site at which their key rows differ
 __global__ void __launch_bounds__(256) neighbour_lcp_kernel(const uint32_t *Trow, int nw, int M, int N, int spw, int siteOffset,
                                                             const int32_t *ordAll, int32_t *dvAll) {
@@ -250,6 +410,60 @@ int row_words(int spw) { return (spw + 31) / 32; }
 int padded_m16(int M) { return (M + 15) / 16 * 16; }  // whole 16-byte units per digit column (TMA bulk copy)
 
 }  // namespace
+
+// plan of the global-memory variant: G CTAs of `chunk` positions per window, all W windows co-resident
+static void global_sort_plan(int M, int maxCtas, int W, int *G, int *chunk) {
+  int g = std::max(1, maxCtas / std::max(W, 1));
+  int ch = ((M + g - 1) / g + 1023) / 1024 * 1024;
+  if (ch > 32768) ch = 32768;
+  g = (M + ch - 1) / ch;
+  *G = g; *chunk = ch;
+}
+
+bool window_sort_global_supported(int M, int W, int maxCtas) {
+  int G, chunk;
+  global_sort_plan(M, maxCtas, W, &G, &chunk);
+  return M >= 2 && (long long)W * G <= maxCtas && (long long)M < (long long)kPadId;
+}
+
+size_t window_sort_global_scratch_words(int M, int spw, int W, int maxCtas) {
+  int G, chunk;
+  global_sort_plan(M, maxCtas, W, &G, &chunk);
+  const size_t MS = (size_t)G * chunk;
+  return (size_t)W * M * row_words(spw) + (size_t)W * 2 * MS * 2 + (size_t)W * G * 256 + (size_t)W * 32 + 256;
+}
+
+int launch_window_sort_global(const uint32_t *panel, int wpc, int M, int N, int spw, int siteOffset, const int32_t *aStart, int W,
+                              int maxCtas, uint32_t *scratch, int32_t *ordOut, int32_t *dvOut, cudaStream_t stream) {
+  if (W <= 0) return 0;
+  int G, chunk;
+  global_sort_plan(M, maxCtas, W, &G, &chunk);
+  const int nw = row_words(spw);
+  const size_t MS = (size_t)G * chunk;
+  uint32_t *Trow = scratch;
+  uint2 *buf = reinterpret_cast<uint2 *>(scratch + (((size_t)W * M * nw + 3) / 4) * 4);
+  uint32_t *ctaTot = reinterpret_cast<uint32_t *>(buf + (size_t)W * 2 * MS);
+  SortGroupSync *gsync = reinterpret_cast<SortGroupSync *>(ctaTot + (size_t)W * G * 256);
+  {
+    dim3 grid((spw + 31) / 32, (wpc + 31) / 32, W);
+    transpose_wide_kernel<<<grid, 256, 0, stream>>>(panel, wpc, M, N, spw, 0, 0, nw, nullptr, Trow);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaMemsetAsync(gsync, 0, sizeof(SortGroupSync) * (size_t)W, stream);
+    if (err != cudaSuccess) return (int)err;
+  }
+  const size_t smemBytes = 32 * 256 * 2 + 256 * 4 + (size_t)chunk * 2;
+  void *kern = (void *)window_sort_global_kernel;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+  if (err != cudaSuccess) return (int)err;
+  void *params[] = {&Trow, (void *)&nw, &M, &N, &spw, &aStart, &buf, &ctaTot, &gsync, &G, &chunk, &ordOut};
+  err = cudaLaunchCooperativeKernel(kern, dim3(W * G), dim3(kThreads), params, smemBytes, stream);
+  if (err != cudaSuccess) return (int)err;
+  {
+    dim3 grid((M + 1 + 255) / 256, W);
+    neighbour_lcp_kernel<<<grid, 256, 0, stream>>>(Trow, nw, M, N, spw, siteOffset, ordOut, dvOut);
+  }
+  return (int)cudaGetLastError();
+}
 
 bool window_sort_wide_supported(int M, int spw) {
   if (M < 2 || (long long)M >= (long long)kPadId) return false;

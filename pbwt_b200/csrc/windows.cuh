@@ -50,4 +50,11 @@ size_t window_sort_wide_scratch_words(int M, int spw, int nodes);
 int launch_window_sort_wide(const uint32_t *panel, int wpc, int M, int N, int spw, int siteOffset, const int32_t *aStart, int nodes,
                             uint32_t *scratch, int32_t *ordOut, int32_t *dvOut, cudaStream_t stream);
 
+// Panels too wide for the cluster (window_sort_wide.cu, global-memory variant): W windows, each sorted by a group of
+// co-resident CTAs (cooperative launch, W * G <= maxCtas), elements in an L2-resident double buffer.
+bool window_sort_global_supported(int M, int W, int maxCtas);
+size_t window_sort_global_scratch_words(int M, int spw, int W, int maxCtas);
+int launch_window_sort_global(const uint32_t *panel, int wpc, int M, int N, int spw, int siteOffset, const int32_t *aStart, int W,
+                              int maxCtas, uint32_t *scratch, int32_t *ordOut, int32_t *dvOut, cudaStream_t stream);
+
 }  // namespace pbwtgpu
