@@ -434,14 +434,51 @@ struct WindowedSweep {
     int32_t *P[2];
     if (int rc = tmp.get(&P[0], AI)) return rc;
     if (int rc = tmp.get(&P[1], AI)) return rc;
-    CUDA_TRY(ctx, cudaMemcpyAsync(P[0], aggs, sizeof(int32_t) * AI, cudaMemcpyDeviceToDevice, ctx->stream));
     int pc = 0;
-    for (int r = 1; r < rank; ++r) {  // P = P (+) Z_r
-      const int32_t *Z = aggs + (size_t)r * AI;
-      if (int rc = combine(1, P[pc], P[pc] + M, true, Z + 2 * M + 1, Z + 3 * M + 1, P[pc ^ 1], P[pc ^ 1] + M,
-                           P[pc ^ 1] + 2 * M + 1, P[pc ^ 1] + 3 * M + 1))
-        return rc;
-      pc ^= 1;
+    if (rank >= 3 && rank - 1 <= std::max(W, 1)) {
+      // P = Z_0 (+) ... (+) Z_{rank-1} by an inclusive Hillis-Steele scan over the earlier shards' aggregates
+      // (ceil(log2 rank) combine launches instead of rank-1 dependent ones); the last node is the state entering this shard
+      const size_t R = (size_t)rank;
+      int32_t *sO[2], *sD[2], *sG[2], *sF[2];
+      uint32_t *keysP = nullptr, *keysSaved = keys;
+      for (int b = 0; b < 2; ++b) {
+        if (int rc = tmp.get(&sO[b], R * M)) return rc;
+        if (int rc = tmp.get(&sD[b], R * (M + 1))) return rc;
+        if (int rc = tmp.get(&sG[b], R * M)) return rc;
+        if (int rc = tmp.get(&sF[b], R * M)) return rc;
+      }
+      if (int rc = tmp.get(&keysP, R * bits * wpc)) return rc;
+      const size_t pitch = sizeof(int32_t) * AI;
+      CUDA_TRY(ctx, cudaMemcpy2DAsync(sO[0], sizeof(int32_t) * M, aggs, pitch, sizeof(int32_t) * M, R, cudaMemcpyDeviceToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpy2DAsync(sD[0], sizeof(int32_t) * (M + 1), aggs + M, pitch, sizeof(int32_t) * (M + 1), R, cudaMemcpyDeviceToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpy2DAsync(sG[0], sizeof(int32_t) * M, aggs + 2 * M + 1, pitch, sizeof(int32_t) * M, R, cudaMemcpyDeviceToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpy2DAsync(sF[0], sizeof(int32_t) * M, aggs + 3 * M + 1, pitch, sizeof(int32_t) * M, R, cudaMemcpyDeviceToDevice, ctx->stream));
+      keys = keysP;
+      int sc = 0;
+      for (size_t stride = 1; stride < R; stride *= 2) {
+        const int sn = sc ^ 1;
+        const int cnt = (int)(R - stride);
+        const int rc = combine(cnt, sO[sc], sD[sc], false, sG[sc] + stride * M, sF[sc] + stride * M, sO[sn] + stride * M,
+                               sD[sn] + stride * (M + 1), sG[sn] + stride * M, sF[sn] + stride * M);
+        if (rc) { keys = keysSaved; return rc; }
+        CUDA_TRY(ctx, cudaMemcpyAsync(sO[sn], sO[sc], sizeof(int32_t) * M * stride, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(sD[sn], sD[sc], sizeof(int32_t) * (M + 1) * stride, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(sG[sn], sG[sc], sizeof(int32_t) * M * stride, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(sF[sn], sF[sc], sizeof(int32_t) * M * stride, cudaMemcpyDeviceToDevice, ctx->stream));
+        sc = sn;
+      }
+      keys = keysSaved;
+      CUDA_TRY(ctx, cudaMemcpyAsync(P[0], sO[sc] + (R - 1) * M, sizeof(int32_t) * M, cudaMemcpyDeviceToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(P[0] + M, sD[sc] + (R - 1) * (M + 1), sizeof(int32_t) * (M + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+      CUDA_TRY(ctx, cudaMemcpyAsync(P[0], aggs, sizeof(int32_t) * AI, cudaMemcpyDeviceToDevice, ctx->stream));
+      for (int r = 1; r < rank; ++r) {  // P = P (+) Z_r
+        const int32_t *Z = aggs + (size_t)r * AI;
+        if (int rc = combine(1, P[pc], P[pc] + M, true, Z + 2 * M + 1, Z + 3 * M + 1, P[pc ^ 1], P[pc ^ 1] + M,
+                             P[pc ^ 1] + 2 * M + 1, P[pc ^ 1] + 3 * M + 1))
+          return rc;
+        pc ^= 1;
+      }
     }
     const int nxt = cur ^ 1;
     if (int rc = combine(nodes, P[pc], P[pc] + M, true, g[cur] + oA(), gfd[cur] + oA(), ord[nxt] + oA(), dv[nxt] + oD(),
