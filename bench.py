@@ -141,7 +141,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     eng = P.Engine(local_rank)
-    stream = torch.cuda.current_stream()
+    # an explicit (non-default) stream: the engine's kernels, the CUDA events and the NCCL all-gather are all ordered on it
+    # (the legacy default stream has handle 0, which pbwtgpu_set_stream reads as "use the context's own stream")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     eng.profile(True)
 

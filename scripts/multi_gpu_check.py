@@ -9,7 +9,9 @@ rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 torch.cuda.set_device(lr)
 eng = P.Engine(lr)
-eng.set_stream(torch.cuda.current_stream().cuda_stream)
+stream = torch.cuda.Stream()  # explicit stream: kernels and the NCCL all-gather are ordered on it (handle 0 would mean "own stream")
+torch.cuda.set_stream(stream)
+eng.set_stream(stream.cuda_stream)
 M, Ns = 6000, 4000
 flags = P.WANT_YZ | P.WANT_MAXWITHIN
 pnl = eng.panel_synthetic(M, Ns, seed=0x5EED0004, L=500, mu=3.0, first_site=rank * Ns)
