@@ -78,6 +78,79 @@ __global__ void __launch_bounds__(1024) make_groups_kernel(const int32_t *ordAll
   }
 }
 
+// The same for panels of up to 16 Ki haplotypes in ONE pass: every thread keeps its (up to 16) positions in registers,
+// the loads of all chunks are in flight together, and the ranks come from per-(chunk, warp) ballot counts with a single
+// scan -- two block barriers instead of three per 1024 positions.
+constexpr int kGroupsFastChunks = 16;
+
+__global__ void __launch_bounds__(1024) make_groups_fast_kernel(const int32_t *ordAll, int32_t *dvAll, const int32_t *gJAll,
+                                                                const int32_t *gfdJAll, int32_t *gAll, int32_t *gfdAll, int M) {
+  __shared__ int wcnt[kGroupsFastChunks * 32];
+  const int node = blockIdx.x;
+  const int32_t *ord = ordAll + (size_t)node * M;
+  int32_t *dv = dvAll + (size_t)node * (M + 1);
+  const int32_t *gJ = gJAll ? gJAll + (size_t)node * M : nullptr;
+  const int32_t *gfdJ = gfdJAll ? gfdJAll + (size_t)node * M : nullptr;
+  int32_t *g = gAll + (size_t)node * M;
+  int32_t *gfd = gfdAll + (size_t)node * M;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nChunks = (M + 1023) / 1024;
+  int h[kGroupsFastChunks], d[kGroupsFastChunks];
+#pragma unroll
+  for (int c = 0; c < kGroupsFastChunks; ++c) {
+    const int i = c * 1024 + tid;
+    const bool valid = c < nChunks && i < M;
+    h[c] = valid ? ord[i] : 0;
+    d[c] = (valid && i > 0) ? dv[i] : 0;
+  }
+#pragma unroll
+  for (int c = 0; c < kGroupsFastChunks; ++c)
+    if (d[c] >= kPseudoLabelBase) {  // separated by a pseudo-site: different groups of the later window
+      d[c] = gfdJ[gJ[h[c]]];
+      dv[c * 1024 + tid] = d[c];
+    }
+#pragma unroll
+  for (int c = 0; c < kGroupsFastChunks; ++c) {
+    if (c < nChunks) {  // uniform
+      const int i = c * 1024 + tid;
+      const unsigned bal = __ballot_sync(kFull, i < M && (i == 0 || d[c] != 0));
+      if (lane == 0) wcnt[c * 32 + warp] = __popc(bal);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of the nChunks*32 counts in position order; lane l owns nChunks consecutive entries
+    int sum = 0;
+    for (int j = 0; j < nChunks; ++j) sum += wcnt[lane * nChunks + j];
+    int inc = sum;
+#pragma unroll
+    for (int dl = 1; dl < 32; dl <<= 1) {
+      const int t = __shfl_up_sync(kFull, inc, dl);
+      if (lane >= dl) inc += t;
+    }
+    int run = inc - sum;
+    for (int j = 0; j < nChunks; ++j) {
+      const int v = wcnt[lane * nChunks + j];
+      wcnt[lane * nChunks + j] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+  const unsigned ltMask = (1u << lane) - 1u;
+#pragma unroll
+  for (int c = 0; c < kGroupsFastChunks; ++c) {
+    const int i = c * 1024 + tid;
+    if (c < nChunks) {  // uniform
+      const bool flag = i < M && (i == 0 || d[c] != 0);
+      const unsigned bal = __ballot_sync(kFull, flag);  // (recomputed rather than kept: 16 more registers would spill)
+      if (i < M) {
+        const int rank = wcnt[c * 32 + warp] + __popc(bal & ltMask) + (flag ? 1 : 0) - 1;  // inclusive count of group heads, minus one
+        g[h[c]] = rank;
+        if (flag) gfd[rank] = d[c];
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) key_bits_kernel(const int32_t *gAll, int M, int bits, int wpc, uint32_t *out) {
   const int lane = threadIdx.x & 31;
   const int nWords = (M + 31) / 32;
@@ -162,7 +235,10 @@ __global__ void iota_u32_kernel(uint32_t *out, long long n) {
 
 int launch_make_groups(const int32_t *ord, int32_t *dv, const int32_t *gJ, const int32_t *gfdJ, int32_t *g, int32_t *gfd,
                        int M, int nodes, cudaStream_t stream) {
-  if (nodes > 0) make_groups_kernel<<<nodes, 1024, 0, stream>>>(ord, dv, gJ, gfdJ, g, gfd, M);
+  if (nodes > 0) {
+    if (M <= kGroupsFastChunks * 1024) make_groups_fast_kernel<<<nodes, 1024, 0, stream>>>(ord, dv, gJ, gfdJ, g, gfd, M);
+    else make_groups_kernel<<<nodes, 1024, 0, stream>>>(ord, dv, gJ, gfdJ, g, gfd, M);
+  }
   return (int)cudaGetLastError();
 }
 
