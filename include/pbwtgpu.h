@@ -61,7 +61,10 @@ const char *pbwtgpu_last_error(pbwtgpu_ctx *ctx);
 int pbwtgpu_set_stream(pbwtgpu_ctx *ctx, void *cuda_stream);
 void *pbwtgpu_get_stream(pbwtgpu_ctx *ctx);
 int pbwtgpu_synchronize(pbwtgpu_ctx *ctx);
-/* Tuning knobs (0 = automatic): number of site windows swept concurrently, match-record capacity. */
+/* Options (0 = automatic / off).  Tuning: "windows" (site windows swept concurrently), "match_capacity" (records the
+ * first attempt allows for), "long_within" (L of PBWTGPU_WANT_LONGWITHIN).  Testing and profiling aids: "force_global"
+ * (wide-panel kernels on narrow panels), "no_cluster" (cooperative-grid groups where clusters would fit),
+ * "no_sort_pass1" (window nodes by sweeping instead of sorting), "window_times", "debug_no_candidates". */
 int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value);
 /* Per-kernel-class device times of the last sweep (ms, CUDA events on the launching stream) and
  * launch counts; arrays of PBWTGPU_NUM_KERNEL_CLASSES. */

@@ -245,8 +245,7 @@ struct WindowedSweep {
       W = (int)std::max<long long>(1, std::min<long long>(want, N / minSites));
     }
     if (useGlobal) {
-      sweep_global_plan(M, ctx->smCount, W, kGather, true, wantMatch, false, 0, !ctx->optNoCluster, &G, &chunk, &W, &gb.cluster,
-                        &gb.stageCol);
+      sweep_global_plan(M, ctx->smCount, W, kGather, true, wantMatch, false, 0, !ctx->optNoCluster, &G, &chunk, &W, &gb.cluster);
     }
     spw = N > 0 ? (N + W - 1) / W : 1;
     W = N > 0 ? (N + spw - 1) / spw : 1;
@@ -620,8 +619,8 @@ struct WindowedSweep {
       CUDA_TRY(ctx, cudaMemcpyAsync(ns.data(), winNanos, sizeof(long long) * ns.size(), cudaMemcpyDeviceToHost, ctx->stream));
       CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
       if (useGlobal)
-        fprintf(stderr, "[pbwtgpu] wide kernel, CTA 0, cycles per site (%d sites, G=%d chunk=%d W=%d cluster=%d stage=%d): phase A %.0f, exchange %.0f, scatter+scans %.0f, end barrier %.0f\n",
-                spw, G, chunk, W, gb.cluster, gb.stageCol, (double)ns[0] / spw, (double)ns[1] / spw, (double)ns[2] / spw, (double)ns[3] / spw);
+        fprintf(stderr, "[pbwtgpu] wide kernel, CTA 0, cycles per site (%d sites, G=%d chunk=%d W=%d cluster=%d): phase A %.0f, exchange %.0f, scatter+scans %.0f, end barrier %.0f\n",
+                spw, G, chunk, W, gb.cluster, (double)ns[0] / spw, (double)ns[1] / spw, (double)ns[2] / spw, (double)ns[3] / spw);
       else {
         fprintf(stderr, "[pbwtgpu] pass-2 window times (us) and records:");
         for (int w = 0; w < W; ++w) fprintf(stderr, " %d:%.0f/%llu", w, ns[w] * 1e-3, counts[w]);
@@ -1086,7 +1085,7 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
   char *scanTemp = nullptr;
   size_t scanTempBytes = 0;
   if (wide) {
-    sweep_global_plan(M, ctx->smCount, 1, kSorted, true, false, true, Q, !ctx->optNoCluster, &G, &chunk, &Wd, &gb.cluster, &gb.stageCol);
+    sweep_global_plan(M, ctx->smCount, 1, kSorted, true, false, true, Q, !ctx->optNoCluster, &G, &chunk, &Wd, &gb.cluster);
     const size_t MS = (size_t)G * chunk;
     gb.G = G; gb.chunk = chunk;
     nSeg = (long long)(N + 1) * G + 1;

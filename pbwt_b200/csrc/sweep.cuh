@@ -93,7 +93,7 @@ int launch_query_sweep_smem(const SweepArgs &args, cudaStream_t stream);
 // plan: G CTAs per window and their chunk of sorted positions, W = windows swept concurrently, and whether each
 // group is a thread-block cluster (M <= 16 * 32768) or part of a cooperative grid (W * G <= maxCtas)
 void sweep_global_plan(int M, int maxCtas, int wantWindows, SweepMode mode, bool with_d, bool match, bool query, int Q,
-                       bool allowCluster, int *G, int *chunk, int *W, int *cluster, int *stageCol);
+                       bool allowCluster, int *G, int *chunk, int *W, int *cluster);
 size_t sweep_global_state_ints(int G, int chunk, int W, bool with_d);  // a (and d) double buffers, in int32
 size_t sweep_global_sync_bytes(int W);
 size_t sweep_global_column_words(int G, int chunk, int W);  // words of ySorted / wmaxG / zpre (double buffered)
@@ -101,8 +101,7 @@ size_t sweep_global_column_words(int G, int chunk, int W);  // words of ySorted 
 // zeroed before every launch.
 struct GlobalBuffers {
   int G = 1, chunk = 0;
-  int cluster = 0;   // groups are thread-block clusters (sweep_global_plan)
-  int stageCol = 0;  // gather mode: bit columns are staged in shared memory (sweep_global_plan)
+  int cluster = 0;  // groups are thread-block clusters (sweep_global_plan)
   int32_t *aBuf = nullptr, *dBuf = nullptr;  // sweep_global_state_ints
   uint32_t *partials = nullptr;
   void *gsync = nullptr;

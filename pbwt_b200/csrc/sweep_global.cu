@@ -991,12 +991,11 @@ static int max_active_clusters(void *kern, int G, size_t smemBytes) {
 // window (hardware barriers, exchange through distributed shared memory); wider ones a cooperative grid of
 // W * G <= maxCtas CTAs synchronised through global memory.
 void sweep_global_plan(int M, int maxCtas, int wantWindows, SweepMode mode, bool with_d, bool match, bool query, int Q,
-                       bool allowCluster, int *G, int *chunk, int *W, int *cluster, int *stageCol) {
+                       bool allowCluster, int *G, int *chunk, int *W, int *cluster) {
   // (staging the gather-mode bit column in shared memory by TMA was measured neutral to slower -- the kernel is issue
   // bound and the gather hits L1 -- and is not done)
   const int colWords = 0;
   const int chunkMax = max_chunk(with_d, match, query, Q, colWords);
-  *stageCol = 0;
   const int gmin = (M + chunkMax - 1) / chunkMax;
   int w = wantWindows > 0 ? wantWindows : 1;
   *cluster = 0;
