@@ -144,6 +144,12 @@ int pbwtgpu_max_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, 
  * alleles of site N-1 are consulted). */
 int pbwtgpu_long_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start, int L,
                         int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches, int64_t *nmatch);
+/* Compatibility path for callers that walk a PbwtCursor themselves (pbwt.h:74-87): the cursor's state ENTERING site k
+ * of a stored stream, i.e. after k x pbwtCursorForwardsReadAD (pbwtCore.c:543-557): a[M], d[M+1] (sentinels k+1) and,
+ * for k < N, the sorted column y[M] with its zero count *c (u->y, u->c).  One device sweep per call: meant for jumping
+ * to a site, not for stepping.  Any of y, a, d, c may be NULL. */
+int pbwtgpu_cursor_at(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start, int k,
+                      uint8_t *y, int32_t *a, int32_t *d, int32_t *c);
 /* pbwtBuildReverse(p) (pbwtCore.c:151-191) over a stored stream: sweeps forwards to aFend (= aRstart), un-sorts every
  * column on the device, and builds the reverse stream zz (malloc()'d) and aRend from the sites in reverse order.
  * a_fend may be NULL. */

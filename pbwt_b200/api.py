@@ -81,6 +81,7 @@ def load_library() -> C.CDLL:
         lib.pbwtgpu_build.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_uint, C.POINTER(_vp), C.POINTER(_i64), _vp, _vp,
                                       C.POINTER(_vp), C.POINTER(_i64)]
         lib.pbwtgpu_max_within.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_i64)]
+        lib.pbwtgpu_cursor_at.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp]
         lib.pbwtgpu_build_reverse.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, C.POINTER(_vp), C.POINTER(_i64), _vp]
         lib.pbwtgpu_long_within.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, C.POINTER(_vp), C.POINTER(_i64)]
         lib.pbwtgpu_match_sweep.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _i64, C.c_int, _vp, C.POINTER(_vp),
@@ -302,6 +303,14 @@ class Engine:
                                                 C.byref(mt) if with_matches else None, C.byref(nm)))
         return {"a_end": a_end, "d_end": d_end,
                 "matches": _take(self.lib, mt, nm.value * 16, MATCH_DTYPE) if with_matches else None}
+
+    def cursor_at(self, yz: np.ndarray, M: int, N: int, k: int, a_start=None):
+        """State of a PbwtCursor entering site k of a stored stream -> (y or None, a, d, c or None)."""
+        yz = np.ascontiguousarray(yz, np.uint8)
+        a0 = None if a_start is None else np.ascontiguousarray(a_start, np.int32)
+        y, a, d, c = np.zeros(M, np.uint8), np.zeros(M, np.int32), np.zeros(M + 1, np.int32), np.zeros(1, np.int32)
+        self._check(self.lib.pbwtgpu_cursor_at(self.ctx, _ptr(yz), yz.size, M, N, _ptr(a0), k, _ptr(y), _ptr(a), _ptr(d), _ptr(c)))
+        return (y, a, d, int(c[0])) if k < N else (None, a, d, None)
 
     def build_reverse(self, yz: np.ndarray, M: int, N: int, a_start=None):
         """pbwtBuildReverse (pbwtCore.c:151-191) -> (aFend, zz, aRend)."""

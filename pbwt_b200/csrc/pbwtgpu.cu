@@ -1021,6 +1021,35 @@ int pbwtgpu_max_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, 
   return rc;
 }
 
+int pbwtgpu_cursor_at(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start, int k,
+                      uint8_t *y, int32_t *a, int32_t *d, int32_t *c) {
+  if (!ctx || nyz < 0 || (nyz > 0 && !yz) || M < 1 || N < 0 || k < 0 || k > N) return fail(ctx, PBWTGPU_ERR_ARG, "cursor_at: bad args");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  Temps tmp(ctx);
+  const int wpc = pbwtgpu_words_per_col(M);
+  uint32_t *ycols = nullptr;
+  int32_t *zc = nullptr;
+  if (int rc = tmp.get(&zc, (size_t)N + 1)) return rc;
+  if (int rc = decode_stream(ctx, tmp, yz, nyz, M, N, &ycols, zc)) return rc;
+  // state entering site k = the result of sweeping the first k sorted columns (pbwtCursorForwardsReadAD x k)
+  pbwtgpu_result *res = new pbwtgpu_result;
+  int rc = run_sweep(ctx, ycols, wpc, M, k, kSorted, a_start, PBWTGPU_WANT_D, res);
+  if (!rc) rc = pbwtgpu_result_fetch(ctx, res, nullptr, a, d, nullptr);
+  pbwtgpu_result_free(ctx, res);
+  if (rc) return rc;
+  if (k < N) {  // the column the cursor holds there, and its zero count (u->y, u->c)
+    if (y) {
+      uint8_t *yDev = nullptr;
+      if (int rc2 = tmp.get(&yDev, (size_t)M)) return rc2;
+      CUDA_TRY(ctx, bits_to_bytes(ycols + (size_t)k * wpc, M, 1, wpc, yDev, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(y, yDev, (size_t)M, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (c) CUDA_TRY(ctx, cudaMemcpyAsync(c, zc + k, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
 int pbwtgpu_build_reverse(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start,
                           int32_t *a_fend, uint8_t **zz, int64_t *nzz, int32_t *a_rend) {
   if (!ctx || nyz < 0 || (nyz > 0 && !yz) || M < 1 || N < 0 || !zz || !nzz || !a_rend)

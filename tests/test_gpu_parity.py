@@ -562,3 +562,18 @@ def test_build_reverse_random(eng, orc, M, N, W, dens, force_global, no_cluster)
         eng.set_option("no_cluster", 0)
     assert (a_fend == want_fend).all() and (a_rend == want_rend).all()
     assert zz.tobytes() == want_zz.tobytes()
+
+
+def test_cursor_at_matches_trace(eng, orc):
+    """pbwtgpu_cursor_at: (y, a, d, c) of the cursor entering site k of a stored stream = the reference's per-site
+    trace (state after k x pbwtCursorForwardsReadAD), at the ends and inside / across window boundaries."""
+    M, N = 700, 900
+    x = O.generate_panel(M, N, seed=0x5EED0041, L=120, mu=5.0)
+    a0 = np.random.default_rng(3).permutation(M).astype(np.int32)
+    yz = orc.build(x, M, N, a0, with_d=False)[0]
+    a_tr, d_tr, y_tr, c_tr = orc.trace(x, M, N, a0)
+    for k in (0, 1, 255, 256, 257, 600, N - 1, N):
+        y, a, d, c = eng.cursor_at(yz, M, N, k, a_start=a0)
+        assert (a == a_tr[k]).all() and (d == d_tr[k]).all(), k
+        if k < N:
+            assert (y == y_tr[k]).all() and c == c_tr[k], k
