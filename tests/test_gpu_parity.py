@@ -577,3 +577,26 @@ def test_cursor_at_matches_trace(eng, orc):
         assert (a == a_tr[k]).all() and (d == d_tr[k]).all(), k
         if k < N:
             assert (y == y_tr[k]).all() and c == c_tr[k], k
+
+
+def test_error_codes(eng, orc):
+    """Bad arguments and unsupported shapes come back as error codes with a message (the host shim turns them into the
+    reference's die()); nothing falls back to a CPU path."""
+    M, N = 64, 20
+    hap = (np.random.default_rng(1).random((M, N)) < 0.3).astype(np.uint8)
+    yz = orc.build(O.pack_panel(hap), M, N, with_d=False)[0]
+    with pytest.raises(pbwt_b200.PbwtGpuError, match="invalid argument"):
+        eng.long_within(yz, M, N, 0)  # L must be >= 1 (pbwtMatch.c:153)
+    with pytest.raises(pbwt_b200.PbwtGpuError, match="invalid argument"):
+        eng.cursor_at(yz, M, N, N + 1)
+    with pytest.raises(pbwt_b200.PbwtGpuError, match="decodes to"):
+        eng.max_within(yz[:-3], M, N)  # truncated stream: the reference's isCheck assertion (pbwtCore.c:301-302)
+    qyz = orc.build(O.pack_panel(np.zeros((9000, N), np.uint8)), 9000, N, with_d=False)[0]
+    with pytest.raises(pbwt_b200.PbwtGpuError, match="unsupported shape"):
+        eng.match_sweep(yz, M, N, qyz, 9000)  # more than 8,192 queries per call
+    with pytest.raises(pbwt_b200.PbwtGpuError, match="unknown option"):
+        eng.set_option("no_such_option", 1)
+    # the context is still usable afterwards
+    got = eng.max_within(yz, M, N)
+    rec, n = orc.max_within(yz, M, N)
+    assert len(got["matches"]) == n and (got["matches"] == rec).all()
