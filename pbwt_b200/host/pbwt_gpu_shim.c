@@ -11,7 +11,7 @@
  * The readers of pbwtIO.c are batched onto the GPU by two more renames applied to pbwtIO.c only (see
  * gpuReaderWriteForwards below).
  * Errors follow the reference's convention: die() (utils.c:31-44).  There is no CPU fallback for the
- * GPU-backed paths; options this shim does not accelerate (-check, -stats) are passed to
+ * GPU-backed paths; options this shim does not accelerate (-check, -stats with -longWithin) are passed to
  * the reference's renamed originals and say so on the log.
  */
 #include "pbwt.h"
@@ -65,9 +65,37 @@ void pbwtLongMatches (PBWT *p, int L)
 {
   if (!p || !p->yz) die ("option -longWithin called without a PBWT") ;
   if (L < 0) die ("L %d for longWithin must be >= 0", L) ;
-  if (isCheck || isStats)
-    { fprintf (logFile, "pbwt_gpu: -check / -stats run the reference CPU path\n") ;
+  if (isCheck || (isStats && L))
+    { fprintf (logFile, "pbwt_gpu: -check (and -stats with -longWithin) run the reference CPU path\n") ;
       ref_pbwtLongMatches (p, L) ;
+      return ;
+    }
+  if (isStats)			/* -stats -maxWithin: histogram of the reporters' match lengths instead of MATCH lines
+				   (pbwtMatch.c:130-131, 161-178), from the GPU's records */
+    { pbwtgpu_match *rec = 0 ;
+      int64_t n = 0, i = 0 ;
+      Array hist = arrayCreate (1000000, int) ;
+      int nTot = 0, len ;
+      long hTot = 0 ;
+      gpuCheck (pbwtgpu_max_within (gpuContext (), arrp(p->yz,0,uchar), arrayMax(p->yz), p->M, p->N,
+				    p->aFstart, 0, 0, &rec, &n), "pbwtgpu_max_within") ;
+      while (i < n)		/* one reporter = a run of records with the same ai and end; its length is the longer
+				   of its two blocks' (k - min(d[i],d[i+1])) */
+	{ int ai = rec[i].ai, end = rec[i].end, best = 0 ;
+	  for ( ; i < n && rec[i].ai == ai && rec[i].end == end ; ++i)
+	    if (rec[i].end - rec[i].start > best) best = rec[i].end - rec[i].start ;
+	  ++array(hist, best, int) ;
+	}
+      for (len = 0 ; len < arrayMax(hist) ; ++len)
+	if (arr(hist, len, int))
+	  { nTot += arr(hist, len, int) ;
+	    hTot += arr(hist, len, int) * len ;
+	    printf ("%d\t%d\n", len, arr(hist, len, int)) ;
+	  }
+      fprintf (logFile, "Average %.1f matches per sample\n", nTot/(double)p->M) ;
+      fprintf (logFile, "Average length %.1f\n", hTot/(double)nTot) ;
+      arrayDestroy (hist) ;
+      pbwtgpu_free (rec) ;
       return ;
     }
   if (L)			/* matchLongWithin2 (pbwtMatch.c:85-113) */

@@ -66,6 +66,23 @@ def test_cli_build_reverse_file(tmp_path, name):
 
 
 @needs_cli
+@pytest.mark.parametrize("name,md5,log", [
+    ("merge1", "8d1029f275f8c490f3c50923db651419", ["Average 2.9 matches per sample", "Average length 4.9"]),
+    ("omni", "3efa4cec8b933c7a984c8b96cae7e035", ["Average 4.0 matches per sample", "Average length 20.7"]),
+    ("mosaic300x400", "a6e0ff75052b0c53c1e193a479eb6965", ["Average 12.4 matches per sample", "Average length 69.8"])])
+def test_cli_stats_maxwithin(tmp_path, name, md5, log):
+    """pbwt_gpu -stats -read X.pbwt -maxWithin: the length histogram and the two summary lines of the reference
+    (stdout md5s and log lines recorded from the reference CLI, `pbwt -log L -stats -read X.pbwt -maxWithin`)."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    M, N = int(g["M"]), int(g["N"])
+    pb, lg = tmp_path / "x.pbwt", tmp_path / "log"
+    write_pbwt(pb, M, N, np.arange(M), g["a_end"], g["yz"])
+    out = subprocess.run([CLI, "-log", str(lg), "-stats", "-read", str(pb), "-maxWithin"], check=True, capture_output=True).stdout
+    assert hashlib.md5(out).hexdigest() == md5
+    assert [ln for ln in open(lg).read().splitlines() if ln.startswith("Average")] == log
+
+
+@needs_cli
 def test_cli_matchdynamic_stdout_and_log(tmp_path):
     g = np.load(os.path.join(GOLD, "query_sweep.npz"))
     M, Q, N = int(g["M"]), int(g["Q"]), int(g["N"])
