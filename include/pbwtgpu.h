@@ -64,7 +64,8 @@ int pbwtgpu_synchronize(pbwtgpu_ctx *ctx);
 /* Options (0 = automatic / off).  Tuning: "windows" (site windows swept concurrently), "match_capacity" (records the
  * first attempt allows for), "long_within" (L of PBWTGPU_WANT_LONGWITHIN).  Testing and profiling aids: "force_global"
  * (wide-panel kernels on narrow panels), "no_cluster" (cooperative-grid groups where clusters would fit),
- * "no_sort_pass1" (window nodes by sweeping instead of sorting), "window_times", "debug_no_candidates". */
+ * "no_sort_pass1" (window nodes by sweeping instead of sorting), "equal_windows" (no shortening of the panel's edge
+ * windows), "window_times", "debug_no_candidates". */
 int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value);
 /* Per-kernel-class device times of the last sweep (ms, CUDA events on the launching stream) and
  * launch counts; arrays of PBWTGPU_NUM_KERNEL_CLASSES. */

@@ -26,6 +26,7 @@ struct pbwtgpu_ctx {
   long long optNoCandidates = 0;  // profiling aid
   long long optForceGlobal = 0;  // testing: use the global-memory kernel even for narrow panels
   long long optLongT = 0;        // L of PBWTGPU_WANT_LONGWITHIN
+  long long optEqualWindows = 0; // testing / profiling: equal windows even where the edge windows would be shortened
   long long optNoSortPass1 = 0;  // testing: pass 1 by sweeping even where the window sort applies
   long long optNoCluster = 0;    // testing: wide panels through the cooperative-grid path even where clusters fit
   // profiling
@@ -203,6 +204,7 @@ struct WindowedSweep {
   bool sharded = false;
   bool useGlobal = false;
   int W = 1, G = 1, chunk = 0, spw = 1, nodes = 0, bits = 1, slots = 1, cur = 0;
+  int firstSites = 0, secondSites = 0;  // > 0: sites of windows 0 and 1; the last window takes what remains (window_range)
   uint32_t *xOutRev = nullptr;  // sorted mode: un-sorted columns in reverse site order (pbwtgpu_build_reverse)
   GlobalBuffers gb;  // wide panels: state, exchange and match-scan buffers of sweep_global.cu
   bool matchWanted = false;
@@ -249,6 +251,17 @@ struct WindowedSweep {
     }
     spw = N > 0 ? (N + W - 1) / W : 1;
     W = N > 0 ? (N + spw - 1) / spw : 1;
+    // A whole panel swept with matches: its first windows (everything still matches back to site 0) and its last one
+    // (every block is reported at site N) carry 10-17 % more work per site than the others (option window_times), so
+    // windows 0 / 1 / last get about 80 / 92 / 74 % of the sites of an inner window.
+    // (shared-memory kernel; shards and wide panels keep equal windows)
+    if (!useGlobal && !sharded && wantMatch && W >= 8 && !ctx->optEqualWindows) {
+      for (int s = (int)(N / (W - 0.54)), tries = 0; tries < 4; ++s, ++tries) {  // smallest s whose last window is no longer than s
+        const int first = (int)(0.80 * s + 0.5), second = (int)(0.92 * s + 0.5);
+        const long long last = (long long)N - first - second - (long long)(W - 3) * s;
+        if (s >= 16 && first >= 1 && second >= 1 && last >= 1 && last <= s) { spw = s; firstSites = first; secondSites = second; break; }
+      }
+    }
     nodes = sharded ? W : W - 1;  // a shard also needs the node of its last window (its aggregate)
     slots = nodes + 1;
     bits = 1;
@@ -349,7 +362,8 @@ struct WindowedSweep {
   int prepare() {
     if (nodes <= 0) return 0;
     SweepArgs a1{};
-    a1.src = src; a1.wpc = wpc; a1.M = M; a1.N = N; a1.sitesPerWindow = spw; a1.nWindows = nodes;
+    a1.src = src; a1.wpc = wpc; a1.M = M; a1.N = N; a1.sitesPerWindow = spw; a1.firstWindowSites = firstSites; a1.secondWindowSites = secondSites;
+    a1.nWindows = nodes;
     a1.siteOffset = siteOffset; a1.nTotal = nTotal;
     a1.aStart = positionSpace ? iota : ord[0]; a1.aStartShared = 1;
     a1.aEnd = ord[0] + oA(); a1.dEnd = dv[0] + oD();
@@ -361,7 +375,7 @@ struct WindowedSweep {
       uint32_t *T = nullptr;
       if (int rc = tmp.get(&T, window_sort_scratch_words(M, spw, nodes))) return rc;
       ScopedTimer t(ctx, PBWTGPU_K_PREPASS);
-      CUDA_TRY(ctx, launch_window_sort(src, wpc, M, N, spw, siteOffset, a1.aStart, nodes, T, a1.aEnd, a1.dEnd, ctx->stream));
+      CUDA_TRY(ctx, launch_window_sort(src, wpc, M, N, spw, firstSites, secondSites, siteOffset, a1.aStart, nodes, T, a1.aEnd, a1.dEnd, ctx->stream));
       ctx->launches[PBWTGPU_K_PREPASS] += 2;
     } else if (useGlobal && mode == kGather && !ctx->optNoSortPass1 && !ctx->optNoCluster && window_sort_wide_supported(M, spw)) {
       // wide panels (to ~120k haplotypes): the same sort, one 16-CTA cluster per window (window_sort_wide.cu)
@@ -524,7 +538,7 @@ struct WindowedSweep {
     }
     SweepArgs a{};
     a.src = src; a.wpc = wpc; a.M = M; a.N = N;
-    a.sitesPerWindow = spw; a.nWindows = W;
+    a.sitesPerWindow = spw; a.firstWindowSites = firstSites; a.secondWindowSites = secondSites; a.nWindows = W;
     a.siteOffset = siteOffset; a.nTotal = nTotal;
     a.aStart = ord[cur];
     a.dStart = haveDStart ? dv[cur] : nullptr;
@@ -782,6 +796,7 @@ int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value) {
   else if (!strcmp(name, "no_cluster")) ctx->optNoCluster = value;
   else if (!strcmp(name, "long_within")) ctx->optLongT = value;
   else if (!strcmp(name, "no_sort_pass1")) ctx->optNoSortPass1 = value;
+  else if (!strcmp(name, "equal_windows")) ctx->optEqualWindows = value;
   else if (!strcmp(name, "debug_no_candidates")) ctx->optNoCandidates = value;
   else return fail(ctx, PBWTGPU_ERR_ARG, "unknown option %s", name);
   return 0;

@@ -9,6 +9,20 @@ constexpr int kRecChunk = 1 << kRecChunkLog;
 
 enum SweepMode { kGather = 0, kSorted = 1 };
 
+// Columns [k0, k1) of window `win`.  Windows are spw sites long, except that windows 0 and 1 may be given `first` and
+// `second` (<= spw) sites and the last window takes what remains: the edge windows of a panel carry extra match work
+// (everything matches back to site 0 at the start, every block is reported at site N), so they get fewer sites.
+__host__ __device__ inline void window_range(int win, int spw, int first, int second, int N, int &k0, int &k1) {
+  if (first > 0) {
+    k0 = win == 0 ? 0 : win == 1 ? first : first + second + (win - 2) * spw;
+    k1 = win == 0 ? first : win == 1 ? first + second : k0 + spw;
+  } else {
+    k0 = win * spw;
+    k1 = k0 + spw;
+  }
+  if (k1 > N) k1 = N;
+}
+
 // One launch sweeps W windows concurrently (one CTA per window), each starting from the exact
 // state (a,d) entering its first site.
 //   regular mode (perWindowSites == 0): window w covers sites [w*sitesPerWindow, min(N,(w+1)*sitesPerWindow))
@@ -21,6 +35,8 @@ struct SweepArgs {
   int wpc;              // words per column
   int M, N;
   int sitesPerWindow;
+  int firstWindowSites;  // shared-memory kernel: > 0 gives window 0 this many sites (see window_range); 0 = like the others
+  int secondWindowSites; // and window 1 this many (only with firstWindowSites > 0)
   int nWindows;
   int siteOffset;  // regular mode: global label of column 0 (a shard of a longer panel), 0 otherwise
   int nTotal;      // global site count (labels run to nTotal); 0 = N

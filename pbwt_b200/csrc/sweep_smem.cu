@@ -119,8 +119,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     colShift = -k0;
     src = p.src + (size_t)win * p.srcWindowStride;
   } else {
-    k0 = p.siteOffset + win * p.sitesPerWindow;
-    k1 = min(p.siteOffset + p.N, k0 + p.sitesPerWindow);
+    window_range(win, p.sitesPerWindow, p.firstWindowSites, p.secondWindowSites, p.N, k0, k1);
+    k0 += p.siteOffset;
+    k1 += p.siteOffset;
     colShift = -p.siteOffset;
     src = p.src;
   }

@@ -36,12 +36,13 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {  // out(
 }
 
 // T16[(win * nq + q) * mpad + h]: bit j = allele of haplotype h at site k0(win) + 16 q + j (0 beyond the window's end)
-__global__ void __launch_bounds__(256) transpose_kernel(const uint32_t *panel, int wpc, int M, int N, int spw, int nq, int mpad,
-                                                        uint16_t *T16) {
+__global__ void __launch_bounds__(256) transpose_kernel(const uint32_t *panel, int wpc, int M, int N, int spw, int first, int second,
+                                                        int nq, int mpad, uint16_t *T16) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int qw = blockIdx.x;  // 32 sites = two key columns
   const int win = blockIdx.z;
-  const int k0 = win * spw, k1 = min(N, k0 + spw);
+  int k0, k1;
+  window_range(win, spw, first, second, N, k0, k1);
   const int site = k0 + 32 * qw + lane;
   const int hw0 = (blockIdx.y * 8 + warp) * 4;  // 4 panel words = 128 haplotypes per warp
   uint32_t in[4];
@@ -60,8 +61,8 @@ __global__ void __launch_bounds__(256) transpose_kernel(const uint32_t *panel, i
 
 template <int E>
 __global__ void __launch_bounds__(kThreads, 1) window_sort_kernel(const uint16_t *T16, int nq, int mpad, int M, int N, int spw,
-                                                                  int siteOffset, const int32_t *aStart, int32_t *ordOut,
-                                                                  int32_t *dvOut) {
+                                                                  int first, int second, int siteOffset,
+                                                                  const int32_t *aStart, int32_t *ordOut, int32_t *dvOut) {
   constexpr int MP = kThreads * E;
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t *buf0 = smem;  // (key16 << 16 | id), double buffered
@@ -73,7 +74,8 @@ __global__ void __launch_bounds__(kThreads, 1) window_sort_kernel(const uint16_t
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int win = blockIdx.x;
-  const int k0 = win * spw, k1 = min(N, k0 + spw);
+  int k0, k1;
+  window_range(win, spw, first, second, N, k0, k1);
   const int nSites = k1 - k0;
   const int nCols = (nSites + 15) / 16;  // key columns in use (<= nq)
   const uint16_t *Tw = T16 + (size_t)win * nq * mpad;
@@ -208,13 +210,13 @@ __global__ void __launch_bounds__(kThreads, 1) window_sort_kernel(const uint16_t
 size_t sort_smem_bytes(int E, int mpad) { return (size_t)kThreads * E * 8 + 32 * 256 * 2 + (size_t)mpad * 4; }
 
 template <int E>
-int launch_sort_e(const uint16_t *T16, int nq, int mpad, int M, int N, int spw, int siteOffset, const int32_t *aStart, int nodes,
-                  int32_t *ordOut, int32_t *dvOut, cudaStream_t stream) {
+int launch_sort_e(const uint16_t *T16, int nq, int mpad, int M, int N, int spw, int first, int second, int siteOffset,
+                  const int32_t *aStart, int nodes, int32_t *ordOut, int32_t *dvOut, cudaStream_t stream) {
   const size_t bytes = sort_smem_bytes(E, mpad);
   auto kern = window_sort_kernel<E>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (err != cudaSuccess) return (int)err;
-  kern<<<nodes, kThreads, bytes, stream>>>(T16, nq, mpad, M, N, spw, siteOffset, aStart, ordOut, dvOut);
+  kern<<<nodes, kThreads, bytes, stream>>>(T16, nq, mpad, M, N, spw, first, second, siteOffset, aStart, ordOut, dvOut);
   return (int)cudaGetLastError();
 }
 
@@ -227,25 +229,25 @@ size_t window_sort_scratch_words(int M, int spw, int nodes) {
   return ((size_t)nodes * key_cols(spw) * padded_m(M) * 2 + 3) / 4;
 }
 
-int launch_window_sort(const uint32_t *panel, int wpc, int M, int N, int spw, int siteOffset, const int32_t *aStart, int nodes,
-                       uint32_t *scratch, int32_t *ordOut, int32_t *dvOut, cudaStream_t stream) {
+int launch_window_sort(const uint32_t *panel, int wpc, int M, int N, int spw, int first, int second, int siteOffset,
+                       const int32_t *aStart, int nodes, uint32_t *scratch, int32_t *ordOut, int32_t *dvOut, cudaStream_t stream) {
   if (nodes <= 0) return 0;
   if (M > window_sort_max_m()) return (int)cudaErrorInvalidValue;
   const int nq = key_cols(spw), mpad = padded_m(M);
   uint16_t *T16 = reinterpret_cast<uint16_t *>(scratch);
   {
     dim3 grid((spw + 31) / 32, (wpc + 31) / 32, nodes);
-    transpose_kernel<<<grid, 256, 0, stream>>>(panel, wpc, M, N, spw, nq, mpad, T16);
+    transpose_kernel<<<grid, 256, 0, stream>>>(panel, wpc, M, N, spw, first, second, nq, mpad, T16);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return (int)err;
   }
   const int e = ((M + 31) / 32 + 31) / 32;
-  if (e <= 1) return launch_sort_e<1>(T16, nq, mpad, M, N, spw, siteOffset, aStart, nodes, ordOut, dvOut, stream);
-  if (e <= 2) return launch_sort_e<2>(T16, nq, mpad, M, N, spw, siteOffset, aStart, nodes, ordOut, dvOut, stream);
-  if (e <= 4) return launch_sort_e<4>(T16, nq, mpad, M, N, spw, siteOffset, aStart, nodes, ordOut, dvOut, stream);
-  if (e <= 7) return launch_sort_e<7>(T16, nq, mpad, M, N, spw, siteOffset, aStart, nodes, ordOut, dvOut, stream);
-  if (e <= 10) return launch_sort_e<10>(T16, nq, mpad, M, N, spw, siteOffset, aStart, nodes, ordOut, dvOut, stream);
-  return launch_sort_e<13>(T16, nq, mpad, M, N, spw, siteOffset, aStart, nodes, ordOut, dvOut, stream);
+  if (e <= 1) return launch_sort_e<1>(T16, nq, mpad, M, N, spw, first, second, siteOffset, aStart, nodes, ordOut, dvOut, stream);
+  if (e <= 2) return launch_sort_e<2>(T16, nq, mpad, M, N, spw, first, second, siteOffset, aStart, nodes, ordOut, dvOut, stream);
+  if (e <= 4) return launch_sort_e<4>(T16, nq, mpad, M, N, spw, first, second, siteOffset, aStart, nodes, ordOut, dvOut, stream);
+  if (e <= 7) return launch_sort_e<7>(T16, nq, mpad, M, N, spw, first, second, siteOffset, aStart, nodes, ordOut, dvOut, stream);
+  if (e <= 10) return launch_sort_e<10>(T16, nq, mpad, M, N, spw, first, second, siteOffset, aStart, nodes, ordOut, dvOut, stream);
+  return launch_sort_e<13>(T16, nq, mpad, M, N, spw, first, second, siteOffset, aStart, nodes, ordOut, dvOut, stream);
 }
 
 }  // namespace pbwtgpu

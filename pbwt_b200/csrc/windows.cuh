@@ -41,8 +41,9 @@ int sort_nomatch(const unsigned long long *keys, const pbwtgpu_nomatch *events, 
 // ordOut [nodes][M], dvOut [nodes][M+1]; labels are siteOffset + column + 1.
 int window_sort_max_m();
 size_t window_sort_scratch_words(int M, int spw, int nodes);
-int launch_window_sort(const uint32_t *panel, int wpc, int M, int N, int spw, int siteOffset, const int32_t *aStart, int nodes,
-                       uint32_t *scratch, int32_t *ordOut, int32_t *dvOut, cudaStream_t stream);
+// `first` > 0: windows 0 and 1 have `first` and `second` sites (window_range, sweep.cuh).
+int launch_window_sort(const uint32_t *panel, int wpc, int M, int N, int spw, int first, int second, int siteOffset,
+                       const int32_t *aStart, int nodes, uint32_t *scratch, int32_t *ordOut, int32_t *dvOut, cudaStream_t stream);
 
 // The same for wide panels (window_sort_wide.cu): one window = one cluster of 16 CTAs, ids in distributed shared memory.
 bool window_sort_wide_supported(int M, int spw);
