@@ -251,16 +251,20 @@ struct WindowedSweep {
     }
     spw = N > 0 ? (N + W - 1) / W : 1;
     W = N > 0 ? (N + spw - 1) / spw : 1;
-    // A whole panel swept with matches: its first windows (everything still matches back to site 0) and its last one
-    // (every block is reported at site N) carry 10-17 % more work per site than the others (option window_times), so
-    // windows 0 / 1 / last get about 80 / 92 / 74 % of the sites of an inner window.
-    // (shared-memory kernel; shards and wide panels keep equal windows)
-    if (!useGlobal && !sharded && wantMatch && W >= 8 && !ctx->optEqualWindows) {
-      for (int s = (int)(N / (W - 0.54)), tries = 0; tries < 4; ++s, ++tries) {  // smallest s whose last window is no longer than s
-        const int first = (int)(0.80 * s + 0.5), second = (int)(0.92 * s + 0.5);
-        const long long last = (long long)N - first - second - (long long)(W - 3) * s;
-        if (s >= 16 && first >= 1 && second >= 1 && last >= 1 && last <= s) { spw = s; firstSites = first; secondSites = second; break; }
-      }
+    // A panel swept with matches: its first windows (everything still matches back to site 0) and its last one (every
+    // block is reported at site N) carry 10-17 % more work per site than the others (option window_times), so windows
+    // 0 / 1 / last get about 80 / 92 / 74 % of the sites of an inner window.  Of a sharded panel only the shard that
+    // starts at site 0 shortens its first windows and only the one that ends at N its last.
+    // (shared-memory kernel; wide panels keep equal windows)
+    if (!useGlobal && wantMatch && W >= 8 && !ctx->optEqualWindows) {
+      const bool atStart = siteOffset == 0, atEnd = siteOffset + N == nTotal;
+      const double f0 = atStart ? 0.80 : 1.0, f1 = atStart ? 0.92 : 1.0, fl = atEnd ? 0.74 : 1.0;
+      if (atStart || atEnd)
+        for (int s = (int)(N / (W - 3 + f0 + f1 + fl)), tries = 0; tries < 4; ++s, ++tries) {  // smallest s whose last window fits
+          const int first = std::min(s, (int)(f0 * s + 0.5)), second = std::min(s, (int)(f1 * s + 0.5));
+          const long long last = (long long)N - first - second - (long long)(W - 3) * s;
+          if (s >= 16 && first >= 1 && second >= 1 && last >= 1 && last <= s) { spw = s; firstSites = first; secondSites = second; break; }
+        }
     }
     nodes = sharded ? W : W - 1;  // a shard also needs the node of its last window (its aggregate)
     slots = nodes + 1;

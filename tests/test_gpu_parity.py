@@ -349,7 +349,8 @@ def test_wide_panel_small_record_pool(eng, orc):
 
 @pytest.mark.parametrize("force_global", [0, 1])
 @pytest.mark.parametrize("M,N,R,W,dens,with_start", [(200, 90, 3, 2, 0.3, False), (1000, 240, 4, 5, 0.05, True), (33, 64, 8, 1, 0.5, False),
-                                                      (3000, 400, 2, 7, 0.02, True), (1000, 480, 8, 9, 0.1, True), (200, 300, 6, 12, 0.4, False)])
+                                                      (3000, 400, 2, 7, 0.02, True), (1000, 480, 8, 9, 0.1, True), (200, 300, 6, 12, 0.4, False),
+                                                      (500, 4000, 3, 10, 0.03, True), (300, 1500, 2, 8, 0.2, False)])
 def test_site_shards_sequential(eng, orc, M, N, R, W, dens, with_start, force_global):
     """The multi-GPU protocol (sites partitioned into R shards: prepare -> gather aggregates -> finish) run
     shard by shard on one GPU: concatenated streams / records and the last shard's a, d equal the sequential sweep."""
