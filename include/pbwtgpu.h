@@ -57,7 +57,10 @@ void pbwtgpu_destroy(pbwtgpu_ctx *ctx);
 const char *pbwtgpu_strerror(int code);
 const char *pbwtgpu_last_error(pbwtgpu_ctx *ctx);
 /* Run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL restores the context's
- * own stream.  Lets a harness bracket the kernels with events on the launching stream. */
+ * own (non-blocking) stream.  Lets a harness bracket the kernels with events on the launching stream.
+ * NB the legacy default stream's handle IS NULL: a caller that orders this library's work against another
+ * library's (an NCCL collective writing the aggregates of pbwtgpu_shard_finish, say) must create an explicit
+ * stream and use it for both. */
 int pbwtgpu_set_stream(pbwtgpu_ctx *ctx, void *cuda_stream);
 void *pbwtgpu_get_stream(pbwtgpu_ctx *ctx);
 int pbwtgpu_synchronize(pbwtgpu_ctx *ctx);
