@@ -130,7 +130,9 @@ def main():
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-                          "config": {"workload": workload_name(M, N), "step": f"bounded sample: first {n_cpu} sites"},
+                          "config": {"workload": workload_name(M, N), "haplotypes": M, "sites": N,
+                                     "step": f"bounded sample: first {n_cpu} sites",
+                                     "generator": f"seed {SEED:#x}, L={L_RECOMB}, mu={MU}"},
                           "cpu_baseline": cb,
                           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
