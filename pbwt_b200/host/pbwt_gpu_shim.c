@@ -11,8 +11,8 @@
  * The readers of pbwtIO.c are batched onto the GPU by two more renames applied to pbwtIO.c only (see
  * gpuReaderWriteForwards below).
  * Errors follow the reference's convention: die() (utils.c:31-44).  There is no CPU fallback for the
- * GPU-backed paths; options this shim does not accelerate (-check, -stats with -longWithin) are passed to
- * the reference's renamed originals and say so on the log.
+ * GPU-backed paths; the one option this shim does not accelerate, -check (it verifies every reported match against
+ * the decoded haplotypes on the CPU), is passed to the reference's renamed originals and says so on the log.
  */
 #include "pbwt.h"
 #include "pbwtgpu.h"
@@ -65,26 +65,35 @@ void pbwtLongMatches (PBWT *p, int L)
 {
   if (!p || !p->yz) die ("option -longWithin called without a PBWT") ;
   if (L < 0) die ("L %d for longWithin must be >= 0", L) ;
-  if (isCheck || (isStats && L))
-    { fprintf (logFile, "pbwt_gpu: -check (and -stats with -longWithin) run the reference CPU path\n") ;
+  if (isCheck)
+    { fprintf (logFile, "pbwt_gpu: -check runs the reference CPU path\n") ;
       ref_pbwtLongMatches (p, L) ;
       return ;
     }
-  if (isStats)			/* -stats -maxWithin: histogram of the reporters' match lengths instead of MATCH lines
-				   (pbwtMatch.c:130-131, 161-178), from the GPU's records */
+  if (isStats)			/* -stats (pbwtMatch.c:130-131, 161-178): with -maxWithin a histogram of the reporters' match
+				   lengths replaces the MATCH lines; matchLongWithin2 never touches the histogram, so with
+				   -longWithin L the MATCH lines are printed and the summary is that of an empty histogram
+				   (the reference's "Average 0.0 matches per sample" and 0/0 length) */
     { pbwtgpu_match *rec = 0 ;
       int64_t n = 0, i = 0 ;
       Array hist = arrayCreate (1000000, int) ;
       int nTot = 0, len ;
       long hTot = 0 ;
-      gpuCheck (pbwtgpu_max_within (gpuContext (), arrp(p->yz,0,uchar), arrayMax(p->yz), p->M, p->N,
-				    p->aFstart, 0, 0, &rec, &n), "pbwtgpu_max_within") ;
-      while (i < n)		/* one reporter = a run of records with the same ai and end; its length is the longer
+      if (L)
+	{ gpuCheck (pbwtgpu_long_within (gpuContext (), arrp(p->yz,0,uchar), arrayMax(p->yz), p->M, p->N,
+					 p->aFstart, L, 0, 0, &rec, &n), "pbwtgpu_long_within") ;
+	  for (i = 0 ; i < n ; ++i) reportMatchLine (rec[i].ai, rec[i].bi, rec[i].start, rec[i].end) ;
+	}
+      else
+	{ gpuCheck (pbwtgpu_max_within (gpuContext (), arrp(p->yz,0,uchar), arrayMax(p->yz), p->M, p->N,
+					p->aFstart, 0, 0, &rec, &n), "pbwtgpu_max_within") ;
+	  while (i < n)		/* one reporter = a run of records with the same ai and end; its length is the longer
 				   of its two blocks' (k - min(d[i],d[i+1])) */
-	{ int ai = rec[i].ai, end = rec[i].end, best = 0 ;
-	  for ( ; i < n && rec[i].ai == ai && rec[i].end == end ; ++i)
-	    if (rec[i].end - rec[i].start > best) best = rec[i].end - rec[i].start ;
-	  ++array(hist, best, int) ;
+	    { int ai = rec[i].ai, end = rec[i].end, best = 0 ;
+	      for ( ; i < n && rec[i].ai == ai && rec[i].end == end ; ++i)
+		if (rec[i].end - rec[i].start > best) best = rec[i].end - rec[i].start ;
+	      ++array(hist, best, int) ;
+	    }
 	}
       for (len = 0 ; len < arrayMax(hist) ; ++len)
 	if (arr(hist, len, int))

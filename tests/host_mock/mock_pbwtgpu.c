@@ -1,0 +1,112 @@
+/* mock_pbwtgpu.c -- TEST INFRASTRUCTURE ONLY: a stand-in for libpbwtgpu.so on machines without a GPU.
+ *
+ * It exports the entry points of include/pbwtgpu.h that the host shim (pbwt_b200/host/pbwt_gpu_shim.c) binds,
+ * answered by the CPU oracle port (oracle/libpbwt_oracle.so, orc_*).  Linked ONLY into
+ * tests/host_mock/_build/pbwt_hostcheck, which the `-m "not gpu"` suite uses to check the shim's HOST logic --
+ * callback order, log lines, Array / aFend ownership, the readers' lazy cursor and its batching -- against the
+ * reference's golden outputs.  Nothing under pbwt_b200/ links or loads this file; the product library has no CPU path
+ * (pbwtgpu_init fails with PBWTGPU_ERR_NODEVICE without a B200), and parity of the device code is established by the
+ * `-m gpu` suite through the real library.
+ */
+#include <stdlib.h>
+#include <string.h>
+
+#include "pbwtgpu.h"
+#define ORACLE_PREFIX orc_
+#include "oracle_api.h"
+
+struct pbwtgpu_ctx { int unused; };
+static struct pbwtgpu_ctx theCtx;
+
+int pbwtgpu_words_per_col(int M) { return 4 * ((M + 127) / 128); }
+int pbwtgpu_init(int device, pbwtgpu_ctx **ctx) { (void)device; *ctx = &theCtx; return PBWTGPU_OK; }
+void pbwtgpu_destroy(pbwtgpu_ctx *ctx) { (void)ctx; }
+const char *pbwtgpu_strerror(int code) { return code == PBWTGPU_OK ? "ok" : "mock device error"; }
+const char *pbwtgpu_last_error(pbwtgpu_ctx *ctx) { (void)ctx; return "mock device (CPU oracle port)"; }
+void pbwtgpu_free(void *p) { free(p); }
+
+int pbwtgpu_build(pbwtgpu_ctx *ctx, const uint32_t *xbits, int M, int N, const int32_t *a_start, unsigned flags,
+                  uint8_t **yz, int64_t *nyz, int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches, int64_t *nmatch) {
+  (void)ctx;
+  if ((flags & ~(unsigned)PBWTGPU_WANT_YZ) || d_end || matches || nmatch) return PBWTGPU_ERR_UNSUPPORTED; /* the shim never asks */
+  const int64_t cap = (int64_t)N * (M + 8) + 16;
+  uint8_t *buf = (uint8_t *)malloc((size_t)cap);
+  int32_t *ae = a_end ? a_end : (int32_t *)malloc(sizeof(int32_t) * (size_t)M);
+  int32_t *de = (int32_t *)malloc(sizeof(int32_t) * ((size_t)M + 1));
+  if (!buf || !ae || !de) return PBWTGPU_ERR_NOMEM;
+  const int rc = orc_build(xbits, pbwtgpu_words_per_col(M), M, N, a_start, 0, buf, cap, nyz, ae, de);
+  if (!a_end) free(ae);
+  free(de);
+  if (rc) { free(buf); return PBWTGPU_ERR_ARG; }
+  *yz = buf;
+  return PBWTGPU_OK;
+}
+
+static int ends(const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start, int32_t *a_end, int32_t *d_end) {
+  if (!a_end && !d_end) return 0;
+  int32_t *ae = (int32_t *)malloc(sizeof(int32_t) * (size_t)M), *de = (int32_t *)malloc(sizeof(int32_t) * ((size_t)M + 1));
+  if (!ae || !de) return PBWTGPU_ERR_NOMEM;
+  orc_sweep_ad(yz, nyz, M, N, a_start, ae, de);
+  if (a_end) memcpy(a_end, ae, sizeof(int32_t) * (size_t)M);
+  if (d_end) memcpy(d_end, de, sizeof(int32_t) * ((size_t)M + 1));
+  free(ae); free(de);
+  return 0;
+}
+
+int pbwtgpu_max_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start,
+                       int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches, int64_t *nmatch) {
+  (void)ctx;
+  int64_t n = 0;
+  orc_max_within(yz, nyz, M, N, a_start, NULL, 0, &n);
+  oracle_match *rec = (oracle_match *)malloc(sizeof(oracle_match) * (size_t)(n > 0 ? n : 1));
+  if (!rec) return PBWTGPU_ERR_NOMEM;
+  orc_max_within(yz, nyz, M, N, a_start, rec, n, &n);
+  *matches = (pbwtgpu_match *)rec;
+  *nmatch = n;
+  return ends(yz, nyz, M, N, a_start, a_end, d_end);
+}
+
+int pbwtgpu_long_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start, int L,
+                        int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches, int64_t *nmatch) {
+  (void)ctx;
+  if (L <= 0) return PBWTGPU_ERR_ARG;
+  int64_t n = 0;
+  orc_long_within(yz, nyz, M, N, a_start, L, NULL, 0, &n);
+  oracle_match *rec = (oracle_match *)malloc(sizeof(oracle_match) * (size_t)(n > 0 ? n : 1));
+  if (!rec) return PBWTGPU_ERR_NOMEM;
+  orc_long_within(yz, nyz, M, N, a_start, L, rec, n, &n);
+  *matches = (pbwtgpu_match *)rec;
+  *nmatch = n;
+  return ends(yz, nyz, M, N, a_start, a_end, d_end);
+}
+
+int pbwtgpu_build_reverse(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start,
+                          int32_t *a_fend, uint8_t **zz, int64_t *nzz, int32_t *a_rend) {
+  (void)ctx;
+  const int64_t cap = (int64_t)M * (N > 0 ? N : 1) + 16;
+  uint8_t *buf = (uint8_t *)malloc((size_t)cap);
+  int32_t *af = a_fend ? a_fend : (int32_t *)malloc(sizeof(int32_t) * (size_t)M);
+  if (!buf || !af) return PBWTGPU_ERR_NOMEM;
+  const int rc = orc_build_reverse(yz, nyz, M, N, a_start, af, buf, cap, nzz, a_rend);
+  if (!a_fend) free(af);
+  if (rc) { free(buf); return PBWTGPU_ERR_ARG; }
+  *zz = buf;
+  return PBWTGPU_OK;
+}
+
+int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int M, int N, const int32_t *pa_start,
+                        const uint8_t *qyz, int64_t nqyz, int Q, const int32_t *qa_start, pbwtgpu_match **matches,
+                        int64_t *nmatch, pbwtgpu_nomatch **nomatch, int64_t *nnomatch) {
+  (void)ctx;
+  int64_t n = 0, nn = 0;
+  orc_match_sweep(pyz, npyz, M, N, pa_start, qyz, nqyz, Q, qa_start, NULL, 0, &n, NULL, 0, &nn);
+  oracle_match *rec = (oracle_match *)malloc(sizeof(oracle_match) * (size_t)(n > 0 ? n : 1));
+  oracle_nomatch *nom = (oracle_nomatch *)malloc(sizeof(oracle_nomatch) * (size_t)(nn > 0 ? nn : 1));
+  if (!rec || !nom) return PBWTGPU_ERR_NOMEM;
+  orc_match_sweep(pyz, npyz, M, N, pa_start, qyz, nqyz, Q, qa_start, rec, n, &n, nom, nn, &nn);
+  *matches = (pbwtgpu_match *)rec;
+  *nmatch = n;
+  *nomatch = (pbwtgpu_nomatch *)nom;
+  *nnomatch = nn;
+  return PBWTGPU_OK;
+}

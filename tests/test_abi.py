@@ -49,3 +49,4 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle_lib" not in txt and "libpbwt_oracle" not in txt and "libpbwtref" not in txt, f
+                assert "mock_pbwtgpu" not in txt and "host_mock" not in txt, f  # the CPU stand-in of tests/host_mock stays in tests/

@@ -1,0 +1,254 @@
+"""CPU tests of the HOST side of the drop-in (pbwt_b200/host/pbwt_gpu_shim.c): the reference's own pbwtMain.c /
+pbwtIO.c / callers linked with the shim exactly as in pbwt_b200/host/Makefile, but against tests/host_mock/
+mock_pbwtgpu.c -- a stand-in for libpbwtgpu.so answered by the CPU oracle port -- so that what is under test without
+a GPU is the shim's own logic: record -> callback order, the interleaving of "no match" log lines, the summary lines,
+-stats histograms, Array / aFend ownership, and the readers' lazy cursor with its batches.  Expected outputs are the
+reference's (golden md5s recorded from the unmodified reference CLI, tests/golden/).  The same commands run against
+the real device library in tests/test_gpu_cli.py."""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from test_gpu_cli import GOLD, ROOT, write_pbwt
+
+MOCK_DIR = os.path.join(ROOT, "tests", "host_mock")
+HOST_OBJ = os.path.join(ROOT, "pbwt_b200", "host", "_build", "pbwt_gpu_shim.o")
+CLI = os.path.join(MOCK_DIR, "_build", "pbwt_hostcheck")
+SELFCHECK = os.path.join(MOCK_DIR, "_build", "shim_selfcheck")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def hostcheck():
+    if not os.path.exists(HOST_OBJ):
+        pytest.skip("host shim objects not built (they need the reference sources at build time)")
+    O.port()  # makes sure oracle/libpbwt_oracle.so exists
+    r = subprocess.run(["make", "-C", MOCK_DIR], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def golden_pbwt(tmp_path, name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    M, N = int(g["M"]), int(g["N"])
+    pb = tmp_path / "x.pbwt"
+    write_pbwt(pb, M, N, np.arange(M), g["a_end"], g["yz"])
+    return g, pb
+
+
+def run(*args, env=None):
+    return subprocess.run([CLI, *map(str, args)], check=True, capture_output=True, env=env).stdout
+
+
+@pytest.mark.parametrize("name", ["merge1", "omni", "mosaic300x400"])
+def test_maxwithin_stdout(tmp_path, name):
+    g, pb = golden_pbwt(tmp_path, name)
+    out = run("-read", pb, "-maxWithin")
+    assert len(out.splitlines()) == int(g["maxwithin_stdout_lines"])
+    assert hashlib.md5(out).hexdigest() == str(g["maxwithin_stdout_md5"])
+
+
+@pytest.mark.parametrize("name,L", [("merge1", 2), ("omni", 20), ("mosaic300x400", 40)])
+def test_longwithin_stdout(tmp_path, name, L):
+    _, pb = golden_pbwt(tmp_path, name)
+    lw = np.load(os.path.join(GOLD, "long_within.npz"))
+    out = run("-read", pb, "-longWithin", L)
+    assert hashlib.md5(out).hexdigest() == str(lw[f"{name}_L{L}_md5"])
+
+
+@pytest.mark.parametrize("name", ["merge1", "omni", "mosaic300x400"])
+def test_build_reverse_file(tmp_path, name):
+    _, pb = golden_pbwt(tmp_path, name)
+    r = np.load(os.path.join(GOLD, "reverse.npz"))
+    rv = tmp_path / "r.pbwt"
+    run("-read", pb, "-buildReverse", "-writeReverse", rv)
+    assert hashlib.md5(open(rv, "rb").read()).hexdigest() == str(r[name + "_md5"])
+
+
+@pytest.mark.parametrize("name,md5,log", [
+    ("merge1", "8d1029f275f8c490f3c50923db651419", ["Average 2.9 matches per sample", "Average length 4.9"]),
+    ("omni", "3efa4cec8b933c7a984c8b96cae7e035", ["Average 4.0 matches per sample", "Average length 20.7"]),
+    ("mosaic300x400", "a6e0ff75052b0c53c1e193a479eb6965", ["Average 12.4 matches per sample", "Average length 69.8"])])
+def test_stats_maxwithin(tmp_path, name, md5, log):
+    _, pb = golden_pbwt(tmp_path, name)
+    lg = tmp_path / "log"
+    out = run("-log", lg, "-stats", "-read", pb, "-maxWithin")
+    assert hashlib.md5(out).hexdigest() == md5
+    assert [ln for ln in open(lg).read().splitlines() if ln.startswith("Average")] == log
+
+
+def test_matchdynamic_stdout_and_log(tmp_path):
+    g = np.load(os.path.join(GOLD, "query_sweep.npz"))
+    M, Q, N = int(g["M"]), int(g["Q"]), int(g["N"])
+    pp, qp, lg = tmp_path / "p.pbwt", tmp_path / "q.pbwt", tmp_path / "log"
+    write_pbwt(pp, M, N, np.arange(M), g["pa_end"], g["pyz"])
+    write_pbwt(qp, Q, N, np.arange(Q), g["qa_end"], g["qyz"])
+    out = run("-log", lg, "-read", pp, "-matchDynamic", qp)
+    assert hashlib.md5(out).hexdigest() == str(g["matchdynamic_stdout_md5"])
+    log = [ln for ln in open(lg).read().splitlines() if ln.startswith("no match") or ln.startswith("Average number")]
+    assert "\n".join(log) == str(g["matchdynamic_log"])
+
+
+@pytest.mark.parametrize("name,batch", [("merge1", 1), ("merge1", 3), ("omni", 7), ("omni", 0), ("mosaic300x400", 128)])
+def test_reader_batched_ingest(tmp_path, name, batch):
+    """The readers' per-site cursor step through the shim's lazy cursor: several batches, order carried between them."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    M, N = int(g["M"]), int(g["N"])
+    hap = O.unpack_panel(g["xbits"], M)
+    vq, pb = tmp_path / "x.vcfq", tmp_path / "x.pbwt"
+    with open(vq, "w") as fh:  # parseVcfqLine, pbwtIO.c:511-554
+        for k in range(N):
+            fh.write("20\t%d\tA\tC\t" % (1000 + k) + "\t".join(str(int(v)) for v in hap[:, k]) + "\n")
+    env = dict(os.environ)
+    if batch:
+        env["PBWTGPU_READER_BATCH"] = str(batch)
+    run("-readVcfq", vq, "-write", pb, env=env)
+    assert hashlib.md5(open(pb, "rb").read()).hexdigest() == str(g["pbwt_md5"])
+    out = run("-readVcfq", vq, "-maxWithin", env=env)
+    assert hashlib.md5(out).hexdigest() == str(g["maxwithin_stdout_md5"])
+
+
+def test_batched_build_writes_reference_file(tmp_path):
+    g = np.load(os.path.join(GOLD, "omni.npz"))
+    M, N = int(g["M"]), int(g["N"])
+    hap = O.unpack_panel(g["xbits"], M)
+    xin, pb = tmp_path / "x.bytes", tmp_path / "x.pbwt"
+    np.ascontiguousarray(hap.T).tofile(xin)
+    subprocess.run([SELFCHECK, str(xin), str(M), str(N), str(pb)], check=True, capture_output=True)
+    assert hashlib.md5(open(pb, "rb").read()).hexdigest() == str(g["pbwt_md5"])
+
+
+# ---- differential runs against the unmodified reference CLI (oracle/_ref/pbwt_ref), where it is present ----
+
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "pbwt_ref")
+needs_ref_cli = pytest.mark.skipif(not os.path.exists(REF_CLI), reason="reference CLI (oracle/_ref/pbwt_ref) not present")
+
+
+def write_vcfq(path, hap):
+    with open(path, "w") as fh:
+        for k in range(hap.shape[1]):
+            fh.write("20\t%d\tA\tC\t" % (1000 + k) + "\t".join(str(int(v)) for v in hap[:, k]) + "\n")
+
+
+def both(tmp_path, args, env=None):
+    """Run the same command line through the reference and through the shim build; returns (stdout, log) of each with
+    the timing lines (utils.c timeUpdate) and the shim's own notices removed."""
+    res = []
+    for tag, exe in (("ref", REF_CLI), ("shim", CLI)):
+        lg = tmp_path / (tag + ".log")
+        a = [str(x).replace("@", tag) for x in args]
+        out = subprocess.run([exe, "-log", str(lg), *a], check=True, capture_output=True, env=env).stdout
+        log = [ln for ln in open(lg).read().splitlines() if "\tsystem\t" not in ln and not ln.startswith("pbwt_gpu:")]
+        res.append((out, log))
+    return res
+
+
+@needs_ref_cli
+@pytest.mark.parametrize("opts", [["-maxWithin"], ["-longWithin", "3"], ["-longWithin", "11"], ["-stats", "-maxWithin"],
+                                  ["-stats", "-longWithin", "4"], ["-check", "-maxWithin"], ["-check", "-longWithin", "5"]])
+@pytest.mark.parametrize("M,N,dens,seed", [(40, 30, 0.3, 5), (9, 64, 0.5, 6), (130, 25, 0.05, 7)])
+def test_match_commands_equal_reference(tmp_path, opts, M, N, dens, seed):
+    rng = np.random.default_rng(seed)
+    hap = (rng.random((M, N)) < dens).astype(np.uint8)
+    hap[: M // 4] = hap[0]
+    vq = tmp_path / "x.vcfq"
+    write_vcfq(vq, hap)
+    pre = [o for o in opts if o in ("-stats", "-check")]
+    cmd = [o for o in opts if o not in ("-stats", "-check")]
+    (ro, rl), (so, sl) = both(tmp_path, [*pre, "-readVcfq", vq, *cmd], env={**os.environ, "PBWTGPU_READER_BATCH": "7"})
+    assert ro == so
+    assert rl == sl
+
+
+@needs_ref_cli
+@pytest.mark.parametrize("M,Q,N,seed", [(30, 5, 40, 1), (8, 12, 25, 2)])
+def test_matchdynamic_equals_reference(tmp_path, M, Q, N, seed):
+    rng = np.random.default_rng(seed)
+    hp = (rng.random((M, N)) < 0.2).astype(np.uint8)
+    hq = (rng.random((Q, N)) < 0.4).astype(np.uint8)
+    hq[0] = hp[1]
+    write_vcfq(tmp_path / "p.vcfq", hp)
+    write_vcfq(tmp_path / "q.vcfq", hq)
+    for tag, exe in (("ref", REF_CLI), ("shim", CLI)):  # the two files each build writes must be identical too
+        subprocess.run([exe, "-readVcfq", str(tmp_path / "p.vcfq"), "-write", str(tmp_path / f"p.{tag}.pbwt")], check=True, capture_output=True)
+        subprocess.run([exe, "-readVcfq", str(tmp_path / "q.vcfq"), "-write", str(tmp_path / f"q.{tag}.pbwt")], check=True, capture_output=True)
+    assert open(tmp_path / "p.ref.pbwt", "rb").read() == open(tmp_path / "p.shim.pbwt", "rb").read()
+    assert open(tmp_path / "q.ref.pbwt", "rb").read() == open(tmp_path / "q.shim.pbwt", "rb").read()
+    (ro, rl), (so, sl) = both(tmp_path, ["-read", tmp_path / "p.ref.pbwt", "-matchDynamic", tmp_path / "q.ref.pbwt"])
+    assert ro == so and rl == sl
+
+
+@needs_ref_cli
+def test_reverse_and_macs_reader_equal_reference(tmp_path):
+    rng = np.random.default_rng(9)
+    M, N = 24, 50
+    hap = (rng.random((M, N)) < 0.35).astype(np.uint8)
+    macs = tmp_path / "x.macs"  # pbwtReadMacs, pbwtIO.c:460-492
+    with open(macs, "w") as fh:
+        fh.write(f"COMMAND:\tmacs {M} 100000\nSEED:\t1\n")
+        for k in range(N):
+            fh.write(f"SITE:\t{k}\t{(k + 1) / (N + 2):.6f}\t0.1\t" + "".join(str(int(v)) for v in hap[:, k]) + "\n")
+        fh.write(f"TOTAL_SAMPLES:\t{M}\nTOTAL_SITES:\t{N}\nBEGIN_SELECTED_SITES\n" + "\t".join(str(k) for k in range(N)) + "\nEND_SELECTED_SITES\n")
+    for batch in ("4", "1000"):
+        (ro, rl), (so, sl) = both(tmp_path, ["-readMacs", macs, "-write", tmp_path / "@.pbwt", "-buildReverse", "-writeReverse", tmp_path / "@.rev", "-maxWithin"],
+                                  env={**os.environ, "PBWTGPU_READER_BATCH": batch})
+        assert ro == so and rl == sl
+        assert open(tmp_path / "ref.pbwt", "rb").read() == open(tmp_path / "shim.pbwt", "rb").read()
+        assert open(tmp_path / "ref.rev", "rb").read() == open(tmp_path / "shim.rev", "rb").read()
+
+
+def founder_haps(rng, M, N, founders=6, flip=0.01):
+    F = (rng.random((founders, N)) < 0.4).astype(np.uint8)
+    hap = np.empty((M, N), np.uint8)
+    for h in range(M):
+        src = rng.integers(founders)
+        for k in range(N):
+            if rng.random() < 0.05:
+                src = rng.integers(founders)
+            hap[h, k] = F[src, k]
+    return hap ^ (rng.random((M, N)) < flip).astype(np.uint8)
+
+
+@needs_ref_cli
+@pytest.mark.parametrize("seed,step", [(3, 3), (4, 1), (5, 7)])
+def test_reference_impute_consumer_equals_reference(tmp_path, seed, step):
+    """-referenceImpute (pbwtImpute.c:1106-1290): the reference's imputation drives matchMaximalWithin / matchSequencesSweep
+    through its own reportMatch callback (:1142-1146, appending per-query arrays in callback order) and pbwtBuildReverse
+    (:1283).  With the shim's versions underneath, the imputed .pbwt, sites, haplotypes and log must be the reference's."""
+    rng = np.random.default_rng(seed)
+    M, N = 60, 80
+    hap = founder_haps(rng, M, N)
+    write_vcfq(tmp_path / "ref.vcfq", hap[:40])
+    with open(tmp_path / "q.vcfq", "w") as fh:  # the query panel is typed at every step-th site only
+        for k in range(0, N, step):
+            fh.write("20\t%d\tA\tC\t" % (1000 + k) + "\t".join(str(int(v)) for v in hap[40:, k]) + "\n")
+    outs = {}
+    for tag, exe in (("ref", REF_CLI), ("shim", CLI)):
+        d = tmp_path / tag
+        d.mkdir()
+        subprocess.run([exe, "-readVcfq", str(tmp_path / "ref.vcfq"), "-writeAll", "panel"], check=True, capture_output=True, cwd=d)
+        out = subprocess.run([exe, "-log", "log", "-readVcfq", str(tmp_path / "q.vcfq"), "-referenceImpute", "panel", "-write", "imp.pbwt",
+                              "-writeSites", "imp.sites", "-haps", "imp.haps"], check=True, capture_output=True, cwd=d).stdout
+        log = [ln for ln in open(d / "log").read().splitlines() if "\tsystem\t" not in ln and not ln.startswith("pbwt_gpu:")]
+        outs[tag] = (out, log, *(open(d / f, "rb").read() for f in ("panel.pbwt", "imp.pbwt", "imp.sites", "imp.haps")))
+    assert outs["ref"] == outs["shim"]
+    assert any(ln.startswith("impute against reference") for ln in outs["ref"][1]) and len(outs["ref"][3]) > 0
+
+
+@needs_ref_cli
+def test_paint_consumer_equals_reference(tmp_path):
+    """-paint (pbwtPaint.c:66-137): chromosome painting accumulates the records of matchMaximalWithin (:87) per
+    haplotype pair; its four output matrices must be the reference's."""
+    rng = np.random.default_rng(8)
+    hap = founder_haps(rng, 40, 90)
+    write_vcfq(tmp_path / "x.vcfq", hap)
+    files = ["pt.chunkcounts.out", "pt.chunklengths.out", "pt.regionchunkcounts.out", "pt.regionsquaredchunkcounts.out"]
+    outs = {}
+    for tag, exe in (("ref", REF_CLI), ("shim", CLI)):
+        d = tmp_path / tag
+        d.mkdir()
+        subprocess.run([exe, "-readVcfq", str(tmp_path / "x.vcfq"), "-paint", "pt", "10", "2"], check=True, capture_output=True, cwd=d)
+        outs[tag] = [open(d / f, "rb").read() for f in files]
+    assert outs["ref"] == outs["shim"] and all(len(b) > 0 for b in outs["ref"])
