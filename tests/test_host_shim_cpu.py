@@ -252,3 +252,23 @@ def test_paint_consumer_equals_reference(tmp_path):
         subprocess.run([exe, "-readVcfq", str(tmp_path / "x.vcfq"), "-paint", "pt", "10", "2"], check=True, capture_output=True, cwd=d)
         outs[tag] = [open(d / f, "rb").read() for f in files]
     assert outs["ref"] == outs["shim"] and all(len(b) > 0 for b in outs["ref"])
+
+
+@needs_ref_cli
+@pytest.mark.parametrize("batch", ["4", "25", "1000"])
+def test_checkpoint_hook_equals_reference(tmp_path, batch):
+    """-checkpoint n (pbwtCheckPoint, pbwtIO.c:158-168, called from the readers every n sites): the hook copies the
+    cursor's order into p->aFend and writes the panel so far; through the shim's lazy cursor that forces a flush of the
+    pending batch in the middle of reading.  Checkpoint files and the final file must be the reference's."""
+    rng = np.random.default_rng(12)
+    hap = founder_haps(rng, 30, 64)
+    write_vcfq(tmp_path / "x.vcfq", hap)
+    files = ["check_A.pbwt", "check_A.sites", "check_B.pbwt", "check_B.sites", "out.pbwt"]
+    outs = {}
+    for tag, exe in (("ref", REF_CLI), ("shim", CLI)):
+        d = tmp_path / tag
+        d.mkdir()
+        subprocess.run([exe, "-checkpoint", "25", "-readVcfq", str(tmp_path / "x.vcfq"), "-write", "out.pbwt"], check=True,
+                       capture_output=True, cwd=d, env={**os.environ, "PBWTGPU_READER_BATCH": batch})
+        outs[tag] = [open(d / f, "rb").read() for f in files]
+    assert outs["ref"] == outs["shim"]
