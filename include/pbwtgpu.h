@@ -159,7 +159,8 @@ int pbwtgpu_cursor_at(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, i
  * a_fend may be NULL. */
 int pbwtgpu_build_reverse(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start,
                           int32_t *a_fend, uint8_t **zz, int64_t *nzz, int32_t *a_rend);
-/* matchSequencesSweep(p, q, report) (pbwtMatch.c:363-443): panel and query streams as stored. */
+/* matchSequencesSweep(p, q, report) (pbwtMatch.c:363-443): panel and query streams as stored.  At most 8,192 queries per
+ * call (PBWTGPU_ERR_UNSUPPORTED beyond); the host shim chunks larger query sets and merges the record streams exactly. */
 int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int M, int N, const int32_t *pa_start,
                         const uint8_t *qyz, int64_t nqyz, int Q, const int32_t *qa_start, pbwtgpu_match **matches,
                         int64_t *nmatch, pbwtgpu_nomatch **nomatch, int64_t *nnomatch);

@@ -148,12 +148,126 @@ void pbwtBuildReverse (PBWT *p)
 
 /* ---- matchSequencesSweep (pbwtMatch.c:363-443) ---- */
 
+static void logNoMatch (const pbwtgpu_nomatch *e)
+{ fprintf (logFile, "no match to query %d value %d at site %d\n", e->query, e->allele, e->site) ; }
+
+/* More queries than one device call takes (8,192; PBWTGPU_QUERY_CHUNK overrides, for tests).  A query's matches depend
+   on the panel and on its own alleles only; the other queries decide nothing but the ORDER of the callbacks (queries
+   are visited in the order of the query PBWT at each site, pbwtMatch.c:377-378,431-432).  So the queries are cut into
+   chunks of consecutive haplotype indices; one walk over q's stream (the reference's run-wise cursor,
+   pbwtCursorForwardsRead) un-sorts every column into per-chunk bit columns; each chunk is built and swept against the
+   panel on the GPU; a second walk supplies every query's position in the query order at each site, and the chunks'
+   record streams -- each already in that order, restricted to its chunk -- are merged site by site. */
+
+typedef struct { int rank, chunk, len ; int64_t start ; } QGroup ;
+
+static int qGroupOrder (const void *a, const void *b)
+{ return ((const QGroup*)a)->rank - ((const QGroup*)b)->rank ; }
+
+static void matchSweepChunked (PBWT *p, PBWT *q, int chunk, void (*report)(int ai, int bi, int start, int end),
+			       int64_t *nOut, long *totLenOut)
+{
+  int Q = q->M, N = q->N, nC = (Q + chunk - 1) / chunk, c, j, k ;
+  uint32_t **bits = myalloc (nC, uint32_t*) ;
+  pbwtgpu_match **rec = mycalloc (nC, pbwtgpu_match*) ;
+  pbwtgpu_nomatch **nom = mycalloc (nC, pbwtgpu_nomatch*) ;
+  int64_t *n = mycalloc (nC, int64_t), *nn = mycalloc (nC, int64_t), *ir = mycalloc (nC, int64_t), *in = mycalloc (nC, int64_t) ;
+  int64_t i, total = 0 ;
+  long totLen = 0 ;
+  int *rank = myalloc (Q, int) ;
+  QGroup *grp = myalloc (Q, QGroup), *ngrp = myalloc (Q, QGroup) ;
+  PbwtCursor *uq ;
+
+  /* 1. un-sort the query columns into per-chunk bit columns */
+  for (c = 0 ; c < nC ; ++c)
+    { int cq = (c+1)*chunk <= Q ? chunk : Q - c*chunk ;
+      bits[c] = mycalloc ((size_t)pbwtgpu_words_per_col (cq) * (N > 0 ? N : 1), uint32_t) ;
+    }
+  uq = pbwtCursorCreate (q, TRUE, TRUE) ;
+  for (k = 0 ; k < N ; ++k)
+    { for (j = 0 ; j < Q ; ++j)
+	if (uq->y[j])
+	  { int h = uq->a[j], l ;
+	    c = h / chunk ; l = h - c*chunk ;
+	    bits[c][(size_t)k * pbwtgpu_words_per_col ((c+1)*chunk <= Q ? chunk : Q - c*chunk) + (l >> 5)] |= 1u << (l & 31) ;
+	  }
+      pbwtCursorForwardsRead (uq) ;
+    }
+  pbwtCursorDestroy (uq) ;
+
+  /* 2. every chunk: its own PBWT (started from q's start order restricted to the chunk), swept against the panel */
+  for (c = 0 ; c < nC ; ++c)
+    { int c0 = c*chunk, cq = (c+1)*chunk <= Q ? chunk : Q - c0, m = 0 ;
+      int *aStart = myalloc (cq, int), *aEnd = myalloc (cq, int) ;
+      uint8_t *yz = 0 ; int64_t nyz = 0 ;
+      for (j = 0 ; j < Q ; ++j)
+	{ int h = q->aFstart ? q->aFstart[j] : j ;
+	  if (h >= c0 && h < c0 + cq) aStart[m++] = h - c0 ;
+	}
+      gpuCheck (pbwtgpu_build (gpuContext (), bits[c], cq, N, aStart, PBWTGPU_WANT_YZ, &yz, &nyz, aEnd, 0, 0, 0),
+		"pbwtgpu_build (query chunk)") ;
+      free (bits[c]) ;
+      gpuCheck (pbwtgpu_match_sweep (gpuContext (), arrp(p->yz,0,uchar), arrayMax(p->yz), p->M, p->N, p->aFstart,
+				     yz, nyz, cq, aStart, &rec[c], &n[c], &nom[c], &nn[c]), "pbwtgpu_match_sweep (query chunk)") ;
+      for (i = 0 ; i < n[c] ; ++i) rec[c][i].ai += c0 ;
+      for (i = 0 ; i < nn[c] ; ++i) nom[c][i].query += c0 ;
+      pbwtgpu_free (yz) ; free (aStart) ; free (aEnd) ;
+    }
+  free (bits) ;
+
+  /* 3. merge site by site in the order of the whole query PBWT */
+  uq = pbwtCursorCreate (q, TRUE, TRUE) ;
+  for (k = 0 ; k <= N ; ++k)
+    { int ng = 0, nng = 0, g ;
+      BOOL any = FALSE ;
+      for (c = 0 ; c < nC && !any ; ++c)
+	any = (ir[c] < n[c] && rec[c][ir[c]].end == k) || (in[c] < nn[c] && nom[c][in[c]].site == k) ;
+      if (any)
+	{ for (j = 0 ; j < Q ; ++j) rank[uq->a[j]] = j ;
+	  for (c = 0 ; c < nC ; ++c)
+	    { while (ir[c] < n[c] && rec[c][ir[c]].end == k)	/* one group = one query's records at this site */
+		{ int ai = rec[c][ir[c]].ai ;
+		  if (ng >= Q) die ("matchSweepChunked: more record groups than queries at site %d", k) ;
+		  grp[ng].rank = rank[ai] ; grp[ng].chunk = c ; grp[ng].start = ir[c] ; grp[ng].len = 0 ;
+		  while (ir[c] < n[c] && rec[c][ir[c]].end == k && rec[c][ir[c]].ai == ai) { ++ir[c] ; ++grp[ng].len ; }
+		  ++ng ;
+		}
+	      while (in[c] < nn[c] && nom[c][in[c]].site == k)
+		{ if (nng >= Q) die ("matchSweepChunked: more no-match events than queries at site %d", k) ;
+		  ngrp[nng].rank = rank[nom[c][in[c]].query] ; ngrp[nng].chunk = c ; ngrp[nng].start = in[c]++ ; ngrp[nng].len = 1 ;
+		  ++nng ;
+		}
+	    }
+	  qsort (grp, ng, sizeof(QGroup), qGroupOrder) ;
+	  qsort (ngrp, nng, sizeof(QGroup), qGroupOrder) ;
+	  for (g = 0 ; g < ng ; ++g)
+	    { const pbwtgpu_match *r = rec[grp[g].chunk] + grp[g].start ;
+	      for (j = 0 ; j < grp[g].len ; ++j)
+		{ (*report) (r[j].ai, r[j].bi, r[j].start, r[j].end) ;
+		  totLen += r[j].end - r[j].start ;
+		}
+	      total += grp[g].len ;
+	    }
+	  for (g = 0 ; g < nng ; ++g) logNoMatch (nom[ngrp[g].chunk] + ngrp[g].start) ;
+	}
+      if (k < N) pbwtCursorForwardsRead (uq) ;
+    }
+  pbwtCursorDestroy (uq) ;
+  for (c = 0 ; c < nC ; ++c)
+    { if (ir[c] != n[c] || in[c] != nn[c]) die ("matchSweepChunked: chunk %d left records behind", c) ;
+      pbwtgpu_free (rec[c]) ; pbwtgpu_free (nom[c]) ;
+    }
+  free (rec) ; free (nom) ; free (n) ; free (nn) ; free (ir) ; free (in) ; free (rank) ; free (grp) ; free (ngrp) ;
+  *nOut = total ; *totLenOut = totLen ;
+}
+
 void matchSequencesSweep (PBWT *p, PBWT *q, void (*report)(int ai, int bi, int start, int end))
 {
   pbwtgpu_match *rec = 0 ;
   pbwtgpu_nomatch *nom = 0 ;
   int64_t n = 0, nn = 0, i, j = 0 ;
   long totLen = 0 ;
+  int chunk = 8192 ;		/* queries per device call (include/pbwtgpu.h: pbwtgpu_match_sweep) */
 
   if (q->N != p->N) die ("query length in matchSequences %d != PBWT length %d", q->N, p->N) ;
   if (isCheck)
@@ -161,23 +275,27 @@ void matchSequencesSweep (PBWT *p, PBWT *q, void (*report)(int ai, int bi, int s
       ref_matchSequencesSweep (p, q, report) ;
       return ;
     }
-  gpuCheck (pbwtgpu_match_sweep (gpuContext (), arrp(p->yz,0,uchar), arrayMax(p->yz), p->M, p->N, p->aFstart,
-				 arrp(q->yz,0,uchar), arrayMax(q->yz), q->M, q->aFstart,
-				 &rec, &n, &nom, &nn), "pbwtgpu_match_sweep") ;
-  /* records and "no match" log lines interleave in site order exactly as the reference emits them:
-     a query with no match at site k logs before any record that ends at a later site */
-  for (i = 0 ; i < n ; ++i)
-    { while (j < nn && nom[j].site < rec[i].end)
-	{ fprintf (logFile, "no match to query %d value %d at site %d\n", nom[j].query, nom[j].allele, nom[j].site) ; ++j ; }
-      (*report) (rec[i].ai, rec[i].bi, rec[i].start, rec[i].end) ;
-      totLen += rec[i].end - rec[i].start ;
+  if (getenv ("PBWTGPU_QUERY_CHUNK") && atoi (getenv ("PBWTGPU_QUERY_CHUNK")) > 0)
+    chunk = atoi (getenv ("PBWTGPU_QUERY_CHUNK")) ;
+  if (q->M > chunk)
+    matchSweepChunked (p, q, chunk, report, &n, &totLen) ;
+  else
+    { gpuCheck (pbwtgpu_match_sweep (gpuContext (), arrp(p->yz,0,uchar), arrayMax(p->yz), p->M, p->N, p->aFstart,
+				     arrp(q->yz,0,uchar), arrayMax(q->yz), q->M, q->aFstart,
+				     &rec, &n, &nom, &nn), "pbwtgpu_match_sweep") ;
+      /* records and "no match" log lines interleave in site order exactly as the reference emits them:
+	 a query with no match at site k logs before any record that ends at a later site */
+      for (i = 0 ; i < n ; ++i)
+	{ while (j < nn && nom[j].site < rec[i].end) logNoMatch (&nom[j++]) ;
+	  (*report) (rec[i].ai, rec[i].bi, rec[i].start, rec[i].end) ;
+	  totLen += rec[i].end - rec[i].start ;
+	}
+      for ( ; j < nn ; ++j) logNoMatch (&nom[j]) ;
+      pbwtgpu_free (rec) ; pbwtgpu_free (nom) ;
     }
-  for ( ; j < nn ; ++j)
-    fprintf (logFile, "no match to query %d value %d at site %d\n", nom[j].query, nom[j].allele, nom[j].site) ;
   /* summary line, pbwtMatch.c:438-439 */
   fprintf (logFile, "Average number of best matches including alternates %.1f, Average length %.1f, Av number per position %.1f\n",
 	   n/(double)q->M, totLen/(double)n, totLen/(double)(q->M*q->N)) ;
-  pbwtgpu_free (rec) ; pbwtgpu_free (nom) ;
 }
 
 void matchSequencesDynamic (PBWT *p, FILE *fp)	/* pbwtMatch.c:352-357 */

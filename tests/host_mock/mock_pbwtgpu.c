@@ -98,6 +98,8 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
                         const uint8_t *qyz, int64_t nqyz, int Q, const int32_t *qa_start, pbwtgpu_match **matches,
                         int64_t *nmatch, pbwtgpu_nomatch **nomatch, int64_t *nnomatch) {
   (void)ctx;
+  const char *qmax = getenv("PBWTGPU_MOCK_QMAX"); /* tests: refuse more queries per call, as the device does beyond 8,192 */
+  if (qmax && Q > atoi(qmax)) return PBWTGPU_ERR_UNSUPPORTED;
   int64_t n = 0, nn = 0;
   orc_match_sweep(pyz, npyz, M, N, pa_start, qyz, nqyz, Q, qa_start, NULL, 0, &n, NULL, 0, &nn);
   oracle_match *rec = (oracle_match *)malloc(sizeof(oracle_match) * (size_t)(n > 0 ? n : 1));

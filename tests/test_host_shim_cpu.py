@@ -272,3 +272,50 @@ def test_checkpoint_hook_equals_reference(tmp_path, batch):
                        capture_output=True, cwd=d, env={**os.environ, "PBWTGPU_READER_BATCH": batch})
         outs[tag] = [open(d / f, "rb").read() for f in files]
     assert outs["ref"] == outs["shim"]
+
+
+@needs_ref_cli
+@pytest.mark.parametrize("M,Q,N,chunk,seed", [(30, 13, 40, 4, 1), (8, 12, 25, 5, 2), (50, 33, 60, 8, 3), (20, 9, 30, 1, 4), (40, 17, 35, 16, 5)])
+def test_matchdynamic_more_queries_than_one_device_call(tmp_path, M, Q, N, chunk, seed):
+    """More queries than one pbwtgpu_match_sweep call takes (8,192 on the device; here the mock refuses more than
+    `chunk`): the shim cuts the queries into chunks, sweeps each against the panel and merges the record streams site by
+    site in the order of the whole query PBWT.  stdout (MATCH lines in callback order) and the log ("no match" lines,
+    summary) must be the reference's."""
+    rng = np.random.default_rng(seed)
+    hap = founder_haps(rng, M + Q, N, founders=4, flip=0.03)
+    hp, hq = hap[:M].copy(), hap[M:].copy()
+    hp[:, 5] = 0  # a monomorphic panel site with some queries carrying the other allele: "no match" events
+    hq[::2, 5] = 1
+    hq[1] = hq[0]  # tied queries
+    write_vcfq(tmp_path / "p.vcfq", hp)
+    write_vcfq(tmp_path / "q.vcfq", hq)
+    subprocess.run([REF_CLI, "-readVcfq", str(tmp_path / "p.vcfq"), "-write", str(tmp_path / "p.pbwt")], check=True, capture_output=True)
+    subprocess.run([REF_CLI, "-readVcfq", str(tmp_path / "q.vcfq"), "-write", str(tmp_path / "q.pbwt")], check=True, capture_output=True)
+    env = {**os.environ, "PBWTGPU_QUERY_CHUNK": str(chunk), "PBWTGPU_MOCK_QMAX": str(chunk)}
+    (ro, rl), (so, sl) = both(tmp_path, ["-read", tmp_path / "p.pbwt", "-matchDynamic", tmp_path / "q.pbwt"], env=env)
+    assert ro == so
+    assert rl == sl
+    assert any(ln.startswith("no match") for ln in rl) and len(ro) > 0
+
+
+@needs_ref_cli
+def test_reference_impute_with_chunked_queries(tmp_path):
+    """-referenceImpute with more target haplotypes than one device call takes: the imputation's per-query arrays are
+    filled in callback order (pbwtImpute.c:1149-1165), so the merged order must be exact."""
+    rng = np.random.default_rng(21)
+    hap = founder_haps(rng, 70, 80)
+    write_vcfq(tmp_path / "ref.vcfq", hap[:40])
+    with open(tmp_path / "q.vcfq", "w") as fh:
+        for k in range(0, 80, 3):
+            fh.write("20\t%d\tA\tC\t" % (1000 + k) + "\t".join(str(int(v)) for v in hap[40:, k]) + "\n")
+    env = {**os.environ, "PBWTGPU_QUERY_CHUNK": "7", "PBWTGPU_MOCK_QMAX": "7"}
+    outs = {}
+    for tag, exe in (("ref", REF_CLI), ("shim", CLI)):
+        d = tmp_path / tag
+        d.mkdir()
+        subprocess.run([exe, "-readVcfq", str(tmp_path / "ref.vcfq"), "-writeAll", "panel"], check=True, capture_output=True, cwd=d)
+        subprocess.run([exe, "-log", "log", "-readVcfq", str(tmp_path / "q.vcfq"), "-referenceImpute", "panel", "-write", "imp.pbwt", "-haps", "imp.haps"],
+                       check=True, capture_output=True, cwd=d, env=env)
+        log = [ln for ln in open(d / "log").read().splitlines() if "\tsystem\t" not in ln and not ln.startswith("pbwt_gpu:")]
+        outs[tag] = (log, open(d / "imp.pbwt", "rb").read(), open(d / "imp.haps", "rb").read())
+    assert outs["ref"] == outs["shim"]
