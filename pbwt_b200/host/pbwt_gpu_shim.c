@@ -11,8 +11,9 @@
  * The readers of pbwtIO.c are batched onto the GPU by two more renames applied to pbwtIO.c only (see
  * gpuReaderWriteForwards below).
  * Errors follow the reference's convention: die() (utils.c:31-44).  There is no CPU fallback for the
- * GPU-backed paths; the one option this shim does not accelerate, -check (it verifies every reported match against
- * the decoded haplotypes on the CPU), is passed to the reference's renamed originals and says so on the log.
+ * GPU-backed paths: under -check the matches still come from the GPU and are verified one by one against the decoded
+ * haplotypes, as the reference's reportMatch does (pbwtMatch.c:33-58), which makes -check a self-test of the device
+ * results.  The reference's renamed originals stay linked but are not called.
  */
 #include "pbwt.h"
 #include "pbwtgpu.h"
@@ -53,10 +54,31 @@ void matchMaximalWithin (PBWT *p, void (*report)(int ai, int bi, int start, int 
 
 /* ---- reportMatch (pbwtMatch.c:46-58): the CLI printer; zero-length matches are dropped ---- */
 
+static uchar **checkHapsA, **checkHapsB ;	/* -check only: decoded haplotypes of the query side and the panel side */
+static int Ncheck ;
+
+static void checkMatchMaximal (uchar *x, uchar *y, int start, int end, int N)	/* pbwtMatch.c:33-44 */
+{
+  int i ;
+
+  if (start && (x[start-1] == y[start-1]))
+    die ("match not maximal - can extend backwards\n") ;
+  if (end < N && (x[end] == y[end]))
+    die ("match not maximal - can extend forwards\n") ;
+  for (i = start ; i < end ; ++i)
+    if (x[i] != y[i])
+      die ("match not a match at %d\n", i) ;
+}
+
+static void freeHaps (uchar **h, int M)
+{ int j ; for (j = 0 ; j < M ; ++j) free (h[j]) ; free (h) ; }
+
 static void reportMatchLine (int ai, int bi, int start, int end)
 {
   if (start == end) return ;
   printf ("MATCH\t%d\t%d\t%d\t%d\t%d\n", ai, bi, start, end, end-start) ;
+  if (isCheck)			/* the GPU's record is a real match and maximal */
+    checkMatchMaximal (checkHapsA[ai], checkHapsB[bi], start, end, Ncheck) ;
 }
 
 /* ---- pbwtLongMatches (pbwtMatch.c:148-183): -maxWithin is L == 0 ---- */
@@ -65,11 +87,7 @@ void pbwtLongMatches (PBWT *p, int L)
 {
   if (!p || !p->yz) die ("option -longWithin called without a PBWT") ;
   if (L < 0) die ("L %d for longWithin must be >= 0", L) ;
-  if (isCheck)
-    { fprintf (logFile, "pbwt_gpu: -check runs the reference CPU path\n") ;
-      ref_pbwtLongMatches (p, L) ;
-      return ;
-    }
+  if (isCheck) { checkHapsA = checkHapsB = pbwtHaplotypes (p) ; Ncheck = p->N ; }	/* pbwtMatch.c:156 */
   if (isStats)			/* -stats (pbwtMatch.c:130-131, 161-178): with -maxWithin a histogram of the reporters' match
 				   lengths replaces the MATCH lines; matchLongWithin2 never touches the histogram, so with
 				   -longWithin L the MATCH lines are printed and the summary is that of an empty histogram
@@ -105,9 +123,8 @@ void pbwtLongMatches (PBWT *p, int L)
       fprintf (logFile, "Average length %.1f\n", hTot/(double)nTot) ;
       arrayDestroy (hist) ;
       pbwtgpu_free (rec) ;
-      return ;
     }
-  if (L)			/* matchLongWithin2 (pbwtMatch.c:85-113) */
+  else if (L)			/* matchLongWithin2 (pbwtMatch.c:85-113) */
     { pbwtgpu_match *rec = 0 ;
       int64_t n = 0, i ;
       gpuCheck (pbwtgpu_long_within (gpuContext (), arrp(p->yz,0,uchar), arrayMax(p->yz), p->M, p->N,
@@ -117,6 +134,7 @@ void pbwtLongMatches (PBWT *p, int L)
     }
   else
     matchMaximalWithin (p, reportMatchLine) ;
+  if (isCheck) { freeHaps (checkHapsA, p->M) ; checkHapsA = checkHapsB = 0 ; }
 }
 
 /* ---- pbwtBuildReverse (pbwtCore.c:151-191); pbwtCore.c is compiled with -DpbwtBuildReverse=ref_pbwtBuildReverse ---- */
@@ -128,7 +146,6 @@ void pbwtBuildReverse (PBWT *p)
   uint8_t *zz = 0 ; int64_t nzz = 0 ;
   int *aFend, *aRend ;
 
-  if (isCheck) { ref_pbwtBuildReverse (p) ; return ; }	/* -check also dumps the reversed haplotypes */
   aFend = myalloc (p->M, int) ; aRend = myalloc (p->M, int) ;
   gpuCheck (pbwtgpu_build_reverse (gpuContext (), arrp(p->yz,0,uchar), arrayMax(p->yz), p->M, p->N, p->aFstart,
 				   aFend, &zz, &nzz, aRend), "pbwtgpu_build_reverse") ;
@@ -144,6 +161,14 @@ void pbwtBuildReverse (PBWT *p)
   p->aRend = aRend ;
   fprintf (logFile, "built reverse PBWT - size %ld\n", arrayMax(p->zz)) ;
   pbwtgpu_free (zz) ;
+  if (isCheck)			/* print out the reversed haplotypes, pbwtCore.c:181-187 */
+    { FILE *fp = fopen ("rev.haps","w") ;
+      Array tz = p->yz ; int *ta = p->aFstart ;
+      p->yz = p->zz ; p->aFstart = p->aRstart ;
+      pbwtWriteHaplotypes (fp, p) ;
+      p->yz = tz ; p->aFstart = ta ;
+      fclose (fp) ;
+    }
 }
 
 /* ---- matchSequencesSweep (pbwtMatch.c:363-443) ---- */
@@ -270,11 +295,7 @@ void matchSequencesSweep (PBWT *p, PBWT *q, void (*report)(int ai, int bi, int s
   int chunk = 8192 ;		/* queries per device call (include/pbwtgpu.h: pbwtgpu_match_sweep) */
 
   if (q->N != p->N) die ("query length in matchSequences %d != PBWT length %d", q->N, p->N) ;
-  if (isCheck)
-    { fprintf (logFile, "pbwt_gpu: -check runs the reference CPU path\n") ;
-      ref_matchSequencesSweep (p, q, report) ;
-      return ;
-    }
+  if (isCheck) { checkHapsA = pbwtHaplotypes (q) ; checkHapsB = pbwtHaplotypes (p) ; Ncheck = p->N ; }	/* pbwtMatch.c:373 */
   if (getenv ("PBWTGPU_QUERY_CHUNK") && atoi (getenv ("PBWTGPU_QUERY_CHUNK")) > 0)
     chunk = atoi (getenv ("PBWTGPU_QUERY_CHUNK")) ;
   if (q->M > chunk)
@@ -296,6 +317,7 @@ void matchSequencesSweep (PBWT *p, PBWT *q, void (*report)(int ai, int bi, int s
   /* summary line, pbwtMatch.c:438-439 */
   fprintf (logFile, "Average number of best matches including alternates %.1f, Average length %.1f, Av number per position %.1f\n",
 	   n/(double)q->M, totLen/(double)n, totLen/(double)(q->M*q->N)) ;
+  if (isCheck) { freeHaps (checkHapsA, q->M) ; freeHaps (checkHapsB, p->M) ; checkHapsA = checkHapsB = 0 ; }
 }
 
 void matchSequencesDynamic (PBWT *p, FILE *fp)	/* pbwtMatch.c:352-357 */

@@ -61,6 +61,9 @@ int pbwtgpu_max_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, 
   oracle_match *rec = (oracle_match *)malloc(sizeof(oracle_match) * (size_t)(n > 0 ? n : 1));
   if (!rec) return PBWTGPU_ERR_NOMEM;
   orc_max_within(yz, nyz, M, N, a_start, rec, n, &n);
+  if (getenv("PBWTGPU_MOCK_CORRUPT")) /* tests: a wrong device result that -check must catch */
+    for (int64_t i = 0; i < n; ++i)
+      if (rec[i].end - rec[i].start > 1) { rec[i].start -= rec[i].start > 0 ? 1 : -1; break; }
   *matches = (pbwtgpu_match *)rec;
   *nmatch = n;
   return ends(yz, nyz, M, N, a_start, a_end, d_end);

@@ -319,3 +319,30 @@ def test_reference_impute_with_chunked_queries(tmp_path):
         log = [ln for ln in open(d / "log").read().splitlines() if "\tsystem\t" not in ln and not ln.startswith("pbwt_gpu:")]
         outs[tag] = (log, open(d / "imp.pbwt", "rb").read(), open(d / "imp.haps", "rb").read())
     assert outs["ref"] == outs["shim"]
+
+
+@needs_ref_cli
+def test_check_option_verifies_device_records(tmp_path):
+    """-check: the matches still come from the device library and every printed one is verified against the decoded
+    haplotypes (the reference's checkMatchMaximal, pbwtMatch.c:33-58); -buildReverse also dumps rev.haps (pbwtCore.c:181-187).
+    Same stdout / log / files as the reference, and a corrupted device record must be fatal."""
+    rng = np.random.default_rng(31)
+    hap = founder_haps(rng, 36, 50, founders=4, flip=0.03)
+    write_vcfq(tmp_path / "p.vcfq", hap[:28])
+    write_vcfq(tmp_path / "q.vcfq", hap[28:])
+    subprocess.run([REF_CLI, "-readVcfq", str(tmp_path / "q.vcfq"), "-write", str(tmp_path / "q.pbwt")], check=True, capture_output=True)
+    outs = {}
+    for tag, exe in (("ref", REF_CLI), ("shim", CLI)):
+        d = tmp_path / tag
+        d.mkdir()
+        out = subprocess.run([exe, "-log", "log", "-check", "-readVcfq", str(tmp_path / "p.vcfq"), "-maxWithin", "-longWithin", "6",
+                              "-matchDynamic", str(tmp_path / "q.pbwt"), "-buildReverse"], check=True, capture_output=True, cwd=d).stdout
+        log = [ln for ln in open(d / "log").read().splitlines() if "\tsystem\t" not in ln]
+        outs[tag] = (out, log, open(d / "rev.haps", "rb").read())
+    assert outs["ref"] == outs["shim"] and len(outs["ref"][2]) > 0
+    bad = subprocess.run([CLI, "-check", "-readVcfq", str(tmp_path / "p.vcfq"), "-maxWithin"], capture_output=True,
+                         env={**os.environ, "PBWTGPU_MOCK_CORRUPT": "1"})
+    assert bad.returncode != 0 and b"FATAL ERROR: match not" in bad.stderr
+    good = subprocess.run([CLI, "-readVcfq", str(tmp_path / "p.vcfq"), "-maxWithin"], capture_output=True,
+                          env={**os.environ, "PBWTGPU_MOCK_CORRUPT": "1"})
+    assert good.returncode == 0  # without -check nobody looks
