@@ -223,17 +223,19 @@ static void matchSweepChunked (PBWT *p, PBWT *q, int chunk, void (*report)(int a
   /* 2. every chunk: its own PBWT (started from q's start order restricted to the chunk), swept against the panel */
   for (c = 0 ; c < nC ; ++c)
     { int c0 = c*chunk, cq = (c+1)*chunk <= Q ? chunk : Q - c0, m = 0 ;
-      int *aStart = myalloc (cq, int), *aEnd = myalloc (cq, int) ;
+      int *aStart = myalloc (cq, int), *aEnd = myalloc (cq, int), *aOrder ;
       uint8_t *yz = 0 ; int64_t nyz = 0 ;
       for (j = 0 ; j < Q ; ++j)
 	{ int h = q->aFstart ? q->aFstart[j] : j ;
 	  if (h >= c0 && h < c0 + cq) aStart[m++] = h - c0 ;
 	}
-      gpuCheck (pbwtgpu_build (gpuContext (), bits[c], cq, N, aStart, PBWTGPU_WANT_YZ, &yz, &nyz, aEnd, 0, 0, 0),
+      for (j = 0 ; j < cq && aStart[j] == j ; ++j) ;
+      aOrder = j < cq ? aStart : 0 ;	/* the usual case: q starts from the identity, and so does every chunk */
+      gpuCheck (pbwtgpu_build (gpuContext (), bits[c], cq, N, aOrder, PBWTGPU_WANT_YZ, &yz, &nyz, aEnd, 0, 0, 0),
 		"pbwtgpu_build (query chunk)") ;
       free (bits[c]) ;
       gpuCheck (pbwtgpu_match_sweep (gpuContext (), arrp(p->yz,0,uchar), arrayMax(p->yz), p->M, p->N, p->aFstart,
-				     yz, nyz, cq, aStart, &rec[c], &n[c], &nom[c], &nn[c]), "pbwtgpu_match_sweep (query chunk)") ;
+				     yz, nyz, cq, aOrder, &rec[c], &n[c], &nom[c], &nn[c]), "pbwtgpu_match_sweep (query chunk)") ;
       for (i = 0 ; i < n[c] ; ++i) rec[c][i].ai += c0 ;
       for (i = 0 ; i < nn[c] ; ++i) nom[c][i].query += c0 ;
       pbwtgpu_free (yz) ; free (aStart) ; free (aEnd) ;
