@@ -271,11 +271,23 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
           carry = max(carry, __reduce_max_sync(kFull, lmax));
           lmax = 0;
           int v = dv;  // inclusive max since the nearest head at or below this lane
+#ifdef PBWTGPU_SCAN_BY_DISTANCE
+          // Experimental (off by default, not yet measured on a B200): one distance to the nearest head at or below the
+          // lane replaces the per-stage window masks.  "No head in (lane - dl, lane]" is dl <= dist; lanes with
+          // dl > lane get their own value back from the shuffle, so they need no separate guard.
+          const int dist = lane - (31 - __clz((int)(H & (ltMask | laneBit))));  // lane + 1 when there is none
+#pragma unroll
+          for (int dl = 1; dl < 32; dl <<= 1) {
+            const int t = __shfl_up_sync(kFull, v, dl);
+            if (dl <= dist) v = max(v, t);
+          }
+#else
 #pragma unroll
           for (int dl = 1; dl < 32; dl <<= 1) {
             const int t = __shfl_up_sync(kFull, v, dl);
             if (lane >= dl && ((H >> (lane - dl + 1)) & ((1u << dl) - 1u)) == 0u) v = max(v, t);
           }
+#endif
           const int prev = __shfl_up_sync(kFull, v, 1);
           const bool isHead = H & laneBit;
           const bool headBelow = (H & ltMask) != 0u;
