@@ -346,3 +346,34 @@ def test_check_option_verifies_device_records(tmp_path):
     good = subprocess.run([CLI, "-readVcfq", str(tmp_path / "p.vcfq"), "-maxWithin"], capture_output=True,
                           env={**os.environ, "PBWTGPU_MOCK_CORRUPT": "1"})
     assert good.returncode == 0  # without -check nobody looks
+
+
+@needs_ref_cli
+@pytest.mark.parametrize("batch", ["5", "1000"])
+def test_other_readers_equal_reference(tmp_path, batch):
+    """The remaining readers of pbwtIO.c that step a cursor per parsed site -- -readHap / -readGen (pbwtReadLineFile,
+    :558-586), -readHapLegend (pbwtReadLineTwoFile, :590-623) and -readPhase (:777-826) -- through the shim's lazy cursor."""
+    rng = np.random.default_rng(17)
+    M, N = 20, 33
+    hap = (rng.random((M, N)) < 0.35).astype(np.uint8)
+    with open(tmp_path / "x.hap", "w") as fh:
+        for k in range(N):
+            fh.write(f"snp{k} rs{k} {1000 + k} A C " + " ".join(str(int(v)) for v in hap[:, k]) + "\n")
+    with open(tmp_path / "x.gen", "w") as fh:
+        for k in range(N):
+            tr = [["1 0 0", "0 1 0", "0 0 1"][int(hap[2 * i, k]) + int(hap[2 * i + 1, k])] for i in range(M // 2)]
+            fh.write(f"snp{k} rs{k} {1000 + k} A C " + " ".join(tr) + "\n")
+    with open(tmp_path / "x.hl.hap", "w") as fh, open(tmp_path / "x.hl.legend", "w") as lh:
+        for k in range(N):
+            fh.write(" ".join(str(int(v)) for v in hap[:, k]) + "\n")
+            lh.write(f"rs{k} {1000 + k} A C\n")
+    with open(tmp_path / "x.phase", "w") as fh:
+        fh.write(f"{M}\n{N}\nP " + " ".join(str(1000 + k) for k in range(N)) + "\n")
+        for h in range(M):
+            fh.write("".join(str(int(v)) for v in hap[h]) + "\n")
+    env = {**os.environ, "PBWTGPU_READER_BATCH": batch}
+    for reader in (["-readHap", tmp_path / "x.hap", "20"], ["-readGen", tmp_path / "x.gen", "20"],
+                   ["-readHapLegend", tmp_path / "x.hl.hap", tmp_path / "x.hl.legend", "20"], ["-readPhase", tmp_path / "x.phase"]):
+        (ro, rl), (so, sl) = both(tmp_path, [*reader, "-write", tmp_path / "@.pbwt", "-maxWithin"], env=env)
+        assert ro == so and rl == sl and len(ro) > 0, reader[0]
+        assert open(tmp_path / "ref.pbwt", "rb").read() == open(tmp_path / "shim.pbwt", "rb").read(), reader[0]
