@@ -99,7 +99,7 @@ def worker(rank, world, port, M, N, seed, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,M,N", [(2, 40, 60), (3, 64, 45), (2, 7, 9)])
+@pytest.mark.parametrize("world,M,N", [(2, 40, 60), (3, 64, 45), (2, 7, 9), (4, 33, 30)])
 def test_site_sharded_build_gloo(world, M, N):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
