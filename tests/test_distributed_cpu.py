@@ -111,3 +111,25 @@ def test_site_sharded_build_gloo(world, M, N):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+@pytest.mark.parametrize("M,N,seed", [(40, 48, 1), (64, 90, 2), (9, 30, 3)])
+def test_combine_is_associative(M, N, seed):
+    """The ranks fold the earlier shards' aggregates with a log-depth scan (pbwtgpu_shard_finish) and the windows of one
+    GPU with a Hillis-Steele scan (windows.cu); both rely on the combine operator being associative and on the fold
+    of all nodes being the state of the sequential sweep."""
+    rng = np.random.default_rng(seed)
+    hap = (rng.random((M, N)) < 0.25).astype(np.uint8)
+    hap[: M // 3] = hap[0]
+    a_start = rng.permutation(M).astype(np.int32)
+    x = O.pack_panel(hap)
+    cuts = [0, N // 4, N // 2, (3 * N) // 4, N]
+    nodes = [aggregate_node(x[cuts[i]:cuts[i + 1]], M, cuts[i + 1] - cuts[i], cuts[i], a_start) for i in range(4)]
+    A, B, C, D = nodes
+    left = combine(combine(combine(A, B, M), C, M), D, M)
+    tree = combine(combine(A, B, M), combine(C, D, M), M)
+    right = combine(A, combine(B, combine(C, D, M), M), M)
+    assert (left == tree).all() and (left == right).all()
+    _, a_ref, d_ref = O.port().build(x, M, N, a_start, with_d=True)
+    assert (split(left, M)[0] == a_ref).all()
+    assert (split(left, M)[1][1:M] == d_ref[1:M]).all()
