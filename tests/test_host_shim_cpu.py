@@ -377,3 +377,20 @@ def test_other_readers_equal_reference(tmp_path, batch):
         (ro, rl), (so, sl) = both(tmp_path, [*reader, "-write", tmp_path / "@.pbwt", "-maxWithin"], env=env)
         assert ro == so and rl == sl and len(ro) > 0, reader[0]
         assert open(tmp_path / "ref.pbwt", "rb").read() == open(tmp_path / "shim.pbwt", "rb").read(), reader[0]
+
+
+@needs_ref_cli
+@pytest.mark.parametrize("batch", ["6", "1000"])
+def test_subsample_rebuild_equals_reference(tmp_path, batch):
+    """-subsample start n (pbwtSubSample, pbwtSample.c:57-93) rebuilds the panel of the selected haplotypes with the same
+    per-site gather + pbwtCursorWriteForwards step as the readers; pbwtSample.c is compiled with the same two renames,
+    so the rebuild is batched onto the device too.  File and matches of the sub-panel must be the reference's."""
+    rng = np.random.default_rng(41)
+    hap = founder_haps(rng, 40, 70)
+    write_vcfq(tmp_path / "x.vcfq", hap)
+    env = {**os.environ, "PBWTGPU_READER_BATCH": batch}
+    (ro, rl), (so, sl) = both(tmp_path, ["-readVcfq", tmp_path / "x.vcfq", "-subsample", "5", "20", "-write", tmp_path / "@.pbwt", "-maxWithin",
+                                         "-subsample", "2", "7", "-write", tmp_path / "@.2.pbwt"], env=env)
+    assert ro == so and rl == sl and len(ro) > 0
+    for f in ("pbwt", "2.pbwt"):
+        assert open(tmp_path / f"ref.{f}", "rb").read() == open(tmp_path / f"shim.{f}", "rb").read()
