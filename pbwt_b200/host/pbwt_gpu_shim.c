@@ -199,14 +199,15 @@ static void matchSweepChunked (PBWT *p, PBWT *q, int chunk, void (*report)(int a
   int64_t *n = mycalloc (nC, int64_t), *nn = mycalloc (nC, int64_t), *ir = mycalloc (nC, int64_t), *in = mycalloc (nC, int64_t) ;
   int64_t i, total = 0 ;
   long totLen = 0 ;
-  int *rank = myalloc (Q, int) ;
+  int *rank = myalloc (Q, int), *wpc = myalloc (nC, int) ;
   QGroup *grp = myalloc (Q, QGroup), *ngrp = myalloc (Q, QGroup) ;
   PbwtCursor *uq ;
 
   /* 1. un-sort the query columns into per-chunk bit columns */
   for (c = 0 ; c < nC ; ++c)
     { int cq = (c+1)*chunk <= Q ? chunk : Q - c*chunk ;
-      bits[c] = mycalloc ((size_t)pbwtgpu_words_per_col (cq) * (N > 0 ? N : 1), uint32_t) ;
+      wpc[c] = pbwtgpu_words_per_col (cq) ;
+      bits[c] = mycalloc ((size_t)wpc[c] * (N > 0 ? N : 1), uint32_t) ;
     }
   uq = pbwtCursorCreate (q, TRUE, TRUE) ;
   for (k = 0 ; k < N ; ++k)
@@ -214,11 +215,12 @@ static void matchSweepChunked (PBWT *p, PBWT *q, int chunk, void (*report)(int a
 	if (uq->y[j])
 	  { int h = uq->a[j], l ;
 	    c = h / chunk ; l = h - c*chunk ;
-	    bits[c][(size_t)k * pbwtgpu_words_per_col ((c+1)*chunk <= Q ? chunk : Q - c*chunk) + (l >> 5)] |= 1u << (l & 31) ;
+	    bits[c][(size_t)k * wpc[c] + (l >> 5)] |= 1u << (l & 31) ;
 	  }
       pbwtCursorForwardsRead (uq) ;
     }
   pbwtCursorDestroy (uq) ;
+  free (wpc) ;
 
   /* 2. every chunk: its own PBWT (started from q's start order restricted to the chunk), swept against the panel */
   for (c = 0 ; c < nC ; ++c)
