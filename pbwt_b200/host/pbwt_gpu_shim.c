@@ -192,7 +192,7 @@ static int qGroupOrder (const void *a, const void *b)
 static void matchSweepChunked (PBWT *p, PBWT *q, int chunk, void (*report)(int ai, int bi, int start, int end),
 			       int64_t *nOut, long *totLenOut)
 {
-  int Q = q->M, N = q->N, nC = (Q + chunk - 1) / chunk, c, j, k ;
+  int Q = q->M, N = q->N, nC = (Q + chunk - 1) / chunk, c, j, k ;	/* chunk: the most one device call takes */
   uint32_t **bits = myalloc (nC, uint32_t*) ;
   pbwtgpu_match **rec = mycalloc (nC, pbwtgpu_match*) ;
   pbwtgpu_nomatch **nom = mycalloc (nC, pbwtgpu_nomatch*) ;
@@ -202,6 +202,8 @@ static void matchSweepChunked (PBWT *p, PBWT *q, int chunk, void (*report)(int a
   int *rank = myalloc (Q, int), *wpc = myalloc (nC, int) ;
   QGroup *grp = myalloc (Q, QGroup), *ngrp = myalloc (Q, QGroup) ;
   PbwtCursor *uq ;
+
+  chunk = (Q + nC - 1) / nC ;	/* equal chunks: no tiny last one */
 
   /* 1. un-sort the query columns into per-chunk bit columns */
   for (c = 0 ; c < nC ; ++c)
