@@ -199,16 +199,16 @@ static void matchSweepChunked (PBWT *p, PBWT *q, int chunk, void (*report)(int a
   int64_t *n = mycalloc (nC, int64_t), *nn = mycalloc (nC, int64_t), *ir = mycalloc (nC, int64_t), *in = mycalloc (nC, int64_t) ;
   int64_t i, total = 0 ;
   long totLen = 0 ;
-  int *rank = myalloc (Q, int), *wpc = myalloc (nC, int) ;
+  int *rank = myalloc (Q, int), *wpc = myalloc (nC, int), *cstart = myalloc (nC+1, int), *chunkOf = myalloc (Q, int) ;
   QGroup *grp = myalloc (Q, QGroup), *ngrp = myalloc (Q, QGroup) ;
   PbwtCursor *uq ;
 
-  chunk = (Q + nC - 1) / nC ;	/* equal chunks: no tiny last one */
+  for (c = 0 ; c <= nC ; ++c) cstart[c] = (int) ((long)c * Q / nC) ;	/* chunk c = queries [cstart[c], cstart[c+1]): sizes differ by at most one */
+  for (c = 0 ; c < nC ; ++c) for (j = cstart[c] ; j < cstart[c+1] ; ++j) chunkOf[j] = c ;
 
   /* 1. un-sort the query columns into per-chunk bit columns */
   for (c = 0 ; c < nC ; ++c)
-    { int cq = (c+1)*chunk <= Q ? chunk : Q - c*chunk ;
-      wpc[c] = pbwtgpu_words_per_col (cq) ;
+    { wpc[c] = pbwtgpu_words_per_col (cstart[c+1] - cstart[c]) ;
       bits[c] = mycalloc ((size_t)wpc[c] * (N > 0 ? N : 1), uint32_t) ;
     }
   uq = pbwtCursorCreate (q, TRUE, TRUE) ;
@@ -216,17 +216,17 @@ static void matchSweepChunked (PBWT *p, PBWT *q, int chunk, void (*report)(int a
     { for (j = 0 ; j < Q ; ++j)
 	if (uq->y[j])
 	  { int h = uq->a[j], l ;
-	    c = h / chunk ; l = h - c*chunk ;
+	    c = chunkOf[h] ; l = h - cstart[c] ;
 	    bits[c][(size_t)k * wpc[c] + (l >> 5)] |= 1u << (l & 31) ;
 	  }
       pbwtCursorForwardsRead (uq) ;
     }
   pbwtCursorDestroy (uq) ;
-  free (wpc) ;
+  free (wpc) ; free (chunkOf) ;
 
   /* 2. every chunk: its own PBWT (started from q's start order restricted to the chunk), swept against the panel */
   for (c = 0 ; c < nC ; ++c)
-    { int c0 = c*chunk, cq = (c+1)*chunk <= Q ? chunk : Q - c0, m = 0 ;
+    { int c0 = cstart[c], cq = cstart[c+1] - c0, m = 0 ;
       int *aStart = myalloc (cq, int), *aEnd = myalloc (cq, int), *aOrder ;
       uint8_t *yz = 0 ; int64_t nyz = 0 ;
       for (j = 0 ; j < Q ; ++j)
@@ -244,7 +244,7 @@ static void matchSweepChunked (PBWT *p, PBWT *q, int chunk, void (*report)(int a
       for (i = 0 ; i < nn[c] ; ++i) nom[c][i].query += c0 ;
       pbwtgpu_free (yz) ; free (aStart) ; free (aEnd) ;
     }
-  free (bits) ;
+  free (bits) ; free (cstart) ;
 
   /* 3. merge site by site in the order of the whole query PBWT */
   uq = pbwtCursorCreate (q, TRUE, TRUE) ;
