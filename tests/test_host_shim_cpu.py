@@ -394,3 +394,24 @@ def test_subsample_rebuild_equals_reference(tmp_path, batch):
     assert ro == so and rl == sl and len(ro) > 0
     for f in ("pbwt", "2.pbwt"):
         assert open(tmp_path / f"ref.{f}", "rb").read() == open(tmp_path / f"shim.{f}", "rb").read()
+
+
+REF_TEST = "/root/reference/test"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_TEST, "merge.1.tab")), reason="the reference's test fixtures are not present")
+def test_reference_test_pl_cases(tmp_path):
+    """The cases of the reference's own test/test.pl that need no htslib, replayed through the drop-in build:
+    test_pbwt (merge.1, merge.2: -readVcfq -> -write / -writeSites, then -read -> -haps), test_merge and
+    test_merge_sites (-merge of the two files), against the reference's expected outputs test/merge.*.out / .sites."""
+    def sh(cmd):
+        return subprocess.run(["/bin/bash", "-o", "pipefail", "-c", cmd], check=True, capture_output=True, env={**os.environ, "PBWTGPU_READER_BATCH": "3"})
+    for name in ("merge.1", "merge.2"):
+        sh(f"{CLI} -readVcfq {REF_TEST}/{name}.tab -write {tmp_path}/{name}.pbwt -writeSites {tmp_path}/{name}.sites")
+        sh(f"{CLI} -read {tmp_path}/{name}.pbwt -haps {tmp_path}/{name}.out")
+        assert open(tmp_path / f"{name}.out").read() == open(f"{REF_TEST}/{name}.out").read()
+    files = f"{tmp_path}/merge.1.pbwt {tmp_path}/merge.2.pbwt"
+    sh(f"{CLI} -merge {files} -write - | {CLI} -read - -haps {tmp_path}/merge.12.out")
+    assert open(tmp_path / "merge.12.out").read() == open(f"{REF_TEST}/merge.12.out").read()
+    sh(f"{CLI} -merge {files} -write - -writeSites {tmp_path}/merge.12.sites > /dev/null")
+    assert open(tmp_path / "merge.12.sites").read() == open(f"{REF_TEST}/merge.12.sites").read()
