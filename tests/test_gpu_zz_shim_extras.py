@@ -53,3 +53,24 @@ def test_cli_stats_longwithin(tmp_path):
     out = subprocess.run([CLI, "-log", str(lg), "-stats", "-read", str(pb), "-longWithin", "20"], check=True, capture_output=True).stdout
     assert hashlib.md5(out).hexdigest() == str(lw["omni_L20_md5"])
     assert "Average 0.0 matches per sample" in open(lg).read()
+
+
+@needs_cli
+def test_cli_read_vcf_gt_config1(tmp_path):
+    """BASELINE config 1's command line, `pbwt -readVcfGT OMNI.vcf -maxWithin`, through the text VCF reader of the drop-in
+    (pbwt_b200/host/vcf_text.c) and the batched device build.  The VCF is regenerated from the golden OMNI genotypes
+    (the reference's fixture does not travel to the GPU box); known answers: .pbwt md5 d2753c04..., stdout md5 b1412a0e...."""
+    import oracle_lib as O
+    g = np.load(os.path.join(GOLD, "omni.npz"))
+    M, N = int(g["M"]), int(g["N"])
+    hap = O.unpack_panel(g["xbits"], M)
+    vcf, pb = tmp_path / "omni.vcf", tmp_path / "omni.pbwt"
+    with open(vcf, "w") as fh:
+        fh.write("##fileformat=VCFv4.2\n##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n")
+        fh.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"S{i}" for i in range(M // 2)) + "\n")
+        for k in range(N):
+            fh.write(f"20\t{1000 + k}\t.\tA\tC\t.\tPASS\t.\tGT\t" + "\t".join(f"{int(hap[2 * i, k])}|{int(hap[2 * i + 1, k])}" for i in range(M // 2)) + "\n")
+    out = subprocess.run([CLI, "-readVcfGT", str(vcf), "-write", str(pb), "-maxWithin"], check=True, capture_output=True,
+                         env={**os.environ, "PBWTGPU_READER_BATCH": "16"}).stdout
+    assert hashlib.md5(open(pb, "rb").read()).hexdigest() == str(g["pbwt_md5"])
+    assert hashlib.md5(out).hexdigest() == str(g["maxwithin_stdout_md5"])

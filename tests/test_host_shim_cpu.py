@@ -415,3 +415,66 @@ def test_reference_test_pl_cases(tmp_path):
     assert open(tmp_path / "merge.12.out").read() == open(f"{REF_TEST}/merge.12.out").read()
     sh(f"{CLI} -merge {files} -write - -writeSites {tmp_path}/merge.12.sites > /dev/null")
     assert open(tmp_path / "merge.12.sites").read() == open(f"{REF_TEST}/merge.12.sites").read()
+
+
+# ---- -readVcfGT without htslib (pbwt_b200/host/vcf_text.c) ----
+
+def write_vcf(path, hap, chrom="20", pos0=1000, phased=True):
+    """Diploid text VCF of a [M, N] haplotype matrix (sample i = haplotypes 2i, 2i+1)."""
+    M, N = hap.shape
+    sep = "|" if phased else "/"
+    with open(path, "w") as fh:
+        fh.write("##fileformat=VCFv4.2\n##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n")
+        fh.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"S{i}" for i in range(M // 2)) + "\n")
+        for k in range(N):
+            gts = "\t".join(f"{int(hap[2 * i, k])}{sep}{int(hap[2 * i + 1, k])}" for i in range(M // 2))
+            fh.write(f"{chrom}\t{pos0 + k}\t.\tA\tC\t.\tPASS\t.\tGT\t{gts}\n")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_TEST, "OMNI.vcf")), reason="the reference's test fixtures are not present")
+def test_baseline_config1_command_line(tmp_path):
+    """BASELINE.json configs[0], verbatim: `pbwt -readVcfGT test/OMNI.vcf -maxWithin` (plus -write).  The reference needs
+    htslib for it; the drop-in's text reader (vcf_text.c, following pbwtHtslib.c:52-172) feeds the batched device build.
+    Known answers of SURVEY section 8c: .pbwt md5 d2753c04..., -maxWithin stdout 21,883 lines md5 b1412a0e...."""
+    pb, lg = tmp_path / "omni.pbwt", tmp_path / "log"
+    out = run("-log", lg, "-readVcfGT", os.path.join(REF_TEST, "OMNI.vcf"), "-write", pb, "-maxWithin",
+              env={**os.environ, "PBWTGPU_READER_BATCH": "7"})
+    assert hashlib.md5(open(pb, "rb").read()).hexdigest() == "d2753c044392ec4f474c7061cff773e9"
+    assert len(out.splitlines()) == 21883 and hashlib.md5(out).hexdigest() == "b1412a0e3057b3e92ade2cee7c4a4824"
+    assert "with 1376 sample names and 38 sites on chromosome 20: M, N are 2752, 38" in open(lg).read()
+
+
+@needs_ref_cli
+@pytest.mark.parametrize("phased", [True, False])
+def test_read_vcf_gt_equals_vcfq_route(tmp_path, phased):
+    """Biallelic, no missing: -readVcfGT must give the file the reference builds from the same genotypes via -readVcfq."""
+    rng = np.random.default_rng(51)
+    hap = founder_haps(rng, 30, 45)
+    write_vcf(tmp_path / "x.vcf", hap, phased=phased)
+    write_vcfq(tmp_path / "x.vcfq", hap)
+    subprocess.run([REF_CLI, "-readVcfq", str(tmp_path / "x.vcfq"), "-write", str(tmp_path / "ref.pbwt")], check=True, capture_output=True)
+    run("-readVcfGT", tmp_path / "x.vcf", "-write", tmp_path / "shim.pbwt", "-writeSites", tmp_path / "shim.sites", env={**os.environ, "PBWTGPU_READER_BATCH": "8"})
+    assert open(tmp_path / "ref.pbwt", "rb").read() == open(tmp_path / "shim.pbwt", "rb").read()
+    assert open(tmp_path / "shim.sites").read().splitlines()[0] == "20\t1000\tA\tC"
+
+
+def test_read_vcf_gt_multiallelic_missing_haploid(tmp_path):
+    """The record handling of pbwtHtslib.c:94-168: multi-allelic records become one site per ALT allele (y = allele == i),
+    missing alleles read as 0 and are counted, all-haploid records as homozygous diploid, ALT '.' stays a site, records
+    without GT are skipped, reading stops at the second chromosome, REF/ALT are upper-cased."""
+    vcf = tmp_path / "m.vcf"
+    with open(vcf, "w") as fh:
+        fh.write("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tA\tB\tC\n")
+        fh.write("X\t10\t.\tt\t.\t.\t.\t.\tGT\t.\t.\t.\n")                          # haploid, all missing, no ALT
+        fh.write("X\t20\t.\tT\tc\t9\tPASS\tDP=3\tGT:DP\t0/1:5\t1/1:7\t1|0:2\n")
+        fh.write("X\t30\t.\tT\tTTTA,TA\t.\t.\t.\tDP:GT\t3:0/2\t4:0/1\t5:1/2\n")       # two sites
+        fh.write("X\t40\t.\tA\tAC\t.\t.\t.\tGT\t0|1\t0|1\t./.\n")                     # missing diploid
+        fh.write("X\t50\t.\tG\tC\t.\t.\t.\tDP\t1\t2\t3\n")                            # no GT: skipped
+        fh.write("X\t60\t.\tG\tC\t.\t.\t.\tGT\t0\t1\t1\n")                            # haploid line
+        fh.write("Y\t70\t.\tG\tC\t.\t.\t.\tGT\t0|1\t0|1\t0|1\n")                      # another chromosome: stop
+    lg = tmp_path / "log"
+    run("-log", lg, "-readVcfGT", vcf, "-haps", tmp_path / "h.out", "-writeSites", tmp_path / "s.out")
+    assert open(tmp_path / "h.out").read().split() == ["000000", "011110", "000110", "010001", "010100", "001111"]
+    assert open(tmp_path / "s.out").read().splitlines() == ["X\t10\tT\t.", "X\t20\tT\tC", "X\t30\tT\tTTTA", "X\t30\tT\tTA", "X\t40\tA\tAC", "X\t60\tG\tC"]
+    log = open(lg).read()
+    assert "with 3 sample names and 6 sites on chromosome X: M, N are 6, 6" in log and "8 missing values at 2 sites" in log
