@@ -478,3 +478,22 @@ def test_read_vcf_gt_multiallelic_missing_haploid(tmp_path):
     assert open(tmp_path / "s.out").read().splitlines() == ["X\t10\tT\t.", "X\t20\tT\tC", "X\t30\tT\tTTTA", "X\t30\tT\tTA", "X\t40\tA\tAC", "X\t60\tG\tC"]
     log = open(lg).read()
     assert "with 3 sample names and 6 sites on chromosome X: M, N are 6, 6" in log and "8 missing values at 2 sites" in log
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_TEST, "refImpute.out.vcf")), reason="the reference's test fixtures are not present")
+def test_reference_test_pl_reference_impute(tmp_path):
+    """test_pbwt_reference_impute of the reference's test/test.pl: -readVcfGT OMNI.vcf -writeAll, then
+    -readVcfGT refImpute.in.vcf -referenceImpute OMNI.  The reference writes a VCF (htslib); here the imputed haplotypes
+    and sites are written with -haps / -writeSites and compared with the GT columns and the fixed fields of the expected
+    test/refImpute.out.vcf."""
+    subprocess.run([CLI, "-readVcfGT", os.path.join(REF_TEST, "OMNI.vcf"), "-writeAll", "OMNI"], check=True, capture_output=True, cwd=tmp_path)
+    subprocess.run([CLI, "-readVcfGT", os.path.join(REF_TEST, "refImpute.in.vcf"), "-referenceImpute", "OMNI", "-haps", "out.haps",
+                    "-writeSites", "out.sites"], check=True, capture_output=True, cwd=tmp_path)
+    want_haps, want_sites = [], []
+    for ln in open(os.path.join(REF_TEST, "refImpute.out.vcf")):
+        if not ln.startswith("#"):
+            f = ln.rstrip("\n").split("\t")
+            want_sites.append("\t".join((f[0], f[1], f[3], f[4])))
+            want_haps.append("".join(g.replace("|", "").replace("/", "") for g in f[9:]))
+    assert open(tmp_path / "out.haps").read().split() == want_haps and len(want_haps) == 2964
+    assert open(tmp_path / "out.sites").read().splitlines() == want_sites
