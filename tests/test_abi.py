@@ -50,3 +50,23 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle_lib" not in txt and "libpbwt_oracle" not in txt and "libpbwtref" not in txt, f
                 assert "mock_pbwtgpu" not in txt and "host_mock" not in txt, f  # the CPU stand-in of tests/host_mock stays in tests/
+
+
+def test_drop_in_cli_fails_loudly_without_device(tmp_path):
+    """The real drop-in binary (linked with libpbwtgpu.so, not the test stand-in) must die() when there is no B200."""
+    import subprocess
+
+    import numpy as np
+    import torch
+
+    cli = os.path.join(ROOT, "pbwt_b200", "host", "_build", "pbwt_gpu")
+    if torch.cuda.is_available() or not os.path.exists(cli):
+        pytest.skip("a GPU is present, or pbwt_gpu is not built")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "merge1.npz"))
+    M, N = int(g["M"]), int(g["N"])
+    pb = tmp_path / "x.pbwt"
+    with open(pb, "wb") as fh:
+        fh.write(b"PBW3" + np.array([M, N], "<i4").tobytes() + np.arange(M, dtype="<i4").tobytes() + np.asarray(g["a_end"], "<i4").tobytes() +
+                 np.array([len(g["yz"])], "<i8").tobytes() + b"    " + np.asarray(g["yz"], np.uint8).tobytes())
+    r = subprocess.run([cli, "-read", str(pb), "-maxWithin"], capture_output=True)
+    assert r.returncode != 0 and b"no CPU fallback" in r.stderr and r.stdout == b""
