@@ -3,17 +3,18 @@
  * The reference reads VCF/BCF through htslib (pbwtHtslib.c:52-172), an un-vendored third-party library that is not
  * part of this image.  This file provides the same entry point, PBWT *pbwtReadVcfGT (char *filename), for what the
  * reference's own fixtures use (test/OMNI.vcf, BASELINE config 1: `pbwt -readVcfGT test/OMNI.vcf -maxWithin`):
- * uncompressed text VCF with a GT field.  It follows pbwtReadVcfGT step by step -- samples (:30-35), one chromosome
+ * text VCF with a GT field, plain or gzip/bgzip-compressed (zlib, which the reference links anyway).  It follows pbwtReadVcfGT step by step -- samples (:30-35), one chromosome
  * only (:78-79), upper-cased REF/ALT (:81-83,141-143), haploid lines as homozygous diploid (:94-110), missing alleles
  * as 0 plus the zMissing / missingOffset arrays (:111-125,150-161), multi-allelic records split into one site per
  * ALT allele with y = (x == i) (:127-168), ALT "." kept as a site with no carriers, the checkpoint hook (:170) -- and
  * hands every column to the shim's lazy cursor (gpuReaderWriteForwards / gpuReaderToAFend, pbwt_gpu_shim.c), so the
  * per-site gather + pbwtCursorWriteForwards of :145-146 runs batched on the GPU like the other readers.
- * Compressed VCF and BCF, -readVcfPL and -writeVcf still need htslib and die() saying so.
+ * BCF, -readVcfPL and -writeVcf still need htslib and die() saying so.
  */
 #define _GNU_SOURCE	/* getline, strndup */
 #include <ctype.h>
 #include <sys/types.h>
+#include <zlib.h>
 #include "pbwt.h"
 
 void gpuReaderWriteForwards (PbwtCursor *u) ;	/* pbwt_gpu_shim.c */
@@ -57,9 +58,24 @@ static char *nextField (char **cp, int *len)
   return s ;
 }
 
+/* getline() over a gzFile: the whole line including its newline, buffer grown as needed; 0 at end of file */
+static ssize_t gzGetLine (char **line, size_t *cap, gzFile fp)
+{
+  size_t n = 0 ;
+  if (!*line) { *cap = 1 << 16 ; *line = myalloc (*cap, char) ; }
+  for (;;)
+    { if (!gzgets (fp, *line + n, (int)(*cap - n))) break ;
+      n += strlen (*line + n) ;
+      if (n && (*line)[n-1] == '\n') break ;
+      if (n + 1 >= *cap) { char *t = myalloc (*cap * 2, char) ; memcpy (t, *line, n + 1) ; free (*line) ; *line = t ; *cap *= 2 ; }
+      else if (gzeof (fp)) break ;	/* last line without a newline */
+    }
+  return (ssize_t) n ;
+}
+
 PBWT *pbwtReadVcfGT (char *filename)
 {
-  FILE *fp = strcmp (filename, "-") ? fopen (filename, "r") : stdin ;
+  gzFile fp = strcmp (filename, "-") ? gzopen (filename, "r") : gzdopen (0, "r") ;	/* reads plain text as well */
   char *line = 0 ; size_t cap = 0 ; ssize_t got ;
   PBWT *p = 0 ;
   PbwtCursor *u = 0 ;
@@ -69,13 +85,14 @@ PBWT *pbwtReadVcfGT (char *filename)
   int nMissingSites = 0, nSamples = 0, i, j ;
 
   if (!fp) die ("failed to open good vcf file\n") ;
-  { int c0 = getc (fp), c1 = getc (fp) ;
-    if (c0 == 0x1f && c1 == 0x8b) die ("pbwtReadVcfGT(%s): compressed VCF / BCF needs htslib, which is not available in this build", filename) ;
-    if (c1 != EOF) ungetc (c1, fp) ;
-    if (c0 != EOF) ungetc (c0, fp) ;	/* (two characters of push-back: fine on glibc, and the file starts with '#') */
-  }
+  gzbuffer (fp, 1 << 20) ;
+  if (strcmp (filename, "-"))		/* (a pipe cannot be rewound) */
+    { int c0 = gzgetc (fp), c1 = gzgetc (fp), c2 = gzgetc (fp) ;
+      if (c0 == 'B' && c1 == 'C' && c2 == 'F') die ("pbwtReadVcfGT(%s): BCF needs htslib, which is not available in this build", filename) ;
+      gzrewind (fp) ;
+    }
 
-  while ((got = getline (&line, &cap, fp)) > 0)
+  while ((got = gzGetLine (&line, &cap, fp)) > 0)
     { char *cp = line, *f ; int len ;
       if (line[0] == '#' && line[1] == '#') continue ;
       if (line[0] == '#')			/* #CHROM POS ID REF ALT QUAL FILTER INFO FORMAT samples... */
@@ -200,7 +217,7 @@ PBWT *pbwtReadVcfGT (char *filename)
   gpuReaderToAFend (u, p) ;
 
   free (line) ; free (gt) ; free (x) ; free (xMissing) ; pbwtCursorDestroy (u) ;
-  if (fp != stdin) fclose (fp) ;
+  gzclose (fp) ;
 
   fprintf (logFile, "read genotypes from %s with %ld sample names and %ld sites on chromosome %s: M, N are %d, %d\n",
 	   filename, arrayMax(p->samples)/2, arrayMax(p->sites), p->chrom, p->M, p->N) ;

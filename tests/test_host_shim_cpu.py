@@ -497,3 +497,28 @@ def test_reference_test_pl_reference_impute(tmp_path):
             want_haps.append("".join(g.replace("|", "").replace("/", "") for g in f[9:]))
     assert open(tmp_path / "out.haps").read().split() == want_haps and len(want_haps) == 2964
     assert open(tmp_path / "out.sites").read().splitlines() == want_sites
+
+
+@needs_ref_cli
+def test_read_vcf_gt_compressed_and_stdin(tmp_path):
+    """The same VCF plain, gzip-compressed, bgzip-like (several concatenated gzip members, a line split across two of
+    them) and on stdin must all give the reference's file; BCF is refused with a message."""
+    import gzip
+    rng = np.random.default_rng(52)
+    hap = founder_haps(rng, 24, 40)
+    write_vcf(tmp_path / "x.vcf", hap)
+    write_vcfq(tmp_path / "x.vcfq", hap)
+    subprocess.run([REF_CLI, "-readVcfq", str(tmp_path / "x.vcfq"), "-write", str(tmp_path / "ref.pbwt")], check=True, capture_output=True)
+    want = open(tmp_path / "ref.pbwt", "rb").read()
+    text = open(tmp_path / "x.vcf", "rb").read()
+    open(tmp_path / "x.vcf.gz", "wb").write(gzip.compress(text))
+    cut = [0, len(text) // 3 + 7, 2 * len(text) // 3 + 5, len(text)]
+    open(tmp_path / "x.bgz.vcf.gz", "wb").write(b"".join(gzip.compress(text[a:b]) for a, b in zip(cut, cut[1:])))
+    for name in ("x.vcf", "x.vcf.gz", "x.bgz.vcf.gz"):
+        run("-readVcfGT", tmp_path / name, "-write", tmp_path / "out.pbwt", env={**os.environ, "PBWTGPU_READER_BATCH": "9"})
+        assert open(tmp_path / "out.pbwt", "rb").read() == want, name
+    subprocess.run([CLI, "-readVcfGT", "-", "-write", str(tmp_path / "stdin.pbwt")], input=text, check=True, capture_output=True)
+    assert open(tmp_path / "stdin.pbwt", "rb").read() == want
+    open(tmp_path / "x.bcf", "wb").write(gzip.compress(b"BCF\x02\x02" + b"\0" * 64))
+    bad = subprocess.run([CLI, "-readVcfGT", str(tmp_path / "x.bcf")], capture_output=True)
+    assert bad.returncode != 0 and b"BCF needs htslib" in bad.stderr
