@@ -17,7 +17,7 @@ from test_gpu_cli import GOLD, ROOT, write_pbwt
 
 MOCK_DIR = os.path.join(ROOT, "tests", "host_mock")
 HOST_OBJ = os.path.join(ROOT, "pbwt_b200", "host", "_build", "pbwt_gpu_shim.o")
-CLI = os.path.join(MOCK_DIR, "_build", "pbwt_hostcheck")
+CLI = os.environ.get("PBWT_HOSTCHECK", os.path.join(MOCK_DIR, "_build", "pbwt_hostcheck"))  # override: e.g. an ASan/UBSan build of the same link
 SELFCHECK = os.path.join(MOCK_DIR, "_build", "shim_selfcheck")
 
 
