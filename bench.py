@@ -5,16 +5,23 @@
 
 A "step" is one pass of the hot path over one synthetic panel: build (a[], d[], pack3 stream) +
 matchMaximalWithin over M x N haplotype-sites.  metric = haplotype-sites/s.
+  parity gate : before anything is timed, the GPU's build + maxWithin of the first sites of the workload must hash to
+          the same values as the reference's (the cpu_baseline leg computes them); on a mismatch no value is printed.
   value : panel resident in HBM, CUDA events on the launching stream around each step.
-  e2e   : the same step through the public host-buffer API: pinned host bit columns -> H2D ->
-          kernels -> D2H of pack3 stream, aFend, d[] and every match record.
+  e2e   : the same step through the C-ABI call the host shim makes (pbwtgpu_build on host bit columns; outputs land in
+          host buffers owned by the library), host<->device copies inside the timed region.
+  configs : BASELINE.json configs[2..4] (100k x 200k build + pack3; 1M x 100k build with d; 1,000 queries vs a 100k
+          panel), each with its own roofline fraction and CPU baseline; at N > 1 config 4 and the query sweep run
+          site-sharded over the N GPUs.
   roofline / cpu_baseline: see DESIGN.md section "Measurement".
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -27,11 +34,45 @@ METRIC = "haplotype-sites/sec build+maxWithin"
 UNIT = "haplotype-sites/s"
 M_DEFAULT, N_DEFAULT = 10000, 100000  # BASELINE.json configs[1]
 SEED, L_RECOMB, MU = 0x5EED0002, 2000, 2.0
-BYTES_PER_HS = 16.125  # read+write a, read+write d, one allele bit
+BYTES_AD, BYTES_A = 16.125, 8.125  # algorithmic bytes per haplotype-site with / without d
+L2_NOTE = ("GPU arm: 256 MiB device memset between timed steps, per-step CUDA events on the launching stream; "
+           "CPU arm: one thread, nothing to flush")
 
 
 def workload_name(M, N):
     return f"synthetic mosaic panel {M} haplotypes x {N} biallelic sites, build + maxWithin"
+
+
+def base_config(M, n_total, world, nyz_all, nmatch_all):
+    """The workload description, identical in the GPU arm and the reference arm."""
+    return {"workload": workload_name(M, n_total), "haplotypes": M, "sites": n_total, "sites_per_gpu": n_total // world,
+            "generator": f"seed {SEED:#x}, L={L_RECOMB}, mu={MU}", "l2": L2_NOTE,
+            "matches_per_haplotype": nmatch_all / M, "pack3_bytes": nyz_all}
+
+
+def host_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return {"cpu_model": model, "nproc": os.cpu_count(), "nproc_allowed": len(os.sched_getaffinity(0))}
+
+
+class PinnedToOneCore:
+    """taskset for the CPU legs: the calling thread is pinned to one core (the reference is single-threaded)."""
+
+    def __enter__(self):
+        self.saved = os.sched_getaffinity(0)
+        self.core = max(self.saved)
+        os.sched_setaffinity(0, {self.core})
+        return self
+
+    def __exit__(self, *a):
+        os.sched_setaffinity(0, self.saved)
 
 
 class ClockSampler:
@@ -72,20 +113,185 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
-def time_reference(xbits, M, N_cpu):
-    """The reference's own single-threaded CPU path on the first N_cpu sites (oracle/_ref when it was
-    compiled here and travelled, else the oracle port)."""
+def oracle():
+    """(implementation, kind): the compiled reference when oracle/_ref exists, else the pinned port.  Only the
+    cpu_baseline / parity-gate leg and --impl reference come here; nothing on the timed GPU path does."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
 
     ref = O.reference()
-    kind = "reference" if ref is not None else "port"
-    imp = ref if ref is not None else O.port()
-    tb, tm, nyz, nmatch = imp.time_build_maxwithin(xbits[:N_cpu], M, N_cpu)
-    return {"value": M * N_cpu / (tb + tm), "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": f"first {N_cpu} of the workload's sites, all {M} haplotypes: build {tb:.2f}s + maxWithin {tm:.2f}s, "
-                      f"{nmatch} matches (counting callback), single thread",
-            "seconds": tb + tm}
+    return (ref, "reference", O) if ref is not None else (O.port(), "port", O)
+
+
+def time_reference(xbits, M, n_cpu, n_workload):
+    """The reference's own single-threaded CPU path on the first n_cpu sites, pinned to one core; also returns the
+    checksums of what it produced (oracle/oracle_api.h) for the parity gate."""
+    imp, kind, _ = oracle()
+    with PinnedToOneCore() as pin:
+        tb, tm, nyz, nmatch, ck = imp.time_build_maxwithin_ck(xbits[:n_cpu], M, n_cpu)
+    what = "all" if n_cpu == n_workload else "first"
+    return {"value": M * n_cpu / (tb + tm), "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"{what} {n_cpu} of the workload's {n_workload} sites, all {M} haplotypes: build {tb:.2f}s + maxWithin {tm:.2f}s, "
+                      f"{nmatch} matches (checksumming callback), single thread pinned to core {pin.core} (sched_setaffinity)",
+            "host": host_info(), "seconds": tb + tm, "nyz": nyz, "nmatch": nmatch, "checksums": ck}
+
+
+def gpu_checksums(O, out):
+    return (O.checksum_join([O.checksum_parts(O.mix_bytes(out["yz"]))]) +
+            O.checksum_join([O.checksum_parts(O.mix_records(out["matches"]))]))
+
+
+def peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def reference_arm(args, M, N):
+    """--impl reference: the unmodified reference (oracle/_ref) on this box's host cores, same workload and metric."""
+    imp, kind, O = oracle()
+    # whole workload per step unless that would take more than a few minutes in total
+    n_cpu = args.cpu_sites or N
+    x = O.generate_panel(M, n_cpu, SEED, L_RECOMB, MU)
+    first = time_reference(x, M, n_cpu, N)
+    reps = args.warmup + args.steps
+    if not args.cpu_sites and first["seconds"] * reps > 300.0:  # keep the run within a few minutes: bounded sample
+        n_cpu = max(2000, int(N * 300.0 / (first["seconds"] * reps)) // 1000 * 1000)
+        first = time_reference(x, M, n_cpu, N)
+    times, cb = [], first
+    for i in range(reps):
+        cb = time_reference(x, M, n_cpu, N)
+        if i >= args.warmup:
+            times.append(cb["seconds"])
+    t = float(np.mean(times)) if times else cb["seconds"]
+    val = M * n_cpu / t
+    for k in ("seconds", "checksums"):
+        cb.pop(k)
+    nyz, nmatch = cb.pop("nyz"), cb.pop("nmatch")
+    cb["value"] = val
+    scale = N / n_cpu  # (only != 1 for a bounded sample)
+    cfg = base_config(M, N, 1, int(nyz * scale), int(nmatch * scale))
+    if n_cpu != N:
+        cfg["step"] = f"bounded sample: first {n_cpu} sites (pack3_bytes / matches extrapolated)"
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                      "config": cfg, "cpu_baseline": cb,
+                      "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2..4] (single GPU unless stated)
+# ---------------------------------------------------------------------------------------------------------------
+def timed_ms(torch, stream, flush, fn, warmup, steps):
+    """mean device time of fn() in ms (CUDA events on the launching stream, L2 flushed between runs)"""
+    for _ in range(warmup):
+        fn()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.zero_()
+        a.record(stream)
+        fn()
+        b.record(stream)
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
+
+def roofline_of(algo_bytes, ms, peak):
+    ach = algo_bytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
+
+
+def run_config_build(P, torch, eng, stream, flush, name, M, N, seed, L, mu, flags, with_d, peak, n_cpu, cpu):
+    """configs[2] / configs[3]: device-resident build of a wide panel; CPU baseline on the first n_cpu sites."""
+    panel = eng.panel_synthetic(M, N, seed=seed, L=L, mu=mu)
+    eng.synchronize()
+    eng.last_timings()
+    sizes = {}
+
+    def step():
+        r = eng.build_device(panel, flags)
+        sizes["nyz"] = r.nyz
+        r.free()
+
+    ms = timed_ms(torch, stream, flush, step, 3, 2)
+    kt = eng.last_timings()
+    per_hs = BYTES_AD if with_d else BYTES_A
+    out = {"workload": name, "haplotypes": M, "sites": N, "ms": ms, "value": M * N / (ms * 1e-3), "unit": UNIT,
+           "pack3_bytes": sizes["nyz"], "algorithmic_bytes_per_hap_site": per_hs,
+           "roofline": roofline_of(per_hs * M * N + sizes["nyz"], ms, peak),
+           "kernel_ms_per_step": {k: v[0] / 5 for k, v in kt.items() if v[0] > 0}}
+    if cpu:
+        imp, kind, O = oracle()
+        x = panel.to_host(0, n_cpu)
+        sub = eng.panel_from_host(x, M)
+        r = eng.build_device(sub, flags)
+        got = r.fetch()
+        r.free()
+        sub.free()
+        with PinnedToOneCore():
+            tb, nyz, ck = imp.time_build(x, M, n_cpu, with_d)
+        mine = O.checksum_join([O.checksum_parts(O.mix_bytes(got["yz"]))])
+        out["cpu_baseline"] = {"value": M * n_cpu / tb, "unit": UNIT, "cores": 1, "kind": kind,
+                               "sample": f"first {n_cpu} of {N} sites (extrapolated linearly), {'a+d' if with_d else 'a only'}: {tb:.2f}s"}
+        out["parity"] = "ok" if (mine == ck and nyz == got["yz"].size) else "MISMATCH"
+    panel.free()
+    return out
+
+
+def run_config_query(P, torch, eng, stream, flush, M, Q, N, peak, n_cpu, cpu):
+    """configs[4]: 1,000 queries (the last Q haplotypes of an (M+Q)-panel) against the other M, matchSequencesSweep."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fullsize_checks import split_panel
+
+    both = eng.panel_synthetic(M + Q, N, seed=0x5EED0005, L=1000, mu=8.0)
+    x = both.to_host()
+    both.free()
+    px, qx = split_panel(x, M, Q)
+    del x
+    panel, queries = eng.panel_from_host(px, M), eng.panel_from_host(qx, Q)
+    rp = eng.build_device(panel, P.WANT_YZ); pyz = rp.fetch()["yz"]; rp.free()
+    rq = eng.build_device(queries, P.WANT_YZ); qyz = rq.fetch()["yz"]; rq.free()
+    panel.free()
+    queries.free()
+    eng.synchronize()
+    eng.last_timings()
+    info = {}
+
+    def step():
+        rec, nom = eng.match_sweep(pyz, M, N, qyz, Q)
+        info["nrec"], info["nnom"] = len(rec), len(nom)
+
+    step()
+    eng.last_timings()
+    t0 = time.time()
+    step()
+    wall = time.time() - t0
+    kt = eng.last_timings()
+    dev_ms = sum(v[0] for v in kt.values())
+    out = {"workload": f"matchSequencesSweep: {Q} queries vs {M} haplotypes x {N} sites (N assumed: BASELINE gives none)",
+           "haplotypes": M, "queries": Q, "sites": N, "ms": dev_ms, "value": M * N / (dev_ms * 1e-3), "unit": "panel " + UNIT,
+           "wall_ms_host_streams_in_records_out": wall * 1e3, "records": info["nrec"], "no_match_events": info["nnom"],
+           "algorithmic_bytes_per_hap_site": BYTES_AD,
+           "roofline": roofline_of(BYTES_AD * M * N + 16.0 * info["nrec"], dev_ms, peak),
+           "kernel_ms_per_step": {k: v[0] for k, v in kt.items() if v[0] > 0}}
+    if cpu:
+        imp, kind, O = oracle()
+        pp, qq = eng.panel_from_host(px[:n_cpu], M), eng.panel_from_host(qx[:n_cpu], Q)
+        r = eng.build_device(pp, P.WANT_YZ); pyz5 = r.fetch()["yz"]; r.free()
+        r = eng.build_device(qq, P.WANT_YZ); qyz5 = r.fetch()["yz"]; r.free()
+        pp.free()
+        qq.free()
+        rec, nom = eng.match_sweep(pyz5, M, n_cpu, qyz5, Q)
+        with PinnedToOneCore():
+            t0 = time.time()
+            want, wnom = imp.match_sweep(pyz5, M, n_cpu, qyz5, Q)
+            tc = (time.time() - t0) / 2  # (the wrapper runs it twice: count, then fill)
+        out["cpu_baseline"] = {"value": M * n_cpu / tc, "unit": "panel " + UNIT, "cores": 1, "kind": kind,
+                               "sample": f"first {n_cpu} of {N} sites (extrapolated linearly): matchSequencesSweep {tc:.2f}s, {len(want)} records"}
+        out["parity"] = "ok" if (np.array_equal(rec, want) and np.array_equal(nom, wnom)) else "MISMATCH"
+    return out
 
 
 def main():
@@ -97,11 +303,10 @@ def main():
     ap.add_argument("--haps", type=int, default=M_DEFAULT)
     ap.add_argument("--sites", type=int, default=N_DEFAULT)
     ap.add_argument("--cpu-sites", type=int, default=0, help="sites timed on the CPU baseline (0 = automatic)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (and with them the parity gate)")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 3-5 (the headline line only)")
+    ap.add_argument("--no-cli", action="store_true", help="skip the command-line wall times")
     args = ap.parse_args()
-
-    import torch
-    import torch.distributed as dist
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -110,32 +315,12 @@ def main():
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     if args.impl == "reference":
-        if rank != 0:
-            return
-        # bit-identical panel from the CPU generator (no GPU needed on this arm)
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import oracle_lib as O
-
-        n_cpu = args.cpu_sites or min(N, 10000)
-        x = O.generate_panel(M, n_cpu, SEED, L_RECOMB, MU)
-        times = []
-        for i in range(args.warmup + args.steps):
-            cb = time_reference(x, M, n_cpu)
-            if i >= args.warmup:
-                times.append(cb["seconds"])
-        t = float(np.mean(times)) if times else cb["seconds"]
-        val = M * n_cpu / t
-        cb.pop("seconds")
-        cb["value"] = val
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-                          "config": {"workload": workload_name(M, N), "haplotypes": M, "sites": N,
-                                     "step": f"bounded sample: first {n_cpu} sites",
-                                     "generator": f"seed {SEED:#x}, L={L_RECOMB}, mu={MU}"},
-                          "cpu_baseline": cb,
-                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        if rank == 0:
+            reference_arm(args, M, N)
         return
+
+    import torch
+    import torch.distributed as dist
 
     import pbwt_b200 as P
 
@@ -149,6 +334,32 @@ def main():
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     eng.profile(True)
+    flags = P.WANT_YZ | P.WANT_MAXWITHIN
+    peak, peak_src = peak_hbm()
+
+    # ---- parity gate (rank 0): GPU vs the reference on the first sites of the workload, before any timing ----
+    cpu = None
+    gate = {"checked": False}
+    if rank == 0 and not args.no_cpu_baseline:
+        n_cpu = args.cpu_sites or min(N, 20000)
+        head = eng.panel_synthetic(M, n_cpu, seed=SEED, L=L_RECOMB, mu=MU)
+        r = eng.build_device(head, flags)
+        got = r.fetch()
+        r.free()
+        x_head = head.to_host()
+        head.free()
+        cpu = time_reference(x_head, M, n_cpu, N * world)
+        _, _, O = oracle()
+        mine = gpu_checksums(O, got)
+        gate = {"checked": True, "sites": n_cpu, "pack3_bytes": int(got["yz"].size), "records": int(len(got["matches"])),
+                "checksums_gpu": mine, "checksums_cpu": cpu["checksums"],
+                "ok": mine == cpu["checksums"] and got["yz"].size == cpu["nyz"] and len(got["matches"]) == cpu["nmatch"]}
+        if not gate["ok"]:
+            print(json.dumps({"error": "parity gate failed: the GPU's build + maxWithin of the first sites differs from the "
+                                       "reference's; no value is reported", "parity_gate": gate}))
+            sys.exit(3)
+        for k in ("seconds", "checksums", "nyz", "nmatch"):
+            cpu.pop(k)
 
     # N GPUs: the SITES of one panel of world*N sites are partitioned across the ranks (weak scaling: N sites per
     # GPU); the only exchange is one NCCL all-gather of per-shard aggregates (include/pbwtgpu.h, multi-GPU)
@@ -156,7 +367,6 @@ def main():
     panel = eng.panel_synthetic(M, N, seed=SEED, L=L_RECOMB, mu=MU, first_site=rank * N)
     eng.synchronize()
     eng.last_timings()
-    flags = P.WANT_YZ | P.WANT_MAXWITHIN
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     agg_ints = eng.shard_aggregate_ints(M)
     agg = torch.zeros(agg_ints, dtype=torch.int32, device="cuda")
@@ -178,6 +388,48 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # ---- multi-GPU parity (N > 1): the shards' outputs, concatenated in site order, against ONE GPU building the
+    # whole panel (rank 0), by checksums of pack3 bytes and records, plus aFend / d of the last shard ----
+    mg_parity = None
+    if world > 1:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+
+        r = device_step(panel)
+        out = r.fetch()
+        r.free()
+        # (uint64 sums travel as int64 bit patterns)
+        parts = torch.from_numpy(np.array([[out["yz"].size, *O.checksum_parts(O.mix_bytes(out["yz"]))[1:]],
+                                           [len(out["matches"]), *O.checksum_parts(O.mix_records(out["matches"]))[1:]]],
+                                          dtype=np.uint64).view(np.int64)).cuda()
+        allparts = torch.zeros((world, 2, 3), dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(allparts, parts)
+        ends = torch.from_numpy(np.concatenate([out["a_end"], out["d_end"]])).cuda()
+        dist.broadcast(ends, src=world - 1)
+        if rank == 0:
+            ap_ = allparts.cpu().numpy().view(np.uint64)
+            joined = (O.checksum_join([tuple(int(v) for v in ap_[w, 0]) for w in range(world)]) +
+                      O.checksum_join([tuple(int(v) for v in ap_[w, 1]) for w in range(world)]))
+            whole = eng.panel_synthetic(M, n_total, seed=SEED, L=L_RECOMB, mu=MU)
+            r1 = eng.build_device(whole, flags)
+            o1 = r1.fetch()
+            r1.free()
+            whole.free()
+            single = gpu_checksums(O, o1)
+            e = ends.cpu().numpy()
+            ok = (joined == single and int(ap_[:, 0, 0].sum()) == o1["yz"].size and int(ap_[:, 1, 0].sum()) == len(o1["matches"])
+                  and np.array_equal(e[:M], o1["a_end"]) and np.array_equal(e[M:], o1["d_end"]))
+            mg_parity = {"ok": bool(ok), "what": f"{world} shards concatenated vs one GPU building all {n_total} sites: checksums of "
+                                                 f"{o1['yz'].size} pack3 bytes and {len(o1['matches'])} records, aFend, d"}
+            if not ok:
+                print(json.dumps({"error": "multi-GPU parity failed: the shards' outputs differ from the single-GPU build",
+                                  "parity": mg_parity}))
+        flag = torch.tensor([1 if (rank != 0 or mg_parity["ok"]) else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) == 0:
+            dist.destroy_process_group()
+            sys.exit(3)
 
     # ---- device-resident steps -------------------------------------------------------------------
     nyz = nmatch = 0
@@ -208,26 +460,41 @@ def main():
     sweep_ms = kt["sweep"][0] + kt["prepass"][0] + kt["combine"][0]
     sweep_launches = kt["sweep"][1] + kt["prepass"][1] + kt["combine"][1]
 
-    # ---- end to end through the host-buffer API ----------------------------------------------------
-    x_host = torch.empty((N, P.words_per_col(M)), dtype=torch.int32).pin_memory()
-    x_np = x_host.numpy().view(np.uint32)
+    # ---- end to end through the C ABI as the host shim calls it ------------------------------------
+    # bit columns in a page-locked buffer of the library's pool (the shim assembles its reader batches in one:
+    # pbwtgpu_host_alloc), ONE pbwtgpu_build call per step (H2D, kernels, D2H inside), outputs in library-owned host
+    # buffers that are read in place and given back with pbwtgpu_free -- exactly the calls of pbwt_gpu_shim.c
+    wpc = P.words_per_col(M)
+    xbuf = eng.host_alloc(N * wpc * 4)
+    x_np = xbuf.view(np.uint32).reshape(N, wpc)
     x_np[:] = panel.to_host()
-    pin = {
-        "yz": torch.empty(max(nyz, 1), dtype=torch.uint8).pin_memory().numpy(),
-        "a_end": torch.empty(M, dtype=torch.int32).pin_memory().numpy(),
-        "d_end": torch.empty(M + 1, dtype=torch.int32).pin_memory().numpy(),
-        "matches": torch.empty((max(nmatch, 1), 4), dtype=torch.int32).pin_memory().numpy().view(P.MATCH_DTYPE).reshape(-1),
-    }
+    a_end, d_end = np.zeros(M, np.int32), np.zeros(M + 1, np.int32)
     h2d = x_np.nbytes
     d2h = nyz + 4 * M + 4 * (M + 1) + 16 * nmatch
+    pin = None
+    if world > 1:  # per-rank pinned output buffers for the device-resident calls of the sharded protocol
+        pin = {"yz": torch.empty(max(nyz, 1), dtype=torch.uint8).pin_memory().numpy(),
+               "a_end": torch.empty(M, dtype=torch.int32).pin_memory().numpy(),
+               "d_end": torch.empty(M + 1, dtype=torch.int32).pin_memory().numpy(),
+               "matches": torch.empty((max(nmatch, 1), 4), dtype=torch.int32).pin_memory().numpy().view(P.MATCH_DTYPE).reshape(-1)}
+
+    def abi_step(e, a_out, d_out):
+        yzp, ny, mtp, nm = e.build_raw(x_np, M, N, flags, a_out, d_out)
+        # the host reads the result where the library left it (the shim walks the records and calls report())
+        last = np.ctypeslib.as_array(ctypes.cast(mtp, ctypes.POINTER(ctypes.c_int32)), shape=(nm * 4,))[-1] if nm else 0
+        e.free_raw(yzp, mtp)
+        return ny, nm, int(last)
 
     def e2e_step():
-        pnl = eng.panel_from_host(x_np, M)
+        if world == 1:
+            return abi_step(eng, a_end, d_end)
+        pnl = eng.panel_from_host(x_np, M)  # N > 1: the sharded protocol needs the device-resident calls
         res = device_step(pnl)
         res.fetch(out=pin)
         res.free()
         pnl.free()
 
+    e2e_step()
     e2e_step()
     barrier()
     t0 = time.time()
@@ -236,26 +503,20 @@ def main():
     barrier()
     t_e2e_serial = (time.time() - t0) / args.steps
     t_e2e, in_flight = t_e2e_serial, 1
+    shim_seq_ms = None
 
-    # Two builds in flight (single GPU): two contexts, each with its own stream and its own host thread, take the
-    # steps alternately, so the PCIe copies of one step overlap the kernels of the other.  Every step still does its
-    # own H2D, kernels and D2H inside the timed region.
     if world == 1:
+        # Two builds in flight: two contexts, each with its own stream and host thread, take the steps alternately, so
+        # that one step's PCIe copies overlap the other's kernels.  Every step is still one complete pbwtgpu_build call.
         engs = [P.Engine(local_rank), P.Engine(local_rank)]
-        pins = [pin, {k: torch.from_numpy(v.view(np.uint8)).clone().pin_memory().numpy().view(v.dtype).reshape(v.shape)
-                      for k, v in pin.items()}]
+        outs = [(np.zeros(M, np.int32), np.zeros(M + 1, np.int32)) for _ in engs]
 
         def worker(w, steps):
-            e = engs[w]
             for _ in range(steps):
-                pnl = e.panel_from_host(x_np, M)
-                res = e.build_device(pnl, flags)
-                res.fetch(out=pins[w])
-                res.free()
-                pnl.free()
+                abi_step(engs[w], *outs[w])
 
         for w in (0, 1):  # warm both contexts (their device-memory caches, kernel attributes)
-            worker(w, 1)
+            worker(w, 2)
         barrier()
         counts = [(args.steps + 1) // 2, args.steps // 2]
         threads = [threading.Thread(target=worker, args=(w, counts[w])) for w in (0, 1) if counts[w]]
@@ -270,6 +531,47 @@ def main():
             e.close()
         if t_pipe < t_e2e:
             t_e2e, in_flight = t_pipe, 2
+        # the two-call sequence of `pbwt_gpu -readMacs ... -maxWithin`: the readers' batch goes through pbwtgpu_build
+        # (pack3 stream + aFend back), then matchMaximalWithin sends the stored stream to pbwtgpu_max_within
+        def shim_sequence():
+            yzp, ny, _, _ = eng.build_raw(x_np, M, N, P.WANT_YZ, a_end, None)
+            mtp, nm = eng.max_within_raw(yzp, ny, M, N)
+            eng.free_raw(yzp, mtp)
+
+        shim_sequence()
+        barrier()
+        t0 = time.time()
+        for _ in range(args.steps):
+            shim_sequence()
+        barrier()
+        shim_seq_ms = (time.time() - t0) / args.steps * 1e3
+    eng.host_free(xbuf)
+
+    # ---- command-line wall times (reported separately; text output dominates) ------------
+    cli = None
+    if rank == 0 and world == 1 and not args.no_cli and (M, N) == (M_DEFAULT, N_DEFAULT):
+        cli = cli_wall_times(eng, P, panel, M, N)
+
+    # ---- BASELINE configs 3-5 -----------------------------------------------------------------------
+    configs = None
+    if not args.no_configs and (M, N) == (M_DEFAULT, N_DEFAULT):
+        panel.free()
+        panel = None
+        if world == 1:
+            want_cpu = not args.no_cpu_baseline
+            configs = {
+                "c3_build_pack3_100k_x_200k": run_config_build(
+                    P, torch, eng, stream, flush, "synthetic mosaic panel 100000 x 200000, build + pack3 (a only)", 100000, 200000,
+                    0x5EED0003, 1000, 8.0, P.WANT_YZ, False, peak, 5000, want_cpu),
+                "c4_build_ad_1m_x_100k_one_gpu": run_config_build(
+                    P, torch, eng, stream, flush, "synthetic mosaic panel 1000000 x 100000, build with d + pack3, ONE GPU", 1000000, 100000,
+                    0x5EED0004, 1000, 8.0, P.WANT_YZ | P.WANT_D, True, peak, 5000, want_cpu),
+                "c5_match_sweep_1000_vs_100k_x_100k": run_config_query(P, torch, eng, stream, flush, 100000, 1000, 100000, peak, 5000, want_cpu),
+            }
+        else:
+            configs = {"c4_build_ad_1m_x_100k_site_sharded": run_config4_sharded(P, torch, dist, eng, stream, flush, rank, world, peak)}
+    if panel is not None:
+        panel.free()
 
     # ---- reduce over ranks (max time) --------------------------------------------------------------
     t_step = torch.tensor([ms_per_step, t_e2e * 1e3], device="cuda", dtype=torch.float64)
@@ -283,21 +585,16 @@ def main():
     nyz_all, nmatch_all, h2d_all, d2h_all, launches_all = [int(v) for v in stats.tolist()]
 
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        algo_bytes = BYTES_PER_HS * M * N + nyz + 16.0 * nmatch  # rank 0's shard; the roofline is per GPU
+        algo_bytes = BYTES_AD * M * N + nyz + 16.0 * nmatch  # rank 0's shard; the roofline is per GPU
         # one unit of algorithmic work (a step) needs ALL sweep-kernel launches of that step (pass 1 + combine
         # rounds + pass 2), so the denominator is their summed duration per step, not one launch's
         sweep_ms_per_step = sweep_ms / args.steps
         achieved = algo_bytes / (sweep_ms_per_step * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    # dram__bytes_read+write of pass 2, the dominant launch (502.2 MB; ncu --set full capture in
-                    # profiles/r01b_c2_pass2_ncu_full_summary.txt), plus the window sort (13.8 MB) and its transpose
-                    # (read 125 MB + write 130 MB); only valid for this config
-                    "traffic": 771.0e6 if (M, N) == (M_DEFAULT, N_DEFAULT) else None, "kernel": "sweep_smem_kernel",
+                    # dram__bytes_read+write per step from the ncu --set full captures under profiles/ (pass 2, the dominant
+                    # launch, plus window sort and transpose); only valid for this config
+                    "traffic": TRAFFIC_C2 if (M, N) == (M_DEFAULT, N_DEFAULT) else None, "kernel": "sweep_smem_kernel",
+                    "frac_of_whole_step": algo_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
                     "kernel_ms_per_step": sweep_ms_per_step, "kernel_launches_per_step": sweep_launches / args.steps,
                     "kernel_ms_per_step_by_role": {"pass1": kt["prepass"][0] / args.steps, "combine": kt["combine"][0] / args.steps,
                                                    "pass2": kt["sweep"][0] / args.steps},
@@ -306,35 +603,158 @@ def main():
                             "launches that do a step's sweep work: pass 1 (window nodes by transpose + radix sort of window "
                             "keys), combine rounds and pass 2 (sweep_smem_kernel, the dominant launch); a[]/d[] stay resident "
                             "in shared memory, so DRAM traffic is far below the algorithmic bytes"}
-        cpu = None
-        if not args.no_cpu_baseline:
-            n_cpu = args.cpu_sites or min(N, 20000)
-            cpu = time_reference(x_np, M, n_cpu)
-            cpu.pop("seconds")
+        cfg = base_config(M, n_total, world, nyz_all, nmatch_all)
+        cfg["parallelism"] = (f"sites partitioned across {world} GPUs, one NCCL all-gather of per-shard aggregates "
+                              f"({agg_ints * 4} B per rank) per step") if world > 1 else "single GPU"
         out = {
             "metric": METRIC, "value": total_hs / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int32", "data": "synthetic",
-            "config": {"workload": workload_name(M, n_total), "haplotypes": M, "sites": n_total, "sites_per_gpu": N,
-                       "parallelism": (f"sites partitioned across {world} GPUs, one NCCL all-gather of per-shard aggregates "
-                                       f"({agg_ints * 4} B per rank) per step") if world > 1 else "single GPU",
-                       "l2": "256 MiB device memset between timed steps; per-step CUDA events on the launching stream",
-                       "matches_per_haplotype": nmatch_all / M, "pack3_bytes": nyz_all, "generator": f"seed {SEED:#x}, L={L_RECOMB}, mu={MU}"},
+            "dtype": "int32", "data": "synthetic", "config": cfg,
             "e2e": {"value": total_hs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
                     "ms_per_step": ms_e2e, "builds_in_flight": in_flight, "ms_per_step_one_in_flight": t_e2e_serial * 1e3,
-                    "note": "host bit columns (pinned) -> pbwtgpu_panel_from_host -> pbwtgpu_build_device -> pbwtgpu_result_fetch of "
-                            "pack3 stream, aFend, d and all match records, every step; with 2 builds in flight two contexts "
-                            "(streams, host threads) alternate steps so one step's PCIe copies overlap the other's kernels"},
+                    "ms_per_step_shim_two_call_sequence": shim_seq_ms,
+                    "note": ("one pbwtgpu_build(host bit columns in a pbwtgpu_host_alloc buffer, WANT_YZ|WANT_MAXWITHIN) per step, as the "
+                             "C host shim calls it: H2D, kernels and D2H of pack3 stream, aFend, d and all match records into "
+                             "library-owned host buffers, freed with pbwtgpu_free; with 2 builds in flight two contexts (streams, "
+                             "host threads) alternate steps; the shim's two-call sequence (pbwtgpu_build, then "
+                             "pbwtgpu_max_within on the stored stream) is timed beside it") if world == 1 else
+                            "per rank: pinned host columns -> pbwtgpu_panel_from_host -> shard protocol -> pbwtgpu_result_fetch"},
             "gpu_launches": launches_all,
-            "kernel_ms": {k: v[0] for k, v in kt.items() if v[1]},
+            "kernel_ms": {k: v[0] for k, v in kt.items() if v[0] > 0},
             "clocks": clocks.summary(),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "parity_gate": gate,
             "wall_s_timed_region": t_wall,
         }
+        if mg_parity:
+            out["parity"] = mg_parity
+        if cli:
+            out["cli"] = cli
+        if configs:
+            out["configs"] = configs
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one config-2 step (ncu --set full, profiles/)
+TRAFFIC_C2 = 771.0e6
+
+
+def cli_wall_times(eng, P, panel, M, N):
+    """`pbwt_gpu -read X.pbwt -maxWithin > /dev/null` next to the reference's CLI on the same file (one run each)."""
+    gpu_cli = os.path.join(ROOT, "pbwt_b200", "host", "_build", "pbwt_gpu")
+    ref_cli = os.path.join(ROOT, "oracle", "_ref", "pbwt_ref")
+    if not (os.path.exists(gpu_cli) and os.path.exists(ref_cli)):
+        return {"unavailable": "pbwt_gpu / pbwt_ref were not prebuilt (they need the reference's sources)"}
+    r = eng.build_device(panel, P.WANT_YZ)
+    o = r.fetch()
+    r.free()
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "c2.pbwt")
+        with open(path, "wb") as fh:  # .pbwt v3, pbwtIO.c:33-57
+            fh.write(b"PBW3" + np.array([M, N], "<i4").tobytes() + np.arange(M, dtype="<i4").tobytes() + o["a_end"].astype("<i4").tobytes() +
+                     np.array([o["yz"].size], "<i8").tobytes() + b"    " + o["yz"].tobytes())
+        for name, exe in (("pbwt_gpu", gpu_cli), ("pbwt_ref", ref_cli)):
+            t0 = time.time()
+            with open(os.devnull, "wb") as null:
+                rc = subprocess.run([exe, "-read", path, "-maxWithin"], stdout=null, stderr=subprocess.DEVNULL).returncode
+            out[name + "_s"] = time.time() - t0
+            out[name + "_rc"] = rc
+    out["command"] = "<cli> -read c2.pbwt -maxWithin > /dev/null (process start, file read, 18.5 M MATCH lines formatted)"
+    return out
+
+
+def run_config4_sharded(P, torch, dist, eng, stream, flush, rank, world, peak):
+    """configs[3] at N > 1: the 1,000,000 x 100,000 panel with its SITES partitioned across the ranks (strong scaling),
+    a + d + pack3; parity of the concatenated pack3 stream and of aFend / d against checksums is by rank 0."""
+    M, N = 1000000, 100000
+    n_loc = N // world
+    first = rank * n_loc
+    if rank == world - 1:
+        n_loc = N - first
+    flags = P.WANT_YZ | P.WANT_D
+    panel = eng.panel_synthetic(M, n_loc, seed=0x5EED0004, L=1000, mu=8.0, first_site=first)
+    agg_ints = eng.shard_aggregate_ints(M)
+    agg = torch.zeros(agg_ints, dtype=torch.int32, device="cuda")
+    aggs = torch.zeros((world, agg_ints), dtype=torch.int32, device="cuda")
+    sizes = {}
+
+    def step():
+        sh = eng.shard_prepare(panel, first, N, flags)
+        sh.export(agg.data_ptr())
+        dist.all_gather_into_tensor(aggs, agg)
+        res = sh.finish(aggs.data_ptr(), rank, flags)
+        sh.free()
+        sizes["nyz"] = res.nyz
+        return res
+
+    for _ in range(2):
+        step().free()
+    eng.synchronize()
+    eng.last_timings()
+    ms = []
+    for _ in range(2):
+        flush.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        res = step()
+        b.record(stream)
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+        res.free()
+    kt = eng.last_timings()
+    t = torch.tensor([float(np.mean(ms))], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot = torch.tensor([float(sizes["nyz"])], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tot)
+    # parity: pack3 bytes of all shards in site order, aFend and d of the last one, against ONE GPU building the panel
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+
+    res = step()
+    out = res.fetch()
+    res.free()
+    panel.free()
+    parts = torch.from_numpy(np.array(O.checksum_parts(O.mix_bytes(out["yz"])), dtype=np.uint64).view(np.int64)).cuda()
+    allparts = torch.zeros((world, 3), dtype=torch.int64, device="cuda")
+    dist.all_gather_into_tensor(allparts, parts)
+    ends = torch.from_numpy(np.concatenate([out["a_end"], out["d_end"]])).cuda()
+    dist.broadcast(ends, src=world - 1)
+    parity, one_gpu_ms = None, None
+    if rank == 0:
+        ap_ = allparts.cpu().numpy().view(np.uint64)
+        joined = O.checksum_join([tuple(int(v) for v in ap_[w]) for w in range(world)])
+        whole = eng.panel_synthetic(M, N, seed=0x5EED0004, L=1000, mu=8.0)
+        eng.build_device(whole, flags).free()
+        eng.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        r1 = eng.build_device(whole, flags)
+        b.record(stream)
+        torch.cuda.synchronize()
+        one_gpu_ms = a.elapsed_time(b)
+        o1 = r1.fetch()
+        r1.free()
+        whole.free()
+        e = ends.cpu().numpy()
+        ok = (joined == O.checksum_join([O.checksum_parts(O.mix_bytes(o1["yz"]))]) and int(ap_[:, 0].sum()) == o1["yz"].size
+              and np.array_equal(e[:M], o1["a_end"]) and np.array_equal(e[M:], o1["d_end"]))
+        parity = "ok" if ok else "MISMATCH"
+    dist.barrier()
+    ms_max = float(t[0])
+    return {"parity_vs_one_gpu": parity, "one_gpu_ms_same_box": one_gpu_ms,
+            "strong_scaling_efficiency": (one_gpu_ms / ms_max / world) if one_gpu_ms else None,"workload": f"synthetic mosaic panel {M} x {N}, build with d + pack3, sites partitioned across {world} GPUs (strong scaling)",
+            "haplotypes": M, "sites": N, "n_gpus": world, "ms": ms_max, "value": M * N / (ms_max * 1e-3), "unit": UNIT,
+            "pack3_bytes": int(tot[0]), "all_gather_bytes_per_rank": agg_ints * 4, "all_gather_bytes_total": agg_ints * 4 * world,
+            "algorithmic_bytes_per_hap_site": BYTES_AD,
+            "roofline_per_gpu": roofline_of((BYTES_AD * M * N + float(tot[0])) / world, ms_max, peak),
+            "kernel_ms_per_step_rank0": {k: v[0] / 2 for k, v in kt.items() if v[0] > 0}}
 
 
 if __name__ == "__main__":

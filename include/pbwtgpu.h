@@ -77,7 +77,8 @@ enum { PBWTGPU_K_SWEEP = 0,    /* the output-producing sweep (pass 2 of the wind
        PBWTGPU_K_AUX = 5,      /* tie groups, key bits, record gather */
        PBWTGPU_K_PREPASS = 6,  /* sweep kernel, pass 1: every window on its own */
        PBWTGPU_K_COMBINE = 7,  /* sweep kernel over pseudo-sites: window-prefix combine rounds */
-       PBWTGPU_NUM_KERNEL_CLASSES = 8 };
+       PBWTGPU_K_COPY = 8,     /* device-to-device copies of window / shard states (no kernels of ours: launch count 0) */
+       PBWTGPU_NUM_KERNEL_CLASSES = 9 };
 int pbwtgpu_profile(pbwtgpu_ctx *ctx, int enable);
 int pbwtgpu_last_timings(pbwtgpu_ctx *ctx, float *ms, int *launches);
 
@@ -133,9 +134,20 @@ int pbwtgpu_shard_finish(pbwtgpu_ctx *ctx, pbwtgpu_shard *shard, const int32_t *
                          pbwtgpu_result **result);
 void pbwtgpu_shard_free(pbwtgpu_ctx *ctx, pbwtgpu_shard *shard);
 
+/* ---- host buffers ---------------------------------------------------------------------------------- */
+/* Page-locked host memory from a process-wide, reusing pool: a caller that assembles its bit columns in such a
+ * buffer (the host shim's reader batch, pbwtIO.c:558-586 batched) gets the H2D copy at the full PCIe rate instead
+ * of the pageable one.  NULL when the allocation fails.  Give it back with pbwtgpu_free. */
+void *pbwtgpu_host_alloc(size_t bytes);
+/* Frees any buffer this library handed out (*yz, *zz, *matches, *nomatch, pbwtgpu_host_alloc): those are page-locked
+ * blocks of the same pool (kept for reuse), so they MUST come back through here, not through free(). */
+void pbwtgpu_free(void *p);
+/* Returns the pool's cached (free) page-locked blocks to the system. */
+void pbwtgpu_host_trim(void);
+
 /* ---- one-shot host-buffer entry points (what the host shim calls) --------------------------- */
-/* H2D of the columns, sweep, D2H.  *yz and *matches are malloc()'d (free with pbwtgpu_free or
- * free); a_end / d_end are caller-allocated (int[M], int[M+1]) or NULL. */
+/* H2D of the columns, sweep, D2H.  *yz and *matches are allocated by the library (give them back with
+ * pbwtgpu_free); a_end / d_end are caller-allocated (int[M], int[M+1]) or NULL. */
 int pbwtgpu_build(pbwtgpu_ctx *ctx, const uint32_t *xbits, int M, int N, const int32_t *a_start, unsigned flags,
                   uint8_t **yz, int64_t *nyz, int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches,
                   int64_t *nmatch);
@@ -167,7 +179,6 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
 /* pack3 / unpack3 of whole streams on the device (pbwtCore.c:254-305): y is N columns of M bytes. */
 int pbwtgpu_pack3(pbwtgpu_ctx *ctx, const uint8_t *y, int M, int N, uint8_t **yz, int64_t *nyz);
 int pbwtgpu_unpack3(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, uint8_t *y, int32_t *zero_counts);
-void pbwtgpu_free(void *p);
 
 #ifdef __cplusplus
 }

@@ -92,6 +92,28 @@ int ORC(unpack3)(const uint8_t *yz, int M, uint8_t *y, int32_t *n0);
 int ORC(time_build_maxwithin)(const uint32_t *xbits, int wpc, int M, int N,
                               double *t_build, double *t_match, int64_t *nyz, int64_t *nmatch);
 
+/* The same two timers with order-sensitive checksums of what was produced, for bench.py's parity gate (the GPU's
+ * outputs for the same sites must hash to the same values before any timing counts).  For items i = 0.. with mix m_i:
+ * S = sum m_i, T = sum (i+1) m_i (mod 2^64); a pack3 byte b mixes to b * 0x9E3779B97F4A7C15 + 1, a record to
+ * oracle_mix_record().  ck = {S_yz, T_yz, S_rec, T_rec}.  time_build times the build alone (with_d selects
+ * pbwtCursorWriteForwardsAD); ck = {S_yz, T_yz}. */
+int ORC(time_build_maxwithin_ck)(const uint32_t *xbits, int wpc, int M, int N, double *t_build, double *t_match,
+                                 int64_t *nyz, int64_t *nmatch, uint64_t *ck);
+int ORC(time_build)(const uint32_t *xbits, int wpc, int M, int N, int with_d, double *t_build, int64_t *nyz, uint64_t *ck);
+
+static inline uint64_t oracle_mix_record(int32_t ai, int32_t bi, int32_t start, int32_t end) {
+  const uint64_t w0 = (uint64_t)(uint32_t)ai | ((uint64_t)(uint32_t)bi << 32);
+  const uint64_t w1 = (uint64_t)(uint32_t)start | ((uint64_t)(uint32_t)end << 32);
+  uint64_t m = (w0 * 0x9E3779B97F4A7C15ull) ^ (w1 * 0xC2B2AE3D27D4EB4Full);
+  m ^= m >> 29;
+  return m | 1u;
+}
+static inline void oracle_ck_bytes(const uint8_t *b, int64_t n, uint64_t *ck) {
+  uint64_t S = 0, T = 0;
+  for (int64_t i = 0; i < n; ++i) { const uint64_t m = (uint64_t)b[i] * 0x9E3779B97F4A7C15ull + 1u; S += m; T += (uint64_t)(i + 1) * m; }
+  ck[0] = S; ck[1] = T;
+}
+
 #ifdef __cplusplus
 }
 #endif

@@ -259,3 +259,59 @@ int ref_time_build_maxwithin(const uint32_t *xbits, int wpc, int M, int N,
   free(x);
   return 0;
 }
+
+/* ---- the same timers with checksums of the outputs (bench.py's parity gate; oracle_api.h) ---- */
+static uint64_t g_S, g_T;
+static void hash_cb(int ai, int bi, int start, int end) {
+  const uint64_t m = oracle_mix_record(ai, bi, start, end);
+  g_S += m;
+  g_T += (uint64_t)(++g_n) * m;
+}
+
+static PBWT *timed_build(const uint32_t *xbits, int wpc, int M, int N, int with_d, double *t_build) {
+  uint8_t *x = malloc((size_t)M + 1);
+  PBWT *p = pbwtCreate(M, 0);
+  PbwtCursor *u = pbwtCursorCreate(p, TRUE, TRUE);
+  double tb = 0;
+  for (int k = 0; k < N; ++k) { /* the readers' per-site loop, pbwtIO.c:572-574 */
+    const uint32_t *col = xbits + (size_t)k * wpc;
+    for (int h = 0; h < M; ++h) x[h] = xbit(col, h);
+    x[M] = Y_SENTINEL;
+    double t0 = now_s();
+    for (int j = 0; j < M; ++j) u->y[j] = x[u->a[j]];
+    if (with_d) pbwtCursorWriteForwardsAD(u, k);
+    else pbwtCursorWriteForwards(u);
+    ++p->N;
+    tb += now_s() - t0;
+  }
+  pbwtCursorToAFend(u, p);
+  pbwtCursorDestroy(u);
+  free(x);
+  *t_build = tb;
+  return p;
+}
+
+int ref_time_build(const uint32_t *xbits, int wpc, int M, int N, int with_d, double *t_build, int64_t *nyz, uint64_t *ck) {
+  ensure_init();
+  PBWT *p = timed_build(xbits, wpc, M, N, with_d, t_build);
+  *nyz = arrayMax(p->yz);
+  oracle_ck_bytes(arrp(p->yz, 0, uchar), *nyz, ck);
+  pbwtDestroy(p);
+  return 0;
+}
+
+int ref_time_build_maxwithin_ck(const uint32_t *xbits, int wpc, int M, int N, double *t_build, double *t_match,
+                                int64_t *nyz, int64_t *nmatch, uint64_t *ck) {
+  ensure_init();
+  PBWT *p = timed_build(xbits, wpc, M, N, 0, t_build);
+  *nyz = arrayMax(p->yz);
+  oracle_ck_bytes(arrp(p->yz, 0, uchar), *nyz, ck);
+  g_n = 0; g_S = g_T = 0;
+  double t0 = now_s();
+  matchMaximalWithin(p, hash_cb); /* pbwtMatch.c:115 */
+  *t_match = now_s() - t0;
+  *nmatch = g_n;
+  ck[2] = g_S; ck[3] = g_T;
+  pbwtDestroy(p);
+  return 0;
+}

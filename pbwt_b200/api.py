@@ -23,7 +23,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpbwtgpu.so")
 
 WANT_YZ, WANT_D, WANT_MAXWITHIN, WANT_LONGWITHIN = 1, 2, 4, 8
-KERNEL_CLASSES = ("sweep", "pack3", "unpack3", "query", "synth", "aux", "prepass", "combine")
+KERNEL_CLASSES = ("sweep", "pack3", "unpack3", "query", "synth", "aux", "prepass", "combine", "copy")
 
 MATCH_DTYPE = np.dtype([("ai", "<i4"), ("bi", "<i4"), ("start", "<i4"), ("end", "<i4")])
 NOMATCH_DTYPE = np.dtype([("query", "<i4"), ("allele", "<i4"), ("site", "<i4")])
@@ -90,6 +90,10 @@ def load_library() -> C.CDLL:
         lib.pbwtgpu_unpack3.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp]
         lib.pbwtgpu_free.argtypes = [_vp]
         lib.pbwtgpu_free.restype = None
+        lib.pbwtgpu_host_alloc.argtypes = [C.c_size_t]
+        lib.pbwtgpu_host_alloc.restype = _vp
+        lib.pbwtgpu_host_trim.argtypes = []
+        lib.pbwtgpu_host_trim.restype = None
         _lib = lib
     return _lib
 
@@ -232,6 +236,17 @@ class Engine:
         self._check(self.lib.pbwtgpu_last_timings(self.ctx, ms, cnt))
         return {k: (ms[i], cnt[i]) for i, k in enumerate(KERNEL_CLASSES)}
 
+    def host_alloc(self, nbytes: int) -> np.ndarray:
+        """Page-locked host buffer from the library's pool (pbwtgpu_host_alloc) as a uint8 array; give it back with
+        host_free(array).  What the host shim assembles its batches of bit columns in."""
+        p = self.lib.pbwtgpu_host_alloc(nbytes)
+        if not p:
+            raise PbwtGpuError(f"pbwtgpu_host_alloc({nbytes}) failed")
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,))
+
+    def host_free(self, arr: np.ndarray):
+        self.lib.pbwtgpu_free(arr.ctypes.data_as(_vp))
+
     # ---- panels --------------------------------------------------------------------------
     def panel_from_host(self, xbits: np.ndarray, M: int) -> Panel:
         xbits = np.ascontiguousarray(xbits, np.uint32)
@@ -293,6 +308,25 @@ class Engine:
             "d_end": d_end,
             "matches": _take(self.lib, mt, nm.value * 16, MATCH_DTYPE) if with_matches else None,
         }
+
+    def build_raw(self, xbits: np.ndarray, M: int, N: int, flags: int, a_end: np.ndarray, d_end: np.ndarray | None):
+        """pbwtgpu_build exactly as the C host shim calls it: host columns in, library-owned host buffers out.
+        -> (yz_ptr, nyz, matches_ptr, nmatch); the caller reads them in place and returns them with free_raw()."""
+        yz, nyz, mt, nm = _vp(), _i64(0), _vp(), _i64(0)
+        self._check(self.lib.pbwtgpu_build(self.ctx, _ptr(xbits), M, N, None, flags, C.byref(yz), C.byref(nyz), _ptr(a_end),
+                                           _ptr(d_end), C.byref(mt), C.byref(nm)))
+        return yz, nyz.value, mt, nm.value
+
+    def max_within_raw(self, yz_ptr, nyz: int, M: int, N: int):
+        """pbwtgpu_max_within on a host stream given by pointer -> (matches_ptr, nmatch); free_raw() afterwards."""
+        mt, nm = _vp(), _i64(0)
+        self._check(self.lib.pbwtgpu_max_within(self.ctx, yz_ptr, nyz, M, N, None, None, None, C.byref(mt), C.byref(nm)))
+        return mt, nm.value
+
+    def free_raw(self, *ptrs):
+        for p in ptrs:
+            if p:
+                self.lib.pbwtgpu_free(p)
 
     def max_within(self, yz: np.ndarray, M: int, N: int, a_start=None, with_matches=True):
         yz = np.ascontiguousarray(yz, np.uint8)

@@ -3,8 +3,11 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <climits>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "pack3.cuh"
@@ -39,6 +42,7 @@ struct pbwtgpu_ctx {
   // freed device blocks kept for reuse (cudaMalloc is far slower than a sweep at small panels)
   struct Block { void *p; size_t bytes; };
   std::vector<Block> freeBlocks;
+  std::unordered_map<void *, size_t> liveBlocks;  // true size of every block handed out (a cached block may be larger than asked for)
   int smCount = 0;
   // pinned host scratch for the few counters read back per sweep (one stream synchronisation instead of one per copy)
   unsigned long long *pinned = nullptr;
@@ -92,6 +96,7 @@ int dev_alloc(pbwtgpu_ctx *ctx, void **out, size_t bytes) {
   }
   if (best >= 0) {
     *out = ctx->freeBlocks[best].p;
+    ctx->liveBlocks[*out] = ctx->freeBlocks[best].bytes;
     ctx->freeBlocks.erase(ctx->freeBlocks.begin() + best);
     return 0;
   }
@@ -102,21 +107,84 @@ int dev_alloc(pbwtgpu_ctx *ctx, void **out, size_t bytes) {
     e = cudaMalloc(out, bytes);
   }
   if (e != cudaSuccess) return fail(ctx, PBWTGPU_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  ctx->liveBlocks[*out] = bytes;
   return 0;
 }
 
-size_t round_bytes(size_t bytes) {
-  if (bytes == 0) bytes = 16;
-  return (bytes + 255) & ~(size_t)255;
-}
-
-void dev_release(pbwtgpu_ctx *ctx, void *p, size_t bytes) {
+// back to the context's cache under the block's TRUE size (the size asked for is not what is recorded: a reused block
+// may be up to twice as large, and the cache's byte cap must count what is really held)
+void dev_release(pbwtgpu_ctx *ctx, void *p, size_t /*bytesAskedFor*/) {
   if (!p) return;
+  size_t bytes = 0;
+  auto it = ctx->liveBlocks.find(p);
+  if (it != ctx->liveBlocks.end()) { bytes = it->second; ctx->liveBlocks.erase(it); }
   size_t cached = 0;
   for (auto &b : ctx->freeBlocks) cached += b.bytes;
-  if (ctx->freeBlocks.size() < 64 && cached + bytes < ((size_t)48 << 30)) ctx->freeBlocks.push_back({p, round_bytes(bytes)});
+  if (bytes && ctx->freeBlocks.size() < 64 && cached + bytes < ((size_t)48 << 30)) ctx->freeBlocks.push_back({p, bytes});
   else cudaFree(p);
 }
+
+// ---- pinned host memory handed across the C ABI (pbwtgpu_host_alloc, malloc-style outputs) ----
+// One process-wide registry: pbwtgpu_free() takes no context.  Freed blocks are kept for reuse (cudaMallocHost of a
+// few hundred MB costs far more than a sweep); pbwtgpu_host_trim() gives them back.
+std::mutex gHostMu;
+std::unordered_map<void *, size_t> gHostLive;
+std::vector<std::pair<void *, size_t>> gHostFree;
+constexpr size_t kHostCacheBytes = (size_t)8 << 30;
+
+void *host_alloc_pinned(size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  bytes = (bytes + 4095) & ~(size_t)4095;
+  {
+    std::lock_guard<std::mutex> lk(gHostMu);
+    int best = -1;
+    for (int i = 0; i < (int)gHostFree.size(); ++i) {
+      const size_t b = gHostFree[i].second;
+      if (b >= bytes && b <= 2 * bytes + (1u << 20) && (best < 0 || b < gHostFree[best].second)) best = i;
+    }
+    if (best >= 0) {
+      void *p = gHostFree[best].first;
+      gHostLive[p] = gHostFree[best].second;
+      gHostFree.erase(gHostFree.begin() + best);
+      return p;
+    }
+  }
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    std::lock_guard<std::mutex> lk(gHostMu);  // give the cache back and retry once
+    for (auto &b : gHostFree) cudaFreeHost(b.first);
+    gHostFree.clear();
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    gHostLive[p] = bytes;
+    return p;
+  }
+  std::lock_guard<std::mutex> lk(gHostMu);
+  gHostLive[p] = bytes;
+  return p;
+}
+
+// true when p came from host_alloc_pinned (and has now been released)
+bool host_release_pinned(void *p) {
+  std::lock_guard<std::mutex> lk(gHostMu);
+  auto it = gHostLive.find(p);
+  if (it == gHostLive.end()) return false;
+  const size_t bytes = it->second;
+  gHostLive.erase(it);
+  size_t cached = 0;
+  for (auto &b : gHostFree) cached += b.second;
+  if (gHostFree.size() < 16 && cached + bytes <= kHostCacheBytes) gHostFree.push_back({p, bytes});
+  else cudaFreeHost(p);
+  return true;
+}
+
+// releases a host buffer handed out by this library unless ownership was passed on (release())
+struct HostGuard {
+  void *p = nullptr;
+  explicit HostGuard(void *q) : p(q) {}
+  ~HostGuard() { if (p && !host_release_pinned(p)) free(p); }
+  void *release() { void *q = p; p = nullptr; return q; }
+};
 
 // scoped temporary device allocations, returned to the context cache on scope exit
 struct Temps {
@@ -239,6 +307,7 @@ struct WindowedSweep {
     // panels wider than one CTA's shared memory sweep with their state in global memory (sweep_global.cu)
     useGlobal = M > sweep_smem_max_m(true) || ctx->optForceGlobal;
     matchWanted = wantMatch;
+
     W = 1;
     positionSpace = mode == kSorted;
     if (M >= 2 && !(positionSpace && sharded_)) {
@@ -248,6 +317,9 @@ struct WindowedSweep {
     }
     if (useGlobal) {
       sweep_global_plan(M, ctx->smCount, W, kGather, true, wantMatch, false, 0, !ctx->optNoCluster, &G, &chunk, &W, &gb.cluster);
+      // the (site, CTA) record segments of a wide-panel match sweep are scanned with 32-bit item counts (windows.cu)
+      if (wantMatch && (long long)(N + 1) * G + 1 > INT_MAX)
+        return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "N=%d too large for a match sweep over a wide panel (%d CTAs per window)", N, G);
     }
     spw = N > 0 ? (N + W - 1) / W : 1;
     W = N > 0 ? (N + spw - 1) / spw : 1;
@@ -414,6 +486,7 @@ struct WindowedSweep {
                            ord[nxt] + s1 * oA(), dv[nxt] + s1 * oD(), g[nxt] + s1 * oA(), gfd[nxt] + s1 * oA()))
         return rc;
       // nodes below the stride are already final
+      ScopedTimer tc(ctx, PBWTGPU_K_COPY);
       CUDA_TRY(ctx, cudaMemcpyAsync(ord[nxt] + oA(), ord[cur] + oA(), sizeof(int32_t) * oA() * stride, cudaMemcpyDeviceToDevice, ctx->stream));
       CUDA_TRY(ctx, cudaMemcpyAsync(dv[nxt] + oD(), dv[cur] + oD(), sizeof(int32_t) * oD() * stride, cudaMemcpyDeviceToDevice, ctx->stream));
       CUDA_TRY(ctx, cudaMemcpyAsync(g[nxt] + oA(), g[cur] + oA(), sizeof(int32_t) * oA() * stride, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -436,6 +509,7 @@ struct WindowedSweep {
   int export_aggregate(int32_t *dst) {
     if (!sharded || nodes < 1) return fail(ctx, PBWTGPU_ERR_ARG, "export_aggregate: not a shard");
     const size_t s = (size_t)nodes;  // last node's slot
+    ScopedTimer tc(ctx, PBWTGPU_K_COPY);
     CUDA_TRY(ctx, cudaMemcpyAsync(dst, ord[cur] + s * oA(), sizeof(int32_t) * M, cudaMemcpyDeviceToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(dst + M, dv[cur] + s * oD(), sizeof(int32_t) * (M + 1), cudaMemcpyDeviceToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(dst + 2 * M + 1, g[cur] + s * oA(), sizeof(int32_t) * M, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -780,6 +854,8 @@ const char *pbwtgpu_last_error(pbwtgpu_ctx *ctx) { return ctx ? ctx->lastError.c
 
 int pbwtgpu_set_stream(pbwtgpu_ctx *ctx, void *s) {
   if (!ctx) return PBWTGPU_ERR_ARG;
+  // cached device blocks are reused without regard to the stream they were last used on: drain the old one first
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->stream = s ? (cudaStream_t)s : ctx->ownStream;
   return 0;
 }
@@ -913,7 +989,10 @@ int pbwtgpu_sweep_yz_device(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, in
   pbwtgpu_result *res = new pbwtgpu_result;
   const int rc = run_sweep(ctx, ycols, pbwtgpu_words_per_col(M), M, N, kSorted, a_start, flags | PBWTGPU_WANT_D, res);
   if (rc) { pbwtgpu_result_free(ctx, res); return rc; }
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // temporaries are recycled on return
+  if (cudaError_t e = cudaStreamSynchronize(ctx->stream)) {  // temporaries are recycled on return
+    pbwtgpu_result_free(ctx, res);
+    return fail(ctx, PBWTGPU_ERR_CUDA, "sweep_yz: %s", cudaGetErrorString(e));
+  }
   *out = res;
   return 0;
 }
@@ -998,22 +1077,16 @@ void pbwtgpu_shard_free(pbwtgpu_ctx *ctx, pbwtgpu_shard *sh) {
 }
 
 // ---- one-shot host-buffer entry points -----------------------------------------------------------
+// Outputs handed to the caller come from the pinned registry (full PCIe rate, reused across calls); the caller gives
+// them back with pbwtgpu_free.
 static int fetch_to_malloc(pbwtgpu_ctx *ctx, pbwtgpu_result *res, uint8_t **yz, int64_t *nyz, int32_t *a_end,
                            int32_t *d_end, pbwtgpu_match **matches, int64_t *nmatch) {
-  uint8_t *hy = nullptr;
-  pbwtgpu_match *hm = nullptr;
-  if (yz) {
-    hy = (uint8_t *)malloc((size_t)std::max<int64_t>(res->nyz, 1));
-    if (!hy) return fail(ctx, PBWTGPU_ERR_NOMEM, "malloc yz");
-  }
-  if (matches) {
-    hm = (pbwtgpu_match *)malloc(sizeof(pbwtgpu_match) * (size_t)std::max<int64_t>(res->nrec, 1));
-    if (!hm) { free(hy); return fail(ctx, PBWTGPU_ERR_NOMEM, "malloc matches"); }
-  }
-  const int rc = pbwtgpu_result_fetch(ctx, res, hy, a_end, d_end, hm);
-  if (rc) { free(hy); free(hm); return rc; }
-  if (yz) { *yz = hy; if (nyz) *nyz = res->nyz; }
-  if (matches) { *matches = hm; if (nmatch) *nmatch = res->nrec; }
+  HostGuard hy(yz ? host_alloc_pinned((size_t)std::max<int64_t>(res->nyz, 1)) : nullptr);
+  HostGuard hm(matches ? host_alloc_pinned(sizeof(pbwtgpu_match) * (size_t)std::max<int64_t>(res->nrec, 1)) : nullptr);
+  if ((yz && !hy.p) || (matches && !hm.p)) return fail(ctx, PBWTGPU_ERR_NOMEM, "pinned host allocation failed");
+  if (int rc = pbwtgpu_result_fetch(ctx, res, (uint8_t *)hy.p, a_end, d_end, (pbwtgpu_match *)hm.p)) return rc;
+  if (yz) { *yz = (uint8_t *)hy.release(); if (nyz) *nyz = res->nyz; }
+  if (matches) { *matches = (pbwtgpu_match *)hm.release(); if (nmatch) *nmatch = res->nrec; }
   return 0;
 }
 
@@ -1137,6 +1210,7 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
     const size_t MS = (size_t)G * chunk;
     gb.G = G; gb.chunk = chunk;
     nSeg = (long long)(N + 1) * G + 1;
+    if (nSeg > INT_MAX) return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "match_sweep: N=%d too large (%lld record segments)", N, nSeg);
     char *sy = nullptr;
     if (int rc = tmp.get(&gb.aBuf, 2 * MS)) return rc;
     if (int rc = tmp.get(&gb.dBuf, 2 * (MS + 4))) return rc;
@@ -1248,15 +1322,15 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
     CUDA_TRY(ctx, launch_gather_records(pool, chunkTab, poolChunks, offsDev, counts, 1, maxChunks, recDev, ctx->stream));
     ctx->launches[PBWTGPU_K_AUX] += maxChunks > 0;
   }
-  pbwtgpu_match *hm = (pbwtgpu_match *)malloc(sizeof(pbwtgpu_match) * (size_t)std::max<unsigned long long>(got[0], 1));
-  pbwtgpu_nomatch *hn = (pbwtgpu_nomatch *)malloc(sizeof(pbwtgpu_nomatch) * (size_t)std::max<unsigned long long>(got[1], 1));
-  if (!hm || !hn) { free(hm); free(hn); return fail(ctx, PBWTGPU_ERR_NOMEM, "malloc records"); }
-  if (got[0]) CUDA_TRY(ctx, cudaMemcpyAsync(hm, recDev, sizeof(pbwtgpu_match) * got[0], cudaMemcpyDeviceToHost, ctx->stream));
-  if (got[1]) CUDA_TRY(ctx, cudaMemcpyAsync(hn, nmSorted, sizeof(pbwtgpu_nomatch) * got[1], cudaMemcpyDeviceToHost, ctx->stream));
+  HostGuard gm(host_alloc_pinned(sizeof(pbwtgpu_match) * (size_t)std::max<unsigned long long>(got[0], 1)));
+  HostGuard gn(host_alloc_pinned(sizeof(pbwtgpu_nomatch) * (size_t)std::max<unsigned long long>(got[1], 1)));
+  if (!gm.p || !gn.p) return fail(ctx, PBWTGPU_ERR_NOMEM, "pinned host allocation failed (records)");
+  if (got[0]) CUDA_TRY(ctx, cudaMemcpyAsync(gm.p, recDev, sizeof(pbwtgpu_match) * got[0], cudaMemcpyDeviceToHost, ctx->stream));
+  if (got[1]) CUDA_TRY(ctx, cudaMemcpyAsync(gn.p, nmSorted, sizeof(pbwtgpu_nomatch) * got[1], cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  *matches = hm;
+  *matches = (pbwtgpu_match *)gm.release();
   *nmatch = (int64_t)got[0];
-  if (nomatch) *nomatch = hn; else free(hn);
+  if (nomatch) *nomatch = (pbwtgpu_nomatch *)gn.release();
   if (nnomatch) *nnomatch = (int64_t)got[1];
   return 0;
 }
@@ -1290,11 +1364,11 @@ int pbwtgpu_pack3(pbwtgpu_ctx *ctx, const uint8_t *y, int M, int N, uint8_t **yz
     CUDA_TRY(ctx, p3_emit_columns(ycols, wpc, M, N, colBase, yzDev, ctx->stream));
     ctx->launches[PBWTGPU_K_PACK3] += (N > 0);
   }
-  uint8_t *h = (uint8_t *)malloc((size_t)std::max<int64_t>(total, 1));
-  if (!h) return fail(ctx, PBWTGPU_ERR_NOMEM, "malloc yz");
-  if (total) CUDA_TRY(ctx, cudaMemcpyAsync(h, yzDev, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+  HostGuard h(host_alloc_pinned((size_t)std::max<int64_t>(total, 1)));
+  if (!h.p) return fail(ctx, PBWTGPU_ERR_NOMEM, "pinned host allocation failed (yz)");
+  if (total) CUDA_TRY(ctx, cudaMemcpyAsync(h.p, yzDev, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  *yz = h;
+  *yz = (uint8_t *)h.release();
   *nyz = total;
   return 0;
 }
@@ -1317,6 +1391,16 @@ int pbwtgpu_unpack3(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int
   return 0;
 }
 
-void pbwtgpu_free(void *p) { free(p); }
+void *pbwtgpu_host_alloc(size_t bytes) { return host_alloc_pinned(bytes); }
+
+void pbwtgpu_free(void *p) {
+  if (p && !host_release_pinned(p)) free(p);
+}
+
+void pbwtgpu_host_trim(void) {
+  std::lock_guard<std::mutex> lk(gHostMu);
+  for (auto &b : gHostFree) cudaFreeHost(b.first);
+  gHostFree.clear();
+}
 
 }  // extern "C"

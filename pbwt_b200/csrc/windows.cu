@@ -17,6 +17,7 @@
 #include "windows.cuh"
 
 #include <algorithm>
+#include <climits>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -284,6 +285,7 @@ size_t segment_scan_temp_bytes(long long nSeg) {
 
 int launch_segment_scan(const int32_t *segCnt, long long nSeg, long long *segDst, void *temp, size_t tempBytes,
                         cudaStream_t stream) {
+  if (nSeg > INT_MAX) return (int)cudaErrorInvalidValue;  // callers refuse such shapes up front (PBWTGPU_ERR_UNSUPPORTED)
   cub::TransformInputIterator<long long, IntToLL, const int32_t *> it(segCnt, IntToLL());
   return (int)cub::DeviceScan::ExclusiveSum(temp, tempBytes, it, segDst, (int)nSeg, stream);
 }
@@ -303,6 +305,7 @@ int launch_gather_segments(const pbwtgpu_match *pool, const int *chunkTab, int p
 int sort_nomatch(const unsigned long long *keys, const pbwtgpu_nomatch *events, long long n, pbwtgpu_nomatch *out,
                  cudaStream_t stream) {
   if (n <= 0) return 0;
+  if (n > INT_MAX) return (int)cudaErrorInvalidValue;
   unsigned long long *keysOut = nullptr;
   uint32_t *idxIn = nullptr, *idxOut = nullptr;
   void *temp = nullptr;

@@ -342,19 +342,17 @@ void matchSequencesDynamic (PBWT *p, FILE *fp)	/* pbwtMatch.c:352-357 */
    UNSORTED column x; columns are bit-packed into a batch, and a full batch (or the final partial one) is swept
    on the GPU by pbwtgpu_build from the true order carried between batches, the pack3 bytes are appended to
    u->z exactly where pack3arrayAdd would have put them, and ToAFend hands the true order to p->aFend.
-   The readers themselves are untouched.  Cursors that do not start from the identity fall back to the
-   reference's functions. ---- */
+   The readers themselves are untouched. ---- */
 
-void pbwtCursorWriteForwards (PbwtCursor *u) ;	/* the reference's own (pbwtCore.c:573-578, :587-591) */
-void pbwtCursorToAFend (PbwtCursor *u, PBWT *p) ;
+void pbwtCursorToAFend (PbwtCursor *u, PBWT *p) ;	/* the reference's own (pbwtCore.c:587-591) */
 
 static struct
 { PbwtCursor *u ;		/* the reader's cursor being batched */
   int M, wpc, cap, n ;		/* batch capacity and fill, in sites */
-  long written ;		/* bytes appended to u->z so far */
-  uint32_t *bits ;
+  long written ;		/* arrayMax(u->z) as this batcher left it: anything else means another cursor at a recycled address */
+  uint32_t *bits ;		/* page-locked (pbwtgpu_host_alloc) */
   int *aTrue ;			/* the real a[] entering the batch */
-  PbwtCursor *plain ;		/* a cursor handed to the reference's functions instead */
+  BOOL startIsIdentity ;	/* u->a, frozen at adoption, is the identity: u->y is the column as parsed */
 } rb ;
 
 static void readerFlush (PbwtCursor *u)
@@ -372,26 +370,28 @@ static void readerFlush (PbwtCursor *u)
   memcpy (arrp(u->z,max,uchar), yz, nyz) ;
   arrayMax(u->z) = max + nyz ;
   u->n += nyz ;
-  rb.written += nyz ;
+  rb.written = max + nyz ;
   memcpy (rb.aTrue, aNew, rb.M*sizeof(int)) ;
   memset (rb.bits, 0, (size_t)rb.wpc * rb.cap * sizeof(uint32_t)) ;
   rb.n = 0 ;
   pbwtgpu_free (yz) ; free (aNew) ;
 }
 
+/* Any cursor is adopted, whatever order it starts from and whether or not its stream is empty (there is no CPU path):
+   u->a is frozen at adoption, so what the reader gathers is y[j] = x[a0[j]] with a0 that frozen order, and the parsed
+   column is recovered as x[a0[j]] = y[j]; the true order starts as a copy of a0 and lives in rb.aTrue. */
 void gpuReaderWriteForwards (PbwtCursor *u)
 {
   int j ;
   uint32_t *col ;
 
-  if (u == rb.plain && u != rb.u) { pbwtCursorWriteForwards (u) ; return ; }
-  if (u != rb.u || arrayMax(u->z) != rb.written)	/* a new reader (possibly at a recycled address) */
-    { BOOL isIdentity = (arrayMax(u->z) == 0) ;
-      for (j = 0 ; isIdentity && j < u->M ; ++j) if (u->a[j] != j) isIdentity = FALSE ;
-      if (!isIdentity) { rb.plain = u ; if (rb.u == u) rb.u = 0 ; pbwtCursorWriteForwards (u) ; return ; }
-      if (rb.u && rb.n) die ("gpuReaderWriteForwards: a batch of another cursor is still pending") ;
-      free (rb.bits) ; free (rb.aTrue) ;
-      rb.u = u ; rb.plain = 0 ; rb.M = u->M ; rb.wpc = pbwtgpu_words_per_col (u->M) ; rb.n = 0 ; rb.written = 0 ;
+  /* a cursor is recognised by its address, which the allocator recycles: it is the one being batched only if its
+     width and the size of its stream are what this batcher left behind; an untouched pair (nothing written, nothing
+     pending) is always (re)adopted, which costs nothing */
+  if (u != rb.u || u->M != rb.M || arrayMax(u->z) != rb.written || (!rb.n && !rb.written))
+    { if (rb.u && rb.n) die ("gpuReaderWriteForwards: a batch of another cursor is still pending") ;
+      pbwtgpu_free (rb.bits) ; free (rb.aTrue) ;
+      rb.u = u ; rb.M = u->M ; rb.wpc = pbwtgpu_words_per_col (u->M) ; rb.n = 0 ; rb.written = arrayMax(u->z) ;
       { const char *e = getenv ("PBWTGPU_READER_BATCH") ;	/* sites per batch; default bounded by 256 MB of columns */
 	long cap = e ? atol (e) : 65536 ;
 	long most = (256L << 20) / (4L * rb.wpc) ;
@@ -399,19 +399,30 @@ void gpuReaderWriteForwards (PbwtCursor *u)
 	if (cap < 1) cap = 1 ;
 	rb.cap = (int) cap ;
       }
-      rb.bits = mycalloc ((size_t)rb.wpc * rb.cap, uint32_t) ;
+      /* page-locked, so that the batch goes up at the full PCIe rate (pbwtgpu_host_alloc) */
+      rb.bits = (uint32_t*) pbwtgpu_host_alloc ((size_t)rb.wpc * rb.cap * sizeof(uint32_t)) ;
+      if (!rb.bits) die ("gpuReaderWriteForwards: no page-locked memory for a batch of %d sites", rb.cap) ;
+      memset (rb.bits, 0, (size_t)rb.wpc * rb.cap * sizeof(uint32_t)) ;
       rb.aTrue = myalloc (rb.M, int) ;
-      for (j = 0 ; j < rb.M ; ++j) rb.aTrue[j] = j ;
+      memcpy (rb.aTrue, u->a, rb.M*sizeof(int)) ;
+      rb.startIsIdentity = TRUE ;
+      for (j = 0 ; j < rb.M ; ++j) if (u->a[j] != j) { rb.startIsIdentity = FALSE ; break ; }
     }
-  col = rb.bits + (size_t)rb.n * rb.wpc ;	/* u->a is the identity, so u->y is the column as parsed */
-  for (j = 0 ; j < rb.M ; ++j) if (u->y[j]) col[j >> 5] |= 1u << (j & 31) ;
+  col = rb.bits + (size_t)rb.n * rb.wpc ;
+  if (rb.startIsIdentity)
+    { for (j = 0 ; j < rb.M ; ++j) if (u->y[j]) col[j >> 5] |= 1u << (j & 31) ; }
+  else
+    for (j = 0 ; j < rb.M ; ++j) if (u->y[j]) { int h = u->a[j] ; col[h >> 5] |= 1u << (h & 31) ; }
   u->isBlockEnd = FALSE ;
   if (++rb.n == rb.cap) readerFlush (u) ;
 }
 
 void gpuReaderToAFend (PbwtCursor *u, PBWT *p)
 {
-  if (u != rb.u) { pbwtCursorToAFend (u, p) ; return ; }
+  /* only the cursor this batch belongs to: same address, same width, and a stream exactly as this batcher left it (a
+     later reader that landed on the recycled address and wrote nothing must not inherit the previous order) */
+  if (u != rb.u || u->M != rb.M || p->M != rb.M || arrayMax(u->z) != rb.written)
+    { pbwtCursorToAFend (u, p) ; return ; }
   readerFlush (u) ;
   if (!p->aFend) p->aFend = myalloc (p->M, int) ;
   memcpy (p->aFend, rb.aTrue, p->M*sizeof(int)) ;

@@ -213,11 +213,20 @@ PBWT *pbwtReadVcfGT (char *filename)
 
       if (nCheckPoint && !(p->N % nCheckPoint)) pbwtCheckPoint (u, p) ;
     }
+  { int zerr = Z_OK ;			/* a NULL from gzgets is the end of the file only when zlib agrees: a truncated
+					   stream or a bad CRC / length trailer must not yield a silently shorter panel */
+    const char *zmsg = gzerror (fp, &zerr) ;
+    if (zerr == Z_BUF_ERROR && !gzeof (fp)) die ("pbwtReadVcfGT(%s): compressed input is truncated", filename) ;
+    if (zerr != Z_OK && zerr != Z_STREAM_END && zerr != Z_BUF_ERROR)
+      die ("pbwtReadVcfGT(%s): error reading compressed input: %s", filename, zmsg ? zmsg : "zlib error") ;
+  }
   if (!p) die ("%s: no #CHROM header line", filename) ;
   gpuReaderToAFend (u, p) ;
 
   free (line) ; free (gt) ; free (x) ; free (xMissing) ; pbwtCursorDestroy (u) ;
-  gzclose (fp) ;
+  { int zrc = gzclose (fp) ;
+    if (zrc != Z_OK && zrc != Z_BUF_ERROR) die ("pbwtReadVcfGT(%s): error closing input (zlib %d)", filename, zrc) ;
+  }
 
   fprintf (logFile, "read genotypes from %s with %ld sample names and %ld sites on chromosome %s: M, N are %d, %d\n",
 	   filename, arrayMax(p->samples)/2, arrayMax(p->sites), p->chrom, p->M, p->N) ;

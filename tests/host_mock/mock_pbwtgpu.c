@@ -24,6 +24,8 @@ void pbwtgpu_destroy(pbwtgpu_ctx *ctx) { (void)ctx; }
 const char *pbwtgpu_strerror(int code) { return code == PBWTGPU_OK ? "ok" : "mock device error"; }
 const char *pbwtgpu_last_error(pbwtgpu_ctx *ctx) { (void)ctx; return "mock device (CPU oracle port)"; }
 void pbwtgpu_free(void *p) { free(p); }
+void *pbwtgpu_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void pbwtgpu_host_trim(void) {}
 
 int pbwtgpu_build(pbwtgpu_ctx *ctx, const uint32_t *xbits, int M, int N, const int32_t *a_start, unsigned flags,
                   uint8_t **yz, int64_t *nyz, int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches, int64_t *nmatch) {

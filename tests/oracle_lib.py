@@ -181,6 +181,64 @@ class Oracle:
         return tb.value, tm.value, nyz.value, nm.value
 
 
+    def time_build_maxwithin_ck(self, xbits, M, N):
+        """-> (t_build, t_match, nyz, nmatch, ck[4]); ck = checksums of the pack3 stream and of the records (oracle_api.h)."""
+        wpc = words_per_col(M)
+        xbits = np.ascontiguousarray(xbits, np.uint32)
+        tb, tm = C.c_double(0), C.c_double(0)
+        nyz, nm = C.c_int64(0), C.c_int64(0)
+        ck = np.zeros(4, np.uint64)
+        self._f("time_build_maxwithin_ck")(_p(xbits, c_u32p), wpc, M, N, C.byref(tb), C.byref(tm), C.byref(nyz), C.byref(nm),
+                                           ck.ctypes.data_as(C.c_void_p))
+        return tb.value, tm.value, nyz.value, nm.value, [int(v) for v in ck]
+
+    def time_build(self, xbits, M, N, with_d):
+        """-> (t_build, nyz, ck[2]): the build alone (pbwtCursorWriteForwards / ...AD over all sites)."""
+        wpc = words_per_col(M)
+        xbits = np.ascontiguousarray(xbits, np.uint32)
+        tb, nyz = C.c_double(0), C.c_int64(0)
+        ck = np.zeros(2, np.uint64)
+        self._f("time_build")(_p(xbits, c_u32p), wpc, M, N, int(with_d), C.byref(tb), C.byref(nyz), ck.ctypes.data_as(C.c_void_p))
+        return tb.value, nyz.value, [int(v) for v in ck]
+
+
+_K1, _K2 = np.uint64(0x9E3779B97F4A7C15), np.uint64(0xC2B2AE3D27D4EB4F)
+
+
+def checksum_parts(mix: np.ndarray):
+    """(count, S, T) of a run of items: S = sum m_i, T = sum (i+1) m_i (mod 2^64)."""
+    n = mix.size
+    with np.errstate(over="ignore"):
+        S = int(mix.sum(dtype=np.uint64))
+        T = int((mix * np.arange(1, n + 1, dtype=np.uint64)).sum(dtype=np.uint64))
+    return n, S, T
+
+
+def checksum_join(parts):
+    """checksums of a concatenation from the (count, S, T) of its pieces, in order -> [S, T]"""
+    mask = (1 << 64) - 1
+    off = S = T = 0
+    for n, s, t in parts:
+        S = (S + s) & mask
+        T = (T + t + off * s) & mask
+        off += n
+    return [S, T]
+
+
+def mix_bytes(b: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        return b.astype(np.uint64) * _K1 + np.uint64(1)
+
+
+def mix_records(rec: np.ndarray) -> np.ndarray:
+    """oracle_api.h: oracle_mix_record over a MATCH_DTYPE array"""
+    w = np.ascontiguousarray(rec).view("<u8").reshape(-1, 2)
+    with np.errstate(over="ignore"):
+        m = (w[:, 0] * _K1) ^ (w[:, 1] * _K2)
+        m ^= m >> np.uint64(29)
+    return m | np.uint64(1)
+
+
 def sweep_from(xbits, M, N, k0, ntotal, a_start, d_start):
     """oracle/pbwt_oracle.c:orc_sweep_from -- build + maxWithin of one site shard from a given state."""
     o = port()
