@@ -20,7 +20,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpbwtgpu.so")
+LIB_PATH = os.environ.get("PBWTGPU_LIB") or os.path.join(_HERE, "libpbwtgpu.so")  # (the override is a development aid: A/B builds)
 
 WANT_YZ, WANT_D, WANT_MAXWITHIN, WANT_LONGWITHIN = 1, 2, 4, 8
 KERNEL_CLASSES = ("sweep", "pack3", "unpack3", "query", "synth", "aux", "prepass", "combine", "copy")

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "pack3.cuh"
+#include "query_chain.cuh"
 #include "sweep.cuh"
 #include "synth.cuh"
 #include "windows.cuh"
@@ -284,6 +285,19 @@ struct WindowedSweep {
   // permutation of sorted positions over its sites (the sorted columns do not depend on the labels)
   bool positionSpace = false;
   int32_t *iota = nullptr, *ordScratch = nullptr;
+  int forceSpw = 0;  // > 0: windows of exactly this many sites (a second sweep that must share another's boundaries)
+  bool allowForceGlobal = true;  // honour the testing option force_global
+  // ---- window-parallel query sweep (matchSequencesSweep, pbwtMatch.c:363-443); set queryQ / qcols / qwpc before init ----
+  // pass 1 sweeps every window from the fresh query state with clamped tiers (SweepArgs::queryMode 1) while it computes
+  // the window nodes; the chain (query_chain.cu) turns the clamped end states into the true state entering every
+  // window; pass 2 (queryMode 2) runs all windows from their true panel AND query states and emits.
+  int queryQ = 0;
+  const uint32_t *qcols = nullptr;
+  int qwpc = 0;
+  const int32_t *qaWin = nullptr;          // [W][Q] query PBWT order entering every window (NULL = identity, W == 1 only)
+  int32_t *qNodeOrd = nullptr;             // [nodes][M] the windows' own permutations (position space), for the chain
+  int32_t *qf1 = nullptr, *qe1 = nullptr;  // [W][Q] clamped end states (pass 1)
+  int32_t *qfT = nullptr, *qeT = nullptr;  // [W][Q] true states entering the windows (chain), pass 2 works in place
 
   explicit WindowedSweep(pbwtgpu_ctx *c) : ctx(c), tmp(c) {}
   size_t oA() const { return (size_t)M; }
@@ -305,7 +319,7 @@ struct WindowedSweep {
     if (M < 1 || N < 0) return fail(ctx, PBWTGPU_ERR_ARG, "bad panel shape M=%d N=%d", M, N);
     if (nTotal >= kPseudoLabelBase - 64) return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "N=%d too large", nTotal);
     // panels wider than one CTA's shared memory sweep with their state in global memory (sweep_global.cu)
-    useGlobal = M > sweep_smem_max_m(true) || ctx->optForceGlobal;
+    useGlobal = M > sweep_smem_max_m(true) || (ctx->optForceGlobal && allowForceGlobal) || queryQ > 0;
     matchWanted = wantMatch;
 
     W = 1;
@@ -314,14 +328,14 @@ struct WindowedSweep {
       const long long want = ctx->optWindows > 0 ? ctx->optWindows : ctx->smCount;
       const int minSites = ctx->optWindows > 0 ? 1 : 256;  // below this a window does not repay its two extra passes
       W = (int)std::max<long long>(1, std::min<long long>(want, N / minSites));
+      if (forceSpw > 0) W = std::max(1, (N + forceSpw - 1) / forceSpw);
     }
     if (useGlobal) {
-      sweep_global_plan(M, ctx->smCount, W, kGather, true, wantMatch, false, 0, !ctx->optNoCluster, &G, &chunk, &W, &gb.cluster);
-      // the (site, CTA) record segments of a wide-panel match sweep are scanned with 32-bit item counts (windows.cu)
-      if (wantMatch && (long long)(N + 1) * G + 1 > INT_MAX)
-        return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "N=%d too large for a match sweep over a wide panel (%d CTAs per window)", N, G);
+      sweep_global_plan(M, ctx->smCount, W, queryQ ? kSorted : kGather, true, wantMatch, queryQ > 0, queryQ, !ctx->optNoCluster, &G, &chunk,
+                        &W, &gb.cluster);
     }
     spw = N > 0 ? (N + W - 1) / W : 1;
+    if (forceSpw > 0) spw = forceSpw;
     W = N > 0 ? (N + spw - 1) / spw : 1;
     // A panel swept with matches: its first windows (everything still matches back to site 0) and its last one (every
     // block is reported at site N) carry 10-17 % more work per site than the others (option window_times), so windows
@@ -351,11 +365,24 @@ struct WindowedSweep {
       char *sy = nullptr;
       if (int rc = tmp.get(&sy, sweep_global_sync_bytes(W))) return rc;
       gb.gsync = sy;
-      if (wantMatch) {
+      if (wantMatch || queryQ) {
+        if ((long long)(N + 1) * G + 1 > INT_MAX)
+          return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "N=%d too large for a match sweep over a wide panel (%d CTAs per window)", N, G);
         if (int rc = tmp.get(&gb.ySorted, sweep_global_column_words(G, chunk, W))) return rc;
         if (int rc = tmp.get(&gb.wmaxG, sweep_global_column_words(G, chunk, W))) return rc;
         if (int rc = tmp.get(&gb.segCnt, (size_t)(N + 1) * G + 1)) return rc;
         if (int rc = tmp.get(&gb.segSrc, (size_t)(N + 1) * G + 1)) return rc;
+      }
+      if (queryQ) {
+        const size_t cw = sweep_global_column_words(G, chunk, W);
+        if (int rc = tmp.get(&gb.zpre, cw)) return rc;
+        if (int rc = tmp.get(&gb.any1, cw / 32)) return rc;
+        if (int rc = tmp.get(&gb.any0, cw / 32)) return rc;
+        if (int rc = tmp.get(&gb.wmax2, cw / 32)) return rc;
+        if (int rc = tmp.get(&qf1, (size_t)W * queryQ)) return rc;
+        if (int rc = tmp.get(&qe1, (size_t)W * queryQ)) return rc;
+        if (int rc = tmp.get(&qfT, (size_t)W * queryQ)) return rc;
+        if (int rc = tmp.get(&qeT, (size_t)W * queryQ)) return rc;
       }
     }
     const bool needNodes = nodes > 0;
@@ -374,6 +401,8 @@ struct WindowedSweep {
       if (int rc = tmp.get(&iota, (size_t)M)) return rc;
       if (int rc = tmp.get(&ordScratch, (size_t)nodes * M)) return rc;
       CUDA_TRY(ctx, launch_iota(iota, M, ctx->stream));
+      if (queryQ)
+        if (int rc = tmp.get(&qNodeOrd, (size_t)nodes * M)) return rc;
     }
     {  // slot 0: the panel's start order
       std::vector<int32_t> ident;
@@ -433,10 +462,36 @@ struct WindowedSweep {
     return 0;
   }
 
+  void query_args(SweepArgs &a, int mode, int32_t *qf, int32_t *qe) {
+    a.qcols = qcols; a.qwpc = qwpc; a.Q = queryQ;
+    a.qaStart = qaWin; a.qaPerWindow = qaWin != nullptr;
+    a.queryMode = mode;
+    gb.qf = qf; gb.qe = qe;
+  }
+  int launch_query(const SweepArgs &args) {
+    const int wl = std::max(W, 1);
+    cudaError_t e = cudaMemsetAsync(gb.partials, 0, sizeof(uint32_t) * (size_t)wl * G * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(gb.gsync, 0, sweep_global_sync_bytes(wl), ctx->stream);
+    if (e != cudaSuccess) return (int)e;
+    return launch_query_sweep_global(args, gb, ctx->stream);
+  }
+
+  // true query state entering every window: fresh at the panel's first site (pbwtMatch.c:368-369), then the chain
+  int query_chain() {
+    QueryChainArgs c{};
+    c.Q = queryQ; c.M = M; c.W = W; c.steps = nodes; c.spw = spw; c.firstLabel = siteOffset;
+    c.dv = dv[cur]; c.nodeOrd = qNodeOrd; c.fClamped = qf1; c.eClamped = qe1;
+    c.fTrue = qfT; c.eTrue = qeT;
+    ScopedTimer t(ctx, PBWTGPU_K_QUERY);
+    CUDA_TRY(ctx, launch_query_chain(c, ctx->stream));
+    ctx->launches[PBWTGPU_K_QUERY] += 1;
+    return 0;
+  }
+
   // pass 1 + tie groups + inclusive scan: afterwards slot w+1 holds the exact state at the end of window w
   // (relative to the start order in slot 0)
   int prepare() {
-    if (nodes <= 0) return 0;
+    if (nodes <= 0) return queryQ ? query_chain() : 0;
     SweepArgs a1{};
     a1.src = src; a1.wpc = wpc; a1.M = M; a1.N = N; a1.sitesPerWindow = spw; a1.firstWindowSites = firstSites; a1.secondWindowSites = secondSites;
     a1.nWindows = nodes;
@@ -468,6 +523,17 @@ struct WindowedSweep {
       CUDA_TRY(ctx, launch_window_sort_global(src, wpc, M, N, spw, siteOffset, a1.aStart, nodes, ctx->smCount, T, a1.aEnd, a1.dEnd,
                                               ctx->stream));
       ctx->launches[PBWTGPU_K_PREPASS] += 3;
+    } else if (queryQ) {
+      // the query sweep's clamped pass rides on pass 1: in position space the window's own sweep holds the true order
+      // (ties keep their entry order) and its fresh divergence is the true one clamped at the window's first site
+      query_args(a1, 1, qf1, qe1);
+      {
+        ScopedTimer t(ctx, PBWTGPU_K_PREPASS);
+        CUDA_TRY(ctx, launch_query(a1));
+        ctx->launches[PBWTGPU_K_PREPASS] += 1;
+      }
+      ScopedTimer tc(ctx, PBWTGPU_K_COPY);
+      CUDA_TRY(ctx, cudaMemcpyAsync(qNodeOrd, a1.aEnd, sizeof(int32_t) * oA() * nodes, cudaMemcpyDeviceToDevice, ctx->stream));
     } else {
       ScopedTimer t(ctx, PBWTGPU_K_PREPASS);
       CUDA_TRY(ctx, launch(a1, mode, true, false));
@@ -501,6 +567,7 @@ struct WindowedSweep {
       ctx->launches[PBWTGPU_K_AUX] += 1;
     }
     haveDStart = true;
+    if (queryQ) return query_chain();
     return 0;
   }
 
@@ -758,6 +825,98 @@ struct WindowedSweep {
     return 0;
   }
 };
+
+// pass 2 of the window-parallel query sweep: every window from its true panel state (slots of the scan) and its true
+// query state (the chain), records through the chunk pool, (site, CTA) segments into callback order, "no match" events
+// sorted by (site, query position).  Outputs are device arrays owned by ws.tmp.
+int finish_query_sweep(WindowedSweep &ws, pbwtgpu_match **recDev, unsigned long long *nrec, pbwtgpu_nomatch **nmDev,
+                       unsigned long long *nnm) {
+  pbwtgpu_ctx *ctx = ws.ctx;
+  Temps &tmp = ws.tmp;
+  const int M = ws.M, N = ws.N, Q = ws.queryQ, G = ws.G, W = ws.W;
+  const long long nSeg = (long long)(N + 1) * G + 1;
+  long long *segDst = nullptr;
+  char *scanTemp = nullptr;
+  if (int rc = tmp.get(&segDst, (size_t)nSeg)) return rc;
+  const size_t scanTempBytes = segment_scan_temp_bytes(nSeg);
+  if (int rc = tmp.get(&scanTemp, scanTempBytes)) return rc;
+  unsigned long long *counts = nullptr;  // [0] unused, [1] "no match" events
+  int *chunkCounter = nullptr, *chunkTab = nullptr;
+  if (int rc = tmp.get(&counts, 2)) return rc;
+  if (int rc = tmp.get(&chunkCounter, 1)) return rc;
+  long long recCap = ctx->optMatchCap > 0 ? ctx->optMatchCap : std::max<long long>(1 << 20, 4096LL * Q);
+  long long nmCap = 1 << 16;
+  pbwtgpu_match *pool = nullptr;
+  pbwtgpu_nomatch *nm = nullptr;
+  unsigned long long got[2] = {0, 0};
+  int poolChunks = 0;
+  const int producers = W * G;
+  // the chain's output is consumed in place by pass 2: keep a copy for a rerun after a pool overflow
+  int32_t *qfKeep = nullptr, *qeKeep = nullptr;
+  if (int rc = tmp.get(&qfKeep, (size_t)W * Q)) return rc;
+  if (int rc = tmp.get(&qeKeep, (size_t)W * Q)) return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(qfKeep, ws.qfT, sizeof(int32_t) * (size_t)W * Q, cudaMemcpyDeviceToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(qeKeep, ws.qeT, sizeof(int32_t) * (size_t)W * Q, cudaMemcpyDeviceToDevice, ctx->stream));
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    poolChunks = (int)((recCap + kRecChunk - 1) >> kRecChunkLog) + producers;
+    if (int rc = tmp.get(&pool, (size_t)poolChunks << kRecChunkLog)) return rc;
+    if (int rc = tmp.get(&chunkTab, (size_t)producers * poolChunks)) return rc;
+    if (int rc = tmp.get(&nm, (size_t)nmCap)) return rc;
+    if (int rc = tmp.get(&ws.gb.nmKeys, (size_t)nmCap)) return rc;
+    CUDA_TRY(ctx, cudaMemsetAsync(chunkCounter, 0, sizeof(int), ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ws.gb.segCnt, 0, sizeof(int32_t) * (size_t)nSeg, ctx->stream));
+    if (attempt) {
+      CUDA_TRY(ctx, cudaMemcpyAsync(ws.qfT, qfKeep, sizeof(int32_t) * (size_t)W * Q, cudaMemcpyDeviceToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(ws.qeT, qeKeep, sizeof(int32_t) * (size_t)W * Q, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    SweepArgs a{};
+    a.src = ws.src; a.wpc = ws.wpc; a.M = M; a.N = N;
+    a.sitesPerWindow = ws.spw; a.nWindows = W;
+    a.siteOffset = ws.siteOffset; a.nTotal = ws.nTotal;
+    a.aStart = ws.ord[ws.cur];
+    a.dStart = ws.haveDStart ? ws.dv[ws.cur] : nullptr;
+    a.recPool = pool; a.poolChunks = poolChunks; a.chunkCounter = chunkCounter; a.chunkTab = chunkTab;
+    a.nomatch = nm; a.nomatchCap = nmCap; a.qCounts = counts;
+    ws.query_args(a, 2, ws.qfT, ws.qeT);
+    {
+      ScopedTimer t(ctx, PBWTGPU_K_QUERY);
+      CUDA_TRY(ctx, ws.launch_query(a));
+      ctx->launches[PBWTGPU_K_QUERY] += 1;
+    }
+    int used = 0;
+    long long segTotal = 0;
+    {
+      ScopedTimer t(ctx, PBWTGPU_K_AUX);
+      CUDA_TRY(ctx, launch_segment_scan(ws.gb.segCnt, nSeg, segDst, scanTemp, scanTempBytes, ctx->stream));
+      ctx->launches[PBWTGPU_K_AUX] += 1;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(&segTotal, segDst + nSeg - 1, sizeof segTotal, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(got, counts, sizeof got, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(&used, chunkCounter, sizeof used, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    got[0] = (unsigned long long)segTotal;
+    if (used <= poolChunks && (long long)got[1] <= nmCap) break;
+    if (attempt == 1) return fail(ctx, PBWTGPU_ERR_CUDA, "query sweep buffer overflow persisted");
+    recCap = std::max<long long>(recCap, (long long)got[0]);
+    nmCap = std::max<long long>(nmCap, (long long)got[1]);
+  }
+  pbwtgpu_match *rec = nullptr;
+  pbwtgpu_nomatch *nmSorted = nm;
+  if (int rc = tmp.get(&rec, (size_t)std::max<unsigned long long>(got[0], 1))) return rc;
+  {
+    ScopedTimer t(ctx, PBWTGPU_K_AUX);
+    CUDA_TRY(ctx, launch_gather_segments(pool, chunkTab, poolChunks, ws.gb.segSrc, segDst, nSeg - 1, (long long)got[0], G, ws.spw, N, W,
+                                         rec, ctx->stream));
+    ctx->launches[PBWTGPU_K_AUX] += 1;
+  }
+  if (got[1]) {  // events were appended in arrival order: put them in (site, query-PBWT position) order
+    if (int rc = tmp.get(&nmSorted, (size_t)got[1])) return rc;
+    CUDA_TRY(ctx, sort_nomatch(ws.gb.nmKeys, nm, (long long)got[1], nmSorted, ctx->stream));
+  }
+  *recDev = rec; *nrec = got[0]; *nmDev = nmSorted; *nnm = got[1];
+  return 0;
+}
 
 int run_sweep(pbwtgpu_ctx *ctx, const uint32_t *src, int wpc, int M, int N, SweepMode mode, const int32_t *aStartHost,
               unsigned flags, pbwtgpu_result *res) {
@@ -1188,52 +1347,69 @@ int pbwtgpu_long_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M,
   return rc;
 }
 
+// records / events of a query sweep: device -> library-owned host buffers
+static int query_results_to_host(pbwtgpu_ctx *ctx, const pbwtgpu_match *recDev, unsigned long long nrec, const pbwtgpu_nomatch *nmDev,
+                                 unsigned long long nnm, pbwtgpu_match **matches, int64_t *nmatch, pbwtgpu_nomatch **nomatch,
+                                 int64_t *nnomatch) {
+  HostGuard gm(host_alloc_pinned(sizeof(pbwtgpu_match) * (size_t)std::max<unsigned long long>(nrec, 1)));
+  HostGuard gn(host_alloc_pinned(sizeof(pbwtgpu_nomatch) * (size_t)std::max<unsigned long long>(nnm, 1)));
+  if (!gm.p || !gn.p) return fail(ctx, PBWTGPU_ERR_NOMEM, "pinned host allocation failed (records)");
+  if (nrec) CUDA_TRY(ctx, cudaMemcpyAsync(gm.p, recDev, sizeof(pbwtgpu_match) * nrec, cudaMemcpyDeviceToHost, ctx->stream));
+  if (nnm) CUDA_TRY(ctx, cudaMemcpyAsync(gn.p, nmDev, sizeof(pbwtgpu_nomatch) * nnm, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  *matches = (pbwtgpu_match *)gm.release();
+  *nmatch = (int64_t)nrec;
+  if (nomatch) *nomatch = (pbwtgpu_nomatch *)gn.release();
+  if (nnomatch) *nnomatch = (int64_t)nnm;
+  return 0;
+}
+
 int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int M, int N, const int32_t *pa_start,
                         const uint8_t *qyz, int64_t nqyz, int Q, const int32_t *qa_start, pbwtgpu_match **matches,
                         int64_t *nmatch, pbwtgpu_nomatch **nomatch, int64_t *nnomatch) {
   if (!ctx || !matches || !nmatch || M < 1 || Q < 1 || N < 0) return fail(ctx, PBWTGPU_ERR_ARG, "match_sweep: bad args");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  // narrow panels: state in shared memory; wide panels: state in global memory, a group of cooperating CTAs
-  // (more queries than the shared-memory kernel holds also go to the wide kernel, which spreads them over its CTAs)
+  // narrow panels: state in shared memory, one CTA, site after site.  Wide panels (and query sets beyond what that kernel
+  // holds): state in global memory, groups of cooperating CTAs, and the SITES cut into windows that run concurrently
+  // (query_chain.cu supplies the exact query state entering every window).
   const bool wide = M > query_sweep_max_m() || ctx->optForceGlobal || Q > query_sweep_max_q(M);
   const int maxQ = wide ? query_sweep_global_max_q() : query_sweep_max_q(M);
   if (Q > maxQ) return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "match_sweep: Q=%d exceeds %d queries per call", Q, maxQ);
   Temps tmp(ctx);
-  int G = 1, chunk = 0, Wd = 1;
-  GlobalBuffers gb;
-  long long nSeg = 0;
-  long long *segDst = nullptr;
-  char *scanTemp = nullptr;
-  size_t scanTempBytes = 0;
-  if (wide) {
-    sweep_global_plan(M, ctx->smCount, 1, kSorted, true, false, true, Q, !ctx->optNoCluster, &G, &chunk, &Wd, &gb.cluster);
-    const size_t MS = (size_t)G * chunk;
-    gb.G = G; gb.chunk = chunk;
-    nSeg = (long long)(N + 1) * G + 1;
-    if (nSeg > INT_MAX) return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "match_sweep: N=%d too large (%lld record segments)", N, nSeg);
-    char *sy = nullptr;
-    if (int rc = tmp.get(&gb.aBuf, 2 * MS)) return rc;
-    if (int rc = tmp.get(&gb.dBuf, 2 * (MS + 4))) return rc;
-    if (int rc = tmp.get(&gb.partials, (size_t)G * 4)) return rc;
-    if (int rc = tmp.get(&sy, sweep_global_sync_bytes(1))) return rc;
-    gb.gsync = sy;
-    if (int rc = tmp.get(&gb.ySorted, sweep_global_column_words(G, chunk, 1))) return rc;
-    if (int rc = tmp.get(&gb.wmaxG, sweep_global_column_words(G, chunk, 1))) return rc;
-    if (int rc = tmp.get(&gb.zpre, sweep_global_column_words(G, chunk, 1))) return rc;
-    if (int rc = tmp.get(&gb.any1, sweep_global_column_words(G, chunk, 1) / 32)) return rc;
-    if (int rc = tmp.get(&gb.any0, sweep_global_column_words(G, chunk, 1) / 32)) return rc;
-    if (int rc = tmp.get(&gb.wmax2, sweep_global_column_words(G, chunk, 1) / 32)) return rc;
-    if (int rc = tmp.get(&gb.segCnt, (size_t)nSeg)) return rc;
-    if (int rc = tmp.get(&gb.segSrc, (size_t)nSeg)) return rc;
-    if (int rc = tmp.get(&gb.qf, (size_t)Q)) return rc;
-    if (int rc = tmp.get(&gb.qe, (size_t)Q)) return rc;
-    if (int rc = tmp.get(&segDst, (size_t)nSeg)) return rc;
-    scanTempBytes = segment_scan_temp_bytes(nSeg);
-    if (int rc = tmp.get(&scanTemp, scanTempBytes)) return rc;
-  }
   uint32_t *pcols = nullptr, *qcols = nullptr;
   if (int rc = decode_stream(ctx, tmp, pyz, npyz, M, N, &pcols, nullptr)) return rc;
   if (int rc = decode_stream(ctx, tmp, qyz, nqyz, Q, N, &qcols, nullptr)) return rc;
+
+  if (wide) {
+    WindowedSweep wp(ctx), wq(ctx);
+    wp.queryQ = Q; wp.qcols = qcols; wp.qwpc = pbwtgpu_words_per_col(Q);
+    if (int rc = wp.init(pcols, pbwtgpu_words_per_col(M), M, N, kSorted, pa_start, false, false, 0, 0)) return rc;
+    // the query PBWT's own order entering every window (pbwtMatch.c:377-378: queries are visited in that order): an
+    // a-only window-parallel sweep of the Q-wide query stream over the same window boundaries
+    int32_t *qaWin = nullptr;
+    if (wp.W > 1 && Q >= 2) {
+      wq.forceSpw = wp.spw;
+      wq.allowForceGlobal = false;
+      if (int rc = wq.init(qcols, pbwtgpu_words_per_col(Q), Q, N, kSorted, qa_start, false, false, 0, 0)) return rc;
+      if (wq.W != wp.W) return fail(ctx, PBWTGPU_ERR_CUDA, "match_sweep: query windows %d != panel windows %d", wq.W, wp.W);
+      if (int rc = wq.prepare()) return rc;
+      qaWin = wq.ord[wq.cur];
+    } else if (wp.W > 1) {  // a single query is always at position 0
+      if (int rc = tmp.get(&qaWin, (size_t)wp.W)) return rc;
+      CUDA_TRY(ctx, cudaMemsetAsync(qaWin, 0, sizeof(int32_t) * wp.W, ctx->stream));
+    } else if (qa_start) {
+      if (int rc = tmp.get(&qaWin, (size_t)Q)) return rc;
+      CUDA_TRY(ctx, cudaMemcpyAsync(qaWin, qa_start, sizeof(int32_t) * Q, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    wp.qaWin = qaWin;
+    if (int rc = wp.prepare()) return rc;
+    pbwtgpu_match *recDev = nullptr;
+    pbwtgpu_nomatch *nmDev = nullptr;
+    unsigned long long nrec = 0, nnm = 0;
+    if (int rc = finish_query_sweep(wp, &recDev, &nrec, &nmDev, &nnm)) return rc;
+    return query_results_to_host(ctx, recDev, nrec, nmDev, nnm, matches, nmatch, nomatch, nnomatch);
+  }
+
   int32_t *pa = nullptr, *qa = nullptr;
   if (pa_start) {
     if (int rc = tmp.get(&pa, (size_t)M)) return rc;
@@ -1253,14 +1429,11 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
   pbwtgpu_nomatch *nm = nullptr;
   unsigned long long got[2] = {0, 0};
   int poolChunks = 0;
-  const int producers = wide ? G : 1;
   for (int attempt = 0; attempt < 2; ++attempt) {
-    poolChunks = (int)((recCap + kRecChunk - 1) >> kRecChunkLog) + producers;
+    poolChunks = (int)((recCap + kRecChunk - 1) >> kRecChunkLog) + 1;
     if (int rc = tmp.get(&pool, (size_t)poolChunks << kRecChunkLog)) return rc;
-    if (int rc = tmp.get(&chunkTab, (size_t)producers * poolChunks)) return rc;
+    if (int rc = tmp.get(&chunkTab, (size_t)poolChunks)) return rc;
     if (int rc = tmp.get(&nm, (size_t)nmCap)) return rc;
-    if (wide)
-      if (int rc = tmp.get(&gb.nmKeys, (size_t)nmCap)) return rc;
     CUDA_TRY(ctx, cudaMemsetAsync(chunkCounter, 0, sizeof(int), ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), ctx->stream));
     SweepArgs a{};
@@ -1272,48 +1445,21 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
     a.nomatch = nm; a.nomatchCap = nmCap; a.qCounts = counts;
     {
       ScopedTimer t(ctx, PBWTGPU_K_QUERY);
-      if (wide) {
-        CUDA_TRY(ctx, cudaMemsetAsync(gb.partials, 0, sizeof(uint32_t) * (size_t)G * 4, ctx->stream));
-        CUDA_TRY(ctx, cudaMemsetAsync(gb.gsync, 0, sweep_global_sync_bytes(1), ctx->stream));
-        CUDA_TRY(ctx, cudaMemsetAsync(gb.segCnt, 0, sizeof(int32_t) * (size_t)nSeg, ctx->stream));
-        CUDA_TRY(ctx, launch_query_sweep_global(a, gb, ctx->stream));
-      } else {
-        CUDA_TRY(ctx, launch_query_sweep_smem(a, ctx->stream));
-      }
+      CUDA_TRY(ctx, launch_query_sweep_smem(a, ctx->stream));
       ctx->launches[PBWTGPU_K_QUERY] += 1;
     }
     int used = 0;
-    long long segTotal = 0;
-    if (wide) {
-      ScopedTimer t(ctx, PBWTGPU_K_AUX);
-      CUDA_TRY(ctx, launch_segment_scan(gb.segCnt, nSeg, segDst, scanTemp, scanTempBytes, ctx->stream));
-      ctx->launches[PBWTGPU_K_AUX] += 1;
-      CUDA_TRY(ctx, cudaMemcpyAsync(&segTotal, segDst + nSeg - 1, sizeof segTotal, cudaMemcpyDeviceToHost, ctx->stream));
-    }
     CUDA_TRY(ctx, cudaMemcpyAsync(got, counts, sizeof got, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(&used, chunkCounter, sizeof used, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (wide) got[0] = (unsigned long long)segTotal;
     if (used <= poolChunks && (long long)got[1] <= nmCap) break;
     if (attempt == 1) return fail(ctx, PBWTGPU_ERR_CUDA, "query sweep buffer overflow persisted");
     recCap = std::max<long long>(recCap, (long long)got[0]);
     nmCap = std::max<long long>(nmCap, (long long)got[1]);
   }
   pbwtgpu_match *recDev = nullptr;
-  pbwtgpu_nomatch *nmSorted = nm;
   if (int rc = tmp.get(&recDev, (size_t)std::max<unsigned long long>(got[0], 1))) return rc;
-  if (wide) {
-    {
-      ScopedTimer t(ctx, PBWTGPU_K_AUX);
-      CUDA_TRY(ctx, launch_gather_segments(pool, chunkTab, poolChunks, gb.segSrc, segDst, nSeg - 1, (long long)got[0], G,
-                                           std::max(N, 1), N, 1, recDev, ctx->stream));
-      ctx->launches[PBWTGPU_K_AUX] += 1;
-    }
-    if (got[1]) {  // events were appended in arrival order: put them in (site, query-PBWT position) order
-      if (int rc = tmp.get(&nmSorted, (size_t)got[1])) return rc;
-      CUDA_TRY(ctx, sort_nomatch(gb.nmKeys, nm, (long long)got[1], nmSorted, ctx->stream));
-    }
-  } else {
+  {
     long long *offsDev = nullptr;
     if (int rc = tmp.get(&offsDev, 1)) return rc;
     CUDA_TRY(ctx, cudaMemsetAsync(offsDev, 0, sizeof(long long), ctx->stream));
@@ -1322,17 +1468,7 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
     CUDA_TRY(ctx, launch_gather_records(pool, chunkTab, poolChunks, offsDev, counts, 1, maxChunks, recDev, ctx->stream));
     ctx->launches[PBWTGPU_K_AUX] += maxChunks > 0;
   }
-  HostGuard gm(host_alloc_pinned(sizeof(pbwtgpu_match) * (size_t)std::max<unsigned long long>(got[0], 1)));
-  HostGuard gn(host_alloc_pinned(sizeof(pbwtgpu_nomatch) * (size_t)std::max<unsigned long long>(got[1], 1)));
-  if (!gm.p || !gn.p) return fail(ctx, PBWTGPU_ERR_NOMEM, "pinned host allocation failed (records)");
-  if (got[0]) CUDA_TRY(ctx, cudaMemcpyAsync(gm.p, recDev, sizeof(pbwtgpu_match) * got[0], cudaMemcpyDeviceToHost, ctx->stream));
-  if (got[1]) CUDA_TRY(ctx, cudaMemcpyAsync(gn.p, nmSorted, sizeof(pbwtgpu_nomatch) * got[1], cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  *matches = (pbwtgpu_match *)gm.release();
-  *nmatch = (int64_t)got[0];
-  if (nomatch) *nomatch = (pbwtgpu_nomatch *)gn.release();
-  if (nnomatch) *nnomatch = (int64_t)got[1];
-  return 0;
+  return query_results_to_host(ctx, recDev, got[0], nm, got[1], matches, nmatch, nomatch, nnomatch);
 }
 
 int pbwtgpu_pack3(pbwtgpu_ctx *ctx, const uint8_t *y, int M, int N, uint8_t **yz, int64_t *nyz) {

@@ -73,6 +73,13 @@ struct SweepArgs {
   pbwtgpu_nomatch *nomatch;      // "no match" events, in emission order
   long long nomatchCap;
   unsigned long long *qCounts;   // [0] records, [1] "no match" events
+  // window-parallel query sweep (wide-panel kernel): W windows at once, query state [W][Q] in GlobalBuffers::qf / qe
+  //   queryMode 0: one window from the fresh state (f = 0, e = first label)
+  //   queryMode 1: CLAMPED pass: every window from the fresh state, divergence tiers below the window's first site
+  //                count as that site, nothing is emitted; what is left in qf / qe is the window's end state
+  //   queryMode 2: final pass: window w starts from the state already in qf / qe [w][.]; records and events are emitted
+  int queryMode;
+  int qaPerWindow;               // qaStart is [W][Q]: the query PBWT order entering every window
 };
 
 

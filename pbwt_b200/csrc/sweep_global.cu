@@ -370,13 +370,19 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
   // this CTA's share of the queries: positions [qLo, qHi) of the query PBWT order
   const int qPer = QUERY ? (p.Q + G - 1) / G : 0;
   const int qLo = min(p.Q, g * qPer), qHi = min(p.Q, qLo + qPer);
+  int32_t *const qfW = QUERY ? ga.qf + (size_t)win * p.Q : nullptr;  // this window's query state, by query id
+  int32_t *const qeW = QUERY ? ga.qe + (size_t)win * p.Q : nullptr;
+  // queryMode 1: divergence tiers that lie before the window count as its first site (the window knows nothing earlier)
+  const int qClamp = (QUERY && p.queryMode == 1) ? k0 : 0;
   if (QUERY) {
-    for (int i = tid; i < QW * 32; i += kThreads) qaS[i] = i < p.Q ? (p.qaStart ? p.qaStart[i] : i) : 0;
-    for (int i = qLo + tid; i < qHi; i += kThreads) {  // pbwtMatch.c:368-369: f and d start at zero
-      const int jj = p.qaStart ? p.qaStart[i] : i;
-      ga.qf[jj] = 0;
-      ga.qe[jj] = 0;
-    }
+    const int32_t *qa0 = p.qaStart ? p.qaStart + (p.qaPerWindow ? (size_t)win * p.Q : 0) : nullptr;
+    for (int i = tid; i < QW * 32; i += kThreads) qaS[i] = i < p.Q ? (qa0 ? qa0[i] : i) : 0;
+    if (p.queryMode != 2)
+      for (int i = qLo + tid; i < qHi; i += kThreads) {  // pbwtMatch.c:368-369: f and d start at zero (the window's first label)
+        const int jj = qa0 ? qa0[i] : i;
+        qfW[jj] = 0;
+        qeW[jj] = k0;
+      }
   }
 
   // records of state k (label kLabel, segment row) for the query share of this CTA: report lists, in rounds
@@ -739,7 +745,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
           const int t = r0 + r;
           const int jj = qaC[t];
           const uint32_t x = (qwS[t >> 5] >> (t & 31)) & 1u;
-          int f = __ldcg(ga.qf + jj), e = __ldcg(ga.qe + jj);
+          int f = __ldcg(qfW + jj), e = __ldcg(qeW + jj);
           int repLo = 0, repHi = 0, repStart = 0;
           bool nm = false;
           if (ybit(st, f) != x) {
@@ -759,8 +765,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
                 nm = true;
                 e = k + 1;
               } else {
-                const int tUp = u >= 0 ? range_max_d(st, u + 1, f, lane) : 0x7fffffff;
-                const int tDown = v < M ? range_max_d(st, hi, v, lane) : 0x7fffffff;
+                const int tUp = u >= 0 ? max(range_max_d(st, u + 1, f, lane), qClamp) : 0x7fffffff;
+                const int tDown = v < M ? max(range_max_d(st, hi, v, lane), qClamp) : 0x7fffffff;
                 if (tUp <= tDown) {
                   const int q = block_start(st, u, tUp, lane);
                   f = first_allele_in(st, q, u + 1, x, lane);
@@ -778,14 +784,14 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
           int nf = x ? c + f - Z : Z;
           if (nf == M) nf = 0;
           if (lane == 0) {
-            ga.qf[jj] = nf;
-            ga.qe[jj] = e;
+            qfW[jj] = nf;
+            qeW[jj] = e;
             resS[r] = make_int4(repLo, repHi, repStart, jj);
             nmS[r] = nm ? (int)(2u | x) : 0;
           }
         }
         __syncthreads();
-        query_emit(st, nR, k);
+        if (p.queryMode != 1) query_emit(st, nR, k);
         if (p.nomatch && tid < nR && nmS[tid]) {  // rare: global append, sorted by (site, position) afterwards
           const unsigned long long o = atomicAdd(&p.qCounts[1], 1ull);
           if ((long long)o < p.nomatchCap) {
@@ -795,7 +801,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
         }
         __syncthreads();  // resS / nmS are reused by the next round
       }
-      if (tid == 0) {
+      if (tid == 0 && ga.segCnt) {
         const size_t seg = (size_t)(k + colShift) * G + g;
         ga.segCnt[seg] = (int32_t)(recBase - before);
         ga.segSrc[seg] = before;
@@ -841,7 +847,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
   // ---- state k1 ----
   const int32_t *aE = aW + (size_t)cur * MS;
   const int32_t *dE = WITH_D ? dW + (size_t)cur * (MS + 4) : nullptr;
-  const bool finalScan = !p.perWindowSites && k1 == nTotal && ((MATCH != 0 && p.reportAtN && (MATCH == 1 || k1 > k0)) || QUERY);
+  const bool finalScan = !p.perWindowSites && k1 == nTotal && ((MATCH != 0 && p.reportAtN && (MATCH == 1 || k1 > k0)) || (QUERY && p.queryMode != 1));
   if (SCAN && finalScan) {  // word maxima of the final d, published to the group
     const int parE = (k1 - k0) & 1;
     for (int w = warp; w < chunkWords; w += 32) {
@@ -890,7 +896,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
         const int nR = min(kResMax, qHi - r0);
         for (int r = warp; r < nR; r += 32) {
           const int jj = qaC[r0 + r];
-          const int f = __ldcg(ga.qf + jj), e = __ldcg(ga.qe + jj);
+          const int f = __ldcg(qfW + jj), e = __ldcg(qeW + jj);
           const int hi = block_end(st, f + 1, e, M, lane);
           if (lane == 0) resS[r] = make_int4(f, hi, e, jj);
         }
@@ -899,7 +905,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
         __syncthreads();
       }
     }
-    if (tid == 0) {
+    if (tid == 0 && ga.segCnt) {
       const size_t seg = (size_t)p.N * G + g;
       ga.segCnt[seg] = (int32_t)(recBase - before);
       ga.segSrc[seg] = before;
@@ -1076,8 +1082,8 @@ int launch_query_sweep_global(const SweepArgs &a, const GlobalBuffers &b, cudaSt
   if (b.cluster && b.G > 16) return (int)cudaErrorInvalidValue;
   void *kern = b.cluster ? pick_kernel<true>(kSorted, true, false, true) : pick_kernel<false>(kSorted, true, false, true);
   SweepArgs args = a;
-  args.nWindows = 1;
-  return launch_any(kern, b.cluster, args, b, b.G, smem_bytes(b.chunk, true, false, true, a.Q, 0), stream);
+  if (args.nWindows < 1) args.nWindows = 1;
+  return launch_any(kern, b.cluster, args, b, args.nWindows * b.G, smem_bytes(b.chunk, true, false, true, a.Q, 0), stream);
 }
 
 size_t sweep_global_sync_bytes(int W) { return sizeof(GroupSync) * (size_t)W; }

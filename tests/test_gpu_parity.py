@@ -423,6 +423,69 @@ def test_query_sweep_wide_kernel_forced(eng, orc, M, Q, N, dp, dq, no_cluster):
     assert len(nom) == len(want_nom) and (nom == want_nom).all()
 
 
+@pytest.mark.parametrize("M,Q,N,W,dp,dq,no_cluster,starts", [
+    (60, 7, 80, 5, 0.03, 0.3, 0, False), (60, 7, 80, 80, 0.03, 0.3, 0, True), (1000, 300, 120, 7, 0.1, 0.1, 0, True),
+    (1000, 300, 121, 7, 0.1, 0.1, 1, False), (3000, 1000, 60, 4, 0.05, 0.05, 0, False), (300, 8192, 40, 3, 0.4, 0.4, 0, False),
+    (2000, 700, 90, 9, 0.004, 0.01, 0, True), (200, 1, 50, 6, 0.2, 0.2, 0, False), (5, 9, 30, 4, 0.5, 0.5, 0, True),
+    (2500, 64, 300, 37, 0.02, 0.02, 0, False)])
+def test_query_sweep_window_parallel(eng, orc, M, Q, N, W, dp, dq, no_cluster, starts):
+    """The window-parallel query sweep forced onto small panels: clamped pass 1 + chain + pass 2 (query_chain.cu) must
+    reproduce matchSequencesSweep record for record, 'no match' events included, also from non-identity start orders."""
+    rng = np.random.default_rng(M + Q + W)
+    hp = (rng.random((M, N)) < dp).astype(np.uint8)
+    hq = (rng.random((Q, N)) < dq).astype(np.uint8)
+    hq[0] = hp[M // 2]
+    for k in rng.choice(N, size=max(1, N // 20), replace=False):  # monomorphic panel columns: 'no match' events
+        hp[:, k] = rng.integers(0, 2)
+    pa = rng.permutation(M).astype(np.int32) if starts else None
+    qa = rng.permutation(Q).astype(np.int32) if starts else None
+    pyz = orc.build(O.pack_panel(hp), M, N, a_start=pa, with_d=False)[0]
+    qyz = orc.build(O.pack_panel(hq), Q, N, a_start=qa, with_d=False)[0]
+    want_rec, want_nom = orc.match_sweep(pyz, M, N, qyz, Q, pa_start=pa, qa_start=qa)
+    eng.set_option("force_global", 1)
+    eng.set_option("no_cluster", no_cluster)
+    eng.set_option("windows", W)
+    try:
+        rec, nom = eng.match_sweep(pyz, M, N, qyz, Q, pa_start=pa, qa_start=qa)
+    finally:
+        eng.set_option("force_global", 0)
+        eng.set_option("no_cluster", 0)
+        eng.set_option("windows", 0)
+    assert len(rec) == len(want_rec) and (rec == want_rec).all()
+    assert len(nom) == len(want_nom) and (nom == want_nom).all()
+
+
+def test_query_sweep_window_parallel_mosaic_small_pool(eng, orc):
+    """Mosaic panel with matches that span many windows; the record pool overflows on the first attempt (rerun of pass 2
+    from the kept chain states)."""
+    M, Q, N = 4000, 500, 1500
+    x = O.generate_panel(M + Q, N, seed=0x5EED0005, L=300, mu=3.0)
+    hap = O.unpack_panel(x, M + Q)
+    pyz, qyz = _split_streams(orc, hap[:M], hap[M:])
+    want_rec, want_nom = orc.match_sweep(pyz, M, N, qyz, Q)
+    eng.set_option("force_global", 1)
+    eng.set_option("windows", 23)
+    eng.set_option("match_capacity", 1000)
+    try:
+        rec, nom = eng.match_sweep(pyz, M, N, qyz, Q)
+    finally:
+        eng.set_option("force_global", 0)
+        eng.set_option("windows", 0)
+        eng.set_option("match_capacity", 0)
+    assert len(rec) == len(want_rec) and (rec == want_rec).all() and (nom == want_nom).all()
+
+
+def test_query_sweep_wide_panel_default_windows(eng, orc):
+    """A panel wider than shared memory and long enough for the default window plan (no options)."""
+    M, Q, N = 40000, 300, 3000
+    x = O.generate_panel(M + Q, N, seed=0x5EED0025, L=400, mu=6.0)
+    hap = O.unpack_panel(x, M + Q)
+    pyz, qyz = _split_streams(orc, hap[:M], hap[M:])
+    want_rec, want_nom = orc.match_sweep(pyz, M, N, qyz, Q)
+    rec, nom = eng.match_sweep(pyz, M, N, qyz, Q)
+    assert len(rec) == len(want_rec) and (rec == want_rec).all() and (nom == want_nom).all()
+
+
 def test_query_sweep_many_queries_narrow_panel(eng, orc):
     """More queries than the shared-memory kernel holds: routed to the wide kernel without forcing."""
     M, Q, N = 900, 3000, 70
