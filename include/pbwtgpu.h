@@ -67,7 +67,8 @@ int pbwtgpu_synchronize(pbwtgpu_ctx *ctx);
 /* Options (0 = automatic / off).  Tuning: "windows" (site windows swept concurrently), "match_capacity" (records the
  * first attempt allows for), "long_within" (L of PBWTGPU_WANT_LONGWITHIN).  Testing and profiling aids: "force_global"
  * (wide-panel kernels on narrow panels), "no_cluster" (cooperative-grid groups where clusters would fit),
- * "no_sort_pass1" (window nodes by sweeping instead of sorting), "equal_windows" (no shortening of the panel's edge
+ * "no_sort_pass1" (window nodes by sweeping instead of sorting), "no_sort_combine" (window combines by sweeping
+ * pseudo-sites instead of the radix sort + range maxima), "equal_windows" (no shortening of the panel's edge
  * windows), "window_times", "debug_no_candidates". */
 int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value);
 /* Per-kernel-class device times of the last sweep (ms, CUDA events on the launching stream) and

@@ -33,6 +33,7 @@ struct pbwtgpu_ctx {
   long long optEqualWindows = 0; // testing / profiling: equal windows even where the edge windows would be shortened
   long long optNoSortPass1 = 0;  // testing: pass 1 by sweeping even where the window sort applies
   long long optNoCluster = 0;    // testing: wide panels through the cooperative-grid path even where clusters fit
+  long long optNoSortCombine = 0;  // testing: window combines by sweeping pseudo-sites even where the sort applies
   // profiling
   bool profile = false;
   float ms[PBWTGPU_NUM_KERNEL_CLASSES] = {0};
@@ -434,8 +435,20 @@ struct WindowedSweep {
       ctx->launches[PBWTGPU_K_AUX] += 2;
       return 0;
     }
+    if (sort_combine()) {
+      CombineSortArgs c{};
+      c.M = M; c.cnt = cnt; c.sharedI = sharedI;
+      c.ordI = ordI; c.dvI = dvI; c.gJ = gJ; c.gfdJ = gfdJ;
+      c.ordOut = ordOut; c.dvOut = dvOut; c.gOut = gOut; c.gfdOut = gfdOut;
+      ScopedTimer t(ctx, PBWTGPU_K_COMBINE);
+      CUDA_TRY(ctx, launch_combine_sort(c, ctx->stream));
+      ctx->launches[PBWTGPU_K_COMBINE] += 1;
+      return 0;
+    }
     return combine_ids(cnt, ordI, sharedI, dvI, sharedI, gJ, gfdJ, ordOut, dvOut, gOut, gfdOut);
   }
+  // the combine as a radix sort + range maxima (combine_sort.cu): haplotype space, panels of the shared-memory kernels
+  bool sort_combine() const { return !positionSpace && !useGlobal && M <= combine_sort_max_m() && !ctx->optNoSortCombine; }
 
   int combine_ids(int cnt, const int32_t *ordI, bool ordShared, const int32_t *dvI, bool dvShared, const int32_t *gJ,
                   const int32_t *gfdJ, int32_t *ordOut, int32_t *dvOut, int32_t *gOut, int32_t *gfdOut) {
@@ -548,6 +561,20 @@ struct WindowedSweep {
     for (int stride = 1; stride < nodes; stride *= 2) {
       const int nxt = cur ^ 1, cnt = nodes - stride;
       const size_t s1 = (size_t)(1 + stride);  // first slot that changes this round
+      if (sort_combine()) {  // one launch per round: the combines, and the nodes below the stride (already final) copied through
+        CombineSortArgs c{};
+        c.M = M; c.cnt = cnt; c.sharedI = 0;
+        c.ordI = ord[cur] + oA(); c.dvI = dv[cur] + oD(); c.gJ = g[cur] + s1 * oA(); c.gfdJ = gfd[cur] + s1 * oA();
+        c.ordOut = ord[nxt] + s1 * oA(); c.dvOut = dv[nxt] + s1 * oD(); c.gOut = g[nxt] + s1 * oA(); c.gfdOut = gfd[nxt] + s1 * oA();
+        c.ncopy = stride;
+        c.ordCopySrc = ord[cur] + oA(); c.dvCopySrc = dv[cur] + oD(); c.gCopySrc = g[cur] + oA(); c.gfdCopySrc = gfd[cur] + oA();
+        c.ordCopyDst = ord[nxt] + oA(); c.dvCopyDst = dv[nxt] + oD(); c.gCopyDst = g[nxt] + oA(); c.gfdCopyDst = gfd[nxt] + oA();
+        ScopedTimer t(ctx, PBWTGPU_K_COMBINE);
+        CUDA_TRY(ctx, launch_combine_sort(c, ctx->stream));
+        ctx->launches[PBWTGPU_K_COMBINE] += 1;
+        cur = nxt;
+        continue;
+      }
       if (int rc = combine(cnt, ord[cur] + oA(), dv[cur] + oD(), false, g[cur] + s1 * oA(), gfd[cur] + s1 * oA(),
                            ord[nxt] + s1 * oA(), dv[nxt] + s1 * oD(), g[nxt] + s1 * oA(), gfd[nxt] + s1 * oA()))
         return rc;
@@ -1033,6 +1060,7 @@ int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value) {
   else if (!strcmp(name, "window_times")) ctx->optWindowTimes = value;
   else if (!strcmp(name, "force_global")) ctx->optForceGlobal = value;
   else if (!strcmp(name, "no_cluster")) ctx->optNoCluster = value;
+  else if (!strcmp(name, "no_sort_combine")) ctx->optNoSortCombine = value;
   else if (!strcmp(name, "long_within")) ctx->optLongT = value;
   else if (!strcmp(name, "no_sort_pass1")) ctx->optNoSortPass1 = value;
   else if (!strcmp(name, "equal_windows")) ctx->optEqualWindows = value;

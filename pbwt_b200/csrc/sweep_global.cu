@@ -741,7 +741,28 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
       const long long before = recBase;
       for (int r0 = qLo; r0 < qHi; r0 += kResMax) {
         const int nR = min(kResMax, qHi - r0);
+        // fast path, one query per thread: the allele at f extends the match -- nothing to report, e stays, f takes the
+        // FM step (the common case by far: a query leaves its block only where its best match ends)
+        if (tid < nR) {
+          const int t = r0 + tid;
+          const int jj = qaC[t];
+          const uint32_t x = (qwS[t >> 5] >> (t & 31)) & 1u;
+          const int f = __ldcg(qfW + jj);
+          const int fw = f >> 5;
+          const uint32_t yw = st.yw(fw);
+          const bool fast = ((yw >> (f & 31)) & 1u) == x;
+          if (fast) {
+            const int Z = __ldcg(zk + fw) + __popc(~yw & lanemask_lt(f & 31));
+            int nf = x ? c + f - Z : Z;
+            if (nf == M) nf = 0;
+            qfW[jj] = nf;
+          }
+          resS[tid] = make_int4(0, 0, 0, jj);
+          nmS[tid] = fast ? 0 : -1;  // -1: needs the scans below
+        }
+        __syncthreads();
         for (int r = warp; r < nR; r += 32) {
+          if (nmS[r] != -1) continue;  // (uniform)
           const int t = r0 + r;
           const int jj = qaC[t];
           const uint32_t x = (qwS[t >> 5] >> (t & 31)) & 1u;

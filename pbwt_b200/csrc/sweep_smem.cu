@@ -271,10 +271,11 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
           carry = max(carry, __reduce_max_sync(kFull, lmax));
           lmax = 0;
           int v = dv;  // inclusive max since the nearest head at or below this lane
-#ifdef PBWTGPU_SCAN_BY_DISTANCE
-          // Experimental (off by default, not yet measured on a B200): one distance to the nearest head at or below the
-          // lane replaces the per-stage window masks.  "No head in (lane - dl, lane]" is dl <= dist; lanes with
-          // dl > lane get their own value back from the shuffle, so they need no separate guard.
+#ifndef PBWTGPU_SCAN_BY_MASK
+          // One distance to the nearest head at or below the lane replaces per-stage window masks (measured on a B200:
+          // pass 2 of config 2 4.33 -> 4.24 ms, and the 16-byte spill of the E = 10 variant disappears).  "No head in
+          // (lane - dl, lane]" is dl <= dist; lanes with dl > lane get their own value back from the shuffle, so they
+          // need no separate guard.  tests/test_segscan_model.py proves both formulations equal the definition.
           const int dist = lane - (31 - __clz((int)(H & (ltMask | laneBit))));  // lane + 1 when there is none
 #pragma unroll
           for (int dl = 1; dl < 32; dl <<= 1) {

@@ -36,6 +36,20 @@ int launch_gather_segments(const pbwtgpu_match *pool, const int *chunkTab, int p
 int sort_nomatch(const unsigned long long *keys, const pbwtgpu_nomatch *events, long long n, pbwtgpu_nomatch *out,
                  cudaStream_t stream);
 
+// The combine of adjacent nodes as a sort + range-maximum queries (combine_sort.cu) instead of a sweep over pseudo-sites:
+// node n of cnt: I = (ordI, dvI)[n] (one node for all when sharedI), J's tie groups (gJ, gfdJ)[n] -> (ordOut, dvOut, gOut,
+// gfdOut)[n].  ncopy further CTAs copy nodes that are already final from one buffer set to the other.
+struct CombineSortArgs {
+  int M, cnt, sharedI;
+  const int32_t *ordI, *dvI, *gJ, *gfdJ;
+  int32_t *ordOut, *dvOut, *gOut, *gfdOut;
+  int ncopy;
+  const int32_t *ordCopySrc, *dvCopySrc, *gCopySrc, *gfdCopySrc;
+  int32_t *ordCopyDst, *dvCopyDst, *gCopyDst, *gfdCopyDst;
+};
+int combine_sort_max_m();
+int launch_combine_sort(const CombineSortArgs &c, cudaStream_t stream);
+
 // Pass 1 as a sort (window_sort.cu): nodes (order, divergence) of windows [w*spw, (w+1)*spw) of the panel columns,
 // w < nodes, each swept on its own from aStart ([M], NULL = identity).  scratch: window_sort_scratch_words words.
 // ordOut [nodes][M], dvOut [nodes][M+1]; labels are siteOffset + column + 1.

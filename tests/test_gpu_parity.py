@@ -184,7 +184,8 @@ def test_full_size_properties(eng):
 def test_window_parallel_forced(eng, orc, M, N, W, dens, no_sort):
     """Force the window-parallel path (pass 1 + combine scan + pass 2) at small sizes: results must equal the
     sequential reference sweep bit for bit, including match-record order across window boundaries.  Pass 1 runs
-    as the window sort (window_sort.cu) or, with no_sort_pass1, as a sweep."""
+    as the window sort (window_sort.cu) or, with no_sort_pass1, as a sweep; with no_sort the combine scan also runs as
+    sweeps over pseudo-sites (windows.cu) instead of the radix sort + range maxima of combine_sort.cu."""
     rng = np.random.default_rng(M * 7 + N)
     hap = (rng.random((M, N)) < dens).astype(np.uint8)
     hap[: M // 3] = hap[0]  # a block of identical haplotypes: ties that survive every window
@@ -192,20 +193,24 @@ def test_window_parallel_forced(eng, orc, M, N, W, dens, no_sort):
     a0 = rng.permutation(M).astype(np.int32)
     eng.set_option("windows", W)
     eng.set_option("no_sort_pass1", no_sort)
+    eng.set_option("no_sort_combine", no_sort)
     try:
         check_build(eng, orc, x, M, N, matches=M * N < 2000000)
         check_build(eng, orc, x, M, N, a_start=a0, matches=M * N < 2000000)
     finally:
         eng.set_option("windows", 0)
         eng.set_option("no_sort_pass1", 0)
+        eng.set_option("no_sort_combine", 0)
 
 
-def test_window_parallel_mosaic(eng, orc):
-    M, N = 2000, 2000
+@pytest.mark.parametrize("M,N,W", [(2000, 2000, 37), (13312, 1500, 21), (4097, 3000, 148)])
+def test_window_parallel_mosaic(eng, orc, M, N, W):
+    """Mosaic panels: long shared segments, so tie groups survive several windows and the combine's range maxima span
+    whole blocks of positions (sparse-table path of combine_sort.cu)."""
     x = O.generate_panel(M, N, seed=0x5EED0003, L=300, mu=2.0)
-    eng.set_option("windows", 37)
+    eng.set_option("windows", W)
     try:
-        check_build(eng, orc, x, M, N)
+        check_build(eng, orc, x, M, N, matches=M <= 4097)
     finally:
         eng.set_option("windows", 0)
 
