@@ -135,6 +135,32 @@ int pbwtgpu_shard_finish(pbwtgpu_ctx *ctx, pbwtgpu_shard *shard, const int32_t *
                          pbwtgpu_result **result);
 void pbwtgpu_shard_free(pbwtgpu_ctx *ctx, pbwtgpu_shard *shard);
 
+/* ---- multi-GPU matchSequencesSweep (pbwtMatch.c:363-443): the SITES are partitioned across GPUs ---------------------
+ * Every GPU gets the whole stored streams of panel and queries (they are small) and sweeps the columns
+ * [first_site, first_site + nsites) with ALL queries; what crosses GPUs is
+ *   1. one all-gather of the query stream's shard aggregates (pbwtgpu_shard_aggregate_ints(Q) int32 each): gives every
+ *      shard the query PBWT's order entering its windows (the callback order, pbwtMatch.c:377-378);
+ *   2. one all-gather of the panel's shard aggregates (pbwtgpu_shard_aggregate_ints(M) int32 each): the exact (a, d)
+ *      entering every shard, as in pbwtgpu_shard_*;
+ *   3. the queries' state (f, e) -- 2 Q int32 -- handed from each shard to the next, in site order: the one sequential
+ *      step, a few hundred microseconds per shard (pbwt_b200/csrc/query_chain.cu).
+ * Call order on every rank: open, export_queries, [all-gather 1], prepare, [all-gather 2], chain (rank r after it
+ * received rank r-1's state_out; rank 0 passes NULL), [send state_out on], finish.  Records and "no match" events of the
+ * shards concatenate in site order into exactly the reference's callback / log order; the matches still open at N are
+ * reported by the last shard.  All dev_* pointers are device memory on ctx's GPU. */
+typedef struct pbwtgpu_qshard pbwtgpu_qshard;
+int pbwtgpu_qshard_open(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int M, int N, const int32_t *pa_start,
+                        const uint8_t *qyz, int64_t nqyz, int Q, const int32_t *qa_start, int first_site, int nsites,
+                        pbwtgpu_qshard **shard);
+int pbwtgpu_qshard_export_queries(pbwtgpu_ctx *ctx, pbwtgpu_qshard *shard, int32_t *dev_dst);
+int pbwtgpu_qshard_prepare(pbwtgpu_ctx *ctx, pbwtgpu_qshard *shard, const int32_t *dev_query_aggs, int rank,
+                           int32_t *dev_panel_agg);
+int pbwtgpu_qshard_chain(pbwtgpu_ctx *ctx, pbwtgpu_qshard *shard, const int32_t *dev_panel_aggs, int rank,
+                         const int32_t *dev_state_in, int32_t *dev_state_out);
+int pbwtgpu_qshard_finish(pbwtgpu_ctx *ctx, pbwtgpu_qshard *shard, pbwtgpu_match **matches, int64_t *nmatch,
+                          pbwtgpu_nomatch **nomatch, int64_t *nnomatch);
+void pbwtgpu_qshard_free(pbwtgpu_ctx *ctx, pbwtgpu_qshard *shard);
+
 /* ---- host buffers ---------------------------------------------------------------------------------- */
 /* Page-locked host memory from a process-wide, reusing pool: a caller that assembles its bit columns in such a
  * buffer (the host shim's reader batch, pbwtIO.c:558-586 batched) gets the H2D copy at the full PCIe rate instead
@@ -173,7 +199,9 @@ int pbwtgpu_cursor_at(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, i
 int pbwtgpu_build_reverse(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start,
                           int32_t *a_fend, uint8_t **zz, int64_t *nzz, int32_t *a_rend);
 /* matchSequencesSweep(p, q, report) (pbwtMatch.c:363-443): panel and query streams as stored.  At most 8,192 queries per
- * call (PBWTGPU_ERR_UNSUPPORTED beyond); the host shim chunks larger query sets and merges the record streams exactly. */
+ * call (PBWTGPU_ERR_UNSUPPORTED beyond); the host shim chunks larger query sets and merges the record streams exactly.
+ * Wide panels are swept window-parallel: a clamped pass per window, the exact query state at every window boundary
+ * (pbwt_b200/csrc/query_chain.cu), then all windows at once. */
 int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int M, int N, const int32_t *pa_start,
                         const uint8_t *qyz, int64_t nqyz, int Q, const int32_t *qa_start, pbwtgpu_match **matches,
                         int64_t *nmatch, pbwtgpu_nomatch **nomatch, int64_t *nnomatch);

@@ -86,6 +86,13 @@ def load_library() -> C.CDLL:
         lib.pbwtgpu_long_within.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, C.POINTER(_vp), C.POINTER(_i64)]
         lib.pbwtgpu_match_sweep.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _i64, C.c_int, _vp, C.POINTER(_vp),
                                             C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_i64)]
+        lib.pbwtgpu_qshard_open.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _i64, C.c_int, _vp, C.c_int, C.c_int, C.POINTER(_vp)]
+        lib.pbwtgpu_qshard_export_queries.argtypes = [_vp, _vp, _vp]
+        lib.pbwtgpu_qshard_prepare.argtypes = [_vp, _vp, _vp, C.c_int, _vp]
+        lib.pbwtgpu_qshard_chain.argtypes = [_vp, _vp, _vp, C.c_int, _vp, _vp]
+        lib.pbwtgpu_qshard_finish.argtypes = [_vp, _vp, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_i64)]
+        lib.pbwtgpu_qshard_free.argtypes = [_vp, _vp]
+        lib.pbwtgpu_qshard_free.restype = None
         lib.pbwtgpu_pack3.argtypes = [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_i64)]
         lib.pbwtgpu_unpack3.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp]
         lib.pbwtgpu_free.argtypes = [_vp]
@@ -183,6 +190,33 @@ class Shard:
     def free(self):
         if self.handle:
             self.eng.lib.pbwtgpu_shard_free(self.eng.ctx, self.handle)
+            self.handle = None
+
+
+class QueryShard:
+    """One GPU's site range of a multi-GPU matchSequencesSweep (include/pbwtgpu.h, pbwtgpu_qshard_*)."""
+
+    def __init__(self, eng: "Engine", handle: _vp):
+        self.eng, self.handle = eng, handle
+
+    def export_queries(self, dev_ptr: int):
+        self.eng._check(self.eng.lib.pbwtgpu_qshard_export_queries(self.eng.ctx, self.handle, dev_ptr))
+
+    def prepare(self, dev_query_aggs_ptr, rank: int, dev_panel_agg_ptr: int):
+        self.eng._check(self.eng.lib.pbwtgpu_qshard_prepare(self.eng.ctx, self.handle, dev_query_aggs_ptr, rank, dev_panel_agg_ptr))
+
+    def chain(self, dev_panel_aggs_ptr, rank: int, dev_state_in_ptr, dev_state_out_ptr: int):
+        self.eng._check(self.eng.lib.pbwtgpu_qshard_chain(self.eng.ctx, self.handle, dev_panel_aggs_ptr, rank, dev_state_in_ptr,
+                                                          dev_state_out_ptr))
+
+    def finish(self):
+        mt, nm, nom, nn = _vp(), _i64(0), _vp(), _i64(0)
+        self.eng._check(self.eng.lib.pbwtgpu_qshard_finish(self.eng.ctx, self.handle, C.byref(mt), C.byref(nm), C.byref(nom), C.byref(nn)))
+        return _take(self.eng.lib, mt, nm.value * 16, MATCH_DTYPE), _take(self.eng.lib, nom, nn.value * 12, NOMATCH_DTYPE)
+
+    def free(self):
+        if self.handle:
+            self.eng.lib.pbwtgpu_qshard_free(self.eng.ctx, self.handle)
             self.handle = None
 
 
@@ -374,6 +408,16 @@ class Engine:
         self._check(self.lib.pbwtgpu_match_sweep(self.ctx, _ptr(pyz), pyz.size, M, N, _ptr(pa), _ptr(qyz), qyz.size, Q,
                                                  _ptr(qa), C.byref(mt), C.byref(nm), C.byref(nom), C.byref(nn)))
         return _take(self.lib, mt, nm.value * 16, MATCH_DTYPE), _take(self.lib, nom, nn.value * 12, NOMATCH_DTYPE)
+
+    def query_shard(self, pyz, M, N, qyz, Q, first_site: int, nsites: int, pa_start=None, qa_start=None) -> QueryShard:
+        pyz = np.ascontiguousarray(pyz, np.uint8)
+        qyz = np.ascontiguousarray(qyz, np.uint8)
+        pa = None if pa_start is None else np.ascontiguousarray(pa_start, np.int32)
+        qa = None if qa_start is None else np.ascontiguousarray(qa_start, np.int32)
+        h = _vp()
+        self._check(self.lib.pbwtgpu_qshard_open(self.ctx, _ptr(pyz), pyz.size, M, N, _ptr(pa), _ptr(qyz), qyz.size, Q, _ptr(qa),
+                                                 first_site, nsites, C.byref(h)))
+        return QueryShard(self, h)
 
     def pack3(self, y: np.ndarray) -> np.ndarray:
         """y: uint8 [N, M] sorted columns -> concatenated pack3 stream."""

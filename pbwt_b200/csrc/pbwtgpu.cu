@@ -325,7 +325,7 @@ struct WindowedSweep {
 
     W = 1;
     positionSpace = mode == kSorted;
-    if (M >= 2 && !(positionSpace && sharded_)) {
+    if (M >= 2) {
       const long long want = ctx->optWindows > 0 ? ctx->optWindows : ctx->smCount;
       const int minSites = ctx->optWindows > 0 ? 1 : 256;  // below this a window does not repay its two extra passes
       W = (int)std::max<long long>(1, std::min<long long>(want, N / minSites));
@@ -490,11 +490,14 @@ struct WindowedSweep {
   }
 
   // true query state entering every window: fresh at the panel's first site (pbwtMatch.c:368-369), then the chain
-  int query_chain() {
+  // (a shard: stateIn [2][Q] = f then e entering its first site, NULL for the first shard; stateOut [2][Q] leaving its last)
+  int query_chain(const int32_t *stateIn = nullptr, int32_t *stateOut = nullptr) {
     QueryChainArgs c{};
     c.Q = queryQ; c.M = M; c.W = W; c.steps = nodes; c.spw = spw; c.firstLabel = siteOffset;
     c.dv = dv[cur]; c.nodeOrd = qNodeOrd; c.fClamped = qf1; c.eClamped = qe1;
     c.fTrue = qfT; c.eTrue = qeT;
+    if (stateIn) { c.fIn = stateIn; c.eIn = stateIn + queryQ; }
+    if (stateOut) { c.fOut = stateOut; c.eOut = stateOut + queryQ; }
     ScopedTimer t(ctx, PBWTGPU_K_QUERY);
     CUDA_TRY(ctx, launch_query_chain(c, ctx->stream));
     ctx->launches[PBWTGPU_K_QUERY] += 1;
@@ -586,7 +589,9 @@ struct WindowedSweep {
       CUDA_TRY(ctx, cudaMemcpyAsync(gfd[nxt] + oA(), gfd[cur] + oA(), sizeof(int32_t) * oA() * stride, cudaMemcpyDeviceToDevice, ctx->stream));
       cur = nxt;
     }
-    if (positionSpace) {  // positions relative to the sweep's start -> haplotypes: compose with the start order
+    // positions relative to the sweep's start -> haplotypes: compose with the start order (a shard's nodes stay in
+    // position space until apply_prefix: the order entering the shard is not known before)
+    if (positionSpace && !sharded) {
       const int nxt = cur ^ 1;
       ScopedTimer t(ctx, PBWTGPU_K_AUX);
       CUDA_TRY(ctx, launch_compose(ord[nxt] + oA(), ord[cur], true, ord[cur] + oA(), M, nodes, ctx->stream));
@@ -594,7 +599,7 @@ struct WindowedSweep {
       ctx->launches[PBWTGPU_K_AUX] += 1;
     }
     haveDStart = true;
-    if (queryQ) return query_chain();
+    if (queryQ && !sharded) return query_chain();  // (a shard's chain also needs the state handed on by the shard before it)
     return 0;
   }
 
@@ -614,7 +619,16 @@ struct WindowedSweep {
   // aggs: [R][agg_ints] aggregates of all shards in site order.  Combines shards 0..rank-1 into the state
   // entering this shard and applies it to every local node and to slot 0.
   int apply_prefix(const int32_t *aggs, int rank) {
-    if (rank <= 0) return 0;
+    if (rank <= 0) {
+      if (positionSpace && sharded && nodes > 0) {  // the first shard: its nodes are relative to the panel's start order
+        const int nxt = cur ^ 1;
+        ScopedTimer t(ctx, PBWTGPU_K_AUX);
+        CUDA_TRY(ctx, launch_compose(ord[nxt] + oA(), ord[cur], true, ord[cur] + oA(), M, nodes, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ord[cur] + oA(), ord[nxt] + oA(), sizeof(int32_t) * oA() * nodes, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->launches[PBWTGPU_K_AUX] += 1;
+      }
+      return 0;
+    }
     const size_t AI = agg_ints(M);
     int32_t *P[2];
     if (int rc = tmp.get(&P[0], AI)) return rc;
@@ -664,6 +678,13 @@ struct WindowedSweep {
           return rc;
         pc ^= 1;
       }
+    }
+    if (positionSpace) {  // the prefix is a permutation of the panel's start positions: name the haplotypes
+      ScopedTimer t(ctx, PBWTGPU_K_AUX);
+      CUDA_TRY(ctx, launch_compose(P[pc ^ 1], ord[cur], true, P[pc], M, 1, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(P[pc ^ 1] + M, P[pc] + M, sizeof(int32_t) * (M + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+      ctx->launches[PBWTGPU_K_AUX] += 1;
+      pc ^= 1;
     }
     const int nxt = cur ^ 1;
     if (int rc = combine(nodes, P[pc], P[pc] + M, true, g[cur] + oA(), gfd[cur] + oA(), ord[nxt] + oA(), dv[nxt] + oD(),
@@ -1497,6 +1518,100 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
     ctx->launches[PBWTGPU_K_AUX] += maxChunks > 0;
   }
   return query_results_to_host(ctx, recDev, got[0], nm, got[1], matches, nmatch, nomatch, nnomatch);
+}
+
+// ---- matchSequencesSweep with the SITES partitioned across GPUs (include/pbwtgpu.h) -------------------------------
+struct pbwtgpu_qshard {
+  Temps tmp;
+  WindowedSweep wp, wq;  // panel (with the queries riding on its passes) and the Q-wide query stream's own order
+  int M = 0, Q = 0;
+  int32_t *qaZero = nullptr;
+  explicit pbwtgpu_qshard(pbwtgpu_ctx *c) : tmp(c), wp(c), wq(c) {}
+};
+
+int pbwtgpu_qshard_open(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int M, int N, const int32_t *pa_start,
+                        const uint8_t *qyz, int64_t nqyz, int Q, const int32_t *qa_start, int first_site, int nsites,
+                        pbwtgpu_qshard **out) {
+  if (!ctx || !out || M < 1 || Q < 1 || N < 1 || first_site < 0 || nsites < 1 || first_site + nsites > N)
+    return fail(ctx, PBWTGPU_ERR_ARG, "qshard_open: bad args");
+  if (Q > query_sweep_global_max_q()) return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "qshard_open: Q=%d exceeds %d queries per call", Q, query_sweep_global_max_q());
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  pbwtgpu_qshard *qs = new pbwtgpu_qshard(ctx);
+  qs->M = M; qs->Q = Q;
+  auto bail = [&](int rc) { cudaStreamSynchronize(ctx->stream); delete qs; return rc; };
+  // every GPU decodes the whole streams (they are small) and sweeps its own range of columns
+  uint32_t *pcols = nullptr, *qcols = nullptr;
+  if (int rc = decode_stream(ctx, qs->tmp, pyz, npyz, M, N, &pcols, nullptr)) return bail(rc);
+  if (int rc = decode_stream(ctx, qs->tmp, qyz, nqyz, Q, N, &qcols, nullptr)) return bail(rc);
+  const int wpc = pbwtgpu_words_per_col(M), qwpc = pbwtgpu_words_per_col(Q);
+  qs->wp.queryQ = Q; qs->wp.qcols = qcols + (size_t)first_site * qwpc; qs->wp.qwpc = qwpc;
+  if (int rc = qs->wp.init(pcols + (size_t)first_site * wpc, wpc, M, nsites, kSorted, pa_start, false, true, first_site, N)) return bail(rc);
+  if (Q >= 2) {
+    qs->wq.forceSpw = qs->wp.spw;
+    qs->wq.allowForceGlobal = false;
+    if (int rc = qs->wq.init(qcols + (size_t)first_site * qwpc, qwpc, Q, nsites, kSorted, qa_start, false, true, first_site, N)) return bail(rc);
+    if (qs->wq.W != qs->wp.W) return bail(fail(ctx, PBWTGPU_ERR_CUDA, "qshard_open: query windows %d != panel windows %d", qs->wq.W, qs->wp.W));
+    if (int rc = qs->wq.prepare()) return bail(rc);
+  } else {
+    if (int rc = qs->tmp.get(&qs->qaZero, (size_t)qs->wp.W + 1)) return bail(rc);
+    if (cudaMemsetAsync(qs->qaZero, 0, sizeof(int32_t) * (qs->wp.W + 1), ctx->stream) != cudaSuccess) return bail(fail(ctx, PBWTGPU_ERR_CUDA, "qshard_open: memset"));
+  }
+  *out = qs;
+  return 0;
+}
+
+int pbwtgpu_qshard_export_queries(pbwtgpu_ctx *ctx, pbwtgpu_qshard *qs, int32_t *dev_dst) {
+  if (!ctx || !qs || !dev_dst) return fail(ctx, PBWTGPU_ERR_ARG, "qshard_export_queries: bad args");
+  if (qs->Q >= 2) {
+    if (int rc = qs->wq.export_aggregate(dev_dst)) return rc;
+  } else {
+    CUDA_TRY(ctx, cudaMemsetAsync(dev_dst, 0, sizeof(int32_t) * WindowedSweep::agg_ints(qs->Q), ctx->stream));
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int pbwtgpu_qshard_prepare(pbwtgpu_ctx *ctx, pbwtgpu_qshard *qs, const int32_t *dev_query_aggs, int rank, int32_t *dev_panel_agg) {
+  if (!ctx || !qs || rank < 0 || (rank > 0 && !dev_query_aggs) || !dev_panel_agg) return fail(ctx, PBWTGPU_ERR_ARG, "qshard_prepare: bad args");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (qs->Q >= 2) {
+    if (int rc = qs->wq.apply_prefix(dev_query_aggs, rank)) return rc;
+    qs->wp.qaWin = qs->wq.ord[qs->wq.cur];  // the query order entering every local window
+  } else {
+    qs->wp.qaWin = qs->qaZero;
+  }
+  if (int rc = qs->wp.prepare()) return rc;
+  if (int rc = qs->wp.export_aggregate(dev_panel_agg)) return rc;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int pbwtgpu_qshard_chain(pbwtgpu_ctx *ctx, pbwtgpu_qshard *qs, const int32_t *dev_panel_aggs, int rank, const int32_t *dev_state_in,
+                         int32_t *dev_state_out) {
+  if (!ctx || !qs || rank < 0 || (rank > 0 && (!dev_panel_aggs || !dev_state_in)) || !dev_state_out)
+    return fail(ctx, PBWTGPU_ERR_ARG, "qshard_chain: bad args");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (int rc = qs->wp.apply_prefix(dev_panel_aggs, rank)) return rc;
+  if (int rc = qs->wp.query_chain(rank > 0 ? dev_state_in : nullptr, dev_state_out)) return rc;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int pbwtgpu_qshard_finish(pbwtgpu_ctx *ctx, pbwtgpu_qshard *qs, pbwtgpu_match **matches, int64_t *nmatch, pbwtgpu_nomatch **nomatch,
+                          int64_t *nnomatch) {
+  if (!ctx || !qs || !matches || !nmatch) return fail(ctx, PBWTGPU_ERR_ARG, "qshard_finish: bad args");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  pbwtgpu_match *recDev = nullptr;
+  pbwtgpu_nomatch *nmDev = nullptr;
+  unsigned long long nrec = 0, nnm = 0;
+  if (int rc = finish_query_sweep(qs->wp, &recDev, &nrec, &nmDev, &nnm)) return rc;
+  return query_results_to_host(ctx, recDev, nrec, nmDev, nnm, matches, nmatch, nomatch, nnomatch);
+}
+
+void pbwtgpu_qshard_free(pbwtgpu_ctx *ctx, pbwtgpu_qshard *qs) {
+  if (!qs) return;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  delete qs;
 }
 
 int pbwtgpu_pack3(pbwtgpu_ctx *ctx, const uint8_t *y, int M, int N, uint8_t **yz, int64_t *nyz) {

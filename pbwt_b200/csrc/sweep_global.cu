@@ -463,29 +463,31 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     int patchIdx = -1;  // CTA-local index (word*32+lane) of the warp's first run head, held by that lane only
     // kBatch words in flight per warp: the loads are L2 round trips.  FULL batches (entirely inside the warp's words
     // and below M: all but the last one) carry no validity predicates.
-    auto phaseA_batch = [&](auto fullTag, const int e0) {
+    // NB words per batch (kBatch, and 4 / 2 / 1 for what is left of the warp's EW words: a batch never reaches beyond them,
+    // so no issue slot is spent on words that do not exist); FULL batches lie entirely below M and carry no predicates
+    auto phaseA_batch = [&](auto fullTag, auto nbTag, const int e0) {
       constexpr bool FULL = decltype(fullTag)::value;
-      int hB[kBatch], dB[kBatch];
-      uint32_t cB[kBatch];
+      constexpr int NB = decltype(nbTag)::value;
+      int hB[NB], dB[NB];
+      uint32_t cB[NB];
       const unsigned iBase = (unsigned)(posBase + e0 * 32 + lane);
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
+      for (int u = 0; u < NB; ++u) {
         const unsigned i = iBase + u * 32;
-        const bool valid = FULL || (e0 + u < EW && (int)i < M);
+        const bool valid = FULL || (int)i < M;
         hB[u] = ((MODE == kGather || p.xOut) && valid) ? __ldcg(aC + i) : 0;
         dB[u] = (WITH_D && valid) ? __ldcg(dC + i) : 0;
       }
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
+      for (int u = 0; u < NB; ++u) {
         const int base = posBase + (e0 + u) * 32;
-        const bool valid = FULL || (e0 + u < EW && base + lane < M);
+        const bool valid = FULL || base + lane < M;
         if (MODE == kGather) cB[u] = valid ? __ldg(col + ((unsigned)hB[u] >> 5)) : kFull;
-        else cB[u] = (FULL || (e0 + u < EW && base < M)) ? __ldg(col + ((unsigned)base >> 5)) : 0u;
+        else cB[u] = (FULL || base < M) ? __ldg(col + ((unsigned)base >> 5)) : 0u;
       }
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u) {
+      for (int u = 0; u < NB; ++u) {
         const int e = e0 + u;
-        if (!FULL && e >= EW) break;
         const int i = posBase + e * 32 + lane;
         uint32_t Bw;
         if (MODE == kGather) {
@@ -538,9 +540,16 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
         zw += __popc(~Bw);
       }
     };
-    for (int e0 = 0; e0 < EW; e0 += kBatch) {
-      if (e0 + kBatch <= EW && posBase + (e0 + kBatch) * 32 <= M) phaseA_batch(std::true_type{}, e0);
-      else phaseA_batch(std::false_type{}, e0);
+    {
+      auto run = [&](auto nbTag, const int e0) {
+        if (posBase + (e0 + decltype(nbTag)::value) * 32 <= M) phaseA_batch(std::true_type{}, nbTag, e0);
+        else phaseA_batch(std::false_type{}, nbTag, e0);
+      };
+      int e0 = 0;
+      for (; e0 + kBatch <= EW; e0 += kBatch) run(std::integral_constant<int, kBatch>{}, e0);
+      if (EW - e0 >= 4) { run(std::integral_constant<int, 4>{}, e0); e0 += 4; }
+      if (EW - e0 >= 2) { run(std::integral_constant<int, 2>{}, e0); e0 += 2; }
+      if (EW - e0 >= 1) run(std::integral_constant<int, 1>{}, e0);
     }
     if (WITH_D) carry = max(carry, __reduce_max_sync(kFull, lmax));
     if (lane == 0) {
@@ -658,19 +667,19 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
     // ---------------- phase C: scatter ----------------
     {
       int zacc = zIn;
-      auto phaseC_batch = [&](auto fullTag, const int e0) {
+      auto phaseC_batch = [&](auto fullTag, auto nbTag, const int e0) {
         constexpr bool FULL = decltype(fullTag)::value;
-        int hB[kBatch];
+        constexpr int NB = decltype(nbTag)::value;
+        int hB[NB];
         const unsigned iBase = (unsigned)(p0 + (wordBase + e0) * 32 + lane);
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
+        for (int u = 0; u < NB; ++u) {
           const unsigned i = iBase + u * 32;
-          hB[u] = (FULL || (e0 + u < EW && (int)i < M)) ? __ldcg(aC + i) : 0;
+          hB[u] = (FULL || (int)i < M) ? __ldcg(aC + i) : 0;
         }
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
+        for (int u = 0; u < NB; ++u) {
           const int e = e0 + u;
-          if (!FULL && e >= EW) break;
           const int li = (wordBase + e) * 32 + lane;
           const int i = p0 + li;
           const uint32_t Bw = smem[oY + wordBase + e];
@@ -685,10 +694,15 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
           zacc += __popc(~Bw);
         }
       };
-      for (int e0 = 0; e0 < EW; e0 += kBatch) {
-        if (e0 + kBatch <= EW && p0 + (wordBase + e0 + kBatch) * 32 <= M) phaseC_batch(std::true_type{}, e0);
-        else phaseC_batch(std::false_type{}, e0);
-      }
+      auto run = [&](auto nbTag, const int e0) {
+        if (p0 + (wordBase + e0 + decltype(nbTag)::value) * 32 <= M) phaseC_batch(std::true_type{}, nbTag, e0);
+        else phaseC_batch(std::false_type{}, nbTag, e0);
+      };
+      int e0 = 0;
+      for (; e0 + kBatch <= EW; e0 += kBatch) run(std::integral_constant<int, kBatch>{}, e0);
+      if (EW - e0 >= 4) { run(std::integral_constant<int, 4>{}, e0); e0 += 4; }
+      if (EW - e0 >= 2) { run(std::integral_constant<int, 2>{}, e0); e0 += 2; }
+      if (EW - e0 >= 1) run(std::integral_constant<int, 1>{}, e0);
     }
     if (p.yOut) {  // sorted column k, pad bits cleared
       for (int w = tid; w < chunkWords; w += kThreads) {
