@@ -569,7 +569,8 @@ def main():
                 "c5_match_sweep_1000_vs_100k_x_100k": run_config_query(P, torch, eng, stream, flush, 100000, 1000, 100000, peak, 5000, want_cpu),
             }
         else:
-            configs = {"c4_build_ad_1m_x_100k_site_sharded": run_config4_sharded(P, torch, dist, eng, stream, flush, rank, world, peak)}
+            configs = {"c4_build_ad_1m_x_100k_site_sharded": run_config4_sharded(P, torch, dist, eng, stream, flush, rank, world, peak),
+                       "c5_match_sweep_1000_vs_100k_x_100k_site_sharded": run_config5_sharded(P, torch, dist, eng, stream, rank, world, peak)}
     if panel is not None:
         panel.free()
 
@@ -755,6 +756,104 @@ def run_config4_sharded(P, torch, dist, eng, stream, flush, rank, world, peak):
             "algorithmic_bytes_per_hap_site": BYTES_AD,
             "roofline_per_gpu": roofline_of((BYTES_AD * M * N + float(tot[0])) / world, ms_max, peak),
             "kernel_ms_per_step_rank0": {k: v[0] / 2 for k, v in kt.items() if v[0] > 0}}
+
+
+def run_config5_sharded(P, torch, dist, eng, stream, rank, world, peak):
+    """configs[4] at N > 1: matchSequencesSweep of 1,000 queries against 100,000 x 100,000 with the SITES partitioned
+    across the ranks (include/pbwtgpu.h, pbwtgpu_qshard_*): two all-gathers of aggregates and the queries' state handed
+    from rank to rank.  Every query is swept on every GPU's site range -- sharding the queries themselves would repeat
+    the whole panel sweep on every GPU.  Parity: rank 0 runs the whole sweep on one GPU and compares the
+    concatenated records and events by checksum."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from fullsize_checks import split_panel
+
+    M, Q, N = 100000, 1000, 100000
+    # the stored streams: built once on rank 0's GPU, broadcast as bytes (every rank reads the same two files in practice)
+    if rank == 0:
+        both = eng.panel_synthetic(M + Q, N, seed=0x5EED0005, L=1000, mu=8.0)
+        x = both.to_host()
+        both.free()
+        px, qx = split_panel(x, M, Q)
+        del x
+        pp, qq = eng.panel_from_host(px, M), eng.panel_from_host(qx, Q)
+        r = eng.build_device(pp, P.WANT_YZ); pyz = r.fetch()["yz"]; r.free()
+        r = eng.build_device(qq, P.WANT_YZ); qyz = r.fetch()["yz"]; r.free()
+        pp.free()
+        qq.free()
+        sizes = torch.tensor([pyz.size, qyz.size], dtype=torch.int64, device="cuda")
+    else:
+        sizes = torch.zeros(2, dtype=torch.int64, device="cuda")
+    dist.broadcast(sizes, src=0)
+    bufs = []
+    for i, nbytes in enumerate(int(v) for v in sizes.tolist()):
+        t = torch.from_numpy((pyz, qyz)[i].copy()).cuda() if rank == 0 else torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, src=0)
+        bufs.append(t.cpu().numpy())
+    pyz, qyz = bufs
+    bounds = [N * r // world for r in range(world + 1)]
+    qaggs = torch.zeros((world, eng.shard_aggregate_ints(Q)), dtype=torch.int32, device="cuda")
+    paggs = torch.zeros((world, eng.shard_aggregate_ints(M)), dtype=torch.int32, device="cuda")
+    qagg, pagg = torch.zeros_like(qaggs[0]), torch.zeros_like(paggs[0])
+    s_in = torch.zeros((2, Q), dtype=torch.int32, device="cuda")
+    s_out = torch.zeros((2, Q), dtype=torch.int32, device="cuda")
+
+    def step():
+        sh = eng.query_shard(pyz, M, N, qyz, Q, bounds[rank], bounds[rank + 1] - bounds[rank])
+        sh.export_queries(qagg.data_ptr())
+        dist.all_gather_into_tensor(qaggs, qagg)
+        sh.prepare(qaggs.data_ptr(), rank, pagg.data_ptr())
+        dist.all_gather_into_tensor(paggs, pagg)
+        if rank > 0:
+            dist.recv(s_in, src=rank - 1)
+        sh.chain(paggs.data_ptr(), rank, s_in.data_ptr() if rank else None, s_out.data_ptr())
+        if rank + 1 < world:
+            dist.send(s_out, dst=rank + 1)
+        out = sh.finish()
+        sh.free()
+        return out
+
+    step()
+    eng.synchronize()
+    eng.last_timings()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    rec, nom = step()
+    torch.cuda.synchronize()
+    wall = time.time() - t0
+    kt = eng.last_timings()
+    t = torch.tensor([wall, sum(v[0] for v in kt.values()) * 1e-3], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    parts = torch.from_numpy(np.array([O.checksum_parts(O.mix_records(rec)), (len(nom), int(nom["site"].sum()) if len(nom) else 0, 0)],
+                                      dtype=np.uint64).view(np.int64)).cuda()
+    allparts = torch.zeros((world, 2, 3), dtype=torch.int64, device="cuda")
+    dist.all_gather_into_tensor(allparts, parts)
+    parity, one_gpu_ms = None, None
+    if rank == 0:
+        ap_ = allparts.cpu().numpy().view(np.uint64)
+        joined = O.checksum_join([tuple(int(v) for v in ap_[w, 0]) for w in range(world)])
+        eng.match_sweep(pyz, M, N, qyz, Q)
+        eng.last_timings()
+        rec1, nom1 = eng.match_sweep(pyz, M, N, qyz, Q)
+        one_gpu_ms = sum(v[0] for v in eng.last_timings().values())
+        ok = (joined == O.checksum_join([O.checksum_parts(O.mix_records(rec1))]) and int(ap_[:, 0, 0].sum()) == len(rec1)
+              and int(ap_[:, 1, 0].sum()) == len(nom1) and int(ap_[:, 1, 1].sum()) == (int(nom1["site"].sum()) if len(nom1) else 0))
+        parity = "ok" if ok else "MISMATCH"
+    dist.barrier()
+    wall_max, dev_max = float(t[0]), float(t[1])
+    nrec = int(allparts[:, 0, 0].sum())
+    return {"workload": f"matchSequencesSweep: {Q} queries vs {M} haplotypes x {N} sites, sites partitioned across {world} GPUs, every "
+                        f"query on every GPU (strong scaling; N assumed: BASELINE gives none)",
+            "haplotypes": M, "queries": Q, "sites": N, "n_gpus": world, "ms_wall_host_streams_in_records_out": wall_max * 1e3,
+            "ms_kernels_max_over_ranks": dev_max * 1e3, "value": M * N / wall_max, "unit": "panel " + UNIT, "records": nrec,
+            "exchanges": {"all_gather_query_aggregate_bytes_per_rank": int(qagg.numel()) * 4, "all_gather_panel_aggregate_bytes_per_rank": int(pagg.numel()) * 4,
+                          "state_hand_off_bytes": 8 * Q},
+            "parity_vs_one_gpu": parity, "one_gpu_kernel_ms_same_box": one_gpu_ms,
+            "strong_scaling_efficiency_kernels": (one_gpu_ms / (dev_max * 1e3) / world) if one_gpu_ms else None,
+            "roofline_per_gpu": roofline_of((BYTES_AD * M * N + 16.0 * nrec) / world, dev_max * 1e3, peak),
+            "kernel_ms_rank0": {k: v[0] for k, v in kt.items() if v[0] > 0}}
 
 
 if __name__ == "__main__":

@@ -491,6 +491,51 @@ def test_query_sweep_wide_panel_default_windows(eng, orc):
     assert len(rec) == len(want_rec) and (rec == want_rec).all() and (nom == want_nom).all()
 
 
+@pytest.mark.parametrize("M,Q,N,R,W,dp,dq,starts", [(60, 7, 80, 3, 2, 0.03, 0.3, False), (1000, 300, 240, 4, 5, 0.1, 0.1, True),
+                                                     (33, 64, 64, 8, 1, 0.5, 0.02, False), (2000, 700, 400, 2, 7, 0.004, 0.01, True),
+                                                     (200, 1, 90, 3, 4, 0.2, 0.2, False), (500, 40, 2000, 5, 6, 0.03, 0.03, True)])
+def test_query_sweep_site_shards_sequential(eng, orc, M, Q, N, R, W, dp, dq, starts):
+    """The multi-GPU query sweep (pbwtgpu_qshard_*: sites partitioned into R shards, two all-gathers of aggregates, the
+    query state handed from shard to shard) run shard by shard on one GPU: the shards' records and 'no match' events,
+    concatenated in site order, are matchSequencesSweep's."""
+    import torch
+
+    rng = np.random.default_rng(M + Q + R)
+    hp = (rng.random((M, N)) < dp).astype(np.uint8)
+    hq = (rng.random((Q, N)) < dq).astype(np.uint8)
+    hq[0] = hp[M // 2]
+    for k in rng.choice(N, size=max(1, N // 20), replace=False):
+        hp[:, k] = rng.integers(0, 2)
+    pa = rng.permutation(M).astype(np.int32) if starts else None
+    qa = rng.permutation(Q).astype(np.int32) if starts else None
+    pyz = orc.build(O.pack_panel(hp), M, N, a_start=pa, with_d=False)[0]
+    qyz = orc.build(O.pack_panel(hq), Q, N, a_start=qa, with_d=False)[0]
+    want_rec, want_nom = orc.match_sweep(pyz, M, N, qyz, Q, pa_start=pa, qa_start=qa)
+    bounds = [N * r // R for r in range(R + 1)]
+    eng.set_option("windows", W)
+    try:
+        shards = [eng.query_shard(pyz, M, N, qyz, Q, bounds[r], bounds[r + 1] - bounds[r], pa_start=pa, qa_start=qa) for r in range(R)]
+        qaggs = torch.zeros((R, eng.shard_aggregate_ints(Q)), dtype=torch.int32, device="cuda")
+        paggs = torch.zeros((R, eng.shard_aggregate_ints(M)), dtype=torch.int32, device="cuda")
+        state = torch.zeros((R + 1, 2, Q), dtype=torch.int32, device="cuda")
+        for r in range(R):
+            shards[r].export_queries(qaggs[r].data_ptr())
+        for r in range(R):
+            shards[r].prepare(qaggs.data_ptr(), r, paggs[r].data_ptr())
+        outs = []
+        for r in range(R):
+            shards[r].chain(paggs.data_ptr(), r, state[r].data_ptr() if r else None, state[r + 1].data_ptr())
+            outs.append(shards[r].finish())
+        for sh in shards:
+            sh.free()
+    finally:
+        eng.set_option("windows", 0)
+    rec = np.concatenate([o[0] for o in outs])
+    nom = np.concatenate([o[1] for o in outs])
+    assert len(rec) == len(want_rec) and (rec == want_rec).all()
+    assert len(nom) == len(want_nom) and (nom == want_nom).all()
+
+
 def test_query_sweep_many_queries_narrow_panel(eng, orc):
     """More queries than the shared-memory kernel holds: routed to the wide kernel without forcing."""
     M, Q, N = 900, 3000, 70
