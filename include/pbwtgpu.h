@@ -45,8 +45,10 @@ enum {
   PBWTGPU_WANT_YZ = 1u,        /* pack3 stream of the sorted columns  (pbwtCore.c:240-277) */
   PBWTGPU_WANT_D = 2u,         /* carry the divergence array           (pbwtCore.c:485-508) */
   PBWTGPU_WANT_MAXWITHIN = 4u, /* set-maximal matches, implies WANT_D  (pbwtMatch.c:115-142) */
-  PBWTGPU_WANT_LONGWITHIN = 8u /* all matches of >= L sites (-longWithin L, matchLongWithin2, pbwtMatch.c:85-113),
+  PBWTGPU_WANT_LONGWITHIN = 8u,/* all matches of >= L sites (-longWithin L, matchLongWithin2, pbwtMatch.c:85-113),
                                   implies WANT_D; L is the option "long_within"; exclusive with WANT_MAXWITHIN */
+  PBWTGPU_WANT_STATS = 16u     /* with WANT_MAXWITHIN: the match records are CONSUMED on the device into the length histogram
+                                  of -stats (pbwtMatch.c:130-131) and never materialised; pbwtgpu_result_fetch_hist */
 };
 
 int pbwtgpu_words_per_col(int M);
@@ -112,6 +114,9 @@ int pbwtgpu_result_sizes(const pbwtgpu_result *result, int64_t *nyz, int64_t *nm
  * matches[nmatch]. */
 int pbwtgpu_result_fetch(pbwtgpu_ctx *ctx, const pbwtgpu_result *result, uint8_t *yz, int32_t *a_end, int32_t *d_end,
                          pbwtgpu_match *matches);
+/* WANT_STATS: hist[len], len = 0 .. N, = number of (position, site) reporters of matchMaximalWithin whose longer block
+ * has that length -- exactly matchLengthHist of the reference (pbwtMatch.c:130-131,161-178). */
+int pbwtgpu_result_fetch_hist(pbwtgpu_ctx *ctx, const pbwtgpu_result *result, int64_t *hist);
 void pbwtgpu_result_free(pbwtgpu_ctx *ctx, pbwtgpu_result *result);
 
 /* ---- multi-GPU: the SITES of one panel are partitioned across GPUs (one process per GPU) ---------------
@@ -181,6 +186,10 @@ int pbwtgpu_build(pbwtgpu_ctx *ctx, const uint32_t *xbits, int M, int N, const i
 /* matchMaximalWithin(p, report) over a stored stream (pbwtMatch.c:115-142). */
 int pbwtgpu_max_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start,
                        int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches, int64_t *nmatch);
+/* pbwtLongMatches(p, 0) under -stats (pbwtMatch.c:148-178): the length histogram alone, hist[0 .. N]; only these
+ * (N + 1) counters cross PCIe, not the match records. */
+int pbwtgpu_max_within_stats(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start,
+                             int64_t *hist);
 /* pbwtLongMatches(p, L) with L > 0 = matchLongWithin2 (pbwtMatch.c:85-113, 148-183) over a stored stream: every
  * pair of haplotypes whose match ending at a site is at least L sites long and cannot be extended.  Records in the
  * reference's callback order, including its quirks (the last block of a site is never reported; at k == N the

@@ -22,7 +22,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PBWTGPU_LIB") or os.path.join(_HERE, "libpbwtgpu.so")  # (the override is a development aid: A/B builds)
 
-WANT_YZ, WANT_D, WANT_MAXWITHIN, WANT_LONGWITHIN = 1, 2, 4, 8
+WANT_YZ, WANT_D, WANT_MAXWITHIN, WANT_LONGWITHIN, WANT_STATS = 1, 2, 4, 8, 16
 KERNEL_CLASSES = ("sweep", "pack3", "unpack3", "query", "synth", "aux", "prepass", "combine", "copy")
 
 MATCH_DTYPE = np.dtype([("ai", "<i4"), ("bi", "<i4"), ("start", "<i4"), ("end", "<i4")])
@@ -81,6 +81,8 @@ def load_library() -> C.CDLL:
         lib.pbwtgpu_build.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_uint, C.POINTER(_vp), C.POINTER(_i64), _vp, _vp,
                                       C.POINTER(_vp), C.POINTER(_i64)]
         lib.pbwtgpu_max_within.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_i64)]
+        lib.pbwtgpu_max_within_stats.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp]
+        lib.pbwtgpu_result_fetch_hist.argtypes = [_vp, _vp, _vp]
         lib.pbwtgpu_cursor_at.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp]
         lib.pbwtgpu_build_reverse.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, C.POINTER(_vp), C.POINTER(_i64), _vp]
         lib.pbwtgpu_long_within.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, C.POINTER(_vp), C.POINTER(_i64)]
@@ -165,6 +167,12 @@ class Result:
         if bufs["matches"] is not None:
             bufs["matches"] = bufs["matches"][: self.nmatch]
         return bufs
+
+    def fetch_hist(self) -> np.ndarray:
+        """WANT_STATS: the -stats length histogram accumulated on the device, hist[0 .. N]."""
+        hist = np.zeros(self.N + 1, np.int64)
+        self.eng._check(self.eng.lib.pbwtgpu_result_fetch_hist(self.eng.ctx, self.handle, _ptr(hist)))
+        return hist
 
     def free(self):
         if self.handle:
@@ -371,6 +379,14 @@ class Engine:
                                                 C.byref(mt) if with_matches else None, C.byref(nm)))
         return {"a_end": a_end, "d_end": d_end,
                 "matches": _take(self.lib, mt, nm.value * 16, MATCH_DTYPE) if with_matches else None}
+
+    def max_within_stats(self, yz: np.ndarray, M: int, N: int, a_start=None) -> np.ndarray:
+        """pbwtLongMatches(p, 0) under -stats: the reporters' length histogram hist[0 .. N], matches consumed on the device."""
+        yz = np.ascontiguousarray(yz, np.uint8)
+        a0 = None if a_start is None else np.ascontiguousarray(a_start, np.int32)
+        hist = np.zeros(N + 1, np.int64)
+        self._check(self.lib.pbwtgpu_max_within_stats(self.ctx, _ptr(yz), yz.size, M, N, _ptr(a0), _ptr(hist)))
+        return hist
 
     def cursor_at(self, yz: np.ndarray, M: int, N: int, k: int, a_start=None):
         """State of a PbwtCursor entering site k of a stored stream -> (y or None, a, d, c or None)."""

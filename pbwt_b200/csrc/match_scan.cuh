@@ -224,7 +224,11 @@ __device__ __forceinline__ void match_rounds(const S &s, int k, bool live, int M
       bool extends = false;
       if (di <= dn1) extends = scan_up(s, i, yi, di, live, lane, lo);
       if (!extends && di >= dn1) extends = scan_down(s, i, yi, dn1, M, live, lane, hi);
-      if (lane == 0) resS[g - g0] = make_int4(i, lo, hi, extends ? 0 : (i - lo) + (hi - i - 1));
+      if (lane == 0) {
+        resS[g - g0] = make_int4(i, lo, hi, extends ? 0 : (i - lo) + (hi - i - 1));
+        // -stats (pbwtMatch.c:130-131): one count per reporter, at the length of the longer of its two blocks
+        if (sink.hist && !extends) atomicAdd(sink.hist + (k - min(di, dn1)), 1u);
+      }
     }
     __syncthreads();  // the round's results are published (first round: the scatter is complete too)
     long long roundTotal = 0;

@@ -64,6 +64,7 @@ struct pbwtgpu_result {
   int32_t *dEnd = nullptr;
   pbwtgpu_match *rec = nullptr;
   int64_t nrec = 0;
+  unsigned int *hist = nullptr;  // WANT_STATS: [N + 1]
   std::vector<void *> owned;  // device blocks released by pbwtgpu_result_free
   std::vector<size_t> ownedBytes;
 };
@@ -706,8 +707,15 @@ struct WindowedSweep {
     if (matchMode == 2 && ctx->optLongT < 1) return fail(ctx, PBWTGPU_ERR_ARG, "long_within: set option long_within to L >= 1 first");
     if (wantMatch && useGlobal && !gb.segCnt) return fail(ctx, PBWTGPU_ERR_ARG, "sweep was prepared without match flags");
     const bool wantYz = (flags & PBWTGPU_WANT_YZ) && mode == kGather;
+    // -stats: the matches are consumed on the device (length histogram); no record pool, no gather
+    const bool statsOnly = (flags & PBWTGPU_WANT_STATS) && matchMode == 1;
+    if ((flags & PBWTGPU_WANT_STATS) && matchMode != 1) return fail(ctx, PBWTGPU_ERR_ARG, "WANT_STATS needs WANT_MAXWITHIN");
     res->M = M;
     res->N = N;
+    if (statsOnly) {
+      if (int rc = result_alloc(ctx, res, &res->hist, (size_t)nTotal + 1)) return rc;
+      CUDA_TRY(ctx, cudaMemsetAsync(res->hist, 0, sizeof(unsigned int) * ((size_t)nTotal + 1), ctx->stream));
+    }
     if (int rc = result_alloc(ctx, res, &res->aEnd, (size_t)M)) return rc;
     if (wantD)
       if (int rc = result_alloc(ctx, res, &res->dEnd, (size_t)M + 1)) return rc;
@@ -742,6 +750,7 @@ struct WindowedSweep {
     a.reportAtN = 1;
     a.longT = (int)ctx->optLongT;
     a.debugNoCandidates = (int)ctx->optNoCandidates;
+    a.lenHist = res->hist;
     std::vector<unsigned long long> counts(W, 0);
     std::vector<long long> offs;  // per-window record offsets: a host temporary that must outlive the last synchronisation
     long long *winNanos = nullptr;
@@ -774,13 +783,16 @@ struct WindowedSweep {
     unsigned long long *pin = ctx->pinned;
     if (W + 3 > pbwtgpu_ctx::kPinnedWords) return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "too many windows");
     for (int attempt = 0; attempt < 2; ++attempt) {
-      if (wantMatch) {
+      if (wantMatch && !statsOnly) {
         poolChunks = (int)((recCap + kRecChunk - 1) >> kRecChunkLog) + producers;
         if (int rc = tmp.get(&pool, (size_t)poolChunks << kRecChunkLog)) return rc;
         if (int rc = tmp.get(&chunkTab, (size_t)producers * poolChunks)) return rc;
         CUDA_TRY(ctx, cudaMemsetAsync(chunkCounter, 0, sizeof(int), ctx->stream));
         if (useGlobal) CUDA_TRY(ctx, cudaMemsetAsync(gb.segCnt, 0, sizeof(int32_t) * (size_t)nSeg, ctx->stream));
         a.recPool = pool; a.poolChunks = poolChunks; a.chunkTab = chunkTab;
+      } else if (statsOnly) {
+        CUDA_TRY(ctx, cudaMemsetAsync(chunkCounter, 0, sizeof(int), ctx->stream));
+        if (useGlobal) CUDA_TRY(ctx, cudaMemsetAsync(gb.segCnt, 0, sizeof(int32_t) * (size_t)nSeg, ctx->stream));
       }
       {
         ScopedTimer t(ctx, PBWTGPU_K_SWEEP);
@@ -809,7 +821,7 @@ struct WindowedSweep {
         CUDA_TRY(ctx, cudaMemcpyAsync(&pin[0], chunkCounter, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
       }
       if (wantMatch || wantYz) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-      if (!wantMatch) break;
+      if (!wantMatch || statsOnly) break;
       const int used = (int)(pin[0] & 0xffffffffull);
       segTotal = (long long)pin[2];
       if (!useGlobal)
@@ -834,7 +846,9 @@ struct WindowedSweep {
         fprintf(stderr, "\n");
       }
     }
-    if (wantMatch && useGlobal) {
+    if (statsOnly) {
+      // (the records were counted, not written: nothing to gather)
+    } else if (wantMatch && useGlobal) {
       res->nrec = segTotal;
       if (int rc = result_alloc(ctx, res, &res->rec, (size_t)std::max<long long>(segTotal, 1))) return rc;
       ScopedTimer t(ctx, PBWTGPU_K_AUX);
@@ -1228,6 +1242,15 @@ int pbwtgpu_result_fetch(pbwtgpu_ctx *ctx, const pbwtgpu_result *r, uint8_t *yz,
   return 0;
 }
 
+int pbwtgpu_result_fetch_hist(pbwtgpu_ctx *ctx, const pbwtgpu_result *r, int64_t *hist) {
+  if (!ctx || !r || !hist || !r->hist) return fail(ctx, PBWTGPU_ERR_ARG, "result_fetch_hist: the sweep was not run with WANT_STATS");
+  std::vector<unsigned int> h((size_t)r->N + 1);
+  CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), r->hist, sizeof(unsigned int) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < h.size(); ++i) hist[i] = (int64_t)h[i];
+  return 0;
+}
+
 void pbwtgpu_result_free(pbwtgpu_ctx *ctx, pbwtgpu_result *r) {
   if (!r) return;
   if (ctx) {
@@ -1317,6 +1340,15 @@ int pbwtgpu_max_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, 
   pbwtgpu_result *res = nullptr;
   int rc = pbwtgpu_sweep_yz_device(ctx, yz, nyz, M, N, a_start, matches ? PBWTGPU_WANT_MAXWITHIN : PBWTGPU_WANT_D, &res);
   if (!rc) rc = fetch_to_malloc(ctx, res, nullptr, nullptr, a_end, d_end, matches, nmatch);
+  pbwtgpu_result_free(ctx, res);
+  return rc;
+}
+
+int pbwtgpu_max_within_stats(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start, int64_t *hist) {
+  if (!hist) return fail(ctx, PBWTGPU_ERR_ARG, "max_within_stats: bad args");
+  pbwtgpu_result *res = nullptr;
+  int rc = pbwtgpu_sweep_yz_device(ctx, yz, nyz, M, N, a_start, PBWTGPU_WANT_MAXWITHIN | PBWTGPU_WANT_STATS, &res);
+  if (!rc) rc = pbwtgpu_result_fetch_hist(ctx, res, hist);
   pbwtgpu_result_free(ctx, res);
   return rc;
 }

@@ -66,6 +66,7 @@ struct SweepArgs {
   int longT;                     // -longWithin L: report matches of at least this many sites (match mode 2)
   long long *winNanos;           // [W] optional: wall time of each window's CTA (globaltimer, debugging aid)
   int debugNoCandidates;         // profiling aid: publish zero match candidates per site (sweep-side cost only)
+  unsigned int *lenHist;         // -stats (pbwtMatch.c:130-131): [nTotal + 1] histogram of the reporters' match lengths, or NULL
   // query sweep (matchSequencesSweep, pbwtMatch.c:363-443): single window, sorted mode, with d
   const uint32_t *qcols;         // [N][qwpc] sorted query columns
   int qwpc, Q;
@@ -93,6 +94,7 @@ struct RecSink {
   const int *mirror;    // shared-memory mirror of the newest kTabMirror entries
   int nChunks;          // chunks allocated so far (uniform)
   int cap;              // entries of the chunk table row (chunks beyond it do not exist: the pool overflowed)
+  unsigned int *hist;   // -stats: histogram of the reporters' match lengths (device consumer of the matches), or NULL
   __device__ __forceinline__ void put(long long o, int4 rec) const {
     const int c = (int)(o >> kRecChunkLog);
     const int id = (nChunks - c <= kTabMirror) ? mirror[c & (kTabMirror - 1)] : (c < cap ? __ldcg(tab + c) : -1);

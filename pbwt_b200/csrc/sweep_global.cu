@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
   sink.mirror = ctabS;
   sink.nChunks = 0;
   sink.cap = p.poolChunks;
+  sink.hist = p.lenHist;
   long long recBase = 0;  // records produced so far by this CTA (uniform)
   auto ensure_chunks = [&](long long upTo) {
     const int need = (int)((upTo + kRecChunk - 1) >> kRecChunkLog);

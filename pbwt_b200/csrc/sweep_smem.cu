@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
   sink.mirror = ctabS;
   sink.nChunks = 0;
   sink.cap = p.poolChunks;
+  sink.hist = p.lenHist;
   long long recBase = 0;  // records produced so far by this window (uniform)
   long long nmBase = 0;   // "no match" events so far (query sweep)
   uint32_t qWord = (QUERY && tid < p.Q && k0 < k1) ? p.qcols[(size_t)(k0 + colShift) * p.qwpc + warp] : 0u;
@@ -356,24 +357,27 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     }
 
     // ---------------- cross-warp prefixes (each warp redundantly) ----------------
-    int zIn, c, zExLane;  // zExLane: zeros in warps below warp index == lane
+    // zeros below this warp / in the column, and the divergence carry entering this warp: single warp reductions (REDUX)
+    // over the 32 per-warp sums instead of 5-step shuffle scans
+    int zIn, c, zExLane = 0;  // zExLane (query sweep only): zeros in warps below warp index == lane
     {
       const int z = wsumZ[lane];
-      int tot;
-      zExLane = warp_excl_scan(z, lane, tot);
-      zIn = __shfl_sync(kFull, zExLane, warp);
-      c = tot;
+      if (QUERY) {
+        int tot;
+        zExLane = warp_excl_scan(z, lane, tot);
+        zIn = __shfl_sync(kFull, zExLane, warp);
+        c = tot;
+      } else {
+        c = __reduce_add_sync(kFull, z);
+        zIn = __reduce_add_sync(kFull, lane < warp ? z : 0);
+      }
     }
     int cIn = 0;
-    if (WITH_D) {
-      uint32_t x = wsumR[lane];
-#pragma unroll
-      for (int dl = 1; dl < 32; dl <<= 1) {
-        const uint32_t t = __shfl_up_sync(kFull, x, dl);
-        if (lane >= dl && !(x >> 31)) x = (t & 0x80000000u) | max(t & 0x7fffffffu, x);
-      }
-      const uint32_t inc = __shfl_sync(kFull, x, warp > 0 ? warp - 1 : 0);
-      cIn = warp > 0 ? (int)(inc & 0x7fffffffu) : 0;
+    if (WITH_D) {  // max of the warps' carries from the last warp below this one that saw a run head (from warp 0 if none did)
+      const uint32_t x = wsumR[lane];
+      const unsigned heads = __ballot_sync(kFull, x >> 31) & lanemask_lt(warp);
+      const int from = heads ? 31 - __clz(heads) : 0;
+      cIn = __reduce_max_sync(kFull, (lane >= from && lane < warp) ? (int)(x & 0x7fffffffu) : 0);
     }
 
     // ---------------- phase C: stable partition scatter ----------------

@@ -89,7 +89,8 @@ void pbwtLongMatches (PBWT *p, int L)
   if (L < 0) die ("L %d for longWithin must be >= 0", L) ;
   if (isCheck) { checkHapsA = checkHapsB = pbwtHaplotypes (p) ; Ncheck = p->N ; }	/* pbwtMatch.c:156 */
   if (isStats)			/* -stats (pbwtMatch.c:130-131, 161-178): with -maxWithin a histogram of the reporters' match
-				   lengths replaces the MATCH lines; matchLongWithin2 never touches the histogram, so with
+				   lengths replaces the MATCH lines (accumulated on the GPU, one count per reporter at the length
+				   of the longer of its two blocks); matchLongWithin2 never touches the histogram, so with
 				   -longWithin L the MATCH lines are printed and the summary is that of an empty histogram
 				   (the reference's "Average 0.0 matches per sample" and 0/0 length) */
     { pbwtgpu_match *rec = 0 ;
@@ -102,16 +103,12 @@ void pbwtLongMatches (PBWT *p, int L)
 					 p->aFstart, L, 0, 0, &rec, &n), "pbwtgpu_long_within") ;
 	  for (i = 0 ; i < n ; ++i) reportMatchLine (rec[i].ai, rec[i].bi, rec[i].start, rec[i].end) ;
 	}
-      else
-	{ gpuCheck (pbwtgpu_max_within (gpuContext (), arrp(p->yz,0,uchar), arrayMax(p->yz), p->M, p->N,
-					p->aFstart, 0, 0, &rec, &n), "pbwtgpu_max_within") ;
-	  while (i < n)		/* one reporter = a run of records with the same ai and end; its length is the longer
-				   of its two blocks' (k - min(d[i],d[i+1])) */
-	    { int ai = rec[i].ai, end = rec[i].end, best = 0 ;
-	      for ( ; i < n && rec[i].ai == ai && rec[i].end == end ; ++i)
-		if (rec[i].end - rec[i].start > best) best = rec[i].end - rec[i].start ;
-	      ++array(hist, best, int) ;
-	    }
+      else			/* the matches are consumed on the device: only the N+1 counters come back */
+	{ int64_t *h = myalloc (p->N + 1, int64_t) ;
+	  gpuCheck (pbwtgpu_max_within_stats (gpuContext (), arrp(p->yz,0,uchar), arrayMax(p->yz), p->M, p->N,
+					      p->aFstart, h), "pbwtgpu_max_within_stats") ;
+	  for (len = 0 ; len <= p->N ; ++len) if (h[len]) array(hist, len, int) = (int) h[len] ;
+	  free (h) ;
 	}
       for (len = 0 ; len < arrayMax(hist) ; ++len)
 	if (arr(hist, len, int))

@@ -71,6 +71,27 @@ int pbwtgpu_max_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, 
   return ends(yz, nyz, M, N, a_start, a_end, d_end);
 }
 
+/* the device consumer of the matches behind -stats: one count per reporter (a run of records with the same ai and end)
+   at the length of the longer of its blocks, derived here from the oracle's records */
+int pbwtgpu_max_within_stats(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start, int64_t *hist) {
+  (void)ctx;
+  int64_t n = 0, i = 0;
+  orc_max_within(yz, nyz, M, N, a_start, NULL, 0, &n);
+  oracle_match *rec = (oracle_match *)malloc(sizeof(oracle_match) * (size_t)(n > 0 ? n : 1));
+  if (!rec) return PBWTGPU_ERR_NOMEM;
+  orc_max_within(yz, nyz, M, N, a_start, rec, n, &n);
+  memset(hist, 0, sizeof(int64_t) * ((size_t)N + 1));
+  while (i < n) {
+    const int ai = rec[i].ai, end = rec[i].end;
+    int best = 0;
+    for (; i < n && rec[i].ai == ai && rec[i].end == end; ++i)
+      if (rec[i].end - rec[i].start > best) best = rec[i].end - rec[i].start;
+    ++hist[best];
+  }
+  free(rec);
+  return PBWTGPU_OK;
+}
+
 int pbwtgpu_long_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start, int L,
                         int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches, int64_t *nmatch) {
   (void)ctx;

@@ -398,6 +398,43 @@ def test_site_shards_sequential(eng, orc, M, N, R, W, dens, with_start, force_gl
     assert all((o["a_end"] == -1).all() for o in outs[:-1])
 
 
+def _stats_hist(rec, N):
+    """-stats (pbwtMatch.c:130-131): one count per reporter = run of records with the same (ai, end), at its longest length"""
+    hist = np.zeros(N + 1, np.int64)
+    if len(rec):
+        key = rec["ai"].astype(np.int64) * (N + 2) + rec["end"]
+        starts = np.flatnonzero(np.r_[True, key[1:] != key[:-1]])
+        best = np.maximum.reduceat((rec["end"] - rec["start"]).astype(np.int64), starts)
+        np.add.at(hist, best, 1)
+    return hist
+
+
+@pytest.mark.parametrize("M,N,W,dens,force_global", [(33, 40, 1, 0.5, 0), (1000, 300, 7, 0.05, 0), (5000, 200, 37, 0.02, 0),
+                                                      (3000, 200, 5, 0.05, 1), (2752, 38, 2, 0.3, 0)])
+def test_stats_histogram_consumed_on_device(eng, orc, M, N, W, dens, force_global):
+    """WANT_STATS: the matches never leave the device; the histogram equals the one the reference's -stats builds."""
+    rng = np.random.default_rng(M + N)
+    hap = (rng.random((M, N)) < dens).astype(np.uint8)
+    hap[: M // 4] = hap[0]
+    yz = orc.build(O.pack_panel(hap), M, N, with_d=False)[0]
+    rec, n = orc.max_within(yz, M, N)
+    eng.set_option("windows", W)
+    eng.set_option("force_global", force_global)
+    try:
+        hist = eng.max_within_stats(yz, M, N)
+        panel = eng.panel_from_host(O.pack_panel(hap), M)
+        r = eng.build_device(panel, pbwt_b200.WANT_MAXWITHIN | pbwt_b200.WANT_STATS)
+        hist2 = r.fetch_hist()
+        assert r.nmatch == 0
+        r.free()
+        panel.free()
+    finally:
+        eng.set_option("windows", 0)
+        eng.set_option("force_global", 0)
+    want = _stats_hist(rec[:n], N)
+    assert np.array_equal(hist, want) and np.array_equal(hist2, want)
+
+
 def test_smem_limit_without_matches(eng, orc):
     """M between the match kernel's limit (12,544) and the shared-memory limit (13,312): a/d/pack3 only."""
     rng = np.random.default_rng(13)
