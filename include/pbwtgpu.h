@@ -70,7 +70,9 @@ int pbwtgpu_synchronize(pbwtgpu_ctx *ctx);
  * first attempt allows for), "long_within" (L of PBWTGPU_WANT_LONGWITHIN).  Testing and profiling aids: "force_global"
  * (wide-panel kernels on narrow panels), "no_cluster" (cooperative-grid groups where clusters would fit),
  * "no_sort_pass1" (window nodes by sweeping instead of sorting), "no_sort_combine" (window combines by sweeping
- * pseudo-sites instead of the radix sort + range maxima), "equal_windows" (no shortening of the panel's edge
+ * pseudo-sites instead of the radix sort + range maxima), "no_fused_pack3" (sorted columns to global memory + the
+ * stand-alone pack3 encoder instead of the encoder fused into the sweep), "pack3_window_capacity" (bytes per window of the
+ * fused encoder's output: small values force its fall-back), "equal_windows" (no shortening of the panel's edge
  * windows), "window_times", "debug_no_candidates". */
 int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value);
 /* Per-kernel-class device times of the last sweep (ms, CUDA events on the launching stream) and

@@ -56,28 +56,27 @@ __device__ __forceinline__ void visit_runs(const uint32_t *col, int M, int nWord
 
 constexpr int kWarpsPerBlock = 8;
 
+// pack3 bytes of one bit column (global or shared memory), by one warp
+__device__ __forceinline__ int count_column(const uint32_t *col, int M, int lane) {
+  const int nWords = (M + 31) / 32;
+  int carryEnd = -1, bytes = 0;
+  for (int w0 = 0; w0 < nWords; w0 += 32)
+    visit_runs(col, M, nWords, w0, lane, carryEnd, [&](int, int n, int) { bytes += p3_run_bytes(n); });
+  return __reduce_add_sync(kFull, bytes);
+}
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) p3_count_kernel(const uint32_t *ycols, int wpc, int M, int N,
                                                                         int32_t *colBytes) {
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (k >= N) return;
-  const uint32_t *col = ycols + (size_t)k * wpc;
-  const int nWords = (M + 31) / 32;
-  int carryEnd = -1, bytes = 0;
-  for (int w0 = 0; w0 < nWords; w0 += 32)
-    visit_runs(col, M, nWords, w0, lane, carryEnd, [&](int, int n, int) { bytes += p3_run_bytes(n); });
-  bytes = __reduce_add_sync(kFull, bytes);
+  const int bytes = count_column(ycols + (size_t)k * wpc, M, lane);
   if (lane == 0) colBytes[k] = bytes;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) p3_emit_kernel(const uint32_t *ycols, int wpc, int M, int N,
-                                                                       const int64_t *colBase, uint8_t *yz) {
-  const int lane = threadIdx.x & 31;
-  const int k = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (k >= N) return;
-  const uint32_t *col = ycols + (size_t)k * wpc;
+// the bytes of one bit column (global or shared memory), by one warp
+__device__ __forceinline__ void emit_column(const uint32_t *col, int M, uint8_t *out, int lane) {
   const int nWords = (M + 31) / 32;
-  uint8_t *out = yz + colBase[k];
   int carryEnd = -1;
   int chunkBase = 0;
   for (int w0 = 0; w0 < nWords; w0 += 32) {
@@ -95,6 +94,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) p3_emit_kernel(const uint
     visit_runs(col, M, nWords, w0, lane, carryEnd, [&](int v, int n, int) { off += p3_run_emit(out + off, v, n); });
     chunkBase += total;
   }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) p3_emit_kernel(const uint32_t *ycols, int wpc, int M, int N,
+                                                                       const int64_t *colBase, uint8_t *yz) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (k >= N) return;
+  emit_column(ycols + (size_t)k * wpc, M, yz + colBase[k], lane);
 }
 
 // Exclusive scan of int32 counts into int64 offsets, out[n] = total. Single block.
@@ -131,6 +138,136 @@ __global__ void __launch_bounds__(1024) scan_i32_to_i64_kernel(const int32_t *in
     __syncthreads();
   }
   if (tid == 0) out[n] = carryS;
+}
+
+// ---- encode from run lists (the sweep kernel's fused run detection, sweep.cuh: SweepArgs::p3Out) ----
+// window of column k for the window layout of sweep.cuh:window_range
+__device__ __forceinline__ int window_of(int k, int spw, int first, int second) {
+  if (first <= 0) return k / spw;
+  if (k < first) return 0;
+  if (k < first + second) return 1;
+  return 2 + (k - first - second) / spw;
+}
+
+constexpr int kRunWarps = 8;
+constexpr int kP3SortedRunsPerSite = 256;  // more heads than this in a site: rebuild its column instead of ranking them
+
+// The sorted column of a site rebuilt in shared memory from its run heads, for sites with too many heads to rank: the
+// heads' positions are a bitmap (that IS their sorted order), and since the allele flips at every head but the first,
+// y[p] = y[0] ^ parity(heads in [1, p]): a prefix-xor inside each word plus a carry across the words.
+__device__ __forceinline__ void column_from_heads(const uint32_t *e, int cnt, int M, uint32_t *col, int lane) {
+  const int nWords = (M + 31) / 32;
+  for (int w = lane; w < nWords; w += 32) col[w] = 0u;
+  __syncwarp();
+  uint32_t y0 = 0u;
+  for (int i = lane; i < cnt; i += 32) {
+    const uint32_t h = e[i];
+    const int pos = (int)(h >> 1);
+    if (pos == 0) y0 = h & 1u;
+    else atomicOr(&col[pos >> 5], 1u << (pos & 31));
+  }
+  y0 = __reduce_or_sync(kFull, y0);
+  __syncwarp();
+  const int per = (nWords + 31) / 32;  // consecutive words per lane
+  const int wLo = min(lane * per, nWords), wHi = min(wLo + per, nWords);
+  uint32_t par = 0u;
+  for (int w = wLo; w < wHi; ++w) par ^= __popc(col[w]) & 1u;
+  uint32_t inc = par;  // parity of the heads in the words of the lanes up to and including this one
+#pragma unroll
+  for (int dl = 1; dl < 32; dl <<= 1) {
+    const uint32_t t = __shfl_up_sync(kFull, inc, dl);
+    if (lane >= dl) inc ^= t;
+  }
+  uint32_t carry = (inc ^ par) ^ y0;  // allele just before this lane's first word
+  for (int w = wLo; w < wHi; ++w) {
+    uint32_t x = col[w];
+    x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16;  // bit j = parity of the heads at bits 0 .. j
+    if (carry) x = ~x;
+    col[w] = x;
+    carry = x >> 31;
+  }
+  __syncwarp();
+}
+
+// One warp per site.  Its run heads arrive in no particular order.  Few heads (the rule once the PBWT order has formed): rank
+// them by position -- each lane counts the heads below its own --, leave them sorted in place, and count the bytes of
+// the runs between them.  Many heads (the first sites of a panel, dense columns): rebuild the column and count as the
+// encoder over columns does.
+__global__ void __launch_bounds__(kRunWarps * 32) p3_count_runs_kernel(uint32_t *runs, long long cap, const int32_t *siteOff,
+                                                                        const int32_t *siteCnt, int M, int N, int spw, int first,
+                                                                        int second, int32_t *colBytes, int *overflow) {
+  __shared__ uint32_t buf[kRunWarps][kP3MaxRunsPerSite];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.x * kRunWarps + warp;
+  if (k >= N) return;
+  const int cnt = siteCnt[k];
+  if ((long long)siteOff[k] + cnt > cap) {  // the sweep dropped heads of this window
+    if (lane == 0) { *overflow = 1; colBytes[k] = 0; }
+    return;
+  }
+  uint32_t *e = runs + (size_t)window_of(k, spw, first, second) * cap + siteOff[k];
+  uint32_t *so = buf[warp];
+  if (cnt > kP3SortedRunsPerSite) {
+    column_from_heads(e, cnt, M, so, lane);
+    const int bytes = count_column(so, M, lane);
+    if (lane == 0) colBytes[k] = bytes;
+    return;
+  }
+  uint32_t *raw = so + kP3SortedRunsPerSite;  // the list as it arrived, staged once (ranking reads it cnt times)
+  for (int i = lane; i < cnt; i += 32) raw[i] = e[i];
+  __syncwarp();
+  for (int i = lane; i < cnt; i += 32) {
+    const uint32_t mine = raw[i];
+    int rank = 0;
+    for (int j = 0; j < cnt; ++j) rank += raw[j] < mine;  // (positions are distinct; raw[j] is a broadcast)
+    so[rank] = mine;
+  }
+  __syncwarp();
+  int bytes = 0;
+  for (int i = lane; i < cnt; i += 32) {
+    const uint32_t v = so[i];
+    e[i] = v;
+    const int next = i + 1 < cnt ? (int)(so[i + 1] >> 1) : M;
+    bytes += p3_run_bytes(next - (int)(v >> 1));
+  }
+  bytes = __reduce_add_sync(kFull, bytes);
+  if (lane == 0) colBytes[k] = bytes;
+}
+
+__global__ void __launch_bounds__(kRunWarps * 32) p3_emit_runs_kernel(const uint32_t *runs, long long cap, const int32_t *siteOff,
+                                                                       const int32_t *siteCnt, int M, int N, int spw, int first,
+                                                                       int second, const int64_t *colBase, uint8_t *yz) {
+  __shared__ uint32_t buf[kRunWarps][kP3MaxRunsPerSite];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.x * kRunWarps + warp;
+  if (k >= N) return;
+  const int cnt = siteCnt[k];
+  const uint32_t *e = runs + (size_t)window_of(k, spw, first, second) * cap + siteOff[k];
+  uint8_t *out = yz + colBase[k];
+  if (cnt > kP3SortedRunsPerSite) {
+    column_from_heads(e, cnt, M, buf[warp], lane);
+    emit_column(buf[warp], M, out, lane);
+    return;
+  }
+  int chunkBase = 0;
+  for (int i0 = 0; i0 < cnt; i0 += 32) {  // 32 runs per step (sorted by the count pass): byte counts, prefix offsets, bytes
+    const int i = i0 + lane;
+    int v = 0, len = 0;
+    if (i < cnt) {
+      const uint32_t h = e[i];
+      v = (int)(h & 1u);
+      len = (i + 1 < cnt ? (int)(e[i + 1] >> 1) : M) - (int)(h >> 1);
+    }
+    const int nb = p3_run_bytes(len);
+    int x = nb;
+#pragma unroll
+    for (int dl = 1; dl < 32; dl <<= 1) {
+      const int t = __shfl_up_sync(kFull, x, dl);
+      if (lane >= dl) x += t;
+    }
+    if (len) p3_run_emit(out + chunkBase + x - nb, v, len);
+    chunkBase += __shfl_sync(kFull, x, 31);
+  }
 }
 
 // ---- decode ---------------------------------------------------------------------------------
@@ -281,23 +418,49 @@ __global__ void bits_to_bytes_kernel(const uint32_t *ycols, int M, int N, int wp
 
 }  // namespace
 
+static int scan_col_bytes(int32_t *colBytes, int64_t *colBase, int N, void *scratch, size_t scratchBytes, cudaStream_t stream);
+
 int p3_count_columns(const uint32_t *ycols, int wpc, int M, int N, int32_t *colBytes, int64_t *colBase, void *scratch,
                      size_t scratchBytes, cudaStream_t stream) {
   if (N > 0) {
     p3_count_kernel<<<(N + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, stream>>>(ycols, wpc, M, N,
                                                                                                    colBytes);
   }
+  return scan_col_bytes(colBytes, colBase, N, scratch, scratchBytes, stream);
+}
+
+// exclusive 64-bit scan of the per-column byte counts, colBase[N] = total
+static int scan_col_bytes(int32_t *colBytes, int64_t *colBase, int N, void *scratch, size_t scratchBytes, cudaStream_t stream) {
   if (N < 4096 || !scratch) {  // short streams: one block is quicker than a library scan
     scan_i32_to_i64_kernel<<<1, 1024, 0, stream>>>(colBytes, colBase, N);
     return (int)cudaGetLastError();
   }
-  // exclusive 64-bit scan of N counts plus a trailing zero, so that colBase[N] = total (CUB)
+  // N counts plus a trailing zero (CUB)
   cudaError_t err = cudaMemsetAsync(colBytes + N, 0, sizeof(int32_t), stream);
   if (err != cudaSuccess) return (int)err;
   return launch_segment_scan(colBytes, (long long)N + 1, reinterpret_cast<long long *>(colBase), scratch, scratchBytes, stream);
 }
 
 size_t p3_scan_scratch_bytes(int N) { return segment_scan_temp_bytes((long long)N + 1); }
+
+int p3_count_runs(uint32_t *runs, long long cap, const int32_t *siteOff, const int32_t *siteCnt, int M, int N, int spw, int first,
+                  int second, int32_t *colBytes, int64_t *colBase, void *scratch, size_t scratchBytes, int *overflow, cudaStream_t stream) {
+  if (N > 0) {
+    p3_count_runs_kernel<<<(N + kRunWarps - 1) / kRunWarps, kRunWarps * 32, 0, stream>>>(runs, cap, siteOff, siteCnt, M, N, spw, first, second,
+                                                                                       colBytes, overflow);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return (int)err;
+  }
+  return scan_col_bytes(colBytes, colBase, N, scratch, scratchBytes, stream);
+}
+
+int p3_emit_runs(const uint32_t *runs, long long cap, const int32_t *siteOff, const int32_t *siteCnt, int M, int N, int spw, int first,
+                 int second, const int64_t *colBase, uint8_t *yz, cudaStream_t stream) {
+  if (N > 0)
+    p3_emit_runs_kernel<<<(N + kRunWarps - 1) / kRunWarps, kRunWarps * 32, 0, stream>>>(runs, cap, siteOff, siteCnt, M, N, spw, first, second,
+                                                                                      colBase, yz);
+  return (int)cudaGetLastError();
+}
 
 int p3_emit_columns(const uint32_t *ycols, int wpc, int M, int N, const int64_t *colBase, uint8_t *yz,
                     cudaStream_t stream) {

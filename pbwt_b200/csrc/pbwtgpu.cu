@@ -34,6 +34,8 @@ struct pbwtgpu_ctx {
   long long optNoSortPass1 = 0;  // testing: pass 1 by sweeping even where the window sort applies
   long long optNoCluster = 0;    // testing: wide panels through the cooperative-grid path even where clusters fit
   long long optNoSortCombine = 0;  // testing: window combines by sweeping pseudo-sites even where the sort applies
+  long long optNoFusedPack3 = 0;   // testing: sorted columns to global memory + the stand-alone encoder even where the sweep encodes
+  long long optPack3Cap = 0;       // testing: bytes per window of the fused encoder's output (0 = automatic)
   // profiling
   bool profile = false;
   float ms[PBWTGPU_NUM_KERNEL_CLASSES] = {0};
@@ -719,9 +721,28 @@ struct WindowedSweep {
     if (int rc = result_alloc(ctx, res, &res->aEnd, (size_t)M)) return rc;
     if (wantD)
       if (int rc = result_alloc(ctx, res, &res->dEnd, (size_t)M + 1)) return rc;
+    // pack3: run detection fused into the sweep where the shared-memory kernel builds from panel columns (every window
+    // appends its columns' run heads to its own region; pack3.cu formats the bytes from those lists), else the sorted
+    // columns go to global memory for the encoder over columns (wide panels, -longWithin, and the fallback when a window
+    // outgrows its region or a column has more runs than the list pass takes)
+    bool fusedP3 = wantYz && N > 0 && !useGlobal && mode == kGather && matchMode != 2 && !xOutRev && !ctx->optNoFusedPack3;
     uint32_t *yOut = nullptr;
-    if (wantYz && N > 0)
+    uint32_t *p3Out = nullptr;
+    int32_t *p3Count = nullptr;  // [W] run heads per window, [W] = overflow flag
+    int32_t *p3SiteOff = nullptr, *p3SiteCnt = nullptr;
+    long long p3Cap = 0;  // run heads per window
+    if (fusedP3) {
+      const long long sitesMax = std::max(spw, std::max(firstSites, secondSites));
+      // (the first sites of a panel, before the order has formed, have thousands of runs each; later ones a few dozen)
+      p3Cap = ctx->optPack3Cap > 0 ? ctx->optPack3Cap : std::min<long long>(sitesMax * (long long)M, std::max<long long>(256 << 10, sitesMax * 512));
+      if (int rc = tmp.get(&p3Out, (size_t)W * (size_t)p3Cap)) return rc;
+      if (int rc = tmp.get(&p3Count, (size_t)W + 1)) return rc;
+      if (int rc = tmp.get(&p3SiteOff, (size_t)N)) return rc;
+      if (int rc = tmp.get(&p3SiteCnt, (size_t)N)) return rc;
+      if (W + 8 > pbwtgpu_ctx::kPinnedWords) return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "too many windows");
+    } else if (wantYz && N > 0) {
       if (int rc = tmp.get(&yOut, (size_t)N * wpc)) return rc;
+    }
 
     unsigned long long *recCount = nullptr;
     int *chunkCounter = nullptr, *chunkTab = nullptr;
@@ -782,7 +803,12 @@ struct WindowedSweep {
     // pinned readback layout: [0] chunks used, [1] pack3 bytes, [2] segment total, [3 ...] per-window record counts
     unsigned long long *pin = ctx->pinned;
     if (W + 3 > pbwtgpu_ctx::kPinnedWords) return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "too many windows");
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    bool poolGrown = false;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+      a.yOut = yOut;
+      a.p3Out = fusedP3 ? p3Out : nullptr; a.p3Cap = p3Cap; a.p3Count = p3Count; a.p3Overflow = fusedP3 ? p3Count + W : nullptr;
+      a.p3SiteOff = p3SiteOff; a.p3SiteCnt = p3SiteCnt;
+      if (fusedP3) CUDA_TRY(ctx, cudaMemsetAsync(p3Count, 0, sizeof(int32_t) * ((size_t)W + 1), ctx->stream));
       if (wantMatch && !statsOnly) {
         poolChunks = (int)((recCap + kRecChunk - 1) >> kRecChunkLog) + producers;
         if (int rc = tmp.get(&pool, (size_t)poolChunks << kRecChunkLog)) return rc;
@@ -800,7 +826,17 @@ struct WindowedSweep {
         ctx->launches[PBWTGPU_K_SWEEP] += 1;
       }
       pin[0] = pin[1] = pin[2] = 0;
-      if (wantYz && attempt == 0) {  // (a rerun rewrites the same sorted columns)
+      int32_t *pinP3 = reinterpret_cast<int32_t *>(&pin[3 + W]);  // [0] the overflow flag of the run lists
+      if (fusedP3) {  // sort every site's run heads, count the bytes; the flag comes back with the other counters
+        ScopedTimer t(ctx, PBWTGPU_K_PACK3);
+        char *scanScratch = nullptr;
+        const size_t scanBytes = p3_scan_scratch_bytes(N);
+        if (int rc = tmp.get(&scanScratch, scanBytes)) return rc;
+        CUDA_TRY(ctx, p3_count_runs(p3Out, p3Cap, p3SiteOff, p3SiteCnt, M, N, spw, firstSites, secondSites, colBytes, colBase, scanScratch,
+                                    scanBytes, p3Count + W, ctx->stream));
+        ctx->launches[PBWTGPU_K_PACK3] += 2;
+        CUDA_TRY(ctx, cudaMemcpyAsync(pinP3, p3Count + W, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      } else if (wantYz) {  // (a rerun rewrites the same sorted columns; counting them again is cheap)
         ScopedTimer t(ctx, PBWTGPU_K_PACK3);
         char *scanScratch = nullptr;
         const size_t scanBytes = p3_scan_scratch_bytes(N);
@@ -821,16 +857,28 @@ struct WindowedSweep {
         CUDA_TRY(ctx, cudaMemcpyAsync(&pin[0], chunkCounter, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
       }
       if (wantMatch || wantYz) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-      if (!wantMatch || statsOnly) break;
-      const int used = (int)(pin[0] & 0xffffffffull);
-      segTotal = (long long)pin[2];
-      if (!useGlobal)
-        for (int w = 0; w < W; ++w) counts[w] = pin[3 + w];
-      if (used <= poolChunks) break;
-      if (attempt == 1) return fail(ctx, PBWTGPU_ERR_CUDA, "match record pool overflow persisted");
-      long long total = segTotal;  // the pool was too small: every count is known now, size it exactly and rerun
-      for (auto cnt : counts) total += (long long)cnt;
-      recCap = total;
+      bool again = false;
+      if (fusedP3 && pinP3[0]) {  // a window outgrew its region (or a column the list pass): sorted columns to global memory instead
+        fusedP3 = false;
+        if (int rc = tmp.get(&yOut, (size_t)N * wpc)) return rc;
+        again = true;
+      }
+      if (wantMatch && !statsOnly) {
+        const int used = (int)(pin[0] & 0xffffffffull);
+        segTotal = (long long)pin[2];
+        if (!useGlobal)
+          for (int w = 0; w < W; ++w) counts[w] = pin[3 + w];
+        if (used > poolChunks) {
+          if (poolGrown) return fail(ctx, PBWTGPU_ERR_CUDA, "match record pool overflow persisted");
+          long long total = segTotal;  // the pool was too small: every count is known now, size it exactly and rerun
+          for (auto cnt : counts) total += (long long)cnt;
+          recCap = total;
+          poolGrown = true;
+          again = true;
+        }
+      }
+      if (!again) break;
+      if (attempt == 2) return fail(ctx, PBWTGPU_ERR_CUDA, "sweep output buffers overflowed three times");
     }
     const int64_t yzTotal = (int64_t)pin[1];
     if (winNanos) {
@@ -880,8 +928,13 @@ struct WindowedSweep {
       res->nyz = yzTotal;
       if (int rc = result_alloc(ctx, res, &res->yz, (size_t)yzTotal)) return rc;
       ScopedTimer t(ctx, PBWTGPU_K_PACK3);
-      CUDA_TRY(ctx, p3_emit_columns(yOut, wpc, M, N, colBase, res->yz, ctx->stream));
-      ctx->launches[PBWTGPU_K_PACK3] += (N > 0);
+      if (fusedP3) {
+        CUDA_TRY(ctx, p3_emit_runs(p3Out, p3Cap, p3SiteOff, p3SiteCnt, M, N, spw, firstSites, secondSites, colBase, res->yz, ctx->stream));
+        ctx->launches[PBWTGPU_K_PACK3] += 1;
+      } else {
+        CUDA_TRY(ctx, p3_emit_columns(yOut, wpc, M, N, colBase, res->yz, ctx->stream));
+        ctx->launches[PBWTGPU_K_PACK3] += (N > 0);
+      }
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // temporaries go back to the cache with this object
     return 0;
@@ -1096,6 +1149,8 @@ int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value) {
   else if (!strcmp(name, "force_global")) ctx->optForceGlobal = value;
   else if (!strcmp(name, "no_cluster")) ctx->optNoCluster = value;
   else if (!strcmp(name, "no_sort_combine")) ctx->optNoSortCombine = value;
+  else if (!strcmp(name, "no_fused_pack3")) ctx->optNoFusedPack3 = value;
+  else if (!strcmp(name, "pack3_window_capacity")) ctx->optPack3Cap = value;
   else if (!strcmp(name, "long_within")) ctx->optLongT = value;
   else if (!strcmp(name, "no_sort_pass1")) ctx->optNoSortPass1 = value;
   else if (!strcmp(name, "equal_windows")) ctx->optEqualWindows = value;

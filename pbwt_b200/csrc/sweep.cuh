@@ -51,6 +51,15 @@ struct SweepArgs {
   int32_t *dEnd;          // [W][M+1]
   int endOnlyLast;
   uint32_t *yOut;         // [N][wpc] sorted columns y_k (input to the pack3 encoder), or NULL
+  // pack3 run detection fused into the sweep (shared-memory kernel, gather mode): window w appends the run heads of its
+  // columns, (position << 1 | allele), to p3Out + w * p3Cap -- site k's at offset p3SiteOff[k], p3SiteCnt[k] of them, in
+  // no particular order -- and leaves their number in p3Count[w]; heads beyond p3Cap are dropped and p3Overflow[0] is set
+  // (the host then falls back to yOut + the encoder over sorted columns).  pack3.cu turns the lists into bytes.
+  uint32_t *p3Out;
+  long long p3Cap;
+  int32_t *p3Count;
+  int32_t *p3SiteOff, *p3SiteCnt;  // [N]
+  int *p3Overflow;
   int32_t *cOut;          // [N] zero counts c_k, or NULL
   uint32_t *xOut;         // sorted mode: [N][wpc] the UN-sorted columns x_k (bit a_k[i] = y_k[i]), written in REVERSE
                           // site order (row N-1-k): the input of the reverse build (pbwtCore.c:170-175); or NULL.
@@ -108,6 +117,7 @@ int sweep_smem_max_m(bool with_d);
 // returns cudaError_t as int
 // match_mode: 0 none, 1 matchMaximalWithin, 2 matchLongWithin2 with args.longT (both imply d)
 int launch_sweep_smem(const SweepArgs &args, SweepMode mode, bool with_d, int match_mode, cudaStream_t stream);
+// (args.p3Out != NULL selects the kernels with the fused pack3 encoder: gather mode, match_mode 0 or 1)
 // query sweep: panel columns in args.src (sorted mode), queries in args.qcols; records go through the chunk pool
 int query_sweep_max_m();
 int query_sweep_max_q(int M);

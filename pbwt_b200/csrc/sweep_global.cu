@@ -444,6 +444,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
   int cur = 0;
   for (int k = k0; k < k1; ++k) {
     const uint32_t *col = src + (size_t)(k + colShift) * wpc;
+    if (!WITH_D) asm volatile("" : "+l"(col));  // (keeps the pointer in registers: rematerialised, it costs a multiply-add per
+                                                // gathered word; with d the registers are needed elsewhere)
     const int32_t *aC = aW + (size_t)cur * MS;
     int32_t *aN = aW + (size_t)(cur ^ 1) * MS;
     const int32_t *dC = WITH_D ? dW + (size_t)cur * (MS + 4) : nullptr;
@@ -471,13 +473,16 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
       constexpr int NB = decltype(nbTag)::value;
       int hB[NB], dB[NB];
       uint32_t cB[NB];
-      const unsigned iBase = (unsigned)(posBase + e0 * 32 + lane);
+      // one 64-bit address per batch, the words of the batch at immediate offsets (an index per load costs four more
+      // instructions of address arithmetic each)
+      const int iBase = posBase + e0 * 32 + lane;
+      const int32_t *aP = aC + iBase;
+      const int32_t *dP = WITH_D ? dC + iBase : nullptr;
 #pragma unroll
       for (int u = 0; u < NB; ++u) {
-        const unsigned i = iBase + u * 32;
-        const bool valid = FULL || (int)i < M;
-        hB[u] = ((MODE == kGather || p.xOut) && valid) ? __ldcg(aC + i) : 0;
-        dB[u] = (WITH_D && valid) ? __ldcg(dC + i) : 0;
+        const bool valid = FULL || iBase + u * 32 < M;
+        hB[u] = ((MODE == kGather || p.xOut) && valid) ? __ldcg(aP + u * 32) : 0;
+        dB[u] = (WITH_D && valid) ? __ldcg(dP + u * 32) : 0;
       }
 #pragma unroll
       for (int u = 0; u < NB; ++u) {
@@ -672,12 +677,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
         constexpr bool FULL = decltype(fullTag)::value;
         constexpr int NB = decltype(nbTag)::value;
         int hB[NB];
-        const unsigned iBase = (unsigned)(p0 + (wordBase + e0) * 32 + lane);
+        const int iBase = p0 + (wordBase + e0) * 32 + lane;
+        const int32_t *aP = aC + iBase;
 #pragma unroll
-        for (int u = 0; u < NB; ++u) {
-          const unsigned i = iBase + u * 32;
-          hB[u] = (FULL || (int)i < M) ? __ldcg(aC + i) : 0;
-        }
+        for (int u = 0; u < NB; ++u) hB[u] = (FULL || iBase + u * 32 < M) ? __ldcg(aP + u * 32) : 0;
 #pragma unroll
         for (int u = 0; u < NB; ++u) {
           const int e = e0 + u;

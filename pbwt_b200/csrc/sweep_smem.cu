@@ -36,7 +36,7 @@ namespace {
 constexpr int kThreads = 1024;
 constexpr int kStages = 3;
 
-template <int E, bool WITH_D, bool MATCH, bool QUERY = false>
+template <int E, bool WITH_D, bool MATCH, bool QUERY = false, bool P3 = false>
 struct SmemLayout {  // offsets in 32-bit words; every array start is 16-byte aligned
   static constexpr int MP = kThreads * E;
   static constexpr int WORDS = 32 * E;
@@ -49,7 +49,9 @@ struct SmemLayout {  // offsets in 32-bit words; every array start is 16-byte al
   static constexpr int xcol = ycol + WORDS;
   static constexpr int xs = xcol + kStages * STAGE;  // un-sorted column being assembled (XOUT kernels)
   static constexpr int wsum = xs + WORDS;
-  static constexpr int mbar = wsum + 3 * 32;
+  static constexpr int p3s = wsum + 3 * 32;  // fused pack3: run heads emitted per site (four rotating counters), and the
+                                             // allele before each warp's first position [32]
+  static constexpr int mbar = p3s + (P3 ? 4 + 32 : 0);
   static constexpr int wmax = mbar + 8;  // room for up to 4 mbarriers, keeps 16-byte alignment
   static constexpr int cmask = wmax + (MATCH ? WORDS : 0);  // per-word maxima of d (skip structure for long blocks)
   static constexpr int res = cmask + (MATCH ? WORDS : 0);       // per-word candidate masks, then result slots
@@ -91,9 +93,16 @@ __device__ __forceinline__ uint32_t ybit(const uint32_t *yc, int j) { return (yc
 
 // MATCH: 0 = none, 1 = matchMaximalWithin (pbwtMatch.c:115-142), 2 = matchLongWithin2 (-longWithin L, pbwtMatch.c:85-113)
 // XOUT: also un-sort every column into p.xOut (sorted mode, no d, no matches: the forward half of pbwtBuildReverse)
-template <int E, int MODE, bool WITH_D, int MATCH, bool QUERY = false, bool XOUT = false>
+// P3: run detection of the pack3 encoder (pbwtCore.c:240-277) fused into the sweep.  The sorted column y_k never goes to
+// global memory; instead every lane that owns a word of it appends the word's run heads -- (position << 1 | allele), a few
+// dozen per site -- to the window's run list, slots drawn from a shared-memory counter.  No cross-warp prefix, no extra
+// barrier: anything more (byte counts need the NEXT head, offsets need a scan over the warps) was measured to sit on the
+// site's critical path, because PBWT order concentrates a column's heads in a few warps (+0.6 ms on 4.1 ms for the full
+// in-kernel encoder, against 0.4 ms for encoding the sorted columns afterwards).  pack3.cu sorts each site's few heads
+// and formats the bytes from the run lists (about 3 % of the sorted columns' volume).
+template <int E, int MODE, bool WITH_D, int MATCH, bool QUERY = false, bool XOUT = false, bool P3 = false>
 __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs p) {
-  using L = SmemLayout<E, WITH_D, MATCH != 0, QUERY>;
+  using L = SmemLayout<E, WITH_D, MATCH != 0, QUERY, P3>;
   extern __shared__ __align__(16) uint32_t smem[];
   int32_t *const sI = reinterpret_cast<int32_t *>(smem);
   int32_t *const wsumZ = sI + L::wsum;
@@ -166,6 +175,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
       }
   }
 
+  int32_t *const p3Cnt = sI + L::p3s;  // run heads of the site being swept / of the three sites before it (rotating)
+  uint32_t *const p3Pb = smem + L::p3s + 4;  // allele before each warp's first position at the site being swept
+  uint32_t *const p3Dst = P3 ? p.p3Out + (size_t)win * p.p3Cap : nullptr;
+  int p3Base = 0;  // run heads of this window so far (uniform)
+  if (P3 && tid < 4) p3Cnt[tid] = 0;  // (published by the barrier that follows the mbarrier set-up)
+
   int32_t *const ctabS = sI + L::ctab;
   RecSink sink;
   sink.pool = (MATCH || QUERY) ? reinterpret_cast<int4 *>(p.recPool) : nullptr;
@@ -227,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
       } else pb = col[wordBase - 1] >> 31;
     }
     const uint32_t pbFirst = pb;
-    const bool storeY = lane == 0 && (MATCH || QUERY || p.yOut != nullptr);  // the sorted column, when someone consumes it
+    const bool storeY = lane == 0 && (MATCH || QUERY || P3 || p.yOut != nullptr);  // the sorted column, when someone consumes it
     int carry = 0;         // max d since the last run head, over completed words (uniform)
     int lmax = 0;          // per-lane max of d over head-free words since then (reduced lazily)
     bool anyHead = false;  // has this warp seen a run head
@@ -313,6 +328,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     if (lane == 0) {
       wsumZ[warp] = zw;
       if (WITH_D) wsumR[warp] = (anyHead ? 0x80000000u : 0u) | (uint32_t)carry;
+      if (P3) p3Pb[warp] = pbFirst;  // (read back after S2 of this site, rewritten after S2 of this site at the earliest)
     }
     if (MATCH == 2) {
       if (lane < E) cmaskS[wordBase + lane] = longMask;
@@ -408,6 +424,41 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     // ---------------- matchMaximalWithin on state k (holds the S2 barrier) ----------------
     if (MATCH) match_rounds(sI + aC, sI + dC, yc, k, true);
     else if (!QUERY) __syncthreads();  // S2: scatter complete
+    // ---------------- fused pack3: this site's run heads to the window's run list ----------------
+    // After S2, in the shadow of the match rounds' record emission (the warps that write records are dealt by candidate
+    // number, the heads sit wherever the minor alleles are): every lane that owns a word of y_k appends the word's run
+    // heads; slots come from a shared-memory counter, so there is no cross-warp prefix and no extra barrier.  The count
+    // of site k is final at S1 of site k + 1 and booked one site later.
+    if (P3) {
+      if (it > 0) {
+        const int cnt = p3Cnt[(it - 1) & 3];  // the site before: everyone appended before this site's S1
+        if (tid == 0) {
+          p.p3SiteOff[k - 1 + colShift] = p3Base;
+          p.p3SiteCnt[k - 1 + colShift] = cnt;
+          p3Cnt[(it + 2) & 3] = 0;  // read for the last time two barriers ago; the site after next appends to it
+        }
+        p3Base += cnt;
+      }
+      if (lane < E && (!WITH_D || anyHead)) {  // (with d, phase A already knows whether a run starts among this warp's positions)
+        const int wd = wordBase + lane, base = wd * 32;
+        if (base < M) {
+          const uint32_t cw = yc[wd];  // (own words: the next site's phase A of this very warp overwrites them, later)
+          const uint32_t pw = lane > 0 ? yc[wd - 1] >> 31 : (warp == 0 ? (~cw & 1u) : p3Pb[warp]);  // position 0 always heads a run
+          uint32_t h = cw ^ ((cw << 1) | pw);
+          if (M - base < 32) h &= (1u << (M - base)) - 1u;  // pad positions (all ones) are not part of the column
+          if (h) {
+            int o = p3Base + atomicAdd(&p3Cnt[it & 3], __popc(h));
+            do {
+              const int j = __ffs(h) - 1;
+              h &= h - 1;
+              if (o < p.p3Cap) p3Dst[o] = ((uint32_t)(base + j) << 1) | ((cw >> j) & 1u);
+              else *p.p3Overflow = 1;
+              ++o;
+            } while (h);
+          }
+        }
+      }
+    }
     if (QUERY) {
       // ---------------- matchSequencesSweep on state k (pbwtMatch.c:376-426), one thread per query ----------------
       constexpr int qaC = CUR ? L::qa1 : L::qa0, qaN = CUR ? L::qa0 : L::qa1;
@@ -572,6 +623,16 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     match_rounds(sI + aC, sI + dC, yc, nTotal, false);
   }
   if (MATCH && p.recCount && tid == 0) p.recCount[win] = (unsigned long long)recBase;
+  if (P3 && tid == 0) {  // the last site's heads (everyone appended before the barrier at the window's end)
+    int total = p3Base;
+    if (k1 > k0) {
+      const int cnt = p3Cnt[(k1 - k0 - 1) & 3];
+      p.p3SiteOff[k1 - 1 + colShift] = p3Base;
+      p.p3SiteCnt[k1 - 1 + colShift] = cnt;
+      total += cnt;
+    }
+    p.p3Count[win] = total;
+  }
   if (p.winNanos && tid == 0) {
     long long tEnd;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tEnd));
@@ -579,32 +640,32 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
   }
 }
 
-template <int E, int MODE, bool WITH_D, int MATCH>
+template <int E, int MODE, bool WITH_D, int MATCH, bool P3 = false>
 int launch_one(const SweepArgs &a, cudaStream_t stream) {
-  using L = SmemLayout<E, WITH_D, MATCH != 0>;
+  using L = SmemLayout<E, WITH_D, MATCH != 0, false, P3>;
   static_assert(L::bytes <= 232448, "shared memory layout exceeds the 227 KB per-CTA limit");
   static_assert(kStages <= 4 && L::xcol % 4 == 0 && L::mbar % 2 == 0 && L::res % 4 == 0 && L::d0 % 4 == 0 && L::d1 % 4 == 0,
                 "shared memory arrays must keep their alignment");
-  auto kern = sweep_smem_kernel<E, MODE, WITH_D, MATCH>;
+  auto kern = sweep_smem_kernel<E, MODE, WITH_D, MATCH, false, false, P3>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
   if (err != cudaSuccess) return (int)err;
   kern<<<a.nWindows, kThreads, L::bytes, stream>>>(a);
   return (int)cudaGetLastError();
 }
 
-template <int MODE, bool WITH_D, int MATCH>
+template <int MODE, bool WITH_D, int MATCH, bool P3 = false>
 int launch_e(const SweepArgs &a, cudaStream_t stream) {
   const int words = (a.M + 31) / 32;
   const int e = (words + 31) / 32;
-  if (e <= 1) return launch_one<1, MODE, WITH_D, MATCH>(a, stream);
-  if (e <= 2) return launch_one<2, MODE, WITH_D, MATCH>(a, stream);
-  if (e <= 4) return launch_one<4, MODE, WITH_D, MATCH>(a, stream);
-  if (e <= 7) return launch_one<7, MODE, WITH_D, MATCH>(a, stream);
-  if (e <= 10) return launch_one<10, MODE, WITH_D, MATCH>(a, stream);
-  if (e <= 13) return launch_one<13, MODE, WITH_D, MATCH>(a, stream);
+  if (e <= 1) return launch_one<1, MODE, WITH_D, MATCH, P3>(a, stream);
+  if (e <= 2) return launch_one<2, MODE, WITH_D, MATCH, P3>(a, stream);
+  if (e <= 4) return launch_one<4, MODE, WITH_D, MATCH, P3>(a, stream);
+  if (e <= 7) return launch_one<7, MODE, WITH_D, MATCH, P3>(a, stream);
+  if (e <= 10) return launch_one<10, MODE, WITH_D, MATCH, P3>(a, stream);
+  if (e <= 13) return launch_one<13, MODE, WITH_D, MATCH, P3>(a, stream);
   if constexpr (!WITH_D) {
-    if (e <= 19) return launch_one<19, MODE, WITH_D, MATCH>(a, stream);
-    if (e <= 25) return launch_one<25, MODE, WITH_D, MATCH>(a, stream);
+    if (e <= 19) return launch_one<19, MODE, WITH_D, MATCH, P3>(a, stream);
+    if (e <= 25) return launch_one<25, MODE, WITH_D, MATCH, P3>(a, stream);
   }
   return (int)cudaErrorInvalidValue;
 }
@@ -666,6 +727,13 @@ int launch_sweep_smem(const SweepArgs &a, SweepMode mode, bool with_d, int match
     return launch_xout(a, stream);
   }
   if (match_mode == 2 && a.longT < 1) return (int)cudaErrorInvalidValue;
+  if (a.p3Out) {  // pack3 run detection fused into the sweep: builds from panel columns
+    if (mode != kGather || match_mode == 2 || !a.p3Count || !a.p3SiteOff || !a.p3SiteCnt || !a.p3Overflow || a.p3Cap < 1)
+      return (int)cudaErrorInvalidValue;
+    if (match_mode) return launch_e<kGather, true, 1, true>(a, stream);
+    if (with_d) return launch_e<kGather, true, 0, true>(a, stream);
+    return launch_e<kGather, false, 0, true>(a, stream);
+  }
   if (mode == kGather) {
     if (match_mode == 2) return launch_e<kGather, true, 2>(a, stream);
     if (match_mode) return launch_e<kGather, true, 1>(a, stream);

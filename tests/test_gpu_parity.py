@@ -435,6 +435,29 @@ def test_stats_histogram_consumed_on_device(eng, orc, M, N, W, dens, force_globa
     assert np.array_equal(hist, want) and np.array_equal(hist2, want)
 
 
+@pytest.mark.parametrize("opt,val", [("no_fused_pack3", 1), ("pack3_window_capacity", 48), ("pack3_window_capacity", 100000)])
+@pytest.mark.parametrize("M,N,W,dens", [(33, 40, 3, 0.5), (1000, 300, 7, 0.05), (1025, 120, 16, 0.5), (5000, 200, 37, 0.02), (12289, 90, 4, 0.3)])
+def test_pack3_fused_and_fallback_paths(eng, orc, M, N, W, dens, opt, val):
+    """The pack3 stream comes from the encoder fused into the sweep (every warp encodes the runs that start among its
+    positions); a window that outgrows its output region (capacity forced tiny here) sends the build back to the
+    stand-alone encoder over the sorted columns, which no_fused_pack3 selects directly.  All three must agree with the
+    reference byte for byte -- dense columns make warps overflow their 32-byte staging row (the re-encode path)."""
+    rng = np.random.default_rng(M + N + W)
+    hap = (rng.random((M, N)) < dens).astype(np.uint8)
+    hap[:, N // 2] = 0  # a monomorphic column: one run of length M
+    hap[M // 2:, N // 3] = 1
+    x = O.pack_panel(hap)
+    eng.set_option("windows", W)
+    eng.set_option(opt, val)
+    try:
+        check_build(eng, orc, x, M, N, matches=True)
+        got = eng.build(x, M, N, with_d=False, with_matches=False)
+        assert got["yz"].tobytes() == orc.build(x, M, N, with_d=False)[0].tobytes()
+    finally:
+        eng.set_option("windows", 0)
+        eng.set_option(opt, 0)
+
+
 def test_smem_limit_without_matches(eng, orc):
     """M between the match kernel's limit (12,544) and the shared-memory limit (13,312): a/d/pack3 only."""
     rng = np.random.default_rng(13)
