@@ -47,6 +47,7 @@ struct pbwtgpu_ctx {
   struct Block { void *p; size_t bytes; };
   std::vector<Block> freeBlocks;
   std::unordered_map<void *, size_t> liveBlocks;  // true size of every block handed out (a cached block may be larger than asked for)
+  size_t cacheCapBytes = (size_t)48 << 30;        // freed blocks kept for reuse: at most this much (60 % of the device's memory)
   int smCount = 0;
   // pinned host scratch for the few counters read back per sweep (one stream synchronisation instead of one per copy)
   unsigned long long *pinned = nullptr;
@@ -125,7 +126,7 @@ void dev_release(pbwtgpu_ctx *ctx, void *p, size_t /*bytesAskedFor*/) {
   if (it != ctx->liveBlocks.end()) { bytes = it->second; ctx->liveBlocks.erase(it); }
   size_t cached = 0;
   for (auto &b : ctx->freeBlocks) cached += b.bytes;
-  if (bytes && ctx->freeBlocks.size() < 64 && cached + bytes < ((size_t)48 << 30)) ctx->freeBlocks.push_back({p, bytes});
+  if (bytes && ctx->freeBlocks.size() < 64 && cached + bytes < ctx->cacheCapBytes) ctx->freeBlocks.push_back({p, bytes});
   else cudaFree(p);
 }
 
@@ -1098,6 +1099,7 @@ int pbwtgpu_init(int device, pbwtgpu_ctx **out) {
   pbwtgpu_ctx *ctx = new pbwtgpu_ctx;
   ctx->device = device;
   ctx->smCount = prop.multiProcessorCount;
+  ctx->cacheCapBytes = (size_t)(0.6 * (double)prop.totalGlobalMem);  // (config 4's temporaries alone are ~50 GB)
   if (cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return PBWTGPU_ERR_CUDA;
@@ -1137,6 +1139,7 @@ void *pbwtgpu_get_stream(pbwtgpu_ctx *ctx) { return ctx ? (void *)ctx->stream : 
 
 int pbwtgpu_synchronize(pbwtgpu_ctx *ctx) {
   if (!ctx) return PBWTGPU_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -1228,6 +1231,7 @@ int pbwtgpu_panel_synthetic_range(pbwtgpu_ctx *ctx, int M, int N, int first_site
 
 int pbwtgpu_panel_to_host(pbwtgpu_ctx *ctx, const pbwtgpu_panel *p, int first, int n, uint32_t *xbits) {
   if (!ctx || !p || first < 0 || n < 0 || first + n > p->N) return fail(ctx, PBWTGPU_ERR_ARG, "panel_to_host: bad range");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if (n)
     CUDA_TRY(ctx, cudaMemcpyAsync(xbits, p->bits + (size_t)first * p->wpc, (size_t)n * p->wpc * 4, cudaMemcpyDeviceToHost,
                                   ctx->stream));
@@ -1238,6 +1242,7 @@ int pbwtgpu_panel_to_host(pbwtgpu_ctx *ctx, const pbwtgpu_panel *p, int first, i
 void pbwtgpu_panel_free(pbwtgpu_ctx *ctx, pbwtgpu_panel *p) {
   if (!p) return;
   if (ctx) {
+    cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     dev_release(ctx, p->bits, (size_t)std::max(p->N, 1) * p->wpc * 4);
   }
@@ -1284,6 +1289,7 @@ int pbwtgpu_result_sizes(const pbwtgpu_result *r, int64_t *nyz, int64_t *nmatch)
 int pbwtgpu_result_fetch(pbwtgpu_ctx *ctx, const pbwtgpu_result *r, uint8_t *yz, int32_t *a_end, int32_t *d_end,
                          pbwtgpu_match *matches) {
   if (!ctx || !r) return fail(ctx, PBWTGPU_ERR_ARG, "result_fetch: bad args");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));  // (callers may come from any host thread)
   if (yz && r->yz && r->nyz)
     CUDA_TRY(ctx, cudaMemcpyAsync(yz, r->yz, (size_t)r->nyz, cudaMemcpyDeviceToHost, ctx->stream));
   if (a_end && r->aEnd)
@@ -1309,6 +1315,7 @@ int pbwtgpu_result_fetch_hist(pbwtgpu_ctx *ctx, const pbwtgpu_result *r, int64_t
 void pbwtgpu_result_free(pbwtgpu_ctx *ctx, pbwtgpu_result *r) {
   if (!r) return;
   if (ctx) {
+    cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (size_t i = 0; i < r->owned.size(); ++i) dev_release(ctx, r->owned[i], r->ownedBytes[i]);
   }
