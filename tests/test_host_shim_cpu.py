@@ -120,6 +120,29 @@ def test_batched_build_writes_reference_file(tmp_path):
     assert hashlib.md5(open(pb, "rb").read()).hexdigest() == str(g["pbwt_md5"])
 
 
+@pytest.mark.parametrize("batch", [0, 5])
+def test_lazy_cursor_adopts_a_non_identity_start_order(tmp_path, batch):
+    """A reader's cursor that does not start from the identity (p->aFstart set) goes through the batched device build as
+    well -- there is no hand-over to the reference's CPU function: u->a stays frozen at the start order, the shim
+    recovers the parsed column through it and carries the true order between batches."""
+    M, N = 37, 23
+    rng = np.random.default_rng(5)
+    hap = (rng.random((M, N)) < 0.4).astype(np.uint8)
+    start = rng.permutation(M).astype(np.int32)
+    xin, sin, pb = tmp_path / "x.bytes", tmp_path / "start.i32", tmp_path / "x.pbwt"
+    np.ascontiguousarray(hap.T).tofile(xin)
+    start.tofile(sin)
+    env = dict(os.environ)
+    if batch:
+        env["PBWTGPU_READER_BATCH"] = str(batch)
+    subprocess.run([SELFCHECK, str(xin), str(M), str(N), str(pb), str(sin)], check=True, capture_output=True, env=env)
+    imp = O.reference() or O.port()
+    yz, a_end, _ = imp.build(O.pack_panel(hap), M, N, a_start=start, with_d=False)
+    want = tmp_path / "want.pbwt"
+    write_pbwt(want, M, N, start, a_end, yz)
+    assert open(pb, "rb").read() == open(want, "rb").read()
+
+
 # ---- differential runs against the unmodified reference CLI (oracle/_ref/pbwt_ref), where it is present ----
 
 REF_CLI = os.path.join(ROOT, "oracle", "_ref", "pbwt_ref")
