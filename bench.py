@@ -345,6 +345,7 @@ def main():
         head = eng.panel_synthetic(M, n_cpu, seed=SEED, L=L_RECOMB, mu=MU)
         r = eng.build_device(head, flags)
         got = r.fetch()
+        grouped = r.fetch_groups()  # the form the e2e path brings to the host: must expand to the very same records
         r.free()
         x_head = head.to_host()
         head.free()
@@ -353,7 +354,9 @@ def main():
         mine = gpu_checksums(O, got)
         gate = {"checked": True, "sites": n_cpu, "pack3_bytes": int(got["yz"].size), "records": int(len(got["matches"])),
                 "checksums_gpu": mine, "checksums_cpu": cpu["checksums"],
-                "ok": mine == cpu["checksums"] and got["yz"].size == cpu["nyz"] and len(got["matches"]) == cpu["nmatch"]}
+                "grouped_words": int(grouped.size),
+                "ok": (mine == cpu["checksums"] and got["yz"].size == cpu["nyz"] and len(got["matches"]) == cpu["nmatch"]
+                       and np.array_equal(P.expand_groups(grouped), got["matches"]))}
         if not gate["ok"]:
             print(json.dumps({"error": "parity gate failed: the GPU's build + maxWithin of the first sites differs from the "
                                        "reference's; no value is reported", "parity_gate": gate}))
@@ -470,7 +473,7 @@ def main():
     x_np[:] = panel.to_host()
     a_end, d_end = np.zeros(M, np.int32), np.zeros(M + 1, np.int32)
     h2d = x_np.nbytes
-    d2h = nyz + 4 * M + 4 * (M + 1) + 16 * nmatch
+    d2h = nyz + 4 * M + 4 * (M + 1) + 16 * nmatch  # (N = 1: replaced below by what the grouped stream really is)
     pin = None
     if world > 1:  # per-rank pinned output buffers for the device-resident calls of the sharded protocol
         pin = {"yz": torch.empty(max(nyz, 1), dtype=torch.uint8).pin_memory().numpy(),
@@ -479,11 +482,16 @@ def main():
                "matches": torch.empty((max(nmatch, 1), 4), dtype=torch.int32).pin_memory().numpy().view(P.MATCH_DTYPE).reshape(-1)}
 
     def abi_step(e, a_out, d_out):
+        # the matches come as the grouped stream ({ai, start, end, n} + n x bi per run of callbacks that share ai, start,
+        # end: include/pbwtgpu.h), which the shim expands while it calls report(); the host reads it where the library left it
+        yzp, ny, gp, nw = e.build_grouped_raw(x_np, M, N, flags, a_out, d_out)
+        last = np.ctypeslib.as_array(ctypes.cast(gp, ctypes.POINTER(ctypes.c_int32)), shape=(nw,))[-1] if nw else 0
+        e.free_raw(yzp, gp)
+        return ny, nw, int(last)
+
+    def abi_step_full_records(e, a_out, d_out):  # the same call with 16-byte records (pbwtgpu_build), for comparison
         yzp, ny, mtp, nm = e.build_raw(x_np, M, N, flags, a_out, d_out)
-        # the host reads the result where the library left it (the shim walks the records and calls report())
-        last = np.ctypeslib.as_array(ctypes.cast(mtp, ctypes.POINTER(ctypes.c_int32)), shape=(nm * 4,))[-1] if nm else 0
         e.free_raw(yzp, mtp)
-        return ny, nm, int(last)
 
     def e2e_step():
         if world == 1:
@@ -494,8 +502,10 @@ def main():
         res.free()
         pnl.free()
 
+    first = e2e_step()
     e2e_step()
-    e2e_step()
+    if world == 1:
+        d2h = nyz + 4 * M + 4 * (M + 1) + 4 * first[1]
     barrier()
     t0 = time.time()
     for _ in range(args.steps):
@@ -503,7 +513,7 @@ def main():
     barrier()
     t_e2e_serial = (time.time() - t0) / args.steps
     t_e2e, in_flight = t_e2e_serial, 1
-    shim_seq_ms = None
+    shim_seq_ms = full_records_ms = None
 
     pipelined_ms = None
     if world > 1:
@@ -602,8 +612,8 @@ def main():
         # (pack3 stream + aFend back), then matchMaximalWithin sends the stored stream to pbwtgpu_max_within
         def shim_sequence():
             yzp, ny, _, _ = eng.build_raw(x_np, M, N, P.WANT_YZ, a_end, None)
-            mtp, nm = eng.max_within_raw(yzp, ny, M, N)
-            eng.free_raw(yzp, mtp)
+            gp, nw = eng.max_within_grouped_raw(yzp, ny, M, N)
+            eng.free_raw(yzp, gp)
 
         shim_sequence()
         barrier()
@@ -612,6 +622,13 @@ def main():
             shim_sequence()
         barrier()
         shim_seq_ms = (time.time() - t0) / args.steps * 1e3
+        abi_step_full_records(eng, a_end, d_end)
+        barrier()
+        t0 = time.time()
+        for _ in range(args.steps):
+            abi_step_full_records(eng, a_end, d_end)
+        barrier()
+        full_records_ms = (time.time() - t0) / args.steps * 1e3
     eng.host_free(xbuf)
 
     # ---- command-line wall times (reported separately; text output dominates) ------------
@@ -681,11 +698,15 @@ def main():
             "e2e": {"value": total_hs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
                     "ms_per_step": ms_e2e, "builds_in_flight": in_flight, "ms_per_step_one_in_flight": t_e2e_serial * 1e3,
                     "ms_per_step_shim_two_call_sequence": shim_seq_ms,
-                    "note": ("one pbwtgpu_build(host bit columns in a pbwtgpu_host_alloc buffer, WANT_YZ|WANT_MAXWITHIN) per step, as the "
-                             "C host shim calls it: H2D, kernels and D2H of pack3 stream, aFend, d and all match records into "
-                             "library-owned host buffers, freed with pbwtgpu_free; with 2 builds in flight two contexts (streams, "
-                             "host threads) alternate steps; the shim's two-call sequence (pbwtgpu_build, then "
-                             "pbwtgpu_max_within on the stored stream) is timed beside it") if world == 1 else
+                    "ms_per_step_one_in_flight_16_byte_records": full_records_ms,
+                    "note": ("one pbwtgpu_build_grouped(host bit columns in a pbwtgpu_host_alloc buffer, WANT_YZ|WANT_MAXWITHIN) per step, "
+                             "the entry point the C host shim's match path uses: H2D, kernels and D2H of pack3 stream, aFend, d and ALL "
+                             "match records -- as the grouped stream ({ai, start, end, n} + n x bi per run of callbacks that share "
+                             "ai, start, end; the shim expands it while it calls report(); the parity gate checks that it expands "
+                             "to exactly the records) -- into library-owned host buffers, freed with pbwtgpu_free; with 2 builds in "
+                             "flight two contexts (streams, host threads) alternate steps; the shim's two-call sequence "
+                             "(pbwtgpu_build, then pbwtgpu_max_within_grouped on the stored stream) and the same call with 16-byte "
+                             "records are timed beside it") if world == 1 else
                             "per rank: pinned host columns -> pbwtgpu_panel_from_host -> shard protocol (one NCCL all-gather) -> "
                             "pbwtgpu_result_fetch of pack3 stream, aFend, d and all match records, every step; builds_in_flight 3 = "
                             "a three-stage pipeline per rank (upload thread, build thread, download thread, each with its own "

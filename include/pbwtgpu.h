@@ -116,6 +116,16 @@ int pbwtgpu_result_sizes(const pbwtgpu_result *result, int64_t *nyz, int64_t *nm
  * matches[nmatch]. */
 int pbwtgpu_result_fetch(pbwtgpu_ctx *ctx, const pbwtgpu_result *result, uint8_t *yz, int32_t *a_end, int32_t *d_end,
                          pbwtgpu_match *matches);
+/* The match records in GROUPED form: the reference's reporters emit runs of callbacks that share ai, start and end (the block
+ * above a position, the block below it, pbwtMatch.c:133-134; the block of a query, :385,433-435) and only bi changes inside a
+ * run.  The grouped stream is int32 words: {ai, start, end, n} followed by the n values of bi, group after group, in
+ * callback order; expanding it -- report(ai, bi[j], start, end) for j < n -- reproduces the record sequence exactly.  About
+ * a third of the bytes of the records (config 2: 95 MB instead of 295 MB), which is what crosses PCIe on the one-shot paths
+ * the host shim uses.  pbwtgpu_result_group builds the stream on the device (once per result; *nwords = its length,
+ * *ngroups = number of groups), pbwtgpu_result_fetch_groups copies it to dst[nwords]. */
+typedef struct { int32_t ai, start, end, n; } pbwtgpu_group; /* followed by n x int32_t bi */
+int pbwtgpu_result_group(pbwtgpu_ctx *ctx, pbwtgpu_result *result, int64_t *nwords, int64_t *ngroups);
+int pbwtgpu_result_fetch_groups(pbwtgpu_ctx *ctx, const pbwtgpu_result *result, int32_t *dst);
 /* WANT_STATS: hist[len], len = 0 .. N, = number of (position, site) reporters of matchMaximalWithin whose longer block
  * has that length -- exactly matchLengthHist of the reference (pbwtMatch.c:130-131,161-178). */
 int pbwtgpu_result_fetch_hist(pbwtgpu_ctx *ctx, const pbwtgpu_result *result, int64_t *hist);
@@ -185,6 +195,12 @@ void pbwtgpu_host_trim(void);
 int pbwtgpu_build(pbwtgpu_ctx *ctx, const uint32_t *xbits, int M, int N, const int32_t *a_start, unsigned flags,
                   uint8_t **yz, int64_t *nyz, int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches,
                   int64_t *nmatch);
+/* pbwtgpu_build / pbwtgpu_max_within with the matches as a grouped stream (*groups, *nwords int32; give it back with
+ * pbwtgpu_free): what the host shim calls -- it expands the groups while it walks them for report(). */
+int pbwtgpu_build_grouped(pbwtgpu_ctx *ctx, const uint32_t *xbits, int M, int N, const int32_t *a_start, unsigned flags,
+                          uint8_t **yz, int64_t *nyz, int32_t *a_end, int32_t *d_end, int32_t **groups, int64_t *nwords);
+int pbwtgpu_max_within_grouped(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start,
+                               int32_t *a_end, int32_t *d_end, int32_t **groups, int64_t *nwords);
 /* matchMaximalWithin(p, report) over a stored stream (pbwtMatch.c:115-142). */
 int pbwtgpu_max_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start,
                        int32_t *a_end, int32_t *d_end, pbwtgpu_match **matches, int64_t *nmatch);

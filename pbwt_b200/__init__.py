@@ -4,4 +4,4 @@ The product is ``pbwt_b200/libpbwtgpu.so`` (CUDA kernels + include/pbwtgpu.h); t
 the thin ctypes binding used by tests and bench.py.  No CPU fallback exists.
 """
 from .api import (Engine, Panel, Shard, QueryShard, PbwtGpuError, Result, KERNEL_CLASSES, MATCH_DTYPE, NOMATCH_DTYPE, WANT_D,  # noqa: F401
-                  WANT_MAXWITHIN, WANT_YZ, WANT_LONGWITHIN, WANT_STATS, LIB_PATH, load_library, words_per_col)
+                  WANT_MAXWITHIN, WANT_YZ, WANT_LONGWITHIN, WANT_STATS, LIB_PATH, load_library, words_per_col, expand_groups)

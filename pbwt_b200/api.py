@@ -81,6 +81,11 @@ def load_library() -> C.CDLL:
         lib.pbwtgpu_build.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_uint, C.POINTER(_vp), C.POINTER(_i64), _vp, _vp,
                                       C.POINTER(_vp), C.POINTER(_i64)]
         lib.pbwtgpu_max_within.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_i64)]
+        lib.pbwtgpu_result_group.argtypes = [_vp, _vp, C.POINTER(_i64), C.POINTER(_i64)]
+        lib.pbwtgpu_result_fetch_groups.argtypes = [_vp, _vp, _vp]
+        lib.pbwtgpu_build_grouped.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, C.c_uint, C.POINTER(_vp), C.POINTER(_i64), _vp, _vp,
+                                              C.POINTER(_vp), C.POINTER(_i64)]
+        lib.pbwtgpu_max_within_grouped.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_i64)]
         lib.pbwtgpu_max_within_stats.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp]
         lib.pbwtgpu_result_fetch_hist.argtypes = [_vp, _vp, _vp]
         lib.pbwtgpu_cursor_at.argtypes = [_vp, _vp, _i64, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp]
@@ -167,6 +172,14 @@ class Result:
         if bufs["matches"] is not None:
             bufs["matches"] = bufs["matches"][: self.nmatch]
         return bufs
+
+    def fetch_groups(self) -> np.ndarray:
+        """The match records as a grouped int32 stream ({ai, start, end, n} + n x bi per run), built on the device."""
+        nw, ng = _i64(0), _i64(0)
+        self.eng._check(self.eng.lib.pbwtgpu_result_group(self.eng.ctx, self.handle, C.byref(nw), C.byref(ng)))
+        out = np.zeros(max(nw.value, 1), np.int32)
+        self.eng._check(self.eng.lib.pbwtgpu_result_fetch_groups(self.eng.ctx, self.handle, _ptr(out)))
+        return out[: nw.value]
 
     def fetch_hist(self) -> np.ndarray:
         """WANT_STATS: the -stats length histogram accumulated on the device, hist[0 .. N]."""
@@ -351,6 +364,25 @@ class Engine:
             "matches": _take(self.lib, mt, nm.value * 16, MATCH_DTYPE) if with_matches else None,
         }
 
+    def build_grouped_raw(self, xbits: np.ndarray, M: int, N: int, flags: int, a_end: np.ndarray, d_end: np.ndarray | None):
+        """pbwtgpu_build_grouped: as build_raw, the matches as a grouped stream -> (yz_ptr, nyz, groups_ptr, nwords)."""
+        yz, nyz, gp, nw = _vp(), _i64(0), _vp(), _i64(0)
+        self._check(self.lib.pbwtgpu_build_grouped(self.ctx, _ptr(xbits), M, N, None, flags, C.byref(yz), C.byref(nyz), _ptr(a_end),
+                                                   _ptr(d_end), C.byref(gp), C.byref(nw)))
+        return yz, nyz.value, gp, nw.value
+
+    def max_within_grouped_raw(self, yz_ptr, nyz: int, M: int, N: int):
+        gp, nw = _vp(), _i64(0)
+        self._check(self.lib.pbwtgpu_max_within_grouped(self.ctx, yz_ptr, nyz, M, N, None, None, None, C.byref(gp), C.byref(nw)))
+        return gp, nw.value
+
+    def max_within_grouped(self, yz: np.ndarray, M: int, N: int, a_start=None) -> np.ndarray:
+        yz = np.ascontiguousarray(yz, np.uint8)
+        a0 = None if a_start is None else np.ascontiguousarray(a_start, np.int32)
+        gp, nw = _vp(), _i64(0)
+        self._check(self.lib.pbwtgpu_max_within_grouped(self.ctx, _ptr(yz), yz.size, M, N, _ptr(a0), None, None, C.byref(gp), C.byref(nw)))
+        return _take(self.lib, gp, nw.value * 4, np.int32)
+
     def build_raw(self, xbits: np.ndarray, M: int, N: int, flags: int, a_end: np.ndarray, d_end: np.ndarray | None):
         """pbwtgpu_build exactly as the C host shim calls it: host columns in, library-owned host buffers out.
         -> (yz_ptr, nyz, matches_ptr, nmatch); the caller reads them in place and returns them with free_raw()."""
@@ -449,3 +481,22 @@ class Engine:
         zc = np.zeros(max(N, 1), np.int32)
         self._check(self.lib.pbwtgpu_unpack3(self.ctx, _ptr(yz), yz.size, M, N, _ptr(y), _ptr(zc)))
         return y[:N], zc[:N]
+
+
+def expand_groups(g: np.ndarray) -> np.ndarray:
+    """grouped stream -> MATCH_DTYPE records, in order (what the host shim does while it calls report())"""
+    g = np.asarray(g, np.int32)
+    heads, i = [], 0
+    while i < g.size:  # (group headers are found by walking: a Python loop over groups, vectorised inside)
+        heads.append(i)
+        i += 4 + int(g[i + 3])
+    heads = np.asarray(heads, np.int64)
+    n = g[heads + 3].astype(np.int64) if heads.size else np.zeros(0, np.int64)
+    out = np.zeros(int(n.sum()), MATCH_DTYPE)
+    if heads.size:
+        rep = np.repeat(np.arange(heads.size), n)
+        first = np.cumsum(n) - n
+        within = np.arange(out.size) - first[rep]
+        out["ai"], out["start"], out["end"] = g[heads][rep], g[heads + 1][rep], g[heads + 2][rep]
+        out["bi"] = g[heads[rep] + 4 + within]
+    return out

@@ -10,6 +10,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "group_records.cuh"
 #include "pack3.cuh"
 #include "query_chain.cuh"
 #include "sweep.cuh"
@@ -68,6 +69,8 @@ struct pbwtgpu_result {
   pbwtgpu_match *rec = nullptr;
   int64_t nrec = 0;
   unsigned int *hist = nullptr;  // WANT_STATS: [N + 1]
+  int32_t *groups = nullptr;     // the records in grouped form (pbwtgpu_result_group), 4 * nGroups + nrec int32
+  int64_t nGroups = -1;          // -1: not grouped yet
   std::vector<void *> owned;  // device blocks released by pbwtgpu_result_free
   std::vector<size_t> ownedBytes;
 };
@@ -1303,6 +1306,44 @@ int pbwtgpu_result_fetch(pbwtgpu_ctx *ctx, const pbwtgpu_result *r, uint8_t *yz,
   return 0;
 }
 
+int pbwtgpu_result_group(pbwtgpu_ctx *ctx, pbwtgpu_result *r, int64_t *nwords, int64_t *ngroups) {
+  if (!ctx || !r) return fail(ctx, PBWTGPU_ERR_ARG, "result_group: bad args");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (r->nGroups < 0) {
+    long long g = 0;
+    if (r->nrec > 0) {
+      if (r->nrec > 0x7fffffffLL) return fail(ctx, PBWTGPU_ERR_UNSUPPORTED, "result_group: %lld records", (long long)r->nrec);
+      Temps tmp(ctx);
+      char *state = nullptr, *temp = nullptr;
+      const size_t tempBytes = group_records_temp_bytes(r->nrec);
+      if (int rc = tmp.get(&state, group_records_state_bytes(r->nrec))) return rc;
+      if (int rc = tmp.get(&temp, tempBytes)) return rc;
+      ScopedTimer t(ctx, PBWTGPU_K_AUX);
+      CUDA_TRY(ctx, launch_group_scan(r->rec, r->nrec, state, temp, tempBytes, ctx->stream));
+      CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->pinned[0], group_scan_total(state, r->nrec), sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      g = (long long)ctx->pinned[0];
+      if (int rc = result_alloc(ctx, r, &r->groups, (size_t)(4 * g + r->nrec))) return rc;
+      CUDA_TRY(ctx, launch_write_groups(r->rec, state, r->nrec, r->groups, ctx->stream));
+      ctx->launches[PBWTGPU_K_AUX] += 2;
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // the temporaries go back to the cache
+    }
+    r->nGroups = g;
+  }
+  if (nwords) *nwords = 4 * r->nGroups + r->nrec;
+  if (ngroups) *ngroups = r->nGroups;
+  return 0;
+}
+
+int pbwtgpu_result_fetch_groups(pbwtgpu_ctx *ctx, const pbwtgpu_result *r, int32_t *dst) {
+  if (!ctx || !r || !dst || r->nGroups < 0) return fail(ctx, PBWTGPU_ERR_ARG, "result_fetch_groups: call pbwtgpu_result_group first");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)(4 * r->nGroups + r->nrec);
+  if (n) CUDA_TRY(ctx, cudaMemcpyAsync(dst, r->groups, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 int pbwtgpu_result_fetch_hist(pbwtgpu_ctx *ctx, const pbwtgpu_result *r, int64_t *hist) {
   if (!ctx || !r || !hist || !r->hist) return fail(ctx, PBWTGPU_ERR_ARG, "result_fetch_hist: the sweep was not run with WANT_STATS");
   std::vector<unsigned int> h((size_t)r->N + 1);
@@ -1402,6 +1443,44 @@ int pbwtgpu_max_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, 
   pbwtgpu_result *res = nullptr;
   int rc = pbwtgpu_sweep_yz_device(ctx, yz, nyz, M, N, a_start, matches ? PBWTGPU_WANT_MAXWITHIN : PBWTGPU_WANT_D, &res);
   if (!rc) rc = fetch_to_malloc(ctx, res, nullptr, nullptr, a_end, d_end, matches, nmatch);
+  pbwtgpu_result_free(ctx, res);
+  return rc;
+}
+
+// yz / a_end / d_end as fetch_to_malloc, the matches as a grouped stream
+static int fetch_grouped(pbwtgpu_ctx *ctx, pbwtgpu_result *res, uint8_t **yz, int64_t *nyz, int32_t *a_end, int32_t *d_end, int32_t **groups,
+                         int64_t *nwords) {
+  int64_t nw = 0;
+  if (int rc = pbwtgpu_result_group(ctx, res, &nw, nullptr)) return rc;
+  HostGuard hg(host_alloc_pinned(sizeof(int32_t) * (size_t)std::max<int64_t>(nw, 1)));
+  if (!hg.p) return fail(ctx, PBWTGPU_ERR_NOMEM, "pinned host allocation failed (grouped records)");
+  if (int rc = pbwtgpu_result_fetch_groups(ctx, res, (int32_t *)hg.p)) return rc;
+  if (int rc = fetch_to_malloc(ctx, res, yz, nyz, a_end, d_end, nullptr, nullptr)) return rc;
+  *groups = (int32_t *)hg.release();
+  *nwords = nw;
+  return 0;
+}
+
+int pbwtgpu_build_grouped(pbwtgpu_ctx *ctx, const uint32_t *xbits, int M, int N, const int32_t *a_start, unsigned flags, uint8_t **yz,
+                          int64_t *nyz, int32_t *a_end, int32_t *d_end, int32_t **groups, int64_t *nwords) {
+  if (!groups || !nwords || !(flags & (PBWTGPU_WANT_MAXWITHIN | PBWTGPU_WANT_LONGWITHIN)) || (flags & PBWTGPU_WANT_STATS))
+    return fail(ctx, PBWTGPU_ERR_ARG, "build_grouped: needs a match flag and somewhere to put the groups");
+  pbwtgpu_panel *panel = nullptr;
+  if (int rc = pbwtgpu_panel_from_host(ctx, xbits, M, N, &panel)) return rc;
+  pbwtgpu_result *res = nullptr;
+  int rc = pbwtgpu_build_device(ctx, panel, a_start, flags, &res);
+  if (!rc) rc = fetch_grouped(ctx, res, (flags & PBWTGPU_WANT_YZ) ? yz : nullptr, nyz, a_end, d_end, groups, nwords);
+  pbwtgpu_result_free(ctx, res);
+  pbwtgpu_panel_free(ctx, panel);
+  return rc;
+}
+
+int pbwtgpu_max_within_grouped(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start, int32_t *a_end,
+                               int32_t *d_end, int32_t **groups, int64_t *nwords) {
+  if (!groups || !nwords) return fail(ctx, PBWTGPU_ERR_ARG, "max_within_grouped: bad args");
+  pbwtgpu_result *res = nullptr;
+  int rc = pbwtgpu_sweep_yz_device(ctx, yz, nyz, M, N, a_start, PBWTGPU_WANT_MAXWITHIN, &res);
+  if (!rc) rc = fetch_grouped(ctx, res, nullptr, nullptr, a_end, d_end, groups, nwords);
   pbwtgpu_result_free(ctx, res);
   return rc;
 }

@@ -42,14 +42,20 @@ static void gpuCheck (int rc, const char *what)
 
 void matchMaximalWithin (PBWT *p, void (*report)(int ai, int bi, int start, int end))
 {
-  pbwtgpu_match *rec = 0 ;
-  int64_t n = 0, i ;
+  int32_t *g = 0 ;		/* grouped records: {ai, start, end, n} + n x bi per run of callbacks that share ai, start, end */
+  int64_t nw = 0, i = 0 ;
 
   if (!p || !p->yz) die ("matchMaximalWithin called without a PBWT") ;
-  gpuCheck (pbwtgpu_max_within (gpuContext (), arrp(p->yz,0,uchar), arrayMax(p->yz), p->M, p->N,
-				p->aFstart, 0, 0, &rec, &n), "pbwtgpu_max_within") ;
-  for (i = 0 ; i < n ; ++i) (*report) (rec[i].ai, rec[i].bi, rec[i].start, rec[i].end) ;
-  pbwtgpu_free (rec) ;
+  gpuCheck (pbwtgpu_max_within_grouped (gpuContext (), arrp(p->yz,0,uchar), arrayMax(p->yz), p->M, p->N,
+					p->aFstart, 0, 0, &g, &nw), "pbwtgpu_max_within_grouped") ;
+  while (i < nw)		/* one callback per record, in the reference's order */
+    { const pbwtgpu_group *h = (const pbwtgpu_group*) (g + i) ;
+      const int32_t *bi = g + i + 4 ;
+      int j ;
+      for (j = 0 ; j < h->n ; ++j) (*report) (h->ai, bi[j], h->start, h->end) ;
+      i += 4 + h->n ;
+    }
+  pbwtgpu_free (g) ;
 }
 
 /* ---- reportMatch (pbwtMatch.c:46-58): the CLI printer; zero-length matches are dropped ---- */

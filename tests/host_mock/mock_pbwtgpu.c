@@ -71,6 +71,29 @@ int pbwtgpu_max_within(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, 
   return ends(yz, nyz, M, N, a_start, a_end, d_end);
 }
 
+/* grouped stream: runs of records that share ai, start, end -> {ai, start, end, n} + n x bi */
+int pbwtgpu_max_within_grouped(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start, int32_t *a_end,
+                               int32_t *d_end, int32_t **groups, int64_t *nwords) {
+  pbwtgpu_match *rec = NULL;
+  int64_t n = 0, i = 0, w = 0;
+  const int rc = pbwtgpu_max_within(ctx, yz, nyz, M, N, a_start, a_end, d_end, &rec, &n);
+  if (rc) return rc;
+  int32_t *g = (int32_t *)malloc(sizeof(int32_t) * (size_t)(5 * n + 4));
+  if (!g) { free(rec); return PBWTGPU_ERR_NOMEM; }
+  while (i < n) {
+    int64_t j = i;
+    while (j < n && rec[j].ai == rec[i].ai && rec[j].start == rec[i].start && rec[j].end == rec[i].end) ++j;
+    g[w] = rec[i].ai; g[w + 1] = rec[i].start; g[w + 2] = rec[i].end; g[w + 3] = (int32_t)(j - i);
+    for (int64_t t = i; t < j; ++t) g[w + 4 + (t - i)] = rec[t].bi;
+    w += 4 + (j - i);
+    i = j;
+  }
+  free(rec);
+  *groups = g;
+  *nwords = w;
+  return PBWTGPU_OK;
+}
+
 /* the device consumer of the matches behind -stats: one count per reporter (a run of records with the same ai and end)
    at the length of the longer of its blocks, derived here from the oracle's records */
 int pbwtgpu_max_within_stats(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int N, const int32_t *a_start, int64_t *hist) {

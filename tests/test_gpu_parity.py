@@ -458,6 +458,35 @@ def test_pack3_fused_and_fallback_paths(eng, orc, M, N, W, dens, opt, val):
         eng.set_option(opt, 0)
 
 
+@pytest.mark.parametrize("M,N,W,dens,force_global", [(8, 10, 1, 0.3, 0), (1000, 300, 7, 0.05, 0), (2752, 38, 2, 0.3, 0), (5000, 200, 37, 0.02, 0),
+                                                      (3000, 200, 5, 0.05, 1)])
+def test_grouped_records_expand_to_the_records(eng, orc, M, N, W, dens, force_global):
+    """The grouped stream ({ai, start, end, n} + n x bi per run of records that share ai, start, end), built on the device,
+    expands to exactly the reference's callback sequence -- through the result object and through the one-shot calls."""
+    rng = np.random.default_rng(M + N)
+    hap = (rng.random((M, N)) < dens).astype(np.uint8)
+    hap[: M // 4] = hap[0]
+    x = O.pack_panel(hap)
+    yz = orc.build(x, M, N, with_d=False)[0]
+    rec, n = orc.max_within(yz, M, N)
+    eng.set_option("windows", W)
+    eng.set_option("force_global", force_global)
+    try:
+        panel = eng.panel_from_host(x, M)
+        r = eng.build_device(panel, pbwt_b200.WANT_MAXWITHIN)
+        g1 = r.fetch_groups()
+        r.free()
+        panel.free()
+        g2 = eng.max_within_grouped(yz, M, N)
+    finally:
+        eng.set_option("windows", 0)
+        eng.set_option("force_global", 0)
+    for g in (g1, g2):
+        got = pbwt_b200.expand_groups(g)
+        assert len(got) == n and (got == rec[:n]).all()
+    assert g1.size <= 5 * n  # (a group has at least one record)
+
+
 def test_smem_limit_without_matches(eng, orc):
     """M between the match kernel's limit (12,544) and the shared-memory limit (13,312): a/d/pack3 only."""
     rng = np.random.default_rng(13)
