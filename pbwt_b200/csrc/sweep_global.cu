@@ -289,6 +289,12 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
   // the same arrays as indices into smem[] for the hot loops (accesses through the derived pointers above are
   // compiled as generic loads/stores with a per-access shared-window conversion in cluster kernels)
   const int oY = 0, oDn = chunkWords, oWmax = oDn + (WITH_D ? chunk : 0), oZloc = oWmax + (SCAN ? chunkWords : 0) + (MATCH ? chunkWords : 0);
+  // a-only builds: the prefix-array values a thread loads in phase A wait in shared memory for its phase C (the same
+  // thread, the same slots) instead of being loaded from L2 a second time behind the group's exchange (config 3's pass 2
+  // 66.0 -> 63.9 ms).  With d the extra 4 bytes per position cost more than they save: smaller chunks, more CTAs per
+  // window, fewer windows (measured: 100k x 50k +8 %, 1M x 20k 2x slower).
+  constexpr bool STAGE_A = MODE == kGather && !SCAN && !WITH_D;
+  const int oAst = oWmax;  // [chunk] (STAGE_A; no scan arrays follow in these variants)
   __shared__ int wexS[32];      // zeros in this CTA's warps below each warp
   __shared__ int wsumZ[32];
   __shared__ uint32_t wsumR[32];
@@ -483,6 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
         const bool valid = FULL || iBase + u * 32 < M;
         hB[u] = ((MODE == kGather || p.xOut) && valid) ? __ldcg(aP + u * 32) : 0;
         dB[u] = (WITH_D && valid) ? __ldcg(dP + u * 32) : 0;
+        if (STAGE_A) smem[oAst + (wordBase + e0 + u) * 32 + lane] = (uint32_t)hB[u];
       }
 #pragma unroll
       for (int u = 0; u < NB; ++u) {
@@ -680,7 +687,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
         const int iBase = p0 + (wordBase + e0) * 32 + lane;
         const int32_t *aP = aC + iBase;
 #pragma unroll
-        for (int u = 0; u < NB; ++u) hB[u] = (FULL || iBase + u * 32 < M) ? __ldcg(aP + u * 32) : 0;
+        for (int u = 0; u < NB; ++u) {
+          if (STAGE_A) hB[u] = (int)smem[oAst + (wordBase + e0 + u) * 32 + lane];
+          else hB[u] = (FULL || iBase + u * 32 < M) ? __ldcg(aP + u * 32) : 0;
+        }
 #pragma unroll
         for (int u = 0; u < NB; ++u) {
           const int e = e0 + u;
@@ -971,20 +981,21 @@ static size_t smem_fixed_words(bool match, bool query, int Q, int colWords) {
   const size_t QW = query ? (size_t)((Q + 31) / 32 + 31) / 32 * 32 : 0;
   return (scan ? kResMax * 4 + kTabMirror : 0) + (query ? kResMax : 0) + QW * 2 + QW * 32 * 2 + (size_t)colWords;
 }
-static size_t smem_bytes(int chunk, bool with_d, bool match, bool query, int Q, int colWords) {
+static bool stages_a(SweepMode mode, bool with_d, bool match, bool query) { return mode == kGather && !with_d && !match && !query; }  // (STAGE_A of the kernel)
+static size_t smem_bytes(int chunk, bool with_d, bool match, bool query, int Q, int colWords, bool stageA) {
   const size_t cw = chunk / 32;
   const bool scan = match || query;
-  const size_t words = cw + (with_d ? chunk : 0) + (scan ? cw : 0) + (match ? cw : 0) + (query ? cw : 0) +
+  const size_t words = cw + (with_d ? chunk : 0) + (stageA ? chunk : 0) + (scan ? cw : 0) + (match ? cw : 0) + (query ? cw : 0) +
                        smem_fixed_words(match, query, Q, colWords);
   return words * 4;
 }
 constexpr size_t kSmemBudget = 232448 - 2048;  // 227 KB per CTA minus the static arrays
 // largest chunk (multiple of 1024, <= kMaxChunk) whose arrays fit beside the fixed part; 0 = does not fit
-static int max_chunk(bool with_d, bool match, bool query, int Q, int colWords) {
+static int max_chunk(bool with_d, bool match, bool query, int Q, int colWords, bool stageA) {
   const size_t fixed = smem_fixed_words(match, query, Q, colWords) * 4;
   if (fixed + 4096 > kSmemBudget) return 0;
   const bool scan = match || query;
-  const double perPos = (with_d ? 4.0 : 0.0) + 4.0 * (1 + (scan ? 1 : 0) + (match ? 1 : 0) + (query ? 1 : 0)) / 32.0;
+  const double perPos = (with_d ? 4.0 : 0.0) + (stageA ? 4.0 : 0.0) + 4.0 * (1 + (scan ? 1 : 0) + (match ? 1 : 0) + (query ? 1 : 0)) / 32.0;
   long long c = (long long)((kSmemBudget - fixed) / perPos);
   c = c / 1024 * 1024;
   return (int)std::min<long long>(c, kMaxChunk);
@@ -1040,7 +1051,8 @@ void sweep_global_plan(int M, int maxCtas, int wantWindows, SweepMode mode, bool
   // (staging the gather-mode bit column in shared memory by TMA was measured neutral to slower -- the kernel is issue
   // bound and the gather hits L1 -- and is not done)
   const int colWords = 0;
-  const int chunkMax = max_chunk(with_d, match, query, Q, colWords);
+  const bool stageA = stages_a(mode, with_d, match, query);
+  const int chunkMax = max_chunk(with_d, match, query, Q, colWords, stageA);
   const int gmin = (M + chunkMax - 1) / chunkMax;
   int w = wantWindows > 0 ? wantWindows : 1;
   *cluster = 0;
@@ -1050,7 +1062,7 @@ void sweep_global_plan(int M, int maxCtas, int wantWindows, SweepMode mode, bool
     for (; g >= gLo; g >>= 1) {
       const int ch = ((M + g - 1) / g + 1023) / 1024 * 1024;
       const int n = max_active_clusters(pick_kernel<true>(mode, with_d, match, query), g,
-                                        smem_bytes(ch, with_d, match, query, Q, colWords));
+                                        smem_bytes(ch, with_d, match, query, Q, colWords, stageA));
       if (n >= 1) {
         *G = g; *chunk = ch; *W = std::min(w, n); *cluster = 1;
         return;
@@ -1111,7 +1123,8 @@ int launch_sweep_global(const SweepArgs &a, SweepMode mode, bool with_d, int wit
   if (b.cluster && b.G > 16) return (int)cudaErrorInvalidValue;
   void *kern = b.cluster ? pick_kernel<true>(mode, with_d, with_match, false) : pick_kernel<false>(mode, with_d, with_match, false);
   const int colWords = 0;
-  return launch_any(kern, b.cluster, a, b, a.nWindows * b.G, smem_bytes(b.chunk, with_d, with_match != 0, false, 0, colWords), stream);
+  return launch_any(kern, b.cluster, a, b, a.nWindows * b.G,
+                    smem_bytes(b.chunk, with_d, with_match != 0, false, 0, colWords, stages_a(mode, with_d, with_match != 0, false)), stream);
 }
 
 int query_sweep_global_max_q() { return kQCap; }
@@ -1122,7 +1135,7 @@ int launch_query_sweep_global(const SweepArgs &a, const GlobalBuffers &b, cudaSt
   void *kern = b.cluster ? pick_kernel<true>(kSorted, true, false, true) : pick_kernel<false>(kSorted, true, false, true);
   SweepArgs args = a;
   if (args.nWindows < 1) args.nWindows = 1;
-  return launch_any(kern, b.cluster, args, b, args.nWindows * b.G, smem_bytes(b.chunk, true, false, true, a.Q, 0), stream);
+  return launch_any(kern, b.cluster, args, b, args.nWindows * b.G, smem_bytes(b.chunk, true, false, true, a.Q, 0, false), stream);
 }
 
 size_t sweep_global_sync_bytes(int W) { return sizeof(GroupSync) * (size_t)W; }

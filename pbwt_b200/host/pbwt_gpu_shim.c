@@ -15,6 +15,7 @@
  * haplotypes, as the reference's reportMatch does (pbwtMatch.c:33-58), which makes -check a self-test of the device
  * results.  The reference's renamed originals stay linked but are not called.
  */
+#include <time.h>
 #include "pbwt.h"
 #include "pbwtgpu.h"
 
@@ -26,11 +27,24 @@ void ref_matchSequencesDynamic (PBWT *p, FILE *fp) ;
 
 static pbwtgpu_ctx *gpu = 0 ;
 
+/* PBWTGPU_SHIM_TIMING=1: where the drop-in's wall time goes (device context, device call, callbacks), on stderr */
+static double shimNow (void)
+{ struct timespec ts ; clock_gettime (CLOCK_MONOTONIC, &ts) ; return ts.tv_sec + 1e-9 * ts.tv_nsec ; }
+
+static void shimTiming (const char *what, double t0)
+{
+  static int on = -1 ;
+  if (on < 0) on = getenv ("PBWTGPU_SHIM_TIMING") != 0 ;
+  if (on) fprintf (stderr, "pbwtgpu shim timing: %s %.3f s\n", what, shimNow () - t0) ;
+}
+
 static pbwtgpu_ctx *gpuContext (void)
 {
   if (!gpu)
-    { int rc = pbwtgpu_init (0, &gpu) ;
+    { double t0 = shimNow () ;
+      int rc = pbwtgpu_init (0, &gpu) ;
       if (rc) die ("pbwtgpu_init failed: %s", pbwtgpu_strerror (rc)) ;
+      shimTiming ("pbwtgpu_init (device context)", t0) ;
     }
   return gpu ;
 }
@@ -45,9 +59,16 @@ void matchMaximalWithin (PBWT *p, void (*report)(int ai, int bi, int start, int 
   int32_t *g = 0 ;		/* grouped records: {ai, start, end, n} + n x bi per run of callbacks that share ai, start, end */
   int64_t nw = 0, i = 0 ;
 
+  pbwtgpu_ctx *ctx ;
+  double t0 ;
+
   if (!p || !p->yz) die ("matchMaximalWithin called without a PBWT") ;
-  gpuCheck (pbwtgpu_max_within_grouped (gpuContext (), arrp(p->yz,0,uchar), arrayMax(p->yz), p->M, p->N,
+  ctx = gpuContext () ;
+  t0 = shimNow () ;
+  gpuCheck (pbwtgpu_max_within_grouped (ctx, arrp(p->yz,0,uchar), arrayMax(p->yz), p->M, p->N,
 					p->aFstart, 0, 0, &g, &nw), "pbwtgpu_max_within_grouped") ;
+  shimTiming ("pbwtgpu_max_within_grouped (H2D, sweep, D2H)", t0) ;
+  t0 = shimNow () ;
   while (i < nw)		/* one callback per record, in the reference's order */
     { const pbwtgpu_group *h = (const pbwtgpu_group*) (g + i) ;
       const int32_t *bi = g + i + 4 ;
@@ -55,6 +76,7 @@ void matchMaximalWithin (PBWT *p, void (*report)(int ai, int bi, int start, int 
       for (j = 0 ; j < h->n ; ++j) (*report) (h->ai, bi[j], h->start, h->end) ;
       i += 4 + h->n ;
     }
+  shimTiming ("report() callbacks", t0) ;
   pbwtgpu_free (g) ;
 }
 
@@ -79,12 +101,41 @@ static void checkMatchMaximal (uchar *x, uchar *y, int start, int end, int N)	/*
 static void freeHaps (uchar **h, int M)
 { int j ; for (j = 0 ; j < M ; ++j) free (h[j]) ; free (h) ; }
 
+/* the printer's lines are assembled in a buffer of our own (18.5 M printf calls are most of the drop-in's wall time on the
+   10,000 x 100,000 panel); matchLinesFlush () hands it to stdout before anyone else writes there */
+static char matchLineBuf[1 << 16] ;
+static int matchLineFill = 0 ;
+
+static void matchLinesFlush (void)
+{ if (matchLineFill) { fwrite (matchLineBuf, 1, matchLineFill, stdout) ; matchLineFill = 0 ; } }
+
+static inline char *putInt (char *c, int v)	/* decimal, as %d prints it */
+{
+  char t[12] ; int n = 0 ;
+  unsigned u = v < 0 ? 0u - (unsigned) v : (unsigned) v ;
+  if (v < 0) *c++ = '-' ;
+  do { t[n++] = (char) ('0' + u % 10) ; u /= 10 ; } while (u) ;
+  while (n) *c++ = t[--n] ;
+  return c ;
+}
+
 static void reportMatchLine (int ai, int bi, int start, int end)
 {
+  char *c ;
   if (start == end) return ;
-  printf ("MATCH\t%d\t%d\t%d\t%d\t%d\n", ai, bi, start, end, end-start) ;
+  if (matchLineFill > (int) sizeof (matchLineBuf) - 80) matchLinesFlush () ;
+  c = matchLineBuf + matchLineFill ;	/* "MATCH\t%d\t%d\t%d\t%d\t%d\n", pbwtMatch.c:46-49 */
+  memcpy (c, "MATCH\t", 6) ; c += 6 ;
+  c = putInt (c, ai) ; *c++ = '\t' ;
+  c = putInt (c, bi) ; *c++ = '\t' ;
+  c = putInt (c, start) ; *c++ = '\t' ;
+  c = putInt (c, end) ; *c++ = '\t' ;
+  c = putInt (c, end-start) ; *c++ = '\n' ;
+  matchLineFill = (int) (c - matchLineBuf) ;
   if (isCheck)			/* the GPU's record is a real match and maximal */
-    checkMatchMaximal (checkHapsA[ai], checkHapsB[bi], start, end, Ncheck) ;
+    { matchLinesFlush () ;	/* (a failed check dies: what was reported so far must be out, as with the reference's printf) */
+      checkMatchMaximal (checkHapsA[ai], checkHapsB[bi], start, end, Ncheck) ;
+    }
 }
 
 /* ---- pbwtLongMatches (pbwtMatch.c:148-183): -maxWithin is L == 0 ---- */
@@ -116,6 +167,7 @@ void pbwtLongMatches (PBWT *p, int L)
 	  for (len = 0 ; len <= p->N ; ++len) if (h[len]) array(hist, len, int) = (int) h[len] ;
 	  free (h) ;
 	}
+      matchLinesFlush () ;
       for (len = 0 ; len < arrayMax(hist) ; ++len)
 	if (arr(hist, len, int))
 	  { nTot += arr(hist, len, int) ;
@@ -137,6 +189,7 @@ void pbwtLongMatches (PBWT *p, int L)
     }
   else
     matchMaximalWithin (p, reportMatchLine) ;
+  matchLinesFlush () ;
   if (isCheck) { freeHaps (checkHapsA, p->M) ; checkHapsA = checkHapsB = 0 ; }
 }
 
@@ -333,6 +386,7 @@ void matchSequencesDynamic (PBWT *p, FILE *fp)	/* pbwtMatch.c:352-357 */
 {
   PBWT *q = pbwtRead (fp) ;
   matchSequencesSweep (p, q, reportMatchLine) ;
+  matchLinesFlush () ;
   pbwtDestroy (q) ;
 }
 
