@@ -264,10 +264,6 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
       if (e == 0 && warp == 0) pb = (~Bw) & 1u;  // sorted position 0 is always a run head
       const uint32_t H = Bw ^ ((Bw << 1) | pb);
       pb = Bw >> 31;
-      if (MATCH == 1) {
-        if (H) bnd |= 1u << e;
-        if (e > 0 && (H & 1u)) bnd |= 1u << (e - 1);  // a head at lane 0 makes the previous word's last lane a tail
-      }
       if (storeY) yc[wordBase + e] = Bw;
       if (WITH_D) {
         const int dv = sLane[dC + e * 32];
@@ -284,6 +280,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
           dn[e] = dv;
           lmax = max(lmax, dv);
         } else {
+          if (MATCH == 1) {  // (with the run heads: head-free words pay nothing for the bookkeeping of match candidates)
+            bnd |= 1u << e;
+            if (e > 0 && (H & 1u)) bnd |= 1u << (e - 1);  // a head at lane 0 makes the previous word's last lane a tail
+          }
           carry = max(carry, __reduce_max_sync(kFull, lmax));
           lmax = 0;
           int v = dv;  // inclusive max since the nearest head at or below this lane

@@ -13,3 +13,4 @@ for name, flags, nocand in [('ad+yz', P.WANT_YZ | P.WANT_D, 0), ('match-nocand',
     for rep in range(3):
         r = eng.build_device(p, flags); eng.synchronize(); tm = eng.last_timings(); n = r.nmatch; r.free()
     print(name, 'nmatch', n, {k: round(v[0], 2) for k, v in tm.items() if v[1]}, flush=True)
+eng.set_option("debug_no_candidates", 0)
