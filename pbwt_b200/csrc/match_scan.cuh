@@ -150,16 +150,20 @@ __device__ __forceinline__ void emit_block(const RecSink &out, long long o, cons
 // Candidate lanes of one word of state k.  cw: the word's alleles, pb: allele before the word, nb: allele
 // after it.  A lane is a candidate unless its first upward/downward neighbour already carries its allele in
 // the direction(s) the reference scans (pbwtMatch.c:124-129).
+// upExtends (per lane, optional knowledge of the caller): this lane heads a run and max d over the whole previous run is
+// <= its own d, i.e. the upward scan would walk through the previous run -- all of the other allele -- and reach the
+// run before it, which carries this lane's allele again: the match extends (pbwtMatch.c:124-126) without any scan.  The
+// sweep has that maximum in hand: it is what the divergence update of a run head needs (pbwtCore.c:496-505).
 template <class S>
 __device__ __forceinline__ uint32_t candidate_mask(const S &s, uint32_t cw, uint32_t pb, uint32_t nb, int base, uint32_t vm,
-                                                   int lane) {
+                                                   int lane, bool upExtends = false) {
   const uint32_t H = cw ^ ((cw << 1) | pb);
   const uint32_t Hn = (H >> 1) | (((nb & 1u) ^ (cw >> 31)) << 31);
   const uint32_t bm = (H | Hn) & vm;
   bool mine = false;
   if ((bm >> lane) & 1u) {
     const int di = s.d(base + lane), dn1 = s.d(base + lane + 1);
-    const bool samePrev = !((H >> lane) & 1u), sameNext = !((Hn >> lane) & 1u);
+    const bool samePrev = !((H >> lane) & 1u) || upExtends, sameNext = !((Hn >> lane) & 1u);
     mine = !((di <= dn1 && samePrev) || (di >= dn1 && sameNext));
   }
   return __ballot_sync(kFull, mine);

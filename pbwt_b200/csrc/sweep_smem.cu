@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     uint32_t pY = 0;
     int zw = 0;  // zeros in this warp so far
     unsigned bnd = 0;  // words of this warp holding a head or a tail of an allele run (match candidates)
+    unsigned headExt = 0;  // MATCH == 1: bit e set = this lane heads a run in word e whose upward scan is known to extend
     uint32_t longMask = 0;  // MATCH == 2: lane e holds the interior heads of word e
     int longCnt = 0;
 #pragma unroll
@@ -310,6 +311,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
           const bool headBelow = (H & ltMask) != 0u;
           const int prevMax = lane == 0 ? carry : (headBelow ? prev : max(carry, prev));
           dn[e] = isHead ? max(dv, prevMax) : dv;
+          // a run head whose d is not exceeded anywhere in the previous run: its match extends upward into the run before
+          // that (candidate_mask); the warp's first head is left out, its previous run may begin in the warps below
+          if (MATCH == 1 && isHead && prevMax <= dv && (anyHead || lane != __ffs(H) - 1)) headExt |= 1u << e;
           if (!anyHead) {
             anyHead = true;
             patchLane = __ffs(H) - 1;
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
         if (base >= M) break;
         const uint32_t vm = (M - base >= 32) ? kFull : ((1u << (M - base)) - 1u);
         const uint32_t m = candidate_mask(SmemState{nullptr, sI + dC, yc, nullptr}, yc[wd], e > 0 ? yc[wd - 1] >> 31 : pbFirst,
-                                          e < E - 1 ? yc[wd + 1] & 1u : nb, base, vm, lane);
+                                          e < E - 1 ? yc[wd + 1] & 1u : nb, base, vm, lane, (headExt >> e) & 1u);
         if (lane == e) myMask = m;
         tw += __popc(m);
       }
