@@ -250,8 +250,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
     int patchLane = 0, pDn = 0, pIdx = 0, pZ = 0;
     uint32_t pY = 0;
     int zw = 0;  // zeros in this warp so far
-    unsigned bnd = 0;  // words of this warp holding a head or a tail of an allele run (match candidates)
-    unsigned headExt = 0;  // MATCH == 1: bit e set = this lane heads a run in word e whose upward scan is known to extend
+    // MATCH == 1, held by lane e for word e of this warp: the word's run heads, and those among them whose upward scan is
+    // known to extend (see candidate_mask)
+    uint32_t myH = 0, myExt = 0;
     uint32_t longMask = 0;  // MATCH == 2: lane e holds the interior heads of word e
     int longCnt = 0;
 #pragma unroll
@@ -281,10 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
           dn[e] = dv;
           lmax = max(lmax, dv);
         } else {
-          if (MATCH == 1) {  // (with the run heads: head-free words pay nothing for the bookkeeping of match candidates)
-            bnd |= 1u << e;
-            if (e > 0 && (H & 1u)) bnd |= 1u << (e - 1);  // a head at lane 0 makes the previous word's last lane a tail
-          }
+          if (MATCH == 1 && lane == e) myH = H;  // (head-free words pay nothing for the bookkeeping of match candidates)
           carry = max(carry, __reduce_max_sync(kFull, lmax));
           lmax = 0;
           int v = dv;  // inclusive max since the nearest head at or below this lane
@@ -313,7 +311,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
           dn[e] = isHead ? max(dv, prevMax) : dv;
           // a run head whose d is not exceeded anywhere in the previous run: its match extends upward into the run before
           // that (candidate_mask); the warp's first head is left out, its previous run may begin in the warps below
-          if (MATCH == 1 && isHead && prevMax <= dv && (anyHead || lane != __ffs(H) - 1)) headExt |= 1u << e;
+          if (MATCH == 1) {
+            const uint32_t em = __ballot_sync(kFull, isHead && prevMax <= dv && (anyHead || lane != __ffs(H) - 1));
+            if (lane == e) myExt = em;
+          }
           if (!anyHead) {
             anyHead = true;
             patchLane = __ffs(H) - 1;
@@ -346,22 +347,27 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
           nb = (col[hn >> 5] >> (hn & 31)) & 1u;
         } else nb = col[wordBase + E] & 1u;
       }
-      __syncwarp();  // yc[] words of this warp were written by lane 0 above
-      unsigned words = bnd | (nb != pb ? 1u << (E - 1) : 0u);  // pb: this warp's last allele
+      // All words at once, lane e for word e: the heads and tails of runs (tails: the position before a head, which may be
+      // the next word's or the next warp's first) are tested exactly as the reference would on its first step
+      // (pbwtMatch.c:124-129; candidate_mask is the same test with one vote per word).
+      const uint32_t hNext = __shfl_down_sync(kFull, myH, 1);
       uint32_t myMask = 0;
-      int tw = 0;
-      while (words) {
-        const int e = __ffs(words) - 1;
-        words &= words - 1;
-        const int wd = wordBase + e, base = wd * 32;
-        if (base >= M) break;
-        const uint32_t vm = (M - base >= 32) ? kFull : ((1u << (M - base)) - 1u);
-        const uint32_t m = candidate_mask(SmemState{nullptr, sI + dC, yc, nullptr}, yc[wd], e > 0 ? yc[wd - 1] >> 31 : pbFirst,
-                                          e < E - 1 ? yc[wd + 1] & 1u : nb, base, vm, lane, (headExt >> e) & 1u);
-        if (lane == e) myMask = m;
-        tw += __popc(m);
+      if (lane < E) {
+        const int base = (wordBase + lane) * 32;
+        const uint32_t vm = (M - base >= 32) ? kFull : (M > base ? ((1u << (M - base)) - 1u) : 0u);
+        const uint32_t headAfter = lane < E - 1 ? (hNext & 1u) : (nb ^ pb);  // pb: this warp's last allele
+        const uint32_t Hn = (myH >> 1) | (headAfter << 31);
+        uint32_t bm = (myH | Hn) & vm;
+        while (bm) {
+          const int l = __ffs(bm) - 1;
+          bm &= bm - 1;
+          const int di = sI[dC + base + l], dn1 = sI[dC + base + l + 1];
+          const bool samePrev = !((myH >> l) & 1u) || ((myExt >> l) & 1u), sameNext = !((Hn >> l) & 1u);
+          if (!((di <= dn1 && samePrev) || (di >= dn1 && sameNext))) myMask |= 1u << l;
+        }
+        cmaskS[wordBase + lane] = myMask;
       }
-      if (lane < E) cmaskS[wordBase + lane] = myMask;
+      const int tw = __reduce_add_sync(kFull, __popc(myMask));
       if (lane == 0) wsumC[warp] = p.debugNoCandidates ? 0 : tw;
     }
     __syncthreads();  // S1: ballots, warp sums, match candidates published; everyone is done with col[]
