@@ -29,6 +29,7 @@ struct pbwtgpu_ctx {
   long long optMatchCap = 0;   // 0 = automatic
   long long optWindowTimes = 0;  // debugging: print per-window CTA times of pass 2 to stderr
   long long optNoCandidates = 0;  // profiling aid
+  long long optEdgePct[3] = {0, 0, 0};  // tuning aid: sites of windows 0 / 1 / last in % of an inner window's (0 = built-in)
   long long optForceGlobal = 0;  // testing: use the global-memory kernel even for narrow panels
   long long optLongT = 0;        // L of PBWTGPU_WANT_LONGWITHIN
   long long optEqualWindows = 0; // testing / profiling: equal windows even where the edge windows would be shortened
@@ -352,7 +353,9 @@ struct WindowedSweep {
     // (shared-memory kernel; wide panels keep equal windows)
     if (!useGlobal && wantMatch && W >= 8 && !ctx->optEqualWindows) {
       const bool atStart = siteOffset == 0, atEnd = siteOffset + N == nTotal;
-      const double f0 = atStart ? 0.80 : 1.0, f1 = atStart ? 0.92 : 1.0, fl = atEnd ? 0.74 : 1.0;
+      const double p0 = ctx->optEdgePct[0] > 0 ? ctx->optEdgePct[0] / 100.0 : 0.80, p1 = ctx->optEdgePct[1] > 0 ? ctx->optEdgePct[1] / 100.0 : 0.92,
+                   pl = ctx->optEdgePct[2] > 0 ? ctx->optEdgePct[2] / 100.0 : 0.74;
+      const double f0 = atStart ? p0 : 1.0, f1 = atStart ? p1 : 1.0, fl = atEnd ? pl : 1.0;
       if (atStart || atEnd)
         for (int s = (int)(N / (W - 3 + f0 + f1 + fl)), tries = 0; tries < 4; ++s, ++tries) {  // smallest s whose last window fits
           const int first = std::min(s, (int)(f0 * s + 0.5)), second = std::min(s, (int)(f1 * s + 0.5));
@@ -1161,6 +1164,9 @@ int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value) {
   else if (!strcmp(name, "no_sort_pass1")) ctx->optNoSortPass1 = value;
   else if (!strcmp(name, "equal_windows")) ctx->optEqualWindows = value;
   else if (!strcmp(name, "debug_no_candidates")) ctx->optNoCandidates = value;
+  else if (!strcmp(name, "edge_first_pct")) ctx->optEdgePct[0] = value;
+  else if (!strcmp(name, "edge_second_pct")) ctx->optEdgePct[1] = value;
+  else if (!strcmp(name, "edge_last_pct")) ctx->optEdgePct[2] = value;
   else return fail(ctx, PBWTGPU_ERR_ARG, "unknown option %s", name);
   return 0;
 }
