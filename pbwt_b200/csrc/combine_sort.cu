@@ -9,7 +9,8 @@
 //   * an LSD radix sort (two 8-bit digits) of I's positions by the group index of the haplotype they hold, the elements
 //     (group << 16 | I-position) resident in shared memory (stable, so members of a group keep their I-order), and
 //   * one range-maximum query over I's divergence per neighbouring pair of the same group: blocks of 32 positions, a
-//     sparse table over the block maxima, and the two partial blocks scanned directly,
+//     sparse table over the block maxima, and for the two partial blocks the block's prefix / suffix maxima (two loads
+//     instead of a walk over up to 31 positions each; up to 10,240 haplotypes, where the two extra arrays fit),
 // followed in the same launch by what make_groups_kernel does for the new node (tie-group index of every haplotype,
 // divergence at every group head).  One CTA per node; bit-identical to the sweep formulation
 // (tests force both paths).  Panels up to 13,312 haplotypes in haplotype space; stored streams (position space) and
@@ -34,6 +35,10 @@ __global__ void __launch_bounds__(kThreads, 1) combine_sort_kernel(const Combine
   int32_t *dS = reinterpret_cast<int32_t *>(buf1 + MP);  // I's divergence by I-position (0 at position 0 and beyond M)
   int32_t *st = dS + MP;                                 // [kLevels][NB] sparse table of block maxima
   uint16_t *hist = reinterpret_cast<uint16_t *>(st + kLevels * NB);  // [32 warps][256 digits]
+  constexpr bool PS = E <= 10;  // prefix / suffix maxima inside every block of 32 positions
+  int32_t *sufS = reinterpret_cast<int32_t *>(hist + 32 * 256);  // [MP] max of dS from the position to its block's end (PS)
+  int32_t *preS = reinterpret_cast<int32_t *>(buf1);             // [MP] max of dS from its block's start to the position (PS;
+                                                                 // the sort's second buffer, free once the sort is done)
   __shared__ int warpTot[32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -87,7 +92,15 @@ __global__ void __launch_bounds__(kThreads, 1) combine_sort_kernel(const Combine
     for (int e = 0; e < E; ++e) {
       const uint32_t v = cur[posBase + e * 32];
       const uint32_t digit = (v >> shift) & 255u;
-      const unsigned peers = __match_any_sync(kFull, digit);
+      // lanes holding the same digit, by eight independent votes: a warp's 32 positions hold haplotypes of many different
+      // groups, and match.any takes time in proportion to the number of distinct values (combine 0.42 -> 0.36 ms per step;
+      // the window sorts' digits are allele bits with few distinct values, there match.any is the faster form by 1.6x)
+      unsigned peers = kFull;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const unsigned m = __ballot_sync(kFull, (digit >> b) & 1u);
+        peers &= ((digit >> b) & 1u) ? m : ~m;
+      }
       const int leader = __ffs(peers) - 1;
       uint32_t old = 0;
       if (lane == leader) {
@@ -141,6 +154,23 @@ __global__ void __launch_bounds__(kThreads, 1) combine_sort_kernel(const Combine
     __syncthreads();
   }
 
+  if (PS) {  // (after two passes the elements are back in buf0)
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = posBase + e * 32;
+      int up = dS[i], dn = up;
+#pragma unroll
+      for (int dl = 1; dl < 32; dl <<= 1) {
+        const int a = __shfl_up_sync(kFull, up, dl), b = __shfl_down_sync(kFull, dn, dl);
+        if (lane >= dl) up = max(up, a);
+        if (lane + dl < 32) dn = max(dn, b);
+      }
+      preS[i] = up;
+      sufS[i] = dn;
+    }
+    __syncthreads();
+  }
+
   // max of I's divergence over I-positions [lo, hi], 1 <= lo <= hi
   auto range_max = [&](int lo, int hi) {
     const int bl = lo >> 5, bh = hi >> 5;
@@ -149,8 +179,11 @@ __global__ void __launch_bounds__(kThreads, 1) combine_sort_kernel(const Combine
       for (int i = lo; i <= hi; ++i) m = max(m, dS[i]);
       return m;
     }
-    for (int i = lo; i < (bl + 1) * 32; ++i) m = max(m, dS[i]);
-    for (int i = bh * 32; i <= hi; ++i) m = max(m, dS[i]);
+    if (PS) m = max(sufS[lo], preS[hi]);
+    else {
+      for (int i = lo; i < (bl + 1) * 32; ++i) m = max(m, dS[i]);
+      for (int i = bh * 32; i <= hi; ++i) m = max(m, dS[i]);
+    }
     const int b0 = bl + 1, cntB = bh - b0;  // whole blocks [b0, bh)
     if (cntB > 0) {
       const int lv = 31 - __clz(cntB);
@@ -212,7 +245,7 @@ __global__ void __launch_bounds__(kThreads, 1) combine_sort_kernel(const Combine
 }
 
 template <int E>
-size_t smem_bytes_e() { return (size_t)kThreads * E * 12 + (size_t)kLevels * 32 * E * 4 + 32 * 256 * 2; }
+size_t smem_bytes_e() { return (size_t)kThreads * E * (E <= 10 ? 16 : 12) + (size_t)kLevels * 32 * E * 4 + 32 * 256 * 2; }
 
 template <int E>
 int launch_e(const CombineSortArgs &c, int ctas, cudaStream_t stream) {
