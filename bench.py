@@ -473,13 +473,23 @@ def main():
     x_np[:] = panel.to_host()
     a_end, d_end = np.zeros(M, np.int32), np.zeros(M + 1, np.int32)
     h2d = x_np.nbytes
-    d2h = nyz + 4 * M + 4 * (M + 1) + 16 * nmatch  # (N = 1: replaced below by what the grouped stream really is)
+    d2h = nyz + 4 * M + 4 * (M + 1) + 16 * nmatch  # (replaced below by what the grouped stream really is)
     pin = None
     if world > 1:  # per-rank pinned output buffers for the device-resident calls of the sharded protocol
+        # (the matches come down in the grouped form, as at N = 1: {ai, start, end, n} + n x bi, at most 5 words per record)
         pin = {"yz": torch.empty(max(nyz, 1), dtype=torch.uint8).pin_memory().numpy(),
                "a_end": torch.empty(M, dtype=torch.int32).pin_memory().numpy(),
                "d_end": torch.empty(M + 1, dtype=torch.int32).pin_memory().numpy(),
-               "matches": torch.empty((max(nmatch, 1), 4), dtype=torch.int32).pin_memory().numpy().view(P.MATCH_DTYPE).reshape(-1)}
+               "groups": None}
+
+    def group_words(e, res):  # the grouped stream is built on the device by the context that owns the result
+        nw, ng = ctypes.c_int64(0), ctypes.c_int64(0)
+        e._check(e.lib.pbwtgpu_result_group(e.ctx, res.handle, ctypes.byref(nw), ctypes.byref(ng)))
+        return nw.value
+
+    def fetch_with(e, res, out):  # pack3 stream, aFend, d and the grouped matches, through context e
+        e._check(e.lib.pbwtgpu_result_fetch(e.ctx, res.handle, out["yz"].ctypes.data, out["a_end"].ctypes.data, out["d_end"].ctypes.data, None))
+        e._check(e.lib.pbwtgpu_result_fetch_groups(e.ctx, res.handle, out["groups"].ctypes.data))
 
     def abi_step(e, a_out, d_out):
         # the matches come as the grouped stream ({ai, start, end, n} + n x bi per run of callbacks that share ai, start,
@@ -498,14 +508,17 @@ def main():
             return abi_step(eng, a_end, d_end)
         pnl = eng.panel_from_host(x_np, M)  # N > 1: the sharded protocol needs the device-resident calls
         res = device_step(pnl)
-        res.fetch(out=pin)
+        nw = group_words(eng, res)
+        if pin["groups"] is None:
+            pin["groups"] = torch.empty(max(nw, 1), dtype=torch.int32).pin_memory().numpy()
+        fetch_with(eng, res, pin)
         res.free()
         pnl.free()
+        return 0, nw, 0
 
     first = e2e_step()
     e2e_step()
-    if world == 1:
-        d2h = nyz + 4 * M + 4 * (M + 1) + 4 * first[1]
+    d2h = nyz + 4 * M + 4 * (M + 1) + 4 * first[1]
     barrier()
     t0 = time.time()
     for _ in range(args.steps):
@@ -526,10 +539,6 @@ def main():
 
         eng_up, eng_down = P.Engine(local_rank), P.Engine(local_rank)
         pins = [pin, {k: torch.from_numpy(v.view(np.uint8)).clone().pin_memory().numpy().view(v.dtype).reshape(v.shape) for k, v in pin.items()}]
-
-        def fetch_with(e, res, out):
-            e._check(e.lib.pbwtgpu_result_fetch(e.ctx, res.handle, out["yz"].ctypes.data, out["a_end"].ctypes.data, out["d_end"].ctypes.data,
-                                                out["matches"].ctypes.data))
 
         def pipeline(steps):
             q_up, q_down, q_free_panels, q_free_results = queue.Queue(2), queue.Queue(2), queue.Queue(), queue.Queue()
@@ -560,7 +569,9 @@ def main():
                 pnl = q_up.get()
                 if pnl is None:
                     break
-                q_down.put((device_step(pnl), pnl))
+                res = device_step(pnl)
+                group_words(eng, res)
+                q_down.put((res, pnl))
                 while not q_free_results.empty():
                     q_free_results.get().free()
             q_down.put(None)
@@ -697,6 +708,7 @@ def main():
             "dtype": "int32", "data": "synthetic", "config": cfg,
             "e2e": {"value": total_hs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
                     "ms_per_step": ms_e2e, "builds_in_flight": in_flight, "ms_per_step_one_in_flight": t_e2e_serial * 1e3,
+                    "ms_per_step_pipelined_rank0": pipelined_ms,
                     "ms_per_step_shim_two_call_sequence": shim_seq_ms,
                     "ms_per_step_one_in_flight_16_byte_records": full_records_ms,
                     "note": ("one pbwtgpu_build_grouped(host bit columns in a pbwtgpu_host_alloc buffer, WANT_YZ|WANT_MAXWITHIN) per step, "
@@ -708,7 +720,8 @@ def main():
                              "(pbwtgpu_build, then pbwtgpu_max_within_grouped on the stored stream) and the same call with 16-byte "
                              "records are timed beside it") if world == 1 else
                             "per rank: pinned host columns -> pbwtgpu_panel_from_host -> shard protocol (one NCCL all-gather) -> "
-                            "pbwtgpu_result_fetch of pack3 stream, aFend, d and all match records, every step; builds_in_flight 3 = "
+                            "pbwtgpu_result_group + pbwtgpu_result_fetch / _fetch_groups of pack3 stream, aFend, d and all match "
+                            "records in the grouped form, every step; builds_in_flight 3 = "
                             "a three-stage pipeline per rank (upload thread, build thread, download thread, each with its own "
                             "context and stream), 1 = strictly one step after the other"},
             "gpu_launches": launches_all,
