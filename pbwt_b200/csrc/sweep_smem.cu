@@ -242,6 +242,14 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
       } else pb = col[wordBase - 1] >> 31;
     }
     const uint32_t pbFirst = pb;
+    uint32_t nb = 1u;  // MATCH == 1: allele just after this warp's last position (pad positions carry ones); looked up here
+                       // so that the two dependent loads are long done when the candidate test at the end of the phase asks
+    if (MATCH == 1 && warp < 31) {
+      if (MODE == kGather) {
+        const int hn = sI[aC + (wordBase + E) * 32];
+        nb = (col[hn >> 5] >> (hn & 31)) & 1u;
+      } else nb = col[wordBase + E] & 1u;
+    }
     const bool storeY = lane == 0 && (MATCH || QUERY || P3 || p.yOut != nullptr);  // the sorted column, when someone consumes it
     int carry = 0;         // max d since the last run head, over completed words (uniform)
     int lmax = 0;          // per-lane max of d over head-free words since then (reduced lazily)
@@ -339,14 +347,9 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
       if (lane < E) cmaskS[wordBase + lane] = longMask;
       if (lane == 0) wsumC[warp] = longCnt;
     }
-    if (MATCH == 1) {  // candidate lanes of this warp's words (exact: the allele after the warp is looked up too)
-      uint32_t nb = 1u;  // pad positions carry ones
-      if (warp < 31) {
-        if (MODE == kGather) {
-          const int hn = sI[aC + (wordBase + E) * 32];
-          nb = (col[hn >> 5] >> (hn & 31)) & 1u;
-        } else nb = col[wordBase + E] & 1u;
-      }
+    if (MATCH == 1 && !anyHead && nb == pb) {  // no run boundary among this warp's positions (most warps, most sites):
+      if (lane == 0) wsumC[warp] = 0;          // its masks are never looked at (locate_candidate only reads owners)
+    } else if (MATCH == 1) {  // candidate lanes of this warp's words (exact: the allele after the warp is looked up too)
       // All words at once, lane e for word e: the heads and tails of runs (tails: the position before a head, which may be
       // the next word's or the next warp's first) are tested exactly as the reference would on its first step
       // (pbwtMatch.c:124-129; candidate_mask is the same test with one vote per word).
