@@ -356,12 +356,19 @@ struct WindowedSweep {
       const double p0 = ctx->optEdgePct[0] > 0 ? ctx->optEdgePct[0] / 100.0 : 0.80, p1 = ctx->optEdgePct[1] > 0 ? ctx->optEdgePct[1] / 100.0 : 0.92,
                    pl = ctx->optEdgePct[2] > 0 ? ctx->optEdgePct[2] / 100.0 : 0.74;
       const double f0 = atStart ? p0 : 1.0, f1 = atStart ? p1 : 1.0, fl = atEnd ? pl : 1.0;
-      if (atStart || atEnd)
-        for (int s = (int)(N / (W - 3 + f0 + f1 + fl)), tries = 0; tries < 4; ++s, ++tries) {  // smallest s whose last window fits
+      if (atStart || atEnd) {
+        // the last window takes what the others leave: of the few window lengths around N / (W - 3 + f0 + f1 + fl) take
+        // the one whose most loaded window (sites over its share) is the lightest -- with the smallest length that fits,
+        // a shard that only ends the panel gave its last window 93 % instead of 74 % (0.55 ms of 4.4 on that rank)
+        double best = 1e30;
+        for (int s = (int)(N / (W - 3 + f0 + f1 + fl)), tries = 0; tries < 4; ++s, ++tries) {
           const int first = std::min(s, (int)(f0 * s + 0.5)), second = std::min(s, (int)(f1 * s + 0.5));
           const long long last = (long long)N - first - second - (long long)(W - 3) * s;
-          if (s >= 16 && first >= 1 && second >= 1 && last >= 1 && last <= s) { spw = s; firstSites = first; secondSites = second; break; }
+          if (!(s >= 16 && first >= 1 && second >= 1 && last >= 1 && last <= s)) continue;
+          const double cost = std::max(std::max((double)s, first / f0), std::max(second / f1, last / fl));
+          if (cost < best) { best = cost; spw = s; firstSites = first; secondSites = second; }
         }
+      }
     }
     nodes = sharded ? W : W - 1;  // a shard also needs the node of its last window (its aggregate)
     slots = nodes + 1;
