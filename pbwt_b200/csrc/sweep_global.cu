@@ -832,6 +832,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_global_kernel(const SweepAr
           const int Z = __ldcg(zk + fw) + __popc(~st.yw(fw) & lanemask_lt(f & 31));
           int nf = x ? c + f - Z : Z;
           if (nf == M) nf = 0;
+          __syncwarp();  // every lane has read nmS[r] (the test at the top of the loop) before lane 0 replaces it
           if (lane == 0) {
             qfW[jj] = nf;
             qeW[jj] = e;

@@ -364,7 +364,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
         while (bm) {
           const int l = __ffs(bm) - 1;
           bm &= bm - 1;
-          const int di = sI[dC + base + l], dn1 = sI[dC + base + l + 1];
+          // (the sentinels d[0] = d[M] = k + 1 are written at the top of the site by the threads that own those positions,
+          // possibly of another warp: read by others only after S1, known here)
+          const int pos = base + l;
+          const int di = pos == 0 ? k + 1 : sI[dC + pos], dn1 = pos + 1 == M ? k + 1 : sI[dC + pos + 1];
           const bool samePrev = !((myH >> l) & 1u) || ((myExt >> l) & 1u), sameNext = !((Hn >> l) & 1u);
           if (!((di <= dn1 && samePrev) || (di >= dn1 && sameNext))) myMask |= 1u << l;
         }
@@ -471,6 +474,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_smem_kernel(const SweepArgs
           }
         }
       }
+      __syncwarp();  // lane 0 rewrites this warp's words of yc[] in the next site's phase A: order the reads above before it
+                     // (the vote that precedes that store converges the warp but is no memory barrier; racecheck)
     }
     if (QUERY) {
       // ---------------- matchSequencesSweep on state k (pbwtMatch.c:376-426), one thread per query ----------------
