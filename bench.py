@@ -744,10 +744,10 @@ def main():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch of a config-2 step, pass 2 of sweep_smem_kernel
-# (ncu --set full, profiles/r02f_c2_pass2_ncu_full_summary.txt: 138.6 MB read -- the panel columns once -- and 252.2 MB
+# (ncu --set full, profiles/r02f_c2_pass2_ncu_full_summary.txt: 139.3 MB read -- the panel columns once -- and 255.2 MB
 # written -- records and run lists).  The step's other sweep launches: pass 1's window sort 182 MB (r01c_*), the eight
 # combine launches 26 MB each (r02f_c2_combine_*).
-TRAFFIC_C2 = 390.8e6
+TRAFFIC_C2 = 394.5e6
 
 
 def cli_wall_times(eng, P, panel, M, N):
