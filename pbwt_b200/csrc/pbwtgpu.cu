@@ -27,6 +27,8 @@ struct pbwtgpu_ctx {
   // options
   long long optWindows = 0;    // 0 = automatic
   long long optMatchCap = 0;   // 0 = automatic
+  double recPerHapSite = 0.0;  // densest match output this context has produced (records per haplotype-site): a panel that
+                               // once overflowed the first attempt's pool does not pay for a second pass 2 on every later call
   long long optWindowTimes = 0;  // debugging: print per-window CTA times of pass 2 to stderr
   long long optNoCandidates = 0;  // profiling aid
   long long optEdgePct[3] = {0, 0, 0};  // tuning aid: sites of windows 0 / 1 / last in % of an inner window's (0 = built-in)
@@ -775,6 +777,8 @@ struct WindowedSweep {
       if (int rc = tmp.get(&recCount, (size_t)W)) return rc;
       if (int rc = tmp.get(&chunkCounter, 1)) return rc;
       recCap = ctx->optMatchCap > 0 ? ctx->optMatchCap : std::min<long long>(std::max<long long>(1 << 20, 4096LL * M), 1LL << 28);
+      if (ctx->optMatchCap <= 0)  // (what this context has seen so far, with a quarter of head room)
+        recCap = std::min<long long>(std::max<long long>(recCap, (long long)(1.25 * ctx->recPerHapSite * (double)M * (double)std::max(N, 1))), 1LL << 31);
     }
     if (siteOffset + N != nTotal) {  // not the shard that ends the panel: no final state here
       CUDA_TRY(ctx, cudaMemsetAsync(res->aEnd, 0xFF, sizeof(int32_t) * M, ctx->stream));
@@ -898,6 +902,11 @@ struct WindowedSweep {
           poolGrown = true;
           again = true;
         }
+      }
+      if (wantMatch && !statsOnly && N > 0) {
+        long long total = segTotal;
+        for (auto cnt : counts) total += (long long)cnt;
+        ctx->recPerHapSite = std::max(ctx->recPerHapSite, (double)total / ((double)M * (double)N));
       }
       if (!again) break;
       if (attempt == 2) return fail(ctx, PBWTGPU_ERR_CUDA, "sweep output buffers overflowed three times");

@@ -352,6 +352,27 @@ def test_wide_panel_small_record_pool(eng, orc):
         eng.set_option("match_capacity", 0)
 
 
+def test_record_pool_overflow_is_paid_once(orc):
+    """A panel denser in matches than the first attempt's pool allows (4,200 identical haplotypes: 17.6 M records at N,
+    the pool starts at 4,096 per haplotype) reruns pass 2 with the exact size -- and the context remembers the density,
+    so that the same call does not pay for the rerun again."""
+    M, N = 4200, 8
+    x = O.pack_panel(np.zeros((M, N), np.uint8))
+    e = pbwt_b200.Engine(0)
+    try:
+        e.profile(True)
+        first = e.build(x, M, N, with_d=True, with_matches=True)
+        n1 = e.last_timings()["sweep"][1]
+        second = e.build(x, M, N, with_d=True, with_matches=True)
+        n2 = e.last_timings()["sweep"][1]
+        yz = orc.build(x, M, N, with_d=False)[0]
+        rec, n = orc.max_within(yz, M, N)
+        assert n == M * (M - 1) and len(first["matches"]) == n and (first["matches"] == rec).all() and (second["matches"] == rec).all()
+        assert n1 == 2 * n2 and n2 >= 1  # two launches of pass 2 the first time, one afterwards
+    finally:
+        e.close()
+
+
 @pytest.mark.parametrize("force_global", [0, 1])
 @pytest.mark.parametrize("M,N,R,W,dens,with_start", [(200, 90, 3, 2, 0.3, False), (1000, 240, 4, 5, 0.05, True), (33, 64, 8, 1, 0.5, False),
                                                       (3000, 400, 2, 7, 0.02, True), (1000, 480, 8, 9, 0.1, True), (200, 300, 6, 12, 0.4, False),
