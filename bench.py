@@ -324,6 +324,7 @@ def main():
 
     import pbwt_b200 as P
 
+    numa_node = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
@@ -538,6 +539,10 @@ def main():
         import queue
 
         eng_up, eng_down = P.Engine(local_rank), P.Engine(local_rank)
+        # more waiting host threads than cores (3 per rank): the library's waits sleep on an event instead of spinning
+        blocking = 3 * world > (os.cpu_count() or 1)
+        for e in (eng, eng_up, eng_down):
+            e.set_option("blocking_sync", 1 if blocking else 0)
         pins = [pin, {k: torch.from_numpy(v.view(np.uint8)).clone().pin_memory().numpy().view(v.dtype).reshape(v.shape) for k, v in pin.items()}]
 
         def pipeline(steps):
@@ -590,6 +595,7 @@ def main():
         pipelined_ms = (time.time() - t0) / args.steps * 1e3
         eng_up.close()
         eng_down.close()
+        eng.set_option("blocking_sync", 0)
         if pipelined_ms * 1e-3 < t_e2e:
             t_e2e, in_flight = pipelined_ms * 1e-3, 3
 
@@ -708,7 +714,7 @@ def main():
             "dtype": "int32", "data": "synthetic", "config": cfg,
             "e2e": {"value": total_hs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
                     "ms_per_step": ms_e2e, "builds_in_flight": in_flight, "ms_per_step_one_in_flight": t_e2e_serial * 1e3,
-                    "ms_per_step_pipelined_rank0": pipelined_ms,
+                    "ms_per_step_pipelined_rank0": pipelined_ms, "host_cores": os.cpu_count(), "numa_node_rank0": numa_node,
                     "ms_per_step_shim_two_call_sequence": shim_seq_ms,
                     "ms_per_step_one_in_flight_16_byte_records": full_records_ms,
                     "note": ("one pbwtgpu_build_grouped(host bit columns in a pbwtgpu_host_alloc buffer, WANT_YZ|WANT_MAXWITHIN) per step, "
@@ -748,6 +754,32 @@ def main():
 # written -- records and run lists).  The step's other sweep launches: pass 1's window sort 182 MB (r01c_*), the eight
 # combine launches 26 MB each (r02f_c2_combine_*).
 TRAFFIC_C2 = 394.5e6
+
+
+def bind_to_gpu_numa_node(torch, local_rank):
+    """N > 1: run this rank on the cores of its GPU's NUMA node, so that the page-locked host buffers it allocates
+    (first touch) and the threads that fill them sit next to the GPU's PCIe root -- eight ranks moving 1.7 GB per step
+    through one socket's memory and the inter-socket link is what the end-to-end number at N = 8 waits for.  Returns the
+    node, or None when the topology cannot be read (nothing is changed then)."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) < 2:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
 
 
 def cli_wall_times(eng, P, panel, M, N):

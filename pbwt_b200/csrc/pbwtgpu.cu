@@ -27,6 +27,8 @@ struct pbwtgpu_ctx {
   // options
   long long optWindows = 0;    // 0 = automatic
   long long optMatchCap = 0;   // 0 = automatic
+  long long optBlockingSync = 0;  // host waits sleep on an event instead of spinning (hosts with more waiting threads than cores)
+  cudaEvent_t syncEvent = nullptr;
   double recPerHapSite = 0.0;  // densest match output this context has produced (records per haplotype-site): a panel that
                                // once overflowed the first attempt's pool does not pay for a second pass 2 on every later call
   long long optWindowTimes = 0;  // debugging: print per-window CTA times of pass 2 to stderr
@@ -57,6 +59,19 @@ struct pbwtgpu_ctx {
   unsigned long long *pinned = nullptr;
   static constexpr int kPinnedWords = 1024;
 };
+
+// Wait for everything enqueued on the context's stream.  By default the calling thread spins (lowest latency); with the
+// option blocking_sync it sleeps on an event created with cudaEventBlockingSync, which matters when a host runs more
+// waiting threads than it has cores (eight ranks with three pipeline threads each on a 16-core box).
+static cudaError_t stream_sync(pbwtgpu_ctx *ctx) {
+  if (!ctx->optBlockingSync) return cudaStreamSynchronize(ctx->stream);
+  if (!ctx->syncEvent) {
+    cudaError_t e = cudaEventCreateWithFlags(&ctx->syncEvent, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  cudaError_t e = cudaEventRecord(ctx->syncEvent, ctx->stream);
+  return e != cudaSuccess ? e : cudaEventSynchronize(ctx->syncEvent);
+}
 
 struct pbwtgpu_panel {
   uint32_t *bits = nullptr;
@@ -441,7 +456,7 @@ struct WindowedSweep {
         h = ident.data();
       }
       CUDA_TRY(ctx, cudaMemcpyAsync(ord[0], h, sizeof(int32_t) * M, cudaMemcpyHostToDevice, ctx->stream));
-      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // ident goes out of scope
+      CUDA_TRY(ctx, stream_sync(ctx));  // ident goes out of scope
       if (needNodes) CUDA_TRY(ctx, cudaMemcpyAsync(ord[1], ord[0], sizeof(int32_t) * M, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     return 0;
@@ -882,7 +897,7 @@ struct WindowedSweep {
         }
         CUDA_TRY(ctx, cudaMemcpyAsync(&pin[0], chunkCounter, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
       }
-      if (wantMatch || wantYz) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      if (wantMatch || wantYz) CUDA_TRY(ctx, stream_sync(ctx));
       bool again = false;
       if (fusedP3 && pinP3[0]) {  // a window outgrew its region (or a column the list pass): sorted columns to global memory instead
         fusedP3 = false;
@@ -915,7 +930,7 @@ struct WindowedSweep {
     if (winNanos) {
       std::vector<long long> ns(std::max(W, 4));
       CUDA_TRY(ctx, cudaMemcpyAsync(ns.data(), winNanos, sizeof(long long) * ns.size(), cudaMemcpyDeviceToHost, ctx->stream));
-      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      CUDA_TRY(ctx, stream_sync(ctx));
       if (useGlobal)
         fprintf(stderr, "[pbwtgpu] wide kernel, CTA 0, cycles per site (%d sites, G=%d chunk=%d W=%d cluster=%d): phase A %.0f, exchange %.0f, scatter+scans %.0f, end barrier %.0f\n",
                 spw, G, chunk, W, gb.cluster, (double)ns[0] / spw, (double)ns[1] / spw, (double)ns[2] / spw, (double)ns[3] / spw);
@@ -967,7 +982,7 @@ struct WindowedSweep {
         ctx->launches[PBWTGPU_K_PACK3] += (N > 0);
       }
     }
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // temporaries go back to the cache with this object
+    CUDA_TRY(ctx, stream_sync(ctx));  // temporaries go back to the cache with this object
     return 0;
   }
 };
@@ -1040,7 +1055,7 @@ int finish_query_sweep(WindowedSweep &ws, pbwtgpu_match **recDev, unsigned long 
     CUDA_TRY(ctx, cudaMemcpyAsync(&segTotal, segDst + nSeg - 1, sizeof segTotal, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(got, counts, sizeof got, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(&used, chunkCounter, sizeof used, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, stream_sync(ctx));
     got[0] = (unsigned long long)segTotal;
     if (used <= poolChunks && (long long)got[1] <= nmCap) break;
     if (attempt == 1) return fail(ctx, PBWTGPU_ERR_CUDA, "query sweep buffer overflow persisted");
@@ -1090,7 +1105,7 @@ int decode_stream(pbwtgpu_ctx *ctx, Temps &tmp, const uint8_t *yzHost, int64_t n
   }
   int64_t symbols = 0;
   CUDA_TRY(ctx, cudaMemcpyAsync(&symbols, tiles + nTiles, sizeof symbols, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, stream_sync(ctx));
   if (symbols != (int64_t)M * N)  // the reference's isCheck assertion, pbwtCore.c:301-302
     return fail(ctx, PBWTGPU_ERR_ARG, "pack3 stream decodes to %lld symbols, expected M*N = %lld", (long long)symbols,
                 (long long)M * N);
@@ -1147,9 +1162,10 @@ int pbwtgpu_init(int device, pbwtgpu_ctx **out) {
 void pbwtgpu_destroy(pbwtgpu_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  stream_sync(ctx);
   reset_timings(ctx);
   for (auto e : ctx->eventPool) cudaEventDestroy(e);
+  if (ctx->syncEvent) cudaEventDestroy(ctx->syncEvent);
   for (auto &b : ctx->freeBlocks) cudaFree(b.p);
   cudaFreeHost(ctx->pinned);
   cudaStreamDestroy(ctx->ownStream);
@@ -1161,7 +1177,7 @@ const char *pbwtgpu_last_error(pbwtgpu_ctx *ctx) { return ctx ? ctx->lastError.c
 int pbwtgpu_set_stream(pbwtgpu_ctx *ctx, void *s) {
   if (!ctx) return PBWTGPU_ERR_ARG;
   // cached device blocks are reused without regard to the stream they were last used on: drain the old one first
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, stream_sync(ctx));
   ctx->stream = s ? (cudaStream_t)s : ctx->ownStream;
   return 0;
 }
@@ -1170,7 +1186,7 @@ void *pbwtgpu_get_stream(pbwtgpu_ctx *ctx) { return ctx ? (void *)ctx->stream : 
 int pbwtgpu_synchronize(pbwtgpu_ctx *ctx) {
   if (!ctx) return PBWTGPU_ERR_ARG;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, stream_sync(ctx));
   return 0;
 }
 
@@ -1178,6 +1194,7 @@ int pbwtgpu_set_option(pbwtgpu_ctx *ctx, const char *name, long long value) {
   if (!ctx || !name) return PBWTGPU_ERR_ARG;
   if (!strcmp(name, "windows")) ctx->optWindows = value;
   else if (!strcmp(name, "match_capacity")) ctx->optMatchCap = value;
+  else if (!strcmp(name, "blocking_sync")) ctx->optBlockingSync = value;
   else if (!strcmp(name, "window_times")) ctx->optWindowTimes = value;
   else if (!strcmp(name, "force_global")) ctx->optForceGlobal = value;
   else if (!strcmp(name, "no_cluster")) ctx->optNoCluster = value;
@@ -1204,7 +1221,7 @@ int pbwtgpu_profile(pbwtgpu_ctx *ctx, int enable) {
 
 int pbwtgpu_last_timings(pbwtgpu_ctx *ctx, float *ms, int *launches) {
   if (!ctx) return PBWTGPU_ERR_ARG;
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, stream_sync(ctx));
   for (auto &p : ctx->pending) {
     float t = 0;
     if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) ctx->ms[p.cls] += t;
@@ -1268,7 +1285,7 @@ int pbwtgpu_panel_to_host(pbwtgpu_ctx *ctx, const pbwtgpu_panel *p, int first, i
   if (n)
     CUDA_TRY(ctx, cudaMemcpyAsync(xbits, p->bits + (size_t)first * p->wpc, (size_t)n * p->wpc * 4, cudaMemcpyDeviceToHost,
                                   ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, stream_sync(ctx));
   return 0;
 }
 
@@ -1276,7 +1293,7 @@ void pbwtgpu_panel_free(pbwtgpu_ctx *ctx, pbwtgpu_panel *p) {
   if (!p) return;
   if (ctx) {
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    stream_sync(ctx);
     dev_release(ctx, p->bits, (size_t)std::max(p->N, 1) * p->wpc * 4);
   }
   delete p;
@@ -1304,7 +1321,7 @@ int pbwtgpu_sweep_yz_device(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, in
   pbwtgpu_result *res = new pbwtgpu_result;
   const int rc = run_sweep(ctx, ycols, pbwtgpu_words_per_col(M), M, N, kSorted, a_start, flags | PBWTGPU_WANT_D, res);
   if (rc) { pbwtgpu_result_free(ctx, res); return rc; }
-  if (cudaError_t e = cudaStreamSynchronize(ctx->stream)) {  // temporaries are recycled on return
+  if (cudaError_t e = stream_sync(ctx)) {  // temporaries are recycled on return
     pbwtgpu_result_free(ctx, res);
     return fail(ctx, PBWTGPU_ERR_CUDA, "sweep_yz: %s", cudaGetErrorString(e));
   }
@@ -1332,7 +1349,7 @@ int pbwtgpu_result_fetch(pbwtgpu_ctx *ctx, const pbwtgpu_result *r, uint8_t *yz,
   if (matches && r->rec && r->nrec)
     CUDA_TRY(ctx, cudaMemcpyAsync(matches, r->rec, sizeof(pbwtgpu_match) * (size_t)r->nrec, cudaMemcpyDeviceToHost,
                                   ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, stream_sync(ctx));
   return 0;
 }
 
@@ -1351,12 +1368,12 @@ int pbwtgpu_result_group(pbwtgpu_ctx *ctx, pbwtgpu_result *r, int64_t *nwords, i
       ScopedTimer t(ctx, PBWTGPU_K_AUX);
       CUDA_TRY(ctx, launch_group_scan(r->rec, r->nrec, state, temp, tempBytes, ctx->stream));
       CUDA_TRY(ctx, cudaMemcpyAsync(&ctx->pinned[0], group_scan_total(state, r->nrec), sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      CUDA_TRY(ctx, stream_sync(ctx));
       g = (long long)ctx->pinned[0];
       if (int rc = result_alloc(ctx, r, &r->groups, (size_t)(4 * g + r->nrec))) return rc;
       CUDA_TRY(ctx, launch_write_groups(r->rec, state, r->nrec, r->groups, ctx->stream));
       ctx->launches[PBWTGPU_K_AUX] += 2;
-      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // the temporaries go back to the cache
+      CUDA_TRY(ctx, stream_sync(ctx));  // the temporaries go back to the cache
     }
     r->nGroups = g;
   }
@@ -1370,7 +1387,7 @@ int pbwtgpu_result_fetch_groups(pbwtgpu_ctx *ctx, const pbwtgpu_result *r, int32
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const size_t n = (size_t)(4 * r->nGroups + r->nrec);
   if (n) CUDA_TRY(ctx, cudaMemcpyAsync(dst, r->groups, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, stream_sync(ctx));
   return 0;
 }
 
@@ -1378,7 +1395,7 @@ int pbwtgpu_result_fetch_hist(pbwtgpu_ctx *ctx, const pbwtgpu_result *r, int64_t
   if (!ctx || !r || !hist || !r->hist) return fail(ctx, PBWTGPU_ERR_ARG, "result_fetch_hist: the sweep was not run with WANT_STATS");
   std::vector<unsigned int> h((size_t)r->N + 1);
   CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), r->hist, sizeof(unsigned int) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, stream_sync(ctx));
   for (size_t i = 0; i < h.size(); ++i) hist[i] = (int64_t)h[i];
   return 0;
 }
@@ -1387,7 +1404,7 @@ void pbwtgpu_result_free(pbwtgpu_ctx *ctx, pbwtgpu_result *r) {
   if (!r) return;
   if (ctx) {
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    stream_sync(ctx);
     for (size_t i = 0; i < r->owned.size(); ++i) dev_release(ctx, r->owned[i], r->ownedBytes[i]);
   }
   delete r;
@@ -1418,7 +1435,7 @@ int pbwtgpu_shard_prepare(pbwtgpu_ctx *ctx, const pbwtgpu_panel *panel, const in
 int pbwtgpu_shard_export(pbwtgpu_ctx *ctx, pbwtgpu_shard *sh, int32_t *dev_dst) {
   if (!ctx || !sh || !dev_dst) return fail(ctx, PBWTGPU_ERR_ARG, "shard_export: bad args");
   if (int rc = sh->ws.export_aggregate(dev_dst)) return rc;
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, stream_sync(ctx));
   return 0;
 }
 
@@ -1436,7 +1453,7 @@ int pbwtgpu_shard_finish(pbwtgpu_ctx *ctx, pbwtgpu_shard *sh, const int32_t *dev
 
 void pbwtgpu_shard_free(pbwtgpu_ctx *ctx, pbwtgpu_shard *sh) {
   if (!sh) return;
-  if (ctx) cudaStreamSynchronize(ctx->stream);
+  if (ctx) stream_sync(ctx);
   delete sh;
 }
 
@@ -1548,7 +1565,7 @@ int pbwtgpu_cursor_at(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, i
       CUDA_TRY(ctx, cudaMemcpyAsync(y, yDev, (size_t)M, cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (c) CUDA_TRY(ctx, cudaMemcpyAsync(c, zc + k, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, stream_sync(ctx));
   }
   return 0;
 }
@@ -1608,7 +1625,7 @@ static int query_results_to_host(pbwtgpu_ctx *ctx, const pbwtgpu_match *recDev, 
   if (!gm.p || !gn.p) return fail(ctx, PBWTGPU_ERR_NOMEM, "pinned host allocation failed (records)");
   if (nrec) CUDA_TRY(ctx, cudaMemcpyAsync(gm.p, recDev, sizeof(pbwtgpu_match) * nrec, cudaMemcpyDeviceToHost, ctx->stream));
   if (nnm) CUDA_TRY(ctx, cudaMemcpyAsync(gn.p, nmDev, sizeof(pbwtgpu_nomatch) * nnm, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, stream_sync(ctx));
   *matches = (pbwtgpu_match *)gm.release();
   *nmatch = (int64_t)nrec;
   if (nomatch) *nomatch = (pbwtgpu_nomatch *)gn.release();
@@ -1703,7 +1720,7 @@ int pbwtgpu_match_sweep(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
     int used = 0;
     CUDA_TRY(ctx, cudaMemcpyAsync(got, counts, sizeof got, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(&used, chunkCounter, sizeof used, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, stream_sync(ctx));
     if (used <= poolChunks && (long long)got[1] <= nmCap) break;
     if (attempt == 1) return fail(ctx, PBWTGPU_ERR_CUDA, "query sweep buffer overflow persisted");
     recCap = std::max<long long>(recCap, (long long)got[0]);
@@ -1741,7 +1758,7 @@ int pbwtgpu_qshard_open(pbwtgpu_ctx *ctx, const uint8_t *pyz, int64_t npyz, int 
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   pbwtgpu_qshard *qs = new pbwtgpu_qshard(ctx);
   qs->M = M; qs->Q = Q;
-  auto bail = [&](int rc) { cudaStreamSynchronize(ctx->stream); delete qs; return rc; };
+  auto bail = [&](int rc) { stream_sync(ctx); delete qs; return rc; };
   // every GPU decodes the whole streams (they are small) and sweeps its own range of columns
   uint32_t *pcols = nullptr, *qcols = nullptr;
   if (int rc = decode_stream(ctx, qs->tmp, pyz, npyz, M, N, &pcols, nullptr)) return bail(rc);
@@ -1770,7 +1787,7 @@ int pbwtgpu_qshard_export_queries(pbwtgpu_ctx *ctx, pbwtgpu_qshard *qs, int32_t 
   } else {
     CUDA_TRY(ctx, cudaMemsetAsync(dev_dst, 0, sizeof(int32_t) * WindowedSweep::agg_ints(qs->Q), ctx->stream));
   }
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, stream_sync(ctx));
   return 0;
 }
 
@@ -1785,7 +1802,7 @@ int pbwtgpu_qshard_prepare(pbwtgpu_ctx *ctx, pbwtgpu_qshard *qs, const int32_t *
   }
   if (int rc = qs->wp.prepare()) return rc;
   if (int rc = qs->wp.export_aggregate(dev_panel_agg)) return rc;
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, stream_sync(ctx));
   return 0;
 }
 
@@ -1796,7 +1813,7 @@ int pbwtgpu_qshard_chain(pbwtgpu_ctx *ctx, pbwtgpu_qshard *qs, const int32_t *de
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   if (int rc = qs->wp.apply_prefix(dev_panel_aggs, rank)) return rc;
   if (int rc = qs->wp.query_chain(rank > 0 ? dev_state_in : nullptr, dev_state_out)) return rc;
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, stream_sync(ctx));
   return 0;
 }
 
@@ -1813,7 +1830,7 @@ int pbwtgpu_qshard_finish(pbwtgpu_ctx *ctx, pbwtgpu_qshard *qs, pbwtgpu_match **
 
 void pbwtgpu_qshard_free(pbwtgpu_ctx *ctx, pbwtgpu_qshard *qs) {
   if (!qs) return;
-  if (ctx) cudaStreamSynchronize(ctx->stream);
+  if (ctx) stream_sync(ctx);
   delete qs;
 }
 
@@ -1839,7 +1856,7 @@ int pbwtgpu_pack3(pbwtgpu_ctx *ctx, const uint8_t *y, int M, int N, uint8_t **yz
     ctx->launches[PBWTGPU_K_PACK3] += 2 * (N > 0) + 1;
   }
   CUDA_TRY(ctx, cudaMemcpyAsync(&total, colBase + N, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, stream_sync(ctx));
   if (int rc = tmp.get(&yzDev, (size_t)total + 16)) return rc;
   {
     ScopedTimer t(ctx, PBWTGPU_K_PACK3);
@@ -1849,7 +1866,7 @@ int pbwtgpu_pack3(pbwtgpu_ctx *ctx, const uint8_t *y, int M, int N, uint8_t **yz
   HostGuard h(host_alloc_pinned((size_t)std::max<int64_t>(total, 1)));
   if (!h.p) return fail(ctx, PBWTGPU_ERR_NOMEM, "pinned host allocation failed (yz)");
   if (total) CUDA_TRY(ctx, cudaMemcpyAsync(h.p, yzDev, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, stream_sync(ctx));
   *yz = (uint8_t *)h.release();
   *nyz = total;
   return 0;
@@ -1869,7 +1886,7 @@ int pbwtgpu_unpack3(pbwtgpu_ctx *ctx, const uint8_t *yz, int64_t nyz, int M, int
   if (N) CUDA_TRY(ctx, cudaMemcpyAsync(y, yDev, (size_t)M * N, cudaMemcpyDeviceToHost, ctx->stream));
   if (zero_counts && N)
     CUDA_TRY(ctx, cudaMemcpyAsync(zero_counts, zc, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, stream_sync(ctx));
   return 0;
 }
 

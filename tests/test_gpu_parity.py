@@ -352,6 +352,21 @@ def test_wide_panel_small_record_pool(eng, orc):
         eng.set_option("match_capacity", 0)
 
 
+def test_blocking_sync_option(eng, orc):
+    """Option blocking_sync: the library's host waits sleep on an event (cudaEventBlockingSync) instead of spinning --
+    for hosts that run more waiting threads than cores.  Same results."""
+    rng = np.random.default_rng(77)
+    M, N = 1500, 300
+    x = O.pack_panel((rng.random((M, N)) < 0.1).astype(np.uint8))
+    eng.set_option("blocking_sync", 1)
+    eng.set_option("windows", 7)
+    try:
+        check_build(eng, orc, x, M, N)
+    finally:
+        eng.set_option("blocking_sync", 0)
+        eng.set_option("windows", 0)
+
+
 def test_record_pool_overflow_is_paid_once(orc):
     """A panel denser in matches than the first attempt's pool allows (4,200 identical haplotypes: 17.6 M records at N,
     the pool starts at 4,096 per haplotype) reruns pass 2 with the exact size -- and the context remembers the density,
