@@ -67,7 +67,10 @@ int pbwtgpu_set_stream(pbwtgpu_ctx *ctx, void *cuda_stream);
 void *pbwtgpu_get_stream(pbwtgpu_ctx *ctx);
 int pbwtgpu_synchronize(pbwtgpu_ctx *ctx);
 /* Options (0 = automatic / off).  Tuning: "windows" (site windows swept concurrently), "match_capacity" (records the
- * first attempt allows for), "long_within" (L of PBWTGPU_WANT_LONGWITHIN).  Testing and profiling aids: "force_global"
+ * first attempt allows for; by default 4,096 per haplotype or 1.25 x the densest output the context has produced),
+ * "long_within" (L of PBWTGPU_WANT_LONGWITHIN), "blocking_sync" (host waits sleep on an event instead of spinning: hosts
+ * with more waiting threads than cores), "edge_first_pct" / "edge_second_pct" / "edge_last_pct" (sites of a panel's first
+ * two and last window in per cent of an inner window's; built in: 80 / 92 / 74).  Testing and profiling aids: "force_global"
  * (wide-panel kernels on narrow panels), "no_cluster" (cooperative-grid groups where clusters would fit),
  * "no_sort_pass1" (window nodes by sweeping instead of sorting), "no_sort_combine" (window combines by sweeping
  * pseudo-sites instead of the radix sort + range maxima), "no_fused_pack3" (sorted columns to global memory + the
