@@ -54,6 +54,9 @@ static void gpuCheck (int rc, const char *what)
 
 /* ---- matchMaximalWithin (pbwtMatch.c:115-142) ---- */
 
+static void reportMatchLine (int ai, int bi, int start, int end) ;	/* the CLI printer, below */
+static void reportMatchGroup (const pbwtgpu_group *h, const int32_t *bi) ;	/* the same lines, a whole group at a time */
+
 void matchMaximalWithin (PBWT *p, void (*report)(int ai, int bi, int start, int end))
 {
   int32_t *g = 0 ;		/* grouped records: {ai, start, end, n} + n x bi per run of callbacks that share ai, start, end */
@@ -73,7 +76,10 @@ void matchMaximalWithin (PBWT *p, void (*report)(int ai, int bi, int start, int 
     { const pbwtgpu_group *h = (const pbwtgpu_group*) (g + i) ;
       const int32_t *bi = g + i + 4 ;
       int j ;
-      for (j = 0 ; j < h->n ; ++j) (*report) (h->ai, bi[j], h->start, h->end) ;
+      if (report == reportMatchLine && !isCheck)	/* the printer: what a group's lines share is formatted once */
+	reportMatchGroup (h, bi) ;
+      else
+	for (j = 0 ; j < h->n ; ++j) (*report) (h->ai, bi[j], h->start, h->end) ;
       i += 4 + h->n ;
     }
   shimTiming ("report() callbacks", t0) ;
@@ -135,6 +141,26 @@ static void reportMatchLine (int ai, int bi, int start, int end)
   if (isCheck)			/* the GPU's record is a real match and maximal */
     { matchLinesFlush () ;	/* (a failed check dies: what was reported so far must be out, as with the reference's printf) */
       checkMatchMaximal (checkHapsA[ai], checkHapsB[bi], start, end, Ncheck) ;
+    }
+}
+
+/* the lines of one group -- n callbacks that share ai, start and end -- exactly as reportMatchLine would print them one
+   by one: "MATCH\t<ai>\t" and "\t<start>\t<end>\t<end-start>\n" are formatted once, only bi changes from line to line */
+static void reportMatchGroup (const pbwtgpu_group *h, const int32_t *bi)
+{
+  char head[24], tail[48], *c ;
+  int nh, nt, j ;
+  if (h->start == h->end) return ;	/* zero-length matches are dropped (pbwtMatch.c:48) */
+  c = head ; memcpy (c, "MATCH\t", 6) ; c += 6 ; c = putInt (c, h->ai) ; *c++ = '\t' ; nh = (int) (c - head) ;
+  c = tail ; *c++ = '\t' ; c = putInt (c, h->start) ; *c++ = '\t' ; c = putInt (c, h->end) ; *c++ = '\t' ;
+  c = putInt (c, h->end - h->start) ; *c++ = '\n' ; nt = (int) (c - tail) ;
+  for (j = 0 ; j < h->n ; ++j)
+    { if (matchLineFill > (int) sizeof (matchLineBuf) - 96) matchLinesFlush () ;
+      c = matchLineBuf + matchLineFill ;
+      memcpy (c, head, nh) ; c += nh ;
+      c = putInt (c, bi[j]) ;
+      memcpy (c, tail, nt) ; c += nt ;
+      matchLineFill = (int) (c - matchLineBuf) ;
     }
 }
 
