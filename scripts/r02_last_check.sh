@@ -1,1 +1,3 @@
-timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "golden or mosaic" 2>&1 | tail -2; timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+#!/bin/bash
+# round 2, last GPU seconds: the drop-in CLI against the real library after the shim's group formatter
+timeout 200 python -m pytest tests/test_gpu_cli.py -x -q 2>&1 | tail -2
