@@ -10,7 +10,13 @@ leaves out (a head whose previous run begins at position 0: d[0] = k + 1 stops e
 
 (2) The candidate test lane by lane.  Lane e of a warp tests the run boundaries of word e with the reference's first step
 (a position whose neighbour in a direction it scans carries its allele is no candidate); the model checks that the set
-it keeps, with the shortcut applied, still contains every position the reference reports."""
+it keeps, with the shortcut applied, still contains every position the reference reports.
+
+(3) Not in the kernel (direction (a)): the mirror image for run TAILS, stated here so that whoever builds
+it starts from a checked formulation.  The downward scan from the last position i of a run walks through the next run
+(head h = i + 1, all of the other allele) and reaches the run after it -- i's allele again, head h2 -- iff nothing in
+(h, h2] exceeds d[h]; when the next run is the last one the scan ends at the d[M] sentinel and never extends.  That is a
+SUFFIX maximum over the next run, which the forward sweep does not have in hand at position i."""
 import numpy as np
 import pytest
 
@@ -68,6 +74,51 @@ def test_run_head_shortcut_equals_the_upward_scan(seed):
             prev_head = heads[j - 1]
             prev_max = d[prev_head:i].max()  # max d over the previous run, what the divergence update carries to this head
             assert (prev_max <= d[i]) == up_ext[i], (M, k, i)
+
+
+def reference_down_extends(y, d, k):
+    """for every position whose downward scan the reference performs without an upward extension first: did it extend"""
+    M = len(y)
+    out = {}
+    for i in range(M):
+        m, extends = i - 1, False
+        if d[i] <= d[i + 1]:
+            while d[m + 1] <= d[i]:
+                if y[m] == y[i]:
+                    extends = True
+                    break
+                m -= 1
+        if not extends and d[i] >= d[i + 1]:
+            n, down = i + 1, False
+            while d[n] <= d[i + 1]:
+                if y[n] == y[i]:
+                    down = True
+                    break
+                n += 1
+            out[i] = down
+    return out
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_run_tail_mirror_image_equals_the_downward_scan(seed):
+    rng = np.random.default_rng(200 + seed)
+    for _ in range(60):
+        M, k = int(rng.integers(2, 400)), int(rng.integers(1, 1000))
+        y, d = random_state(rng, M, k, float(rng.choice([1.5, 4.0, 30.0])))
+        down = reference_down_extends(y, d, k)
+        heads = [i for i in range(M) if i == 0 or y[i] != y[i - 1]] + [M]
+        for j in range(len(heads) - 1):
+            i = heads[j + 1] - 1  # the tail of run j
+            if i not in down:
+                continue
+            if j + 2 >= len(heads):  # no run after this one
+                continue
+            h = heads[j + 1]
+            if j + 2 == len(heads) - 1:  # the next run is the last: the scan ends at d[M] = k + 1
+                assert down[i] is False, (M, k, i)
+                continue
+            h2 = heads[j + 2]
+            assert (d[h + 1:h2 + 1].max() <= d[h]) == down[i], (M, k, i)
 
 
 def kernel_candidates(y, d, k):
